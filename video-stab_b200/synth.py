@@ -1,0 +1,58 @@
+"""Seeded synthetic shaky-clip generator shared by the tests, the bench and the oracle
+(SURVEY.md §8d).  Data tooling only — not on the stabilization path.
+
+Base texture: uniform uint8 noise (seed S), (H+2m)x(W+2m)x3, Gaussian-blurred sigma=2
+and min-max normalised to 0..255 (gives several hundred well-spread Shi-Tomasi corners).
+Frame k is the base seen through a ground-truth camera pose: slow sinusoidal pan
+(<= ~1 px/frame) + per-frame jitter N(0, 3^2) px and N(0, 0.004^2) rad (clipped so the
+view never leaves the margin m=64), RNG numpy.default_rng(S+1).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MARGIN = 64
+
+
+def base_texture(width: int, height: int, seed: int) -> np.ndarray:
+    import cv2  # data tooling only
+    rng = np.random.default_rng(seed)
+    noise = rng.integers(0, 256, (height + 2 * MARGIN, width + 2 * MARGIN, 3), dtype=np.uint8)
+    blur = cv2.GaussianBlur(noise, (0, 0), 2.0).astype(np.float32)
+    lo, hi = blur.min(), blur.max()
+    return ((blur - lo) / (hi - lo) * 255.0).astype(np.uint8)
+
+
+def camera_path(n_frames: int, seed: int) -> np.ndarray:
+    """(n,3) float64 ground-truth pose (x, y, angle) per frame."""
+    rng = np.random.default_rng(seed + 1)
+    k = np.arange(n_frames, dtype=np.float64)
+    px = 40.0 * np.sin(2 * np.pi * k / 240.0)
+    py = 20.0 * np.sin(2 * np.pi * k / 180.0 + 1.0)
+    jx = np.clip(rng.normal(0.0, 3.0, n_frames), -10, 10)
+    jy = np.clip(rng.normal(0.0, 3.0, n_frames), -10, 10)
+    ja = np.clip(rng.normal(0.0, 0.004, n_frames), -0.012, 0.012)
+    return np.stack([px + jx, py + jy, ja], axis=1)
+
+
+def render_frame(base: np.ndarray, pose, width: int, height: int) -> np.ndarray:
+    import cv2  # data tooling only
+    x, y, a = (float(v) for v in pose)
+    cx = base.shape[1] / 2.0
+    cy = base.shape[0] / 2.0
+    c, s = np.cos(a), np.sin(a)
+    # rotate about the base centre, translate, then shift so the output is the centre crop
+    m = np.array([[c, -s, cx - c * cx + s * cy + x - MARGIN],
+                  [s, c, cy - s * cx - c * cy + y - MARGIN]], np.float64)
+    return cv2.warpAffine(base, m, (width, height), flags=cv2.INTER_LINEAR,
+                          borderMode=cv2.BORDER_CONSTANT)
+
+
+def make_clip(width: int, height: int, n_frames: int, seed: int) -> np.ndarray:
+    """(n, H, W, 3) uint8 BGR clip."""
+    base = base_texture(width, height, seed)
+    poses = camera_path(n_frames, seed)
+    out = np.empty((n_frames, height, width, 3), np.uint8)
+    for k in range(n_frames):
+        out[k] = render_frame(base, poses[k], width, height)
+    return out
