@@ -1,0 +1,246 @@
+/* vstab_b200.h — C-ABI of the B200-native stabilization hot path.
+ *
+ * Drop-in boundary for OmerMersin/video-stab's `vs::Stabilizer` (reference
+ * include/video/Stabilizer.h:70-198, src/Stabilizer.cpp).  Every entry point below names
+ * the reference interface it replaces.  Plain pointers and sizes only; no C++/torch types.
+ * The header-only C++ shim `include/video/Stabilizer.h` re-creates `vs::Stabilizer` on top
+ * of this ABI; `INTEGRATION.md` shows the binding a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns a vs_status (0 = OK); nothing throws or aborts across the ABI
+ *    (the reference never throws on the hot path either: Stabilizer.cpp:620-626,653-658,1061-1066)
+ *  - "not ready yet" (reference: empty cv::Mat, Stabilizer.cpp:367,384-387) is *produced = 0
+ *  - frames are 8-bit BGR interleaved (CV_8UC3), arbitrary row stride in bytes
+ *  - one handle = one CUDA stream; calls on one handle must be externally serialised
+ *    (same contract as the reference: examples/vsg.cpp:185-228); handles are independent
+ *  - there is NO CPU fallback: without a CUDA device vs_stabilizer_create fails with
+ *    VS_ERR_NO_DEVICE
+ */
+#ifndef VSTAB_B200_H
+#define VSTAB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSTAB_B200_ABI_VERSION 1
+
+typedef enum vs_status {
+    VS_OK = 0,
+    VS_ERR_INVALID_ARG = 1,
+    VS_ERR_NO_DEVICE = 2,      /* no CUDA device / not an sm_100 part */
+    VS_ERR_CUDA = 3,           /* a CUDA call failed; vs_last_error() has the text */
+    VS_ERR_OUT_OF_MEMORY = 4,
+    VS_ERR_BUFFER_TOO_SMALL = 5,
+    VS_ERR_IO = 6,             /* config file unreadable */
+    VS_ERR_UNSUPPORTED = 7     /* flag accepted by the reference but not built here yet */
+} vs_status;
+
+/* ---- vs::Stabilizer::Parameters (Stabilizer.h:76-175), field for field -------------------
+ * std::string fields are fixed-size char arrays.  "live" = changes stabilize() output on the
+ * reference's CPU path today; inert fields are stored and ignored, exactly
+ * like the reference. */
+typedef struct vs_params {
+    int32_t use_cuda;                 /* useCuda — accepted, ignored (always GPU)           */
+    int32_t logging;                  /* logging                                             */
+    int32_t smoothing_radius;         /* smoothingRadius (30) live                           */
+    int32_t max_corners;              /* maxCorners (200) live, first frame                  */
+    double  quality_level;            /* qualityLevel (0.01) live, first frame               */
+    double  min_distance;             /* minDistance (30.0) live, first frame                */
+    int32_t block_size;               /* blockSize (3) — only 3 is supported (the default)   */
+    char    border_type[32];          /* borderType ("black") live                           */
+    int32_t border_size;              /* borderSize (0) live                                 */
+    int32_t crop_n_zoom;              /* cropNZoom (false) live                              */
+    char    smoothing_method[32];     /* smoothingMethod ("box") live                        */
+    double  gaussian_sigma;           /* gaussianSigma (2.0) live with "gaussian"            */
+    int32_t motion_prediction;        /* motionPrediction — inert                            */
+    int32_t horizon_lock;             /* horizonLock (false) live                            */
+    int32_t feature_detector;         /* featureDetector — inert (detectFeatures is dead)    */
+    int32_t orb_features;             /* inert */
+    int32_t fast_threshold;           /* inert */
+    int32_t use_roi;                  /* inert */
+    int32_t roi_x, roi_y, roi_width, roi_height;   /* inert */
+    int32_t adaptive_smoothing;       /* adaptiveSmoothing (false) live                      */
+    int32_t min_smoothing_radius;     /* (5) live with adaptive_smoothing                    */
+    int32_t max_smoothing_radius;     /* (50) live with adaptive_smoothing                   */
+    double  outlier_threshold;        /* inert */
+    double  intentional_motion_threshold; /* inert */
+    int32_t stage_one_radius;         /* inert */
+    int32_t stage_two_radius;         /* inert */
+    int32_t use_temporal_filtering;   /* inert */
+    int32_t temporal_window_size;     /* inert */
+    float   fade_alpha;               /* fadeAlpha — only with border_type "fade" (unsupported) */
+    int32_t fade_duration;            /* fadeDuration                                        */
+    float   motion_threshold_low;     /* inert */
+    float   motion_threshold_high;    /* inert */
+    float   border_scale_factor;      /* inert */
+    int32_t roll_compensation;        /* inert */
+    double  roll_compensation_factor; /* inert */
+    int32_t deep_stabilization;       /* inert */
+    char    model_path[256];          /* inert */
+    int32_t jitter_frequency;         /* inert */
+    int32_t separate_translation_rotation; /* inert */
+    int32_t use_imu_data;             /* inert */
+    int32_t enable_virtual_canvas;    /* enableVirtualCanvas — VS_ERR_UNSUPPORTED if set     */
+    float   canvas_scale_factor;
+    int32_t temporal_buffer_size;
+    float   canvas_blend_weight;
+    int32_t adaptive_canvas_size;
+    float   max_canvas_scale;
+    float   min_canvas_scale;
+    int32_t preserve_edge_quality;
+    int32_t edge_blend_radius;
+    int32_t drone_high_freq_mode;     /* droneHighFreqMode — VS_ERR_UNSUPPORTED if set       */
+    float   hf_shake_px;
+    int32_t hf_analysis_max_width;
+    float   hf_rot_lp_alpha;
+    int32_t enable_conditional_clahe;
+    float   hf_dead_zone_threshold;
+    int32_t hf_freeze_duration;
+    float   hf_motion_accumulator_decay;
+} vs_params;
+
+/* Defaults of Stabilizer.h:78-174. */
+vs_status vs_params_default(vs_params* p);
+/* Reads the `stabilizer:` section of a reference config.yaml (keys of examples/vsg.cpp:1003-1114,
+ * OpenCV FileStorage "%YAML:1.0" subset).  Missing keys keep their current value, like
+ * cv::FileNode >> does. */
+vs_status vs_params_from_yaml(const char* path, vs_params* p);
+vs_status vs_params_from_yaml_string(const char* text, vs_params* p);
+
+/* ---- per-frame record, for tests and diagnostics --------------------------------------- */
+typedef struct vs_frame_record {
+    int32_t frame_index;      /* n = index of the generateTransform() call (frame n), 1-based  */
+    int32_t n_prev_pts;       /* key points LK started from                                    */
+    int32_t n_tracked;        /* status != 0                                                   */
+    int32_t n_inliers;        /* RANSAC inliers (-1: estimate not run / failed)                */
+    int32_t ransac_iters;     /* hypotheses the sequential reference loop would have evaluated */
+    int32_t n_detected;       /* corners re-detected on this frame (-1: no detection)          */
+    float   transform[3];     /* dx, dy, da   (Stabilizer.cpp:660-662)                         */
+    float   path[3];          /* cumulative   (Stabilizer.cpp:681-687)                         */
+    double  affine[6];        /* refined 2x3 from the partial-affine fit                       */
+} vs_frame_record;
+
+typedef struct vs_output_record {
+    int32_t index;            /* frame index this output belongs to                            */
+    int32_t passthrough;      /* 1: returned un-warped (Stabilizer.cpp:774-780)                */
+    int32_t path_len;
+    int32_t radius;           /* adaptive box radius before the [2,8] clamp                    */
+    int32_t intent;           /* 0 NORMAL 1 DELIBERATE_PAN 2 SHAKE_REMOVAL 3 FOLLOW_ACTION     */
+    float   smoothed[3];
+    float   T[6];             /* 2x3 float32 handed to the warp (Stabilizer.cpp:902-908)       */
+} vs_output_record;
+
+/* ---- the stabilizer handle -------------------------------------------------------------- */
+typedef struct vs_stabilizer vs_stabilizer;
+
+/* Stabilizer::Stabilizer(const Parameters&)  — Stabilizer.h:177, Stabilizer.cpp:50-164 */
+vs_status vs_stabilizer_create(const vs_params* params, int device, vs_stabilizer** out);
+/* Stabilizer::~Stabilizer()                  — Stabilizer.cpp:216-219 */
+void      vs_stabilizer_destroy(vs_stabilizer* s);
+
+/* cv::Mat Stabilizer::stabilize(const cv::Mat&) — Stabilizer.h:187, Stabilizer.cpp:258-392.
+ * Host frame in, host frame out (synchronous).  out must hold out_capacity bytes;
+ * worst case (width+2*border_size)*3 per row * (height+2*border_size) rows.
+ * *produced = 0 while the reference would return an empty Mat. */
+vs_status vs_stabilizer_push(vs_stabilizer* s, const uint8_t* bgr, int width, int height, size_t stride,
+                             uint8_t* out, size_t out_stride, size_t out_capacity,
+                             int* out_width, int* out_height, int* produced);
+/* cv::Mat Stabilizer::flush()                — Stabilizer.h:193, Stabilizer.cpp:394-400 */
+vs_status vs_stabilizer_flush(vs_stabilizer* s, uint8_t* out, size_t out_stride, size_t out_capacity,
+                              int* out_width, int* out_height, int* produced);
+/* void Stabilizer::clean()                   — Stabilizer.h:198, Stabilizer.cpp:221-256 */
+vs_status vs_stabilizer_clean(vs_stabilizer* s);
+
+/* Device-resident variants of stabilize()/flush(): `d_bgr` and `d_out` are device pointers on the
+ * handle's device.  Asynchronous on the handle's stream; call vs_stabilizer_sync() before reading
+ * d_out.  flags: VS_PUSH_BORROW — the caller keeps d_bgr alive and unmodified until the output of
+ * that frame has been produced (the reference itself queues frames without cloning them,
+ * Stabilizer.cpp:376); without it the frame is copied into an internal ring. */
+#define VS_PUSH_BORROW 1u
+vs_status vs_stabilizer_push_device(vs_stabilizer* s, const uint8_t* d_bgr, int width, int height, size_t stride,
+                                    uint8_t* d_out, size_t out_stride, size_t out_capacity, unsigned flags,
+                                    int* out_width, int* out_height, int* produced);
+vs_status vs_stabilizer_flush_device(vs_stabilizer* s, uint8_t* d_out, size_t out_stride, size_t out_capacity,
+                                     int* out_width, int* out_height, int* produced);
+vs_status vs_stabilizer_sync(vs_stabilizer* s);
+/* cudaStream_t of the handle (as void*), so callers can time/order work on it. */
+void*     vs_stabilizer_stream(vs_stabilizer* s);
+
+/* Diagnostics: number of frames analysed so far / outputs produced so far, and their records
+ * (synchronises the stream).  Used by the parity tests; not on the hot path. */
+vs_status vs_stabilizer_counts(vs_stabilizer* s, int* n_frame_records, int* n_output_records);
+vs_status vs_stabilizer_frame_record(vs_stabilizer* s, int i, vs_frame_record* rec);
+vs_status vs_stabilizer_output_record(vs_stabilizer* s, int i, vs_output_record* rec);
+/* Copies the points of frame record i: prev/next are n_prev_pts*2 floats, status n_prev_pts bytes,
+ * inlier_mask n_tracked bytes, detected n_detected*2 floats (any pointer may be NULL). */
+vs_status vs_stabilizer_frame_points(vs_stabilizer* s, int i, float* prev_xy, float* next_xy, uint8_t* status,
+                                     uint8_t* inlier_mask, float* detected_xy);
+/* corners found on the very first frame (Stabilizer.cpp:355-357); returns count in *n. */
+vs_status vs_stabilizer_first_corners(vs_stabilizer* s, float* xy, int capacity, int* n);
+/* kernels this handle has launched since creation (the bench's gpu_launches claim). */
+vs_status vs_stabilizer_launch_count(vs_stabilizer* s, uint64_t* n);
+
+/* ---- multi-stream batch: N independent streams advanced in lock-step, one kernel launch per
+ * stage for the whole batch (BASELINE config 4).  Semantically N vs_stabilizers. -------------- */
+typedef struct vs_batch vs_batch;
+vs_status vs_batch_create(const vs_params* params, int device, int n_streams, vs_batch** out);
+void      vs_batch_destroy(vs_batch* b);
+/* d_frames / d_outs: host arrays of n_streams device pointers (same geometry for all streams). */
+vs_status vs_batch_push_device(vs_batch* b, const uint8_t* const* d_frames, int width, int height, size_t stride,
+                               uint8_t* const* d_outs, size_t out_stride, size_t out_capacity, unsigned flags,
+                               int* out_width, int* out_height, int* produced);
+vs_status vs_batch_flush_device(vs_batch* b, uint8_t* const* d_outs, size_t out_stride, size_t out_capacity,
+                                int* out_width, int* out_height, int* produced);
+vs_status vs_batch_sync(vs_batch* b);
+void*     vs_batch_stream(vs_batch* b);
+vs_status vs_batch_launch_count(vs_batch* b, uint64_t* n);
+vs_status vs_batch_stream_counts(vs_batch* b, int stream, int* n_frame_records, int* n_output_records);
+vs_status vs_batch_frame_record(vs_batch* b, int stream, int i, vs_frame_record* rec);
+vs_status vs_batch_output_record(vs_batch* b, int stream, int i, vs_output_record* rec);
+
+/* ---- single-kernel entry points (device pointers; stream = cudaStream_t as void*, NULL = default).
+ * One per OpenCV call the reference makes on the path; used by the per-kernel parity tests and
+ * by the bench's roofline measurement. ------------------------------------------------------ */
+/* cv::warpAffine(src, dst, T, dsize, INTER_LINEAR, BORDER_CONSTANT) — Stabilizer.cpp:1056-1060.
+ * n_frames frames in one launch: frame i at d_src + i*src_frame_bytes, matrix T + 6*i. */
+vs_status vs_k_warp_affine_bgr8(const uint8_t* d_src, int src_w, int src_h, size_t src_stride, size_t src_frame_bytes,
+                                uint8_t* d_dst, int dst_w, int dst_h, size_t dst_stride, size_t dst_frame_bytes,
+                                const float* T_host, int n_frames, void* stream);
+/* cv::resize(INTER_LINEAR) + cv::cvtColor(BGR2GRAY) + the 3-level cv::pyrDown pyramid PyrLK builds —
+ * Stabilizer.cpp:449-450, 611.  Writes three tightly packed gray levels (aw x ah, then halves). */
+vs_status vs_k_gray_pyramid(const uint8_t* d_bgr, int w, int h, size_t stride, int aw, int ah,
+                            uint8_t* d_l0, uint8_t* d_l1, uint8_t* d_l2, void* stream);
+/* cv::resize(INTER_LINEAR) on 8UC1 / 8UC3 — Stabilizer.cpp:304,602,1121 */
+vs_status vs_k_resize_linear_u8(const uint8_t* d_src, int sw, int sh, size_t sstride, int channels,
+                                uint8_t* d_dst, int dw, int dh, size_t dstride, void* stream);
+/* cv::goodFeaturesToTrack(gray, maxCorners, q, minDist, noArray, 3) — Stabilizer.cpp:355-357,740-744.
+ * d_gray tightly packed w x h.  Writes up to capacity (x,y) pairs to host xy_out. */
+vs_status vs_k_good_features(const uint8_t* d_gray, int w, int h, int max_corners, double quality, double min_dist,
+                             float* xy_out_host, int capacity, int* n_out, void* stream);
+/* cv::calcOpticalFlowPyrLK(prev, next, pts, 15x15, maxLevel 2, COUNT+EPS 20/0.03) — Stabilizer.cpp:611-619.
+ * d_prev/d_next tightly packed w x h gray. */
+vs_status vs_k_pyr_lk(const uint8_t* d_prev, const uint8_t* d_next, int w, int h, const float* pts_xy_host, int n,
+                      float* next_xy_host, uint8_t* status_host, void* stream);
+/* cv::estimateAffinePartial2D(from, to, noArray, RANSAC, 5.0, 500) — Stabilizer.cpp:647-649.
+ * affine_out: 6 doubles; returns *ok = 0 when the reference would get an empty Mat. */
+vs_status vs_k_estimate_affine_partial(const float* from_xy_host, const float* to_xy_host, int n,
+                                       double* affine_out, uint8_t* inlier_mask_host, int* iters_out, int* ok,
+                                       void* stream);
+/* cv::copyMakeBorder + warpAffine (Stabilizer.cpp:982-987,1056-1060) or warpAffine + crop + resize
+ * (Stabilizer.cpp:1108-1124), fused.  mode: 0 plain, 1 border (border_mode = cv border code), 2 crop+zoom. */
+vs_status vs_k_warp_output(const uint8_t* d_src, int w, int h, size_t stride, const float* T_host,
+                           int mode, int border_size, int border_mode,
+                           uint8_t* d_dst, size_t dst_stride, int* out_w, int* out_h, void* stream);
+
+const char* vs_last_error(void);
+const char* vs_version(void);
+int         vs_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSTAB_B200_H */

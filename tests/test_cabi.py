@@ -1,0 +1,153 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol the header
+declares, the parameter block mirrors vs::Stabilizer::Parameters, the YAML reader understands the
+reference's config.yaml keys, and the product path fails loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vstab_b200.h")
+
+
+@pytest.fixture(scope="module")
+def vsb():
+    import __graft_entry__
+    __graft_entry__.build()
+    import video_stab_b200
+    return video_stab_b200
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(vsb):
+    from video_stab_b200 import _capi
+    declared = _declared_symbols()
+    assert len(declared) >= 35
+    assert sorted(_capi.SYMBOLS) == declared, "ctypes table and header disagree"
+    out = subprocess.run(["nm", "-D", "--defined-only", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\sT\s+(vs_[a-z0-9_]+)", out))
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"library does not export {missing}"
+
+
+def test_abi_version_and_struct_sizes(vsb):
+    from video_stab_b200 import _capi
+    assert vsb.lib.vs_abi_version() == 1
+    assert b"sm_100a" in vsb.lib.vs_version()
+    # field-for-field layout checks against the C compiler
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "vstab_b200.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(vs_params), sizeof(vs_frame_record), sizeof(vs_output_record),
+                           offsetof(vs_params, hf_motion_accumulator_decay), offsetof(vs_params, model_path)); return 0; }
+    '''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes[0] == C.sizeof(_capi.VsParams)
+    assert sizes[1] == C.sizeof(_capi.VsFrameRecord)
+    assert sizes[2] == C.sizeof(_capi.VsOutputRecord)
+    assert sizes[3] == _capi.VsParams.hf_motion_accumulator_decay.offset
+    assert sizes[4] == _capi.VsParams.model_path.offset
+
+
+def test_params_defaults_match_reference_header(vsb):
+    p = vsb.Parameters.from_c(vsb.Parameters().to_c())
+    d = vsb.Parameters()
+    assert p == d
+    # Stabilizer.h:78-174
+    assert (d.smoothingRadius, d.maxCorners, d.qualityLevel, d.minDistance, d.blockSize) == (30, 200, 0.01, 30.0, 3)
+    assert (d.borderType, d.borderSize, d.cropNZoom, d.smoothingMethod, d.gaussianSigma) == ("black", 0, False, "box", 2.0)
+    assert (d.minSmoothingRadius, d.maxSmoothingRadius, d.fadeDuration) == (5, 50, 30)
+    c = vsb._capi.VsParams()
+    assert vsb.lib.vs_params_default(C.byref(c)) == 0
+    assert c.smoothing_radius == 30 and c.max_corners == 200 and c.border_type == b"black"
+    assert abs(c.hf_motion_accumulator_decay - 0.9) < 1e-6 and c.jitter_frequency == 3
+
+
+REFERENCE_STYLE_YAML = """%YAML:1.0
+---
+mode:
+  width: 1920
+  smoothing_radius: 99      # not in the stabilizer section: must be ignored
+stabilizer:
+  # Basic parameters
+  smoothing_radius: 15            # comment
+  border_type: "reflect_101"
+  fadeDuration: 30
+  fadeAlpha: 0.9
+  border_size: 30
+  crop_n_zoom: true
+  logging: true
+  use_cuda: true
+  max_corners: 300
+  quality_level: 0.01
+  min_distance: 10.0
+  block_size: 3
+  smoothing_method: "gausian"       # the sample config's typo => box
+  gaussian_sigma: 15.0
+  adaptive_smoothing: true
+  min_smoothing_radius: 10
+  max_smoothing_radius: 35
+  horizon_lock: true
+  model_path: ""
+  hf_motion_accumulator_decay: 0.85
+  shake_level_threshold: 3.0
+camera:
+  smoothing_radius: 7
+"""
+
+
+def test_yaml_reader_understands_reference_config(vsb, tmp_path):
+    p = vsb.Parameters.from_yaml_string(REFERENCE_STYLE_YAML)
+    assert p.smoothingRadius == 15 and p.borderType == "reflect_101" and p.borderSize == 30
+    assert p.cropNZoom and p.logging and p.useCuda and p.horizonLock and p.adaptiveSmoothing
+    assert p.maxCorners == 300 and p.minDistance == 10.0 and p.smoothingMethod == "gausian"
+    assert p.gaussianSigma == 15.0 and (p.minSmoothingRadius, p.maxSmoothingRadius) == (10, 35)
+    assert abs(p.fadeAlpha - 0.9) < 1e-6 and abs(p.hfMotionAccumulatorDecay - 0.85) < 1e-6
+    assert p.stageOneRadius == 10                      # untouched key keeps its default
+    f = tmp_path / "config.yaml"
+    f.write_text(REFERENCE_STYLE_YAML)
+    assert vsb.Parameters.from_yaml(str(f)) == p
+    with pytest.raises(vsb.VsError) as ei:
+        vsb.Parameters.from_yaml(str(tmp_path / "missing.yaml"))
+    assert ei.value.status == 6
+
+
+def test_no_cpu_fallback(vsb):
+    """Without a GPU the product path must fail loudly, never route to a CPU implementation."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(vsb.VsError) as ei:
+        vsb.Stabilizer(vsb.Parameters())
+    assert ei.value.status == 2            # VS_ERR_NO_DEVICE
+    # and the product package never imports the oracle
+    pkg = os.path.join(ROOT, "video-stab_b200")
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|#\s*include\s+.*oracle)|oracle\.(cv_models|stabilizer_ref)\.", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                assert not pat.search(open(os.path.join(dirpath, fn)).read()), f"{fn} uses the oracle"
+
+
+def test_unsupported_flags_are_reported(vsb):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a device to get past the device check")
+    for kw in ({"borderType": "fade"}, {"droneHighFreqMode": True}, {"enableVirtualCanvas": True}):
+        with pytest.raises(vsb.VsError) as ei:
+            vsb.Stabilizer(vsb.Parameters(**kw))
+        assert ei.value.status == 7

@@ -1,0 +1,196 @@
+"""Per-kernel parity through the C-ABI (vs_k_*) against the oracle (cv2 4.13 on its baseline
+path + oracle/cv_models.py), on seeded inputs.  Integer/byte/index work is compared bit-exactly."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def vsb():
+    import __graft_entry__
+    __graft_entry__.build()
+    import video_stab_b200
+    assert torch.cuda.is_available()
+    return video_stab_b200
+
+
+def _tex(vsb, w, h, seed, ch=3):
+    m = vsb.synth.MARGIN
+    img = vsb.synth.base_texture(w, h, seed)[m:-m, m:-m]
+    return np.ascontiguousarray(img if ch == 3 else img[..., 1])
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _matrices(n, seed, scale=8.0):
+    rng = np.random.default_rng(seed)
+    T = np.zeros((n, 2, 3), np.float32)
+    for i in range(n):
+        da = np.float32(rng.normal(0, 0.01))
+        T[i] = [[np.cos(da), -np.sin(da), rng.normal(0, scale)], [np.sin(da), np.cos(da), rng.normal(0, scale)]]
+    T[0] = [[1, 0, 0], [0, 1, 0]]
+    return T
+
+
+@pytest.mark.parametrize("w,h", [(1280, 720), (1920, 1080), (641, 359)])
+def test_warp_affine_bit_exact(vsb, cv2_noopt, w, h):
+    cv2 = cv2_noopt
+    n = 4
+    frames = np.stack([_tex(vsb, w, h, 20 + i) for i in range(n)])
+    T = _matrices(n, w)
+    T[1, :, 2] = (w * 1.5, -h * 1.5)          # completely outside -> all black
+    T[2, :, 2] = (-37.25, 21.5)               # large shift: wide zero band
+    out = vsb.kernels.warp_affine(_dev(frames), T).cpu().numpy()
+    for i in range(n):
+        ref = cv2.warpAffine(frames[i], T[i], (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+        assert np.array_equal(out[i], ref), f"frame {i}: max diff {np.abs(out[i].astype(int) - ref).max()}"
+
+
+def test_warp_affine_4k_and_linearity_property(vsb, cv2_noopt):
+    cv2 = cv2_noopt
+    w, h = 3840, 2160
+    f = _tex(vsb, w, h, 31)
+    T = _matrices(2, 5)
+    out = vsb.kernels.warp_affine(_dev(np.stack([f, f])), T).cpu().numpy()
+    assert np.array_equal(out[0], f)                               # identity is the identity
+    ref = cv2.warpAffine(f, T[1], (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+    assert np.array_equal(out[1], ref)
+    # size-independent property: integer translation == shifted copy with a zero band
+    Tt = np.array([[[1, 0, 7], [0, 1, -3]]], np.float32)
+    o = vsb.kernels.warp_affine(_dev(f[None]), Tt).cpu().numpy()[0]
+    exp = np.zeros_like(f)
+    exp[:-3, 7:] = f[3:, :-7]
+    assert np.array_equal(o, exp)
+
+
+@pytest.mark.parametrize("mode,bmode,cvname", [(1, 0, "BORDER_CONSTANT"), (1, 1, "BORDER_REPLICATE"),
+                                              (1, 2, "BORDER_REFLECT"), (1, 3, "BORDER_WRAP"),
+                                              (1, 4, "BORDER_REFLECT_101")])
+def test_border_then_warp(vsb, cv2_noopt, mode, bmode, cvname):
+    cv2 = cv2_noopt
+    w, h, b = 640, 360, 24
+    f = _tex(vsb, w, h, 41)
+    T = _matrices(3, 9)[2]
+    out = vsb.kernels.warp_output(_dev(f), T, mode, b, bmode).cpu().numpy()
+    src = cv2.copyMakeBorder(f, b, b, b, b, getattr(cv2, cvname), value=(0, 0, 0))
+    ref = cv2.warpAffine(src, T, (w + 2 * b, h + 2 * b), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("w,h,b", [(1280, 720, 30), (1920, 1080, 50)])
+def test_warp_crop_zoom(vsb, cv2_noopt, w, h, b):
+    cv2 = cv2_noopt
+    f = _tex(vsb, w, h, 43)
+    T = _matrices(3, 11)[1]
+    out = vsb.kernels.warp_output(_dev(f), T, 2, b, 0).cpu().numpy()
+    wr = cv2.warpAffine(f, T, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+    ref = cv2.resize(wr[b:h - b, b:w - b].copy(), (w, h))
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (1280, 720), (3840, 2160), (1000, 562)])
+def test_gray_pyramid_bit_exact(vsb, cv2_noopt, w, h):
+    cv2 = cv2_noopt
+    f = _tex(vsb, w, h, 51)
+    lv = [t.cpu().numpy() for t in vsb.kernels.gray_pyramid(_dev(f))]
+    g = cv2.cvtColor(cv2.resize(f, (960, 540), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY)
+    assert np.array_equal(lv[0], g)
+    g1 = cv2.pyrDown(g)
+    assert np.array_equal(lv[1], g1)
+    assert np.array_equal(lv[2], cv2.pyrDown(g1))
+    small = vsb.kernels.gray_pyramid(_dev(f), first_frame=True)[0].cpu().numpy()
+    assert np.array_equal(small, cv2.cvtColor(cv2.resize(f, (480, 270), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY))
+
+
+@pytest.mark.parametrize("src,dst,ch", [((480, 270), (960, 540), 1), ((1860, 1020), (1920, 1080), 3),
+                                        ((1920, 1080), (960, 540), 3), ((641, 359), (960, 540), 3)])
+def test_resize_linear_bit_exact(vsb, cv2_noopt, src, dst, ch):
+    cv2 = cv2_noopt
+    rng = np.random.default_rng(src[0])
+    shape = (src[1], src[0], 3) if ch == 3 else (src[1], src[0])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    out = vsb.kernels.resize_linear(_dev(img), dst).cpu().numpy()
+    assert np.array_equal(out, cv2.resize(img, dst, interpolation=cv2.INTER_LINEAR))
+
+
+@pytest.mark.parametrize("w,h,mc,q,md", [(960, 540, 200, 0.02, 15.0), (480, 270, 200, 0.01, 30.0),
+                                         (960, 540, 50, 0.05, 7.5), (480, 270, 0, 0.3, 0.0),
+                                         (960, 540, 1000, 0.001, 3.0), (480, 270, 300, 0.01, 10.0)])
+def test_good_features_ordered_list_bit_exact(vsb, cv2_noopt, w, h, mc, q, md):
+    cv2 = cv2_noopt
+    for seed in (1, 2, 3):
+        g = _tex(vsb, w, h, seed, 1)
+        ref = cv2.goodFeaturesToTrack(g, mc, q, md, None, blockSize=3)
+        ref = np.zeros((0, 2), np.float32) if ref is None else ref.reshape(-1, 2)
+        got = vsb.kernels.good_features(_dev(g), mc, q, md)
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        assert np.array_equal(got, ref)
+
+
+def test_good_features_flat_and_sparse(vsb, cv2_noopt):
+    cv2 = cv2_noopt
+    flat = np.full((540, 960), 90, np.uint8)
+    assert len(vsb.kernels.good_features(_dev(flat), 200, 0.02, 15.0)) == 0
+    one = flat.copy()
+    one[200:230, 300:340] = 200                       # a single bright rectangle: 4 corners
+    ref = cv2.goodFeaturesToTrack(one, 200, 0.02, 15.0, None, blockSize=3).reshape(-1, 2)
+    assert np.array_equal(vsb.kernels.good_features(_dev(one), 200, 0.02, 15.0), ref)
+
+
+def _moved_pair(vsb, cv2, seed, ang, shift, w=960, h=540):
+    big = vsb.synth.base_texture(w, h, seed)[..., 1].copy()
+    m = cv2.getRotationMatrix2D((big.shape[1] / 2, big.shape[0] / 2), ang, 1.0)
+    m[:, 2] += shift
+    moved = cv2.warpAffine(big, m, (big.shape[1], big.shape[0]))
+    s = vsb.synth.MARGIN
+    return np.ascontiguousarray(big[s:-s, s:-s]), np.ascontiguousarray(moved[s:-s, s:-s])
+
+
+@pytest.mark.parametrize("seed,ang,shift", [(5, 0.3, (3.3, -2.1)), (6, -0.5, (-9.5, 6.25)), (7, 0.0, (25.0, 14.0))])
+def test_pyr_lk_bit_exact(vsb, cv2_noopt, seed, ang, shift):
+    cv2 = cv2_noopt
+    prev, nxt = _moved_pair(vsb, cv2, seed, ang, shift)
+    pts = cv2.goodFeaturesToTrack(prev, 200, 0.02, 15.0, None, blockSize=3).reshape(-1, 2)
+    edge = np.array([[0, 0], [959, 539], [3, 200], [958, 10], [500, 538], [1, 1], [480.5, 270.25]], np.float32)
+    pts = np.vstack([pts, edge])
+    ref, st, _ = cv2.calcOpticalFlowPyrLK(prev, nxt, pts, None, winSize=(15, 15), maxLevel=2,
+                                          criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 20, 0.03))
+    got, gst = vsb.kernels.pyr_lk(_dev(prev), _dev(nxt), pts)
+    assert np.array_equal(gst, st.ravel())
+    ok = st.ravel() == 1
+    assert np.array_equal(got[ok].view(np.uint32), ref.reshape(-1, 2)[ok].view(np.uint32)), \
+        f"max diff {np.abs(got[ok] - ref.reshape(-1, 2)[ok]).max()}"
+
+
+@pytest.mark.parametrize("n,outl,noise", [(200, 0.0, 0.05), (200, 0.3, 0.2), (60, 0.5, 0.5), (12, 0.25, 0.1),
+                                          (4, 0.0, 0.01), (150, 0.7, 0.3), (1500, 0.4, 0.3), (3, 0.0, 0.0), (0, 0, 0)])
+def test_ransac_partial_affine(vsb, cv2_noopt, n, outl, noise):
+    cv2 = cv2_noopt
+    for seed in range(6):
+        rng = np.random.default_rng(1000 * n + seed)
+        src = (rng.random((n, 2)) * (960, 540)).astype(np.float32)
+        a = rng.normal(0, 0.01)
+        sc = 1 + rng.normal(0, 0.01)
+        r = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]) * sc
+        dst = src @ r.T + rng.normal(0, 5, 2) + rng.normal(0, noise, (n, 2))
+        k = int(outl * n)
+        if k:
+            dst[:k] += rng.normal(0, 40, (k, 2))
+        dst = dst.astype(np.float32)
+        got, gmask, iters = vsb.kernels.estimate_affine_partial(src, dst)
+        if n < 4:                       # the reference only calls the estimator with >= 4 pairs (:645)
+            assert got is None
+            continue
+        ref, mask = cv2.estimateAffinePartial2D(src, dst, None, cv2.RANSAC, 5.0, 500)
+        if ref is None or ref.size == 0:
+            assert got is None
+            continue
+        assert got is not None
+        assert np.array_equal(gmask, mask.ravel()), "inlier mask differs"
+        # 1e-3 px of corner displacement (north star); the fit itself agrees to ~1e-9
+        assert np.abs(got - ref).max() < 1e-8

@@ -1,0 +1,194 @@
+"""Whole-path parity through the reference-shaped API (vs::Stabilizer mirror over the C-ABI) against
+the oracle run live and against the committed golden fixtures: bit-exact corner lists, LK status and
+RANSAC inlier masks; transforms within 1e-3 px of corner displacement; frames within 1 LSB."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HALF_DIAG = 1102.0      # half diagonal of the 960x540 analysis image: rad -> px of corner displacement
+
+
+@pytest.fixture(scope="module")
+def vsb():
+    import __graft_entry__
+    __graft_entry__.build()
+    import video_stab_b200
+    assert torch.cuda.is_available()
+    return video_stab_b200
+
+
+def _run(vsb, clip, params):
+    st = vsb.Stabilizer(params)
+    outs = []
+    for f in clip:
+        o = st.stabilize(f)
+        if o is not None:
+            outs.append(o)
+    while True:
+        o = st.flush()
+        if o is None:
+            break
+        outs.append(o)
+    return outs, st
+
+
+def _crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF
+
+
+def _check_against_golden(vsb, name, w, h, n, seed, params, frame_tol=1):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    clip = vsb.synth.make_clip(w, h, n, seed)
+    assert np.array_equal(np.array([_crc(f) for f in clip], np.uint32), g["input_crc"]), \
+        "synthetic clip differs from the one the goldens were made from"
+    outs, st = _run(vsb, clip, params)
+    nf, no = st.counts()
+    assert nf == len(g["transforms"]) and no == len(g["out_index"]) == len(outs)
+    assert np.array_equal(st.first_corners(), g["first_corners"])
+    exact_pts = 0
+    for i in range(nf):
+        rec = st.frame_record(i)
+        pts = st.frame_points(i)
+        pn = int(g["prev_n"][i])
+        assert rec.n_prev_pts == pn
+        assert np.array_equal(pts["prev"], g["prev_pts"][i, :pn])
+        assert np.array_equal(pts["status"], g["status"][i, :pn]), f"frame {i}: LK status"
+        ok = pts["status"] == 1
+        assert np.abs(pts["next"][ok] - g["next_pts"][i, :pn][ok]).max(initial=0) < 1e-3
+        exact_pts += int(np.array_equal(pts["next"][ok].view(np.uint32), g["next_pts"][i, :pn][ok].view(np.uint32)))
+        mn = int(g["inlier_n"][i])
+        if mn >= 0:
+            assert np.array_equal(pts["inlier_mask"], g["inlier_mask"][i, :mn]), f"frame {i}: inlier mask"
+        else:
+            assert pts["inlier_mask"] is None
+        dn = int(g["detected_n"][i])
+        if dn >= 0:
+            assert np.array_equal(pts["detected"], g["detected"][i, :dn]), f"frame {i}: corner list"
+        else:
+            assert pts["detected"] is None
+        d = np.abs(np.asarray(rec.transform) - g["transforms"][i])
+        assert d[0] < 1e-3 and d[1] < 1e-3 and d[2] * HALF_DIAG < 1e-3, f"frame {i}: transform {d}"
+        dp = np.abs(np.asarray(rec.path) - g["path"][i])
+        assert dp[0] < 2e-3 and dp[1] < 2e-3 and dp[2] * HALF_DIAG < 2e-3
+    worst = 0
+    exact_frames = 0
+    for k in range(no):
+        r = st.output_record(k)
+        assert r.index == g["out_index"][k] and r.passthrough == g["out_passthrough"][k]
+        if not r.passthrough:
+            assert r.radius == g["out_radius"][k] and r.intent == g["out_intent"][k]
+            dT = np.abs(np.asarray(r.T).reshape(2, 3) - g["out_T"][k])
+            assert dT[:, 2].max() < 1e-3 and dT[:, :2].max() * HALF_DIAG < 1e-3
+        assert tuple(outs[k].shape) == tuple(g["out_shape"][k])
+        row = outs[k][outs[k].shape[0] // 2, 100:260, :].astype(np.int16)
+        worst = max(worst, int(np.abs(row - g["out_row"][k].astype(np.int16)).max()))
+        exact_frames += int(_crc(outs[k]) == g["out_crc"][k])
+    assert worst <= frame_tol
+    return exact_pts / max(nf, 1), exact_frames / max(no, 1)
+
+
+def test_config1_720p_300_frames_vs_golden(vsb):
+    """BASELINE config 1: 1280x720, 300 frames, defaults."""
+    lk_exact, frames_exact = _check_against_golden(vsb, "cfg1_720p_default", 1280, 720, 300, 1234, vsb.Parameters())
+    print(f"cfg1: LK point sets bit-exact on {lk_exact:.1%} of frames, output frames bit-exact on {frames_exact:.1%}")
+    assert lk_exact > 0.95
+
+
+def test_config2_1080p_radius15_vs_golden(vsb):
+    _check_against_golden(vsb, "cfg2_1080p_r15", 1920, 1080, 48, 2000, vsb.Parameters(smoothingRadius=15))
+
+
+def test_config3_4k_cropzoom_vs_golden(vsb):
+    _check_against_golden(vsb, "cfg3_4k_cropzoom", 3840, 2160, 10, 3000,
+                          vsb.Parameters(smoothingRadius=5, cropNZoom=True, borderSize=30))
+
+
+def test_border_reflect_vs_golden(vsb):
+    _check_against_golden(vsb, "border_reflect_720p", 1280, 720, 12, 77,
+                          vsb.Parameters(smoothingRadius=5, borderType="reflect", borderSize=24))
+
+
+def test_gaussian_vs_golden(vsb):
+    _check_against_golden(vsb, "gaussian_720p", 1280, 720, 40, 78,
+                          vsb.Parameters(smoothingRadius=10, smoothingMethod="gaussian", gaussianSigma=2.0))
+
+
+def test_kalman_horizon_lock_vs_golden(vsb):
+    _check_against_golden(vsb, "kalman_hlock_720p", 1280, 720, 40, 79,
+                          vsb.Parameters(smoothingRadius=10, smoothingMethod="kalman", horizonLock=True))
+
+
+def test_live_oracle_full_frames(vsb, cv2_noopt):
+    """Full-frame comparison against the oracle run on this box (not just the golden row slices)."""
+    from oracle.stabilizer_ref import Parameters, run_clip
+    clip = vsb.synth.make_clip(1280, 720, 24, 555)
+    outs, st = _run(vsb, clip, vsb.Parameters(smoothingRadius=8))
+    ref_outs, ref = run_clip(clip, Parameters(smoothingRadius=8))
+    assert len(outs) == len(ref_outs) == 24
+    for k, (a, b) in enumerate(zip(outs, ref_outs)):
+        assert a.shape == b.shape
+        d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+        assert d.max() <= 1, f"output {k}: {d.max()} LSB"
+    assert np.array_equal(outs[-1], clip[-1])        # last frame has no transform: passed through (:774-780)
+
+
+def test_adaptive_smoothing_gate(vsb, cv2_noopt):
+    from oracle.stabilizer_ref import Parameters, run_clip
+    clip = vsb.synth.make_clip(640, 360, 40, 91)
+    kw = dict(smoothingRadius=12, adaptiveSmoothing=True, minSmoothingRadius=6, maxSmoothingRadius=20)
+    ref_outs, ref = run_clip(clip, Parameters(**kw), flush=False)
+    st = vsb.Stabilizer(vsb.Parameters(**kw))
+    produced = [st.stabilize(f) is not None for f in clip]
+    ref_st = __import__("oracle.stabilizer_ref", fromlist=["StabilizerRef"]).StabilizerRef(Parameters(**kw))
+    ref_produced = [ref_st.stabilize(f) is not None for f in clip]
+    assert produced == ref_produced
+
+
+def test_empty_frame_and_clean(vsb):
+    st = vsb.Stabilizer(vsb.Parameters(smoothingRadius=5))
+    assert st.stabilize(None) is None
+    assert st.flush() is None
+    clip = vsb.synth.make_clip(640, 360, 8, 3)
+    a = [st.stabilize(f) for f in clip]
+    st.clean()
+    b = [st.stabilize(f) for f in clip]
+    assert [x is None for x in a] == [x is None for x in b] == [True] * 4 + [False] * 4
+    for x, y in zip(a, b):
+        if x is not None:
+            assert np.array_equal(x, y)             # clean() restores a fresh stabilizer
+
+
+def test_device_api_and_batch_equal_single(vsb):
+    """Config 4 in miniature: 3 streams in one lock-step batch == 3 independent stabilizers."""
+    w, h, n, S = 640, 360, 14, 3
+    clips = [vsb.synth.make_clip(w, h, n, 2000 + s) for s in range(S)]
+    params = vsb.Parameters(smoothingRadius=6)
+    singles = [_run(vsb, c, params)[0] for c in clips]
+    d_clips = [torch.from_numpy(c).cuda() for c in clips]
+    d_out = torch.zeros((S, n, h, w, 3), dtype=torch.uint8, device="cuda")
+    batch = vsb.StabilizerBatch(params, S)
+    k = 0
+    for i in range(n):
+        r = batch.push_device([d_clips[s][i].data_ptr() for s in range(S)], w, h, w * 3,
+                              [d_out[s, k].data_ptr() for s in range(S)], w * 3, h * w * 3, borrow=True)
+        if r is not None:
+            k += 1
+    while True:
+        r = batch.flush_device([d_out[s, min(k, n - 1)].data_ptr() for s in range(S)], w * 3, h * w * 3)
+        if r is None:
+            break
+        k += 1
+    batch.sync()
+    assert k == n
+    got = d_out.cpu().numpy()
+    for s in range(S):
+        for i in range(n):
+            assert np.array_equal(got[s, i], singles[s][i]), f"stream {s} frame {i}"
+    assert batch.launch_count() > 0

@@ -1,0 +1,107 @@
+// common.cuh — device-side data layout shared by every kernel of the stabilization path.
+//
+// Vocabulary follows the reference (src/Stabilizer.cpp): a *lane* is one independent video
+// stream (one vs::Stabilizer instance); lanes of a batch advance in lock-step so every stage
+// is ONE kernel launch over all lanes (blockIdx.z = lane).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/vstab_b200.h"
+
+#define VS_PAD 16            // reflect-101 border kept around every gray pyramid level
+#define VS_WIN 15            // LK window (Stabilizer.cpp:616)
+#define VS_LEVELS 3          // maxLevel 2 (Stabilizer.cpp:617)
+#define VS_AW 960            // analysis size (Stabilizer.cpp:410)
+#define VS_AH 540
+#define VS_FW 480            // first-frame analysis size (Stabilizer.cpp:277)
+#define VS_FH 270
+#define VS_RANSAC_MAX_ITERS 500
+#define VS_KAL_FLOATS 32      // per-lane scalar block: 3 x 6 Kalman state floats + hand-off slots
+#define VS_KAL_RADIUS_SLOT 18
+#define VS_GRID_SLOTS 4      // max accepted corners per min-distance cell (geometric bound)
+
+// One gray level in HBM: `base` addresses pixel (0,0); rows are `pitch` bytes apart; a VS_PAD-wide
+// BORDER_REFLECT_101 frame around the image is materialised so window/tap reads never branch.
+struct GrayLevel {
+    uint8_t* base;
+    int w, h, pitch;
+};
+
+struct Pyramid {
+    GrayLevel lv[VS_LEVELS];
+};
+
+// Inverse-mapped warp set-up, produced on device by the motion kernel, consumed by the warp kernel.
+struct WarpParams {
+    double m[6];        // inverted matrix (cv::warpAffine's M after invertAffineTransform)
+    float  T[6];        // forward float32 matrix (for the record)
+    int    passthrough; // 1: copy the frame unchanged (Stabilizer.cpp:774-780)
+    int    pad;
+};
+
+// Per-lane device state.  An array of these lives in HBM; kernels index it with blockIdx.z.
+struct LaneDev {
+    Pyramid pyr[2];                 // ping-pong: previous / current analysis pyramid
+    GrayLevel small0;               // 480x270 gray of the very first frame
+    float* eig;                     // min-eigenvalue map, VS_AW*VS_AH floats
+    unsigned int* eig_max;          // max(eig) as float bits (non-negative => orderable)
+    unsigned long long* cand;       // corner candidates: (float bits << 32) | linear address
+    int* cand_count;
+    unsigned int* grid;             // min-distance grid: per cell [count, slot0..slot3]
+    float2* kp;                     // "prevKeypointsCPU_"
+    int* kp_count;
+    float2* lk_next;
+    uint8_t* lk_status;
+    uint8_t* inlier_mask;
+    float* transforms;              // 3 floats per frame  (transforms_)
+    float* path;                    // 3 floats per frame  (path_)
+    float* kalman;                  // 3 x {x0,x1,P00,P01,P10,P11} incremental Kalman state
+    vs_frame_record* frec;
+    vs_output_record* orec;
+    float2* log_prev;               // ring of per-frame point logs (tests)
+    float2* log_next;
+    uint8_t* log_status;
+    uint8_t* log_mask;
+    float2* log_detected;
+    float2* first_corners;
+    int* first_count;
+    WarpParams* wp;
+    int kp_capacity;
+    int log_depth;
+    int record_capacity;
+    int pad0;
+};
+
+// Host-known scalars of one lock-step frame step, passed by value to the motion kernel.
+struct StepInfo {
+    int frame_no;          // n >= 1: this is the n-th generateTransform() call (frame n)
+    int cur;               // pyramid slot holding the current frame
+    int pop_index;         // index of the frame to emit after this step, or -1
+    int path_len_at_pop;   // path_.size() when that frame is popped
+    int smoothing_radius;  // params_.smoothingRadius as of this step
+    int method;            // 0 box, 1 gaussian, 2 kalman
+    float gaussian_sigma;
+    int horizon_lock;
+    int n_out;             // output-record slot
+    int adaptive;          // adaptiveSmoothing
+    int min_radius, max_radius;
+};
+
+static __device__ __forceinline__ int reflect101(int p, int len) {
+    // cv::borderInterpolate(BORDER_REFLECT_101) for |overshoot| < len
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) {
+        if (p < 0) p = -p;
+        else p = 2 * len - 2 - p;
+    }
+    return p;
+}
+
+#define CUDA_TRY(x)                                                                   \
+    do {                                                                              \
+        cudaError_t e__ = (x);                                                        \
+        if (e__ != cudaSuccess) return vs_set_cuda_error(e__, #x, __FILE__, __LINE__); \
+    } while (0)
+
+vs_status vs_set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
+vs_status vs_set_error(vs_status st, const char* msg);

@@ -1,0 +1,462 @@
+// engine.cu — host orchestration.  Mirrors the control flow of Stabilizer::stabilize / flush / clean /
+// generateTransform / applyNextSmoothTransform (Stabilizer.cpp:221-400, 402-761, 763-1137): every
+// decision the reference takes on the host from frame COUNTS stays on the host; every decision it
+// takes from DATA (tracked-pair count, RANSAC outcome, adaptive radius, motion intent) is taken on
+// the device, so a step is a pure launch sequence with no host<->device round trip.
+#include "engine.h"
+
+#include <cstdio>
+#include <cstring>
+
+static thread_local char g_err[512] = "";
+
+vs_status vs_set_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorMemoryAllocation) return VS_ERR_OUT_OF_MEMORY;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return VS_ERR_NO_DEVICE;
+    return VS_ERR_CUDA;
+}
+vs_status vs_set_error(vs_status st, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return st;
+}
+extern "C" const char* vs_last_error(void) { return g_err; }
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+#define MO_MAXP_HOST 2048
+
+vs_status Engine::create(const vs_params& p, int device, int n_lanes, Engine** out) {
+    *out = nullptr;
+    if (n_lanes < 1 || n_lanes > VS_MAX_GROUP) return vs_set_error(VS_ERR_INVALID_ARG, "n_streams must be 1..64");
+    if (!strcmp(p.border_type, "fade"))
+        return vs_set_error(VS_ERR_UNSUPPORTED, "border_type \"fade\" is not built yet (SURVEY.md 8f rank 4)");
+    if (p.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode is not built yet");
+    if (p.enable_virtual_canvas) return vs_set_error(VS_ERR_UNSUPPORTED, "enable_virtual_canvas is not built yet");
+    if (p.block_size != 3) return vs_set_error(VS_ERR_UNSUPPORTED, "only block_size 3 (the reference default) is supported");
+    if (p.adaptive_smoothing && n_lanes > 1)
+        return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing makes the latency gate data dependent; single-stream handles only");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return vs_set_error(VS_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return vs_set_error(VS_ERR_INVALID_ARG, "bad device ordinal");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return vs_set_error(VS_ERR_NO_DEVICE, "kernels are built for sm_100a (B200) only");
+    Engine* eng = new Engine();
+    vs_status st = eng->init(p, device, n_lanes);
+    if (st != VS_OK) { delete eng; return st; }
+    *out = eng;
+    return VS_OK;
+}
+
+template <typename T>
+static vs_status dalloc(std::vector<void*>& allocs, T** out, size_t n) {
+    void* ptr = nullptr;
+    CUDA_TRY(cudaMalloc(&ptr, n * sizeof(T)));
+    allocs.push_back(ptr);
+    CUDA_TRY(cudaMemset(ptr, 0, n * sizeof(T)));
+    *out = (T*)ptr;
+    return VS_OK;
+}
+#define VS_TRY(x) do { vs_status s__ = (x); if (s__ != VS_OK) return s__; } while (0)
+
+static vs_status alloc_level(std::vector<void*>& allocs, int w, int h, GrayLevel* lv) {
+    int pitch = (int)align_up((size_t)w + 2 * VS_PAD, 16);
+    uint8_t* mem = nullptr;
+    VS_TRY(dalloc(allocs, &mem, (size_t)pitch * (h + 2 * VS_PAD)));
+    lv->base = mem + (size_t)VS_PAD * pitch + VS_PAD;
+    lv->w = w; lv->h = h; lv->pitch = pitch;
+    return VS_OK;
+}
+
+vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
+    p_ = p;
+    device_ = device;
+    n_lanes_ = n_lanes;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    // mapBorderMode, Stabilizer.cpp:31-38 and the cropNZoom override :67-71
+    border_mode_ = !strcmp(p.border_type, "reflect") ? 2 : !strcmp(p.border_type, "reflect_101") ? 4
+                 : !strcmp(p.border_type, "replicate") ? 1 : !strcmp(p.border_type, "wrap") ? 3 : 0;
+    if (p.crop_n_zoom) border_mode_ = 0;
+    method_ = !strcmp(p.smoothing_method, "gaussian") ? 1 : !strcmp(p.smoothing_method, "kalman") ? 2 : 0;
+    smoothing_radius_ = p.smoothing_radius;
+    cap_first_ = p.max_corners > 0 ? (p.max_corners < MO_MAXP_HOST ? p.max_corners : MO_MAXP_HOST) : MO_MAXP_HOST;
+    int mc = p.max_corners < 200 ? p.max_corners : 200;                 // std::min(maxCorners, 200) :741
+    cap_redetect_ = mc > 0 ? mc : MO_MAXP_HOST;
+    kp_cap_ = cap_first_ > cap_redetect_ ? cap_first_ : cap_redetect_;
+    log_depth_ = n_lanes == 1 ? 512 : 8;
+    traj_cap_ = 1 << 15;
+    return alloc_fixed();
+}
+
+vs_status Engine::alloc_fixed() {
+    h_lanes_.assign(n_lanes_, LaneDev{});
+    VS_TRY(dalloc(allocs_, &d_lanes_, (size_t)n_lanes_));
+    VS_TRY(dalloc(allocs_, &d_detect_counters_, (size_t)n_lanes_ * 2));
+    int* small_counters = nullptr;
+    VS_TRY(dalloc(allocs_, &small_counters, (size_t)n_lanes_ * 2));
+    size_t gw = gftt_grid_words(VS_FW, VS_FH, p_.min_distance);
+    size_t gw2 = gftt_grid_words(VS_AW, VS_AH, 15.0);
+    if (gw2 > gw) gw = gw2;
+    traj_bufs_.clear();
+    for (int l = 0; l < n_lanes_; ++l) {
+        LaneDev& L = h_lanes_[l];
+        for (int s = 0; s < 2; ++s) {
+            int w = VS_AW, h = VS_AH;
+            for (int k = 0; k < VS_LEVELS; ++k) {
+                VS_TRY(alloc_level(allocs_, w, h, &L.pyr[s].lv[k]));
+                w = (w + 1) / 2; h = (h + 1) / 2;
+            }
+        }
+        VS_TRY(alloc_level(allocs_, VS_FW, VS_FH, &L.small0));
+        VS_TRY(dalloc(allocs_, &L.eig, (size_t)VS_AW * VS_AH));
+        VS_TRY(dalloc(allocs_, &L.cand, (size_t)VS_AW * VS_AH));
+        VS_TRY(dalloc(allocs_, &L.grid, gw));
+        L.eig_max = d_detect_counters_ + 2 * l;
+        L.cand_count = (int*)(d_detect_counters_ + 2 * l + 1);
+        L.kp_count = small_counters + 2 * l;
+        L.first_count = small_counters + 2 * l + 1;
+        VS_TRY(dalloc(allocs_, &L.kp, (size_t)kp_cap_));
+        VS_TRY(dalloc(allocs_, &L.lk_next, (size_t)kp_cap_));
+        VS_TRY(dalloc(allocs_, &L.lk_status, (size_t)kp_cap_));
+        VS_TRY(dalloc(allocs_, &L.inlier_mask, (size_t)kp_cap_));
+        VS_TRY(dalloc(allocs_, &L.first_corners, (size_t)kp_cap_));
+        VS_TRY(dalloc(allocs_, &L.kalman, (size_t)VS_KAL_FLOATS));
+        VS_TRY(dalloc(allocs_, &L.wp, (size_t)1));
+        size_t ln = (size_t)log_depth_ * kp_cap_;
+        VS_TRY(dalloc(allocs_, &L.log_prev, ln));
+        VS_TRY(dalloc(allocs_, &L.log_next, ln));
+        VS_TRY(dalloc(allocs_, &L.log_status, ln));
+        VS_TRY(dalloc(allocs_, &L.log_mask, ln));
+        VS_TRY(dalloc(allocs_, &L.log_detected, ln));
+        // trajectory + records: separately tracked so they can grow
+        CUDA_TRY(cudaMalloc((void**)&L.transforms, (size_t)traj_cap_ * 3 * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&L.path, (size_t)traj_cap_ * 3 * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&L.frec, (size_t)traj_cap_ * sizeof(vs_frame_record)));
+        CUDA_TRY(cudaMalloc((void**)&L.orec, (size_t)traj_cap_ * sizeof(vs_output_record)));
+        L.kp_capacity = kp_cap_;
+        L.log_depth = log_depth_;
+        L.record_capacity = traj_cap_;
+    }
+    CUDA_TRY(cudaMemcpy(d_lanes_, h_lanes_.data(), sizeof(LaneDev) * n_lanes_, cudaMemcpyHostToDevice));
+    return VS_OK;
+}
+
+vs_status Engine::grow_trajectory() {
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    int ncap = traj_cap_ * 2;
+    for (int l = 0; l < n_lanes_; ++l) {
+        LaneDev& L = h_lanes_[l];
+        float *t = nullptr, *pa = nullptr;
+        vs_frame_record* fr = nullptr;
+        vs_output_record* orr = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&t, (size_t)ncap * 3 * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&pa, (size_t)ncap * 3 * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&fr, (size_t)ncap * sizeof(vs_frame_record)));
+        CUDA_TRY(cudaMalloc((void**)&orr, (size_t)ncap * sizeof(vs_output_record)));
+        CUDA_TRY(cudaMemcpy(t, L.transforms, (size_t)traj_cap_ * 3 * sizeof(float), cudaMemcpyDeviceToDevice));
+        CUDA_TRY(cudaMemcpy(pa, L.path, (size_t)traj_cap_ * 3 * sizeof(float), cudaMemcpyDeviceToDevice));
+        CUDA_TRY(cudaMemcpy(fr, L.frec, (size_t)traj_cap_ * sizeof(vs_frame_record), cudaMemcpyDeviceToDevice));
+        CUDA_TRY(cudaMemcpy(orr, L.orec, (size_t)traj_cap_ * sizeof(vs_output_record), cudaMemcpyDeviceToDevice));
+        cudaFree(L.transforms); cudaFree(L.path); cudaFree(L.frec); cudaFree(L.orec);
+        L.transforms = t; L.path = pa; L.frec = fr; L.orec = orr;
+        L.record_capacity = ncap;
+    }
+    traj_cap_ = ncap;
+    CUDA_TRY(cudaMemcpy(d_lanes_, h_lanes_.data(), sizeof(LaneDev) * n_lanes_, cudaMemcpyHostToDevice));
+    return VS_OK;
+}
+
+void Engine::free_all() {
+    if (stream_) cudaStreamSynchronize(stream_);
+    for (auto& L : h_lanes_) {
+        cudaFree(L.transforms); cudaFree(L.path); cudaFree(L.frec); cudaFree(L.orec);
+    }
+    h_lanes_.clear();
+    for (void* p : allocs_) cudaFree(p);
+    allocs_.clear();
+    if (d_ring_) cudaFree(d_ring_);
+    if (d_out_) cudaFree(d_out_);
+    if (d_scratch_) cudaFree(d_scratch_);
+    d_ring_ = d_out_ = d_scratch_ = nullptr;
+    if (stream_) cudaStreamDestroy(stream_);
+    stream_ = nullptr;
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device_);
+    free_all();
+}
+
+vs_status Engine::sync() {
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    return VS_OK;
+}
+
+vs_status Engine::clean() {
+    // Stabilizer::clean, Stabilizer.cpp:221-256
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    queue_.clear();
+    first_ = true;
+    next_index_ = 0;
+    n_frames_ = 0;
+    n_out_ = 0;
+    detect_counter_ = 0;
+    smoothing_radius_ = p_.smoothing_radius;
+    W_ = H_ = 0;
+    return VS_OK;
+}
+
+vs_status Engine::ensure_geometry(int w, int h, bool need_ring, bool need_out, bool need_scratch) {
+    if (W_ == 0) {
+        W_ = w; H_ = h;
+        frame_bytes_ = (size_t)w * 3 * h;
+        int b = (p_.border_size > 0 && !p_.crop_n_zoom) ? p_.border_size : 0;
+        out_bytes_ = (size_t)(w + 2 * b) * 3 * (h + 2 * b);
+        ring_slots_ = 36;           // latency gate is at most 35 frames (Stabilizer.cpp:383)
+        if (d_ring_) { cudaFree(d_ring_); d_ring_ = nullptr; }
+        if (d_out_) { cudaFree(d_out_); d_out_ = nullptr; }
+        if (d_scratch_) { cudaFree(d_scratch_); d_scratch_ = nullptr; }
+    } else if (w != W_ || h != H_) {
+        return vs_set_error(VS_ERR_INVALID_ARG, "frame size changed mid-stream (call clean() first)");
+    }
+    if (need_ring && !d_ring_) CUDA_TRY(cudaMalloc((void**)&d_ring_, frame_bytes_ * ring_slots_ * n_lanes_));
+    if (need_out && !d_out_) CUDA_TRY(cudaMalloc((void**)&d_out_, out_bytes_ * n_lanes_));
+    if (need_scratch && !d_scratch_) CUDA_TRY(cudaMalloc((void**)&d_scratch_, frame_bytes_ * n_lanes_));
+    return VS_OK;
+}
+
+StepInfo Engine::step_info(int pop_index) const {
+    StepInfo s{};
+    s.frame_no = n_frames_;
+    s.cur = n_frames_ & 1;
+    s.pop_index = pop_index;
+    s.path_len_at_pop = n_frames_;
+    s.smoothing_radius = smoothing_radius_;
+    s.method = method_;
+    s.gaussian_sigma = (float)p_.gaussian_sigma;
+    s.horizon_lock = p_.horizon_lock;
+    s.n_out = n_out_;
+    s.adaptive = p_.adaptive_smoothing;
+    s.min_radius = p_.min_smoothing_radius;
+    s.max_radius = p_.max_smoothing_radius;
+    return s;
+}
+
+// generateTransform, Stabilizer.cpp:402-761 (CPU branch) as a launch sequence
+vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
+    if (n_frames_ + 1 >= traj_cap_) VS_TRY(grow_trajectory());
+    const int frame_no = ++n_frames_;
+    const int cur = frame_no & 1, prev = cur ^ 1;
+    PtrPack src;
+    for (int l = 0; l < n_lanes_; ++l) src.p[l] = e.frames[l];
+    if (frame_no == 1) {
+        // prevGray is still the 480x270 first-frame image: cv::resize it up (Stabilizer.cpp:598-603)
+        launch_upsample_small(d_lanes_, n_lanes_, prev, stream_);
+        launch_pyrdown(d_lanes_, n_lanes_, prev, stream_);
+        launches_ += 3;
+    }
+    launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, stream_);      // :449-450
+    launch_pyrdown(d_lanes_, n_lanes_, cur, stream_);
+    launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, stream_);   // :611-619
+    launches_ += 4;
+
+    const bool adaptive = p_.adaptive_smoothing != 0;
+    int pop_index = -1;
+    if (!adaptive) {
+        int gate = clampi(smoothing_radius_, 5, 35);                                  // :383
+        *will_pop = (int)queue_.size() >= gate;
+        if (*will_pop) pop_index = queue_.front().index;
+    }
+    launch_motion(d_lanes_, n_lanes_, step_info(pop_index), stream_);                  // :629-688 (+ :783-908)
+    launches_ += 1;
+
+    if ((++detect_counter_ % 2) == 0) {                                               // :696-697
+        CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, stream_));
+        int mc = p_.max_corners < 200 ? p_.max_corners : 200;
+        launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, frame_no, stream_);   // :740-744
+        launches_ += 3;
+    }
+    if (adaptive) {
+        // updateAdaptiveParameters (:691-693, :1562-1574) changes params_.smoothingRadius, which moves the
+        // latency gate: the one data-dependent host decision of the path, so this mode reads it back.
+        if (frame_no >= 3) {
+            int nr = 0;
+            CUDA_TRY(cudaMemcpyAsync(&nr, h_lanes_[0].kalman + VS_KAL_RADIUS_SLOT, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+            CUDA_TRY(cudaStreamSynchronize(stream_));
+            smoothing_radius_ = nr;
+        }
+        int gate = clampi(smoothing_radius_, 5, 35);
+        *will_pop = (int)queue_.size() >= gate;
+        if (*will_pop) {
+            launch_smooth_only(d_lanes_, n_lanes_, step_info(queue_.front().index), stream_);
+            launches_ += 1;
+        }
+    }
+    return VS_OK;
+}
+
+// the warp half of applyNextSmoothTransform, Stabilizer.cpp:979-1137
+vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, bool host_io, int* ow, int* oh) {
+    QueueEntry e = queue_.front();
+    queue_.pop_front();
+    const bool passthrough = e.index >= n_frames_;                                    // :774-780
+    const int b = p_.border_size;
+    const int mode = (passthrough || b <= 0) ? 0 : (p_.crop_n_zoom ? 2 : 1);
+    int w = W_, h = H_;
+    if (mode == 1) { w = W_ + 2 * b; h = H_ + 2 * b; }
+    if (mode == 2 && (W_ - 2 * b <= 0 || H_ - 2 * b <= 0)) {}                         // :1114-1115 handled below
+    *ow = w; *oh = h;
+    const size_t tight = (size_t)w * 3;
+    if (out_stride == 0) out_stride = tight;
+    if (out_stride < tight || out_stride * (size_t)(h - 1) + tight > out_capacity)
+        return vs_set_error(VS_ERR_BUFFER_TOO_SMALL, "output buffer too small for the stabilized frame");
+    VS_TRY(ensure_geometry(W_, H_, false, host_io, mode == 2));
+
+    MutPtrPack dst;
+    for (int l = 0; l < n_lanes_; ++l) dst.p[l] = host_io ? d_out_ + out_bytes_ * l : outs[l];
+    const size_t dstride = host_io ? tight : out_stride;
+    if (passthrough) {
+        for (int l = 0; l < n_lanes_; ++l)
+            CUDA_TRY(cudaMemcpy2DAsync(dst.p[l], dstride, e.frames[l], e.stride, tight, h, cudaMemcpyDeviceToDevice, stream_));
+    } else {
+        PtrPack src;
+        for (int l = 0; l < n_lanes_; ++l) src.p[l] = e.frames[l];
+        WarpGeom g{};
+        g.src_w = W_; g.src_h = H_; g.src_stride = e.stride;
+        g.mode = mode; g.border = b; g.border_mode = border_mode_;
+        g.out_w = w; g.out_h = h; g.out_stride = dstride;
+        int m2 = mode;
+        if (mode == 2 && (W_ - 2 * b <= 0 || H_ - 2 * b <= 0)) m2 = 0;                // border larger than image
+        g.mode = m2;
+        std::vector<uint8_t*> scratch(n_lanes_);
+        for (int l = 0; l < n_lanes_; ++l) scratch[l] = d_scratch_ ? d_scratch_ + frame_bytes_ * l : nullptr;
+        launch_warp(d_lanes_, n_lanes_, src, dst, g, scratch.data(), stream_);
+        launches_ += (m2 == 2) ? 1 + n_lanes_ : 1;
+    }
+    if (host_io) {
+        for (int l = 0; l < n_lanes_; ++l)
+            CUDA_TRY(cudaMemcpy2DAsync(outs[l], out_stride, dst.p[l], dstride, tight, h, cudaMemcpyDeviceToHost, stream_));
+        CUDA_TRY(cudaStreamSynchronize(stream_));
+    }
+    ++n_out_;
+    return VS_OK;
+}
+
+// Stabilizer::stabilize, Stabilizer.cpp:258-392
+vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride, uint8_t* const* outs, size_t out_stride,
+                       size_t out_capacity, unsigned flags, bool host_io, int* ow, int* oh, int* produced) {
+    *produced = 0;
+    if (!frames || w <= 0 || h <= 0) return VS_OK;                                    // frame.empty() -> empty Mat (:263)
+    if (w < 4 || h < 4) return vs_set_error(VS_ERR_INVALID_ARG, "frame too small");
+    if (stride == 0) stride = (size_t)w * 3;
+    if (stride < (size_t)w * 3) return vs_set_error(VS_ERR_INVALID_ARG, "stride smaller than a row");
+    CUDA_TRY(cudaSetDevice(device_));
+    const bool borrow = !host_io && (flags & VS_PUSH_BORROW);
+    VS_TRY(ensure_geometry(w, h, !borrow, false, false));
+
+    QueueEntry e;
+    e.index = next_index_;
+    e.slot = next_index_ % ring_slots_;
+    e.frames.resize(n_lanes_);
+    if (borrow) {
+        for (int l = 0; l < n_lanes_; ++l) e.frames[l] = frames[l];
+        e.stride = stride;
+    } else {
+        const size_t tight = (size_t)w * 3;
+        for (int l = 0; l < n_lanes_; ++l) {
+            uint8_t* dst = d_ring_ + ((size_t)l * ring_slots_ + e.slot) * frame_bytes_;
+            CUDA_TRY(cudaMemcpy2DAsync(dst, tight, frames[l], stride, tight, h,
+                                       host_io ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream_));
+            e.frames[l] = dst;
+        }
+        e.stride = tight;
+    }
+
+    if (first_) {
+        // first frame: 480x270 analysis image + GFTT with the user's parameters (:271-368)
+        PtrPack src;
+        for (int l = 0; l < n_lanes_; ++l) src.p[l] = e.frames[l];
+        launch_gray_resize(d_lanes_, n_lanes_, src, w, h, e.stride, -1, stream_);     // :304-305
+        CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, stream_));
+        launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, stream_);  // :355-357
+        launches_ += 4;
+        queue_.push_back(e);
+        first_ = false;
+        next_index_ = 1;
+        if (host_io) CUDA_TRY(cudaStreamSynchronize(stream_));
+        return VS_OK;
+    }
+    queue_.push_back(e);
+    bool will_pop = false;
+    VS_TRY(generate_transform(e, &will_pop));
+    if (will_pop) {
+        VS_TRY(emit(outs, out_stride, out_capacity, host_io, ow, oh));
+        *produced = 1;
+    } else if (host_io) {
+        CUDA_TRY(cudaStreamSynchronize(stream_));     // the caller may reuse its frame buffer
+    }
+    ++next_index_;
+    return VS_OK;
+}
+
+// Stabilizer::flush, Stabilizer.cpp:394-400
+vs_status Engine::flush(uint8_t* const* outs, size_t out_stride, size_t out_capacity, bool host_io, int* ow, int* oh,
+                        int* produced) {
+    *produced = 0;
+    if (queue_.empty()) return VS_OK;
+    CUDA_TRY(cudaSetDevice(device_));
+    launch_smooth_only(d_lanes_, n_lanes_, step_info(queue_.front().index), stream_);
+    launches_ += 1;
+    VS_TRY(emit(outs, out_stride, out_capacity, host_io, ow, oh));
+    *produced = 1;
+    return VS_OK;
+}
+
+vs_status Engine::reset_detect_counters() {
+    CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, stream_));
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------------------ diagnostics
+vs_status Engine::frame_record(int lane, int i, vs_frame_record* r) {
+    if (lane < 0 || lane >= n_lanes_ || i < 0 || i >= n_frames_ || !r) return vs_set_error(VS_ERR_INVALID_ARG, "bad record index");
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    CUDA_TRY(cudaMemcpy(r, h_lanes_[lane].frec + i, sizeof(*r), cudaMemcpyDeviceToHost));
+    return VS_OK;
+}
+vs_status Engine::output_record(int lane, int i, vs_output_record* r) {
+    if (lane < 0 || lane >= n_lanes_ || i < 0 || i >= n_out_ || !r) return vs_set_error(VS_ERR_INVALID_ARG, "bad record index");
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    CUDA_TRY(cudaMemcpy(r, h_lanes_[lane].orec + i, sizeof(*r), cudaMemcpyDeviceToHost));
+    return VS_OK;
+}
+vs_status Engine::frame_points(int lane, int i, float* prev, float* next, uint8_t* status, uint8_t* mask, float* det) {
+    if (lane < 0 || lane >= n_lanes_ || i < 0 || i >= n_frames_) return vs_set_error(VS_ERR_INVALID_ARG, "bad record index");
+    if (i < n_frames_ - log_depth_) return vs_set_error(VS_ERR_INVALID_ARG, "point log of that frame has been recycled");
+    vs_frame_record r;
+    VS_TRY(frame_record(lane, i, &r));
+    const LaneDev& L = h_lanes_[lane];
+    size_t o = (size_t)(i % log_depth_) * kp_cap_;
+    if (prev && r.n_prev_pts > 0) CUDA_TRY(cudaMemcpy(prev, L.log_prev + o, sizeof(float2) * r.n_prev_pts, cudaMemcpyDeviceToHost));
+    if (next && r.n_prev_pts > 0) CUDA_TRY(cudaMemcpy(next, L.log_next + o, sizeof(float2) * r.n_prev_pts, cudaMemcpyDeviceToHost));
+    if (status && r.n_prev_pts > 0) CUDA_TRY(cudaMemcpy(status, L.log_status + o, r.n_prev_pts, cudaMemcpyDeviceToHost));
+    if (mask && r.n_tracked > 0 && r.n_inliers >= 0) CUDA_TRY(cudaMemcpy(mask, L.log_mask + o, r.n_tracked, cudaMemcpyDeviceToHost));
+    if (det && r.n_detected > 0) CUDA_TRY(cudaMemcpy(det, L.log_detected + o, sizeof(float2) * r.n_detected, cudaMemcpyDeviceToHost));
+    return VS_OK;
+}
+vs_status Engine::first_corners(int lane, float* xy, int cap, int* n) {
+    if (lane < 0 || lane >= n_lanes_ || !n) return vs_set_error(VS_ERR_INVALID_ARG, "bad lane");
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    int c = 0;
+    CUDA_TRY(cudaMemcpy(&c, h_lanes_[lane].first_count, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = c;
+    if (xy && c > 0) CUDA_TRY(cudaMemcpy(xy, h_lanes_[lane].first_corners, sizeof(float2) * (c < cap ? c : cap), cudaMemcpyDeviceToHost));
+    return VS_OK;
+}

@@ -1,0 +1,86 @@
+// engine.h — host side of the stabilizer: the reference's stabilize()/flush()/clean() control flow
+// (Stabilizer.cpp:258-400) re-expressed as an asynchronous launch sequence on one CUDA stream.
+// One Engine advances n_lanes independent streams in lock-step (n_lanes == 1 is vs::Stabilizer).
+#pragma once
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+struct QueueEntry {
+    int index;                               // frameIndexQueue_
+    int slot;                                // ring slot (copy mode)
+    std::vector<const uint8_t*> frames;      // per-lane device pointer of the queued frame
+    size_t stride;
+};
+
+class Engine {
+public:
+    static vs_status create(const vs_params& p, int device, int n_lanes, Engine** out);
+    ~Engine();
+
+    // frames/outs: n_lanes pointers.  host_io: pointers are host memory (copies + sync inside).
+    vs_status push(const uint8_t* const* frames, int w, int h, size_t stride, uint8_t* const* outs, size_t out_stride,
+                   size_t out_capacity, unsigned flags, bool host_io, int* ow, int* oh, int* produced);
+    vs_status flush(uint8_t* const* outs, size_t out_stride, size_t out_capacity, bool host_io, int* ow, int* oh,
+                    int* produced);
+    vs_status clean();
+    vs_status sync();
+
+    cudaStream_t stream() const { return stream_; }
+    uint64_t launches() const { return launches_; }
+    int n_lanes() const { return n_lanes_; }
+    int n_frame_records() const { return n_frames_; }
+    int n_output_records() const { return n_out_; }
+    vs_status frame_record(int lane, int i, vs_frame_record* r);
+    vs_status output_record(int lane, int i, vs_output_record* r);
+    vs_status frame_points(int lane, int i, float* prev, float* next, uint8_t* status, uint8_t* mask, float* det);
+    vs_status first_corners(int lane, float* xy, int cap, int* n);
+
+    // single-op helpers behind the vs_k_* entry points (lane 0 scratch)
+    const LaneDev* d_lanes() const { return d_lanes_; }
+    const LaneDev& h_lane(int i) const { return h_lanes_[i]; }
+    vs_status reset_detect_counters();
+    int kp_capacity() const { return kp_cap_; }
+
+private:
+    Engine() = default;
+    vs_status init(const vs_params& p, int device, int n_lanes);
+    vs_status alloc_fixed();
+    vs_status ensure_geometry(int w, int h, bool need_ring, bool need_out, bool need_scratch);
+    vs_status grow_trajectory();
+    vs_status generate_transform(const QueueEntry& e, bool* will_pop);
+    vs_status emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, bool host_io, int* ow, int* oh);
+    StepInfo step_info(int pop_index) const;
+    void free_all();
+
+    vs_params p_{};
+    int device_ = 0, n_lanes_ = 0;
+    cudaStream_t stream_ = nullptr;
+    int border_mode_ = 0, method_ = 0;
+    int smoothing_radius_ = 30;
+
+    // state mirrored from the reference
+    bool first_ = true;
+    int next_index_ = 0;
+    int n_frames_ = 0;        // transforms_.size()
+    int n_out_ = 0;
+    int detect_counter_ = 0;  // per instance (the reference's is a process-global static)
+    std::deque<QueueEntry> queue_;
+    int W_ = 0, H_ = 0;
+
+    // device memory
+    std::vector<void*> allocs_;
+    std::vector<LaneDev> h_lanes_;
+    LaneDev* d_lanes_ = nullptr;
+    unsigned int* d_detect_counters_ = nullptr;   // [lane][2] = eig_max, cand_count
+    int kp_cap_ = 0, cap_first_ = 0, cap_redetect_ = 0, log_depth_ = 0, traj_cap_ = 0;
+    int ring_slots_ = 0;
+    size_t frame_bytes_ = 0, out_bytes_ = 0;
+    uint8_t* d_ring_ = nullptr;       // [lane][slot][frame]
+    uint8_t* d_out_ = nullptr;        // [lane][out frame]  (host-io staging)
+    uint8_t* d_scratch_ = nullptr;    // [lane][frame]      (crop+zoom first pass)
+    std::vector<float*> traj_bufs_;
+    uint64_t launches_ = 0;
+};

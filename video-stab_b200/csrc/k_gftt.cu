@@ -1,0 +1,309 @@
+// k_gftt.cu — Shi-Tomasi corner detection ("good features to track").
+// Replaces cv::goodFeaturesToTrack(gray, maxCorners, quality, minDistance, noArray, blockSize=3)
+// at Stabilizer.cpp:355-357 (first frame, user parameters) and :740-744 (every 2nd frame,
+// hard-coded 200 / 0.02 / 15.0 / 3).
+// Specification: oracle/cv_models.py min_eigen_map + gftt (ordered corner list bit-exact vs cv2 4.13
+// on its baseline code path).  Three kernels:
+//   k_min_eig   Sobel -> products -> 3x3 box -> min eigenvalue, shared-memory tiled, + global max
+//   k_candidates threshold + 3x3 non-max suppression, warp-ballot compaction into 64-bit sort keys
+//   k_select    per lane: radix-select of the strongest chunk, shared-memory bitonic sort, and the
+//               order-dependent min-distance greedy pass done 32 candidates at a time by one warp
+// The float map must match OpenCV's op order exactly (no FMA contraction: explicit _rn intrinsics).
+#include "kernels.h"
+
+#define EIG_TW 64
+#define EIG_TH 16
+#define SEL_THREADS 1024
+#define SEL_CHUNK_MAX 8192
+#define SEL_CHUNK_FIRST 1024
+
+static __device__ __forceinline__ GrayLevel gftt_src(const LaneDev& L, int slot) {
+    return slot < 0 ? L.small0 : L.pyr[slot].lv[0];
+}
+
+// ------------------------------------------------------------------------------------ k_min_eig
+__global__ void __launch_bounds__(256) k_min_eig(const LaneDev* __restrict__ lanes, int slot) {
+    __shared__ float sxx[EIG_TH + 2][EIG_TW + 2];
+    __shared__ float sxy[EIG_TH + 2][EIG_TW + 2];
+    __shared__ float syy[EIG_TH + 2][EIG_TW + 2];
+    __shared__ unsigned int smax;
+    const LaneDev& L = lanes[blockIdx.z];
+    const GrayLevel G = gftt_src(L, slot);
+    const int x0 = blockIdx.x * EIG_TW, y0 = blockIdx.y * EIG_TH;
+    const float f1 = (float)(1.0 / (4.0 * 3.0 * 255.0));
+    const float f0 = 2.f * f1;
+    if (threadIdx.x == 0) smax = 0u;
+
+    // products at the tile + 1 halo; the box filter's BORDER_REFLECT_101 acts on the PRODUCT maps,
+    // so a halo position outside the image takes the product computed AT its reflected coordinate
+    for (int i = threadIdx.x; i < (EIG_TH + 2) * (EIG_TW + 2); i += 256) {
+        int r = i / (EIG_TW + 2), c = i - r * (EIG_TW + 2);
+        int gx = min(max(reflect101(x0 - 1 + c, G.w), 0), G.w - 1);
+        int gy = min(max(reflect101(y0 - 1 + r, G.h), 0), G.h - 1);
+        const uint8_t* p = G.base + (ptrdiff_t)gy * G.pitch + gx;
+        const uint8_t* pu = p - G.pitch;
+        const uint8_t* pd = p + G.pitch;
+        float a00 = pu[-1], a01 = pu[0], a02 = pu[1];
+        float a10 = p[-1], a11 = p[0], a12 = p[1];
+        float a20 = pd[-1], a21 = pd[0], a22 = pd[1];
+        // Dx: row pass [-1 0 1] (exact), column pass [1 2 1]*scale as (S0+S2)*f1 + S1*f0
+        float r0 = a02 - a00, r1 = a12 - a10, r2 = a22 - a20;
+        float dx = __fadd_rn(__fmul_rn(__fadd_rn(r0, r2), f1), __fmul_rn(r1, f0));
+        // Dy: row pass [1 2 1]*scale left-to-right, column pass [-1 0 1] (exact difference of floats)
+        float t0 = __fadd_rn(__fadd_rn(__fmul_rn(a00, f1), __fmul_rn(a01, f0)), __fmul_rn(a02, f1));
+        float t2 = __fadd_rn(__fadd_rn(__fmul_rn(a20, f1), __fmul_rn(a21, f0)), __fmul_rn(a22, f1));
+        float dy = __fsub_rn(t2, t0);
+        sxx[r][c] = __fmul_rn(dx, dx);
+        sxy[r][c] = __fmul_rn(dx, dy);
+        syy[r][c] = __fmul_rn(dy, dy);
+    }
+    __syncthreads();
+    unsigned int lmax = 0u;
+    for (int i = threadIdx.x; i < EIG_TH * EIG_TW; i += 256) {
+        int r = i / EIG_TW, c = i - r * EIG_TW;
+        int x = x0 + c, y = y0 + r;
+        if (x >= G.w || y >= G.h) continue;
+        double bxx = 0, bxy = 0, byy = 0;        // OpenCV's box filter sums float in double: exact here
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                bxx += (double)sxx[r + dy][c + dx];
+                bxy += (double)sxy[r + dy][c + dx];
+                byy += (double)syy[r + dy][c + dx];
+            }
+        float a = __fmul_rn((float)bxx, 0.5f), b = (float)bxy, cc = __fmul_rn((float)byy, 0.5f);
+        float d = __fsub_rn(a, cc);
+        float e = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+        L.eig[(size_t)y * G.w + x] = e;
+        if (e > 0.f) lmax = max(lmax, __float_as_uint(e));
+    }
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+    if ((threadIdx.x & 31) == 0 && lmax) atomicMax(&smax, lmax);
+    __syncthreads();
+    if (threadIdx.x == 0 && smax) atomicMax(L.eig_max, smax);
+}
+
+// --------------------------------------------------------------------------------- k_candidates
+__global__ void __launch_bounds__(256) k_candidates(const LaneDev* __restrict__ lanes, int slot, double quality) {
+    const LaneDev& L = lanes[blockIdx.z];
+    const GrayLevel G = gftt_src(L, slot);
+    const int w = G.w, h = G.h;
+    int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const float mx = __uint_as_float(*L.eig_max);
+    const float thr = (float)((double)mx * quality);
+    bool is = false;
+    float e = 0.f;
+    if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
+        const float* p = L.eig + (size_t)y * w + x;
+        e = p[0];
+        if (e > thr) {
+            is = e >= p[-1] && e >= p[1] && e >= p[-w - 1] && e >= p[-w] && e >= p[-w + 1] &&
+                 e >= p[w - 1] && e >= p[w] && e >= p[w + 1];
+        }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, is);
+    if (m) {
+        int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+        if (lane == leader) base = atomicAdd(L.cand_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (is) {
+            int pos = base + __popc(m & ((1u << lane) - 1u));
+            L.cand[pos] = ((unsigned long long)__float_as_uint(e) << 32) | (unsigned)(y * w + x);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------- k_select
+struct SelSmem {
+    unsigned int hist[256];
+    unsigned long long prefix, mask, T;
+    int k, count, accepted, done;
+};
+
+// K-th largest key strictly below U (keys are unique): MSD radix select, 8 bits per pass
+static __device__ unsigned long long radix_select(const unsigned long long* __restrict__ keys, int n,
+                                                  unsigned long long U, int K, SelSmem& S) {
+    if (threadIdx.x == 0) { S.prefix = 0ull; S.mask = 0ull; S.k = K; }
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) S.hist[threadIdx.x] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = S.prefix, mask = S.mask;
+        for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
+            unsigned long long k = keys[i];
+            if (k < U && (k & mask) == prefix) atomicAdd(&S.hist[(unsigned)(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int k = S.k, c = 0, d = 255;
+            for (; d > 0; --d) {
+                int hcount = (int)S.hist[d];
+                if (c + hcount >= k) break;
+                c += hcount;
+            }
+            S.k = k - c;
+            S.prefix = prefix | ((unsigned long long)d << shift);
+            S.mask = mask | (0xffull << shift);
+        }
+        __syncthreads();
+    }
+    return S.prefix;
+}
+
+static __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long x = a[i], y = a[ixj];
+                    bool desc = (i & k) == 0;
+                    if (desc ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restrict__ lanes, int slot, int max_corners,
+                                                         double min_dist, int record_frame_no) {
+    extern __shared__ unsigned long long skeys[];      // SEL_CHUNK_MAX
+    __shared__ SelSmem S;
+    const LaneDev& L = lanes[blockIdx.z];
+    const GrayLevel G = gftt_src(L, slot);
+    const int w = G.w, h = G.h;
+    const int N = min(*L.cand_count, w * h);
+    const int cap = (max_corners > 0) ? min(max_corners, L.kp_capacity) : L.kp_capacity;
+    const bool use_grid = min_dist >= 1.0;
+    const int cell = use_grid ? (int)rint(min_dist) : 1;
+    const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+    const double md2 = min_dist * min_dist;
+    unsigned int* gcount = L.grid;
+    unsigned int* gslot = L.grid + (size_t)gw * gh;
+    if (use_grid)
+        for (int i = threadIdx.x; i < gw * gh; i += SEL_THREADS) gcount[i] = 0u;
+    if (threadIdx.x == 0) { S.accepted = 0; S.done = 0; }
+    __syncthreads();
+
+    unsigned long long U = ~0ull;
+    int remaining = N;
+    bool first = true;
+    while (remaining > 0) {
+        int m;
+        unsigned long long T;
+        if (remaining <= SEL_CHUNK_MAX) { m = remaining; T = 0ull; }
+        else {
+            m = first ? SEL_CHUNK_FIRST : SEL_CHUNK_MAX;
+            T = radix_select(L.cand, N, U, m, S);
+        }
+        first = false;
+        int npad = 32;
+        while (npad < m) npad <<= 1;
+        if (threadIdx.x == 0) S.count = 0;
+        for (int i = threadIdx.x; i < npad; i += SEL_THREADS) skeys[i] = 0ull;
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += SEL_THREADS) {
+            unsigned long long k = L.cand[i];
+            if (k < U && k >= T) skeys[atomicAdd(&S.count, 1)] = k;
+        }
+        __syncthreads();
+        bitonic_sort_desc(skeys, npad);
+
+        // ---- ordered min-distance greedy pass, one warp, 32 candidates per step
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            int accepted = S.accepted;
+            bool stop = false;
+            for (int base = 0; base < m && !stop; base += 32) {
+                bool ok = base + lane < m;
+                unsigned addr = ok ? (unsigned)(skeys[base + lane] & 0xffffffffull) : 0u;
+                int y = addr / w, x = addr - y * w;
+                if (ok && use_grid) {
+                    int cx = x / cell, cy = y / cell;
+                    int xa = max(cx - 1, 0), xb = min(cx + 1, gw - 1), ya = max(cy - 1, 0), yb = min(cy + 1, gh - 1);
+                    for (int yy = ya; yy <= yb && ok; ++yy)
+                        for (int xx = xa; xx <= xb && ok; ++xx) {
+                            int ci = yy * gw + xx;
+                            unsigned cnt = __ldcg(&gcount[ci]);
+                            for (unsigned s = 0; s < cnt; ++s) {
+                                unsigned q = __ldcg(&gslot[(size_t)ci * VS_GRID_SLOTS + s]);
+                                int dx = x - (int)(q & 0xffffu), dy = y - (int)(q >> 16);
+                                if ((double)(dx * dx + dy * dy) < md2) { ok = false; break; }
+                            }
+                        }
+                }
+                unsigned pending = __ballot_sync(0xffffffffu, ok);
+                while (pending) {
+                    int leader = __ffs(pending) - 1;
+                    int lx = __shfl_sync(0xffffffffu, x, leader), ly = __shfl_sync(0xffffffffu, y, leader);
+                    if (lane == leader) {
+                        L.kp[accepted] = make_float2((float)lx, (float)ly);
+                        if (use_grid) {
+                            int ci = (ly / cell) * gw + (lx / cell);
+                            unsigned c = __ldcg(&gcount[ci]);
+                            if (c < VS_GRID_SLOTS) {
+                                __stcg(&gslot[(size_t)ci * VS_GRID_SLOTS + c], (unsigned)lx | ((unsigned)ly << 16));
+                                __stcg(&gcount[ci], c + 1);
+                            }
+                        }
+                        ok = false;
+                    }
+                    ++accepted;
+                    if (accepted >= cap) { stop = true; break; }
+                    if (ok && use_grid) {
+                        int dx = x - lx, dy = y - ly;
+                        if ((double)(dx * dx + dy * dy) < md2) ok = false;
+                    }
+                    pending = __ballot_sync(0xffffffffu, ok);
+                }
+                __threadfence_block();
+                __syncwarp();
+            }
+            if (lane == 0) { S.accepted = accepted; S.done = stop ? 1 : 0; }
+        }
+        __syncthreads();
+        if (S.done) break;
+        U = T;
+        remaining -= m;
+    }
+    __syncthreads();
+    const int n = S.accepted;
+    if (threadIdx.x == 0) *L.kp_count = n;
+    if (slot < 0) {
+        for (int i = threadIdx.x; i < n; i += SEL_THREADS) L.first_corners[i] = L.kp[i];
+        if (threadIdx.x == 0) *L.first_count = n;
+    }
+    if (record_frame_no > 0) {
+        if (threadIdx.x == 0 && record_frame_no <= L.record_capacity) L.frec[record_frame_no - 1].n_detected = n;
+        if (L.log_depth > 0) {
+            float2* dst = L.log_detected + (size_t)((record_frame_no - 1) % L.log_depth) * L.kp_capacity;
+            for (int i = threadIdx.x; i < n; i += SEL_THREADS) dst[i] = L.kp[i];
+        }
+    }
+}
+
+size_t gftt_grid_words(int w, int h, double min_dist) {
+    if (min_dist < 1.0) return 8;
+    int cell = (int)rint(min_dist);
+    size_t cells = (size_t)((w + cell - 1) / cell) * ((h + cell - 1) / cell);
+    return cells * (1 + VS_GRID_SLOTS);
+}
+
+void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_corners, double quality,
+                          double min_dist, int record_frame_no, cudaStream_t st) {
+    const int w = slot < 0 ? VS_FW : VS_AW, h = slot < 0 ? VS_FH : VS_AH;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SEL_CHUNK_MAX * (int)sizeof(unsigned long long));
+        attr_set = true;
+    }
+    dim3 g1((w + EIG_TW - 1) / EIG_TW, (h + EIG_TH - 1) / EIG_TH, n_lanes);
+    k_min_eig<<<g1, 256, 0, st>>>(lanes, slot);
+    dim3 g2((w + 63) / 64, (h + 3) / 4, n_lanes);
+    k_candidates<<<g2, 256, 0, st>>>(lanes, slot, quality);
+    k_select<<<dim3(1, 1, n_lanes), SEL_THREADS, SEL_CHUNK_MAX * sizeof(unsigned long long), st>>>(
+        lanes, slot, max_corners, min_dist, record_frame_no);
+}

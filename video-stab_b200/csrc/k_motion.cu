@@ -1,0 +1,474 @@
+// k_motion.cu — everything between the tracker and the warp, fused into one launch per step:
+//   status filter (Stabilizer.cpp:629-641)  ->  cv::estimateAffinePartial2D RANSAC 5.0/500/0.99 + refine
+//   (:645-659)  ->  dx,dy,da decomposition (:660-662)  ->  trajectory accumulation (:681-688)  ->
+//   path smoothing box|gaussian|kalman (:797-823, :1139-1172, :1364-1458, :1637-1673)  ->  motion intent
+//   (:854-888, :1676-1780)  ->  2x3 matrix (:890-908) and cv::warpAffine's matrix inversion.
+// One CTA of 32 warps per lane.  RANSAC is batched: 32 hypotheses are scored in parallel, one warp per
+// hypothesis with ballot/popc inlier counting, then the reference's *sequential* adaptive-termination
+// rule is replayed over the scores so the same hypothesis wins as on the CPU.
+// Specification: oracle/cv_models.py estimate_affine_partial_2d + oracle/stabilizer_ref.py.
+#include "kernels.h"
+
+#define MO_THREADS 1024
+#define MO_MAXP 2048                 // key-point capacity handled in shared memory
+#define MO_BATCH 32                  // hypotheses per round
+
+struct MoSmem {
+    float2 from[MO_MAXP];
+    float2 to[MO_MAXP];
+    int warp_tot[MO_THREADS / 32];
+    int idx[MO_BATCH][2];
+    int good[MO_BATCH];
+    double model[6];
+    float bestF[6];
+    double red[7][32];
+    unsigned long long rng;
+    int n, niters, iter, max_good, best_found, cont;
+    float gk[512];                   // gaussian kernel taps
+};
+
+static __device__ __forceinline__ unsigned rng_next(unsigned long long& s) {
+    s = (unsigned long long)(unsigned)s * 4164903690ull + (unsigned)(s >> 32);
+    return (unsigned)s;
+}
+
+static __device__ void model_from_pair(float2 a1, float2 a2, float2 b1, float2 b2, double* M) {
+    // AffinePartial2DEstimatorCallback::runKernel — exact 2-point similarity in double
+    double x1 = a1.x, y1 = a1.y, x2 = a2.x, y2 = a2.y;
+    double X1 = b1.x, Y1 = b1.y, X2 = b2.x, Y2 = b2.y;
+    double d = 1. / ((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
+    double S0 = d * ((X1 - X2) * (x1 - x2) + (Y1 - Y2) * (y1 - y2));
+    double S1 = d * ((Y1 - Y2) * (x1 - x2) - (X1 - X2) * (y1 - y2));
+    double S2 = d * ((Y1 - Y2) * (x1 * y2 - x2 * y1) - (X1 * y2 - X2 * y1) * (y1 - y2) - (X1 * x2 - X2 * x1) * (x1 - x2));
+    double S3 = d * (-(X1 - X2) * (x1 * y2 - x2 * y1) - (Y1 * x2 - Y2 * x1) * (x1 - x2) - (Y1 * y2 - Y2 * y1) * (y1 - y2));
+    M[0] = S0; M[1] = -S1; M[2] = S2; M[3] = S1; M[4] = S0; M[5] = S3;
+}
+
+static __device__ __forceinline__ bool is_inlier(const float* F, float2 f, float2 t) {
+    // Affine2DEstimatorCallback::computeError in float32 (no contraction), threshold 5^2
+    float a = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(F[0], f.x), __fmul_rn(F[1], f.y)), F[2]), t.x);
+    float b = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(F[3], f.x), __fmul_rn(F[4], f.y)), F[5]), t.y);
+    float e = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+    return e <= 25.0f;
+}
+
+static __device__ int ransac_update_iters(double p, double ep, int max_iters) {
+    // cv::RANSACUpdateNumIters(confidence, outlier ratio, modelPoints = 2, maxIters)
+    p = fmax(p, 0.); p = fmin(p, 1.);
+    ep = fmax(ep, 0.); ep = fmin(ep, 1.);
+    double num = fmax(1. - p, 2.2250738585072014e-308);
+    double denom = 1. - (1. - ep) * (1. - ep);
+    if (denom < 2.2250738585072014e-308) return 0;
+    num = log(num);
+    denom = log(denom);
+    return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
+}
+
+// ---- scalar float32 helpers restating the reference's host arithmetic (one thread) -----------------
+static __device__ float f_sqrt(float x) { return __fsqrt_rn(x); }
+static __device__ float f_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
+
+static __device__ int adaptive_radius(const float* path, int n, int smoothing_radius) {
+    // calculateAdaptiveRadius, Stabilizer.cpp:1637-1673
+    if (n < 10) return smoothing_radius;
+    int start = max(0, n - 20);
+    float cnt = (float)(n - start);
+    float mx = 0.f, my = 0.f, ma = 0.f;
+    for (int i = start; i < n; ++i) {
+        mx = __fadd_rn(mx, path[3 * i]); my = __fadd_rn(my, path[3 * i + 1]); ma = __fadd_rn(ma, path[3 * i + 2]);
+    }
+    mx = __fdiv_rn(mx, cnt); my = __fdiv_rn(my, cnt); ma = __fdiv_rn(ma, cnt);
+    float vx = 0.f, vy = 0.f, va = 0.f;
+    for (int i = start; i < n; ++i) {
+        float dx = __fsub_rn(path[3 * i], mx), dy = __fsub_rn(path[3 * i + 1], my), da = __fsub_rn(path[3 * i + 2], ma);
+        vx = __fadd_rn(vx, __fmul_rn(dx, dx)); vy = __fadd_rn(vy, __fmul_rn(dy, dy)); va = __fadd_rn(va, __fmul_rn(da, da));
+    }
+    vx = __fdiv_rn(vx, cnt); vy = __fdiv_rn(vy, cnt); va = __fdiv_rn(va, cnt);
+    float total = f_sqrt(__fadd_rn(__fadd_rn(vx, vy), __fmul_rn(va, 1000.f)));
+    return (int)fmaxf(5.0f, fminf(25.0f, __fmul_rn(total, 2.0f)));
+}
+
+static __device__ float box_at(const float* path, int comp, int n, int radius, int i) {
+    // boxFilterConvolve (normal mode), Stabilizer.cpp:1139-1172 — only element i is ever consumed
+    int r = max(2, min(radius, 8));
+    if (n <= r) return path[3 * i + comp];
+    int lo = max(0, i - r), hi = min(n - 1, i + r);
+    float s = 0.f;
+    for (int j = lo; j <= hi; ++j) s = __fadd_rn(s, path[3 * j + comp]);
+    return __fdiv_rn(s, (float)(hi - lo + 1));
+}
+
+static __device__ float variance_f(const float* v, int n) {
+    if (n == 0) return 0.f;
+    float m = 0.f;
+    for (int i = 0; i < n; ++i) m = __fadd_rn(m, v[i]);
+    m = __fdiv_rn(m, (float)n);
+    float var = 0.f;
+    for (int i = 0; i < n; ++i) { float d = __fsub_rn(v[i], m); var = __fadd_rn(var, __fmul_rn(d, d)); }
+    return __fdiv_rn(var, (float)n);
+}
+static __device__ float consistency_f(const float* v, int n) {
+    if (n < 2) return 0.f;
+    float var = variance_f(v, n);
+    float m = 0.f;
+    for (int i = 0; i < n; ++i) m = __fadd_rn(m, v[i]);
+    m = __fdiv_rn(m, (float)n);
+    if (m == 0.f) return 0.f;
+    float c = __fdiv_rn(1.f, __fadd_rn(1.f, __fdiv_rn(var, __fmul_rn(m, m))));
+    return fmaxf(0.f, fminf(1.f, c));
+}
+
+static __device__ int motion_intent(const float* tr, int n_tr, const float* motion, int idx) {
+    // analyzeMotionIntent, Stabilizer.cpp:1676-1719
+    float mag = f_sqrt(__fadd_rn(__fmul_rn(motion[0], motion[0]), __fmul_rn(motion[1], motion[1])));
+    float ang = (float)((double)__fmul_rn(fabsf(motion[2]), 180.0f) / 3.14159265358979323846 * (double)30.0f);
+    if (n_tr >= 15) {
+        float mags[15], dirs[15];
+        int c = 0;
+        for (int i = max(0, idx - 15); i < idx; ++i) {
+            if (i < n_tr) {
+                float tx = tr[3 * i], ty = tr[3 * i + 1];
+                mags[c] = f_sqrt(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)));
+                dirs[c] = f_atan2(ty, tx);
+                ++c;
+            }
+        }
+        if (c) {
+            float dv = variance_f(dirs, c), mc = consistency_f(mags, c);
+            if (dv < 0.5f && mc > 0.7f && mag > 5.0f) return 1;
+            if (mag < 3.0f && mc < 0.3f && ang > 10.0f) return 2;
+            if (mag > 3.0f && mag < 15.0f && dv > 0.5f) return 3;
+        }
+    }
+    return 0;
+}
+
+// cv::warpAffine's inversion of the float32 matrix promoted to double (imgwarp.cpp)
+static __host__ __device__ void invert_affine(const float* T, double* m) {
+    double M[6];
+    for (int i = 0; i < 6; ++i) M[i] = (double)T[i];
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0. ? 1. / D : 0.;
+    double A11 = M[4] * D, A22 = M[0] * D;
+    M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+    double b1 = -M[0] * M[2] - M[1] * M[5];
+    double b2 = -M[3] * M[2] - M[4] * M[5];
+    M[2] = b1; M[5] = b2;
+    for (int i = 0; i < 6; ++i) m[i] = M[i];
+}
+void warp_params_from_T(const float* T, WarpParams* wp) {
+    invert_affine(T, wp->m);
+    for (int i = 0; i < 6; ++i) wp->T[i] = T[i];
+    wp->passthrough = 0;
+    wp->pad = 0;
+}
+
+// Smoothing + intent + matrix for the frame being emitted.  Runs on one thread (sequential float32
+// arithmetic in the reference's order); S.gk is scratch for the gaussian taps.
+static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, float* gk) {
+    const int i = info.pop_index, n = info.path_len_at_pop;
+    vs_output_record rec;
+    rec.index = i; rec.passthrough = 0; rec.path_len = n; rec.radius = 0; rec.intent = 0;
+    for (int k = 0; k < 3; ++k) rec.smoothed[k] = 0.f;
+    for (int k = 0; k < 6; ++k) rec.T[k] = 0.f;
+    WarpParams wp;
+    if (i >= n) {                                           // Stabilizer.cpp:774-780
+        rec.passthrough = 1;
+        wp.passthrough = 1; wp.pad = 0;
+        for (int k = 0; k < 6; ++k) { wp.m[k] = (k == 0 || k == 4) ? 1. : 0.; wp.T[k] = (k == 0 || k == 4) ? 1.f : 0.f; }
+        *L.wp = wp;
+        if (info.n_out < L.record_capacity) L.orec[info.n_out] = rec;
+        return;
+    }
+    const float* path = L.path;
+    float sm[3];
+    bool have = false;
+    if (info.method == 1) {                                 // gaussianFilterConvolve :1364-1413
+        float sigma = info.gaussian_sigma;
+        int ksz = max(3, (int)ceilf(__fmul_rn(6.f, sigma)));
+        if ((ksz & 1) == 0) ++ksz;
+        int c = ksz / 2;
+        if (n > c && ksz <= 512) {
+            float tot = 0.f;
+            for (int j = 0; j < ksz; ++j) {
+                float x = (float)(j - c);
+                float arg = __fdiv_rn(-__fmul_rn(x, x), __fmul_rn(__fmul_rn(2.f, sigma), sigma));
+                float kv = (float)exp((double)arg);
+                gk[j] = kv;
+                tot = __fadd_rn(tot, kv);
+            }
+            for (int j = 0; j < ksz; ++j) gk[j] = __fdiv_rn(gk[j], tot);
+            for (int comp = 0; comp < 3; ++comp) {
+                float s = 0.f;
+                for (int j = 0; j < ksz; ++j) {
+                    int q = i + j;                          // index into the padded array
+                    float v;
+                    if (q < c) v = path[3 * (c - q) + comp];
+                    else if (q < c + n) v = path[3 * (q - c) + comp];
+                    else v = path[3 * (n - 1 - (q - c - n)) + comp];
+                    s = __fadd_rn(s, __fmul_rn(v, gk[j]));
+                }
+                sm[comp] = s;
+            }
+            have = true;
+        }
+    } else if (info.method == 2) {                          // kalmanFilterSmooth :1416-1458, incremental
+        for (int comp = 0; comp < 3; ++comp) {
+            float* ks = L.kalman + 6 * comp;                // x0 x1 P00 P01 P10 P11
+            float z = path[3 * i + comp];
+            if (i == 0) {
+                ks[0] = z; ks[1] = 0.f; ks[2] = ks[3] = ks[4] = ks[5] = 0.f;
+                sm[comp] = z;
+            } else {
+                // predict: x' = A x ; P' = A P A^T + Q, A = [1 1; 0 1], Q = 0.01 I
+                float x0 = __fadd_rn(ks[0], ks[1]), x1 = ks[1];
+                float t00 = __fadd_rn(ks[2], ks[4]), t01 = __fadd_rn(ks[3], ks[5]), t10 = ks[4], t11 = ks[5];
+                float p00 = __fadd_rn(__fadd_rn(t00, t01), 0.01f), p01 = t01;
+                float p10 = __fadd_rn(t10, t11), p11 = __fadd_rn(t11, 0.01f);
+                // correct: H = [1 0], R = 0.1
+                float s = __fadd_rn(p00, 0.1f);
+                float k0 = __fdiv_rn(p00, s), k1 = __fdiv_rn(p01, s);
+                float y = __fsub_rn(z, x0);
+                ks[0] = __fadd_rn(x0, __fmul_rn(k0, y));
+                ks[1] = __fadd_rn(x1, __fmul_rn(k1, y));
+                ks[2] = __fsub_rn(p00, __fmul_rn(k0, p00)); ks[3] = __fsub_rn(p01, __fmul_rn(k0, p01));
+                ks[4] = __fsub_rn(p10, __fmul_rn(k1, p00)); ks[5] = __fsub_rn(p11, __fmul_rn(k1, p01));
+                sm[comp] = ks[0];
+            }
+        }
+        have = true;
+    }
+    if (!have) {                                            // box with adaptive radius :808-823
+        rec.radius = adaptive_radius(path, n, info.smoothing_radius);
+        for (int comp = 0; comp < 3; ++comp) sm[comp] = box_at(path, comp, n, rec.radius, i);
+    }
+    float raw[3], diff[3];
+    for (int k = 0; k < 3; ++k) {
+        raw[k] = L.transforms[3 * i + k];
+        diff[k] = __fsub_rn(sm[k], path[3 * i + k]);
+        rec.smoothed[k] = sm[k];
+    }
+    if (i > 0) {                                            // :854-888
+        rec.intent = motion_intent(L.transforms, n, raw, i);
+        float sc = rec.intent == 1 ? 0.5f : rec.intent == 2 ? 1.0f : rec.intent == 3 ? 0.8f : 0.7f;
+        for (int k = 0; k < 3; ++k) diff[k] = __fmul_rn(diff[k], sc);
+    }
+    float dx = __fadd_rn(raw[0], diff[0]), dy = __fadd_rn(raw[1], diff[1]), da = __fadd_rn(raw[2], diff[2]);
+    if (info.horizon_lock) da = 0.f;
+    float cs = (float)cos((double)da), sn = (float)sin((double)da);
+    float T[6] = {cs, -sn, dx, sn, cs, dy};
+    invert_affine(T, wp.m);
+    for (int k = 0; k < 6; ++k) { wp.T[k] = T[k]; rec.T[k] = T[k]; }
+    wp.passthrough = 0; wp.pad = 0;
+    *L.wp = wp;
+    if (info.n_out < L.record_capacity) L.orec[info.n_out] = rec;
+}
+
+__global__ void __launch_bounds__(32) k_smooth_only(const LaneDev* __restrict__ lanes, StepInfo info) {
+    __shared__ float gk[512];
+    if (threadIdx.x == 0) smooth_and_setup(lanes[blockIdx.z], info, gk);
+}
+
+__global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict__ lanes, StepInfo info) {
+    extern __shared__ unsigned char mo_raw[];
+    MoSmem& S = *reinterpret_cast<MoSmem*>(mo_raw);
+    const LaneDev& L = lanes[blockIdx.z];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const int n_prev = min(min(*L.kp_count, L.kp_capacity), MO_MAXP);
+    const int fidx = info.frame_no - 1;
+    float2* lprev = nullptr; float2* lnext = nullptr; uint8_t* lstat = nullptr; uint8_t* lmask = nullptr;
+    if (L.log_depth > 0) {
+        size_t o = (size_t)(fidx % L.log_depth) * L.kp_capacity;
+        lprev = L.log_prev + o; lnext = L.log_next + o; lstat = L.log_status + o; lmask = L.log_mask + o;
+    }
+
+    // ---- order-preserving compaction of the tracked pairs (status != 0)
+    int running = 0;
+    for (int base = 0; base < n_prev; base += MO_THREADS) {
+        int i = base + tid;
+        bool ok = false;
+        float2 a = make_float2(0.f, 0.f), b = a;
+        if (i < n_prev) {
+            a = L.kp[i]; b = L.lk_next[i];
+            uint8_t s = L.lk_status[i];
+            ok = s != 0;
+            if (lprev) { lprev[i] = a; lnext[i] = b; lstat[i] = s; }
+        }
+        unsigned m = __ballot_sync(FULL, ok);
+        if (lane == 0) S.warp_tot[warp] = __popc(m);
+        __syncthreads();
+        int off = running;
+        for (int w = 0; w < warp; ++w) off += S.warp_tot[w];
+        if (ok) {
+            int pos = off + __popc(m & ((1u << lane) - 1u));
+            S.from[pos] = a; S.to[pos] = b;
+        }
+        int tot = 0;
+        for (int w = 0; w < MO_THREADS / 32; ++w) tot += S.warp_tot[w];
+        running += tot;
+        __syncthreads();
+    }
+    const int n = running;
+
+    if (tid == 0) {
+        S.n = n; S.niters = VS_RANSAC_MAX_ITERS; S.iter = 0; S.max_good = 0; S.best_found = 0;
+        S.rng = 0xFFFFFFFFFFFFFFFFull; S.cont = (n_prev > 0 && n >= 4) ? 1 : 0;
+    }
+    __syncthreads();
+
+    // ---- RANSAC: rounds of 32 hypotheses, warp per hypothesis, sequential replay of the stop rule
+    while (S.cont) {
+        if (tid == 0) {
+            unsigned long long r = S.rng;
+            for (int h = 0; h < MO_BATCH; ++h) {
+                int i0 = (int)(rng_next(r) % (unsigned)n), i1;
+                do { i1 = (int)(rng_next(r) % (unsigned)n); } while (i1 == i0);
+                S.idx[h][0] = i0; S.idx[h][1] = i1;
+            }
+            S.rng = r;
+        }
+        __syncthreads();
+        {
+            double M[6];
+            float F[6];
+            int i0 = S.idx[warp][0], i1 = S.idx[warp][1];
+            model_from_pair(S.from[i0], S.from[i1], S.to[i0], S.to[i1], M);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) F[k] = (float)M[k];
+            int cnt = 0;
+            for (int i = lane; i < n + (32 - (n & 31)) % 32; i += 32) {
+                bool in = i < n && is_inlier(F, S.from[i], S.to[i]);
+                cnt += __popc(__ballot_sync(FULL, in));
+            }
+            if (lane == 0) S.good[warp] = cnt;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int iter = S.iter, niters = S.niters, max_good = S.max_good, adv = 0, best = -1;
+            for (int h = 0; h < MO_BATCH && iter < niters; ++h, ++iter, ++adv) {
+                int g = S.good[h];
+                if (g > max(max_good, 1)) {
+                    max_good = g; best = h;
+                    niters = ransac_update_iters(0.99, (double)(n - g) / n, niters);
+                }
+            }
+            // The RNG is consumed only by iterations that ran; draws for skipped hypotheses are
+            // irrelevant because the loop ends (fresh RNG per call in the reference).
+            S.iter = iter; S.niters = niters; S.max_good = max_good;
+            if (best >= 0) {
+                S.best_found = 1;
+                double M[6];
+                int i0 = S.idx[best][0], i1 = S.idx[best][1];
+                model_from_pair(S.from[i0], S.from[i1], S.to[i0], S.to[i1], M);
+                for (int k = 0; k < 6; ++k) { S.model[k] = M[k]; S.bestF[k] = (float)M[k]; }
+            }
+            S.cont = (iter < niters) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+
+    // ---- inlier mask of the winning hypothesis + least-squares similarity refit (double)
+    const bool found = S.best_found != 0;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (found) {
+        float F[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) F[k] = S.bestF[k];
+        // pass 1: means over inliers
+        double sx = 0, sy = 0, su = 0, sv = 0, cnt = 0;
+        for (int i = tid; i < n; i += MO_THREADS) {
+            bool in = is_inlier(F, S.from[i], S.to[i]);
+            L.inlier_mask[i] = in;
+            if (lmask) lmask[i] = in;
+            if (in) { sx += S.from[i].x; sy += S.from[i].y; su += S.to[i].x; sv += S.to[i].y; cnt += 1.; }
+        }
+        acc[0] = sx; acc[1] = sy; acc[2] = su; acc[3] = sv; acc[4] = cnt;
+    }
+    auto block_reduce = [&](int nvals) {
+        for (int k = 0; k < nvals; ++k) {
+            double v = acc[k];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+            if (lane == 0) S.red[k][warp] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int k = 0; k < nvals; ++k) {
+                double v = S.red[k][lane];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+                if (lane == 0) S.red[k][0] = v;
+            }
+        }
+        __syncthreads();
+    };
+    double A = 1., B = 0., TX = 0., TY = 0.;
+    int n_inl = -1;
+    if (found) {                                            // uniform across the CTA
+        block_reduce(5);
+        double cnt = S.red[4][0];
+        double mx = S.red[0][0] / cnt, my = S.red[1][0] / cnt, mu = S.red[2][0] / cnt, mv = S.red[3][0] / cnt;
+        n_inl = (int)cnt;
+        __syncthreads();
+        for (int k = 0; k < 7; ++k) acc[k] = 0;
+        for (int i = tid; i < n; i += MO_THREADS) {
+            if (L.inlier_mask[i]) {
+                double xc = S.from[i].x - mx, yc = S.from[i].y - my, uc = S.to[i].x - mu, vc = S.to[i].y - mv;
+                acc[0] += xc * xc + yc * yc;
+                acc[1] += xc * uc + yc * vc;
+                acc[2] += xc * vc - yc * uc;
+            }
+        }
+        block_reduce(3);
+        double den = S.red[0][0];
+        A = S.red[1][0] / den; B = S.red[2][0] / den;
+        TX = mu - (A * mx - B * my);
+        TY = mv - (B * mx + A * my);
+    }
+    __syncthreads();
+
+    // ---- decomposition, trajectory, record, smoothing (one thread; sequential float32 semantics)
+    if (tid == 0) {
+        float t[3] = {0.f, 0.f, 0.f};
+        if (found) {
+            float T00 = (float)A, T10 = (float)B;
+            t[0] = (float)TX; t[1] = (float)TY;
+            t[2] = f_atan2(T10, T00);
+        }
+        float* tr = L.transforms + 3 * fidx;
+        float* pa = L.path + 3 * fidx;
+        for (int k = 0; k < 3; ++k) {
+            tr[k] = t[k];
+            pa[k] = fidx == 0 ? t[k] : __fadd_rn(L.path[3 * (fidx - 1) + k], t[k]);
+        }
+        if (fidx < L.record_capacity) {
+            vs_frame_record& r = L.frec[fidx];
+            r.frame_index = info.frame_no; r.n_prev_pts = n_prev; r.n_tracked = n;
+            r.n_inliers = found ? n_inl : -1; r.ransac_iters = S.iter; r.n_detected = -1;
+            for (int k = 0; k < 3; ++k) { r.transform[k] = t[k]; r.path[k] = pa[k]; }
+            r.affine[0] = found ? A : 1.; r.affine[1] = found ? -B : 0.; r.affine[2] = found ? TX : 0.;
+            r.affine[3] = found ? B : 0.; r.affine[4] = found ? A : 1.; r.affine[5] = found ? TY : 0.;
+        }
+        if (info.adaptive && info.frame_no >= 3) {          // adaptSmoothingRadius :1461-1492, :1562-1574
+            float mag = f_sqrt(__fadd_rn(__fmul_rn(t[0], t[0]), __fmul_rn(t[1], t[1])));
+            float sc = fmaxf(0.0f, fminf(1.0f, __fdiv_rn(mag, 50.0f)));
+            sc = __fsub_rn(1.0f, sc);
+            int nr = info.min_radius + (int)__fmul_rn(sc, (float)(info.max_radius - info.min_radius));
+            L.kalman[VS_KAL_RADIUS_SLOT] = __int_as_float(nr);   // adaptive radius hand-off to the host
+        }
+        __threadfence_block();
+        if (info.pop_index >= 0) smooth_and_setup(L, info, S.gk);
+    }
+}
+
+void launch_motion(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_motion, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoSmem));
+        attr_set = true;
+    }
+    k_motion<<<dim3(1, 1, n_lanes), MO_THREADS, sizeof(MoSmem), st>>>(lanes, info);
+}
+
+void launch_smooth_only(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_t st) {
+    k_smooth_only<<<dim3(1, 1, n_lanes), 32, 0, st>>>(lanes, info);
+}

@@ -1,0 +1,62 @@
+// kernels.h — host-callable launchers of the stabilization kernels (one .cu per stage).
+#pragma once
+#include "common.cuh"
+
+#define VS_MAX_GROUP 64     // lanes per launch group (frame pointers travel as kernel arguments)
+
+struct PtrPack {
+    const uint8_t* p[VS_MAX_GROUP];
+};
+struct MutPtrPack {
+    uint8_t* p[VS_MAX_GROUP];
+};
+
+// ---- k_pyramid.cu : resize + gray + pyrDown (Stabilizer.cpp:304-305,449-450,602; pyramid of :611)
+// full-res BGR -> padded gray level `dst_level` of every lane's pyramid slot `slot`
+// (slot < 0: the lanes' `small0` first-frame level)
+void launch_gray_resize(const LaneDev* lanes, int n_lanes, const PtrPack& src, int w, int h, size_t stride,
+                        int slot, cudaStream_t st);
+// gray `small0` (480x270) -> level 0 of pyramid slot `slot`, cv::resize INTER_LINEAR up-sampling (:602)
+void launch_upsample_small(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st);
+// levels 1 and 2 of pyramid slot `slot` from level 0 (cv::pyrDown x2)
+void launch_pyrdown(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st);
+// generic cv::resize INTER_LINEAR on tightly addressed 8UC1/8UC3 (tests, crop+zoom second pass)
+void launch_resize_linear(const uint8_t* src, int sw, int sh, size_t sstride, int ch,
+                          uint8_t* dst, int dw, int dh, size_t dstride, cudaStream_t st);
+// copy a tightly packed gray image into a padded level / back (tests)
+void launch_pack_level(const uint8_t* src, GrayLevel dst, cudaStream_t st);
+void launch_unpack_level(GrayLevel src, uint8_t* dst, cudaStream_t st);
+
+// ---- k_gftt.cu : cv::goodFeaturesToTrack (Stabilizer.cpp:355-357, 740-744)
+// source = pyramid slot `slot` level 0 (slot >= 0) or small0 (slot < 0); result -> lanes[].kp / kp_count
+// (and first_corners when slot < 0).  record_frame_no > 0: also log into the frame record ring.
+void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_corners, double quality,
+                          double min_dist, int record_frame_no, cudaStream_t st);
+size_t gftt_grid_words(int w, int h, double min_dist);
+
+// ---- k_lk.cu : cv::calcOpticalFlowPyrLK (Stabilizer.cpp:611-619)
+// tracks lanes[].kp from pyramid slot `prev` to slot `cur`; writes lk_next / lk_status
+void launch_pyr_lk(const LaneDev* lanes, int n_lanes, int prev, int cur, int max_pts, cudaStream_t st);
+
+// ---- k_motion.cu : status filter + estimateAffinePartial2D + decomposition + trajectory +
+//                    smoothing + warp set-up (Stabilizer.cpp:629-688, 783-908, 1139-1172, 1364-1458, 1637-1780)
+void launch_motion(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_t st);
+// flush-time variant: no new frame, only the smoothing + warp set-up for `info.pop_index`
+void launch_smooth_only(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_t st);
+
+// ---- k_warp.cu : copyMakeBorder + warpAffine + crop/zoom (Stabilizer.cpp:981-990, 1056-1060, 1108-1124)
+struct WarpGeom {
+    int src_w, src_h;       // frame as pushed
+    size_t src_stride;
+    int mode;               // 0 plain, 1 border (output grows by 2b), 2 crop+zoom
+    int border, border_mode;
+    int out_w, out_h;
+    size_t out_stride;
+};
+void launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, WarpGeom g,
+                 uint8_t* const* scratch, cudaStream_t st);
+// stand-alone batched warp with host-supplied matrices (tests + roofline bench)
+void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe,
+                          uint8_t* dst, int dw, int dh, size_t dstride, size_t dframe,
+                          const WarpParams* d_wp, int n_frames, cudaStream_t st);
+void warp_params_from_T(const float* T, WarpParams* wp);   // host: cv::warpAffine's matrix inversion
