@@ -184,6 +184,12 @@ vs_status vs_stabilizer_first_corners(vs_stabilizer* s, float* xy, int capacity,
 /* kernels this handle has launched since creation (the bench's gpu_launches claim). */
 vs_status vs_stabilizer_launch_count(vs_stabilizer* s, uint64_t* n);
 
+/* Per-stage device timing with CUDA events on the handle's stream (off by default; bench/profiles).
+ * stage: 0 resize+gray, 1 pyrDown, 2 PyrLK, 3 RANSAC+trajectory+smoothing, 4 GFTT, 5 warp.
+ * vs_*_stage_time synchronises and returns the summed duration and launch-group count since enabling. */
+vs_status vs_stabilizer_set_timing(vs_stabilizer* s, int enable);
+vs_status vs_stabilizer_stage_time(vs_stabilizer* s, int stage, double* total_ms, long long* count);
+
 /* ---- multi-stream batch: N independent streams advanced in lock-step, one kernel launch per
  * stage for the whole batch (BASELINE config 4).  Semantically N vs_stabilizers. -------------- */
 typedef struct vs_batch vs_batch;
@@ -198,6 +204,8 @@ vs_status vs_batch_flush_device(vs_batch* b, uint8_t* const* d_outs, size_t out_
 vs_status vs_batch_sync(vs_batch* b);
 void*     vs_batch_stream(vs_batch* b);
 vs_status vs_batch_launch_count(vs_batch* b, uint64_t* n);
+vs_status vs_batch_set_timing(vs_batch* b, int enable);
+vs_status vs_batch_stage_time(vs_batch* b, int stage, double* total_ms, long long* count);
 vs_status vs_batch_stream_counts(vs_batch* b, int stream, int* n_frame_records, int* n_output_records);
 vs_status vs_batch_frame_record(vs_batch* b, int stream, int i, vs_frame_record* rec);
 vs_status vs_batch_output_record(vs_batch* b, int stream, int i, vs_output_record* rec);

@@ -71,6 +71,10 @@ SYMBOLS = {
     "vs_stabilizer_frame_points": (_I, [_P, _I, _P, _P, _P, _P, _P]),
     "vs_stabilizer_first_corners": (_I, [_P, _P, _I, _IP]),
     "vs_stabilizer_launch_count": (_I, [_P, C.POINTER(C.c_uint64)]),
+    "vs_stabilizer_set_timing": (_I, [_P, _I]),
+    "vs_stabilizer_stage_time": (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "vs_batch_set_timing": (_I, [_P, _I]),
+    "vs_batch_stage_time": (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "vs_batch_create": (_I, [C.POINTER(VsParams), _I, _I, C.POINTER(_P)]),
     "vs_batch_destroy": (None, [_P]),
     "vs_batch_push_device": (_I, [_P, C.POINTER(_P), _I, _I, _SZ, C.POINTER(_P), _SZ, _SZ, C.c_uint, _IP, _IP, _IP]),

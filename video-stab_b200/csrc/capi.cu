@@ -229,6 +229,27 @@ vs_status vs_stabilizer_launch_count(vs_stabilizer* s, uint64_t* n) {
     return VS_OK;
 }
 
+vs_status vs_stabilizer_set_timing(vs_stabilizer* s, int enable) {
+    if (!s) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
+    s->eng->set_timing(enable != 0);
+    return VS_OK;
+}
+vs_status vs_stabilizer_stage_time(vs_stabilizer* s, int stage, double* total_ms, long long* count) {
+    if (!s || !total_ms || !count) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    s->eng->stage_time(stage, total_ms, count);
+    return VS_OK;
+}
+vs_status vs_batch_set_timing(vs_batch* b, int enable) {
+    if (!b) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
+    b->eng->set_timing(enable != 0);
+    return VS_OK;
+}
+vs_status vs_batch_stage_time(vs_batch* b, int stage, double* total_ms, long long* count) {
+    if (!b || !total_ms || !count) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    b->eng->stage_time(stage, total_ms, count);
+    return VS_OK;
+}
+
 // ------------------------------------------------------------------------------------ batch
 vs_status vs_batch_create(const vs_params* params, int device, int n_streams, vs_batch** out) {
     if (!params || !out) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");

@@ -22,6 +22,44 @@ vs_status vs_set_error(vs_status st, const char* msg) {
 }
 extern "C" const char* vs_last_error(void) { return g_err; }
 
+// ---- optional per-stage CUDA-event timing (bench / profiles); off by default
+struct StageScope {
+    Engine* e; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    StageScope(Engine* e_, int s) : e(e_), stage(s) { if (e->timing_on()) { a = e->take_event(); b = e->take_event(); cudaEventRecord(a, e->stream()); } }
+    ~StageScope() { if (a) { cudaEventRecord(b, e->stream()); e->add_pending(stage, a, b); } }
+};
+
+cudaEvent_t Engine::take_event() {
+    if (!event_pool_.empty()) { cudaEvent_t ev = event_pool_.back(); event_pool_.pop_back(); return ev; }
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    return ev;
+}
+void Engine::add_pending(int stage, cudaEvent_t a, cudaEvent_t b) {
+    pending_.push_back({stage, a, b});
+    if (pending_.size() >= 8192) collect_timing();
+}
+void Engine::collect_timing() {
+    if (pending_.empty()) return;
+    cudaStreamSynchronize(stream_);
+    for (auto& p : pending_) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { stage_ms_[p.stage] += ms; stage_n_[p.stage] += 1; }
+        event_pool_.push_back(p.a); event_pool_.push_back(p.b);
+    }
+    pending_.clear();
+}
+void Engine::set_timing(bool on) {
+    collect_timing();
+    timing_ = on;
+    for (int i = 0; i < VS_N_STAGES; ++i) { stage_ms_[i] = 0.; stage_n_[i] = 0; }
+}
+void Engine::stage_time(int stage, double* ms, long long* n) {
+    collect_timing();
+    *ms = (stage >= 0 && stage < VS_N_STAGES) ? stage_ms_[stage] : 0.;
+    *n = (stage >= 0 && stage < VS_N_STAGES) ? stage_n_[stage] : 0;
+}
+
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -104,6 +142,8 @@ vs_status Engine::alloc_fixed() {
     size_t gw = gftt_grid_words(VS_FW, VS_FH, p_.min_distance);
     size_t gw2 = gftt_grid_words(VS_AW, VS_AH, 15.0);
     if (gw2 > gw) gw = gw2;
+    gw2 = gftt_grid_words(VS_AW, VS_AH, p_.min_distance);     // single-kernel entry point on a 960x540 image
+    if (gw2 > gw) gw = gw2;
     traj_bufs_.clear();
     for (int l = 0; l < n_lanes_; ++l) {
         LaneDev& L = h_lanes_[l];
@@ -175,6 +215,9 @@ vs_status Engine::grow_trajectory() {
 
 void Engine::free_all() {
     if (stream_) cudaStreamSynchronize(stream_);
+    collect_timing();
+    for (cudaEvent_t ev : event_pool_) cudaEventDestroy(ev);
+    event_pool_.clear();
     for (auto& L : h_lanes_) {
         cudaFree(L.transforms); cudaFree(L.path); cudaFree(L.frec); cudaFree(L.orec);
     }
@@ -262,9 +305,12 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         launch_pyrdown(d_lanes_, n_lanes_, prev, stream_);
         launches_ += 3;
     }
-    launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, stream_);      // :449-450
-    launch_pyrdown(d_lanes_, n_lanes_, cur, stream_);
-    launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, stream_);   // :611-619
+    { StageScope t(this, VS_STAGE_GRAY);
+      launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, stream_); }   // :449-450
+    { StageScope t(this, VS_STAGE_PYRDOWN);
+      launch_pyrdown(d_lanes_, n_lanes_, cur, stream_); }
+    { StageScope t(this, VS_STAGE_LK);
+      launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, stream_); }   // :611-619
     launches_ += 4;
 
     const bool adaptive = p_.adaptive_smoothing != 0;
@@ -274,10 +320,12 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         *will_pop = (int)queue_.size() >= gate;
         if (*will_pop) pop_index = queue_.front().index;
     }
-    launch_motion(d_lanes_, n_lanes_, step_info(pop_index), stream_);                  // :629-688 (+ :783-908)
+    { StageScope t(this, VS_STAGE_MOTION);
+      launch_motion(d_lanes_, n_lanes_, step_info(pop_index), stream_); }              // :629-688 (+ :783-908)
     launches_ += 1;
 
     if ((++detect_counter_ % 2) == 0) {                                               // :696-697
+        StageScope t(this, VS_STAGE_GFTT);
         CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, stream_));
         int mc = p_.max_corners < 200 ? p_.max_corners : 200;
         launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, frame_no, stream_);   // :740-744
@@ -337,7 +385,8 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         g.mode = m2;
         std::vector<uint8_t*> scratch(n_lanes_);
         for (int l = 0; l < n_lanes_; ++l) scratch[l] = d_scratch_ ? d_scratch_ + frame_bytes_ * l : nullptr;
-        launch_warp(d_lanes_, n_lanes_, src, dst, g, scratch.data(), stream_);
+        { StageScope t(this, VS_STAGE_WARP);
+          launch_warp(d_lanes_, n_lanes_, src, dst, g, scratch.data(), stream_); }
         launches_ += (m2 == 2) ? 1 + n_lanes_ : 1;
     }
     if (host_io) {

@@ -8,6 +8,8 @@
 
 #include "kernels.h"
 
+enum { VS_STAGE_GRAY = 0, VS_STAGE_PYRDOWN, VS_STAGE_LK, VS_STAGE_MOTION, VS_STAGE_GFTT, VS_STAGE_WARP, VS_N_STAGES };
+
 struct QueueEntry {
     int index;                               // frameIndexQueue_
     int slot;                                // ring slot (copy mode)
@@ -37,6 +39,14 @@ public:
     vs_status output_record(int lane, int i, vs_output_record* r);
     vs_status frame_points(int lane, int i, float* prev, float* next, uint8_t* status, uint8_t* mask, float* det);
     vs_status first_corners(int lane, float* xy, int cap, int* n);
+
+    // per-stage CUDA-event timing (off by default; used by bench.py and the profiles)
+    void set_timing(bool on);
+    void stage_time(int stage, double* ms, long long* n);
+    bool timing_on() const { return timing_; }
+    cudaEvent_t take_event();
+    void add_pending(int stage, cudaEvent_t a, cudaEvent_t b);
+    void collect_timing();
 
     // single-op helpers behind the vs_k_* entry points (lane 0 scratch)
     const LaneDev* d_lanes() const { return d_lanes_; }
@@ -83,4 +93,11 @@ private:
     uint8_t* d_scratch_ = nullptr;    // [lane][frame]      (crop+zoom first pass)
     std::vector<float*> traj_bufs_;
     uint64_t launches_ = 0;
+
+    struct Pending { int stage; cudaEvent_t a, b; };
+    bool timing_ = false;
+    std::vector<cudaEvent_t> event_pool_;
+    std::vector<Pending> pending_;
+    double stage_ms_[VS_N_STAGES] = {};
+    long long stage_n_[VS_N_STAGES] = {};
 };

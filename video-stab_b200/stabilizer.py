@@ -267,6 +267,24 @@ class Stabilizer:
         check(lib.vs_stabilizer_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def set_timing(self, on: bool):
+        check(lib.vs_stabilizer_set_timing(self._h, int(on)))
+
+    def stage_times(self) -> dict:
+        return _stage_times(None, lib.vs_stabilizer_stage_time, self._h)
+
+
+STAGES = ("resize_gray", "pyrdown", "pyr_lk", "motion", "gftt", "warp")
+
+
+def _stage_times(set_fn, get_fn, h):
+    out = {}
+    for i, name in enumerate(STAGES):
+        ms, n = C.c_double(), C.c_longlong()
+        check(get_fn(h, i, C.byref(ms), C.byref(n)))
+        out[name] = {"ms": ms.value, "count": n.value}
+    return out
+
 
 class StabilizerBatch:
     """N independent streams advanced in lock-step on one GPU, one launch per stage for the whole
@@ -310,6 +328,12 @@ class StabilizerBatch:
         n = C.c_uint64()
         check(lib.vs_batch_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def set_timing(self, on: bool):
+        check(lib.vs_batch_set_timing(self._h, int(on)))
+
+    def stage_times(self) -> dict:
+        return _stage_times(None, lib.vs_batch_stage_time, self._h)
 
     def counts(self, stream: int = 0):
         a, b = C.c_int(), C.c_int()
