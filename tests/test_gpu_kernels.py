@@ -142,6 +142,21 @@ def test_good_features_flat_and_sparse(vsb, cv2_noopt):
     assert np.array_equal(vsb.kernels.good_features(_dev(one), 200, 0.02, 15.0), ref)
 
 
+def test_good_features_massive_ties(vsb, cv2_noopt):
+    """Checkerboards give thousands of candidates with IDENTICAL eigenvalues: exercises the tie order
+    (higher address first), the multi-chunk path and the single-bin overflow split of k_select."""
+    cv2 = cv2_noopt
+    yy, xx = np.mgrid[0:540, 0:960]
+    for sq, md, mc in ((8, 3.0, 0), (8, 0.0, 0), (12, 15.0, 200), (6, 1.0, 1500)):
+        img = (((yy // sq) + (xx // sq)) % 2 * 160 + 40).astype(np.uint8)
+        ref = cv2.goodFeaturesToTrack(img, mc, 0.02, md, None, blockSize=3)
+        ref = np.zeros((0, 2), np.float32) if ref is None else ref.reshape(-1, 2)
+        got = vsb.kernels.good_features(_dev(img), mc, 0.02, md)
+        n = min(len(got), 2048)                 # the kernel caps "unlimited" at 2048 corners
+        assert len(ref) >= n and (len(got) == len(ref) or len(got) == 2048)
+        assert np.array_equal(got[:n], ref[:n]), f"square {sq} minDist {md}"
+
+
 def _moved_pair(vsb, cv2, seed, ang, shift, w=960, h=540):
     big = vsb.synth.base_texture(w, h, seed)[..., 1].copy()
     m = cv2.getRotationMatrix2D((big.shape[1] / 2, big.shape[0] / 2), ang, 1.0)

@@ -106,7 +106,7 @@ static vs_status dalloc(std::vector<void*>& allocs, T** out, size_t n) {
 static vs_status alloc_level(std::vector<void*>& allocs, int w, int h, GrayLevel* lv) {
     int pitch = (int)align_up((size_t)w + 2 * VS_PAD, 16);
     uint8_t* mem = nullptr;
-    VS_TRY(dalloc(allocs, &mem, (size_t)pitch * (h + 2 * VS_PAD)));
+    VS_TRY(dalloc(allocs, &mem, (size_t)pitch * (h + 2 * VS_PAD) + 64));   // +64: aligned 32-bit patch loads may over-read a few bytes
     lv->base = mem + (size_t)VS_PAD * pitch + VS_PAD;
     lv->w = w; lv->h = h; lv->pitch = pitch;
     return VS_OK;

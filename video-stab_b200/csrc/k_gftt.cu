@@ -14,7 +14,7 @@
 #define EIG_TW 64
 #define EIG_TH 16
 #define SEL_THREADS 1024
-#define SEL_CHUNK_MAX 8192
+#define SEL_CHUNK_MAX 4096
 #define SEL_CHUNK_FIRST 1024
 
 static __device__ __forceinline__ GrayLevel gftt_src(const LaneDev& L, int slot) {
@@ -85,12 +85,18 @@ __global__ void __launch_bounds__(256) k_min_eig(const LaneDev* __restrict__ lan
 }
 
 // --------------------------------------------------------------------------------- k_candidates
+// threshold + 3x3 non-max suppression; compaction is warp-ballot -> CTA-level prefix in shared memory
+// -> one global atomic per CTA.
 __global__ void __launch_bounds__(256) k_candidates(const LaneDev* __restrict__ lanes, int slot, double quality) {
+    __shared__ int s_count, s_base;
+    __shared__ int s_warp_off[8];
     const LaneDev& L = lanes[blockIdx.z];
     const GrayLevel G = gftt_src(L, slot);
     const int w = G.w, h = G.h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int x = blockIdx.x * 64 + (threadIdx.x & 63);
     int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (threadIdx.x == 0) s_count = 0;
     const float mx = __uint_as_float(*L.eig_max);
     const float thr = (float)((double)mx * quality);
     bool is = false;
@@ -103,26 +109,32 @@ __global__ void __launch_bounds__(256) k_candidates(const LaneDev* __restrict__ 
                  e >= p[w - 1] && e >= p[w] && e >= p[w + 1];
         }
     }
-    unsigned m = __ballot_sync(0xffffffffu, is);
-    if (m) {
-        int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
-        if (lane == leader) base = atomicAdd(L.cand_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (is) {
-            int pos = base + __popc(m & ((1u << lane) - 1u));
-            L.cand[pos] = ((unsigned long long)__float_as_uint(e) << 32) | (unsigned)(y * w + x);
-        }
+    __syncthreads();
+    const unsigned m = __ballot_sync(0xffffffffu, is);
+    if (lane == 0 && m) s_warp_off[warp] = atomicAdd(&s_count, __popc(m));
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count) s_base = atomicAdd(L.cand_count, s_count);
+    __syncthreads();
+    if (is) {
+        int pos = s_base + s_warp_off[warp] + __popc(m & ((1u << lane) - 1u));
+        L.cand[pos] = ((unsigned long long)__float_as_uint(e) << 32) | (unsigned)(y * w + x);
     }
 }
 
 // ------------------------------------------------------------------------------------- k_select
+#define SEL_BINS 4096
+#define SEL_GRID_CELLS 2560          // min-distance grids up to this many cells live in shared memory
+
 struct SelSmem {
     unsigned int hist[256];
     unsigned long long prefix, mask, T;
     int k, count, accepted, done;
+    int warp_sum[32];
+    int lo_bin, chunk_count;
 };
 
-// K-th largest key strictly below U (keys are unique): MSD radix select, 8 bits per pass
+// K-th largest key strictly below U (keys are unique): MSD radix select, 8 bits per pass.
+// Only used when one histogram bin alone overflows the sort buffer (massive ties).
 static __device__ unsigned long long radix_select(const unsigned long long* __restrict__ keys, int n,
                                                   unsigned long long U, int K, SelSmem& S) {
     if (threadIdx.x == 0) { S.prefix = 0ull; S.mask = 0ull; S.k = K; }
@@ -167,122 +179,203 @@ static __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
     }
 }
 
+// The order-dependent min-distance pass of cv::goodFeaturesToTrack over m sorted candidates, run by
+// one warp 32 candidates at a time: every lane tests its candidate against the accepted set in the 3x3
+// neighbouring grid cells in parallel; conflicts INSIDE the batch are resolved in rank order with ballots.
+template <bool SMEM_GRID>
+static __device__ bool greedy_pass(const LaneDev& L, const unsigned long long* skeys, int m, int w, int cell, int gw,
+                                   int gh, bool use_grid, double md2, int cap, unsigned int* gcount,
+                                   unsigned int* gslot, int& accepted_io) {
+    const int lane = threadIdx.x;
+    int accepted = accepted_io;
+    bool stop = false;
+    for (int base = 0; base < m && !stop; base += 32) {
+        bool ok = base + lane < m;
+        unsigned addr = ok ? (unsigned)(skeys[base + lane] & 0xffffffffull) : 0u;
+        int y = addr / w, x = addr - y * w;
+        if (ok && use_grid) {
+            int cx = x / cell, cy = y / cell;
+            int xa = max(cx - 1, 0), xb = min(cx + 1, gw - 1), ya = max(cy - 1, 0), yb = min(cy + 1, gh - 1);
+            for (int yy = ya; yy <= yb && ok; ++yy)
+                for (int xx = xa; xx <= xb && ok; ++xx) {
+                    int ci = yy * gw + xx;
+                    unsigned cnt = SMEM_GRID ? gcount[ci] : __ldcg(&gcount[ci]);
+                    for (unsigned s = 0; s < cnt; ++s) {
+                        unsigned q = SMEM_GRID ? gslot[ci * VS_GRID_SLOTS + s] : __ldcg(&gslot[(size_t)ci * VS_GRID_SLOTS + s]);
+                        int dx = x - (int)(q & 0xffffu), dy = y - (int)(q >> 16);
+                        if ((double)(dx * dx + dy * dy) < md2) { ok = false; break; }
+                    }
+                }
+        }
+        unsigned pending = __ballot_sync(0xffffffffu, ok);
+        while (pending) {
+            int leader = __ffs(pending) - 1;
+            int lx = __shfl_sync(0xffffffffu, x, leader), ly = __shfl_sync(0xffffffffu, y, leader);
+            if (lane == leader) {
+                L.kp[accepted] = make_float2((float)lx, (float)ly);
+                if (use_grid) {
+                    int ci = (ly / cell) * gw + (lx / cell);
+                    unsigned c = SMEM_GRID ? gcount[ci] : __ldcg(&gcount[ci]);
+                    if (c < VS_GRID_SLOTS) {
+                        unsigned v = (unsigned)lx | ((unsigned)ly << 16);
+                        if (SMEM_GRID) { gslot[ci * VS_GRID_SLOTS + c] = v; gcount[ci] = c + 1; }
+                        else { __stcg(&gslot[(size_t)ci * VS_GRID_SLOTS + c], v); __stcg(&gcount[ci], c + 1); }
+                    }
+                }
+                ok = false;
+            }
+            ++accepted;
+            if (accepted >= cap) { stop = true; break; }
+            if (ok && use_grid) {
+                int dx = x - lx, dy = y - ly;
+                if ((double)(dx * dx + dy * dy) < md2) ok = false;
+            }
+            pending = __ballot_sync(0xffffffffu, ok);
+        }
+        if (!SMEM_GRID) __threadfence_block();
+        __syncwarp();
+    }
+    accepted_io = accepted;
+    return stop;
+}
+
+// One CTA per lane.  Candidates arrive unordered (tens of thousands on textured frames) but the greedy
+// pass usually stops after a few hundred, so the strongest ones are peeled off in value order chunk by
+// chunk: a 4096-bin histogram of the float bits (one pass), a block-wide suffix scan to find the bin
+// boundary that holds the next >= `target` candidates, a gather + shared-memory bitonic sort of just
+// those, then the greedy pass.  Bins are value-ordered, so chunk order == global order.
 __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restrict__ lanes, int slot, int max_corners,
-                                                         double min_dist, int record_frame_no) {
-    extern __shared__ unsigned long long skeys[];      // SEL_CHUNK_MAX
+                                                         double quality, double min_dist, int record_frame_no) {
+    extern __shared__ unsigned long long sel_dyn[];
+    unsigned long long* skeys = sel_dyn;                                        // SEL_CHUNK_MAX keys
+    unsigned int* hist = reinterpret_cast<unsigned int*>(sel_dyn + SEL_CHUNK_MAX);   // SEL_BINS
+    unsigned int* sgrid = hist + SEL_BINS;                                      // SEL_GRID_CELLS * (1 + slots)
     __shared__ SelSmem S;
     const LaneDev& L = lanes[blockIdx.z];
     const GrayLevel G = gftt_src(L, slot);
     const int w = G.w, h = G.h;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = min(*L.cand_count, w * h);
     const int cap = (max_corners > 0) ? min(max_corners, L.kp_capacity) : L.kp_capacity;
     const bool use_grid = min_dist >= 1.0;
     const int cell = use_grid ? (int)rint(min_dist) : 1;
     const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
     const double md2 = min_dist * min_dist;
-    unsigned int* gcount = L.grid;
-    unsigned int* gslot = L.grid + (size_t)gw * gh;
+    const bool smem_grid = gw * gh <= SEL_GRID_CELLS;
+    unsigned int* gcount = smem_grid ? sgrid : L.grid;
+    unsigned int* gslot = gcount + (smem_grid ? SEL_GRID_CELLS : gw * gh);
     if (use_grid)
-        for (int i = threadIdx.x; i < gw * gh; i += SEL_THREADS) gcount[i] = 0u;
-    if (threadIdx.x == 0) { S.accepted = 0; S.done = 0; }
-    __syncthreads();
+        for (int i = tid; i < gw * gh; i += SEL_THREADS) gcount[i] = 0u;
+    for (int i = tid; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0u;
+    if (tid == 0) { S.accepted = 0; S.done = 0; }
 
+    // bin = (float bits - bits(threshold)) >> shift, top bin holds the maximum
+    const float mxv = __uint_as_float(*L.eig_max);
+    const unsigned lo = __float_as_uint((float)((double)mxv * quality));
+    const unsigned range = __float_as_uint(mxv) - lo;
+    int shift = 0;
+    while ((range >> shift) >= (unsigned)SEL_BINS) ++shift;
+    __syncthreads();
+    for (int i = tid; i < N; i += SEL_THREADS) {
+        unsigned bits = (unsigned)(L.cand[i] >> 32);
+        atomicAdd(&hist[(bits - lo) >> shift], 1u);
+    }
+    __syncthreads();
+    // suffix scan (from the top bin down): thread r owns bins 4095-4r .. 4092-4r
+    int own[4];
+    int local = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { own[k] = (int)hist[SEL_BINS - 1 - 4 * tid - k]; local += own[k]; }
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) S.warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = S.warp_sum[lane], sc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, sc, o);
+            if (lane >= o) sc += u;
+        }
+        S.warp_sum[lane] = sc - v;             // exclusive
+    }
+    __syncthreads();
+    const int before = S.warp_sum[warp] + incl - local;    // candidates in bins above this thread's four
+
+    int taken = 0;               // candidates already handed to the greedy pass (exactly those with key >= U)
     unsigned long long U = ~0ull;
-    int remaining = N;
     bool first = true;
-    while (remaining > 0) {
-        int m;
-        unsigned long long T;
-        if (remaining <= SEL_CHUNK_MAX) { m = remaining; T = 0ull; }
-        else {
-            m = first ? SEL_CHUNK_FIRST : SEL_CHUNK_MAX;
+    while (taken < N) {
+        const int target = min(first ? SEL_CHUNK_FIRST : SEL_CHUNK_MAX / 2, N - taken);
+        first = false;
+        // lowest bin such that the not-yet-taken candidates in bins >= lo_bin number >= target
+        {
+            int cum = before;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int prev = cum;
+                cum += own[k];
+                if (prev - taken < target && cum - taken >= target) {
+                    S.lo_bin = SEL_BINS - 1 - 4 * tid - k;
+                    S.chunk_count = cum - taken;
+                }
+            }
+        }
+        __syncthreads();
+        const int lo_bin = S.lo_bin;
+        int m = S.chunk_count;
+        // key lower bound of the chunk: bin >= lo_bin  <=>  float bits >= lo + (lo_bin << shift)
+        unsigned long long T = (unsigned long long)((unsigned long long)lo + ((unsigned long long)lo_bin << shift)) << 32;
+        if (m > SEL_CHUNK_MAX) {
+            // one bin overflows the sort buffer (massive ties): split it exactly by key
+            m = SEL_CHUNK_MAX;
             T = radix_select(L.cand, N, U, m, S);
         }
-        first = false;
         int npad = 32;
         while (npad < m) npad <<= 1;
-        if (threadIdx.x == 0) S.count = 0;
-        for (int i = threadIdx.x; i < npad; i += SEL_THREADS) skeys[i] = 0ull;
+        if (tid == 0) S.count = 0;
+        for (int i = tid; i < npad; i += SEL_THREADS) skeys[i] = 0ull;
         __syncthreads();
-        for (int i = threadIdx.x; i < N; i += SEL_THREADS) {
+        for (int i = tid; i < N; i += SEL_THREADS) {
             unsigned long long k = L.cand[i];
             if (k < U && k >= T) skeys[atomicAdd(&S.count, 1)] = k;
         }
         __syncthreads();
         bitonic_sort_desc(skeys, npad);
-
-        // ---- ordered min-distance greedy pass, one warp, 32 candidates per step
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
+        if (tid < 32) {
             int accepted = S.accepted;
-            bool stop = false;
-            for (int base = 0; base < m && !stop; base += 32) {
-                bool ok = base + lane < m;
-                unsigned addr = ok ? (unsigned)(skeys[base + lane] & 0xffffffffull) : 0u;
-                int y = addr / w, x = addr - y * w;
-                if (ok && use_grid) {
-                    int cx = x / cell, cy = y / cell;
-                    int xa = max(cx - 1, 0), xb = min(cx + 1, gw - 1), ya = max(cy - 1, 0), yb = min(cy + 1, gh - 1);
-                    for (int yy = ya; yy <= yb && ok; ++yy)
-                        for (int xx = xa; xx <= xb && ok; ++xx) {
-                            int ci = yy * gw + xx;
-                            unsigned cnt = __ldcg(&gcount[ci]);
-                            for (unsigned s = 0; s < cnt; ++s) {
-                                unsigned q = __ldcg(&gslot[(size_t)ci * VS_GRID_SLOTS + s]);
-                                int dx = x - (int)(q & 0xffffu), dy = y - (int)(q >> 16);
-                                if ((double)(dx * dx + dy * dy) < md2) { ok = false; break; }
-                            }
-                        }
-                }
-                unsigned pending = __ballot_sync(0xffffffffu, ok);
-                while (pending) {
-                    int leader = __ffs(pending) - 1;
-                    int lx = __shfl_sync(0xffffffffu, x, leader), ly = __shfl_sync(0xffffffffu, y, leader);
-                    if (lane == leader) {
-                        L.kp[accepted] = make_float2((float)lx, (float)ly);
-                        if (use_grid) {
-                            int ci = (ly / cell) * gw + (lx / cell);
-                            unsigned c = __ldcg(&gcount[ci]);
-                            if (c < VS_GRID_SLOTS) {
-                                __stcg(&gslot[(size_t)ci * VS_GRID_SLOTS + c], (unsigned)lx | ((unsigned)ly << 16));
-                                __stcg(&gcount[ci], c + 1);
-                            }
-                        }
-                        ok = false;
-                    }
-                    ++accepted;
-                    if (accepted >= cap) { stop = true; break; }
-                    if (ok && use_grid) {
-                        int dx = x - lx, dy = y - ly;
-                        if ((double)(dx * dx + dy * dy) < md2) ok = false;
-                    }
-                    pending = __ballot_sync(0xffffffffu, ok);
-                }
-                __threadfence_block();
-                __syncwarp();
-            }
+            bool stop = smem_grid ? greedy_pass<true>(L, skeys, m, w, cell, gw, gh, use_grid, md2, cap, gcount, gslot, accepted)
+                                  : greedy_pass<false>(L, skeys, m, w, cell, gw, gh, use_grid, md2, cap, gcount, gslot, accepted);
             if (lane == 0) { S.accepted = accepted; S.done = stop ? 1 : 0; }
         }
         __syncthreads();
         if (S.done) break;
+        taken += m;
         U = T;
-        remaining -= m;
+        __syncthreads();
     }
     __syncthreads();
     const int n = S.accepted;
-    if (threadIdx.x == 0) *L.kp_count = n;
+    if (tid == 0) *L.kp_count = n;
     if (slot < 0) {
-        for (int i = threadIdx.x; i < n; i += SEL_THREADS) L.first_corners[i] = L.kp[i];
-        if (threadIdx.x == 0) *L.first_count = n;
+        for (int i = tid; i < n; i += SEL_THREADS) L.first_corners[i] = L.kp[i];
+        if (tid == 0) *L.first_count = n;
     }
     if (record_frame_no > 0) {
-        if (threadIdx.x == 0 && record_frame_no <= L.record_capacity) L.frec[record_frame_no - 1].n_detected = n;
+        if (tid == 0 && record_frame_no <= L.record_capacity) L.frec[record_frame_no - 1].n_detected = n;
         if (L.log_depth > 0) {
             float2* dst = L.log_detected + (size_t)((record_frame_no - 1) % L.log_depth) * L.kp_capacity;
-            for (int i = threadIdx.x; i < n; i += SEL_THREADS) dst[i] = L.kp[i];
+            for (int i = tid; i < n; i += SEL_THREADS) dst[i] = L.kp[i];
         }
     }
 }
+
+#define SEL_DYN_BYTES (SEL_CHUNK_MAX * sizeof(unsigned long long) + SEL_BINS * sizeof(unsigned int) + \
+                       SEL_GRID_CELLS * (1 + VS_GRID_SLOTS) * sizeof(unsigned int))
 
 size_t gftt_grid_words(int w, int h, double min_dist) {
     if (min_dist < 1.0) return 8;
@@ -296,14 +389,13 @@ void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_c
     const int w = slot < 0 ? VS_FW : VS_AW, h = slot < 0 ? VS_FH : VS_AH;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SEL_CHUNK_MAX * (int)sizeof(unsigned long long));
+        cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_DYN_BYTES);
         attr_set = true;
     }
     dim3 g1((w + EIG_TW - 1) / EIG_TW, (h + EIG_TH - 1) / EIG_TH, n_lanes);
     k_min_eig<<<g1, 256, 0, st>>>(lanes, slot);
     dim3 g2((w + 63) / 64, (h + 3) / 4, n_lanes);
     k_candidates<<<g2, 256, 0, st>>>(lanes, slot, quality);
-    k_select<<<dim3(1, 1, n_lanes), SEL_THREADS, SEL_CHUNK_MAX * sizeof(unsigned long long), st>>>(
-        lanes, slot, max_corners, min_dist, record_frame_no);
+    k_select<<<dim3(1, 1, n_lanes), SEL_THREADS, SEL_DYN_BYTES, st>>>(
+        lanes, slot, max_corners, quality, min_dist, record_frame_no);
 }

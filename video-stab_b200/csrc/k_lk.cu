@@ -2,23 +2,34 @@
 // Replaces cv::calcOpticalFlowPyrLK(prev, cur, pts, winSize 15x15, maxLevel 2,
 // TermCriteria(COUNT+EPS, 20, 0.03)) at Stabilizer.cpp:611-619.
 // Specification: oracle/cv_models.py lk_track (bit-exact against cv2 4.13, including the float32
-// accumulation ORDER of OpenCV's 128-bit SIMD loop, which this kernel reproduces with ordered
-// per-lane chains).  Patches are staged in shared memory; the 2x2 normal equations are reduced
-// with warp shuffles.  Latency/occupancy-bound: ~200 warps per frame per lane.
+// accumulation ORDER of OpenCV's 128-bit SIMD loop).
+//
+// Per pyramid level a warp stages, with aligned 32-bit loads, the 18x18 template patch of the previous
+// frame and a 32x32 search region of the current frame into shared memory (one memory round trip per
+// level; iterations then run entirely out of shared memory and only re-stage if the window leaves the
+// region).  The 2x2 normal equations are reduced with warp shuffles.  The reference accumulates its
+// sums in float32 in a fixed order; that order only matters when a partial sum can leave the exactly
+// representable integer range, so the kernel first reduces sum(|term|) with integer shuffles and
+//   - if it is <= 2^24, every float add in the reference is exact and the result equals the exact
+//     integer sum: one warp-wide integer reduction (fast path, the common case near convergence);
+//   - otherwise it replays the reference's ordered chains (4 SIMD lanes + scalar tail) from terms
+//     pre-converted in parallel (slow path).
+// Latency/occupancy-bound: ~200 warps per frame per lane.
 #include "kernels.h"
 
 #define LK_WARPS 4
 #define LK_NPIX (VS_WIN * VS_WIN)        // 225
-#define LK_PP 18                         // prev patch edge: 15 + 1 (bilinear) + 2 (Scharr)
-#define LK_JP 16                         // next patch edge: 15 + 1
+#define LK_PP 18                         // template patch edge: 15 + 1 (bilinear) + 2 (Scharr)
+#define LK_PW 24                         // staged template row: 18 + up to 3 bytes of alignment slack
+#define LK_JR 32                         // search region edge
 
 struct LkSmem {
-    uint8_t P[LK_PP][LK_PP + 2];         // prev-level patch, origin (ipx-1, ipy-1)
-    short2 D[LK_JP][LK_JP];              // Scharr (Ix,Iy) at (ipx+c, ipy+r); zero outside the image
-    uint8_t J[LK_JP][LK_JP];             // next-level patch, origin (inx, iny)
-    short Iw[LK_NPIX];                   // interpolated I window   (5 fractional bits)
+    uint32_t P[LK_PP][LK_PW / 4];        // template patch rows (bytes), origin (px0, ipy-1)
+    short2 D[16][16];                    // Scharr (Ix,Iy) at (ipx+c, ipy+r); zero outside the image
+    uint32_t J[LK_JR][LK_JR / 4];        // search region rows (bytes), origin (jx0, jy0)
+    short Iw[LK_NPIX + 1];               // interpolated I window   (5 fractional bits)
     short2 dI[LK_NPIX];                  // interpolated derivative window
-    int diff[LK_NPIX];                   // J - I per window pixel
+    int term[3][LK_NPIX];                // per-pixel products (int, or float bits for the scalar tails)
 };
 
 static __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
@@ -27,6 +38,65 @@ static __device__ __forceinline__ void lk_weights(float a, float b, int& w00, in
     w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, 1.f - b), s));
     w10 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, b), s));
     w11 = 16384 - w00 - w01 - w10;
+}
+
+static __device__ __forceinline__ int clamp_abs_sum(unsigned v) { return (int)min(v, 1u << 25); }
+
+// Ordered replay of one float32 accumulation of the reference over the 15x15 window.
+//   COV = true : terms are single products; SIMD lane j sees x=j then x=j+4 of each row
+//   COV = false: terms are pair sums of pixels x and x+4 (x = 0..3), one per row
+// `t` holds ints for x < 8 and float bits for the scalar tail x >= 8.  Lanes 0..3 run the four SIMD
+// chains, lane 4 the tail; the result (tail + ((q0+q2)+(q1+q3))) is returned on every lane.
+template <bool COV>
+static __device__ __forceinline__ float ordered_sum(const int* t, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    float acc = 0.f;
+    if (lane < 4) {
+#pragma unroll 5
+        for (int y = 0; y < VS_WIN; ++y) {
+            const int a = t[y * VS_WIN + lane], b = t[y * VS_WIN + lane + 4];
+            if (COV) {
+                acc = __fadd_rn(__int2float_rn(a), acc);
+                acc = __fadd_rn(__int2float_rn(b), acc);
+            } else {
+                acc = __fadd_rn(acc, __int2float_rn(a + b));
+            }
+        }
+    } else if (lane == 4) {
+#pragma unroll 5
+        for (int y = 0; y < VS_WIN; ++y) {
+#pragma unroll
+            for (int x = 8; x < VS_WIN; ++x) acc = __fadd_rn(acc, __int_as_float(t[y * VS_WIN + x]));
+        }
+    }
+    const float q0 = __shfl_sync(FULL, acc, 0), q1 = __shfl_sync(FULL, acc, 1);
+    const float q2 = __shfl_sync(FULL, acc, 2), q3 = __shfl_sync(FULL, acc, 3);
+    const float tl = __shfl_sync(FULL, acc, 4);
+    return __fadd_rn(tl, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
+}
+
+// The mismatch vector has its SIMD chains interleaved differently (OpenCV zips Ix/Iy): for the x
+// component chains are (pixels 0&4, 1&5 -> vector qb0 lanes 0,2 ; 2&6, 3&7 -> qb1 lanes 0,2) and the
+// total is tail + ((qb0[0]+qb1[0]) + (qb0[2]+qb1[2])).  Lane l<4 accumulates pixel pair (l, l+4).
+static __device__ __forceinline__ float ordered_sum_b(const int* t, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    float acc = 0.f;
+    if (lane < 4) {
+#pragma unroll 5
+        for (int y = 0; y < VS_WIN; ++y)
+            acc = __fadd_rn(acc, __int2float_rn(t[y * VS_WIN + lane] + t[y * VS_WIN + lane + 4]));
+    } else if (lane == 4) {
+#pragma unroll 5
+        for (int y = 0; y < VS_WIN; ++y) {
+#pragma unroll
+            for (int x = 8; x < VS_WIN; ++x) acc = __fadd_rn(acc, __int_as_float(t[y * VS_WIN + x]));
+        }
+    }
+    // pixel pairs: lane0=(0,4) -> qb0[.], lane1=(1,5) -> qb0[.+2], lane2=(2,6) -> qb1[.], lane3=(3,7) -> qb1[.+2]
+    const float p0 = __shfl_sync(FULL, acc, 0), p1 = __shfl_sync(FULL, acc, 1);
+    const float p2 = __shfl_sync(FULL, acc, 2), p3 = __shfl_sync(FULL, acc, 3);
+    const float tl = __shfl_sync(FULL, acc, 4);
+    return __fadd_rn(tl, __fadd_rn(__fadd_rn(p0, p2), __fadd_rn(p1, p3)));
 }
 
 __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restrict__ lanes, int prev, int cur) {
@@ -39,6 +109,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
     LkSmem& S = smem[warp];
     const unsigned FULL = 0xffffffffu;
     const float FLT_SCALE = 1.f / (1 << 20);
+    const uint8_t* Pb = reinterpret_cast<const uint8_t*>(&S.P[0][0]);
+    const uint8_t* Jb = reinterpret_cast<const uint8_t*>(&S.J[0][0]);
 
     const float2 pt = L.kp[pidx];
     float nx = 0.f, ny = 0.f;                          // nextPts[ptidx]
@@ -61,72 +133,73 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
         }
         int w00, w01, w10, w11;
         lk_weights(px - (float)ipx, py - (float)ipy, w00, w01, w10, w11);
+        qx -= 7.f; qy -= 7.f;
 
         __syncwarp();
-        // ---- stage the prev patch (always inside image + reflect-101 frame)
-        for (int i = lane; i < LK_PP * LK_PP; i += 32) {
-            int r = i / LK_PP, c = i - r * LK_PP;
-            S.P[r][c] = I.base[(ptrdiff_t)(ipy - 1 + r) * I.pitch + (ipx - 1 + c)];
+        // ---- stage the template patch and the search region (aligned 32-bit loads, one round trip)
+        const int px0 = (ipx - 1) & ~3, pofs = (ipx - 1) - px0;            // patch column offset 0..3
+        int jx0 = 0, jy0 = 0;
+        {
+            const int inx = (int)floorf(qx), iny = (int)floorf(qy);
+            jx0 = min(max((inx - 8) & ~3, -VS_PAD), Jl.w + VS_PAD - LK_JR);
+            jy0 = min(max(iny - 8, -VS_PAD), Jl.h + VS_PAD - LK_JR);
+            for (int i = lane; i < LK_PP * (LK_PW / 4); i += 32) {
+                int r = i / (LK_PW / 4), c = i - r * (LK_PW / 4);
+                S.P[r][c] = *reinterpret_cast<const uint32_t*>(I.base + (ptrdiff_t)(ipy - 1 + r) * I.pitch + px0 + 4 * c);
+            }
+            const uint32_t* jr = reinterpret_cast<const uint32_t*>(Jl.base + (ptrdiff_t)(jy0 + lane) * Jl.pitch + jx0);
+#pragma unroll
+            for (int c = 0; c < LK_JR / 4; ++c) S.J[lane][c] = jr[c];
         }
         __syncwarp();
         // ---- Scharr derivatives on the 16x16 support; the derivative plane is ZERO outside the image
-        for (int i = lane; i < LK_JP * LK_JP; i += 32) {
+        for (int i = lane; i < 256; i += 32) {
             int r = i >> 4, c = i & 15;
             int gx = 0, gy = 0;
             int ix = ipx + c, iy = ipy + r;
             if (ix >= 0 && ix < I.w && iy >= 0 && iy < I.h) {
-                int p00 = S.P[r][c], p01 = S.P[r][c + 1], p02 = S.P[r][c + 2];
-                int p10 = S.P[r + 1][c], p12 = S.P[r + 1][c + 2];
-                int p20 = S.P[r + 2][c], p21 = S.P[r + 2][c + 1], p22 = S.P[r + 2][c + 2];
+                const uint8_t* p0 = Pb + r * LK_PW + c + pofs;
+                int p00 = p0[0], p01 = p0[1], p02 = p0[2];
+                int p10 = p0[LK_PW], p12 = p0[LK_PW + 2];
+                int p20 = p0[2 * LK_PW], p21 = p0[2 * LK_PW + 1], p22 = p0[2 * LK_PW + 2];
                 gx = 3 * (p02 - p00) + 10 * (p12 - p10) + 3 * (p22 - p20);
                 gy = 3 * (p20 - p00) + 10 * (p21 - p01) + 3 * (p22 - p02);
             }
             S.D[r][c] = make_short2((short)gx, (short)gy);
         }
         __syncwarp();
-        // ---- interpolated template window
+        // ---- interpolated template window + covariance terms
+        unsigned abs11 = 0, abs12 = 0, abs22 = 0;
+        int s11 = 0, s12 = 0, s22 = 0;
         for (int p = lane; p < LK_NPIX; p += 32) {
             int y = p / VS_WIN, x = p - y * VS_WIN;
-            int iv = S.P[y + 1][x + 1] * w00 + S.P[y + 1][x + 2] * w01 + S.P[y + 2][x + 1] * w10 + S.P[y + 2][x + 2] * w11;
+            const uint8_t* q0 = Pb + (y + 1) * LK_PW + x + 1 + pofs;
+            int iv = q0[0] * w00 + q0[1] * w01 + q0[LK_PW] * w10 + q0[LK_PW + 1] * w11;
             short2 d00 = S.D[y][x], d01 = S.D[y][x + 1], d10 = S.D[y + 1][x], d11 = S.D[y + 1][x + 1];
-            int gx = d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11;
-            int gy = d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11;
+            int gx = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + 8192) >> 14;
+            int gy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + 8192) >> 14;
             S.Iw[p] = (short)((iv + 256) >> 9);
-            S.dI[p] = make_short2((short)((gx + 8192) >> 14), (short)((gy + 8192) >> 14));
+            S.dI[p] = make_short2((short)gx, (short)gy);
+            int t11 = gx * gx, t12 = gx * gy, t22 = gy * gy;
+            s11 += t11; s12 += t12; s22 += t22;
+            abs11 += (unsigned)t11; abs12 += (unsigned)abs(t12); abs22 += (unsigned)t22;
+            const bool tail = x >= 8;
+            S.term[0][p] = tail ? __float_as_int(__int2float_rn(t11)) : t11;
+            S.term[1][p] = tail ? __float_as_int(__int2float_rn(t12)) : t12;
+            S.term[2][p] = tail ? __float_as_int(__int2float_rn(t22)) : t22;
         }
         __syncwarp();
-        // ---- covariance, ordered chains: lane c<15 -> sum k=c/5 (A11,A12,A22), chain j=c%5
-        //      (j<4: SIMD lane j sees x=j then x=j+4 of each row; j==4: scalar tail x=8..14)
-        float acc = 0.f;
-        if (lane < 15) {
-            const int k = lane / 5, j = lane - 5 * k;
-            for (int y = 0; y < VS_WIN; ++y) {
-                if (j < 4) {
-#pragma unroll
-                    for (int hh = 0; hh < 8; hh += 4) {
-                        short2 d = S.dI[y * VS_WIN + j + hh];
-                        int pr = (k == 0) ? d.x * d.x : (k == 1) ? d.x * d.y : d.y * d.y;
-                        acc = __fadd_rn(__int2float_rn(pr), acc);
-                    }
-                } else {
-#pragma unroll
-                    for (int x = 8; x < VS_WIN; ++x) {
-                        short2 d = S.dI[y * VS_WIN + x];
-                        int pr = (k == 0) ? d.x * d.x : (k == 1) ? d.x * d.y : d.y * d.y;
-                        acc = __fadd_rn(acc, __int2float_rn(pr));
-                    }
-                }
-            }
-        }
         float A[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float q0 = __shfl_sync(FULL, acc, 5 * k + 0), q1 = __shfl_sync(FULL, acc, 5 * k + 1);
-            float q2 = __shfl_sync(FULL, acc, 5 * k + 2), q3 = __shfl_sync(FULL, acc, 5 * k + 3);
-            float t = __shfl_sync(FULL, acc, 5 * k + 4);
-            A[k] = __fmul_rn(__fadd_rn(t, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3))), FLT_SCALE);
+        {
+            const int b11 = __reduce_add_sync(FULL, clamp_abs_sum(abs11));
+            const int b12 = __reduce_add_sync(FULL, clamp_abs_sum(abs12));
+            const int b22 = __reduce_add_sync(FULL, clamp_abs_sum(abs22));
+            const int e11 = __reduce_add_sync(FULL, s11), e12 = __reduce_add_sync(FULL, s12), e22 = __reduce_add_sync(FULL, s22);
+            A[0] = (b11 <= (1 << 24)) ? (float)e11 : ordered_sum<true>(S.term[0], lane);
+            A[1] = (b12 <= (1 << 24)) ? (float)e12 : ordered_sum<true>(S.term[1], lane);
+            A[2] = (b22 <= (1 << 24)) ? (float)e22 : ordered_sum<true>(S.term[2], lane);
         }
-        const float A11 = A[0], A12 = A[1], A22 = A[2];
+        const float A11 = __fmul_rn(A[0], FLT_SCALE), A12 = __fmul_rn(A[1], FLT_SCALE), A22 = __fmul_rn(A[2], FLT_SCALE);
         float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         float dd = __fsub_rn(A11, A22);
         float minEig = __fdiv_rn(
@@ -138,7 +211,6 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
             continue;
         }
         Dt = __fdiv_rn(1.f, Dt);
-        qx -= 7.f; qy -= 7.f;
         float pdx = 0.f, pdy = 0.f;
         for (int j = 0; j < 20; ++j) {
             const int inx = (int)floorf(qx), iny = (int)floorf(qy);
@@ -147,47 +219,44 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
                 break;
             }
             lk_weights(qx - (float)inx, qy - (float)iny, w00, w01, w10, w11);
-            __syncwarp();
-            for (int i = lane; i < LK_JP * LK_JP; i += 32) {
-                int r = i >> 4, c = i & 15;
-                S.J[r][c] = Jl.base[(ptrdiff_t)(iny + r) * Jl.pitch + (inx + c)];
+            if (inx < jx0 || inx + 16 > jx0 + LK_JR || iny < jy0 || iny + 16 > jy0 + LK_JR) {
+                // the window left the staged region: re-centre it (rare)
+                __syncwarp();
+                jx0 = min(max((inx - 8) & ~3, -VS_PAD), Jl.w + VS_PAD - LK_JR);
+                jy0 = min(max(iny - 8, -VS_PAD), Jl.h + VS_PAD - LK_JR);
+                const uint32_t* jr = reinterpret_cast<const uint32_t*>(Jl.base + (ptrdiff_t)(jy0 + lane) * Jl.pitch + jx0);
+#pragma unroll
+                for (int c = 0; c < LK_JR / 4; ++c) S.J[lane][c] = jr[c];
+                __syncwarp();
             }
-            __syncwarp();
+            const uint8_t* jb = Jb + (iny - jy0) * LK_JR + (inx - jx0);
+            int sx = 0, sy = 0;
+            unsigned absx = 0, absy = 0;
             for (int p = lane; p < LK_NPIX; p += 32) {
                 int y = p / VS_WIN, x = p - y * VS_WIN;
-                int jv = S.J[y][x] * w00 + S.J[y][x + 1] * w01 + S.J[y + 1][x] * w10 + S.J[y + 1][x + 1] * w11;
-                S.diff[p] = ((jv + 256) >> 9) - (int)S.Iw[p];
+                const uint8_t* q0 = jb + y * LK_JR + x;
+                int jv = q0[0] * w00 + q0[1] * w01 + q0[LK_JR] * w10 + q0[LK_JR + 1] * w11;
+                int diff = ((jv + 256) >> 9) - (int)S.Iw[p];
+                short2 g = S.dI[p];
+                int tx = diff * g.x, ty = diff * g.y;
+                sx += tx; sy += ty;
+                absx += (unsigned)abs(tx); absy += (unsigned)abs(ty);
+                const bool tail = x >= 8;
+                S.term[0][p] = tail ? __float_as_int(__int2float_rn(tx)) : tx;
+                S.term[1][p] = tail ? __float_as_int(__int2float_rn(ty)) : ty;
             }
-            __syncwarp();
-            // ---- mismatch vector, ordered chains: lanes 0..7 = (v=lane>>2, l=lane&3) pair sums of
-            //      pixels x=2v+(l>>1) and x+4, component l&1; lanes 8,9 = scalar tails (gx, gy)
-            float bacc = 0.f;
-            if (lane < 8) {
-                const int x0 = 2 * (lane >> 2) + ((lane & 3) >> 1), comp = lane & 1;
-                for (int y = 0; y < VS_WIN; ++y) {
-                    int i0 = y * VS_WIN + x0;
-                    short2 g0 = S.dI[i0], g1 = S.dI[i0 + 4];
-                    int v = S.diff[i0] * (comp ? g0.y : g0.x) + S.diff[i0 + 4] * (comp ? g1.y : g1.x);
-                    bacc = __fadd_rn(bacc, __int2float_rn(v));
-                }
-            } else if (lane < 10) {
-                const int comp = lane - 8;
-                for (int y = 0; y < VS_WIN; ++y) {
-#pragma unroll
-                    for (int x = 8; x < VS_WIN; ++x) {
-                        int i0 = y * VS_WIN + x;
-                        short2 g = S.dI[i0];
-                        bacc = __fadd_rn(bacc, __int2float_rn(S.diff[i0] * (comp ? g.y : g.x)));
-                    }
-                }
+            const int bx = __reduce_add_sync(FULL, clamp_abs_sum(absx)), by = __reduce_add_sync(FULL, clamp_abs_sum(absy));
+            const int ex = __reduce_add_sync(FULL, sx), ey = __reduce_add_sync(FULL, sy);
+            float ib1, ib2;
+            if (bx <= (1 << 24) && by <= (1 << 24)) {
+                ib1 = (float)ex; ib2 = (float)ey;
+            } else {
+                __syncwarp();
+                ib1 = ordered_sum_b(S.term[0], lane);
+                ib2 = ordered_sum_b(S.term[1], lane);
+                __syncwarp();
             }
-            float hi = __shfl_down_sync(FULL, bacc, 4);
-            float qs = __fadd_rn(bacc, hi);                      // lanes 0..3: qb0 + qb1
-            float qs0 = __shfl_sync(FULL, qs, 0), qs1 = __shfl_sync(FULL, qs, 1);
-            float qs2 = __shfl_sync(FULL, qs, 2), qs3 = __shfl_sync(FULL, qs, 3);
-            float s1 = __shfl_sync(FULL, bacc, 8), s2 = __shfl_sync(FULL, bacc, 9);
-            float b1 = __fmul_rn(__fadd_rn(s1, __fadd_rn(qs0, qs2)), FLT_SCALE);
-            float b2 = __fmul_rn(__fadd_rn(s2, __fadd_rn(qs1, qs3)), FLT_SCALE);
+            float b1 = __fmul_rn(ib1, FLT_SCALE), b2 = __fmul_rn(ib2, FLT_SCALE);
             float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
             float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt);
             qx = __fadd_rn(qx, ddx); qy = __fadd_rn(qy, ddy);

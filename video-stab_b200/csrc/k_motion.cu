@@ -12,6 +12,7 @@
 #define MO_THREADS 1024
 #define MO_MAXP 2048                 // key-point capacity handled in shared memory
 #define MO_BATCH 32                  // hypotheses per round
+#define MO_TAIL 128                  // trajectory entries staged in shared memory for the sequential part
 
 struct MoSmem {
     float2 from[MO_MAXP];
@@ -25,6 +26,8 @@ struct MoSmem {
     unsigned long long rng;
     int n, niters, iter, max_good, best_found, cont;
     float gk[512];                   // gaussian kernel taps
+    float tail_path[3 * MO_TAIL];
+    float tail_trf[3 * MO_TAIL];
 };
 
 static __device__ __forceinline__ unsigned rng_next(unsigned long long& s) {
@@ -64,23 +67,32 @@ static __device__ int ransac_update_iters(double p, double ep, int max_iters) {
     return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
 }
 
+// Trajectory view used by the sequential smoothing code: element i of transforms_/path_ lives at
+// p[3*(i-base)+c].  In the motion kernel the last MO_TAIL entries are staged in shared memory in
+// parallel first, so the one-thread float32 replay never waits on a global-memory round trip.
+struct Traj {
+    const float* p;
+    int base;
+    __device__ __forceinline__ float at(int i, int c) const { return p[3 * (i - base) + c]; }
+};
+
 // ---- scalar float32 helpers restating the reference's host arithmetic (one thread) -----------------
 static __device__ float f_sqrt(float x) { return __fsqrt_rn(x); }
 static __device__ float f_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
 
-static __device__ int adaptive_radius(const float* path, int n, int smoothing_radius) {
+static __device__ int adaptive_radius(const Traj path, int n, int smoothing_radius) {
     // calculateAdaptiveRadius, Stabilizer.cpp:1637-1673
     if (n < 10) return smoothing_radius;
     int start = max(0, n - 20);
     float cnt = (float)(n - start);
     float mx = 0.f, my = 0.f, ma = 0.f;
     for (int i = start; i < n; ++i) {
-        mx = __fadd_rn(mx, path[3 * i]); my = __fadd_rn(my, path[3 * i + 1]); ma = __fadd_rn(ma, path[3 * i + 2]);
+        mx = __fadd_rn(mx, path.at(i, 0)); my = __fadd_rn(my, path.at(i, 1)); ma = __fadd_rn(ma, path.at(i, 2));
     }
     mx = __fdiv_rn(mx, cnt); my = __fdiv_rn(my, cnt); ma = __fdiv_rn(ma, cnt);
     float vx = 0.f, vy = 0.f, va = 0.f;
     for (int i = start; i < n; ++i) {
-        float dx = __fsub_rn(path[3 * i], mx), dy = __fsub_rn(path[3 * i + 1], my), da = __fsub_rn(path[3 * i + 2], ma);
+        float dx = __fsub_rn(path.at(i, 0), mx), dy = __fsub_rn(path.at(i, 1), my), da = __fsub_rn(path.at(i, 2), ma);
         vx = __fadd_rn(vx, __fmul_rn(dx, dx)); vy = __fadd_rn(vy, __fmul_rn(dy, dy)); va = __fadd_rn(va, __fmul_rn(da, da));
     }
     vx = __fdiv_rn(vx, cnt); vy = __fdiv_rn(vy, cnt); va = __fdiv_rn(va, cnt);
@@ -88,13 +100,13 @@ static __device__ int adaptive_radius(const float* path, int n, int smoothing_ra
     return (int)fmaxf(5.0f, fminf(25.0f, __fmul_rn(total, 2.0f)));
 }
 
-static __device__ float box_at(const float* path, int comp, int n, int radius, int i) {
+static __device__ float box_at(const Traj path, int comp, int n, int radius, int i) {
     // boxFilterConvolve (normal mode), Stabilizer.cpp:1139-1172 — only element i is ever consumed
     int r = max(2, min(radius, 8));
-    if (n <= r) return path[3 * i + comp];
+    if (n <= r) return path.at(i, comp);
     int lo = max(0, i - r), hi = min(n - 1, i + r);
     float s = 0.f;
-    for (int j = lo; j <= hi; ++j) s = __fadd_rn(s, path[3 * j + comp]);
+    for (int j = lo; j <= hi; ++j) s = __fadd_rn(s, path.at(j, comp));
     return __fdiv_rn(s, (float)(hi - lo + 1));
 }
 
@@ -118,7 +130,7 @@ static __device__ float consistency_f(const float* v, int n) {
     return fmaxf(0.f, fminf(1.f, c));
 }
 
-static __device__ int motion_intent(const float* tr, int n_tr, const float* motion, int idx) {
+static __device__ int motion_intent(const Traj tr, int n_tr, const float* motion, int idx) {
     // analyzeMotionIntent, Stabilizer.cpp:1676-1719
     float mag = f_sqrt(__fadd_rn(__fmul_rn(motion[0], motion[0]), __fmul_rn(motion[1], motion[1])));
     float ang = (float)((double)__fmul_rn(fabsf(motion[2]), 180.0f) / 3.14159265358979323846 * (double)30.0f);
@@ -127,7 +139,7 @@ static __device__ int motion_intent(const float* tr, int n_tr, const float* moti
         int c = 0;
         for (int i = max(0, idx - 15); i < idx; ++i) {
             if (i < n_tr) {
-                float tx = tr[3 * i], ty = tr[3 * i + 1];
+                float tx = tr.at(i, 0), ty = tr.at(i, 1);
                 mags[c] = f_sqrt(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)));
                 dirs[c] = f_atan2(ty, tx);
                 ++c;
@@ -165,7 +177,7 @@ void warp_params_from_T(const float* T, WarpParams* wp) {
 
 // Smoothing + intent + matrix for the frame being emitted.  Runs on one thread (sequential float32
 // arithmetic in the reference's order); S.gk is scratch for the gaussian taps.
-static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, float* gk) {
+static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, float* gk, Traj path, Traj trf) {
     const int i = info.pop_index, n = info.path_len_at_pop;
     vs_output_record rec;
     rec.index = i; rec.passthrough = 0; rec.path_len = n; rec.radius = 0; rec.intent = 0;
@@ -180,7 +192,6 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
         if (info.n_out < L.record_capacity) L.orec[info.n_out] = rec;
         return;
     }
-    const float* path = L.path;
     float sm[3];
     bool have = false;
     if (info.method == 1) {                                 // gaussianFilterConvolve :1364-1413
@@ -188,6 +199,7 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
         int ksz = max(3, (int)ceilf(__fmul_rn(6.f, sigma)));
         if ((ksz & 1) == 0) ++ksz;
         int c = ksz / 2;
+        if (i - c < path.base) { path.p = L.path; path.base = 0; }      // window reaches below the staged tail
         if (n > c && ksz <= 512) {
             float tot = 0.f;
             for (int j = 0; j < ksz; ++j) {
@@ -203,9 +215,9 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
                 for (int j = 0; j < ksz; ++j) {
                     int q = i + j;                          // index into the padded array
                     float v;
-                    if (q < c) v = path[3 * (c - q) + comp];
-                    else if (q < c + n) v = path[3 * (q - c) + comp];
-                    else v = path[3 * (n - 1 - (q - c - n)) + comp];
+                    if (q < c) v = (c - q >= path.base) ? path.at(c - q, comp) : L.path[3 * (c - q) + comp];
+                    else if (q < c + n) v = path.at(q - c, comp);
+                    else v = path.at(n - 1 - (q - c - n), comp);
                     s = __fadd_rn(s, __fmul_rn(v, gk[j]));
                 }
                 sm[comp] = s;
@@ -215,7 +227,7 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
     } else if (info.method == 2) {                          // kalmanFilterSmooth :1416-1458, incremental
         for (int comp = 0; comp < 3; ++comp) {
             float* ks = L.kalman + 6 * comp;                // x0 x1 P00 P01 P10 P11
-            float z = path[3 * i + comp];
+            float z = path.at(i, comp);
             if (i == 0) {
                 ks[0] = z; ks[1] = 0.f; ks[2] = ks[3] = ks[4] = ks[5] = 0.f;
                 sm[comp] = z;
@@ -244,12 +256,12 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
     }
     float raw[3], diff[3];
     for (int k = 0; k < 3; ++k) {
-        raw[k] = L.transforms[3 * i + k];
-        diff[k] = __fsub_rn(sm[k], path[3 * i + k]);
+        raw[k] = trf.at(i, k);
+        diff[k] = __fsub_rn(sm[k], path.at(i, k));
         rec.smoothed[k] = sm[k];
     }
     if (i > 0) {                                            // :854-888
-        rec.intent = motion_intent(L.transforms, n, raw, i);
+        rec.intent = motion_intent(trf, n, raw, i);
         float sc = rec.intent == 1 ? 0.5f : rec.intent == 2 ? 1.0f : rec.intent == 3 ? 0.8f : 0.7f;
         for (int k = 0; k < 3; ++k) diff[k] = __fmul_rn(diff[k], sc);
     }
@@ -266,7 +278,8 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
 
 __global__ void __launch_bounds__(32) k_smooth_only(const LaneDev* __restrict__ lanes, StepInfo info) {
     __shared__ float gk[512];
-    if (threadIdx.x == 0) smooth_and_setup(lanes[blockIdx.z], info, gk);
+    const LaneDev& L = lanes[blockIdx.z];
+    if (threadIdx.x == 0) smooth_and_setup(L, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0});
 }
 
 __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict__ lanes, StepInfo info) {
@@ -283,6 +296,12 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         lprev = L.log_prev + o; lnext = L.log_next + o; lstat = L.log_status + o; lmask = L.log_mask + o;
     }
 
+    // ---- stage the tail of the trajectory (entries written by earlier steps) for the sequential part
+    const int tail_base = max(0, fidx + 1 - MO_TAIL);
+    for (int i = tid; i < 3 * (fidx - tail_base); i += MO_THREADS) {
+        S.tail_path[i] = L.path[3 * tail_base + i];
+        S.tail_trf[i] = L.transforms[3 * tail_base + i];
+    }
     // ---- order-preserving compaction of the tracked pairs (status != 0)
     int running = 0;
     for (int base = 0; base < n_prev; base += MO_THREADS) {
@@ -438,7 +457,9 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         float* pa = L.path + 3 * fidx;
         for (int k = 0; k < 3; ++k) {
             tr[k] = t[k];
-            pa[k] = fidx == 0 ? t[k] : __fadd_rn(L.path[3 * (fidx - 1) + k], t[k]);
+            pa[k] = fidx == 0 ? t[k] : __fadd_rn(S.tail_path[3 * (fidx - 1 - tail_base) + k], t[k]);
+            S.tail_trf[3 * (fidx - tail_base) + k] = t[k];
+            S.tail_path[3 * (fidx - tail_base) + k] = pa[k];
         }
         if (fidx < L.record_capacity) {
             vs_frame_record& r = L.frec[fidx];
@@ -456,7 +477,11 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
             L.kalman[VS_KAL_RADIUS_SLOT] = __int_as_float(nr);   // adaptive radius hand-off to the host
         }
         __threadfence_block();
-        if (info.pop_index >= 0) smooth_and_setup(L, info, S.gk);
+        if (info.pop_index >= 0) {
+            const bool in_tail = info.pop_index - 20 >= tail_base || tail_base == 0;
+            if (in_tail) smooth_and_setup(L, info, S.gk, Traj{S.tail_path, tail_base}, Traj{S.tail_trf, tail_base});
+            else smooth_and_setup(L, info, S.gk, Traj{L.path, 0}, Traj{L.transforms, 0});
+        }
     }
 }
 

@@ -5,6 +5,7 @@
 // position, 15-bit bilinear weights.  HBM-bound: algorithmic traffic is one read + one write of the
 // frame (2*3*W*H bytes).
 #include "kernels.h"
+#include <climits>
 
 // Source coordinate of one output pixel, exactly as cv::warpAffine computes it:
 //   adelta[x] = rint(M0*x*1024), X0 = rint((M1*y+M2)*1024) + 16, X = (X0 + adelta[x]) >> 5
@@ -78,6 +79,209 @@ static __device__ __forceinline__ void warp_pixel(const uint8_t* __restrict__ sr
     out[2] = (uint8_t)((acc2 + 512) >> 10);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled fast path (plain warp, mode 0).  One CTA = one 128x32 output tile:
+//   1. the exact source bounding box of the tile is derived from its four corners (the fixed-point
+//      coordinate is monotone in x and in y), widened to 4-pixel (12-byte) groups;
+//   2. the box is staged into shared memory with coalesced 32-bit loads (a warp reads 384 contiguous
+//      bytes per 3 instructions) and re-packed on the fly to 4-byte BGRx pixels, one conflict-free
+//      STS.128 per lane; rows/columns outside the frame are staged as zeros, which IS
+//      cv::BORDER_CONSTANT(0), so the inner loop has no border logic at all;
+//   3. lane l produces pixels x0+l+32j (consecutive lanes -> consecutive shared-memory words, no bank
+//      conflicts): 4 aligned LDS.32 taps, byte gathers with PRMT, horizontal pass on DP4A (weights
+//      32-ax, ax), vertical pass on IMAD with the weight pre-scaled by 64 so the rounded 8-bit result
+//      sits in byte 2 of the accumulator ((acc+512)>>10 without a shift);
+//   4. the 128x32x3 output tile is staged in shared memory and written once with 128-bit stores.
+// Tiles whose source box does not fit (large rotations) or whose coordinates approach the int16
+// saturation of cv::remap fall back to the per-pixel path, CTA-uniformly.
+#define WT_W 128
+#define WT_H 32
+#define WT_PITCH 144                 // fixed source-tile row pitch in BGRx words (128 + rotation slack + alignment)
+#define WT_ROWS 42                   // source-tile row capacity  (144*42*4 = 24 KB)
+#define WT_THREADS 256
+#define WT_STAGE_IT 6                // staging tasks per thread (36 groups x 42 rows <= 6 x 256)
+
+struct WarpTileSmem {
+    uint32_t src[WT_PITCH * WT_ROWS];
+    uint32_t out[WT_H * WT_W];           // 16 KB, BGRx
+    int2 rowXY[WT_H];
+    int2 colAB[WT_W];
+    int box[6];                          // ax0, by0, ngrp, nrows, ok, unused
+};
+
+static __device__ __forceinline__ void warp_tile(WarpTileSmem& S, const uint8_t* __restrict__ src, int sw, int sh,
+                                                 size_t sstride, uint8_t* __restrict__ dst, int dw, int dh,
+                                                 size_t dstride, const double* __restrict__ m, bool src_vec, bool dst_vec) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * WT_W, y0 = blockIdx.y * WT_H;
+    const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5];
+
+    // fixed-point row/column terms of cv::warpAffine, one per thread; columns beyond the frame reuse the
+    // last valid column so that their (discarded) taps stay inside the staged box
+    if (tid < WT_W) {
+        double xd = (double)min(x0 + tid, dw - 1);
+        S.colAB[tid] = make_int2(sat_int(m0 * xd * 1024.0), sat_int(m3 * xd * 1024.0));
+    } else if (tid < WT_W + WT_H) {
+        double yd = (double)min(y0 + tid - WT_W, dh - 1);
+        S.rowXY[tid - WT_W] = make_int2(sat_int((m1 * yd + m2) * 1024.0) + 16, sat_int((m4 * yd + m5) * 1024.0) + 16);
+    } else if (tid == WT_W + WT_H) {
+        const int xa = x0, xb = min(x0 + WT_W, dw) - 1, ya = y0, yb = min(y0 + WT_H, dh) - 1;
+        int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double xd = (double)((c & 1) ? xb : xa), yd = (double)((c & 2) ? yb : ya);
+            int X = (sat_int((m1 * yd + m2) * 1024.0) + 16 + sat_int(m0 * xd * 1024.0)) >> 10;
+            int Y = (sat_int((m4 * yd + m5) * 1024.0) + 16 + sat_int(m3 * xd * 1024.0)) >> 10;
+            minx = min(minx, X); maxx = max(maxx, X); miny = min(miny, Y); maxy = max(maxy, Y);
+        }
+        int ax0 = minx & ~3;                                   // floor to a 4-pixel group (also for negatives)
+        int ngrp = (maxx + 1 - ax0) / 4 + 1;
+        int nrows = maxy + 2 - miny;
+        bool ok = minx > -30000 && maxx < 30000 && miny > -30000 && maxy < 30000 &&
+                  ngrp * 4 <= WT_PITCH && nrows <= WT_ROWS && ngrp > 0 && nrows > 0;
+        S.box[0] = ax0; S.box[1] = miny; S.box[2] = ngrp; S.box[3] = nrows; S.box[4] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    const int ax0 = S.box[0], by0 = S.box[1], ngrp = S.box[2], nrows = S.box[3];
+    if (!S.box[4]) {
+        // generic per-pixel path for this tile
+        for (int i = tid; i < WT_W * WT_H; i += WT_THREADS) {
+            int x = x0 + (i & (WT_W - 1)), y = y0 + i / WT_W;
+            if (x < dw && y < dh) warp_pixel<false>(src, sw, sh, sstride, m, 0, 0, x, y, dst + (size_t)y * dstride + 3 * x);
+        }
+        return;
+    }
+    // ---- stage the source box as BGRx: one task = 4 pixels = 12 source bytes -> one 16-byte store.
+    //      All of a thread's loads are issued before the first one is consumed (one memory round trip).
+    {
+        const int ntask = ngrp * nrows;                          // <= 36 * 42 = 1512 <= 6 * 256
+        const float inv = 1.0f / (float)ngrp;
+        uint32_t w0[WT_STAGE_IT], w1[WT_STAGE_IT], w2[WT_STAGE_IT];
+        int mode[WT_STAGE_IT];                                   // 0 zero, 1 fast (loaded), 2 edge (per-pixel)
+#pragma unroll
+        for (int k = 0; k < WT_STAGE_IT; ++k) {
+            const int t = tid + k * WT_THREADS;
+            mode[k] = 0; w0[k] = w1[k] = w2[k] = 0u;
+            if (t < ntask) {
+                const int r = __float2int_rd(((float)t + 0.5f) * inv);   // t / ngrp (exact for these ranges)
+                const int q = t - r * ngrp;
+                const int gx = ax0 + 4 * q, gy = by0 + r;
+                if ((unsigned)gy < (unsigned)sh) {
+                    if (gx >= 0 && gx + 4 <= sw && src_vec) {
+                        const uint32_t* gw = reinterpret_cast<const uint32_t*>(src + (size_t)gy * sstride + 3 * gx);
+                        w0[k] = __ldg(gw); w1[k] = __ldg(gw + 1); w2[k] = __ldg(gw + 2);
+                        mode[k] = 1;
+                    } else if (gx + 4 > 0 && gx < sw) {
+                        mode[k] = 2;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < WT_STAGE_IT; ++k) {
+            const int t = tid + k * WT_THREADS;
+            if (t < ntask) {
+                const int r = __float2int_rd(((float)t + 0.5f) * inv);
+                const int q = t - r * ngrp;
+                uint4 o;
+                o.x = w0[k];                                    // [B0 G0 R0 --]
+                o.y = __byte_perm(w0[k], w1[k], 0x0543);        // [B1 G1 R1 --]
+                o.z = __byte_perm(w1[k], w2[k], 0x0432);        // [B2 G2 R2 --]
+                o.w = w2[k] >> 8;                               // [B3 G3 R3 --]
+                if (mode[k] == 2) {
+                    const int gx = ax0 + 4 * q, gy = by0 + r;
+                    const uint8_t* g = src + (size_t)gy * sstride + 3 * gx;
+                    uint32_t v[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        v[c] = 0u;
+                        if ((unsigned)(gx + c) < (unsigned)sw) {
+                            const uint8_t* p = g + 3 * c;
+                            v[c] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+                        }
+                    }
+                    o = make_uint4(v[0], v[1], v[2], v[3]);
+                }
+                *reinterpret_cast<uint4*>(S.src + r * WT_PITCH + 4 * q) = o;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- compute: warp -> rows, lane -> pixels x0 + lane + 32 j
+    int ad[4], bd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int2 c = S.colAB[lane + 32 * j];
+        ad[j] = c.x - (ax0 << 10);                               // fold the box origin into the fixed-point terms
+        bd[j] = c.y - (by0 << 10);
+    }
+    for (int rr = warp; rr < WT_H; rr += WT_THREADS / 32) {
+        if (y0 + rr >= dh) break;
+        const int2 xy = S.rowXY[rr];
+        uint32_t* const orow = S.out + rr * WT_W + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t1 = xy.x + ad[j], t2 = xy.y + bd[j];
+            const int sx = t1 >> 10, sy = t2 >> 10;              // box-relative integer source coordinates
+            const uint32_t ax = (uint32_t)(t1 >> 5) & 31u;
+            const uint32_t wy1 = ((uint32_t)t2 << 1) & 0x7c0u;   // ay * 64
+            const uint32_t wy0 = 2048u - wy1;                    // (32 - ay) * 64
+            const uint32_t* p = S.src + sy * WT_PITCH + sx;
+            const uint32_t t00 = p[0], t01 = p[1], t10 = p[WT_PITCH], t11 = p[WT_PITCH + 1];
+            const uint32_t Wa = __byte_perm(32u - ax, ax, 0x7740);   // bytes [32-ax, ax, 0, 0]
+            const uint32_t Wb = Wa << 16;                            // bytes [0, 0, 32-ax, ax]
+            const uint32_t u0 = __byte_perm(t00, t01, 0x5140);   // [b00 b01 g00 g01]
+            const uint32_t u1 = __byte_perm(t00, t01, 0x5162);   // [r00 r01 ..]
+            const uint32_t l0 = __byte_perm(t10, t11, 0x5140);
+            const uint32_t l1 = __byte_perm(t10, t11, 0x5162);
+            const uint32_t hb0 = __dp4a(u0, Wa, 0u), hg0 = __dp4a(u0, Wb, 0u), hr0 = __dp4a(u1, Wa, 0u);
+            const uint32_t hb1 = __dp4a(l0, Wa, 0u), hg1 = __dp4a(l0, Wb, 0u), hr1 = __dp4a(l1, Wa, 0u);
+            const uint32_t vb = hb0 * wy0 + (hb1 * wy1 + 32768u);     // (acc + 512) << 6 : result in byte 2
+            const uint32_t vg = hg0 * wy0 + (hg1 * wy1 + 32768u);
+            const uint32_t vr = hr0 * wy0 + (hr1 * wy1 + 32768u);
+            orow[32 * j] = __byte_perm(__byte_perm(vb, vg, 0x0062), vr, 0x0610);   // [B G R --]
+        }
+    }
+    __syncthreads();
+    // ---- write the tile once: one task = 4 pixels -> 12 packed bytes
+    const int tw = min(WT_W, dw - x0), th = min(WT_H, dh - y0);
+    if (dst_vec && tw == WT_W) {
+        for (int i = tid; i < th * (WT_W / 4); i += WT_THREADS) {
+            const int r = i >> 5, c = i & 31;
+            const uint4 v = *reinterpret_cast<const uint4*>(S.out + r * WT_W + 4 * c);
+            uint32_t* g = reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r) * dstride + (size_t)x0 * 3) + 3 * c;
+            g[0] = __byte_perm(v.x, v.y, 0x4210);            // B0 G0 R0 B1
+            g[1] = __byte_perm(v.y, v.z, 0x5421);            // G1 R1 B2 G2
+            g[2] = __byte_perm(v.z, v.w, 0x6542);            // R2 B3 G3 R3
+        }
+    } else {
+        for (int i = tid; i < th * tw; i += WT_THREADS) {
+            int r = i / tw, c = i - r * tw;
+            uint32_t v = S.out[r * WT_W + c];
+            uint8_t* g = dst + (size_t)(y0 + r) * dstride + (size_t)(x0 + c) * 3;
+            g[0] = (uint8_t)v; g[1] = (uint8_t)(v >> 8); g[2] = (uint8_t)(v >> 16);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 5) k_warp_tiled_lanes(const LaneDev* __restrict__ lanes, PtrPack src, MutPtrPack dst,
+                                                                  WarpGeom g, int src_vec, int dst_vec) {
+    __shared__ WarpTileSmem S;
+    warp_tile(S, src.p[blockIdx.z], g.src_w, g.src_h, g.src_stride, dst.p[blockIdx.z], g.out_w, g.out_h, g.out_stride,
+              lanes[blockIdx.z].wp->m, src_vec != 0, dst_vec != 0);
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 5) k_warp_tiled_frames(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride,
+                                                                   size_t sframe, uint8_t* __restrict__ dst, int dw, int dh,
+                                                                   size_t dstride, size_t dframe,
+                                                                   const WarpParams* __restrict__ wps, int src_vec, int dst_vec) {
+    __shared__ WarpTileSmem S;
+    warp_tile(S, src + blockIdx.z * sframe, sw, sh, sstride, dst + blockIdx.z * dframe, dw, dh, dstride,
+              wps[blockIdx.z].m, src_vec != 0, dst_vec != 0);
+}
+
+static inline bool vec_ok(const void* p, size_t stride, int a) { return ((uintptr_t)p % a == 0) && (stride % a == 0); }
+
 template <bool BORDER>
 __global__ void __launch_bounds__(256) k_warp_lanes(const LaneDev* __restrict__ lanes, PtrPack src, MutPtrPack dst, WarpGeom g) {
     const WarpParams* wp = lanes[blockIdx.z].wp;
@@ -98,6 +302,17 @@ __global__ void __launch_bounds__(256) k_warp_frames(const uint8_t* __restrict__
     warp_pixel<false>(src + blockIdx.z * sframe, sw, sh, sstride, wps[blockIdx.z].m, 0, 0, x, y, o);
 }
 
+static void launch_warp_plain(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, const WarpGeom& g,
+                              cudaStream_t st) {
+    bool sv = true, dv = true;
+    for (int i = 0; i < n_lanes; ++i) {
+        sv = sv && vec_ok(src.p[i], g.src_stride, 4);
+        dv = dv && vec_ok(dst.p[i], g.out_stride, 4);
+    }
+    dim3 grid((g.out_w + WT_W - 1) / WT_W, (g.out_h + WT_H - 1) / WT_H, n_lanes);
+    k_warp_tiled_lanes<<<grid, WT_THREADS, 0, st>>>(lanes, src, dst, g, sv ? 1 : 0, dv ? 1 : 0);
+}
+
 void launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, WarpGeom g,
                  uint8_t* const* scratch, cudaStream_t st) {
     if (g.mode == 2) {
@@ -107,24 +322,26 @@ void launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const Mu
         for (int i = 0; i < n_lanes; ++i) tmp.p[i] = scratch[i];
         WarpGeom g1 = g;
         g1.mode = 0; g1.out_w = g.src_w; g1.out_h = g.src_h; g1.out_stride = (size_t)g.src_w * 3;
-        dim3 grid((g1.out_w + 63) / 64, (g1.out_h + 3) / 4, n_lanes);
-        k_warp_lanes<false><<<grid, 256, 0, st>>>(lanes, src, tmp, g1);
+        launch_warp_plain(lanes, n_lanes, src, tmp, g1, st);
         int b = g.border, cw = g.src_w - 2 * b, ch = g.src_h - 2 * b;
         for (int i = 0; i < n_lanes; ++i)
             launch_resize_linear(scratch[i] + (size_t)b * g1.out_stride + 3 * b, cw, ch, g1.out_stride, 3,
                                  dst.p[i], g.out_w, g.out_h, g.out_stride, st);
         return;
     }
-    dim3 grid((g.out_w + 63) / 64, (g.out_h + 3) / 4, n_lanes);
-    if (g.mode == 1)
+    if (g.mode == 1) {
+        dim3 grid((g.out_w + 63) / 64, (g.out_h + 3) / 4, n_lanes);
         k_warp_lanes<true><<<grid, 256, 0, st>>>(lanes, src, dst, g);
-    else
-        k_warp_lanes<false><<<grid, 256, 0, st>>>(lanes, src, dst, g);
+    } else {
+        launch_warp_plain(lanes, n_lanes, src, dst, g, st);
+    }
 }
 
 void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe,
                           uint8_t* dst, int dw, int dh, size_t dstride, size_t dframe,
                           const WarpParams* d_wp, int n_frames, cudaStream_t st) {
-    dim3 grid((dw + 63) / 64, (dh + 3) / 4, n_frames);
-    k_warp_frames<<<grid, 256, 0, st>>>(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp);
+    const bool sv = vec_ok(src, sstride, 4) && sframe % 4 == 0, dv = vec_ok(dst, dstride, 4) && dframe % 4 == 0;
+    dim3 grid((dw + WT_W - 1) / WT_W, (dh + WT_H - 1) / WT_H, n_frames);
+    k_warp_tiled_frames<<<grid, WT_THREADS, 0, st>>>(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp,
+                                                     sv ? 1 : 0, dv ? 1 : 0);
 }
