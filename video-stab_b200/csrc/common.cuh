@@ -55,6 +55,7 @@ struct LaneDev {
     uint8_t* inlier_mask;
     float* transforms;              // 3 floats per frame  (transforms_)
     float* path;                    // 3 floats per frame  (path_)
+    float* aux;                     // 2 floats per frame: |t| and atan2(ty,tx) of each transform (motion-intent terms)
     float* kalman;                  // 3 x {x0,x1,P00,P01,P10,P11} incremental Kalman state
     vs_frame_record* frec;
     vs_output_record* orec;

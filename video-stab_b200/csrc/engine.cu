@@ -178,6 +178,7 @@ vs_status Engine::alloc_fixed() {
         // trajectory + records: separately tracked so they can grow
         CUDA_TRY(cudaMalloc((void**)&L.transforms, (size_t)traj_cap_ * 3 * sizeof(float)));
         CUDA_TRY(cudaMalloc((void**)&L.path, (size_t)traj_cap_ * 3 * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&L.aux, (size_t)traj_cap_ * 2 * sizeof(float)));
         CUDA_TRY(cudaMalloc((void**)&L.frec, (size_t)traj_cap_ * sizeof(vs_frame_record)));
         CUDA_TRY(cudaMalloc((void**)&L.orec, (size_t)traj_cap_ * sizeof(vs_output_record)));
         L.kp_capacity = kp_cap_;
@@ -193,19 +194,21 @@ vs_status Engine::grow_trajectory() {
     int ncap = traj_cap_ * 2;
     for (int l = 0; l < n_lanes_; ++l) {
         LaneDev& L = h_lanes_[l];
-        float *t = nullptr, *pa = nullptr;
+        float *t = nullptr, *pa = nullptr, *ax = nullptr;
         vs_frame_record* fr = nullptr;
         vs_output_record* orr = nullptr;
         CUDA_TRY(cudaMalloc((void**)&t, (size_t)ncap * 3 * sizeof(float)));
         CUDA_TRY(cudaMalloc((void**)&pa, (size_t)ncap * 3 * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&ax, (size_t)ncap * 2 * sizeof(float)));
         CUDA_TRY(cudaMalloc((void**)&fr, (size_t)ncap * sizeof(vs_frame_record)));
         CUDA_TRY(cudaMalloc((void**)&orr, (size_t)ncap * sizeof(vs_output_record)));
         CUDA_TRY(cudaMemcpy(t, L.transforms, (size_t)traj_cap_ * 3 * sizeof(float), cudaMemcpyDeviceToDevice));
         CUDA_TRY(cudaMemcpy(pa, L.path, (size_t)traj_cap_ * 3 * sizeof(float), cudaMemcpyDeviceToDevice));
+        CUDA_TRY(cudaMemcpy(ax, L.aux, (size_t)traj_cap_ * 2 * sizeof(float), cudaMemcpyDeviceToDevice));
         CUDA_TRY(cudaMemcpy(fr, L.frec, (size_t)traj_cap_ * sizeof(vs_frame_record), cudaMemcpyDeviceToDevice));
         CUDA_TRY(cudaMemcpy(orr, L.orec, (size_t)traj_cap_ * sizeof(vs_output_record), cudaMemcpyDeviceToDevice));
-        cudaFree(L.transforms); cudaFree(L.path); cudaFree(L.frec); cudaFree(L.orec);
-        L.transforms = t; L.path = pa; L.frec = fr; L.orec = orr;
+        cudaFree(L.transforms); cudaFree(L.path); cudaFree(L.aux); cudaFree(L.frec); cudaFree(L.orec);
+        L.transforms = t; L.path = pa; L.aux = ax; L.frec = fr; L.orec = orr;
         L.record_capacity = ncap;
     }
     traj_cap_ = ncap;
@@ -219,7 +222,7 @@ void Engine::free_all() {
     for (cudaEvent_t ev : event_pool_) cudaEventDestroy(ev);
     event_pool_.clear();
     for (auto& L : h_lanes_) {
-        cudaFree(L.transforms); cudaFree(L.path); cudaFree(L.frec); cudaFree(L.orec);
+        cudaFree(L.transforms); cudaFree(L.path); cudaFree(L.aux); cudaFree(L.frec); cudaFree(L.orec);
     }
     h_lanes_.clear();
     for (void* p : allocs_) cudaFree(p);

@@ -15,7 +15,7 @@
 #define EIG_TH 16
 #define SEL_THREADS 1024
 #define SEL_CHUNK_MAX 4096
-#define SEL_CHUNK_FIRST 1024
+#define SEL_CHUNK_FIRST 960
 
 static __device__ __forceinline__ GrayLevel gftt_src(const LaneDev& L, int slot) {
     return slot < 0 ? L.small0 : L.pyr[slot].lv[0];
@@ -180,58 +180,88 @@ static __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
 }
 
 // The order-dependent min-distance pass of cv::goodFeaturesToTrack over m sorted candidates, run by
-// one warp 32 candidates at a time: every lane tests its candidate against the accepted set in the 3x3
-// neighbouring grid cells in parallel; conflicts INSIDE the batch are resolved in rank order with ballots.
+// one warp 32 candidates at a time (a single warp is latency-bound, so the pass is written to be
+// branch-free and shallow):
+//   1. every lane tests its candidate against the corners accepted so far: 9 grid cells x 4 slots,
+//      slots pre-filled with a far-away sentinel so no counts are read and nothing branches;
+//   2. conflicts INSIDE the batch: each lane builds, once, the bit mask of earlier lanes closer than
+//      minDistance; the rank-ordered greedy outcome is then the fixed point of a few ballot rounds
+//      (a lane is accepted when no earlier undecided lane conflicts with it, rejected when an accepted
+//      one does) - exactly the sequential result, without walking the lanes one by one;
+//   3. accepted lanes append themselves in rank order (ballot prefix) and enter the grid.
+// `sxy` / `scell` hold, per sorted candidate, (x | y << 16) and the grid cell index, computed in
+// parallel by the whole CTA beforehand (all integer divisions live there).
+#define GRID_EMPTY 0x40004000u      // sentinel slot: x = y = 16384, never within minDistance of a real pixel (no int overflow)
 template <bool SMEM_GRID>
-static __device__ bool greedy_pass(const LaneDev& L, const unsigned long long* skeys, int m, int w, int cell, int gw,
-                                   int gh, bool use_grid, double md2, int cap, unsigned int* gcount,
-                                   unsigned int* gslot, int& accepted_io) {
+static __device__ bool greedy_pass(const LaneDev& L, const unsigned* sxy, const int* scell, int m, int gw, int gh,
+                                   bool use_grid, int imd2, int cap, unsigned int* gcount, unsigned int* gslot,
+                                   int& accepted_io) {
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x;
+    const unsigned lt = (1u << lane) - 1u;
     int accepted = accepted_io;
     bool stop = false;
     for (int base = 0; base < m && !stop; base += 32) {
         bool ok = base + lane < m;
-        unsigned addr = ok ? (unsigned)(skeys[base + lane] & 0xffffffffull) : 0u;
-        int y = addr / w, x = addr - y * w;
-        if (ok && use_grid) {
-            int cx = x / cell, cy = y / cell;
-            int xa = max(cx - 1, 0), xb = min(cx + 1, gw - 1), ya = max(cy - 1, 0), yb = min(cy + 1, gh - 1);
-            for (int yy = ya; yy <= yb && ok; ++yy)
-                for (int xx = xa; xx <= xb && ok; ++xx) {
-                    int ci = yy * gw + xx;
-                    unsigned cnt = SMEM_GRID ? gcount[ci] : __ldcg(&gcount[ci]);
-                    for (unsigned s = 0; s < cnt; ++s) {
-                        unsigned q = SMEM_GRID ? gslot[ci * VS_GRID_SLOTS + s] : __ldcg(&gslot[(size_t)ci * VS_GRID_SLOTS + s]);
-                        int dx = x - (int)(q & 0xffffu), dy = y - (int)(q >> 16);
-                        if ((double)(dx * dx + dy * dy) < md2) { ok = false; break; }
+        const unsigned xy = ok ? sxy[base + lane] : GRID_EMPTY;
+        const int ci = ok ? scell[base + lane] : 0;
+        const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+        unsigned cmask = 0u;
+        if (use_grid) {
+            const int cy = ci / gw, cx = ci - cy * gw;
+            bool hit = false;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = min(max(cy + dy, 0), gh - 1);
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int xx = min(max(cx + dx, 0), gw - 1);
+                    const int c2 = yy * gw + xx;
+                    uint4 q;
+                    if (SMEM_GRID) q = *reinterpret_cast<const uint4*>(gslot + c2 * VS_GRID_SLOTS);
+                    else q = __ldcg(reinterpret_cast<const uint4*>(gslot + (size_t)c2 * VS_GRID_SLOTS));
+                    const unsigned qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const int ddx = x - (int)(qq[s] & 0xffffu), ddy = y - (int)(qq[s] >> 16);
+                        hit |= (ddx * ddx + ddy * ddy) < imd2;
                     }
                 }
+            }
+            ok = ok && !hit;
+            // earlier lanes of this batch closer than minDistance
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const unsigned o = __shfl_sync(FULL, xy, k);
+                const int ddx = x - (int)(o & 0xffffu), ddy = y - (int)(o >> 16);
+                if ((ddx * ddx + ddy * ddy) < imd2) cmask |= 1u << k;
+            }
+            cmask &= lt;
         }
-        unsigned pending = __ballot_sync(0xffffffffu, ok);
-        while (pending) {
-            int leader = __ffs(pending) - 1;
-            int lx = __shfl_sync(0xffffffffu, x, leader), ly = __shfl_sync(0xffffffffu, y, leader);
-            if (lane == leader) {
-                L.kp[accepted] = make_float2((float)lx, (float)ly);
-                if (use_grid) {
-                    int ci = (ly / cell) * gw + (lx / cell);
-                    unsigned c = SMEM_GRID ? gcount[ci] : __ldcg(&gcount[ci]);
-                    if (c < VS_GRID_SLOTS) {
-                        unsigned v = (unsigned)lx | ((unsigned)ly << 16);
-                        if (SMEM_GRID) { gslot[ci * VS_GRID_SLOTS + c] = v; gcount[ci] = c + 1; }
-                        else { __stcg(&gslot[(size_t)ci * VS_GRID_SLOTS + c], v); __stcg(&gcount[ci], c + 1); }
-                    }
+        unsigned undecided = __ballot_sync(FULL, ok);
+        unsigned acc = 0u;
+        while (undecided) {
+            const unsigned now = __ballot_sync(FULL, ok && (cmask & undecided) == 0u);
+            acc |= now;
+            if (ok && (((now >> lane) & 1u) || (cmask & acc))) ok = false;
+            undecided = __ballot_sync(FULL, ok);
+        }
+        // cap: keep only the first (cap - accepted) of this batch in rank order
+        int room = cap - accepted;
+        int rank = __popc(acc & lt);
+        const bool mine = ((acc >> lane) & 1u) && rank < room;
+        if (mine) {
+            L.kp[accepted + rank] = make_float2((float)x, (float)y);
+            if (use_grid) {
+                unsigned slot = atomicAdd(&gcount[ci], 1u);
+                if (slot < VS_GRID_SLOTS) {
+                    if (SMEM_GRID) gslot[ci * VS_GRID_SLOTS + slot] = xy;
+                    else __stcg(&gslot[(size_t)ci * VS_GRID_SLOTS + slot], xy);
                 }
-                ok = false;
             }
-            ++accepted;
-            if (accepted >= cap) { stop = true; break; }
-            if (ok && use_grid) {
-                int dx = x - lx, dy = y - ly;
-                if ((double)(dx * dx + dy * dy) < md2) ok = false;
-            }
-            pending = __ballot_sync(0xffffffffu, ok);
         }
+        accepted += min(__popc(acc), room);
+        if (accepted >= cap) stop = true;
         if (!SMEM_GRID) __threadfence_block();
         __syncwarp();
     }
@@ -249,7 +279,9 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     extern __shared__ unsigned long long sel_dyn[];
     unsigned long long* skeys = sel_dyn;                                        // SEL_CHUNK_MAX keys
     unsigned int* hist = reinterpret_cast<unsigned int*>(sel_dyn + SEL_CHUNK_MAX);   // SEL_BINS
-    unsigned int* sgrid = hist + SEL_BINS;                                      // SEL_GRID_CELLS * (1 + slots)
+    unsigned int* sgrid = hist + SEL_BINS;                                      // SEL_GRID_CELLS * (slots + 1)
+    unsigned int* sxy = sgrid + SEL_GRID_CELLS * (1 + VS_GRID_SLOTS);           // SEL_CHUNK_MAX packed (x | y << 16)
+    int* scell = reinterpret_cast<int*>(sxy + SEL_CHUNK_MAX);                   // SEL_CHUNK_MAX grid cell indices
     __shared__ SelSmem S;
     const LaneDev& L = lanes[blockIdx.z];
     const GrayLevel G = gftt_src(L, slot);
@@ -262,10 +294,16 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
     const double md2 = min_dist * min_dist;
     const bool smem_grid = gw * gh <= SEL_GRID_CELLS;
-    unsigned int* gcount = smem_grid ? sgrid : L.grid;
-    unsigned int* gslot = gcount + (smem_grid ? SEL_GRID_CELLS : gw * gh);
+    // grid layout: [slots: cells x 4 (16-byte aligned)] [counts: cells]
+    unsigned int* gslot = smem_grid ? sgrid : L.grid;
+    unsigned int* gcount = gslot + (size_t)(smem_grid ? SEL_GRID_CELLS : gw * gh) * VS_GRID_SLOTS;
+    const int imd2 = (int)ceil(md2);             // integer d2 < md2  <=>  d2 < ceil(md2)
     if (use_grid)
-        for (int i = tid; i < gw * gh; i += SEL_THREADS) gcount[i] = 0u;
+        for (int i = tid; i < gw * gh; i += SEL_THREADS) {
+            gcount[i] = 0u;
+            if (smem_grid) *reinterpret_cast<uint4*>(gslot + i * VS_GRID_SLOTS) = make_uint4(GRID_EMPTY, GRID_EMPTY, GRID_EMPTY, GRID_EMPTY);
+            else __stcg(reinterpret_cast<uint4*>(gslot + (size_t)i * VS_GRID_SLOTS), make_uint4(GRID_EMPTY, GRID_EMPTY, GRID_EMPTY, GRID_EMPTY));
+        }
     for (int i = tid; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0u;
     if (tid == 0) { S.accepted = 0; S.done = 0; }
 
@@ -346,10 +384,17 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
         }
         __syncthreads();
         bitonic_sort_desc(skeys, npad);
+        for (int i = tid; i < m; i += SEL_THREADS) {       // unpack coordinates / cells in parallel
+            const unsigned addr = (unsigned)(skeys[i] & 0xffffffffull);
+            const int y = addr / w, x = addr - y * w;
+            sxy[i] = (unsigned)x | ((unsigned)y << 16);
+            scell[i] = use_grid ? (y / cell) * gw + (x / cell) : 0;
+        }
+        __syncthreads();
         if (tid < 32) {
             int accepted = S.accepted;
-            bool stop = smem_grid ? greedy_pass<true>(L, skeys, m, w, cell, gw, gh, use_grid, md2, cap, gcount, gslot, accepted)
-                                  : greedy_pass<false>(L, skeys, m, w, cell, gw, gh, use_grid, md2, cap, gcount, gslot, accepted);
+            bool stop = smem_grid ? greedy_pass<true>(L, sxy, scell, m, gw, gh, use_grid, imd2, cap, gcount, gslot, accepted)
+                                  : greedy_pass<false>(L, sxy, scell, m, gw, gh, use_grid, imd2, cap, gcount, gslot, accepted);
             if (lane == 0) { S.accepted = accepted; S.done = stop ? 1 : 0; }
         }
         __syncthreads();
@@ -375,7 +420,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
 }
 
 #define SEL_DYN_BYTES (SEL_CHUNK_MAX * sizeof(unsigned long long) + SEL_BINS * sizeof(unsigned int) + \
-                       SEL_GRID_CELLS * (1 + VS_GRID_SLOTS) * sizeof(unsigned int))
+                       SEL_GRID_CELLS * (1 + VS_GRID_SLOTS) * sizeof(unsigned int) + SEL_CHUNK_MAX * 2 * sizeof(unsigned int))
 
 size_t gftt_grid_words(int w, int h, double min_dist) {
     if (min_dist < 1.0) return 8;

@@ -28,6 +28,8 @@ struct MoSmem {
     float gk[512];                   // gaussian kernel taps
     float tail_path[3 * MO_TAIL];
     float tail_trf[3 * MO_TAIL];
+    float tail_aux[2 * MO_TAIL];
+    unsigned long long fastmod_M;
 };
 
 static __device__ __forceinline__ unsigned rng_next(unsigned long long& s) {
@@ -74,6 +76,7 @@ struct Traj {
     const float* p;
     int base;
     __device__ __forceinline__ float at(int i, int c) const { return p[3 * (i - base) + c]; }
+    __device__ __forceinline__ float at2(int i, int c) const { return p[2 * (i - base) + c]; }   // aux rows
 };
 
 // ---- scalar float32 helpers restating the reference's host arithmetic (one thread) -----------------
@@ -130,18 +133,18 @@ static __device__ float consistency_f(const float* v, int n) {
     return fmaxf(0.f, fminf(1.f, c));
 }
 
-static __device__ int motion_intent(const Traj tr, int n_tr, const float* motion, int idx) {
-    // analyzeMotionIntent, Stabilizer.cpp:1676-1719
-    float mag = f_sqrt(__fadd_rn(__fmul_rn(motion[0], motion[0]), __fmul_rn(motion[1], motion[1])));
+static __device__ int motion_intent(const Traj aux, int n_tr, const float* motion, int idx) {
+    // analyzeMotionIntent, Stabilizer.cpp:1676-1719.  |t| and atan2(ty,tx) of every transform were
+    // computed once when it was appended (pure functions of the transform), so this is loads + adds.
+    float mag = aux.at2(idx, 0);
     float ang = (float)((double)__fmul_rn(fabsf(motion[2]), 180.0f) / 3.14159265358979323846 * (double)30.0f);
     if (n_tr >= 15) {
         float mags[15], dirs[15];
         int c = 0;
         for (int i = max(0, idx - 15); i < idx; ++i) {
             if (i < n_tr) {
-                float tx = tr.at(i, 0), ty = tr.at(i, 1);
-                mags[c] = f_sqrt(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)));
-                dirs[c] = f_atan2(ty, tx);
+                mags[c] = aux.at2(i, 0);
+                dirs[c] = aux.at2(i, 1);
                 ++c;
             }
         }
@@ -177,7 +180,7 @@ void warp_params_from_T(const float* T, WarpParams* wp) {
 
 // Smoothing + intent + matrix for the frame being emitted.  Runs on one thread (sequential float32
 // arithmetic in the reference's order); S.gk is scratch for the gaussian taps.
-static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, float* gk, Traj path, Traj trf) {
+static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, float* gk, Traj path, Traj trf, Traj aux) {
     const int i = info.pop_index, n = info.path_len_at_pop;
     vs_output_record rec;
     rec.index = i; rec.passthrough = 0; rec.path_len = n; rec.radius = 0; rec.intent = 0;
@@ -261,7 +264,7 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
         rec.smoothed[k] = sm[k];
     }
     if (i > 0) {                                            // :854-888
-        rec.intent = motion_intent(trf, n, raw, i);
+        rec.intent = motion_intent(aux, n, raw, i);
         float sc = rec.intent == 1 ? 0.5f : rec.intent == 2 ? 1.0f : rec.intent == 3 ? 0.8f : 0.7f;
         for (int k = 0; k < 3; ++k) diff[k] = __fmul_rn(diff[k], sc);
     }
@@ -279,7 +282,7 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
 __global__ void __launch_bounds__(32) k_smooth_only(const LaneDev* __restrict__ lanes, StepInfo info) {
     __shared__ float gk[512];
     const LaneDev& L = lanes[blockIdx.z];
-    if (threadIdx.x == 0) smooth_and_setup(L, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0});
+    if (threadIdx.x == 0) smooth_and_setup(L, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
 }
 
 __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict__ lanes, StepInfo info) {
@@ -302,6 +305,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         S.tail_path[i] = L.path[3 * tail_base + i];
         S.tail_trf[i] = L.transforms[3 * tail_base + i];
     }
+    for (int i = tid; i < 2 * (fidx - tail_base); i += MO_THREADS) S.tail_aux[i] = L.aux[2 * tail_base + i];
     // ---- order-preserving compaction of the tracked pairs (status != 0)
     int running = 0;
     for (int base = 0; base < n_prev; base += MO_THREADS) {
@@ -333,22 +337,25 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
     if (tid == 0) {
         S.n = n; S.niters = VS_RANSAC_MAX_ITERS; S.iter = 0; S.max_good = 0; S.best_found = 0;
         S.rng = 0xFFFFFFFFFFFFFFFFull; S.cont = (n_prev > 0 && n >= 4) ? 1 : 0;
+        S.fastmod_M = n > 0 ? 0xFFFFFFFFFFFFFFFFull / (unsigned)n + 1ull : 0ull;      // Lemire: r % n without a divide
     }
     __syncthreads();
+    int batch = 8;               // the sequential loop usually stops after a handful of hypotheses
 
     // ---- RANSAC: rounds of 32 hypotheses, warp per hypothesis, sequential replay of the stop rule
     while (S.cont) {
         if (tid == 0) {
             unsigned long long r = S.rng;
-            for (int h = 0; h < MO_BATCH; ++h) {
-                int i0 = (int)(rng_next(r) % (unsigned)n), i1;
-                do { i1 = (int)(rng_next(r) % (unsigned)n); } while (i1 == i0);
+            const unsigned long long M = S.fastmod_M;
+            for (int h = 0; h < batch; ++h) {
+                int i0 = (int)__umul64hi(M * rng_next(r), (unsigned long long)n), i1;
+                do { i1 = (int)__umul64hi(M * rng_next(r), (unsigned long long)n); } while (i1 == i0);
                 S.idx[h][0] = i0; S.idx[h][1] = i1;
             }
             S.rng = r;
         }
         __syncthreads();
-        {
+        if (warp < batch) {
             double M[6];
             float F[6];
             int i0 = S.idx[warp][0], i1 = S.idx[warp][1];
@@ -365,7 +372,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         __syncthreads();
         if (tid == 0) {
             int iter = S.iter, niters = S.niters, max_good = S.max_good, adv = 0, best = -1;
-            for (int h = 0; h < MO_BATCH && iter < niters; ++h, ++iter, ++adv) {
+            for (int h = 0; h < batch && iter < niters; ++h, ++iter, ++adv) {
                 int g = S.good[h];
                 if (g > max(max_good, 1)) {
                     max_good = g; best = h;
@@ -385,6 +392,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
             S.cont = (iter < niters) ? 1 : 0;
         }
         __syncthreads();
+        batch = MO_BATCH;
     }
 
     // ---- inlier mask of the winning hypothesis + least-squares similarity refit (double)
@@ -461,6 +469,12 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
             S.tail_trf[3 * (fidx - tail_base) + k] = t[k];
             S.tail_path[3 * (fidx - tail_base) + k] = pa[k];
         }
+        {
+            const float mag = f_sqrt(__fadd_rn(__fmul_rn(t[0], t[0]), __fmul_rn(t[1], t[1])));
+            const float dir = f_atan2(t[1], t[0]);
+            L.aux[2 * fidx] = mag; L.aux[2 * fidx + 1] = dir;
+            S.tail_aux[2 * (fidx - tail_base)] = mag; S.tail_aux[2 * (fidx - tail_base) + 1] = dir;
+        }
         if (fidx < L.record_capacity) {
             vs_frame_record& r = L.frec[fidx];
             r.frame_index = info.frame_no; r.n_prev_pts = n_prev; r.n_tracked = n;
@@ -479,8 +493,8 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         __threadfence_block();
         if (info.pop_index >= 0) {
             const bool in_tail = info.pop_index - 20 >= tail_base || tail_base == 0;
-            if (in_tail) smooth_and_setup(L, info, S.gk, Traj{S.tail_path, tail_base}, Traj{S.tail_trf, tail_base});
-            else smooth_and_setup(L, info, S.gk, Traj{L.path, 0}, Traj{L.transforms, 0});
+            if (in_tail) smooth_and_setup(L, info, S.gk, Traj{S.tail_path, tail_base}, Traj{S.tail_trf, tail_base}, Traj{S.tail_aux, tail_base});
+            else smooth_and_setup(L, info, S.gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
         }
     }
 }
