@@ -99,11 +99,13 @@ static __device__ __forceinline__ void warp_pixel(const uint8_t* __restrict__ sr
 #define WT_PITCH 144                 // fixed source-tile row pitch in BGRx words (128 + rotation slack + alignment)
 #define WT_ROWS 42                   // source-tile row capacity  (144*42*4 = 24 KB)
 #define WT_THREADS 256
-#define WT_STAGE_IT 6                // staging tasks per thread (36 groups x 42 rows <= 6 x 256)
+#define WT_GRPS 36                   // 4-pixel column groups of the staged box (= WT_PITCH / 4)
+#define WT_SROWS 7                   // staging rows in flight: 36 x 7 = 252 threads
+#define WT_STAGE_IT 6                // staging tasks per thread (42 rows / 7)
 
 struct WarpTileSmem {
     uint32_t src[WT_PITCH * WT_ROWS];
-    uint32_t out[WT_H * WT_W];           // 16 KB, BGRx
+    uint32_t out[(WT_THREADS / 32) * WT_W];   // one BGRx output row per warp (4 KB)
     int2 rowXY[WT_H];
     int2 colAB[WT_W];
     int box[6];                          // ax0, by0, ngrp, nrows, ok, unused
@@ -152,57 +154,52 @@ static __device__ __forceinline__ void warp_tile(WarpTileSmem& S, const uint8_t*
         return;
     }
     // ---- stage the source box as BGRx: one task = 4 pixels = 12 source bytes -> one 16-byte store.
-    //      All of a thread's loads are issued before the first one is consumed (one memory round trip).
+    //      Fixed 2-D thread map: 36 column groups x 7 rows (252 of 256 threads), each thread walks down
+    //      its column 7 rows at a time; all its loads are issued before the first is consumed.
     {
-        const int ntask = ngrp * nrows;                          // <= 36 * 42 = 1512 <= 6 * 256
-        const float inv = 1.0f / (float)ngrp;
-        uint32_t w0[WT_STAGE_IT], w1[WT_STAGE_IT], w2[WT_STAGE_IT];
-        int mode[WT_STAGE_IT];                                   // 0 zero, 1 fast (loaded), 2 edge (per-pixel)
+        const bool interior = src_vec && ax0 >= 0 && ax0 + 4 * ngrp <= sw && by0 >= 0 && by0 + nrows <= sh;
+        const int r7 = tid / WT_GRPS, q = tid - r7 * WT_GRPS;    // constant divisor
+        const bool colok = q < ngrp && r7 < WT_SROWS;
+        if (interior) {
+            uint32_t w0[WT_STAGE_IT], w1[WT_STAGE_IT], w2[WT_STAGE_IT];
+            const uint32_t* gw = reinterpret_cast<const uint32_t*>(src + (size_t)(by0 + r7) * sstride + (size_t)(3 * ax0)) + 3 * q;
+            const size_t gstep = (size_t)WT_SROWS * sstride / 4;
 #pragma unroll
-        for (int k = 0; k < WT_STAGE_IT; ++k) {
-            const int t = tid + k * WT_THREADS;
-            mode[k] = 0; w0[k] = w1[k] = w2[k] = 0u;
-            if (t < ntask) {
-                const int r = __float2int_rd(((float)t + 0.5f) * inv);   // t / ngrp (exact for these ranges)
-                const int q = t - r * ngrp;
-                const int gx = ax0 + 4 * q, gy = by0 + r;
-                if ((unsigned)gy < (unsigned)sh) {
-                    if (gx >= 0 && gx + 4 <= sw && src_vec) {
-                        const uint32_t* gw = reinterpret_cast<const uint32_t*>(src + (size_t)gy * sstride + 3 * gx);
-                        w0[k] = __ldg(gw); w1[k] = __ldg(gw + 1); w2[k] = __ldg(gw + 2);
-                        mode[k] = 1;
-                    } else if (gx + 4 > 0 && gx < sw) {
-                        mode[k] = 2;
-                    }
+            for (int k = 0; k < WT_STAGE_IT; ++k) {
+                if (colok && r7 + k * WT_SROWS < nrows) {
+                    w0[k] = __ldg(gw); w1[k] = __ldg(gw + 1); w2[k] = __ldg(gw + 2);
                 }
+                gw += gstep;
             }
-        }
+            uint32_t* d = S.src + r7 * WT_PITCH + 4 * q;
 #pragma unroll
-        for (int k = 0; k < WT_STAGE_IT; ++k) {
-            const int t = tid + k * WT_THREADS;
-            if (t < ntask) {
-                const int r = __float2int_rd(((float)t + 0.5f) * inv);
-                const int q = t - r * ngrp;
-                uint4 o;
-                o.x = w0[k];                                    // [B0 G0 R0 --]
-                o.y = __byte_perm(w0[k], w1[k], 0x0543);        // [B1 G1 R1 --]
-                o.z = __byte_perm(w1[k], w2[k], 0x0432);        // [B2 G2 R2 --]
-                o.w = w2[k] >> 8;                               // [B3 G3 R3 --]
-                if (mode[k] == 2) {
-                    const int gx = ax0 + 4 * q, gy = by0 + r;
+            for (int k = 0; k < WT_STAGE_IT; ++k) {
+                if (colok && r7 + k * WT_SROWS < nrows) {
+                    uint4 o;
+                    o.x = w0[k];                                    // [B0 G0 R0 --]
+                    o.y = __byte_perm(w0[k], w1[k], 0x0543);        // [B1 G1 R1 --]
+                    o.z = __byte_perm(w1[k], w2[k], 0x0432);        // [B2 G2 R2 --]
+                    o.w = w2[k] >> 8;                               // [B3 G3 R3 --]
+                    *reinterpret_cast<uint4*>(d) = o;
+                }
+                d += WT_SROWS * WT_PITCH;
+            }
+        } else if (colok) {
+            // tiles touching the frame border (or unaligned frames): per-pixel, zero outside = BORDER_CONSTANT
+            for (int r = r7; r < nrows; r += WT_SROWS) {
+                const int gx = ax0 + 4 * q, gy = by0 + r;
+                uint32_t v[4] = {0u, 0u, 0u, 0u};
+                if ((unsigned)gy < (unsigned)sh) {
                     const uint8_t* g = src + (size_t)gy * sstride + 3 * gx;
-                    uint32_t v[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        v[c] = 0u;
                         if ((unsigned)(gx + c) < (unsigned)sw) {
-                            const uint8_t* p = g + 3 * c;
-                            v[c] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+                            const uint8_t* pp = g + 3 * c;
+                            v[c] = (uint32_t)pp[0] | ((uint32_t)pp[1] << 8) | ((uint32_t)pp[2] << 16);
                         }
                     }
-                    o = make_uint4(v[0], v[1], v[2], v[3]);
                 }
-                *reinterpret_cast<uint4*>(S.src + r * WT_PITCH + 4 * q) = o;
+                *reinterpret_cast<uint4*>(S.src + r * WT_PITCH + 4 * q) = make_uint4(v[0], v[1], v[2], v[3]);
             }
         }
     }
@@ -215,10 +212,12 @@ static __device__ __forceinline__ void warp_tile(WarpTileSmem& S, const uint8_t*
         ad[j] = c.x - (ax0 << 10);                               // fold the box origin into the fixed-point terms
         bd[j] = c.y - (by0 << 10);
     }
+    const int tw = min(WT_W, dw - x0);
+    const bool vec_out = dst_vec && tw == WT_W;
+    uint32_t* const orow = S.out + warp * WT_W;
     for (int rr = warp; rr < WT_H; rr += WT_THREADS / 32) {
         if (y0 + rr >= dh) break;
         const int2 xy = S.rowXY[rr];
-        uint32_t* const orow = S.out + rr * WT_W + lane;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int t1 = xy.x + ad[j], t2 = xy.y + bd[j];
@@ -239,39 +238,36 @@ static __device__ __forceinline__ void warp_tile(WarpTileSmem& S, const uint8_t*
             const uint32_t vb = hb0 * wy0 + (hb1 * wy1 + 32768u);     // (acc + 512) << 6 : result in byte 2
             const uint32_t vg = hg0 * wy0 + (hg1 * wy1 + 32768u);
             const uint32_t vr = hr0 * wy0 + (hr1 * wy1 + 32768u);
-            orow[32 * j] = __byte_perm(__byte_perm(vb, vg, 0x0062), vr, 0x0610);   // [B G R --]
+            orow[lane + 32 * j] = __byte_perm(__byte_perm(vb, vg, 0x0062), vr, 0x0610);   // [B G R --]
         }
-    }
-    __syncthreads();
-    // ---- write the tile once: one task = 4 pixels -> 12 packed bytes
-    const int tw = min(WT_W, dw - x0), th = min(WT_H, dh - y0);
-    if (dst_vec && tw == WT_W) {
-        for (int i = tid; i < th * (WT_W / 4); i += WT_THREADS) {
-            const int r = i >> 5, c = i & 31;
-            const uint4 v = *reinterpret_cast<const uint4*>(S.out + r * WT_W + 4 * c);
-            uint32_t* g = reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r) * dstride + (size_t)x0 * 3) + 3 * c;
+        __syncwarp();
+        // ---- the warp writes its finished row once: lane -> 4 pixels -> 12 packed bytes, a warp stores
+        //      384 contiguous bytes
+        uint8_t* grow = dst + (size_t)(y0 + rr) * dstride + (size_t)x0 * 3;
+        if (vec_out) {
+            const uint4 v = *reinterpret_cast<const uint4*>(orow + 4 * lane);
+            uint32_t* g = reinterpret_cast<uint32_t*>(grow) + 3 * lane;
             g[0] = __byte_perm(v.x, v.y, 0x4210);            // B0 G0 R0 B1
             g[1] = __byte_perm(v.y, v.z, 0x5421);            // G1 R1 B2 G2
             g[2] = __byte_perm(v.z, v.w, 0x6542);            // R2 B3 G3 R3
+        } else {
+            for (int c = lane; c < tw; c += 32) {
+                const uint32_t v = orow[c];
+                grow[3 * c] = (uint8_t)v; grow[3 * c + 1] = (uint8_t)(v >> 8); grow[3 * c + 2] = (uint8_t)(v >> 16);
+            }
         }
-    } else {
-        for (int i = tid; i < th * tw; i += WT_THREADS) {
-            int r = i / tw, c = i - r * tw;
-            uint32_t v = S.out[r * WT_W + c];
-            uint8_t* g = dst + (size_t)(y0 + r) * dstride + (size_t)(x0 + c) * 3;
-            g[0] = (uint8_t)v; g[1] = (uint8_t)(v >> 8); g[2] = (uint8_t)(v >> 16);
-        }
+        __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(WT_THREADS, 5) k_warp_tiled_lanes(const LaneDev* __restrict__ lanes, PtrPack src, MutPtrPack dst,
+__global__ void __launch_bounds__(WT_THREADS, 6) k_warp_tiled_lanes(const LaneDev* __restrict__ lanes, PtrPack src, MutPtrPack dst,
                                                                   WarpGeom g, int src_vec, int dst_vec) {
     __shared__ WarpTileSmem S;
     warp_tile(S, src.p[blockIdx.z], g.src_w, g.src_h, g.src_stride, dst.p[blockIdx.z], g.out_w, g.out_h, g.out_stride,
               lanes[blockIdx.z].wp->m, src_vec != 0, dst_vec != 0);
 }
 
-__global__ void __launch_bounds__(WT_THREADS, 5) k_warp_tiled_frames(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride,
+__global__ void __launch_bounds__(WT_THREADS, 6) k_warp_tiled_frames(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride,
                                                                    size_t sframe, uint8_t* __restrict__ dst, int dw, int dh,
                                                                    size_t dstride, size_t dframe,
                                                                    const WarpParams* __restrict__ wps, int src_vec, int dst_vec) {
