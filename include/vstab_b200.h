@@ -190,6 +190,23 @@ vs_status vs_stabilizer_launch_count(vs_stabilizer* s, uint64_t* n);
 vs_status vs_stabilizer_set_timing(vs_stabilizer* s, int enable);
 vs_status vs_stabilizer_stage_time(vs_stabilizer* s, int stage, double* total_ms, long long* count);
 
+/* ---- offline clip mode: one temporal chunk of a long clip per handle / GPU (BASELINE config 5) -----------
+ * The reference has no such mode (it is single-stream, single-process); results are defined as "identical to
+ * pushing the whole clip through stabilize()+flush() on one handle".  Motion estimation is pairwise-local, so
+ * a chunk [first, first+count) needs only vs_clip_halo(first) <= 2 leading frames of pixels; the trajectory is
+ * then stitched from ALL chunks' transforms (a few hundred KB: one all-gather) and accumulated in the
+ * reference's sequential float32 order, so every rank's path_ is bit-identical to a single-GPU run.
+ *   vs_clip_analyze: d_frames = frames [first - vs_clip_halo(first), first + count), tight rows, device memory.
+ *                    Writes transforms_[n-1] for n = max(first,1) .. first+count-1 (3 floats each) to host.
+ *   vs_clip_render : all_transforms_host = the n_total-1 transforms of the whole clip; d_frames = frames
+ *                    [first, first+count); d_out = count output frames, tight rows of out_width*3 bytes.
+ * Not available with adaptive_smoothing (the latency gate becomes data dependent). */
+int       vs_clip_halo(int first);
+vs_status vs_clip_analyze(vs_stabilizer* s, const uint8_t* d_frames, int width, int height, int first, int count,
+                          float* transforms_out_host, int* n_out);
+vs_status vs_clip_render(vs_stabilizer* s, const float* all_transforms_host, int n_total, const uint8_t* d_frames,
+                         int width, int height, int first, int count, uint8_t* d_out, int* out_width, int* out_height);
+
 /* ---- multi-stream batch: N independent streams advanced in lock-step, one kernel launch per
  * stage for the whole batch (BASELINE config 4).  Semantically N vs_stabilizers. -------------- */
 typedef struct vs_batch vs_batch;

@@ -75,6 +75,9 @@ SYMBOLS = {
     "vs_stabilizer_stage_time": (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "vs_batch_set_timing": (_I, [_P, _I]),
     "vs_batch_stage_time": (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "vs_clip_halo": (_I, [_I]),
+    "vs_clip_analyze": (_I, [_P, _U8P, _I, _I, _I, _I, _P, _IP]),
+    "vs_clip_render": (_I, [_P, _P, _I, _U8P, _I, _I, _I, _I, _U8P, _IP, _IP]),
     "vs_batch_create": (_I, [C.POINTER(VsParams), _I, _I, C.POINTER(_P)]),
     "vs_batch_destroy": (None, [_P]),
     "vs_batch_push_device": (_I, [_P, C.POINTER(_P), _I, _I, _SZ, C.POINTER(_P), _SZ, _SZ, C.c_uint, _IP, _IP, _IP]),

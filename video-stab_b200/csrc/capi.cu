@@ -301,6 +301,23 @@ vs_status vs_batch_output_record(vs_batch* b, int stream, int i, vs_output_recor
     return b ? b->eng->output_record(stream, i, rec) : vs_set_error(VS_ERR_INVALID_ARG, "null handle");
 }
 
+// ------------------------------------------------------------------------------------ offline clip mode
+int vs_clip_halo(int first) { return Engine::chunk_halo(first); }
+vs_status vs_clip_analyze(vs_stabilizer* s, const uint8_t* d_frames, int width, int height, int first, int count,
+                          float* transforms_out_host, int* n_out) {
+    if (!s) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
+    API_BEGIN
+    return s->eng->analyze_chunk(d_frames, width, height, first, count, transforms_out_host, n_out);
+    API_END
+}
+vs_status vs_clip_render(vs_stabilizer* s, const float* all_transforms_host, int n_total, const uint8_t* d_frames,
+                         int width, int height, int first, int count, uint8_t* d_out, int* out_width, int* out_height) {
+    if (!s || !out_width || !out_height) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    return s->eng->render_chunk(all_transforms_host, n_total, d_frames, width, height, first, count, d_out, out_width, out_height);
+    API_END
+}
+
 // ------------------------------------------------------------------------------------ single kernels
 static vs_status scratch_engine(Engine** e, int max_corners = 200, double min_dist = 1.0) {
     vs_params p;

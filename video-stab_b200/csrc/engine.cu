@@ -230,6 +230,8 @@ void Engine::free_all() {
     if (d_ring_) cudaFree(d_ring_);
     if (d_out_) cudaFree(d_out_);
     if (d_scratch_) cudaFree(d_scratch_);
+    if (d_wp_batch_) cudaFree(d_wp_batch_);
+    d_wp_batch_ = nullptr; wp_batch_cap_ = 0;
     d_ring_ = d_out_ = d_scratch_ = nullptr;
     if (stream_) cudaStreamDestroy(stream_);
     stream_ = nullptr;
@@ -510,5 +512,126 @@ vs_status Engine::first_corners(int lane, float* xy, int cap, int* n) {
     CUDA_TRY(cudaMemcpy(&c, h_lanes_[lane].first_count, sizeof(int), cudaMemcpyDeviceToHost));
     *n = c;
     if (xy && c > 0) CUDA_TRY(cudaMemcpy(xy, h_lanes_[lane].first_corners, sizeof(float2) * (c < cap ? c : cap), cudaMemcpyDeviceToHost));
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------------------ offline clip mode
+// Motion estimation is pairwise-local: transform n needs gray(n-1), gray(n) and the
+// corners detected on the latest even frame <= n-1 (or the first-frame corners while n <= 2).  A chunk
+// starting at `first` therefore needs at most two leading halo frames.
+int Engine::chunk_halo(int first) {
+    if (first <= 2) return first;                    // start from frame 0 (first-frame quirks B-Q1 included)
+    int m = (first - 1) & ~1;                        // frame whose corners transform `first` starts from
+    return first - m;                                // 1 or 2
+}
+
+vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first, int count, float* out_host, int* n_out) {
+    if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "clip mode uses single-lane handles");
+    if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
+    if (!d_frames || first < 0 || count <= 0) return vs_set_error(VS_ERR_INVALID_ARG, "bad chunk");
+    CUDA_TRY(cudaSetDevice(device_));
+    VS_TRY(clean());
+    VS_TRY(ensure_geometry(w, h, false, false, false));
+    while (first + count + 2 >= traj_cap_) VS_TRY(grow_trajectory());
+    const size_t fb = frame_bytes_, tight = (size_t)w * 3;
+    const int halo = chunk_halo(first);
+    const uint8_t* base = d_frames;                  // frame (first - halo)
+    auto entry = [&](int frame_index) {
+        QueueEntry e;
+        e.index = frame_index; e.slot = 0; e.stride = tight;
+        e.frames.assign(1, base + (size_t)(frame_index - (first - halo)) * fb);
+        return e;
+    };
+    int f = first - halo;                            // next frame to feed
+    if (f == 0) {
+        // frame 0: first-frame analysis (Stabilizer.cpp:271-368)
+        PtrPack src; src.p[0] = entry(0).frames[0];
+        launch_gray_resize(d_lanes_, 1, src, w, h, tight, -1, stream_);
+        CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2, stream_));
+        launch_good_features(d_lanes_, 1, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, stream_);
+        launches_ += 4;
+        first_ = false;
+        n_frames_ = 0; detect_counter_ = 0;
+        f = 1;
+    } else {
+        // halo: corners from the even frame m, pyramid of frame first-1
+        const int m = f;
+        PtrPack src; src.p[0] = entry(m).frames[0];
+        launch_gray_resize(d_lanes_, 1, src, w, h, tight, m & 1, stream_);
+        launch_pyrdown(d_lanes_, 1, m & 1, stream_);
+        CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2, stream_));
+        int mc = p_.max_corners < 200 ? p_.max_corners : 200;
+        launch_good_features(d_lanes_, 1, m & 1, mc, 0.02, 15.0, 0, stream_);
+        launches_ += 6;
+        if (first - 1 > m) {
+            PtrPack s2; s2.p[0] = entry(first - 1).frames[0];
+            launch_gray_resize(d_lanes_, 1, s2, w, h, tight, (first - 1) & 1, stream_);
+            launch_pyrdown(d_lanes_, 1, (first - 1) & 1, stream_);
+            launches_ += 3;
+        }
+        first_ = false;
+        n_frames_ = first - 1; detect_counter_ = first - 1;      // the counters equal the frame number
+        f = first;
+    }
+    const int first_tr = f;                          // first generateTransform call computed here
+    for (; f < first + count; ++f) {
+        bool pop = false;
+        QueueEntry e = entry(f);
+        VS_TRY(generate_transform(e, &pop));         // queue_ is empty: never pops
+    }
+    const int n = first + count - first_tr;
+    if (n_out) *n_out = n;
+    if (n > 0 && out_host)
+        CUDA_TRY(cudaMemcpyAsync(out_host, h_lanes_[0].transforms + 3 * (size_t)(first_tr - 1), sizeof(float) * 3 * n,
+                                 cudaMemcpyDeviceToHost, stream_));
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    return VS_OK;
+}
+
+vs_status Engine::render_chunk(const float* all_tr_host, int n_total, const uint8_t* d_frames, int w, int h, int first,
+                               int count, uint8_t* d_out, int* ow, int* oh) {
+    if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "clip mode uses single-lane handles");
+    if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
+    if (!all_tr_host || !d_frames || !d_out || n_total < 1 || first < 0 || count <= 0 || first + count > n_total)
+        return vs_set_error(VS_ERR_INVALID_ARG, "bad chunk");
+    CUDA_TRY(cudaSetDevice(device_));
+    VS_TRY(clean());
+    const int b = p_.border_size;
+    const int mode = b <= 0 ? 0 : (p_.crop_n_zoom ? ((w - 2 * b > 0 && h - 2 * b > 0) ? 2 : 0) : 1);
+    VS_TRY(ensure_geometry(w, h, false, false, mode == 2));
+    while (n_total + 2 >= traj_cap_) VS_TRY(grow_trajectory());
+    const int n_tr = n_total - 1;
+    if (count > wp_batch_cap_) {
+        if (d_wp_batch_) cudaFree(d_wp_batch_);
+        CUDA_TRY(cudaMalloc((void**)&d_wp_batch_, sizeof(WarpParams) * count));
+        wp_batch_cap_ = count;
+    }
+    if (n_tr > 0) {
+        CUDA_TRY(cudaMemcpyAsync(h_lanes_[0].transforms, all_tr_host, sizeof(float) * 3 * n_tr, cudaMemcpyHostToDevice, stream_));
+        launch_traj_build(d_lanes_, 1, n_tr, stream_);
+        launches_ += 1;
+    }
+    n_frames_ = n_tr;
+    const int gate = clampi(smoothing_radius_, 5, 35);
+    const int ow_ = mode == 1 ? w + 2 * b : w, oh_ = mode == 1 ? h + 2 * b : h;
+    *ow = ow_; *oh = oh_;
+    const size_t tight_in = (size_t)w * 3, tight_out = (size_t)ow_ * 3, oframe = tight_out * oh_;
+    // frames with a transform are warped in one batched launch; the clip's last frame has none and is
+    // passed through unchanged (Stabilizer.cpp:774-780)
+    const int n_warp = (first + count == n_total) ? count - 1 : count;
+    if (n_warp > 0) {
+        StepInfo base = step_info(0);
+        launch_smooth_batch(d_lanes_, 1, base, first, n_warp, n_total, gate, d_wp_batch_, stream_);
+        launch_warp_frames_mode(d_frames, w, h, tight_in, frame_bytes_, d_out, tight_out, oframe, d_wp_batch_, n_warp, mode, b,
+                                border_mode_, d_scratch_, stream_);
+        launches_ += 2 + (mode == 2 ? 2 * n_warp - 1 : 0);
+    }
+    if (n_warp < count) {
+        // un-warped original frame, written at the top-left of its output slot (smaller than a bordered frame)
+        CUDA_TRY(cudaMemcpy2DAsync(d_out + oframe * n_warp, tight_out, d_frames + frame_bytes_ * n_warp, tight_in, tight_in, h,
+                                   cudaMemcpyDeviceToDevice, stream_));
+    }
+    n_out_ = n_warp;
+    CUDA_TRY(cudaStreamSynchronize(stream_));
     return VS_OK;
 }

@@ -40,6 +40,16 @@ public:
     vs_status frame_points(int lane, int i, float* prev, float* next, uint8_t* status, uint8_t* mask, float* det);
     vs_status first_corners(int lane, float* xy, int cap, int* n);
 
+    // ---- offline clip mode (temporal chunk of a long clip; BASELINE config 5) -------------------------
+    // frames before `first` that analyze_chunk needs (the pixel halo: <= 2 frames, or `first` itself if <= 2)
+    static int chunk_halo(int first);
+    // d_frames: frames [first - chunk_halo(first), first + count), tight rows.  Writes transforms_[n-1] for
+    // the generateTransform calls n = max(first,1) .. first+count-1 to out_host (3 floats each).
+    vs_status analyze_chunk(const uint8_t* d_frames, int w, int h, int first, int count, float* out_host, int* n_out);
+    // all_tr_host: the n_total-1 transforms of the whole clip.  d_frames: frames [first, first+count).
+    vs_status render_chunk(const float* all_tr_host, int n_total, const uint8_t* d_frames, int w, int h, int first,
+                           int count, uint8_t* d_out, int* ow, int* oh);
+
     // per-stage CUDA-event timing (off by default; used by bench.py and the profiles)
     void set_timing(bool on);
     void stage_time(int stage, double* ms, long long* n);
@@ -91,6 +101,8 @@ private:
     uint8_t* d_ring_ = nullptr;       // [lane][slot][frame]
     uint8_t* d_out_ = nullptr;        // [lane][out frame]  (host-io staging)
     uint8_t* d_scratch_ = nullptr;    // [lane][frame]      (crop+zoom first pass)
+    WarpParams* d_wp_batch_ = nullptr;
+    int wp_batch_cap_ = 0;
     std::vector<float*> traj_bufs_;
     uint64_t launches_ = 0;
 

@@ -511,3 +511,70 @@ void launch_motion(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_
 void launch_smooth_only(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_t st) {
     k_smooth_only<<<dim3(1, 1, n_lanes), 32, 0, st>>>(lanes, info);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Offline clip mode (temporal chunking): the per-frame transforms of the WHOLE clip
+// are known up front (each rank analysed its chunk, one all-gather stitched them), so trajectory and
+// smoothing become batch kernels.
+//   k_traj_build    path_ = running sum of transforms_ in float32, STRICTLY in the reference's sequential
+//                   order (Stabilizer.cpp:681-687) so the result is bit-identical to a streamed run; three
+//                   lanes (x, y, angle) walk the clip, the |t| / atan2 terms are filled in parallel.
+//   k_smooth_batch  one thread per output frame replays applyNextSmoothTransform's smoothing for the path
+//                   length the streamed reference would have seen when that frame left the queue.
+__global__ void __launch_bounds__(256) k_traj_build(const LaneDev* __restrict__ lanes, int n_tr) {
+    const LaneDev& L = lanes[blockIdx.z];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_tr; i += blockDim.x) {
+        const float tx = L.transforms[3 * i], ty = L.transforms[3 * i + 1];
+        L.aux[2 * i] = f_sqrt(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)));
+        L.aux[2 * i + 1] = f_atan2(ty, tx);
+    }
+    if (tid < 3) {
+        float acc = 0.f;
+        for (int i = 0; i < n_tr; ++i) {
+            const float t = L.transforms[3 * i + tid];
+            acc = (i == 0) ? t : __fadd_rn(acc, t);
+            L.path[3 * i + tid] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_smooth_batch(const LaneDev* __restrict__ lanes, StepInfo base, int first, int count,
+                                                       int n_total, int gate, WarpParams* __restrict__ wps) {
+    __shared__ float gk[512];
+    const LaneDev& L = lanes[blockIdx.z];
+    const int n_tr = n_total - 1;
+    if (base.method != 0) {
+        // gaussian taps / Kalman state are shared scratch: walk the frames sequentially on one thread
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            for (int i = (base.method == 2 ? 0 : first); i < first + count; ++i) {
+                StepInfo info = base;
+                info.pop_index = i;
+                info.path_len_at_pop = min(i + gate - 1, n_tr);
+                info.n_out = max(i - first, 0);
+                smooth_and_setup(L, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
+                if (i >= first) wps[i - first] = *L.wp;
+            }
+        }
+        return;
+    }
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int i = first + k;
+    StepInfo info = base;
+    info.pop_index = i;
+    info.path_len_at_pop = min(i + gate - 1, n_tr);
+    info.n_out = k;
+    // box smoothing touches no shared scratch; every thread writes its own record and warp set-up
+    LaneDev Lk = L;
+    Lk.wp = wps + k;
+    smooth_and_setup(Lk, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
+}
+
+void launch_traj_build(const LaneDev* lanes, int n_lanes, int n_tr, cudaStream_t st) {
+    k_traj_build<<<dim3(1, 1, n_lanes), 256, 0, st>>>(lanes, n_tr);
+}
+void launch_smooth_batch(const LaneDev* lanes, int n_lanes, StepInfo base, int first, int count, int n_total, int gate,
+                         WarpParams* wps, cudaStream_t st) {
+    k_smooth_batch<<<dim3((count + 127) / 128, 1, n_lanes), 128, 0, st>>>(lanes, base, first, count, n_total, gate, wps);
+}

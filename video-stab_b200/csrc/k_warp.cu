@@ -341,3 +341,35 @@ void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, si
     k_warp_tiled_frames<<<grid, WT_THREADS, 0, st>>>(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp,
                                                      sv ? 1 : 0, dv ? 1 : 0);
 }
+
+__global__ void __launch_bounds__(256) k_warp_frames_border(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride,
+                                                             size_t sframe, uint8_t* __restrict__ dst, int dw, int dh,
+                                                             size_t dstride, size_t dframe, const WarpParams* __restrict__ wps,
+                                                             int border, int border_mode) {
+    int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= dw || y >= dh) return;
+    uint8_t* o = dst + blockIdx.z * dframe + (size_t)y * dstride + 3 * x;
+    warp_pixel<true>(src + blockIdx.z * sframe, sw, sh, sstride, wps[blockIdx.z].m, border, border_mode, x, y, o);
+}
+
+void launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe, uint8_t* dst,
+                             size_t dstride, size_t dframe, const WarpParams* d_wp, int n_frames, int mode, int border,
+                             int border_mode, uint8_t* scratch, cudaStream_t st) {
+    if (n_frames <= 0) return;
+    if (mode == 0) {
+        launch_warp_matrices(src, sw, sh, sstride, sframe, dst, sw, sh, dstride, dframe, d_wp, n_frames, st);
+    } else if (mode == 1) {
+        const int dw = sw + 2 * border, dh = sh + 2 * border;
+        dim3 grid((dw + 63) / 64, (dh + 3) / 4, n_frames);
+        k_warp_frames_border<<<grid, 256, 0, st>>>(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp, border, border_mode);
+    } else {
+        // crop+zoom: warp each frame into the scratch frame, then cv::resize the (b,b,w-2b,h-2b) crop
+        const size_t tight = (size_t)sw * 3;
+        for (int i = 0; i < n_frames; ++i) {
+            launch_warp_matrices(src + i * sframe, sw, sh, sstride, sframe, scratch, sw, sh, tight, tight * sh, d_wp + i, 1, st);
+            launch_resize_linear(scratch + (size_t)border * tight + 3 * border, sw - 2 * border, sh - 2 * border, tight, 3,
+                                 dst + i * dframe, sw, sh, dstride, st);
+        }
+    }
+}

@@ -44,6 +44,11 @@ void launch_motion(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_
 // flush-time variant: no new frame, only the smoothing + warp set-up for `info.pop_index`
 void launch_smooth_only(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_t st);
 
+// offline clip mode: trajectory of the whole clip + batched smoothing (k_motion.cu)
+void launch_traj_build(const LaneDev* lanes, int n_lanes, int n_tr, cudaStream_t st);
+void launch_smooth_batch(const LaneDev* lanes, int n_lanes, StepInfo base, int first, int count, int n_total, int gate,
+                         WarpParams* wps, cudaStream_t st);
+
 // ---- k_warp.cu : copyMakeBorder + warpAffine + crop/zoom (Stabilizer.cpp:981-990, 1056-1060, 1108-1124)
 struct WarpGeom {
     int src_w, src_h;       // frame as pushed
@@ -60,3 +65,7 @@ void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, si
                           uint8_t* dst, int dw, int dh, size_t dstride, size_t dframe,
                           const WarpParams* d_wp, int n_frames, cudaStream_t st);
 void warp_params_from_T(const float* T, WarpParams* wp);   // host: cv::warpAffine's matrix inversion
+// batched output stage for contiguous frames with device-resident warp set-ups (offline clip mode)
+void launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe, uint8_t* dst,
+                             size_t dstride, size_t dframe, const WarpParams* d_wp, int n_frames, int mode, int border,
+                             int border_mode, uint8_t* scratch, cudaStream_t st);

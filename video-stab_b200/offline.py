@@ -1,0 +1,103 @@
+"""Offline clip mode (BASELINE config 5): a long clip is split into contiguous temporal chunks, one per
+GPU.  Each rank analyses its own frames (plus a <= 2 frame pixel halo), the per-frame transforms are
+exchanged with ONE tiny all-gather (12 bytes per frame), every rank rebuilds the whole trajectory in the
+reference's sequential float32 order, then smooths and warps its own frames in batched launches.  The
+result is bit-identical to pushing the whole clip through `Stabilizer.stabilize()` + `flush()`.
+
+`torch.distributed` is only the plumbing for the all-gather (NCCL over NVLink on GPUs, gloo in the CPU
+tests); all arithmetic is in the CUDA library."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._capi import check, lib
+from .stabilizer import Parameters, Stabilizer
+
+
+def chunk_bounds(n_frames: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous chunk [first, first+count) of rank `rank`; chunk starts are kept even so every chunk
+    needs the same 2-frame halo (corners come from the even frame before it)."""
+    per = -(-n_frames // world)
+    per += per & 1
+    first = min(rank * per, n_frames)
+    return first, max(0, min(per, n_frames - first))
+
+
+def halo(first: int) -> int:
+    return lib.vs_clip_halo(first)
+
+
+def analyze_chunk(st: Stabilizer, d_frames_ptr: int, w: int, h: int, first: int, count: int) -> np.ndarray:
+    """Transforms of the generateTransform calls n = max(first,1)..first+count-1, shape (k,3) float32.
+    `d_frames_ptr`: device address of frame `first - halo(first)` (tight rows, frames contiguous)."""
+    out = np.zeros((max(count, 1), 3), np.float32)
+    n = C.c_int()
+    check(lib.vs_clip_analyze(st._h, d_frames_ptr, w, h, first, count, out.ctypes.data, C.byref(n)))
+    return out[: n.value].copy()
+
+
+def render_chunk(st: Stabilizer, all_transforms: np.ndarray, n_total: int, d_frames_ptr: int, w: int, h: int,
+                 first: int, count: int, d_out_ptr: int) -> tuple[int, int]:
+    tr = np.ascontiguousarray(all_transforms, np.float32).reshape(-1, 3)
+    assert len(tr) == n_total - 1
+    ow, oh = C.c_int(), C.c_int()
+    check(lib.vs_clip_render(st._h, tr.ctypes.data, n_total, d_frames_ptr, w, h, first, count, d_out_ptr,
+                             C.byref(ow), C.byref(oh)))
+    return ow.value, oh.value
+
+
+def stitch_transforms(local: np.ndarray, first: int, count: int, n_total: int, group=None) -> np.ndarray:
+    """All-gather of the per-chunk transforms -> the (n_total-1, 3) transform list of the whole clip.
+    Every rank contributes transforms_[max(first,1)-1 .. first+count-2]; payload 12 bytes per frame."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        assert len(local) == n_total - 1
+        return np.ascontiguousarray(local, np.float32)
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    per = max(chunk_bounds(n_total, world, r)[1] for r in range(world))
+    buf = torch.zeros((per, 3), dtype=torch.float32, device=dev)
+    if len(local):
+        buf[: len(local)] = torch.from_numpy(np.ascontiguousarray(local, np.float32)).to(dev)
+    gathered = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf, group=group)
+    parts = []
+    for r in range(world):
+        f, c = chunk_bounds(n_total, world, r)
+        k = f + c - max(f, 1) if c > 0 else 0
+        parts.append(gathered[r][:k].cpu().numpy())
+    out = np.concatenate(parts, axis=0) if parts else np.zeros((0, 3), np.float32)
+    assert len(out) == n_total - 1, (len(out), n_total)
+    return out
+
+
+def stabilize_clip(frames, params: Parameters | None = None, out=None, n_chunks: int = 1, device: int = 0):
+    """Single-process driver: `frames` is a (N,H,W,3) uint8 CUDA tensor.  With n_chunks > 1 the clip is
+    processed chunk by chunk exactly as n_chunks ranks would (used to test the chunked path on one GPU)."""
+    import torch
+    params = params or Parameters()
+    n, h, w, _ = frames.shape
+    b = params.borderSize if (params.borderSize > 0 and not params.cropNZoom) else 0
+    if out is None:
+        out = torch.zeros((n, h + 2 * b, w + 2 * b, 3), dtype=torch.uint8, device=frames.device)
+    st = Stabilizer(params, device=device)
+    fb = h * w * 3
+    parts = []
+    for r in range(n_chunks):
+        first, count = chunk_bounds(n, n_chunks, r)
+        if count == 0:
+            continue
+        hl = halo(first)
+        parts.append(analyze_chunk(st, frames.data_ptr() + (first - hl) * fb, w, h, first, count))
+    tr = np.concatenate(parts, axis=0) if parts else np.zeros((0, 3), np.float32)
+    for r in range(n_chunks):
+        first, count = chunk_bounds(n, n_chunks, r)
+        if count == 0:
+            continue
+        render_chunk(st, tr, n, frames.data_ptr() + first * fb, w, h, first, count, out[first].data_ptr())
+    torch.cuda.synchronize()
+    return out, tr
