@@ -1,0 +1,32 @@
+"""Print selected metrics of every kernel in an .ncu-rep (raw page)."""
+import csv, subprocess, sys
+rep = sys.argv[1]
+pat = sys.argv[2] if len(sys.argv) > 2 else ""
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
+KEYS = """gpu__time_duration.sum dram__bytes_read.sum dram__bytes_write.sum dram__throughput.avg.pct_of_peak_sustained_elapsed
+sm__throughput.avg.pct_of_peak_sustained_elapsed l1tex__throughput.avg.pct_of_peak_sustained_elapsed lts__throughput.avg.pct_of_peak_sustained_elapsed
+sm__warps_active.avg.pct_of_peak_sustained_active smsp__inst_executed.sum smsp__issue_active.avg.pct_of_peak_sustained_active
+launch__registers_per_thread launch__grid_size launch__block_size launch__occupancy_limit_shared_mem launch__occupancy_limit_registers launch__waves_per_multiprocessor
+sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active
+l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum l1tex__data_pipe_lsu_wavefronts_mem_shared.sum lts__t_sector_hit_rate.pct l1tex__t_sector_hit_rate.pct
+lts__t_bytes.sum l1tex__t_bytes.sum
+smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio
+smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio
+smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio
+smsp__average_warps_issue_stalled_wait_per_issue_active.ratio smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio
+smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio
+smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio smsp__average_warps_issue_stalled_membar_per_issue_active.ratio
+smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio""".split()
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    if pat and pat not in d["Kernel Name"]:
+        continue
+    print("==", d["Kernel Name"], d.get("ID"))
+    for k in KEYS:
+        if k in d:
+            print(f"   {k:90s} {d[k]:>16s} {units[hdr.index(k)]}")
+    if "--all" in sys.argv:
+        for k in hdr:
+            print(k, d[k])
