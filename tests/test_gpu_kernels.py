@@ -51,6 +51,42 @@ def test_warp_affine_bit_exact(vsb, cv2_noopt, w, h):
         assert np.array_equal(out[i], ref), f"frame {i}: max diff {np.abs(out[i].astype(int) - ref).max()}"
 
 
+@pytest.mark.parametrize("w,h", [(1920, 1080), (644, 362)])
+def test_warp_affine_general_matrices(vsb, cv2_noopt, w, h):
+    """Rotations from 0.5 to 60 degrees, scales, flips, shears and far translations: exercises the widest staged
+    boxes, the per-tile generic fallback and tiles that lie partly or wholly outside the source."""
+    cv2 = cv2_noopt
+    f = _tex(vsb, w, h, 77)
+    rng = np.random.default_rng(w)
+    mats = []
+    for ang in (0.009, 0.02, 0.03, 0.05, 0.069, 0.075, 0.2, 1.05, -0.4, 3.1):
+        for sc in (1.0, 0.8, 1.3):
+            c, s = np.cos(ang) * sc, np.sin(ang) * sc
+            mats.append([[c, -s, rng.normal(0, 40)], [s, c, rng.normal(0, 40)]])
+    mats += [[[-1, 0, w - 1], [0, 1, 0]], [[1, 0.2, -30], [0.1, 1, 5]], [[1, 0, 0.5], [0, 1, 0.5]],
+             [[1, 0, -w + 3], [0, 1, 2.25]], [[1, 0, 5.03125], [0, 1, h - 2]], [[0.25, 0, 0], [0, 0.25, 0]],
+             [[4, 0, -w], [0, 4, -h]], [[1e-3, 0, 10], [0, 1e-3, 10]], [[1, 0, 1e6], [0, 1, -1e6]]]
+    T = np.asarray(mats, np.float32)
+    n = len(T)
+    out = vsb.kernels.warp_affine(_dev(np.broadcast_to(f, (n,) + f.shape)), T).cpu().numpy()
+    for i in range(n):
+        ref = cv2.warpAffine(f, T[i], (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+        assert np.array_equal(out[i], ref), f"matrix {i} {T[i].tolist()}: max diff {np.abs(out[i].astype(int) - ref).max()}"
+
+
+def test_warp_affine_unaligned_views(vsb, cv2_noopt):
+    """Source / destination views whose base address or row stride is not 4-byte aligned (ROI of a larger frame)."""
+    cv2 = cv2_noopt
+    big = _tex(vsb, 700, 400, 78)
+    T = _matrices(3, 3)[1:2]
+    for x0, ww in ((1, 641), (3, 640), (2, 322)):
+        view = big[5:365, x0:x0 + ww]
+        d = _dev(big)[5:365, x0:x0 + ww]
+        out = vsb.kernels.warp_affine(d[None], T).cpu().numpy()[0]
+        ref = cv2.warpAffine(np.ascontiguousarray(view), T[0], (ww, 360), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+        assert np.array_equal(out, ref)
+
+
 def test_warp_affine_4k_and_linearity_property(vsb, cv2_noopt):
     cv2 = cv2_noopt
     w, h = 3840, 2160

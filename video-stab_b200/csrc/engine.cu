@@ -145,6 +145,7 @@ vs_status Engine::alloc_fixed() {
     gw2 = gftt_grid_words(VS_AW, VS_AH, p_.min_distance);     // single-kernel entry point on a 960x540 image
     if (gw2 > gw) gw = gw2;
     traj_bufs_.clear();
+    if (n_lanes_ > 8) VS_TRY(dalloc(allocs_, &d_tmaps_, (size_t)VS_MAX_GROUP * 128));
     for (int l = 0; l < n_lanes_; ++l) {
         LaneDev& L = h_lanes_[l];
         for (int s = 0; s < 2; ++s) {
@@ -385,6 +386,7 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         g.src_w = W_; g.src_h = H_; g.src_stride = e.stride;
         g.mode = mode; g.border = b; g.border_mode = border_mode_;
         g.out_w = w; g.out_h = h; g.out_stride = dstride;
+        g.d_tmaps = d_tmaps_;
         int m2 = mode;
         if (mode == 2 && (W_ - 2 * b <= 0 || H_ - 2 * b <= 0)) m2 = 0;                // border larger than image
         g.mode = m2;

@@ -101,6 +101,7 @@ private:
     uint8_t* d_ring_ = nullptr;       // [lane][slot][frame]
     uint8_t* d_out_ = nullptr;        // [lane][out frame]  (host-io staging)
     uint8_t* d_scratch_ = nullptr;    // [lane][frame]      (crop+zoom first pass)
+    unsigned char* d_tmaps_ = nullptr;   // tensor-map scratch for the warp kernel (batches of more than 8 lanes)
     WarpParams* d_wp_batch_ = nullptr;
     int wp_batch_cap_ = 0;
     std::vector<float*> traj_bufs_;

@@ -6,6 +6,7 @@
 // frame (2*3*W*H bytes).
 #include "kernels.h"
 #include <climits>
+#include <cuda.h>
 
 // Source coordinate of one output pixel, exactly as cv::warpAffine computes it:
 //   adelta[x] = rint(M0*x*1024), X0 = rint((M1*y+M2)*1024) + 16, X = (X0 + adelta[x]) >> 5
@@ -80,200 +81,501 @@ static __device__ __forceinline__ void warp_pixel(const uint8_t* __restrict__ sr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tiled fast path (plain warp, mode 0).  One CTA = one 128x32 output tile:
-//   1. the exact source bounding box of the tile is derived from its four corners (the fixed-point
-//      coordinate is monotone in x and in y), widened to 4-pixel (12-byte) groups;
-//   2. the box is staged into shared memory with coalesced 32-bit loads (a warp reads 384 contiguous
-//      bytes per 3 instructions) and re-packed on the fly to 4-byte BGRx pixels, one conflict-free
-//      STS.128 per lane; rows/columns outside the frame are staged as zeros, which IS
-//      cv::BORDER_CONSTANT(0), so the inner loop has no border logic at all;
-//   3. lane l produces pixels x0+l+32j (consecutive lanes -> consecutive shared-memory words, no bank
-//      conflicts): 4 aligned LDS.32 taps, byte gathers with PRMT, horizontal pass on DP4A (weights
-//      32-ax, ax), vertical pass on IMAD with the weight pre-scaled by 64 so the rounded 8-bit result
-//      sits in byte 2 of the accumulator ((acc+512)>>10 without a shift);
-//   4. the 128x32x3 output tile is staged in shared memory and written once with 128-bit stores.
-// Tiles whose source box does not fit (large rotations) or whose coordinates approach the int16
+// Tiled fast path (plain warp, mode 0).  One CTA walks a vertical strip of up to WT_MAXT 128x32 output
+// tiles.  The kernel is ISSUE-bound, not HBM-bound (profiles/r01_b_summary.md), so everything below is
+// arranged to cut instructions per output pixel:
+//   0. per strip: the fixed-point column terms (adelta,bdelta) and row terms (X0,Y0) of cv::warpAffine are
+//      computed once, in double, one entry per thread, and kept in shared memory / registers;
+//   1. per tile: one thread derives the exact source bounding box from the four corner coordinates (the
+//      fixed-point coordinate is monotone in x and in y), widened to 4-pixel (12-byte) groups;
+//   2. the box is staged with coalesced 32-bit loads and re-packed to 4-byte words [B G R R'] where R' is
+//      the red of the NEXT pixel (so the red pair of a bilinear tap is already adjacent), one conflict-free
+//      STS.128 per 4 pixels; positions outside the frame are staged as zeros, which IS cv::BORDER_CONSTANT(0).
+//      The shared row pitch is exactly 1024 bytes, so the row offset of a tap is (t2 & ~1023): no multiply;
+//   3. lane l produces pixels x0+l+32j: 4 aligned LDS.32 taps, two PRMT, the horizontal pass as six
+//      IDP.2A with ONE 16-bit weight pair (16384-512ax | 512ax), the vertical pass as six IMAD with weights
+//      (1024-32ay, 32ay).  Total scale 2^24, so the rounded 8-bit result is byte 3 of the accumulator:
+//      ((acc + 512) >> 10 without a shift; exactness argument in DESIGN.md);
+//   4. each warp transposes its finished row through 512 bytes of shared memory and writes it once with
+//      coalesced 32-bit stores (a warp stores 384 contiguous bytes).
+// Tiles whose source box does not fit (large rotations / scales) or whose coordinates approach the int16
 // saturation of cv::remap fall back to the per-pixel path, CTA-uniformly.
 #define WT_W 128
 #define WT_H 32
-#define WT_PITCH 144                 // fixed source-tile row pitch in BGRx words (128 + rotation slack + alignment)
-#define WT_ROWS 42                   // source-tile row capacity  (144*42*4 = 24 KB)
+#define WT_PITCHW 256                // shared row pitch in words (1024 bytes)
+#define WT_ROWS 42                   // source-tile row capacity (42 KB)
 #define WT_THREADS 256
-#define WT_GRPS 36                   // 4-pixel column groups of the staged box (= WT_PITCH / 4)
+#define WT_GRPS 36                   // 4-pixel column groups of the staged box (box width <= 144)
 #define WT_SROWS 7                   // staging rows in flight: 36 x 7 = 252 threads
-#define WT_STAGE_IT 6                // staging tasks per thread (42 rows / 7)
+#define WT_STAGE_IT 6                // staging tasks per thread (7 * 6 = 42 = WT_ROWS)
+#define WT_MAXT 4                    // tiles per CTA strip
 
 struct WarpTileSmem {
-    uint32_t src[WT_PITCH * WT_ROWS];
-    uint32_t out[(WT_THREADS / 32) * WT_W];   // one BGRx output row per warp (4 KB)
-    int2 rowXY[WT_H];
-    int2 colAB[WT_W];
-    int box[6];                          // ax0, by0, ngrp, nrows, ok, unused
+    uint32_t src[WT_ROWS * WT_PITCHW];        // must stay first: 1024-byte aligned (the row offset trick)
+    uint32_t out[(WT_THREADS / 32) * WT_W];   // one BGRx output row per warp (4 KB); aliased by colAB in the strip prologue
+    int2 rowXY[WT_H * WT_MAXT];
+    int box[2][8];                            // ax0, by0, ngrp, nrows, ok, interior
 };
 
-static __device__ __forceinline__ void warp_tile(WarpTileSmem& S, const uint8_t* __restrict__ src, int sw, int sh,
-                                                 size_t sstride, uint8_t* __restrict__ dst, int dw, int dh,
-                                                 size_t dstride, const double* __restrict__ m, bool src_vec, bool dst_vec) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * WT_W, y0 = blockIdx.y * WT_H;
-    const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5];
+// shared-memory accesses with explicit 32-bit addresses (the tap address is built with integer tricks)
+template <int OFF>
+static __device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF>
+static __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0+%1], %2;" :: "r"(a), "n"(OFF), "r"(v) : "memory");
+}
+template <int OFF>
+static __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0+%1], {%2, %3, %4, %5};" :: "r"(a), "n"(OFF), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 
-    // fixed-point row/column terms of cv::warpAffine, one per thread; columns beyond the frame reuse the
-    // last valid column so that their (discarded) taps stay inside the staged box
+// 16 source bytes (4 pixels + the next pixel's red) -> 4 words [B G R R']
+//   bytes: w0 = B0 G0 R0 B1 | w1 = G1 R1 B2 G2 | w2 = R2 B3 G3 R3 | w3 = B4 G4 R4 ..
+static __device__ __forceinline__ uint4 repack_bgrr(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    uint4 o;
+    o.x = __byte_perm(w0, w1, 0x5210);                                   // [B0 G0 R0 R1]
+    o.y = __byte_perm(__byte_perm(w0, w1, 0x0543), w2, 0x4210);          // [B1 G1 R1 R2]
+    o.z = __byte_perm(w1, w2, 0x7432);                                   // [B2 G2 R2 R3]
+    o.w = __byte_perm(w2, w3, 0x6321);                                   // [B3 G3 R3 R4]
+    return o;
+}
+
+// one staging task of a tile that touches the frame border: positions gx0..gx0+3 of source row gy
+static __device__ __noinline__ uint4 stage_edge_task(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride,
+                                                     int gx0, int gy, bool src_vec) {
+    if ((unsigned)gy >= (unsigned)sh || gx0 + 4 < 0 || gx0 >= sw) return make_uint4(0u, 0u, 0u, 0u);   // BORDER_CONSTANT 0
+    const uint8_t* row = src + (size_t)gy * sstride;
+    // the 16-byte read may spill into the neighbouring row (masked below); it must stay inside the frame buffer
+    const bool legal = src_vec && !(gy == 0 && gx0 < 0) && !(gy == sh - 1 && gx0 + 6 > sw);
+    if (legal) {
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(row + 3 * gx0);
+        uint4 o = repack_bgrr(__ldg(gw), __ldg(gw + 1), __ldg(gw + 2), __ldg(gw + 3));
+        if (gx0 < 0 || gx0 + 5 > sw) {
+            uint32_t v[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) v[c] = ((unsigned)(gx0 + c) < (unsigned)sw) ? 0xFFFFFFFFu : 0u;
+            o.x &= (v[0] & 0x00FFFFFFu) | (v[1] & 0xFF000000u);
+            o.y &= (v[1] & 0x00FFFFFFu) | (v[2] & 0xFF000000u);
+            o.z &= (v[2] & 0x00FFFFFFu) | (v[3] & 0xFF000000u);
+            o.w &= (v[3] & 0x00FFFFFFu) | (v[4] & 0xFF000000u);
+        }
+        return o;
+    }
+    uint32_t v[5] = {0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        if ((unsigned)(gx0 + c) < (unsigned)sw) {
+            const uint8_t* pp = row + 3 * (gx0 + c);
+            v[c] = (uint32_t)pp[0] | ((uint32_t)pp[1] << 8) | ((uint32_t)pp[2] << 16);
+        }
+    }
+    return make_uint4(v[0] | ((v[1] >> 16) << 24), v[1] | ((v[2] >> 16) << 24), v[2] | ((v[3] >> 16) << 24),
+                      v[3] | ((v[4] >> 16) << 24));
+}
+
+static __device__ __forceinline__ void warp_strip(WarpTileSmem& S, const uint8_t* __restrict__ src, int sw, int sh,
+                                                  size_t sstride, uint8_t* __restrict__ dst, int dw, int dh,
+                                                  size_t dstride, const double* __restrict__ m, int rows_per_cta,
+                                                  bool src_vec, bool dst_vec) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * WT_W, ys = blockIdx.y * rows_per_cta;
+    const int ye = min(ys + rows_per_cta, dh);
+    int2* const colAB = reinterpret_cast<int2*>(S.out);
+
+    // ---- 0. strip prologue: fixed-point column/row terms of cv::warpAffine, one per thread.  Columns beyond
+    //         the frame reuse the last valid column so that their (discarded) taps stay inside the staged box.
     if (tid < WT_W) {
-        double xd = (double)min(x0 + tid, dw - 1);
-        S.colAB[tid] = make_int2(sat_int(m0 * xd * 1024.0), sat_int(m3 * xd * 1024.0));
-    } else if (tid < WT_W + WT_H) {
-        double yd = (double)min(y0 + tid - WT_W, dh - 1);
-        S.rowXY[tid - WT_W] = make_int2(sat_int((m1 * yd + m2) * 1024.0) + 16, sat_int((m4 * yd + m5) * 1024.0) + 16);
-    } else if (tid == WT_W + WT_H) {
-        const int xa = x0, xb = min(x0 + WT_W, dw) - 1, ya = y0, yb = min(y0 + WT_H, dh) - 1;
+        const double xd = (double)min(x0 + tid, dw - 1);
+        colAB[tid] = make_int2(sat_int(m[0] * xd * 1024.0), sat_int(m[3] * xd * 1024.0));
+    } else if (tid - WT_W < ye - ys) {
+        const double yd = (double)(ys + tid - WT_W);
+        S.rowXY[tid - WT_W] = make_int2(sat_int((m[1] * yd + m[2]) * 1024.0) + 16, sat_int((m[4] * yd + m[5]) * 1024.0) + 16);
+    }
+    __syncthreads();
+    uint32_t adT[4], bd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int2 c = colAB[lane + 32 * j];
+        adT[j] = (uint32_t)c.x * 16u;                            // 14 fractional bits: 512*ax sits at bits 9..13
+        bd[j] = (uint32_t)c.y;
+    }
+    const int tw = min(WT_W, dw - x0);
+    const int2 cA = colAB[0], cB = colAB[tw - 1];
+    const bool col_ok = max(max(abs(cA.x), abs(cB.x)), max(abs(cA.y), abs(cB.y))) < (1 << 26);
+    const bool vec_out = dst_vec && tw == WT_W;
+    const uint32_t s_src = (uint32_t)__cvta_generic_to_shared(S.src);          // multiple of 1024
+    const uint32_t s_px = (uint32_t)__cvta_generic_to_shared(S.out + warp * WT_W + lane);        // pixel lane + 32 j at +128 j bytes
+    const uint32_t s_v4 = (uint32_t)__cvta_generic_to_shared(S.out + warp * WT_W + 4 * lane);    // pixels 4 lane .. 4 lane + 3
+    // staging thread map: 36 column groups x 7 rows
+    const int r7 = tid / WT_GRPS, q = tid - r7 * WT_GRPS;
+    const uint32_t s_stage = s_src + (uint32_t)(r7 * WT_PITCHW + 4 * q) * 4u;
+
+    int buf = 0;
+    for (int y0 = ys; y0 < ye; y0 += WT_H, buf ^= 1) {
+        // ---- 1. source box of this tile (thread 0); the barrier also orders the previous tile's reads of
+        //         S.src / colAB before this tile's staging
+        if (tid == 0) {
+            const int yb = min(y0 + WT_H, ye) - 1;
+            const int2 rA = S.rowXY[y0 - ys], rB = S.rowXY[yb - ys];
+            int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int2 cc = (c & 1) ? cB : cA, rr = (c & 2) ? rB : rA;
+                const int X = (rr.x + cc.x) >> 10, Y = (rr.y + cc.y) >> 10;
+                minx = min(minx, X); maxx = max(maxx, X); miny = min(miny, Y); maxy = max(maxy, Y);
+            }
+            const int ax0 = minx & ~3;                           // floor to a 4-pixel group (also for negatives)
+            const int ngrp = (maxx + 1 - ax0) / 4 + 1;
+            const int nrows = maxy + 2 - miny;
+            const bool row_ok = max(max(abs(rA.x), abs(rB.x)), max(abs(rA.y), abs(rB.y))) < (1 << 26);
+            const bool ok = col_ok && row_ok && minx > -30000 && maxx < 30000 && miny > -30000 && maxy < 30000 &&
+                            ngrp <= WT_GRPS && nrows <= WT_ROWS && ngrp > 0 && nrows > 0;
+            // interior: every 16-byte task of the box (12 bytes + the next pixel's red) lies inside its frame row
+            const bool interior = src_vec && ax0 >= 0 && ax0 + 4 * ngrp + 2 <= sw && miny >= 0 && miny + nrows <= sh;
+            int* bx = S.box[buf];
+            bx[0] = ax0; bx[1] = miny; bx[2] = ngrp; bx[3] = nrows; bx[4] = ok ? 1 : 0; bx[5] = interior ? 1 : 0;
+        }
+        __syncthreads();
+        const int ax0 = S.box[buf][0], by0 = S.box[buf][1], ngrp = S.box[buf][2], nrows = S.box[buf][3];
+        if (!S.box[buf][4]) {
+            // generic per-pixel path for this tile
+            for (int i = tid; i < WT_W * WT_H; i += WT_THREADS) {
+                const int x = x0 + (i & (WT_W - 1)), y = y0 + i / WT_W;
+                if (x < dw && y < ye) warp_pixel<false>(src, sw, sh, sstride, m, 0, 0, x, y, dst + (size_t)y * dstride + 3 * x);
+            }
+            continue;
+        }
+        // ---- 2. stage the source box: one task = 4 positions = 16 source bytes -> one 16-byte store.  Each
+        //         thread walks down its column group 7 rows at a time; all its loads are issued before the
+        //         first is consumed.
+        {
+            const bool colok = q < ngrp && r7 < WT_SROWS;
+            if (S.box[buf][5]) {
+                // Loads are unconditional from clamped (always valid) addresses, so only the store is predicated:
+                // idle lanes re-read the last group / last row of the box (L1 hits).  Two batches of three rows:
+                // 12 loads in flight per thread, then their three 16-byte stores.
+                const uint8_t* tbase = src + (size_t)by0 * sstride + (size_t)(3 * ax0 + 12 * min(q, ngrp - 1));
+                const unsigned stride32 = (unsigned)sstride, rlast = (unsigned)(nrows - 1);
+#define WT_BATCH(k0)                                                                                           \
+                if ((k0) * WT_SROWS < nrows) {                          /* CTA-uniform */                      \
+                    uint32_t w0[3], w1[3], w2[3], w3[3];                                                       \
+                    _Pragma("unroll") for (int k = 0; k < 3; ++k) {                                            \
+                        const unsigned r = min((unsigned)(r7 + ((k0) + k) * WT_SROWS), rlast);                 \
+                        const uint32_t* gw = reinterpret_cast<const uint32_t*>(tbase + (size_t)r * stride32);  \
+                        w0[k] = __ldg(gw); w1[k] = __ldg(gw + 1); w2[k] = __ldg(gw + 2); w3[k] = __ldg(gw + 3); \
+                    }                                                                                          \
+                    _Pragma("unroll") for (int k = 0; k < 3; ++k) {                                            \
+                        const uint4 o = repack_bgrr(w0[k], w1[k], w2[k], w3[k]);                               \
+                        if (colok && r7 + ((k0) + k) * WT_SROWS < nrows) {                                     \
+                            if (k == 0) sts128<((k0) + 0) * WT_SROWS * WT_PITCHW * 4>(s_stage, o.x, o.y, o.z, o.w); \
+                            if (k == 1) sts128<((k0) + 1) * WT_SROWS * WT_PITCHW * 4>(s_stage, o.x, o.y, o.z, o.w); \
+                            if (k == 2) sts128<((k0) + 2) * WT_SROWS * WT_PITCHW * 4>(s_stage, o.x, o.y, o.z, o.w); \
+                        }                                                                                      \
+                    }                                                                                          \
+                }
+                WT_BATCH(0) WT_BATCH(3)
+#undef WT_BATCH
+            } else if (colok) {
+                // tiles touching the frame border: zeros outside = BORDER_CONSTANT
+                for (int r = r7; r < nrows; r += WT_SROWS) {
+                    const uint4 o = stage_edge_task(src, sw, sh, sstride, ax0 + 4 * q, by0 + r, src_vec);
+                    *reinterpret_cast<uint4*>(S.src + r * WT_PITCHW + 4 * q) = o;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 3. compute: warp -> rows, lane -> pixels x0 + lane + 32 j
+        const uint32_t bx14 = (uint32_t)ax0 << 14, by10 = ((uint32_t)by0 << 10) - s_src;
+        uint8_t* grow = dst + (size_t)(y0 + warp) * dstride + (size_t)x0 * 3 + (vec_out ? 12 * lane : 0);
+#pragma unroll
+        for (int rr = warp; rr < WT_H; rr += WT_THREADS / 32) {
+            const int y = y0 + rr;
+            if (y >= ye) break;
+            const int2 xy = S.rowXY[y - ys];
+            const uint32_t rxT = (uint32_t)xy.x * 16u - bx14;
+            const uint32_t ryS = (uint32_t)xy.y - by10;          // box-relative y (10 fractional bits) + shared base of S.src
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t T1 = rxT + adT[j];                     // box-relative x, 14 fractional bits
+                const uint32_t t2 = ryS + bd[j];
+                const uint32_t a = (t2 & 0xFFFFFC00u) + ((T1 >> 14) << 2);   // &S.src[sy][sx]
+                const uint32_t A16 = T1 & 0x3E00u;                    // 512 * ax
+                const uint32_t W16 = A16 * 0xFFFFu + 16384u;          // u16 pair (16384 - 512 ax | 512 ax)
+                const uint32_t B = t2 & 0x3E0u, Bc = 1024u - B;       // 32 * ay, 32 * (32 - ay)
+                const uint32_t t00 = lds32<0>(a), t01 = lds32<4>(a), t10 = lds32<WT_PITCHW * 4>(a), t11 = lds32<WT_PITCHW * 4 + 4>(a);
+                const uint32_t u0 = __byte_perm(t00, t01, 0x5140);    // [b00 b01 g00 g01]; the red pair is bytes 2,3 of t00
+                const uint32_t l0 = __byte_perm(t10, t11, 0x5140);
+                const uint32_t hb0 = __dp2a_lo(W16, u0, 0u), hg0 = __dp2a_hi(W16, u0, 0u), hr0 = __dp2a_hi(W16, t00, 0u);
+                const uint32_t hb1 = __dp2a_lo(W16, l0, 0u), hg1 = __dp2a_hi(W16, l0, 0u), hr1 = __dp2a_hi(W16, t10, 0u);
+                const uint32_t vb = hb0 * Bc + (hb1 * B + 0x800000u);  // (acc + 512) << 14 : result in byte 3
+                const uint32_t vg = hg0 * Bc + (hg1 * B + 0x800000u);
+                const uint32_t vr = hr0 * Bc + (hr1 * B + 0x800000u);
+                const uint32_t px = __byte_perm(__byte_perm(vb, vg, 0x0073), vr, 0x0710);   // [B G R --]
+                if (j == 0) sts32<0>(s_px, px);
+                else if (j == 1) sts32<128>(s_px, px);
+                else if (j == 2) sts32<256>(s_px, px);
+                else sts32<384>(s_px, px);
+            }
+            __syncwarp();
+            // ---- 4. the warp writes its finished row once: lane -> 4 pixels -> 12 packed bytes
+            if (vec_out) {
+                uint32_t vx, vy, vz, vw;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(vx), "=r"(vy), "=r"(vz), "=r"(vw) : "r"(s_v4));
+                uint32_t* g = reinterpret_cast<uint32_t*>(grow);
+                g[0] = __byte_perm(vx, vy, 0x4210);              // B0 G0 R0 B1
+                g[1] = __byte_perm(vy, vz, 0x5421);              // G1 R1 B2 G2
+                g[2] = __byte_perm(vz, vw, 0x6542);              // R2 B3 G3 R3
+            } else {
+                const uint32_t* orow = S.out + warp * WT_W;
+                for (int c = lane; c < tw; c += 32) {
+                    const uint32_t v = orow[c];
+                    grow[3 * c] = (uint8_t)v; grow[3 * c + 1] = (uint8_t)(v >> 8); grow[3 * c + 2] = (uint8_t)(v >> 16);
+                }
+            }
+            grow += (size_t)(WT_THREADS / 32) * dstride;
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA variant of the tiled fast path (the default whenever the frame geometry allows a tensor map: 16-byte
+// aligned base and strides, width % 4 == 0).  Differences from warp_strip above:
+//   * the raw source box (packed BGR, 480 bytes x 42 rows) is fetched by ONE cp.async.bulk.tensor.3d issued by
+//     thread 0 into shared memory, completion on an mbarrier; the tensor map is over {row words, rows, frames}
+//     and TMA zero-fills everything outside the frame, which IS cv::BORDER_CONSTANT(0) - there is no edge path;
+//   * the fetch of tile t+1 is issued right after tile t has been re-packed, so it overlaps tile t's compute;
+//   * the re-pack to [B G R R'] words reads the raw box from shared memory (stride-12-byte LDS.32, conflict
+//     free), so no global load instruction, address arithmetic or predicate is left in the kernel.
+#define WT_RAW_PITCH 480                 // bytes per raw row: 3 * (12 + 4 * WT_GRPS + 1) = 471 rounded to 16; TMA needs a 16-byte
+                                         // aligned start, i.e. a 16-pixel aligned box origin (48 bytes), hence the 12 extra pixels
+#define WT_RAW_WORDS (WT_RAW_PITCH / 4)
+#define WT_TMA_SMEM (WT_ROWS * WT_PITCHW * 4 + WT_ROWS * WT_RAW_PITCH + (WT_THREADS / 32) * WT_W * 4 + WT_H * WT_MAXT * 8 + 64 + 16)
+#define WT_TMA_MAXPACK 8
+
+struct TmapPack {
+    CUtensorMap m[WT_TMA_MAXPACK];
+};
+
+static __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(mbar), "r"(parity) : "memory");
+}
+
+// lanes_mode: one 2-D-like map per lane (maps[z], frame coordinate 0); else one map, frame coordinate z
+__global__ void __launch_bounds__(WT_THREADS, 3)
+k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict__ dmaps, int lanes_mode,
+           const LaneDev* __restrict__ lanes, const WarpParams* __restrict__ wps,
+           PtrPack srcp, const uint8_t* __restrict__ src0, size_t sframe, size_t sstride, int sw, int sh,
+           MutPtrPack dstp, uint8_t* __restrict__ dst0, size_t dframe, int dw, int dh, size_t dstride,
+           int rows_per_cta, int dst_vec) {
+    extern __shared__ __align__(1024) unsigned char wt_smem[];
+    uint32_t* const S_src = reinterpret_cast<uint32_t*>(wt_smem);
+    unsigned char* const S_raw = wt_smem + WT_ROWS * WT_PITCHW * 4;
+    uint32_t* const S_out = reinterpret_cast<uint32_t*>(S_raw + WT_ROWS * WT_RAW_PITCH);
+    int2* const S_rowXY = reinterpret_cast<int2*>(S_out + (WT_THREADS / 32) * WT_W);
+    int (*S_box)[8] = reinterpret_cast<int (*)[8]>(S_rowXY + WT_H * WT_MAXT);
+    unsigned long long* const S_mbar = reinterpret_cast<unsigned long long*>(S_box + 2);
+
+    const int z = blockIdx.z;
+    const double* __restrict__ m = lanes_mode ? lanes[z].wp->m : wps[z].m;
+    uint8_t* __restrict__ dst = lanes_mode ? dstp.p[z] : dst0 + (size_t)z * dframe;
+    const CUtensorMap* tmap = dmaps ? dmaps + (lanes_mode ? z : 0) : &pack.m[lanes_mode ? z : 0];
+    const int zc = lanes_mode ? 0 : z;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * WT_W, ys = blockIdx.y * rows_per_cta;
+    const int ye = min(ys + rows_per_cta, dh);
+    int2* const colAB = reinterpret_cast<int2*>(S_out);
+    const uint32_t s_src = (uint32_t)__cvta_generic_to_shared(S_src);          // multiple of 1024
+    const uint32_t s_raw = (uint32_t)__cvta_generic_to_shared(S_raw);
+    const uint32_t s_mbar = (uint32_t)__cvta_generic_to_shared(S_mbar);
+
+    // ---- 0. strip prologue
+    if (tid < WT_W) {
+        const double xd = (double)min(x0 + tid, dw - 1);
+        colAB[tid] = make_int2(sat_int(m[0] * xd * 1024.0), sat_int(m[3] * xd * 1024.0));
+    } else if (tid - WT_W < ye - ys) {
+        const double yd = (double)(ys + tid - WT_W);
+        S_rowXY[tid - WT_W] = make_int2(sat_int((m[1] * yd + m[2]) * 1024.0) + 16, sat_int((m[4] * yd + m[5]) * 1024.0) + 16);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(s_mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (dmaps) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(tmap) : "memory");
+    }
+    __syncthreads();
+    uint32_t adT[4], bd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int2 c = colAB[lane + 32 * j];
+        adT[j] = (uint32_t)c.x * 16u;
+        bd[j] = (uint32_t)c.y;
+    }
+    const int tw = min(WT_W, dw - x0);
+    const int2 cA = colAB[0], cB = colAB[tw - 1];
+    const bool col_ok = max(max(abs(cA.x), abs(cB.x)), max(abs(cA.y), abs(cB.y))) < (1 << 26);
+    const bool vec_out = dst_vec && tw == WT_W;
+    const uint32_t s_px = (uint32_t)__cvta_generic_to_shared(S_out + warp * WT_W + lane);
+    const uint32_t s_v4 = (uint32_t)__cvta_generic_to_shared(S_out + warp * WT_W + 4 * lane);
+    // re-pack thread map: 36 column groups x 7 rows
+    const int r7 = tid / WT_GRPS, q = tid - r7 * WT_GRPS;
+    const uint32_t s_stage = s_src + (uint32_t)(r7 * WT_PITCHW + 4 * q) * 4u;
+    const uint32_t s_rawt = s_raw + (uint32_t)(r7 * WT_RAW_PITCH + 12 * q);
+
+    // source box of the tile starting at row y0 -> S_box[b]; issues its fetch when the box fits (thread 0 only)
+    auto box_and_fetch = [&](int y0, int b) {
+        const int yb = min(y0 + WT_H, ye) - 1;
+        const int2 rA = S_rowXY[y0 - ys], rB = S_rowXY[yb - ys];
         int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            double xd = (double)((c & 1) ? xb : xa), yd = (double)((c & 2) ? yb : ya);
-            int X = (sat_int((m1 * yd + m2) * 1024.0) + 16 + sat_int(m0 * xd * 1024.0)) >> 10;
-            int Y = (sat_int((m4 * yd + m5) * 1024.0) + 16 + sat_int(m3 * xd * 1024.0)) >> 10;
+            const int2 cc = (c & 1) ? cB : cA, rr = (c & 2) ? rB : rA;
+            const int X = (rr.x + cc.x) >> 10, Y = (rr.y + cc.y) >> 10;
             minx = min(minx, X); maxx = max(maxx, X); miny = min(miny, Y); maxy = max(maxy, Y);
         }
-        int ax0 = minx & ~3;                                   // floor to a 4-pixel group (also for negatives)
-        int ngrp = (maxx + 1 - ax0) / 4 + 1;
-        int nrows = maxy + 2 - miny;
-        bool ok = minx > -30000 && maxx < 30000 && miny > -30000 && maxy < 30000 &&
-                  ngrp * 4 <= WT_PITCH && nrows <= WT_ROWS && ngrp > 0 && nrows > 0;
-        S.box[0] = ax0; S.box[1] = miny; S.box[2] = ngrp; S.box[3] = nrows; S.box[4] = ok ? 1 : 0;
-    }
-    __syncthreads();
-    const int ax0 = S.box[0], by0 = S.box[1], ngrp = S.box[2], nrows = S.box[3];
-    if (!S.box[4]) {
-        // generic per-pixel path for this tile
-        for (int i = tid; i < WT_W * WT_H; i += WT_THREADS) {
-            int x = x0 + (i & (WT_W - 1)), y = y0 + i / WT_W;
-            if (x < dw && y < dh) warp_pixel<false>(src, sw, sh, sstride, m, 0, 0, x, y, dst + (size_t)y * dstride + 3 * x);
+        const int ax0 = minx & ~3;
+        const int ngrp = (maxx + 1 - ax0) / 4 + 1;
+        const int nrows = maxy + 2 - miny;
+        const bool row_ok = max(max(abs(rA.x), abs(rB.x)), max(abs(rA.y), abs(rB.y))) < (1 << 26);
+        const bool ok = col_ok && row_ok && minx > -30000 && maxx < 30000 && miny > -30000 && maxy < 30000 &&
+                        ngrp <= WT_GRPS && nrows <= WT_ROWS && ngrp > 0 && nrows > 0;
+        const int axT = minx & ~15;                          // TMA box origin: 16 pixels = 48 bytes = 12 words
+        int* bx = S_box[b];
+        bx[0] = ax0; bx[1] = miny; bx[2] = ngrp; bx[3] = nrows; bx[4] = ok ? 1 : 0; bx[5] = 3 * (ax0 - axT);
+        if (ok) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s_mbar), "r"(WT_ROWS * WT_RAW_PITCH) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         :: "r"(s_raw), "l"(tmap), "r"(s_mbar), "r"(3 * (axT >> 2)), "r"(miny), "r"(zc) : "memory");
         }
-        return;
-    }
-    // ---- stage the source box as BGRx: one task = 4 pixels = 12 source bytes -> one 16-byte store.
-    //      Fixed 2-D thread map: 36 column groups x 7 rows (252 of 256 threads), each thread walks down
-    //      its column 7 rows at a time; all its loads are issued before the first is consumed.
-    {
-        const bool interior = src_vec && ax0 >= 0 && ax0 + 4 * ngrp <= sw && by0 >= 0 && by0 + nrows <= sh;
-        const int r7 = tid / WT_GRPS, q = tid - r7 * WT_GRPS;    // constant divisor
-        const bool colok = q < ngrp && r7 < WT_SROWS;
-        if (interior) {
-            uint32_t w0[WT_STAGE_IT], w1[WT_STAGE_IT], w2[WT_STAGE_IT];
-            const uint32_t* gw = reinterpret_cast<const uint32_t*>(src + (size_t)(by0 + r7) * sstride + (size_t)(3 * ax0)) + 3 * q;
-            const size_t gstep = (size_t)WT_SROWS * sstride / 4;
-#pragma unroll
-            for (int k = 0; k < WT_STAGE_IT; ++k) {
-                if (colok && r7 + k * WT_SROWS < nrows) {
-                    w0[k] = __ldg(gw); w1[k] = __ldg(gw + 1); w2[k] = __ldg(gw + 2);
-                }
-                gw += gstep;
+    };
+    if (tid == 0) box_and_fetch(ys, 0);
+    __syncthreads();
+
+    int buf = 0;
+    uint32_t phase = 0;
+    for (int y0 = ys; y0 < ye; y0 += WT_H, buf ^= 1) {
+        const int ax0 = S_box[buf][0], by0 = S_box[buf][1], ngrp = S_box[buf][2], nrows = S_box[buf][3];
+        const bool ok = S_box[buf][4] != 0;
+        const bool more = y0 + WT_H < ye;
+        if (ok) {
+            // ---- 2. wait for the raw box, re-pack it: one task = 16 raw bytes -> 4 words [B G R R']
+            mbar_wait(s_mbar, phase);
+            phase ^= 1;
+            const bool colok = q < ngrp && r7 < WT_SROWS;
+            const uint32_t s_rawq = s_rawt + (uint32_t)S_box[buf][5];
+#define WT_REPACK(k)                                                                                           \
+            if ((k) * WT_SROWS < nrows) {                               /* CTA-uniform */                      \
+                if (colok && r7 + (k) * WT_SROWS < nrows) {                                                    \
+                    const uint32_t w0 = lds32<(k) * WT_SROWS * WT_RAW_PITCH>(s_rawq);                          \
+                    const uint32_t w1 = lds32<(k) * WT_SROWS * WT_RAW_PITCH + 4>(s_rawq);                      \
+                    const uint32_t w2 = lds32<(k) * WT_SROWS * WT_RAW_PITCH + 8>(s_rawq);                      \
+                    const uint32_t w3 = lds32<(k) * WT_SROWS * WT_RAW_PITCH + 12>(s_rawq);                     \
+                    const uint4 o = repack_bgrr(w0, w1, w2, w3);                                               \
+                    sts128<(k) * WT_SROWS * WT_PITCHW * 4>(s_stage, o.x, o.y, o.z, o.w);                       \
+                }                                                                                              \
             }
-            uint32_t* d = S.src + r7 * WT_PITCH + 4 * q;
-#pragma unroll
-            for (int k = 0; k < WT_STAGE_IT; ++k) {
-                if (colok && r7 + k * WT_SROWS < nrows) {
-                    uint4 o;
-                    o.x = w0[k];                                    // [B0 G0 R0 --]
-                    o.y = __byte_perm(w0[k], w1[k], 0x0543);        // [B1 G1 R1 --]
-                    o.z = __byte_perm(w1[k], w2[k], 0x0432);        // [B2 G2 R2 --]
-                    o.w = w2[k] >> 8;                               // [B3 G3 R3 --]
-                    *reinterpret_cast<uint4*>(d) = o;
-                }
-                d += WT_SROWS * WT_PITCH;
+            WT_REPACK(0) WT_REPACK(1) WT_REPACK(2) WT_REPACK(3) WT_REPACK(4) WT_REPACK(5)
+#undef WT_REPACK
+        }
+        __syncthreads();                                   // S_src ready, raw box free
+        if (tid == 0 && more) box_and_fetch(y0 + WT_H, buf ^ 1);      // overlaps this tile's compute
+        if (!ok) {
+            // generic per-pixel path for this tile
+            for (int i = tid; i < WT_W * WT_H; i += WT_THREADS) {
+                const int x = x0 + (i & (WT_W - 1)), y = y0 + i / WT_W;
+                if (x < dw && y < ye) warp_pixel<false>(lanes_mode ? srcp.p[z] : src0 + (size_t)z * sframe, sw, sh, sstride, m, 0, 0, x, y, dst + (size_t)y * dstride + 3 * x);
             }
-        } else if (colok) {
-            // tiles touching the frame border (or unaligned frames): per-pixel, zero outside = BORDER_CONSTANT
-            for (int r = r7; r < nrows; r += WT_SROWS) {
-                const int gx = ax0 + 4 * q, gy = by0 + r;
-                uint32_t v[4] = {0u, 0u, 0u, 0u};
-                if ((unsigned)gy < (unsigned)sh) {
-                    const uint8_t* g = src + (size_t)gy * sstride + 3 * gx;
+        } else {
+            // ---- 3. compute: warp -> rows, lane -> pixels x0 + lane + 32 j
+            const uint32_t bx14 = (uint32_t)ax0 << 14, by10 = ((uint32_t)by0 << 10) - s_src;
+            uint8_t* grow = dst + (size_t)(y0 + warp) * dstride + (size_t)x0 * 3 + (vec_out ? 12 * lane : 0);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if ((unsigned)(gx + c) < (unsigned)sw) {
-                            const uint8_t* pp = g + 3 * c;
-                            v[c] = (uint32_t)pp[0] | ((uint32_t)pp[1] << 8) | ((uint32_t)pp[2] << 16);
-                        }
+            for (int rr = warp; rr < WT_H; rr += WT_THREADS / 32) {
+                const int y = y0 + rr;
+                if (y >= ye) break;
+                const int2 xy = S_rowXY[y - ys];
+                const uint32_t rxT = (uint32_t)xy.x * 16u - bx14;
+                const uint32_t ryS = (uint32_t)xy.y - by10;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t T1 = rxT + adT[j];
+                    const uint32_t t2 = ryS + bd[j];
+                    const uint32_t a = (t2 & 0xFFFFFC00u) + ((T1 >> 14) << 2);
+                    const uint32_t A16 = T1 & 0x3E00u;
+                    const uint32_t W16 = A16 * 0xFFFFu + 16384u;
+                    const uint32_t B = t2 & 0x3E0u, Bc = 1024u - B;
+                    const uint32_t t00 = lds32<0>(a), t01 = lds32<4>(a), t10 = lds32<WT_PITCHW * 4>(a), t11 = lds32<WT_PITCHW * 4 + 4>(a);
+                    const uint32_t u0 = __byte_perm(t00, t01, 0x5140);
+                    const uint32_t l0 = __byte_perm(t10, t11, 0x5140);
+                    const uint32_t hb0 = __dp2a_lo(W16, u0, 0u), hg0 = __dp2a_hi(W16, u0, 0u), hr0 = __dp2a_hi(W16, t00, 0u);
+                    const uint32_t hb1 = __dp2a_lo(W16, l0, 0u), hg1 = __dp2a_hi(W16, l0, 0u), hr1 = __dp2a_hi(W16, t10, 0u);
+                    const uint32_t vb = hb0 * Bc + (hb1 * B + 0x800000u);
+                    const uint32_t vg = hg0 * Bc + (hg1 * B + 0x800000u);
+                    const uint32_t vr = hr0 * Bc + (hr1 * B + 0x800000u);
+                    const uint32_t px = __byte_perm(__byte_perm(vb, vg, 0x0073), vr, 0x0710);
+                    if (j == 0) sts32<0>(s_px, px);
+                    else if (j == 1) sts32<128>(s_px, px);
+                    else if (j == 2) sts32<256>(s_px, px);
+                    else sts32<384>(s_px, px);
+                }
+                __syncwarp();
+                if (vec_out) {
+                    uint32_t vx, vy, vz, vw;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(vx), "=r"(vy), "=r"(vz), "=r"(vw) : "r"(s_v4));
+                    uint32_t* g = reinterpret_cast<uint32_t*>(grow);
+                    g[0] = __byte_perm(vx, vy, 0x4210);
+                    g[1] = __byte_perm(vy, vz, 0x5421);
+                    g[2] = __byte_perm(vz, vw, 0x6542);
+                } else {
+                    const uint32_t* orow = S_out + warp * WT_W;
+                    for (int c = lane; c < tw; c += 32) {
+                        const uint32_t v = orow[c];
+                        grow[3 * c] = (uint8_t)v; grow[3 * c + 1] = (uint8_t)(v >> 8); grow[3 * c + 2] = (uint8_t)(v >> 16);
                     }
                 }
-                *reinterpret_cast<uint4*>(S.src + r * WT_PITCH + 4 * q) = make_uint4(v[0], v[1], v[2], v[3]);
+                grow += (size_t)(WT_THREADS / 32) * dstride;
+                __syncwarp();
             }
         }
-    }
-    __syncthreads();
-    // ---- compute: warp -> rows, lane -> pixels x0 + lane + 32 j
-    int ad[4], bd[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int2 c = S.colAB[lane + 32 * j];
-        ad[j] = c.x - (ax0 << 10);                               // fold the box origin into the fixed-point terms
-        bd[j] = c.y - (by0 << 10);
-    }
-    const int tw = min(WT_W, dw - x0);
-    const bool vec_out = dst_vec && tw == WT_W;
-    uint32_t* const orow = S.out + warp * WT_W;
-    for (int rr = warp; rr < WT_H; rr += WT_THREADS / 32) {
-        if (y0 + rr >= dh) break;
-        const int2 xy = S.rowXY[rr];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int t1 = xy.x + ad[j], t2 = xy.y + bd[j];
-            const int sx = t1 >> 10, sy = t2 >> 10;              // box-relative integer source coordinates
-            const uint32_t ax = (uint32_t)(t1 >> 5) & 31u;
-            const uint32_t wy1 = ((uint32_t)t2 << 1) & 0x7c0u;   // ay * 64
-            const uint32_t wy0 = 2048u - wy1;                    // (32 - ay) * 64
-            const uint32_t* p = S.src + sy * WT_PITCH + sx;
-            const uint32_t t00 = p[0], t01 = p[1], t10 = p[WT_PITCH], t11 = p[WT_PITCH + 1];
-            const uint32_t Wa = __byte_perm(32u - ax, ax, 0x7740);   // bytes [32-ax, ax, 0, 0]
-            const uint32_t Wb = Wa << 16;                            // bytes [0, 0, 32-ax, ax]
-            const uint32_t u0 = __byte_perm(t00, t01, 0x5140);   // [b00 b01 g00 g01]
-            const uint32_t u1 = __byte_perm(t00, t01, 0x5162);   // [r00 r01 ..]
-            const uint32_t l0 = __byte_perm(t10, t11, 0x5140);
-            const uint32_t l1 = __byte_perm(t10, t11, 0x5162);
-            const uint32_t hb0 = __dp4a(u0, Wa, 0u), hg0 = __dp4a(u0, Wb, 0u), hr0 = __dp4a(u1, Wa, 0u);
-            const uint32_t hb1 = __dp4a(l0, Wa, 0u), hg1 = __dp4a(l0, Wb, 0u), hr1 = __dp4a(l1, Wa, 0u);
-            const uint32_t vb = hb0 * wy0 + (hb1 * wy1 + 32768u);     // (acc + 512) << 6 : result in byte 2
-            const uint32_t vg = hg0 * wy0 + (hg1 * wy1 + 32768u);
-            const uint32_t vr = hr0 * wy0 + (hr1 * wy1 + 32768u);
-            orow[lane + 32 * j] = __byte_perm(__byte_perm(vb, vg, 0x0062), vr, 0x0610);   // [B G R --]
-        }
-        __syncwarp();
-        // ---- the warp writes its finished row once: lane -> 4 pixels -> 12 packed bytes, a warp stores
-        //      384 contiguous bytes
-        uint8_t* grow = dst + (size_t)(y0 + rr) * dstride + (size_t)x0 * 3;
-        if (vec_out) {
-            const uint4 v = *reinterpret_cast<const uint4*>(orow + 4 * lane);
-            uint32_t* g = reinterpret_cast<uint32_t*>(grow) + 3 * lane;
-            g[0] = __byte_perm(v.x, v.y, 0x4210);            // B0 G0 R0 B1
-            g[1] = __byte_perm(v.y, v.z, 0x5421);            // G1 R1 B2 G2
-            g[2] = __byte_perm(v.z, v.w, 0x6542);            // R2 B3 G3 R3
-        } else {
-            for (int c = lane; c < tw; c += 32) {
-                const uint32_t v = orow[c];
-                grow[3 * c] = (uint8_t)v; grow[3 * c + 1] = (uint8_t)(v >> 8); grow[3 * c + 2] = (uint8_t)(v >> 16);
-            }
-        }
-        __syncwarp();
+        if (more) __syncthreads();                         // S_src (and S_box[buf]) free for the next tile
     }
 }
 
-__global__ void __launch_bounds__(WT_THREADS, 6) k_warp_tiled_lanes(const LaneDev* __restrict__ lanes, PtrPack src, MutPtrPack dst,
-                                                                  WarpGeom g, int src_vec, int dst_vec) {
-    __shared__ WarpTileSmem S;
-    warp_tile(S, src.p[blockIdx.z], g.src_w, g.src_h, g.src_stride, dst.p[blockIdx.z], g.out_w, g.out_h, g.out_stride,
-              lanes[blockIdx.z].wp->m, src_vec != 0, dst_vec != 0);
+__global__ void __launch_bounds__(WT_THREADS, 4) k_warp_tiled_lanes(const LaneDev* __restrict__ lanes, PtrPack src, MutPtrPack dst,
+                                                                  WarpGeom g, int rows_per_cta, int src_vec, int dst_vec) {
+    __shared__ __align__(16) WarpTileSmem S;
+    warp_strip(S, src.p[blockIdx.z], g.src_w, g.src_h, g.src_stride, dst.p[blockIdx.z], g.out_w, g.out_h, g.out_stride,
+               lanes[blockIdx.z].wp->m, rows_per_cta, src_vec != 0, dst_vec != 0);
 }
 
-__global__ void __launch_bounds__(WT_THREADS, 6) k_warp_tiled_frames(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride,
+__global__ void __launch_bounds__(WT_THREADS, 4) k_warp_tiled_frames(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride,
                                                                    size_t sframe, uint8_t* __restrict__ dst, int dw, int dh,
                                                                    size_t dstride, size_t dframe,
-                                                                   const WarpParams* __restrict__ wps, int src_vec, int dst_vec) {
-    __shared__ WarpTileSmem S;
-    warp_tile(S, src + blockIdx.z * sframe, sw, sh, sstride, dst + blockIdx.z * dframe, dw, dh, dstride,
-              wps[blockIdx.z].m, src_vec != 0, dst_vec != 0);
+                                                                   const WarpParams* __restrict__ wps, int rows_per_cta,
+                                                                   int src_vec, int dst_vec) {
+    __shared__ __align__(16) WarpTileSmem S;
+    warp_strip(S, src + blockIdx.z * sframe, sw, sh, sstride, dst + blockIdx.z * dframe, dw, dh, dstride,
+               wps[blockIdx.z].m, rows_per_cta, src_vec != 0, dst_vec != 0);
+}
+
+// tiles per CTA strip: enough CTAs to fill the machine first (148 SMs x 4 resident CTAs), then longer strips
+static inline int strip_rows(int dw, int dh, int n_frames) {
+    const long tiles = (long)((dw + WT_W - 1) / WT_W) * ((dh + WT_H - 1) / WT_H) * n_frames;
+    int t = 1;
+    while (t < WT_MAXT && tiles / (t * 2) >= 148L * 4 * 4) t *= 2;
+    return t * WT_H;
 }
 
 static inline bool vec_ok(const void* p, size_t stride, int a) { return ((uintptr_t)p % a == 0) && (stride % a == 0); }
@@ -298,15 +600,79 @@ __global__ void __launch_bounds__(256) k_warp_frames(const uint8_t* __restrict__
     warp_pixel<false>(src + blockIdx.z * sframe, sw, sh, sstride, wps[blockIdx.z].m, 0, 0, x, y, o);
 }
 
+// ---- host side of the TMA path ------------------------------------------------------------------------
+typedef CUresult (*TmaEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmaEncodeFn tma_encode_fn() {
+    static TmaEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (TmaEncodeFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+static inline bool tma_geometry_ok(const void* base, int w, size_t stride, size_t frame_bytes, int n) {
+    return ((uintptr_t)base % 16 == 0) && stride % 16 == 0 && (n <= 1 || frame_bytes % 16 == 0) && w % 4 == 0 &&
+           (size_t)w * 3 <= stride && w >= 16;
+}
+// tensor map over {row words (u32), rows, frames}; box = one raw source box (WT_RAW_WORDS x WT_ROWS x 1)
+static bool tma_make_map(CUtensorMap* m, const uint8_t* base, int w, int h, size_t stride, size_t frame_bytes, int n) {
+    TmaEncodeFn enc = tma_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)w * 3 / 4, (cuuint64_t)h, (cuuint64_t)(n > 0 ? n : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)stride, (cuuint64_t)(n > 1 ? frame_bytes : stride * (size_t)h)};
+    cuuint32_t box[3] = {WT_RAW_WORDS, WT_ROWS, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool tma_kernel_ready() {
+    static int state[64] = {0};                   // per device: 0 unknown, 1 ready, -1 unavailable
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    if (state[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(k_warp_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_TMA_SMEM);
+        state[dev] = (e == cudaSuccess && tma_encode_fn()) ? 1 : -1;
+        cudaGetLastError();
+    }
+    return state[dev] == 1;
+}
+
 static void launch_warp_plain(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, const WarpGeom& g,
                               cudaStream_t st) {
-    bool sv = true, dv = true;
+    bool sv = true, dv = true, tma = tma_kernel_ready() && (n_lanes <= WT_TMA_MAXPACK || g.d_tmaps != nullptr);
     for (int i = 0; i < n_lanes; ++i) {
         sv = sv && vec_ok(src.p[i], g.src_stride, 4);
         dv = dv && vec_ok(dst.p[i], g.out_stride, 4);
+        tma = tma && tma_geometry_ok(src.p[i], g.src_w, g.src_stride, 0, 1);
     }
-    dim3 grid((g.out_w + WT_W - 1) / WT_W, (g.out_h + WT_H - 1) / WT_H, n_lanes);
-    k_warp_tiled_lanes<<<grid, WT_THREADS, 0, st>>>(lanes, src, dst, g, sv ? 1 : 0, dv ? 1 : 0);
+    const int rows = strip_rows(g.out_w, g.out_h, n_lanes);
+    dim3 grid((g.out_w + WT_W - 1) / WT_W, (g.out_h + rows - 1) / rows, n_lanes);
+    if (tma) {
+        TmapPack pack;
+        CUtensorMap big[VS_MAX_GROUP];
+        CUtensorMap* maps = n_lanes <= WT_TMA_MAXPACK ? pack.m : big;
+        for (int i = 0; i < n_lanes && tma; ++i) tma = tma_make_map(maps + i, src.p[i], g.src_w, g.src_h, g.src_stride, 0, 1);
+        if (tma) {
+            const CUtensorMap* dmaps = nullptr;
+            if (n_lanes > WT_TMA_MAXPACK) {
+                cudaMemcpyAsync(g.d_tmaps, big, sizeof(CUtensorMap) * n_lanes, cudaMemcpyHostToDevice, st);
+                dmaps = (const CUtensorMap*)g.d_tmaps;
+            }
+            k_warp_tma<<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, dmaps, 1, lanes, nullptr, src, nullptr, 0, g.src_stride,
+                                                               g.src_w, g.src_h, dst, nullptr, 0, g.out_w, g.out_h, g.out_stride,
+                                                               rows, dv ? 1 : 0);
+            return;
+        }
+    }
+    k_warp_tiled_lanes<<<grid, WT_THREADS, 0, st>>>(lanes, src, dst, g, rows, sv ? 1 : 0, dv ? 1 : 0);
 }
 
 void launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, WarpGeom g,
@@ -337,8 +703,19 @@ void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, si
                           uint8_t* dst, int dw, int dh, size_t dstride, size_t dframe,
                           const WarpParams* d_wp, int n_frames, cudaStream_t st) {
     const bool sv = vec_ok(src, sstride, 4) && sframe % 4 == 0, dv = vec_ok(dst, dstride, 4) && dframe % 4 == 0;
-    dim3 grid((dw + WT_W - 1) / WT_W, (dh + WT_H - 1) / WT_H, n_frames);
-    k_warp_tiled_frames<<<grid, WT_THREADS, 0, st>>>(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp,
+    const int rows = strip_rows(dw, dh, n_frames);
+    dim3 grid((dw + WT_W - 1) / WT_W, (dh + rows - 1) / rows, n_frames);
+    if (tma_kernel_ready() && tma_geometry_ok(src, sw, sstride, sframe, n_frames)) {
+        TmapPack pack;
+        if (tma_make_map(pack.m, src, sw, sh, sstride, sframe, n_frames)) {
+            PtrPack sp{};
+            MutPtrPack dp{};
+            k_warp_tma<<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, nullptr, 0, nullptr, d_wp, sp, src, sframe, sstride, sw, sh, dp,
+                                                               dst, dframe, dw, dh, dstride, rows, dv ? 1 : 0);
+            return;
+        }
+    }
+    k_warp_tiled_frames<<<grid, WT_THREADS, 0, st>>>(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp, rows,
                                                      sv ? 1 : 0, dv ? 1 : 0);
 }
 
