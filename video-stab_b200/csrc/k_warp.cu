@@ -302,7 +302,8 @@ static __device__ __forceinline__ void warp_strip(WarpTileSmem& S, const uint8_t
             for (int j = 0; j < 4; ++j) {
                 const uint32_t T1 = rxT + adT[j];                     // box-relative x, 14 fractional bits
                 const uint32_t t2 = ryS + bd[j];
-                const uint32_t a = (t2 & 0xFFFFFC00u) + ((T1 >> 14) << 2);   // &S.src[sy][sx]
+                uint32_t a;                                           // &S.src[sy][sx] = (t2 & ~1023) + 4 * (T1 >> 14)
+                asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(T1 >> 14), "r"(t2 & 0xFFFFFC00u));
                 const uint32_t A16 = T1 & 0x3E00u;                    // 512 * ax
                 const uint32_t W16 = A16 * 0xFFFFu + 16384u;          // u16 pair (16384 - 512 ax | 512 ax)
                 const uint32_t B = t2 & 0x3E0u, Bc = 1024u - B;       // 32 * ay, 32 * (32 - ay)
@@ -354,8 +355,11 @@ static __device__ __forceinline__ void warp_strip(WarpTileSmem& S, const uint8_t
 #define WT_RAW_PITCH 480                 // bytes per raw row: 3 * (12 + 4 * WT_GRPS + 1) = 471 rounded to 16; TMA needs a 16-byte
                                          // aligned start, i.e. a 16-pixel aligned box origin (48 bytes), hence the 12 extra pixels
 #define WT_RAW_WORDS (WT_RAW_PITCH / 4)
-#define WT_TMA_SMEM (WT_ROWS * WT_PITCHW * 4 + WT_ROWS * WT_RAW_PITCH + (WT_THREADS / 32) * WT_W * 4 + WT_H * WT_MAXT * 8 + 64 + 16)
+#define WT_TPITCH 640                    // shared row pitch of the re-packed box in the TMA kernel (160 words; 4 CTAs/SM)
+#define WT_TMA_SMEM (WT_ROWS * WT_TPITCH + WT_ROWS * WT_RAW_PITCH + (WT_THREADS / 32) * WT_W * 4 + WT_H * WT_MAXT * 8 + 64 + 16)
 #define WT_TMA_MAXPACK 8
+#define WT_TGRPS 40                      // re-pack thread map: threads per row (WT_GRPS of them active)
+#define WT_TSROWS 6                      // rows in flight: 40 x 6 = 240 threads, 7 iterations cover WT_ROWS
 
 struct TmapPack {
     CUtensorMap m[WT_TMA_MAXPACK];
@@ -374,7 +378,7 @@ static __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
 }
 
 // lanes_mode: one 2-D-like map per lane (maps[z], frame coordinate 0); else one map, frame coordinate z
-__global__ void __launch_bounds__(WT_THREADS, 3)
+__global__ void __launch_bounds__(WT_THREADS, 4)
 k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict__ dmaps, int lanes_mode,
            const LaneDev* __restrict__ lanes, const WarpParams* __restrict__ wps,
            PtrPack srcp, const uint8_t* __restrict__ src0, size_t sframe, size_t sstride, int sw, int sh,
@@ -382,7 +386,7 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
            int rows_per_cta, int dst_vec) {
     extern __shared__ __align__(1024) unsigned char wt_smem[];
     uint32_t* const S_src = reinterpret_cast<uint32_t*>(wt_smem);
-    unsigned char* const S_raw = wt_smem + WT_ROWS * WT_PITCHW * 4;
+    unsigned char* const S_raw = wt_smem + WT_ROWS * WT_TPITCH;
     uint32_t* const S_out = reinterpret_cast<uint32_t*>(S_raw + WT_ROWS * WT_RAW_PITCH);
     int2* const S_rowXY = reinterpret_cast<int2*>(S_out + (WT_THREADS / 32) * WT_W);
     int (*S_box)[8] = reinterpret_cast<int (*)[8]>(S_rowXY + WT_H * WT_MAXT);
@@ -429,9 +433,11 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
     const bool vec_out = dst_vec && tw == WT_W;
     const uint32_t s_px = (uint32_t)__cvta_generic_to_shared(S_out + warp * WT_W + lane);
     const uint32_t s_v4 = (uint32_t)__cvta_generic_to_shared(S_out + warp * WT_W + 4 * lane);
-    // re-pack thread map: 36 column groups x 7 rows
-    const int r7 = tid / WT_GRPS, q = tid - r7 * WT_GRPS;
-    const uint32_t s_stage = s_src + (uint32_t)(r7 * WT_PITCHW + 4 * q) * 4u;
+    // re-pack thread map: 40 threads per row (36 active column groups) x 6 rows.  40 = 8 * 5 keeps every
+    // quarter-warp of the 16-byte stores inside one row, and 3 q + 120 r (the raw word bank of lane (q, r), raw
+    // pitch 480 bytes) is collision-free across the two rows a warp can straddle: both accesses are conflict free.
+    const int r7 = tid / WT_TGRPS, q = tid - r7 * WT_TGRPS;
+    const uint32_t s_stage = s_src + (uint32_t)(r7 * WT_TPITCH + 16 * q);
     const uint32_t s_rawt = s_raw + (uint32_t)(r7 * WT_RAW_PITCH + 12 * q);
 
     // source box of the tile starting at row y0 -> S_box[b]; issues its fetch when the box fits (thread 0 only)
@@ -473,20 +479,20 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
             // ---- 2. wait for the raw box, re-pack it: one task = 16 raw bytes -> 4 words [B G R R']
             mbar_wait(s_mbar, phase);
             phase ^= 1;
-            const bool colok = q < ngrp && r7 < WT_SROWS;
+            const bool colok = q < ngrp && r7 < WT_TSROWS;
             const uint32_t s_rawq = s_rawt + (uint32_t)S_box[buf][5];
 #define WT_REPACK(k)                                                                                           \
-            if ((k) * WT_SROWS < nrows) {                               /* CTA-uniform */                      \
-                if (colok && r7 + (k) * WT_SROWS < nrows) {                                                    \
-                    const uint32_t w0 = lds32<(k) * WT_SROWS * WT_RAW_PITCH>(s_rawq);                          \
-                    const uint32_t w1 = lds32<(k) * WT_SROWS * WT_RAW_PITCH + 4>(s_rawq);                      \
-                    const uint32_t w2 = lds32<(k) * WT_SROWS * WT_RAW_PITCH + 8>(s_rawq);                      \
-                    const uint32_t w3 = lds32<(k) * WT_SROWS * WT_RAW_PITCH + 12>(s_rawq);                     \
+            if ((k) * WT_TSROWS < nrows) {                               /* CTA-uniform */                      \
+                if (colok && r7 + (k) * WT_TSROWS < nrows) {                                                    \
+                    const uint32_t w0 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH>(s_rawq);                          \
+                    const uint32_t w1 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 4>(s_rawq);                      \
+                    const uint32_t w2 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 8>(s_rawq);                      \
+                    const uint32_t w3 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 12>(s_rawq);                     \
                     const uint4 o = repack_bgrr(w0, w1, w2, w3);                                               \
-                    sts128<(k) * WT_SROWS * WT_PITCHW * 4>(s_stage, o.x, o.y, o.z, o.w);                       \
+                    sts128<(k) * WT_TSROWS * WT_TPITCH>(s_stage, o.x, o.y, o.z, o.w);                       \
                 }                                                                                              \
             }
-            WT_REPACK(0) WT_REPACK(1) WT_REPACK(2) WT_REPACK(3) WT_REPACK(4) WT_REPACK(5)
+            WT_REPACK(0) WT_REPACK(1) WT_REPACK(2) WT_REPACK(3) WT_REPACK(4) WT_REPACK(5) WT_REPACK(6)
 #undef WT_REPACK
         }
         __syncthreads();                                   // S_src ready, raw box free
@@ -499,7 +505,7 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
             }
         } else {
             // ---- 3. compute: warp -> rows, lane -> pixels x0 + lane + 32 j
-            const uint32_t bx14 = (uint32_t)ax0 << 14, by10 = ((uint32_t)by0 << 10) - s_src;
+            const uint32_t bx14 = (uint32_t)ax0 << 14, by10 = (uint32_t)by0 << 10;
             uint8_t* grow = dst + (size_t)(y0 + warp) * dstride + (size_t)x0 * 3 + (vec_out ? 12 * lane : 0);
 #pragma unroll
             for (int rr = warp; rr < WT_H; rr += WT_THREADS / 32) {
@@ -512,11 +518,11 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t T1 = rxT + adT[j];
                     const uint32_t t2 = ryS + bd[j];
-                    const uint32_t a = (t2 & 0xFFFFFC00u) + ((T1 >> 14) << 2);
+                    const uint32_t a = s_src + 4u * ((t2 >> 10) * (WT_TPITCH / 4) + (T1 >> 14));   // &S_src[sy][sx]
                     const uint32_t A16 = T1 & 0x3E00u;
                     const uint32_t W16 = A16 * 0xFFFFu + 16384u;
                     const uint32_t B = t2 & 0x3E0u, Bc = 1024u - B;
-                    const uint32_t t00 = lds32<0>(a), t01 = lds32<4>(a), t10 = lds32<WT_PITCHW * 4>(a), t11 = lds32<WT_PITCHW * 4 + 4>(a);
+                    const uint32_t t00 = lds32<0>(a), t01 = lds32<4>(a), t10 = lds32<WT_TPITCH>(a), t11 = lds32<WT_TPITCH + 4>(a);
                     const uint32_t u0 = __byte_perm(t00, t01, 0x5140);
                     const uint32_t l0 = __byte_perm(t10, t11, 0x5140);
                     const uint32_t hb0 = __dp2a_lo(W16, u0, 0u), hg0 = __dp2a_hi(W16, u0, 0u), hr0 = __dp2a_hi(W16, t00, 0u);
