@@ -108,12 +108,13 @@ static __device__ __forceinline__ void warp_pixel(const uint8_t* __restrict__ sr
 #define WT_GRPS 36                   // 4-pixel column groups of the staged box (box width <= 144)
 #define WT_SROWS 7                   // staging rows in flight: 36 x 7 = 252 threads
 #define WT_STAGE_IT 6                // staging tasks per thread (7 * 6 = 42 = WT_ROWS)
-#define WT_MAXT 4                    // tiles per CTA strip
+#define WT_MAXT 4                    // tiles per CTA strip (TMA kernel; 8 measured no faster: tail imbalance)
+#define WT_MAXT_F 4                  // tiles per CTA strip (fallback kernel: static shared memory limit)
 
 struct WarpTileSmem {
     uint32_t src[WT_ROWS * WT_PITCHW];        // must stay first: 1024-byte aligned (the row offset trick)
     uint32_t out[(WT_THREADS / 32) * WT_W];   // one BGRx output row per warp (4 KB); aliased by colAB in the strip prologue
-    int2 rowXY[WT_H * WT_MAXT];
+    int2 rowXY[WT_H * WT_MAXT_F];
     int box[2][8];                            // ax0, by0, ngrp, nrows, ok, interior
 };
 
@@ -191,9 +192,11 @@ static __device__ __forceinline__ void warp_strip(WarpTileSmem& S, const uint8_t
     if (tid < WT_W) {
         const double xd = (double)min(x0 + tid, dw - 1);
         colAB[tid] = make_int2(sat_int(m[0] * xd * 1024.0), sat_int(m[3] * xd * 1024.0));
-    } else if (tid - WT_W < ye - ys) {
-        const double yd = (double)(ys + tid - WT_W);
-        S.rowXY[tid - WT_W] = make_int2(sat_int((m[1] * yd + m[2]) * 1024.0) + 16, sat_int((m[4] * yd + m[5]) * 1024.0) + 16);
+    } else {
+        for (int r = tid - WT_W; r < ye - ys; r += WT_THREADS - WT_W) {
+            const double yd = (double)(ys + r);
+            S.rowXY[r] = make_int2(sat_int((m[1] * yd + m[2]) * 1024.0) + 16, sat_int((m[4] * yd + m[5]) * 1024.0) + 16);
+        }
     }
     __syncthreads();
     uint32_t adT[4], bd[4];
@@ -410,9 +413,11 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
     if (tid < WT_W) {
         const double xd = (double)min(x0 + tid, dw - 1);
         colAB[tid] = make_int2(sat_int(m[0] * xd * 1024.0), sat_int(m[3] * xd * 1024.0));
-    } else if (tid - WT_W < ye - ys) {
-        const double yd = (double)(ys + tid - WT_W);
-        S_rowXY[tid - WT_W] = make_int2(sat_int((m[1] * yd + m[2]) * 1024.0) + 16, sat_int((m[4] * yd + m[5]) * 1024.0) + 16);
+    } else {
+        for (int r = tid - WT_W; r < ye - ys; r += WT_THREADS - WT_W) {
+            const double yd = (double)(ys + r);
+            S_rowXY[r] = make_int2(sat_int((m[1] * yd + m[2]) * 1024.0) + 16, sat_int((m[4] * yd + m[5]) * 1024.0) + 16);
+        }
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(s_mbar));
@@ -577,10 +582,10 @@ __global__ void __launch_bounds__(WT_THREADS, 4) k_warp_tiled_frames(const uint8
 }
 
 // tiles per CTA strip: enough CTAs to fill the machine first (148 SMs x 4 resident CTAs), then longer strips
-static inline int strip_rows(int dw, int dh, int n_frames) {
+static inline int strip_rows(int dw, int dh, int n_frames, int max_tiles) {
     const long tiles = (long)((dw + WT_W - 1) / WT_W) * ((dh + WT_H - 1) / WT_H) * n_frames;
     int t = 1;
-    while (t < WT_MAXT && tiles / (t * 2) >= 148L * 4 * 4) t *= 2;
+    while (t < max_tiles && tiles / (t * 2) >= 148L * 4 * 4) t *= 2;
     return t * WT_H;
 }
 
@@ -659,9 +664,9 @@ static void launch_warp_plain(const LaneDev* lanes, int n_lanes, const PtrPack& 
         dv = dv && vec_ok(dst.p[i], g.out_stride, 4);
         tma = tma && tma_geometry_ok(src.p[i], g.src_w, g.src_stride, 0, 1);
     }
-    const int rows = strip_rows(g.out_w, g.out_h, n_lanes);
-    dim3 grid((g.out_w + WT_W - 1) / WT_W, (g.out_h + rows - 1) / rows, n_lanes);
     if (tma) {
+        const int rows = strip_rows(g.out_w, g.out_h, n_lanes, WT_MAXT);
+        dim3 grid((g.out_w + WT_W - 1) / WT_W, (g.out_h + rows - 1) / rows, n_lanes);
         TmapPack pack;
         CUtensorMap big[VS_MAX_GROUP];
         CUtensorMap* maps = n_lanes <= WT_TMA_MAXPACK ? pack.m : big;
@@ -678,6 +683,8 @@ static void launch_warp_plain(const LaneDev* lanes, int n_lanes, const PtrPack& 
             return;
         }
     }
+    const int rows = strip_rows(g.out_w, g.out_h, n_lanes, WT_MAXT_F);
+    dim3 grid((g.out_w + WT_W - 1) / WT_W, (g.out_h + rows - 1) / rows, n_lanes);
     k_warp_tiled_lanes<<<grid, WT_THREADS, 0, st>>>(lanes, src, dst, g, rows, sv ? 1 : 0, dv ? 1 : 0);
 }
 
@@ -709,9 +716,9 @@ void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, si
                           uint8_t* dst, int dw, int dh, size_t dstride, size_t dframe,
                           const WarpParams* d_wp, int n_frames, cudaStream_t st) {
     const bool sv = vec_ok(src, sstride, 4) && sframe % 4 == 0, dv = vec_ok(dst, dstride, 4) && dframe % 4 == 0;
-    const int rows = strip_rows(dw, dh, n_frames);
-    dim3 grid((dw + WT_W - 1) / WT_W, (dh + rows - 1) / rows, n_frames);
     if (tma_kernel_ready() && tma_geometry_ok(src, sw, sstride, sframe, n_frames)) {
+        const int rows = strip_rows(dw, dh, n_frames, WT_MAXT);
+        dim3 grid((dw + WT_W - 1) / WT_W, (dh + rows - 1) / rows, n_frames);
         TmapPack pack;
         if (tma_make_map(pack.m, src, sw, sh, sstride, sframe, n_frames)) {
             PtrPack sp{};
@@ -721,6 +728,8 @@ void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, si
             return;
         }
     }
+    const int rows = strip_rows(dw, dh, n_frames, WT_MAXT_F);
+    dim3 grid((dw + WT_W - 1) / WT_W, (dh + rows - 1) / rows, n_frames);
     k_warp_tiled_frames<<<grid, WT_THREADS, 0, st>>>(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp, rows,
                                                      sv ? 1 : 0, dv ? 1 : 0);
 }
