@@ -212,6 +212,7 @@ def run_gpu(args, rank, world, local_rank):
     e0.record(ext)
     for _ in range(args.steps):
         step()
+    st.join()                      # the public stream waits for the handle's analysis / detection streams
     e1.record(ext)
     st.sync()
     barrier()

@@ -167,8 +167,12 @@ vs_status vs_stabilizer_push_device(vs_stabilizer* s, const uint8_t* d_bgr, int 
 vs_status vs_stabilizer_flush_device(vs_stabilizer* s, uint8_t* d_out, size_t out_stride, size_t out_capacity,
                                      int* out_width, int* out_height, int* produced);
 vs_status vs_stabilizer_sync(vs_stabilizer* s);
-/* cudaStream_t of the handle (as void*), so callers can time/order work on it. */
+/* cudaStream_t of the handle (as void*), so callers can time/order work on it.  A handle runs its analysis and
+ * corner-detection kernels on two further internal streams; every OUTPUT frame is produced on this public
+ * stream.  vs_stabilizer_join() makes the public stream wait for everything enqueued so far on the internal
+ * ones (so an event recorded on it afterwards covers all the handle's work) without blocking the host. */
 void*     vs_stabilizer_stream(vs_stabilizer* s);
+vs_status vs_stabilizer_join(vs_stabilizer* s);
 
 /* Diagnostics: number of frames analysed so far / outputs produced so far, and their records
  * (synchronises the stream).  Used by the parity tests; not on the hot path. */
@@ -219,6 +223,7 @@ vs_status vs_batch_push_device(vs_batch* b, const uint8_t* const* d_frames, int 
 vs_status vs_batch_flush_device(vs_batch* b, uint8_t* const* d_outs, size_t out_stride, size_t out_capacity,
                                 int* out_width, int* out_height, int* produced);
 vs_status vs_batch_sync(vs_batch* b);
+vs_status vs_batch_join(vs_batch* b);
 void*     vs_batch_stream(vs_batch* b);
 vs_status vs_batch_launch_count(vs_batch* b, uint64_t* n);
 vs_status vs_batch_set_timing(vs_batch* b, int enable);

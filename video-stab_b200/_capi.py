@@ -64,6 +64,7 @@ SYMBOLS = {
     "vs_stabilizer_push_device": (_I, [_P, _U8P, _I, _I, _SZ, _U8P, _SZ, _SZ, C.c_uint, _IP, _IP, _IP]),
     "vs_stabilizer_flush_device": (_I, [_P, _U8P, _SZ, _SZ, _IP, _IP, _IP]),
     "vs_stabilizer_sync": (_I, [_P]),
+    "vs_stabilizer_join": (_I, [_P]),
     "vs_stabilizer_stream": (_P, [_P]),
     "vs_stabilizer_counts": (_I, [_P, _IP, _IP]),
     "vs_stabilizer_frame_record": (_I, [_P, _I, C.POINTER(VsFrameRecord)]),
@@ -83,6 +84,7 @@ SYMBOLS = {
     "vs_batch_push_device": (_I, [_P, C.POINTER(_P), _I, _I, _SZ, C.POINTER(_P), _SZ, _SZ, C.c_uint, _IP, _IP, _IP]),
     "vs_batch_flush_device": (_I, [_P, C.POINTER(_P), _SZ, _SZ, _IP, _IP, _IP]),
     "vs_batch_sync": (_I, [_P]),
+    "vs_batch_join": (_I, [_P]),
     "vs_batch_stream": (_P, [_P]),
     "vs_batch_launch_count": (_I, [_P, C.POINTER(C.c_uint64)]),
     "vs_batch_stream_counts": (_I, [_P, _I, _IP, _IP]),

@@ -202,6 +202,7 @@ vs_status vs_stabilizer_flush_device(vs_stabilizer* s, uint8_t* d_out, size_t ou
     API_END
 }
 vs_status vs_stabilizer_sync(vs_stabilizer* s) { return s ? s->eng->sync() : vs_set_error(VS_ERR_INVALID_ARG, "null handle"); }
+vs_status vs_stabilizer_join(vs_stabilizer* s) { return s ? s->eng->join() : vs_set_error(VS_ERR_INVALID_ARG, "null handle"); }
 void* vs_stabilizer_stream(vs_stabilizer* s) { return s ? (void*)s->eng->stream() : nullptr; }
 vs_status vs_stabilizer_counts(vs_stabilizer* s, int* nf, int* no) {
     if (!s) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
@@ -282,6 +283,7 @@ vs_status vs_batch_flush_device(vs_batch* b, uint8_t* const* d_outs, size_t out_
     API_END
 }
 vs_status vs_batch_sync(vs_batch* b) { return b ? b->eng->sync() : vs_set_error(VS_ERR_INVALID_ARG, "null handle"); }
+vs_status vs_batch_join(vs_batch* b) { return b ? b->eng->join() : vs_set_error(VS_ERR_INVALID_ARG, "null handle"); }
 void* vs_batch_stream(vs_batch* b) { return b ? (void*)b->eng->stream() : nullptr; }
 vs_status vs_batch_launch_count(vs_batch* b, uint64_t* n) {
     if (!b || !n) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
@@ -405,7 +407,7 @@ vs_status vs_k_good_features(const uint8_t* d_gray, int w, int h, int max_corner
     const int slot = (w == VS_FW) ? -1 : 0;
     launch_pack_level(d_gray, slot < 0 ? L.small0 : L.pyr[0].lv[0], st);
     e->reset_detect_counters();
-    launch_good_features(e->d_lanes(), 1, slot, max_corners, quality, min_dist, 0, st);
+    launch_good_features(e->d_lanes(), 1, slot, max_corners, quality, min_dist, 0, 0, st);
     int n = 0;
     cudaError_t ce = cudaMemcpyAsync(&n, L.kp_count, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
@@ -437,7 +439,7 @@ vs_status vs_k_pyr_lk(const uint8_t* d_prev, const uint8_t* d_next, int w, int h
     cudaError_t ce = cudaMemcpyAsync(L.kp, pts_xy_host, sizeof(float2) * n, cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(L.kp_count, &n, sizeof(int), cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess) {
-        launch_pyr_lk(e->d_lanes(), 1, 0, 1, n, st);
+        launch_pyr_lk(e->d_lanes(), 1, 0, 1, n, 0, 0, st);
         ce = cudaStreamSynchronize(st);
     }
     if (ce == cudaSuccess && n > 0) {

@@ -48,10 +48,16 @@ struct LaneDev {
     unsigned long long* cand;       // corner candidates: (float bits << 32) | linear address
     int* cand_count;
     unsigned int* grid;             // min-distance grid: per cell [count, slot0..slot3]
-    float2* kp;                     // "prevKeypointsCPU_"
+    float2* kp;                     // "prevKeypointsCPU_"  (slot 0; the single-kernel entry points use these four)
     int* kp_count;
     float2* lk_next;
     uint8_t* lk_status;
+    // double-buffered copies so that detection / tracking / motion of neighbouring frames can overlap on
+    // different CUDA streams (engine.cu): key points by detection generation, tracker output by frame parity
+    float2* kpb[2];
+    int* kpc[2];
+    float2* lkn[2];
+    uint8_t* lks[2];
     uint8_t* inlier_mask;
     float* transforms;              // 3 floats per frame  (transforms_)
     float* path;                    // 3 floats per frame  (path_)
@@ -86,6 +92,9 @@ struct StepInfo {
     int n_out;             // output-record slot
     int adaptive;          // adaptiveSmoothing
     int min_radius, max_radius;
+    int kp_slot;           // key-point buffer this frame tracks from (LaneDev::kpb)
+    int lk_slot;           // tracker output buffer of this frame (LaneDev::lkn / lks)
+    int will_detect;       // corners are re-detected on this frame (the detector writes n_detected itself)
 };
 
 static __device__ __forceinline__ int reflect101(int p, int len) {

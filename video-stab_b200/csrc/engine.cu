@@ -24,9 +24,9 @@ extern "C" const char* vs_last_error(void) { return g_err; }
 
 // ---- optional per-stage CUDA-event timing (bench / profiles); off by default
 struct StageScope {
-    Engine* e; int stage; cudaEvent_t a = nullptr, b = nullptr;
-    StageScope(Engine* e_, int s) : e(e_), stage(s) { if (e->timing_on()) { a = e->take_event(); b = e->take_event(); cudaEventRecord(a, e->stream()); } }
-    ~StageScope() { if (a) { cudaEventRecord(b, e->stream()); e->add_pending(stage, a, b); } }
+    Engine* e; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    StageScope(Engine* e_, int s, cudaStream_t st_) : e(e_), stage(s), st(st_) { if (e->timing_on()) { a = e->take_event(); b = e->take_event(); cudaEventRecord(a, st); } }
+    ~StageScope() { if (a) { cudaEventRecord(b, st); e->add_pending(stage, a, b); } }
 };
 
 cudaEvent_t Engine::take_event() {
@@ -41,7 +41,7 @@ void Engine::add_pending(int stage, cudaEvent_t a, cudaEvent_t b) {
 }
 void Engine::collect_timing() {
     if (pending_.empty()) return;
-    cudaStreamSynchronize(stream_);
+    sync();
     for (auto& p : pending_) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { stage_ms_[p.stage] += ms; stage_n_[p.stage] += 1; }
@@ -118,6 +118,18 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     n_lanes_ = n_lanes;
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    // Three streams per handle (engine.h): analysis (gray, pyramid, LK), motion + output (the public stream), and
+    // corner detection.  adaptive_smoothing reads one int back per frame, so that mode stays on one stream.
+    multi_ = !p.adaptive_smoothing;
+    if (multi_) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&sA_, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sC_, cudaStreamNonBlocking));
+        for (auto& ev : evA_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : evB_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : evJ_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&evG_, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&evC_, cudaEventDisableTiming));
+    }
     // mapBorderMode, Stabilizer.cpp:31-38 and the cropNZoom override :67-71
     border_mode_ = !strcmp(p.border_type, "reflect") ? 2 : !strcmp(p.border_type, "reflect_101") ? 4
                  : !strcmp(p.border_type, "replicate") ? 1 : !strcmp(p.border_type, "wrap") ? 3 : 0;
@@ -138,7 +150,7 @@ vs_status Engine::alloc_fixed() {
     VS_TRY(dalloc(allocs_, &d_lanes_, (size_t)n_lanes_));
     VS_TRY(dalloc(allocs_, &d_detect_counters_, (size_t)n_lanes_ * 2));
     int* small_counters = nullptr;
-    VS_TRY(dalloc(allocs_, &small_counters, (size_t)n_lanes_ * 2));
+    VS_TRY(dalloc(allocs_, &small_counters, (size_t)n_lanes_ * 3));
     size_t gw = gftt_grid_words(VS_FW, VS_FH, p_.min_distance);
     size_t gw2 = gftt_grid_words(VS_AW, VS_AH, 15.0);
     if (gw2 > gw) gw = gw2;
@@ -161,12 +173,18 @@ vs_status Engine::alloc_fixed() {
         VS_TRY(dalloc(allocs_, &L.grid, gw));
         L.eig_max = d_detect_counters_ + 2 * l;
         L.cand_count = (int*)(d_detect_counters_ + 2 * l + 1);
-        L.kp_count = small_counters + 2 * l;
-        L.first_count = small_counters + 2 * l + 1;
+        L.kp_count = small_counters + 3 * l;
+        L.first_count = small_counters + 3 * l + 1;
+        L.kpc[0] = L.kp_count;
+        L.kpc[1] = small_counters + 3 * l + 2;
         VS_TRY(dalloc(allocs_, &L.kp, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.lk_next, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.lk_status, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.inlier_mask, (size_t)kp_cap_));
+        L.kpb[0] = L.kp; L.lkn[0] = L.lk_next; L.lks[0] = L.lk_status;
+        VS_TRY(dalloc(allocs_, &L.kpb[1], (size_t)kp_cap_));
+        VS_TRY(dalloc(allocs_, &L.lkn[1], (size_t)kp_cap_));
+        VS_TRY(dalloc(allocs_, &L.lks[1], (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.first_corners, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.kalman, (size_t)VS_KAL_FLOATS));
         VS_TRY(dalloc(allocs_, &L.wp, (size_t)1));
@@ -191,7 +209,7 @@ vs_status Engine::alloc_fixed() {
 }
 
 vs_status Engine::grow_trajectory() {
-    CUDA_TRY(cudaStreamSynchronize(stream_));
+    VS_TRY(sync());
     int ncap = traj_cap_ * 2;
     for (int l = 0; l < n_lanes_; ++l) {
         LaneDev& L = h_lanes_[l];
@@ -218,8 +236,15 @@ vs_status Engine::grow_trajectory() {
 }
 
 void Engine::free_all() {
-    if (stream_) cudaStreamSynchronize(stream_);
+    sync();
     collect_timing();
+    for (auto& ev : evA_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : evB_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : evJ_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+    if (evG_) { cudaEventDestroy(evG_); evG_ = nullptr; }
+    if (evC_) { cudaEventDestroy(evC_); evC_ = nullptr; }
+    if (sA_) { cudaStreamDestroy(sA_); sA_ = nullptr; }
+    if (sC_) { cudaStreamDestroy(sC_); sC_ = nullptr; }
     for (cudaEvent_t ev : event_pool_) cudaEventDestroy(ev);
     event_pool_.clear();
     for (auto& L : h_lanes_) {
@@ -244,13 +269,27 @@ Engine::~Engine() {
 }
 
 vs_status Engine::sync() {
-    CUDA_TRY(cudaStreamSynchronize(stream_));
+    if (sA_) CUDA_TRY(cudaStreamSynchronize(sA_));
+    if (sC_) CUDA_TRY(cudaStreamSynchronize(sC_));
+    if (stream_) CUDA_TRY(cudaStreamSynchronize(stream_));
+    return VS_OK;
+}
+
+// Orders everything enqueued so far (on all three streams) before whatever is enqueued on the public stream next.
+vs_status Engine::join() {
+    if (!multi_) return VS_OK;
+    CUDA_TRY(cudaEventRecord(evJ_[0], sA_));
+    CUDA_TRY(cudaEventRecord(evJ_[1], sC_));
+    CUDA_TRY(cudaStreamWaitEvent(stream_, evJ_[0], 0));
+    CUDA_TRY(cudaStreamWaitEvent(stream_, evJ_[1], 0));
     return VS_OK;
 }
 
 vs_status Engine::clean() {
     // Stabilizer::clean, Stabilizer.cpp:221-256
-    CUDA_TRY(cudaStreamSynchronize(stream_));
+    VS_TRY(sync());
+    for (bool& b : evB_set_) b = false;
+    c_pending_ = false;
     queue_.clear();
     first_ = true;
     next_index_ = 0;
@@ -295,29 +334,77 @@ StepInfo Engine::step_info(int pop_index) const {
     s.adaptive = p_.adaptive_smoothing;
     s.min_radius = p_.min_smoothing_radius;
     s.max_radius = p_.max_smoothing_radius;
+    s.kp_slot = ((n_frames_ - 1) / 2) & 1;
+    s.lk_slot = n_frames_ & 1;
+    s.will_detect = ((detect_counter_ + 1) % 2) == 0;            // (++featureDetectionCounter % 2) == 0, Stabilizer.cpp:696-697
     return s;
 }
 
-// generateTransform, Stabilizer.cpp:402-761 (CPU branch) as a launch sequence
+// First-frame analysis (Stabilizer.cpp:271-368): 480x270 gray + GFTT with the user's parameters -> key-point slot 0
+vs_status Engine::first_frame_detect(const PtrPack& src, int w, int h, size_t stride) {
+    launch_gray_resize(d_lanes_, n_lanes_, src, w, h, stride, -1, sa());                  // :304-305
+    if (multi_) { CUDA_TRY(cudaEventRecord(evG_, sa())); CUDA_TRY(cudaStreamWaitEvent(sc(), evG_, 0)); }
+    CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc()));
+    launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, 0, sc());  // :355-357
+    if (multi_) { CUDA_TRY(cudaEventRecord(evC_, sc())); c_pending_ = true; }
+    launches_ += 4;
+    return VS_OK;
+}
+
+// Corner re-detection on analysis frame `frame_no` (pyramid slot `cur`) -> key-point slot (frame_no / 2) & 1, on the
+// detection stream.  It reads level 0 of the frame (ready at evG_) and overwrites the key points last read by
+// the motion kernel of frame_no - 2.
+vs_status Engine::redetect(int cur, int frame_no, int record_frame_no) {
+    if (multi_) {
+        CUDA_TRY(cudaStreamWaitEvent(sc(), evG_, 0));
+        if (frame_no >= 2 && evB_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sc(), evB_[(frame_no - 2) & 3], 0));
+    }
+    StageScope t(this, VS_STAGE_GFTT, sc());
+    CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc()));
+    int mc = p_.max_corners < 200 ? p_.max_corners : 200;
+    launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, record_frame_no, (frame_no / 2) & 1, sc());   // :740-744
+    if (multi_) { CUDA_TRY(cudaEventRecord(evC_, sc())); c_pending_ = true; }
+    launches_ += 3;
+    return VS_OK;
+}
+
+// generateTransform, Stabilizer.cpp:402-761 (CPU branch) as a launch sequence over three streams:
+//   A (analysis)  gray -> pyramid -> LK            needs: key points of the last detection (evC_)
+//   B (public)    motion [-> warp, in emit()]      needs: LK of this frame (evA_)
+//   C (detection) min-eig -> candidates -> select  needs: gray of this frame (evG_)
+// Tracker output is double-buffered by frame parity and key points by detection generation, so LK of frame
+// n+1 runs while frame n is still in its motion / detection kernels.
 vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     if (n_frames_ + 1 >= traj_cap_) VS_TRY(grow_trajectory());
     const int frame_no = ++n_frames_;
     const int cur = frame_no & 1, prev = cur ^ 1;
+    const int kp_slot = ((frame_no - 1) / 2) & 1, lk_slot = frame_no & 1;
+    const bool detect = ((detect_counter_ + 1) % 2) == 0;                             // :696-697
     PtrPack src;
     for (int l = 0; l < n_lanes_; ++l) src.p[l] = e.frames[l];
     if (frame_no == 1) {
         // prevGray is still the 480x270 first-frame image: cv::resize it up (Stabilizer.cpp:598-603)
-        launch_upsample_small(d_lanes_, n_lanes_, prev, stream_);
-        launch_pyrdown(d_lanes_, n_lanes_, prev, stream_);
+        launch_upsample_small(d_lanes_, n_lanes_, prev, sa());
+        launch_pyrdown(d_lanes_, n_lanes_, prev, sa());
         launches_ += 3;
     }
-    { StageScope t(this, VS_STAGE_GRAY);
-      launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, stream_); }   // :449-450
-    { StageScope t(this, VS_STAGE_PYRDOWN);
-      launch_pyrdown(d_lanes_, n_lanes_, cur, stream_); }
-    { StageScope t(this, VS_STAGE_LK);
-      launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, stream_); }   // :611-619
+    { StageScope t(this, VS_STAGE_GRAY, sa());
+      launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sa()); }       // :449-450
+    if (multi_ && detect) CUDA_TRY(cudaEventRecord(evG_, sa()));
+    { StageScope t(this, VS_STAGE_PYRDOWN, sa());
+      launch_pyrdown(d_lanes_, n_lanes_, cur, sa()); }
+    if (multi_) {
+        // LK writes tracker slot lk_slot (last read by the motion kernel of frame_no - 2) and reads key points
+        if (frame_no >= 3 && evB_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sa(), evB_[(frame_no - 2) & 3], 0));
+        if (c_pending_) { CUDA_TRY(cudaStreamWaitEvent(sa(), evC_, 0)); c_pending_ = false; }
+    }
+    { StageScope t(this, VS_STAGE_LK, sa());
+      launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa()); }   // :611-619
     launches_ += 4;
+    if (multi_) {
+        CUDA_TRY(cudaEventRecord(evA_[lk_slot], sa()));
+        CUDA_TRY(cudaStreamWaitEvent(stream_, evA_[lk_slot], 0));
+    }
 
     const bool adaptive = p_.adaptive_smoothing != 0;
     int pop_index = -1;
@@ -326,17 +413,13 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         *will_pop = (int)queue_.size() >= gate;
         if (*will_pop) pop_index = queue_.front().index;
     }
-    { StageScope t(this, VS_STAGE_MOTION);
+    { StageScope t(this, VS_STAGE_MOTION, stream_);
       launch_motion(d_lanes_, n_lanes_, step_info(pop_index), stream_); }              // :629-688 (+ :783-908)
     launches_ += 1;
+    if (multi_) { CUDA_TRY(cudaEventRecord(evB_[frame_no & 3], stream_)); evB_set_[frame_no & 3] = true; }
 
-    if ((++detect_counter_ % 2) == 0) {                                               // :696-697
-        StageScope t(this, VS_STAGE_GFTT);
-        CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, stream_));
-        int mc = p_.max_corners < 200 ? p_.max_corners : 200;
-        launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, frame_no, stream_);   // :740-744
-        launches_ += 3;
-    }
+    ++detect_counter_;
+    if (detect) VS_TRY(redetect(cur, frame_no, frame_no));
     if (adaptive) {
         // updateAdaptiveParameters (:691-693, :1562-1574) changes params_.smoothingRadius, which moves the
         // latency gate: the one data-dependent host decision of the path, so this mode reads it back.
@@ -392,7 +475,7 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         g.mode = m2;
         std::vector<uint8_t*> scratch(n_lanes_);
         for (int l = 0; l < n_lanes_; ++l) scratch[l] = d_scratch_ ? d_scratch_ + frame_bytes_ * l : nullptr;
-        { StageScope t(this, VS_STAGE_WARP);
+        { StageScope t(this, VS_STAGE_WARP, stream_);
           launch_warp(d_lanes_, n_lanes_, src, dst, g, scratch.data(), stream_); }
         launches_ += (m2 == 2) ? 1 + n_lanes_ : 1;
     }
@@ -429,7 +512,7 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
         for (int l = 0; l < n_lanes_; ++l) {
             uint8_t* dst = d_ring_ + ((size_t)l * ring_slots_ + e.slot) * frame_bytes_;
             CUDA_TRY(cudaMemcpy2DAsync(dst, tight, frames[l], stride, tight, h,
-                                       host_io ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream_));
+                                       host_io ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, sa()));
             e.frames[l] = dst;
         }
         e.stride = tight;
@@ -439,14 +522,11 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
         // first frame: 480x270 analysis image + GFTT with the user's parameters (:271-368)
         PtrPack src;
         for (int l = 0; l < n_lanes_; ++l) src.p[l] = e.frames[l];
-        launch_gray_resize(d_lanes_, n_lanes_, src, w, h, e.stride, -1, stream_);     // :304-305
-        CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, stream_));
-        launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, stream_);  // :355-357
-        launches_ += 4;
+        VS_TRY(first_frame_detect(src, w, h, e.stride));
         queue_.push_back(e);
         first_ = false;
         next_index_ = 1;
-        if (host_io) CUDA_TRY(cudaStreamSynchronize(stream_));
+        if (host_io) CUDA_TRY(cudaStreamSynchronize(sa()));     // the caller may reuse its frame buffer
         return VS_OK;
     }
     queue_.push_back(e);
@@ -456,7 +536,7 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
         VS_TRY(emit(outs, out_stride, out_capacity, host_io, ow, oh));
         *produced = 1;
     } else if (host_io) {
-        CUDA_TRY(cudaStreamSynchronize(stream_));     // the caller may reuse its frame buffer
+        CUDA_TRY(cudaStreamSynchronize(sa()));        // the caller may reuse its frame buffer
     }
     ++next_index_;
     return VS_OK;
@@ -476,20 +556,20 @@ vs_status Engine::flush(uint8_t* const* outs, size_t out_stride, size_t out_capa
 }
 
 vs_status Engine::reset_detect_counters() {
-    CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, stream_));
+    CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, stream_));   // single-kernel entry points
     return VS_OK;
 }
 
 // ------------------------------------------------------------------------------ diagnostics
 vs_status Engine::frame_record(int lane, int i, vs_frame_record* r) {
     if (lane < 0 || lane >= n_lanes_ || i < 0 || i >= n_frames_ || !r) return vs_set_error(VS_ERR_INVALID_ARG, "bad record index");
-    CUDA_TRY(cudaStreamSynchronize(stream_));
+    VS_TRY(sync());
     CUDA_TRY(cudaMemcpy(r, h_lanes_[lane].frec + i, sizeof(*r), cudaMemcpyDeviceToHost));
     return VS_OK;
 }
 vs_status Engine::output_record(int lane, int i, vs_output_record* r) {
     if (lane < 0 || lane >= n_lanes_ || i < 0 || i >= n_out_ || !r) return vs_set_error(VS_ERR_INVALID_ARG, "bad record index");
-    CUDA_TRY(cudaStreamSynchronize(stream_));
+    VS_TRY(sync());
     CUDA_TRY(cudaMemcpy(r, h_lanes_[lane].orec + i, sizeof(*r), cudaMemcpyDeviceToHost));
     return VS_OK;
 }
@@ -509,7 +589,7 @@ vs_status Engine::frame_points(int lane, int i, float* prev, float* next, uint8_
 }
 vs_status Engine::first_corners(int lane, float* xy, int cap, int* n) {
     if (lane < 0 || lane >= n_lanes_ || !n) return vs_set_error(VS_ERR_INVALID_ARG, "bad lane");
-    CUDA_TRY(cudaStreamSynchronize(stream_));
+    VS_TRY(sync());
     int c = 0;
     CUDA_TRY(cudaMemcpy(&c, h_lanes_[lane].first_count, sizeof(int), cudaMemcpyDeviceToHost));
     *n = c;
@@ -548,10 +628,7 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
     if (f == 0) {
         // frame 0: first-frame analysis (Stabilizer.cpp:271-368)
         PtrPack src; src.p[0] = entry(0).frames[0];
-        launch_gray_resize(d_lanes_, 1, src, w, h, tight, -1, stream_);
-        CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2, stream_));
-        launch_good_features(d_lanes_, 1, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, stream_);
-        launches_ += 4;
+        VS_TRY(first_frame_detect(src, w, h, tight));
         first_ = false;
         n_frames_ = 0; detect_counter_ = 0;
         f = 1;
@@ -559,16 +636,15 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
         // halo: corners from the even frame m, pyramid of frame first-1
         const int m = f;
         PtrPack src; src.p[0] = entry(m).frames[0];
-        launch_gray_resize(d_lanes_, 1, src, w, h, tight, m & 1, stream_);
-        launch_pyrdown(d_lanes_, 1, m & 1, stream_);
-        CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2, stream_));
-        int mc = p_.max_corners < 200 ? p_.max_corners : 200;
-        launch_good_features(d_lanes_, 1, m & 1, mc, 0.02, 15.0, 0, stream_);
-        launches_ += 6;
+        launch_gray_resize(d_lanes_, 1, src, w, h, tight, m & 1, sa());
+        if (multi_) CUDA_TRY(cudaEventRecord(evG_, sa()));
+        launch_pyrdown(d_lanes_, 1, m & 1, sa());
+        launches_ += 3;
+        VS_TRY(redetect(m & 1, m, 0));
         if (first - 1 > m) {
             PtrPack s2; s2.p[0] = entry(first - 1).frames[0];
-            launch_gray_resize(d_lanes_, 1, s2, w, h, tight, (first - 1) & 1, stream_);
-            launch_pyrdown(d_lanes_, 1, (first - 1) & 1, stream_);
+            launch_gray_resize(d_lanes_, 1, s2, w, h, tight, (first - 1) & 1, sa());
+            launch_pyrdown(d_lanes_, 1, (first - 1) & 1, sa());
             launches_ += 3;
         }
         first_ = false;
@@ -586,7 +662,7 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
     if (n > 0 && out_host)
         CUDA_TRY(cudaMemcpyAsync(out_host, h_lanes_[0].transforms + 3 * (size_t)(first_tr - 1), sizeof(float) * 3 * n,
                                  cudaMemcpyDeviceToHost, stream_));
-    CUDA_TRY(cudaStreamSynchronize(stream_));
+    VS_TRY(sync());
     return VS_OK;
 }
 

@@ -1,5 +1,6 @@
 // engine.h — host side of the stabilizer: the reference's stabilize()/flush()/clean() control flow
-// (Stabilizer.cpp:258-400) re-expressed as an asynchronous launch sequence on one CUDA stream.
+// (Stabilizer.cpp:258-400) re-expressed as an asynchronous launch sequence on three CUDA streams per handle
+// (analysis / motion+output / detection) joined by events; see Engine::generate_transform.
 // One Engine advances n_lanes independent streams in lock-step (n_lanes == 1 is vs::Stabilizer).
 #pragma once
 #include <deque>
@@ -29,6 +30,7 @@ public:
                     int* produced);
     vs_status clean();
     vs_status sync();
+    vs_status join();       // public stream waits for the analysis and detection streams
 
     cudaStream_t stream() const { return stream_; }
     uint64_t launches() const { return launches_; }
@@ -71,13 +73,22 @@ private:
     vs_status ensure_geometry(int w, int h, bool need_ring, bool need_out, bool need_scratch);
     vs_status grow_trajectory();
     vs_status generate_transform(const QueueEntry& e, bool* will_pop);
+    vs_status first_frame_detect(const PtrPack& src, int w, int h, size_t stride);
+    vs_status redetect(int cur, int frame_no, int record_frame_no);
+    cudaStream_t sa() const { return multi_ ? sA_ : stream_; }
+    cudaStream_t sc() const { return multi_ ? sC_ : stream_; }
     vs_status emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, bool host_io, int* ow, int* oh);
     StepInfo step_info(int pop_index) const;
     void free_all();
 
     vs_params p_{};
     int device_ = 0, n_lanes_ = 0;
-    cudaStream_t stream_ = nullptr;
+    cudaStream_t stream_ = nullptr;           // public stream: motion + output stage
+    cudaStream_t sA_ = nullptr, sC_ = nullptr; // analysis (gray, pyramid, LK) and corner detection
+    bool multi_ = false;
+    cudaEvent_t evA_[2] = {}, evB_[4] = {}, evJ_[2] = {}, evG_ = nullptr, evC_ = nullptr;
+    bool evB_set_[4] = {};
+    bool c_pending_ = false;
     int border_mode_ = 0, method_ = 0;
     int smoothing_radius_ = 30;
 

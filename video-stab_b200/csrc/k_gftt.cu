@@ -275,7 +275,7 @@ static __device__ bool greedy_pass(const LaneDev& L, const unsigned* sxy, const 
 // boundary that holds the next >= `target` candidates, a gather + shared-memory bitonic sort of just
 // those, then the greedy pass.  Bins are value-ordered, so chunk order == global order.
 __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restrict__ lanes, int slot, int max_corners,
-                                                         double quality, double min_dist, int record_frame_no) {
+                                                         double quality, double min_dist, int record_frame_no, int kp_slot) {
     extern __shared__ unsigned long long sel_dyn[];
     unsigned long long* skeys = sel_dyn;                                        // SEL_CHUNK_MAX keys
     unsigned int* hist = reinterpret_cast<unsigned int*>(sel_dyn + SEL_CHUNK_MAX);   // SEL_BINS
@@ -283,7 +283,10 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     unsigned int* sxy = sgrid + SEL_GRID_CELLS * (1 + VS_GRID_SLOTS);           // SEL_CHUNK_MAX packed (x | y << 16)
     int* scell = reinterpret_cast<int*>(sxy + SEL_CHUNK_MAX);                   // SEL_CHUNK_MAX grid cell indices
     __shared__ SelSmem S;
-    const LaneDev& L = lanes[blockIdx.z];
+    LaneDev Lm = lanes[blockIdx.z];
+    Lm.kp = Lm.kpb[kp_slot];                       // key-point generation this detection writes (engine.cu)
+    Lm.kp_count = Lm.kpc[kp_slot];
+    const LaneDev& L = Lm;
     const GrayLevel G = gftt_src(L, slot);
     const int w = G.w, h = G.h;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -430,7 +433,7 @@ size_t gftt_grid_words(int w, int h, double min_dist) {
 }
 
 void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_corners, double quality,
-                          double min_dist, int record_frame_no, cudaStream_t st) {
+                          double min_dist, int record_frame_no, int kp_slot, cudaStream_t st) {
     const int w = slot < 0 ? VS_FW : VS_AW, h = slot < 0 ? VS_FH : VS_AH;
     static bool attr_set = false;
     if (!attr_set) {
@@ -442,5 +445,5 @@ void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_c
     dim3 g2((w + 63) / 64, (h + 3) / 4, n_lanes);
     k_candidates<<<g2, 256, 0, st>>>(lanes, slot, quality);
     k_select<<<dim3(1, 1, n_lanes), SEL_THREADS, SEL_DYN_BYTES, st>>>(
-        lanes, slot, max_corners, quality, min_dist, record_frame_no);
+        lanes, slot, max_corners, quality, min_dist, record_frame_no, kp_slot);
 }

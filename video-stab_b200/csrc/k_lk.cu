@@ -99,12 +99,12 @@ static __device__ __forceinline__ float ordered_sum_b(const int* t, int lane) {
     return __fadd_rn(tl, __fadd_rn(__fadd_rn(p0, p2), __fadd_rn(p1, p3)));
 }
 
-__global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restrict__ lanes, int prev, int cur) {
+__global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restrict__ lanes, int prev, int cur, int kp_slot, int lk_slot) {
     __shared__ LkSmem smem[LK_WARPS];
     const LaneDev& L = lanes[blockIdx.z];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pidx = blockIdx.x * LK_WARPS + warp;
-    const int npts = min(*L.kp_count, L.kp_capacity);
+    const int npts = min(*L.kpc[kp_slot], L.kp_capacity);
     if (pidx >= npts) return;                         // warp-uniform
     LkSmem& S = smem[warp];
     const unsigned FULL = 0xffffffffu;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
     const uint8_t* Pb = reinterpret_cast<const uint8_t*>(&S.P[0][0]);
     const uint8_t* Jb = reinterpret_cast<const uint8_t*>(&S.J[0][0]);
 
-    const float2 pt = L.kp[pidx];
+    const float2 pt = L.kpb[kp_slot][pidx];
     float nx = 0.f, ny = 0.f;                          // nextPts[ptidx]
     int status = 1;
 
@@ -271,13 +271,13 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
         }
     }
     if (lane == 0) {
-        L.lk_next[pidx] = make_float2(nx, ny);
-        L.lk_status[pidx] = (uint8_t)status;
+        L.lkn[lk_slot][pidx] = make_float2(nx, ny);
+        L.lks[lk_slot][pidx] = (uint8_t)status;
     }
 }
 
-void launch_pyr_lk(const LaneDev* lanes, int n_lanes, int prev, int cur, int max_pts, cudaStream_t st) {
+void launch_pyr_lk(const LaneDev* lanes, int n_lanes, int prev, int cur, int max_pts, int kp_slot, int lk_slot, cudaStream_t st) {
     if (max_pts <= 0) return;
     dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, 1, n_lanes);
-    k_pyr_lk<<<grid, LK_WARPS * 32, 0, st>>>(lanes, prev, cur);
+    k_pyr_lk<<<grid, LK_WARPS * 32, 0, st>>>(lanes, prev, cur, kp_slot, lk_slot);
 }

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
     const LaneDev& L = lanes[blockIdx.z];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
-    const int n_prev = min(min(*L.kp_count, L.kp_capacity), MO_MAXP);
+    const int n_prev = min(min(*L.kpc[info.kp_slot], L.kp_capacity), MO_MAXP);
     const int fidx = info.frame_no - 1;
     float2* lprev = nullptr; float2* lnext = nullptr; uint8_t* lstat = nullptr; uint8_t* lmask = nullptr;
     if (L.log_depth > 0) {
@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         bool ok = false;
         float2 a = make_float2(0.f, 0.f), b = a;
         if (i < n_prev) {
-            a = L.kp[i]; b = L.lk_next[i];
-            uint8_t s = L.lk_status[i];
+            a = L.kpb[info.kp_slot][i]; b = L.lkn[info.lk_slot][i];
+            uint8_t s = L.lks[info.lk_slot][i];
             ok = s != 0;
             if (lprev) { lprev[i] = a; lnext[i] = b; lstat[i] = s; }
         }
@@ -478,7 +478,8 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         if (fidx < L.record_capacity) {
             vs_frame_record& r = L.frec[fidx];
             r.frame_index = info.frame_no; r.n_prev_pts = n_prev; r.n_tracked = n;
-            r.n_inliers = found ? n_inl : -1; r.ransac_iters = S.iter; r.n_detected = -1;
+            r.n_inliers = found ? n_inl : -1; r.ransac_iters = S.iter;
+            if (!info.will_detect) r.n_detected = -1;          // else the detector (another stream) writes it
             for (int k = 0; k < 3; ++k) { r.transform[k] = t[k]; r.path[k] = pa[k]; }
             r.affine[0] = found ? A : 1.; r.affine[1] = found ? -B : 0.; r.affine[2] = found ? TX : 0.;
             r.affine[3] = found ? B : 0.; r.affine[4] = found ? A : 1.; r.affine[5] = found ? TY : 0.;

@@ -31,12 +31,12 @@ void launch_unpack_level(GrayLevel src, uint8_t* dst, cudaStream_t st);
 // source = pyramid slot `slot` level 0 (slot >= 0) or small0 (slot < 0); result -> lanes[].kp / kp_count
 // (and first_corners when slot < 0).  record_frame_no > 0: also log into the frame record ring.
 void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_corners, double quality,
-                          double min_dist, int record_frame_no, cudaStream_t st);
+                          double min_dist, int record_frame_no, int kp_slot, cudaStream_t st);
 size_t gftt_grid_words(int w, int h, double min_dist);
 
 // ---- k_lk.cu : cv::calcOpticalFlowPyrLK (Stabilizer.cpp:611-619)
 // tracks lanes[].kp from pyramid slot `prev` to slot `cur`; writes lk_next / lk_status
-void launch_pyr_lk(const LaneDev* lanes, int n_lanes, int prev, int cur, int max_pts, cudaStream_t st);
+void launch_pyr_lk(const LaneDev* lanes, int n_lanes, int prev, int cur, int max_pts, int kp_slot, int lk_slot, cudaStream_t st);
 
 // ---- k_motion.cu : status filter + estimateAffinePartial2D + decomposition + trajectory +
 //                    smoothing + warp set-up (Stabilizer.cpp:629-688, 783-908, 1139-1172, 1364-1458, 1637-1780)

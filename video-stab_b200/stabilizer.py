@@ -223,6 +223,10 @@ class Stabilizer:
     def sync(self):
         check(lib.vs_stabilizer_sync(self._h))
 
+    def join(self):
+        """Public stream waits for the handle's internal analysis / detection streams (no host block)."""
+        check(lib.vs_stabilizer_join(self._h))
+
     @property
     def stream(self) -> int:
         return lib.vs_stabilizer_stream(self._h) or 0
@@ -319,6 +323,9 @@ class StabilizerBatch:
 
     def sync(self):
         check(lib.vs_batch_sync(self._h))
+
+    def join(self):
+        check(lib.vs_batch_join(self._h))
 
     @property
     def stream(self) -> int:
