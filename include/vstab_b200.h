@@ -152,6 +152,18 @@ vs_status vs_stabilizer_push(vs_stabilizer* s, const uint8_t* bgr, int width, in
 /* cv::Mat Stabilizer::flush()                — Stabilizer.h:193, Stabilizer.cpp:394-400 */
 vs_status vs_stabilizer_flush(vs_stabilizer* s, uint8_t* out, size_t out_stride, size_t out_capacity,
                               int* out_width, int* out_height, int* produced);
+/* n consecutive stabilize() calls in one: the loop of the reference's file-processing apps
+ * (examples/file-capture.cpp:55-75: read frame, stabilize, keep if non-empty).  Frame k is at bgr + k*frame_step,
+ * produced frame j is written at out + j*out_frame_capacity.  Results are identical to n vs_stabilizer_push() calls;
+ * the difference is that frame k+1's host->device copy, frame k's kernels and frame k-1's device->host copy overlap
+ * (copy-in / compute / copy-out streams), so throughput is bounded by PCIe rather than by the sum.  Returns when
+ * all *n_produced frames are in `out`.  Host buffers should be page-locked for the copies to overlap. */
+vs_status vs_stabilizer_push_many(vs_stabilizer* s, const uint8_t* bgr, size_t frame_step, int n_frames, int width, int height,
+                                  size_t stride, uint8_t* out, size_t out_stride, size_t out_frame_capacity,
+                                  int* out_width, int* out_height, int* n_produced);
+/* the `while (!(f = flush()).empty())` drain loop, up to max_frames frames */
+vs_status vs_stabilizer_flush_many(vs_stabilizer* s, uint8_t* out, size_t out_stride, size_t out_frame_capacity, int max_frames,
+                                   int* out_width, int* out_height, int* n_produced);
 /* void Stabilizer::clean()                   — Stabilizer.h:198, Stabilizer.cpp:221-256 */
 vs_status vs_stabilizer_clean(vs_stabilizer* s);
 

@@ -197,3 +197,34 @@ def test_device_api_and_batch_equal_single(vsb):
         for i in range(n):
             assert np.array_equal(got[s, i], singles[s][i]), f"stream {s} frame {i}"
     assert batch.launch_count() > 0
+
+
+@pytest.mark.parametrize("kw", [dict(smoothingRadius=6), dict(smoothingRadius=5, borderType="reflect", borderSize=12),
+                                dict(smoothingRadius=7, cropNZoom=True, borderSize=16),
+                                dict(smoothingRadius=5, adaptiveSmoothing=True)])
+def test_push_many_equals_per_frame_push(vsb, kw):
+    """The pipelined host call (copy-in / compute / copy-out streams, staging rings) returns exactly the frames
+    of n stabilize() calls + flush(), for ragged chunk sizes, page-locked and pageable buffers, more frames than the
+    36-slot device ring, and the single-stream adaptive mode."""
+    w, h, n = 640, 360, 90
+    clip = vsb.synth.make_clip(w, h, n, 77)
+    ref, st0 = _run(vsb, clip, vsb.Parameters(**kw))
+    for pinned in (True, False):
+        st = vsb.Stabilizer(vsb.Parameters(**kw))
+        src = torch.from_numpy(clip).pin_memory().numpy() if pinned else clip
+        got = []
+        pos = 0
+        for chunk in (1, 3, 40, 17, 29):
+            got += [f.copy() for f in st.stabilize_many(src[pos:pos + chunk])]
+            pos += chunk
+        assert pos == n
+        while True:
+            tail = st.flush_many(8)
+            if len(tail) == 0:
+                break
+            got += [f.copy() for f in tail]
+        assert len(got) == len(ref) == n
+        for i, (a, b) in enumerate(zip(got, ref)):
+            assert a.shape == b.shape and np.array_equal(a, b), f"pinned={pinned}: frame {i} differs"
+        for i in range(n - 1):
+            assert list(st.frame_record(i).transform) == list(st0.frame_record(i).transform)

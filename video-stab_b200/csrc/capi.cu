@@ -179,6 +179,23 @@ vs_status vs_stabilizer_flush(vs_stabilizer* s, uint8_t* out, size_t out_stride,
     return s->eng->flush(o, out_stride, out_capacity, true, out_width, out_height, produced);
     API_END
 }
+vs_status vs_stabilizer_push_many(vs_stabilizer* s, const uint8_t* bgr, size_t frame_step, int n_frames, int width, int height,
+                                  size_t stride, uint8_t* out, size_t out_stride, size_t out_frame_capacity,
+                                  int* out_width, int* out_height, int* n_produced) {
+    if (!s || !n_produced || !out_width || !out_height || !bgr || !out || n_frames < 0)
+        return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    return s->eng->push_many(bgr, frame_step, n_frames, width, height, stride, out, out_stride, out_frame_capacity,
+                             out_width, out_height, n_produced);
+    API_END
+}
+vs_status vs_stabilizer_flush_many(vs_stabilizer* s, uint8_t* out, size_t out_stride, size_t out_frame_capacity, int max_frames,
+                                   int* out_width, int* out_height, int* n_produced) {
+    if (!s || !n_produced || !out_width || !out_height || !out) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    return s->eng->flush_many(out, out_stride, out_frame_capacity, max_frames, out_width, out_height, n_produced);
+    API_END
+}
 vs_status vs_stabilizer_clean(vs_stabilizer* s) {
     if (!s) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
     return s->eng->clean();

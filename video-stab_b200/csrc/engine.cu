@@ -129,6 +129,13 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
         for (auto& ev : evJ_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&evG_, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&evC_, cudaEventDisableTiming));
+        // pipelined host I/O (push_many / flush_many): copy-in and copy-out streams
+        CUDA_TRY(cudaStreamCreateWithFlags(&sH_, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sO_, cudaStreamNonBlocking));
+        for (auto& ev : evH_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : evRing_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : evOutReady_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : evOutFree_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
     // mapBorderMode, Stabilizer.cpp:31-38 and the cropNZoom override :67-71
     border_mode_ = !strcmp(p.border_type, "reflect") ? 2 : !strcmp(p.border_type, "reflect_101") ? 4
@@ -243,8 +250,14 @@ void Engine::free_all() {
     for (auto& ev : evJ_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     if (evG_) { cudaEventDestroy(evG_); evG_ = nullptr; }
     if (evC_) { cudaEventDestroy(evC_); evC_ = nullptr; }
+    for (auto& ev : evH_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : evRing_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : evOutReady_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : evOutFree_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     if (sA_) { cudaStreamDestroy(sA_); sA_ = nullptr; }
     if (sC_) { cudaStreamDestroy(sC_); sC_ = nullptr; }
+    if (sH_) { cudaStreamDestroy(sH_); sH_ = nullptr; }
+    if (sO_) { cudaStreamDestroy(sO_); sO_ = nullptr; }
     for (cudaEvent_t ev : event_pool_) cudaEventDestroy(ev);
     event_pool_.clear();
     for (auto& L : h_lanes_) {
@@ -269,9 +282,11 @@ Engine::~Engine() {
 }
 
 vs_status Engine::sync() {
+    if (sH_) CUDA_TRY(cudaStreamSynchronize(sH_));
     if (sA_) CUDA_TRY(cudaStreamSynchronize(sA_));
     if (sC_) CUDA_TRY(cudaStreamSynchronize(sC_));
     if (stream_) CUDA_TRY(cudaStreamSynchronize(stream_));
+    if (sO_) CUDA_TRY(cudaStreamSynchronize(sO_));
     return VS_OK;
 }
 
@@ -289,6 +304,8 @@ vs_status Engine::clean() {
     // Stabilizer::clean, Stabilizer.cpp:221-256
     VS_TRY(sync());
     for (bool& b : evB_set_) b = false;
+    for (bool& b : ring_ev_set_) b = false;
+    for (bool& b : out_free_set_) b = false;
     c_pending_ = false;
     queue_.clear();
     first_ = true;
@@ -315,7 +332,7 @@ vs_status Engine::ensure_geometry(int w, int h, bool need_ring, bool need_out, b
         return vs_set_error(VS_ERR_INVALID_ARG, "frame size changed mid-stream (call clean() first)");
     }
     if (need_ring && !d_ring_) CUDA_TRY(cudaMalloc((void**)&d_ring_, frame_bytes_ * ring_slots_ * n_lanes_));
-    if (need_out && !d_out_) CUDA_TRY(cudaMalloc((void**)&d_out_, out_bytes_ * n_lanes_));
+    if (need_out && !d_out_) CUDA_TRY(cudaMalloc((void**)&d_out_, out_bytes_ * n_lanes_ * VS_OUT_SLOTS));
     if (need_scratch && !d_scratch_) CUDA_TRY(cudaMalloc((void**)&d_scratch_, frame_bytes_ * n_lanes_));
     return VS_OK;
 }
@@ -440,7 +457,8 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
 }
 
 // the warp half of applyNextSmoothTransform, Stabilizer.cpp:979-1137
-vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, bool host_io, int* ow, int* oh) {
+vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, int io, int* ow, int* oh) {
+    const bool host_io = io != VS_IO_DEVICE, pipe = io == VS_IO_HOST_PIPE && multi_;
     QueueEntry e = queue_.front();
     queue_.pop_front();
     const bool passthrough = e.index >= n_frames_;                                    // :774-780
@@ -456,8 +474,11 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         return vs_set_error(VS_ERR_BUFFER_TOO_SMALL, "output buffer too small for the stabilized frame");
     VS_TRY(ensure_geometry(W_, H_, false, host_io, mode == 2));
 
+    // pipelined host I/O: warp into one of VS_OUT_SLOTS staging frames, copy out on the copy-out stream
+    const int oslot = pipe ? n_out_ % VS_OUT_SLOTS : 0;
+    if (pipe && out_free_set_[oslot]) CUDA_TRY(cudaStreamWaitEvent(stream_, evOutFree_[oslot], 0));
     MutPtrPack dst;
-    for (int l = 0; l < n_lanes_; ++l) dst.p[l] = host_io ? d_out_ + out_bytes_ * l : outs[l];
+    for (int l = 0; l < n_lanes_; ++l) dst.p[l] = host_io ? d_out_ + out_bytes_ * ((size_t)l * VS_OUT_SLOTS + oslot) : outs[l];
     const size_t dstride = host_io ? tight : out_stride;
     if (passthrough) {
         for (int l = 0; l < n_lanes_; ++l)
@@ -479,7 +500,16 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
           launch_warp(d_lanes_, n_lanes_, src, dst, g, scratch.data(), stream_); }
         launches_ += (m2 == 2) ? 1 + n_lanes_ : 1;
     }
-    if (host_io) {
+    if (pipe) {
+        CUDA_TRY(cudaEventRecord(evRing_[e.slot], stream_));            // the ring slot of this frame may be refilled
+        ring_ev_set_[e.slot] = true;
+        CUDA_TRY(cudaEventRecord(evOutReady_[oslot], stream_));
+        CUDA_TRY(cudaStreamWaitEvent(sO_, evOutReady_[oslot], 0));
+        for (int l = 0; l < n_lanes_; ++l)
+            CUDA_TRY(cudaMemcpy2DAsync(outs[l], out_stride, dst.p[l], dstride, tight, h, cudaMemcpyDeviceToHost, sO_));
+        CUDA_TRY(cudaEventRecord(evOutFree_[oslot], sO_));
+        out_free_set_[oslot] = true;
+    } else if (host_io) {
         for (int l = 0; l < n_lanes_; ++l)
             CUDA_TRY(cudaMemcpy2DAsync(outs[l], out_stride, dst.p[l], dstride, tight, h, cudaMemcpyDeviceToHost, stream_));
         CUDA_TRY(cudaStreamSynchronize(stream_));
@@ -490,7 +520,8 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
 
 // Stabilizer::stabilize, Stabilizer.cpp:258-392
 vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride, uint8_t* const* outs, size_t out_stride,
-                       size_t out_capacity, unsigned flags, bool host_io, int* ow, int* oh, int* produced) {
+                       size_t out_capacity, unsigned flags, int io, int* ow, int* oh, int* produced) {
+    const bool host_io = io != VS_IO_DEVICE, pipe = io == VS_IO_HOST_PIPE && multi_;
     *produced = 0;
     if (!frames || w <= 0 || h <= 0) return VS_OK;                                    // frame.empty() -> empty Mat (:263)
     if (w < 4 || h < 4) return vs_set_error(VS_ERR_INVALID_ARG, "frame too small");
@@ -509,13 +540,21 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
         e.stride = stride;
     } else {
         const size_t tight = (size_t)w * 3;
+        // pipelined host I/O: copy in on the copy-in stream, after the warp that last read this ring slot
+        cudaStream_t cs = pipe ? sH_ : sa();
+        if (pipe && ring_ev_set_[e.slot]) CUDA_TRY(cudaStreamWaitEvent(sH_, evRing_[e.slot], 0));
         for (int l = 0; l < n_lanes_; ++l) {
             uint8_t* dst = d_ring_ + ((size_t)l * ring_slots_ + e.slot) * frame_bytes_;
             CUDA_TRY(cudaMemcpy2DAsync(dst, tight, frames[l], stride, tight, h,
-                                       host_io ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, sa()));
+                                       host_io ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cs));
             e.frames[l] = dst;
         }
         e.stride = tight;
+        if (pipe) {
+            cudaEvent_t ev = evH_[h_seq_++ & 7];
+            CUDA_TRY(cudaEventRecord(ev, sH_));
+            CUDA_TRY(cudaStreamWaitEvent(sa(), ev, 0));
+        }
     }
 
     if (first_) {
@@ -526,16 +565,16 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
         queue_.push_back(e);
         first_ = false;
         next_index_ = 1;
-        if (host_io) CUDA_TRY(cudaStreamSynchronize(sa()));     // the caller may reuse its frame buffer
+        if (host_io && !pipe) CUDA_TRY(cudaStreamSynchronize(sa()));     // the caller may reuse its frame buffer
         return VS_OK;
     }
     queue_.push_back(e);
     bool will_pop = false;
     VS_TRY(generate_transform(e, &will_pop));
     if (will_pop) {
-        VS_TRY(emit(outs, out_stride, out_capacity, host_io, ow, oh));
+        VS_TRY(emit(outs, out_stride, out_capacity, io, ow, oh));
         *produced = 1;
-    } else if (host_io) {
+    } else if (host_io && !pipe) {
         CUDA_TRY(cudaStreamSynchronize(sa()));        // the caller may reuse its frame buffer
     }
     ++next_index_;
@@ -543,16 +582,55 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
 }
 
 // Stabilizer::flush, Stabilizer.cpp:394-400
-vs_status Engine::flush(uint8_t* const* outs, size_t out_stride, size_t out_capacity, bool host_io, int* ow, int* oh,
+vs_status Engine::flush(uint8_t* const* outs, size_t out_stride, size_t out_capacity, int io, int* ow, int* oh,
                         int* produced) {
     *produced = 0;
     if (queue_.empty()) return VS_OK;
     CUDA_TRY(cudaSetDevice(device_));
     launch_smooth_only(d_lanes_, n_lanes_, step_info(queue_.front().index), stream_);
     launches_ += 1;
-    VS_TRY(emit(outs, out_stride, out_capacity, host_io, ow, oh));
+    VS_TRY(emit(outs, out_stride, out_capacity, io, ow, oh));
     *produced = 1;
     return VS_OK;
+}
+
+// Pipelined host I/O: n frames in, up to n frames out per call.  Frame k+1's host->device copy, frame k's
+// kernels and frame k-1's device->host copy overlap on the copy-in / compute / copy-out streams; the call returns
+// when every output of this call is in host memory.  Results are identical to n calls of push().
+vs_status Engine::push_many(const uint8_t* frames, size_t frame_step, int n, int w, int h, size_t stride, uint8_t* outs,
+                            size_t out_stride, size_t out_frame_capacity, int* ow, int* oh, int* n_produced) {
+    *n_produced = 0;
+    if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "push_many is a single-stream call");
+    vs_status rc = VS_OK;
+    for (int k = 0; k < n && rc == VS_OK; ++k) {
+        const uint8_t* f = frames + (size_t)k * frame_step;
+        uint8_t* o = outs + (size_t)(*n_produced) * out_frame_capacity;
+        int produced = 0;
+        rc = push(&f, w, h, stride, &o, out_stride, out_frame_capacity, 0, VS_IO_HOST_PIPE, ow, oh, &produced);
+        *n_produced += produced;
+    }
+    vs_status rs = sync();
+    return rc != VS_OK ? rc : rs;
+}
+
+vs_status Engine::flush_many(uint8_t* outs, size_t out_stride, size_t out_frame_capacity, int max_frames, int* ow, int* oh,
+                             int* n_produced) {
+    *n_produced = 0;
+    if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "flush_many is a single-stream call");
+    vs_status rc = VS_OK;
+    while (*n_produced < max_frames && !queue_.empty() && rc == VS_OK) {
+        // one (width, height) per call: stop before a frame of another size (the clip's last frame comes back
+        // un-warped, i.e. without the copyMakeBorder margin - Stabilizer.cpp:774-780)
+        const bool passthrough = queue_.front().index >= n_frames_;
+        const int b = (!passthrough && p_.border_size > 0 && !p_.crop_n_zoom) ? p_.border_size : 0;
+        if (*n_produced > 0 && (W_ + 2 * b != *ow || H_ + 2 * b != *oh)) break;
+        uint8_t* o = outs + (size_t)(*n_produced) * out_frame_capacity;
+        int produced = 0;
+        rc = flush(&o, out_stride, out_frame_capacity, VS_IO_HOST_PIPE, ow, oh, &produced);
+        *n_produced += produced;
+    }
+    vs_status rs = sync();
+    return rc != VS_OK ? rc : rs;
 }
 
 vs_status Engine::reset_detect_counters() {

@@ -9,6 +9,8 @@
 
 #include "kernels.h"
 
+enum { VS_IO_DEVICE = 0, VS_IO_HOST_SYNC = 1, VS_IO_HOST_PIPE = 2 };   // where push()/flush() frames live
+#define VS_OUT_SLOTS 3                    // output staging frames of the pipelined host path
 enum { VS_STAGE_GRAY = 0, VS_STAGE_PYRDOWN, VS_STAGE_LK, VS_STAGE_MOTION, VS_STAGE_GFTT, VS_STAGE_WARP, VS_N_STAGES };
 
 struct QueueEntry {
@@ -23,11 +25,16 @@ public:
     static vs_status create(const vs_params& p, int device, int n_lanes, Engine** out);
     ~Engine();
 
-    // frames/outs: n_lanes pointers.  host_io: pointers are host memory (copies + sync inside).
+    // frames/outs: n_lanes pointers.  io: VS_IO_DEVICE (device pointers, asynchronous), VS_IO_HOST_SYNC (host
+    // memory, copies + sync inside) or VS_IO_HOST_PIPE (host memory, copies on their own streams, no sync).
     vs_status push(const uint8_t* const* frames, int w, int h, size_t stride, uint8_t* const* outs, size_t out_stride,
-                   size_t out_capacity, unsigned flags, bool host_io, int* ow, int* oh, int* produced);
-    vs_status flush(uint8_t* const* outs, size_t out_stride, size_t out_capacity, bool host_io, int* ow, int* oh,
+                   size_t out_capacity, unsigned flags, int io, int* ow, int* oh, int* produced);
+    vs_status flush(uint8_t* const* outs, size_t out_stride, size_t out_capacity, int io, int* ow, int* oh,
                     int* produced);
+    vs_status push_many(const uint8_t* frames, size_t frame_step, int n, int w, int h, size_t stride, uint8_t* outs,
+                        size_t out_stride, size_t out_frame_capacity, int* ow, int* oh, int* n_produced);
+    vs_status flush_many(uint8_t* outs, size_t out_stride, size_t out_frame_capacity, int max_frames, int* ow, int* oh,
+                         int* n_produced);
     vs_status clean();
     vs_status sync();
     vs_status join();       // public stream waits for the analysis and detection streams
@@ -77,7 +84,7 @@ private:
     vs_status redetect(int cur, int frame_no, int record_frame_no);
     cudaStream_t sa() const { return multi_ ? sA_ : stream_; }
     cudaStream_t sc() const { return multi_ ? sC_ : stream_; }
-    vs_status emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, bool host_io, int* ow, int* oh);
+    vs_status emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, int io, int* ow, int* oh);
     StepInfo step_info(int pop_index) const;
     void free_all();
 
@@ -89,6 +96,10 @@ private:
     cudaEvent_t evA_[2] = {}, evB_[4] = {}, evJ_[2] = {}, evG_ = nullptr, evC_ = nullptr;
     bool evB_set_[4] = {};
     bool c_pending_ = false;
+    cudaStream_t sH_ = nullptr, sO_ = nullptr; // copy-in / copy-out streams of the pipelined host path
+    cudaEvent_t evH_[8] = {}, evRing_[36] = {}, evOutReady_[VS_OUT_SLOTS] = {}, evOutFree_[VS_OUT_SLOTS] = {};
+    bool ring_ev_set_[36] = {}, out_free_set_[VS_OUT_SLOTS] = {};
+    unsigned h_seq_ = 0;
     int border_mode_ = 0, method_ = 0;
     int smoothing_radius_ = 30;
 

@@ -206,6 +206,41 @@ class Stabilizer:
     def clean(self):
         check(lib.vs_stabilizer_clean(self._h))
 
+    # ---- pipelined host API: n stabilize() calls in one (copy-in / compute / copy-out overlap)
+    def _border(self) -> int:
+        p = self.params
+        return p.borderSize if (p.borderSize > 0 and not p.cropNZoom) else 0
+
+    def stabilize_many(self, frames: np.ndarray, out: np.ndarray | None = None):
+        """frames: (n,H,W,3) uint8, C-contiguous (page-locked memory overlaps best).  Returns the produced frames as
+        an (m,H',W',3) view of `out` (m <= n), exactly the non-empty results of n stabilize() calls in order."""
+        if frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[3] != 3 or not frames.flags.c_contiguous:
+            raise ValueError("frames must be a C-contiguous (n,H,W,3) uint8 array")
+        n, h, w, _ = frames.shape
+        b = self._border()
+        cap = (h + 2 * b) * (w + 2 * b) * 3
+        if out is None:
+            out = np.empty((n, cap), np.uint8)
+        if out.size < n * cap or not out.flags.c_contiguous:
+            raise ValueError("out too small")
+        self._many_shape = (h, w)
+        ow, oh, m = C.c_int(), C.c_int(), C.c_int()
+        check(lib.vs_stabilizer_push_many(self._h, _addr(frames), h * w * 3, n, w, h, w * 3, _addr(out), 0, cap,
+                                          C.byref(ow), C.byref(oh), C.byref(m)))
+        flat = out.reshape(-1)[: n * cap].reshape(n, cap)
+        return flat[: m.value, : oh.value * ow.value * 3].reshape(m.value, oh.value, ow.value, 3) if m.value else flat[:0]
+
+    def flush_many(self, max_frames: int = 64, out: np.ndarray | None = None):
+        h, w = self._many_shape
+        b = self._border()
+        cap = (h + 2 * b) * (w + 2 * b) * 3
+        if out is None:
+            out = np.empty((max_frames, cap), np.uint8)
+        ow, oh, m = C.c_int(), C.c_int(), C.c_int()
+        check(lib.vs_stabilizer_flush_many(self._h, _addr(out), 0, cap, max_frames, C.byref(ow), C.byref(oh), C.byref(m)))
+        flat = out.reshape(-1)[: max_frames * cap].reshape(max_frames, cap)
+        return flat[: m.value, : oh.value * ow.value * 3].reshape(m.value, oh.value, ow.value, 3) if m.value else flat[:0]
+
     # ---- device-resident API (raw device pointers, e.g. torch tensor.data_ptr())
     def push_device(self, d_frame: int, w: int, h: int, stride: int, d_out: int, out_stride: int, out_capacity: int,
                     borrow: bool = False):
