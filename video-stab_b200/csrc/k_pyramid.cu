@@ -5,6 +5,7 @@
 // Arithmetic specification: oracle/cv_models.py resize_linear / bgr2gray / pyr_down (pinned
 // bit-exact against cv2 4.13).  Pure integer work, HBM-bound: one pass over the BGR frame.
 #include "kernels.h"
+#include <climits>
 
 // ---------------------------------------------------------------- cv::resize INTER_LINEAR tables
 struct AxisTap {
@@ -88,12 +89,88 @@ __global__ void __launch_bounds__(128) k_gray_resize(const LaneDev* __restrict__
     lv.base[(ptrdiff_t)py * lv.pitch + px] = (uint8_t)v;
 }
 
+// ---------------------------------------------------------------- exact-2x fast path (1080p -> 960x540)
+// One thread = 4 output pixels = one 32-bit store, from 24 source bytes x 2 rows (three aligned 64-bit loads per
+// row; a warp reads 768 contiguous bytes per row).  The 2x2 box sums are taken straight off the packed BGR words
+// with DP4A byte-select masks (byte k of a 12-byte group belongs to pixel k/3, channel k%3), so there is no byte
+// unpacking at all.  A thread also writes the BORDER_REFLECT_101 images of its pixels into the level's
+// materialised frame (rows: whole words; columns: bytes), so the padded level is complete after one launch.
+static __device__ __forceinline__ uint32_t gray4_from_sums(const uint32_t* sb, const uint32_t* sg, const uint32_t* sr) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = (int)((sb[k] + 2u) >> 2), g = (int)((sg[k] + 2u) >> 2), r = (int)((sr[k] + 2u) >> 2);
+        out |= (uint32_t)gray_of(b, g, r) << (8 * k);
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(256) k_gray_half(const LaneDev* __restrict__ lanes, PtrPack src, size_t stride, int slot) {
+    const LaneDev& L = lanes[blockIdx.z];
+    const GrayLevel lv = L.pyr[slot].lv[0];
+    const int per_row = lv.w >> 2;                                   // threads per output row
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= per_row * lv.h) return;
+    const int y = id / per_row, x = (id - y * per_row) << 2;
+    const uint2* r0 = reinterpret_cast<const uint2*>(src.p[blockIdx.z] + (size_t)(2 * y) * stride + 6 * x);
+    const uint2* r1 = reinterpret_cast<const uint2*>(src.p[blockIdx.z] + (size_t)(2 * y + 1) * stride + 6 * x);
+    uint32_t w[2][6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint2 a = __ldg(r0 + k), b = __ldg(r1 + k);
+        w[0][2 * k] = a.x; w[0][2 * k + 1] = a.y; w[1][2 * k] = b.x; w[1][2 * k + 1] = b.y;
+    }
+    // bytes of a 12-byte group (3 words): B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3 ; output pixel A = source pixels 0,1, B = 2,3
+    uint32_t sb[4] = {0u, 0u, 0u, 0u}, sg[4] = {0u, 0u, 0u, 0u}, sr[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const uint32_t w0 = w[row][3 * g], w1 = w[row][3 * g + 1], w2 = w[row][3 * g + 2];
+            sb[2 * g] = __dp4a(w0, 0x01000001u, sb[2 * g]);                                   // B0 + B1
+            sg[2 * g] = __dp4a(w1, 0x00000001u, __dp4a(w0, 0x00000100u, sg[2 * g]));          // G0 + G1
+            sr[2 * g] = __dp4a(w1, 0x00000100u, __dp4a(w0, 0x00010000u, sr[2 * g]));          // R0 + R1
+            sb[2 * g + 1] = __dp4a(w2, 0x00000100u, __dp4a(w1, 0x00010000u, sb[2 * g + 1]));  // B2 + B3
+            sg[2 * g + 1] = __dp4a(w2, 0x00010000u, __dp4a(w1, 0x01000000u, sg[2 * g + 1]));  // G2 + G3
+            sr[2 * g + 1] = __dp4a(w2, 0x01000001u, sr[2 * g + 1]);                           // R2 + R3
+        }
+    }
+    const uint32_t v = gray4_from_sums(sb, sg, sr);
+    uint8_t* row_ptr = lv.base + (ptrdiff_t)y * lv.pitch;
+    *reinterpret_cast<uint32_t*>(row_ptr + x) = v;
+    // reflect-101 frame: mirror rows ym (at most one per pixel row), mirror columns xm
+    int ym = INT_MIN;
+    if (y >= 1 && y <= VS_PAD) ym = -y;
+    else if (y >= lv.h - 1 - VS_PAD && y <= lv.h - 2) ym = 2 * (lv.h - 1) - y;
+    uint8_t* mrow_ptr = lv.base + (ptrdiff_t)(ym == INT_MIN ? y : ym) * lv.pitch;
+    if (ym != INT_MIN) *reinterpret_cast<uint32_t*>(mrow_ptr + x) = v;
+    if (x <= VS_PAD || x + 3 >= lv.w - 1 - VS_PAD) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xx = x + k;
+            int xm = INT_MIN;
+            if (xx >= 1 && xx <= VS_PAD) xm = -xx;
+            else if (xx >= lv.w - 1 - VS_PAD && xx <= lv.w - 2) xm = 2 * (lv.w - 1) - xx;
+            if (xm != INT_MIN) {
+                const uint8_t b = (uint8_t)(v >> (8 * k));
+                row_ptr[xm] = b;
+                if (ym != INT_MIN) mrow_ptr[xm] = b;
+            }
+        }
+    }
+}
+
 void launch_gray_resize(const LaneDev* lanes, int n_lanes, const PtrPack& src, int w, int h, size_t stride,
                         int slot, cudaStream_t st) {
     int aw = slot < 0 ? VS_FW : VS_AW, ah = slot < 0 ? VS_FH : VS_AH;
     dim3 grid((aw + 2 * VS_PAD + 127) / 128, ah + 2 * VS_PAD, n_lanes);
     double sx = 1.0 / ((double)aw / (double)w), sy = 1.0 / ((double)ah / (double)h);
-    if (w == 2 * aw && h == 2 * ah)
+    bool aligned = slot >= 0 && stride % 8 == 0 && aw % 4 == 0;
+    for (int i = 0; i < n_lanes; ++i) aligned = aligned && ((uintptr_t)src.p[i] % 8 == 0);
+    if (w == 2 * aw && h == 2 * ah && aligned) {
+        dim3 g2(((aw / 4) * ah + 255) / 256, 1, n_lanes);
+        k_gray_half<<<g2, 256, 0, st>>>(lanes, src, stride, slot);
+    } else if (w == 2 * aw && h == 2 * ah)
         k_gray_resize<0><<<grid, 128, 0, st>>>(lanes, src, w, h, stride, slot, sx, sy);
     else
         k_gray_resize<1><<<grid, 128, 0, st>>>(lanes, src, w, h, stride, slot, sx, sy);
@@ -145,14 +222,112 @@ __global__ void __launch_bounds__(128) k_pyrdown(const LaneDev* __restrict__ lan
     d.base[(ptrdiff_t)py * d.pitch + px] = (uint8_t)((acc + 128) >> 8);
 }
 
-void launch_pyrdown(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st) {
-    int w = VS_AW, h = VS_AH;
-    for (int l = 1; l < VS_LEVELS; ++l) {
-        w = (w + 1) / 2;
-        h = (h + 1) / 2;
-        dim3 grid((w + 2 * VS_PAD + 127) / 128, h + 2 * VS_PAD, n_lanes);
-        k_pyrdown<<<grid, 128, 0, st>>>(lanes, slot, l);
+// Both pyrDown levels in one launch.  One CTA = one 16x16 tile of level 2; it needs a 36x36 region of level 1
+// (recomputed per CTA, 27 % redundancy) and that a 76x76 region of level 0, read once from the padded level-0
+// plane into shared memory.  Both passes are separable ([1 4 6 4 1] rows then columns, exact integers).  The CTA
+// owns (and stores, with their reflect-101 images) the 32x32 level-1 pixels under its tile and the tile itself.
+#define PD_T2 16
+#define PD_R1 36
+#define PD_R0 76
+
+static __device__ __forceinline__ void store_with_mirrors(const GrayLevel& lv, int x, int y, uint8_t v) {
+    int xm = INT_MIN, ym = INT_MIN;
+    if (x >= 1 && x <= VS_PAD) xm = -x;
+    else if (x >= lv.w - 1 - VS_PAD && x <= lv.w - 2) xm = 2 * (lv.w - 1) - x;
+    if (y >= 1 && y <= VS_PAD) ym = -y;
+    else if (y >= lv.h - 1 - VS_PAD && y <= lv.h - 2) ym = 2 * (lv.h - 1) - y;
+    uint8_t* r = lv.base + (ptrdiff_t)y * lv.pitch;
+    r[x] = v;
+    if (xm != INT_MIN) r[xm] = v;
+    if (ym != INT_MIN) {
+        uint8_t* rm = lv.base + (ptrdiff_t)ym * lv.pitch;
+        rm[x] = v;
+        if (xm != INT_MIN) rm[xm] = v;
     }
+}
+
+__global__ void __launch_bounds__(256) k_pyrdown2(const LaneDev* __restrict__ lanes, int slot) {
+    __shared__ uint32_t L0w[PD_R0][PD_R0 / 4 + 1];    // 80-byte rows: columns x0o-2 .. x0o+77 (word aligned)
+    __shared__ unsigned short H1[PD_R0][PD_R1];
+    __shared__ uint8_t L1[PD_R1][PD_R1];
+    __shared__ unsigned short H2[PD_R1][PD_T2];
+    const LaneDev& L = lanes[blockIdx.z];
+    const GrayLevel g0 = L.pyr[slot].lv[0], g1 = L.pyr[slot].lv[1], g2 = L.pyr[slot].lv[2];
+    const int tid = threadIdx.x;
+    const int x2o = blockIdx.x * PD_T2, y2o = blockIdx.y * PD_T2;     // level-2 tile origin
+    const int x1o = 2 * x2o - 2, y1o = 2 * y2o - 2;                   // level-1 region origin
+    const int x0o = 2 * x1o - 2, y0o = 2 * y1o - 2;                   // level-0 region origin (>= -6: inside the frame)
+    // 1. level-0 region: 76 rows x 20 aligned words (x0o - 2 is a multiple of 4 and >= -8, the right end stays inside
+    //    the 16-pixel frame), rows clamped into the padded plane (clamped rows are never used).  Six independent
+    //    loads per thread, all issued before the first store.
+    {
+        constexpr int RW = PD_R0 / 4 + 1, NW = PD_R0 * RW, PER = (NW + 255) / 256;
+        uint32_t v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + 256 * k;
+            const int r = min(i / RW, PD_R0 - 1), cw = i - (i / RW) * RW;
+            const int gy = min(max(y0o + r, -VS_PAD), g0.h + VS_PAD - 1);
+            v[k] = __ldg(reinterpret_cast<const uint32_t*>(g0.base + (ptrdiff_t)gy * g0.pitch + (x0o - 2)) + cw);
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + 256 * k;
+            if (i < NW) L0w[i / RW][i - (i / RW) * RW] = v[k];
+        }
+    }
+    const uint8_t (*L0)[(PD_R0 / 4 + 1) * 4] = reinterpret_cast<const uint8_t (*)[(PD_R0 / 4 + 1) * 4]>(&L0w[0][0]);
+    __syncthreads();
+    // 2. level 1, row pass: H1[r][c] = sum_i k_i L0[r][2c+i]
+    for (int i = tid; i < PD_R0 * PD_R1; i += 256) {
+        const int r = i / PD_R1, c = i - r * PD_R1;
+        const uint8_t* p = &L0[r][2 * c + 2];
+        H1[r][c] = (unsigned short)(p[0] + 4 * p[1] + 6 * p[2] + 4 * p[3] + p[4]);
+    }
+    __syncthreads();
+    // 3. level 1, column pass (in-image positions), stored by the owner
+    for (int i = tid; i < PD_R1 * PD_R1; i += 256) {
+        const int r = i / PD_R1, c = i - r * PD_R1;
+        const int x1 = x1o + c, y1 = y1o + r;
+        if ((unsigned)x1 < (unsigned)g1.w && (unsigned)y1 < (unsigned)g1.h) {
+            const int acc = H1[2 * r][c] + 4 * H1[2 * r + 1][c] + 6 * H1[2 * r + 2][c] + 4 * H1[2 * r + 3][c] + H1[2 * r + 4][c];
+            const uint8_t v = (uint8_t)((acc + 128) >> 8);
+            L1[r][c] = v;
+            if (r >= 2 && r < 2 + 2 * PD_T2 && c >= 2 && c < 2 + 2 * PD_T2) store_with_mirrors(g1, x1, y1, v);
+        }
+    }
+    __syncthreads();
+    // 3b. positions outside the level-1 image take their BORDER_REFLECT_101 source (always inside this region)
+    for (int i = tid; i < PD_R1 * PD_R1; i += 256) {
+        const int r = i / PD_R1, c = i - r * PD_R1;
+        const int x1 = x1o + c, y1 = y1o + r;
+        if (!((unsigned)x1 < (unsigned)g1.w && (unsigned)y1 < (unsigned)g1.h)) {
+            const int rx = reflect101(x1, g1.w) - x1o, ry = reflect101(y1, g1.h) - y1o;
+            if ((unsigned)rx < PD_R1 && (unsigned)ry < PD_R1) L1[r][c] = L1[ry][rx];
+        }
+    }
+    __syncthreads();
+    // 4. level 2: row pass over the 36 region rows, then column pass
+    for (int i = tid; i < PD_R1 * PD_T2; i += 256) {
+        const int r = i / PD_T2, c = i - r * PD_T2;
+        const uint8_t* p = &L1[r][2 * c];
+        H2[r][c] = (unsigned short)(p[0] + 4 * p[1] + 6 * p[2] + 4 * p[3] + p[4]);
+    }
+    __syncthreads();
+    {
+        const int r = tid / PD_T2, c = tid - r * PD_T2;
+        const int x2 = x2o + c, y2 = y2o + r;
+        if (x2 < g2.w && y2 < g2.h) {
+            const int acc = H2[2 * r][c] + 4 * H2[2 * r + 1][c] + 6 * H2[2 * r + 2][c] + 4 * H2[2 * r + 3][c] + H2[2 * r + 4][c];
+            store_with_mirrors(g2, x2, y2, (uint8_t)((acc + 128) >> 8));
+        }
+    }
+}
+
+void launch_pyrdown(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st) {
+    const int w2 = ((VS_AW + 1) / 2 + 1) / 2, h2 = ((VS_AH + 1) / 2 + 1) / 2;
+    dim3 grid((w2 + PD_T2 - 1) / PD_T2, (h2 + PD_T2 - 1) / PD_T2, n_lanes);
+    k_pyrdown2<<<grid, 256, 0, st>>>(lanes, slot);
 }
 
 // ---------------------------------------------------------------- generic cv::resize INTER_LINEAR (8UC1/8UC3)
