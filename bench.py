@@ -307,6 +307,12 @@ def run_gpu(args, rank, world, local_rank):
     w1.record()
     torch.cuda.synchronize()
     warp_ms = w0.elapsed_time(w1) / reps
+    traffic = None                                  # dram read+write bytes of that launch from the committed ncu capture
+    try:
+        cap = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_warp_ncu.json"))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", cap[-1])))["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     alg_bytes = 2 * 3 * W * H * FRAMES_PER_STEP
     peak, peak_src = _peaks()
     achieved = alg_bytes / (warp_ms * 1e-3) / 1e9
@@ -340,8 +346,8 @@ def run_gpu(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_us_per_launch_group": stage_us,
-            "roofline": {"bound": "hbm", "kernel": "k_warp_frames (cv::warpAffine, 64 frames per launch, timed alone)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "k_warp_tma (cv::warpAffine, 64 frames per launch, timed alone)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "ms_per_launch": warp_ms, "frac_of_nominal_8000": achieved / 8000.0},
         }

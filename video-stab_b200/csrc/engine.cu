@@ -403,7 +403,7 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         // prevGray is still the 480x270 first-frame image: cv::resize it up (Stabilizer.cpp:598-603)
         launch_upsample_small(d_lanes_, n_lanes_, prev, sa());
         launch_pyrdown(d_lanes_, n_lanes_, prev, sa());
-        launches_ += 3;
+        launches_ += 2;
     }
     { StageScope t(this, VS_STAGE_GRAY, sa());
       launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sa()); }       // :449-450
@@ -417,7 +417,7 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     }
     { StageScope t(this, VS_STAGE_LK, sa());
       launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa()); }   // :611-619
-    launches_ += 4;
+    launches_ += 3;
     if (multi_) {
         CUDA_TRY(cudaEventRecord(evA_[lk_slot], sa()));
         CUDA_TRY(cudaStreamWaitEvent(stream_, evA_[lk_slot], 0));
@@ -717,13 +717,13 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
         launch_gray_resize(d_lanes_, 1, src, w, h, tight, m & 1, sa());
         if (multi_) CUDA_TRY(cudaEventRecord(evG_, sa()));
         launch_pyrdown(d_lanes_, 1, m & 1, sa());
-        launches_ += 3;
+        launches_ += 2;
         VS_TRY(redetect(m & 1, m, 0));
         if (first - 1 > m) {
             PtrPack s2; s2.p[0] = entry(first - 1).frames[0];
             launch_gray_resize(d_lanes_, 1, s2, w, h, tight, (first - 1) & 1, sa());
             launch_pyrdown(d_lanes_, 1, (first - 1) & 1, sa());
-            launches_ += 3;
+            launches_ += 2;
         }
         first_ = false;
         n_frames_ = first - 1; detect_counter_ = first - 1;      // the counters equal the frame number
