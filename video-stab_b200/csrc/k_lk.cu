@@ -16,19 +16,19 @@
 //     pre-converted in parallel (slow path).
 // Latency/occupancy-bound: ~200 warps per frame per lane.
 #include "kernels.h"
+#include <climits>
 
 #define LK_WARPS 4
 #define LK_NPIX (VS_WIN * VS_WIN)        // 225
 #define LK_PP 18                         // template patch edge: 15 + 1 (bilinear) + 2 (Scharr)
 #define LK_PW 24                         // staged template row: 18 + up to 3 bytes of alignment slack
 #define LK_JR 32                         // search region edge
+#define LK_PER_LANE 8                    // window pixels per lane: ceil(225 / 32)
 
 struct LkSmem {
     uint32_t P[LK_PP][LK_PW / 4];        // template patch rows (bytes), origin (px0, ipy-1)
     short2 D[16][16];                    // Scharr (Ix,Iy) at (ipx+c, ipy+r); zero outside the image
     uint32_t J[LK_JR][LK_JR / 4];        // search region rows (bytes), origin (jx0, jy0)
-    short Iw[LK_NPIX + 1];               // interpolated I window   (5 fractional bits)
-    short2 dI[LK_NPIX];                  // interpolated derivative window
     int term[3][LK_NPIX];                // per-pixel products (int, or float bits for the scalar tails)
 };
 
@@ -38,6 +38,18 @@ static __device__ __forceinline__ void lk_weights(float a, float b, int& w00, in
     w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, 1.f - b), s));
     w10 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, b), s));
     w11 = 16384 - w00 - w01 - w10;
+}
+
+// IDP.2A with SIGNED 16-bit weights and unsigned bytes: w11 = 16384 - w00 - w01 - w10 can come out as -1
+static __device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+static __device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
 static __device__ __forceinline__ int clamp_abs_sum(unsigned v) { return (int)min(v, 1u << 25); }
@@ -168,36 +180,58 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
             S.D[r][c] = make_short2((short)gx, (short)gy);
         }
         __syncwarp();
-        // ---- interpolated template window + covariance terms
+        // ---- interpolated template window + covariance terms.  The lane's 8 window pixels (p = lane + 32 k) stay
+        //      in registers for the whole level: Iw (5 fractional bits) and the packed (Ix, Iy) pair.
         unsigned abs11 = 0, abs12 = 0, abs22 = 0;
         int s11 = 0, s12 = 0, s22 = 0;
-        for (int p = lane; p < LK_NPIX; p += 32) {
-            int y = p / VS_WIN, x = p - y * VS_WIN;
-            const uint8_t* q0 = Pb + (y + 1) * LK_PW + x + 1 + pofs;
-            int iv = q0[0] * w00 + q0[1] * w01 + q0[LK_PW] * w10 + q0[LK_PW + 1] * w11;
-            short2 d00 = S.D[y][x], d01 = S.D[y][x + 1], d10 = S.D[y + 1][x], d11 = S.D[y + 1][x + 1];
-            int gx = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + 8192) >> 14;
-            int gy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + 8192) >> 14;
-            S.Iw[p] = (short)((iv + 256) >> 9);
-            S.dI[p] = make_short2((short)gx, (short)gy);
-            int t11 = gx * gx, t12 = gx * gy, t22 = gy * gy;
-            s11 += t11; s12 += t12; s22 += t22;
-            abs11 += (unsigned)t11; abs12 += (unsigned)abs(t12); abs22 += (unsigned)t22;
-            const bool tail = x >= 8;
-            S.term[0][p] = tail ? __float_as_int(__int2float_rn(t11)) : t11;
-            S.term[1][p] = tail ? __float_as_int(__int2float_rn(t12)) : t12;
-            S.term[2][p] = tail ? __float_as_int(__int2float_rn(t22)) : t22;
+        int Iw_r[LK_PER_LANE], dI_r[LK_PER_LANE];
+#pragma unroll
+        for (int k = 0; k < LK_PER_LANE; ++k) {
+            const int p = lane + 32 * k;
+            Iw_r[k] = 0; dI_r[k] = 0;
+            if (p < LK_NPIX) {
+                const int y = p / VS_WIN, x = p - y * VS_WIN;
+                const uint8_t* q0 = Pb + (y + 1) * LK_PW + x + 1 + pofs;
+                const int iv = q0[0] * w00 + q0[1] * w01 + q0[LK_PW] * w10 + q0[LK_PW + 1] * w11;
+                const short2 d00 = S.D[y][x], d01 = S.D[y][x + 1], d10 = S.D[y + 1][x], d11 = S.D[y + 1][x + 1];
+                const int gx = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + 8192) >> 14;
+                const int gy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + 8192) >> 14;
+                Iw_r[k] = (iv + 256) >> 9;
+                dI_r[k] = (gx & 0xffff) | (gy << 16);
+                const int t11 = gx * gx, t12 = gx * gy, t22 = gy * gy;
+                s11 += t11; s12 += t12; s22 += t22;
+                abs11 += (unsigned)t11; abs12 += (unsigned)abs(t12); abs22 += (unsigned)t22;
+            }
         }
-        __syncwarp();
         float A[3];
         {
             const int b11 = __reduce_add_sync(FULL, clamp_abs_sum(abs11));
             const int b12 = __reduce_add_sync(FULL, clamp_abs_sum(abs12));
             const int b22 = __reduce_add_sync(FULL, clamp_abs_sum(abs22));
             const int e11 = __reduce_add_sync(FULL, s11), e12 = __reduce_add_sync(FULL, s12), e22 = __reduce_add_sync(FULL, s22);
-            A[0] = (b11 <= (1 << 24)) ? (float)e11 : ordered_sum<true>(S.term[0], lane);
-            A[1] = (b12 <= (1 << 24)) ? (float)e12 : ordered_sum<true>(S.term[1], lane);
-            A[2] = (b22 <= (1 << 24)) ? (float)e22 : ordered_sum<true>(S.term[2], lane);
+            if (b11 <= (1 << 24) && b12 <= (1 << 24) && b22 <= (1 << 24)) {
+                A[0] = (float)e11; A[1] = (float)e12; A[2] = (float)e22;
+            } else {
+                // a partial sum can leave the exact-integer range of float32: replay the reference's ordered chains
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < LK_PER_LANE; ++k) {
+                    const int p = lane + 32 * k;
+                    if (p < LK_NPIX) {
+                        const int gx = (int)(short)(dI_r[k] & 0xffff), gy = dI_r[k] >> 16;
+                        const int t11 = gx * gx, t12 = gx * gy, t22 = gy * gy;
+                        const bool tail = (p - (p / VS_WIN) * VS_WIN) >= 8;
+                        S.term[0][p] = tail ? __float_as_int(__int2float_rn(t11)) : t11;
+                        S.term[1][p] = tail ? __float_as_int(__int2float_rn(t12)) : t12;
+                        S.term[2][p] = tail ? __float_as_int(__int2float_rn(t22)) : t22;
+                    }
+                }
+                __syncwarp();
+                A[0] = (b11 <= (1 << 24)) ? (float)e11 : ordered_sum<true>(S.term[0], lane);
+                A[1] = (b12 <= (1 << 24)) ? (float)e12 : ordered_sum<true>(S.term[1], lane);
+                A[2] = (b22 <= (1 << 24)) ? (float)e22 : ordered_sum<true>(S.term[2], lane);
+                __syncwarp();
+            }
         }
         const float A11 = __fmul_rn(A[0], FLT_SCALE), A12 = __fmul_rn(A[1], FLT_SCALE), A22 = __fmul_rn(A[2], FLT_SCALE);
         float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
@@ -212,6 +246,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
         }
         Dt = __fdiv_rn(1.f, Dt);
         float pdx = 0.f, pdy = 0.f;
+        uint32_t jw[LK_PER_LANE];
+        int cur_inx = INT_MIN, cur_iny = INT_MIN;
+#pragma unroll
+        for (int k = 0; k < LK_PER_LANE; ++k) jw[k] = 0u;
         for (int j = 0; j < 20; ++j) {
             const int inx = (int)floorf(qx), iny = (int)floorf(qy);
             if (inx < -VS_WIN || inx >= Jl.w || iny < -VS_WIN || iny >= Jl.h) {
@@ -228,22 +266,35 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
 #pragma unroll
                 for (int c = 0; c < LK_JR / 4; ++c) S.J[lane][c] = jr[c];
                 __syncwarp();
+                cur_inx = INT_MIN;
             }
-            const uint8_t* jb = Jb + (iny - jy0) * LK_JR + (inx - jx0);
+            if (inx != cur_inx || iny != cur_iny) {
+                // (re)build the lane's 2x2 tap words [q00 q01 q10 q11] for this integer window position
+                const uint8_t* jb = Jb + (iny - jy0) * LK_JR + (inx - jx0);
+#pragma unroll
+                for (int k = 0; k < LK_PER_LANE; ++k) {
+                    const int p = lane + 32 * k;
+                    if (p < LK_NPIX) {
+                        const int y = p / VS_WIN, x = p - y * VS_WIN;
+                        const uint8_t* q0 = jb + y * LK_JR + x;
+                        jw[k] = (uint32_t)q0[0] | ((uint32_t)q0[1] << 8) | ((uint32_t)q0[LK_JR] << 16) | ((uint32_t)q0[LK_JR + 1] << 24);
+                    }
+                }
+                cur_inx = inx; cur_iny = iny;
+            }
+            // bilinear sample as two IDP.2A with signed 16-bit weight pairs and unsigned pixel bytes
+            const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
             int sx = 0, sy = 0;
             unsigned absx = 0, absy = 0;
-            for (int p = lane; p < LK_NPIX; p += 32) {
-                int y = p / VS_WIN, x = p - y * VS_WIN;
-                const uint8_t* q0 = jb + y * LK_JR + x;
-                int jv = q0[0] * w00 + q0[1] * w01 + q0[LK_JR] * w10 + q0[LK_JR + 1] * w11;
-                int diff = ((jv + 256) >> 9) - (int)S.Iw[p];
-                short2 g = S.dI[p];
-                int tx = diff * g.x, ty = diff * g.y;
-                sx += tx; sy += ty;
-                absx += (unsigned)abs(tx); absy += (unsigned)abs(ty);
-                const bool tail = x >= 8;
-                S.term[0][p] = tail ? __float_as_int(__int2float_rn(tx)) : tx;
-                S.term[1][p] = tail ? __float_as_int(__int2float_rn(ty)) : ty;
+#pragma unroll
+            for (int k = 0; k < LK_PER_LANE; ++k) {
+                if (lane + 32 * k < LK_NPIX) {
+                    const int jv = dp2a_hi_su(Wb, jw[k], dp2a_lo_su(Wt, jw[k], 256));
+                    const int diff = (jv >> 9) - Iw_r[k];
+                    const int tx = diff * (int)(short)(dI_r[k] & 0xffff), ty = diff * (dI_r[k] >> 16);
+                    sx += tx; sy += ty;
+                    absx += (unsigned)abs(tx); absy += (unsigned)abs(ty);
+                }
             }
             const int bx = __reduce_add_sync(FULL, clamp_abs_sum(absx)), by = __reduce_add_sync(FULL, clamp_abs_sum(absy));
             const int ex = __reduce_add_sync(FULL, sx), ey = __reduce_add_sync(FULL, sy);
@@ -251,6 +302,19 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
             if (bx <= (1 << 24) && by <= (1 << 24)) {
                 ib1 = (float)ex; ib2 = (float)ey;
             } else {
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < LK_PER_LANE; ++k) {
+                    const int p = lane + 32 * k;
+                    if (p < LK_NPIX) {
+                        const int jv = dp2a_hi_su(Wb, jw[k], dp2a_lo_su(Wt, jw[k], 256));
+                        const int diff = (jv >> 9) - Iw_r[k];
+                        const int tx = diff * (int)(short)(dI_r[k] & 0xffff), ty = diff * (dI_r[k] >> 16);
+                        const bool tail = (p - (p / VS_WIN) * VS_WIN) >= 8;
+                        S.term[0][p] = tail ? __float_as_int(__int2float_rn(tx)) : tx;
+                        S.term[1][p] = tail ? __float_as_int(__int2float_rn(ty)) : ty;
+                    }
+                }
                 __syncwarp();
                 ib1 = ordered_sum_b(S.term[0], lane);
                 ib2 = ordered_sum_b(S.term[1], lane);
