@@ -41,7 +41,7 @@ struct WarpParams {
 
 // Per-lane device state.  An array of these lives in HBM; kernels index it with blockIdx.z.
 struct LaneDev {
-    Pyramid pyr[2];                 // ping-pong: previous / current analysis pyramid
+    Pyramid pyr[3];                 // analysis pyramids of frames n, n-1 and the one being built (slot = frame % 3)
     GrayLevel small0;               // 480x270 gray of the very first frame
     float* eig;                     // min-eigenvalue map, VS_AW*VS_AH floats
     unsigned int* eig_max;          // max(eig) as float bits (non-negative => orderable)

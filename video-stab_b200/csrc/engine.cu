@@ -124,6 +124,8 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     if (multi_) {
         CUDA_TRY(cudaStreamCreateWithFlags(&sA_, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&sC_, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sP_, cudaStreamNonBlocking));
+        for (auto& ev : evP_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evA_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evB_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evJ_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -167,7 +169,7 @@ vs_status Engine::alloc_fixed() {
     if (n_lanes_ > 8) VS_TRY(dalloc(allocs_, &d_tmaps_, (size_t)VS_MAX_GROUP * 128));
     for (int l = 0; l < n_lanes_; ++l) {
         LaneDev& L = h_lanes_[l];
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 3; ++s) {
             int w = VS_AW, h = VS_AH;
             for (int k = 0; k < VS_LEVELS; ++k) {
                 VS_TRY(alloc_level(allocs_, w, h, &L.pyr[s].lv[k]));
@@ -246,6 +248,8 @@ void Engine::free_all() {
     sync();
     collect_timing();
     for (auto& ev : evA_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : evP_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+    if (sP_) { cudaStreamDestroy(sP_); sP_ = nullptr; }
     for (auto& ev : evB_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evJ_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     if (evG_) { cudaEventDestroy(evG_); evG_ = nullptr; }
@@ -283,6 +287,7 @@ Engine::~Engine() {
 
 vs_status Engine::sync() {
     if (sH_) CUDA_TRY(cudaStreamSynchronize(sH_));
+    if (sP_) CUDA_TRY(cudaStreamSynchronize(sP_));
     if (sA_) CUDA_TRY(cudaStreamSynchronize(sA_));
     if (sC_) CUDA_TRY(cudaStreamSynchronize(sC_));
     if (stream_) CUDA_TRY(cudaStreamSynchronize(stream_));
@@ -295,8 +300,8 @@ vs_status Engine::join() {
     if (!multi_) return VS_OK;
     CUDA_TRY(cudaEventRecord(evJ_[0], sA_));
     CUDA_TRY(cudaEventRecord(evJ_[1], sC_));
-    CUDA_TRY(cudaStreamWaitEvent(stream_, evJ_[0], 0));
-    CUDA_TRY(cudaStreamWaitEvent(stream_, evJ_[1], 0));
+    CUDA_TRY(cudaEventRecord(evJ_[2], sP_));
+    for (auto& ev : evJ_) CUDA_TRY(cudaStreamWaitEvent(stream_, ev, 0));
     return VS_OK;
 }
 
@@ -304,6 +309,8 @@ vs_status Engine::clean() {
     // Stabilizer::clean, Stabilizer.cpp:221-256
     VS_TRY(sync());
     for (bool& b : evB_set_) b = false;
+    for (bool& b : evA_set_) b = false;
+    last_detect_frame_ = -100;
     for (bool& b : ring_ev_set_) b = false;
     for (bool& b : out_free_set_) b = false;
     c_pending_ = false;
@@ -340,7 +347,7 @@ vs_status Engine::ensure_geometry(int w, int h, bool need_ring, bool need_out, b
 StepInfo Engine::step_info(int pop_index) const {
     StepInfo s{};
     s.frame_no = n_frames_;
-    s.cur = n_frames_ & 1;
+    s.cur = n_frames_ % 3;
     s.pop_index = pop_index;
     s.path_len_at_pop = n_frames_;
     s.smoothing_radius = smoothing_radius_;
@@ -359,8 +366,8 @@ StepInfo Engine::step_info(int pop_index) const {
 
 // First-frame analysis (Stabilizer.cpp:271-368): 480x270 gray + GFTT with the user's parameters -> key-point slot 0
 vs_status Engine::first_frame_detect(const PtrPack& src, int w, int h, size_t stride) {
-    launch_gray_resize(d_lanes_, n_lanes_, src, w, h, stride, -1, sa());                  // :304-305
-    if (multi_) { CUDA_TRY(cudaEventRecord(evG_, sa())); CUDA_TRY(cudaStreamWaitEvent(sc(), evG_, 0)); }
+    launch_gray_resize(d_lanes_, n_lanes_, src, w, h, stride, -1, sp());                  // :304-305
+    if (multi_) { CUDA_TRY(cudaEventRecord(evG_, sp())); CUDA_TRY(cudaStreamWaitEvent(sc(), evG_, 0)); }
     CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc()));
     launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, 0, sc());  // :355-357
     if (multi_) { CUDA_TRY(cudaEventRecord(evC_, sc())); c_pending_ = true; }
@@ -380,37 +387,47 @@ vs_status Engine::redetect(int cur, int frame_no, int record_frame_no) {
     CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc()));
     int mc = p_.max_corners < 200 ? p_.max_corners : 200;
     launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, record_frame_no, (frame_no / 2) & 1, sc());   // :740-744
-    if (multi_) { CUDA_TRY(cudaEventRecord(evC_, sc())); c_pending_ = true; }
+    if (multi_) { CUDA_TRY(cudaEventRecord(evC_, sc())); c_pending_ = true; last_detect_frame_ = frame_no; }
     launches_ += 3;
     return VS_OK;
 }
 
-// generateTransform, Stabilizer.cpp:402-761 (CPU branch) as a launch sequence over three streams:
-//   A (analysis)  gray -> pyramid -> LK            needs: key points of the last detection (evC_)
+// generateTransform, Stabilizer.cpp:402-761 (CPU branch) as a launch sequence over four streams:
+//   P (pyramid)   gray -> pyramid                  needs: LK(n-2) done with the slot being overwritten (evA_)
+//   A (tracking)  LK                               needs: pyramid(n) (evP_), key points of the last detection (evC_)
 //   B (public)    motion [-> warp, in emit()]      needs: LK of this frame (evA_)
 //   C (detection) min-eig -> candidates -> select  needs: gray of this frame (evG_)
-// Tracker output is double-buffered by frame parity and key points by detection generation, so LK of frame
-// n+1 runs while frame n is still in its motion / detection kernels.
+// Pyramids live in three slots (frame % 3), tracker output is double-buffered by frame parity and key points by
+// detection generation, so the pyramid (and with it the detection) of frame n+1 is built while frame n is still
+// being tracked: the detection -> tracking dependency no longer stalls the stream that feeds the detector.
 vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     if (n_frames_ + 1 >= traj_cap_) VS_TRY(grow_trajectory());
     const int frame_no = ++n_frames_;
-    const int cur = frame_no & 1, prev = cur ^ 1;
+    const int cur = frame_no % 3, prev = (frame_no - 1) % 3;
     const int kp_slot = ((frame_no - 1) / 2) & 1, lk_slot = frame_no & 1;
     const bool detect = ((detect_counter_ + 1) % 2) == 0;                             // :696-697
     PtrPack src;
     for (int l = 0; l < n_lanes_; ++l) src.p[l] = e.frames[l];
     if (frame_no == 1) {
         // prevGray is still the 480x270 first-frame image: cv::resize it up (Stabilizer.cpp:598-603)
-        launch_upsample_small(d_lanes_, n_lanes_, prev, sa());
-        launch_pyrdown(d_lanes_, n_lanes_, prev, sa());
+        launch_upsample_small(d_lanes_, n_lanes_, prev, sp());
+        launch_pyrdown(d_lanes_, n_lanes_, prev, sp());
         launches_ += 2;
     }
-    { StageScope t(this, VS_STAGE_GRAY, sa());
-      launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sa()); }       // :449-450
-    if (multi_ && detect) CUDA_TRY(cudaEventRecord(evG_, sa()));
-    { StageScope t(this, VS_STAGE_PYRDOWN, sa());
-      launch_pyrdown(d_lanes_, n_lanes_, cur, sa()); }
     if (multi_) {
+        // slot `cur` was last read by LK(frame_no - 2) (as its previous frame) and, if frame_no - 3 re-detected,
+        // by that detection
+        if (frame_no >= 3 && evA_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sp(), evA_[(frame_no - 2) & 3], 0));
+        if (frame_no - last_detect_frame_ == 3) CUDA_TRY(cudaStreamWaitEvent(sp(), evC_, 0));
+    }
+    { StageScope t(this, VS_STAGE_GRAY, sp());
+      launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sp()); }       // :449-450
+    if (multi_ && detect) CUDA_TRY(cudaEventRecord(evG_, sp()));
+    { StageScope t(this, VS_STAGE_PYRDOWN, sp());
+      launch_pyrdown(d_lanes_, n_lanes_, cur, sp()); }
+    if (multi_) {
+        CUDA_TRY(cudaEventRecord(evP_[frame_no & 3], sp()));
+        CUDA_TRY(cudaStreamWaitEvent(sa(), evP_[frame_no & 3], 0));
         // LK writes tracker slot lk_slot (last read by the motion kernel of frame_no - 2) and reads key points
         if (frame_no >= 3 && evB_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sa(), evB_[(frame_no - 2) & 3], 0));
         if (c_pending_) { CUDA_TRY(cudaStreamWaitEvent(sa(), evC_, 0)); c_pending_ = false; }
@@ -419,8 +436,9 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
       launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa()); }   // :611-619
     launches_ += 3;
     if (multi_) {
-        CUDA_TRY(cudaEventRecord(evA_[lk_slot], sa()));
-        CUDA_TRY(cudaStreamWaitEvent(stream_, evA_[lk_slot], 0));
+        CUDA_TRY(cudaEventRecord(evA_[frame_no & 3], sa()));
+        evA_set_[frame_no & 3] = true;
+        CUDA_TRY(cudaStreamWaitEvent(stream_, evA_[frame_no & 3], 0));
     }
 
     const bool adaptive = p_.adaptive_smoothing != 0;
@@ -541,7 +559,7 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
     } else {
         const size_t tight = (size_t)w * 3;
         // pipelined host I/O: copy in on the copy-in stream, after the warp that last read this ring slot
-        cudaStream_t cs = pipe ? sH_ : sa();
+        cudaStream_t cs = pipe ? sH_ : sp();
         if (pipe && ring_ev_set_[e.slot]) CUDA_TRY(cudaStreamWaitEvent(sH_, evRing_[e.slot], 0));
         for (int l = 0; l < n_lanes_; ++l) {
             uint8_t* dst = d_ring_ + ((size_t)l * ring_slots_ + e.slot) * frame_bytes_;
@@ -553,7 +571,7 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
         if (pipe) {
             cudaEvent_t ev = evH_[h_seq_++ & 7];
             CUDA_TRY(cudaEventRecord(ev, sH_));
-            CUDA_TRY(cudaStreamWaitEvent(sa(), ev, 0));
+            CUDA_TRY(cudaStreamWaitEvent(sp(), ev, 0));
         }
     }
 
@@ -565,7 +583,7 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
         queue_.push_back(e);
         first_ = false;
         next_index_ = 1;
-        if (host_io && !pipe) CUDA_TRY(cudaStreamSynchronize(sa()));     // the caller may reuse its frame buffer
+        if (host_io && !pipe) CUDA_TRY(cudaStreamSynchronize(sp()));     // the caller may reuse its frame buffer
         return VS_OK;
     }
     queue_.push_back(e);
@@ -575,7 +593,7 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
         VS_TRY(emit(outs, out_stride, out_capacity, io, ow, oh));
         *produced = 1;
     } else if (host_io && !pipe) {
-        CUDA_TRY(cudaStreamSynchronize(sa()));        // the caller may reuse its frame buffer
+        CUDA_TRY(cudaStreamSynchronize(sp()));        // the caller may reuse its frame buffer
     }
     ++next_index_;
     return VS_OK;
@@ -714,15 +732,15 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
         // halo: corners from the even frame m, pyramid of frame first-1
         const int m = f;
         PtrPack src; src.p[0] = entry(m).frames[0];
-        launch_gray_resize(d_lanes_, 1, src, w, h, tight, m & 1, sa());
-        if (multi_) CUDA_TRY(cudaEventRecord(evG_, sa()));
-        launch_pyrdown(d_lanes_, 1, m & 1, sa());
+        launch_gray_resize(d_lanes_, 1, src, w, h, tight, m % 3, sp());
+        if (multi_) CUDA_TRY(cudaEventRecord(evG_, sp()));
+        launch_pyrdown(d_lanes_, 1, m % 3, sp());
         launches_ += 2;
-        VS_TRY(redetect(m & 1, m, 0));
+        VS_TRY(redetect(m % 3, m, 0));
         if (first - 1 > m) {
             PtrPack s2; s2.p[0] = entry(first - 1).frames[0];
-            launch_gray_resize(d_lanes_, 1, s2, w, h, tight, (first - 1) & 1, sa());
-            launch_pyrdown(d_lanes_, 1, (first - 1) & 1, sa());
+            launch_gray_resize(d_lanes_, 1, s2, w, h, tight, (first - 1) % 3, sp());
+            launch_pyrdown(d_lanes_, 1, (first - 1) % 3, sp());
             launches_ += 2;
         }
         first_ = false;

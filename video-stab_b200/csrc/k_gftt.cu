@@ -228,10 +228,13 @@ static __device__ bool greedy_pass(const LaneDev& L, const unsigned* sxy, const 
                     }
                 }
             }
+            // earlier lanes of this batch closer than minDistance.  Only lanes that survived the grid test can
+            // ever be accepted, so only those are walked (the mask is warp-uniform: no divergence).
             ok = ok && !hit;
-            // earlier lanes of this batch closer than minDistance
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
+            unsigned walk = __ballot_sync(FULL, ok);
+            while (walk) {
+                const int k = __ffs(walk) - 1;
+                walk &= walk - 1u;
                 const unsigned o = __shfl_sync(FULL, xy, k);
                 const int ddx = x - (int)(o & 0xffffu), ddy = y - (int)(o >> 16);
                 if ((ddx * ddx + ddy * ddy) < imd2) cmask |= 1u << k;
@@ -317,9 +320,13 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     int shift = 0;
     while ((range >> shift) >= (unsigned)SEL_BINS) ++shift;
     __syncthreads();
-    for (int i = tid; i < N; i += SEL_THREADS) {
-        unsigned bits = (unsigned)(L.cand[i] >> 32);
-        atomicAdd(&hist[(bits - lo) >> shift], 1u);
+    for (int i0 = tid; i0 < N; i0 += 4 * SEL_THREADS) {          // four independent loads in flight per thread
+        unsigned long long kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) kk[u] = (i0 + u * SEL_THREADS < N) ? __ldcg(L.cand + i0 + u * SEL_THREADS) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * SEL_THREADS < N) atomicAdd(&hist[((unsigned)(kk[u] >> 32) - lo) >> shift], 1u);
     }
     __syncthreads();
     // suffix scan (from the top bin down): thread r owns bins 4095-4r .. 4092-4r
@@ -381,9 +388,13 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
         if (tid == 0) S.count = 0;
         for (int i = tid; i < npad; i += SEL_THREADS) skeys[i] = 0ull;
         __syncthreads();
-        for (int i = tid; i < N; i += SEL_THREADS) {
-            unsigned long long k = L.cand[i];
-            if (k < U && k >= T) skeys[atomicAdd(&S.count, 1)] = k;
+        for (int i0 = tid; i0 < N; i0 += 4 * SEL_THREADS) {
+            unsigned long long kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kk[u] = (i0 + u * SEL_THREADS < N) ? __ldcg(L.cand + i0 + u * SEL_THREADS) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * SEL_THREADS < N && kk[u] < U && kk[u] >= T) skeys[atomicAdd(&S.count, 1)] = kk[u];
         }
         __syncthreads();
         bitonic_sort_desc(skeys, npad);
