@@ -72,7 +72,8 @@ struct LaneDev {
     float2* log_detected;
     float2* first_corners;
     int* first_count;
-    WarpParams* wp;
+    WarpParams* wp;                 // == wpb[0] (single-kernel entry points, clip mode scratch)
+    WarpParams* wpb[2];             // warp set-ups by output parity: motion of frame n+1 may run while output n is warped
     int kp_capacity;
     int log_depth;
     int record_capacity;
@@ -95,6 +96,7 @@ struct StepInfo {
     int kp_slot;           // key-point buffer this frame tracks from (LaneDev::kpb)
     int lk_slot;           // tracker output buffer of this frame (LaneDev::lkn / lks)
     int will_detect;       // corners are re-detected on this frame (the detector writes n_detected itself)
+    int wp_slot;           // warp set-up buffer of the output produced by this step (LaneDev::wpb)
 };
 
 static __device__ __forceinline__ int reflect101(int p, int len) {

@@ -125,6 +125,9 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
         CUDA_TRY(cudaStreamCreateWithFlags(&sA_, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&sC_, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&sP_, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sM_, cudaStreamNonBlocking));
+        for (auto& ev : evS_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : evW_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evP_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evA_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evB_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -196,7 +199,8 @@ vs_status Engine::alloc_fixed() {
         VS_TRY(dalloc(allocs_, &L.lks[1], (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.first_corners, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.kalman, (size_t)VS_KAL_FLOATS));
-        VS_TRY(dalloc(allocs_, &L.wp, (size_t)1));
+        VS_TRY(dalloc(allocs_, &L.wp, (size_t)2));
+        L.wpb[0] = L.wp; L.wpb[1] = L.wp + 1;
         size_t ln = (size_t)log_depth_ * kp_cap_;
         VS_TRY(dalloc(allocs_, &L.log_prev, ln));
         VS_TRY(dalloc(allocs_, &L.log_next, ln));
@@ -250,6 +254,9 @@ void Engine::free_all() {
     for (auto& ev : evA_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evP_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     if (sP_) { cudaStreamDestroy(sP_); sP_ = nullptr; }
+    if (sM_) { cudaStreamDestroy(sM_); sM_ = nullptr; }
+    for (auto& ev : evS_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : evW_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evB_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evJ_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     if (evG_) { cudaEventDestroy(evG_); evG_ = nullptr; }
@@ -288,6 +295,7 @@ Engine::~Engine() {
 vs_status Engine::sync() {
     if (sH_) CUDA_TRY(cudaStreamSynchronize(sH_));
     if (sP_) CUDA_TRY(cudaStreamSynchronize(sP_));
+    if (sM_) CUDA_TRY(cudaStreamSynchronize(sM_));
     if (sA_) CUDA_TRY(cudaStreamSynchronize(sA_));
     if (sC_) CUDA_TRY(cudaStreamSynchronize(sC_));
     if (stream_) CUDA_TRY(cudaStreamSynchronize(stream_));
@@ -301,6 +309,7 @@ vs_status Engine::join() {
     CUDA_TRY(cudaEventRecord(evJ_[0], sA_));
     CUDA_TRY(cudaEventRecord(evJ_[1], sC_));
     CUDA_TRY(cudaEventRecord(evJ_[2], sP_));
+    CUDA_TRY(cudaEventRecord(evJ_[3], sM_));
     for (auto& ev : evJ_) CUDA_TRY(cudaStreamWaitEvent(stream_, ev, 0));
     return VS_OK;
 }
@@ -310,6 +319,7 @@ vs_status Engine::clean() {
     VS_TRY(sync());
     for (bool& b : evB_set_) b = false;
     for (bool& b : evA_set_) b = false;
+    for (bool& b : evW_set_) b = false;
     last_detect_frame_ = -100;
     for (bool& b : ring_ev_set_) b = false;
     for (bool& b : out_free_set_) b = false;
@@ -361,6 +371,7 @@ StepInfo Engine::step_info(int pop_index) const {
     s.kp_slot = ((n_frames_ - 1) / 2) & 1;
     s.lk_slot = n_frames_ & 1;
     s.will_detect = ((detect_counter_ + 1) % 2) == 0;            // (++featureDetectionCounter % 2) == 0, Stabilizer.cpp:696-697
+    s.wp_slot = n_out_ & 1;
     return s;
 }
 
@@ -438,7 +449,7 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     if (multi_) {
         CUDA_TRY(cudaEventRecord(evA_[frame_no & 3], sa()));
         evA_set_[frame_no & 3] = true;
-        CUDA_TRY(cudaStreamWaitEvent(stream_, evA_[frame_no & 3], 0));
+        CUDA_TRY(cudaStreamWaitEvent(sm(), evA_[frame_no & 3], 0));
     }
 
     const bool adaptive = p_.adaptive_smoothing != 0;
@@ -448,10 +459,12 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         *will_pop = (int)queue_.size() >= gate;
         if (*will_pop) pop_index = queue_.front().index;
     }
-    { StageScope t(this, VS_STAGE_MOTION, stream_);
-      launch_motion(d_lanes_, n_lanes_, step_info(pop_index), stream_); }              // :629-688 (+ :783-908)
+    if (pop_index >= 0) VS_TRY(setup_slot_guard());
+    { StageScope t(this, VS_STAGE_MOTION, sm());
+      launch_motion(d_lanes_, n_lanes_, step_info(pop_index), sm()); }                 // :629-688 (+ :783-908)
     launches_ += 1;
-    if (multi_) { CUDA_TRY(cudaEventRecord(evB_[frame_no & 3], stream_)); evB_set_[frame_no & 3] = true; }
+    if (multi_) { CUDA_TRY(cudaEventRecord(evB_[frame_no & 3], sm())); evB_set_[frame_no & 3] = true; }
+    if (pop_index >= 0) VS_TRY(setup_ready());
 
     ++detect_counter_;
     if (detect) VS_TRY(redetect(cur, frame_no, frame_no));
@@ -460,16 +473,32 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         // latency gate: the one data-dependent host decision of the path, so this mode reads it back.
         if (frame_no >= 3) {
             int nr = 0;
-            CUDA_TRY(cudaMemcpyAsync(&nr, h_lanes_[0].kalman + VS_KAL_RADIUS_SLOT, sizeof(int), cudaMemcpyDeviceToHost, stream_));
-            CUDA_TRY(cudaStreamSynchronize(stream_));
+            CUDA_TRY(cudaMemcpyAsync(&nr, h_lanes_[0].kalman + VS_KAL_RADIUS_SLOT, sizeof(int), cudaMemcpyDeviceToHost, sm()));
+            CUDA_TRY(cudaStreamSynchronize(sm()));
             smoothing_radius_ = nr;
         }
         int gate = clampi(smoothing_radius_, 5, 35);
         *will_pop = (int)queue_.size() >= gate;
         if (*will_pop) {
-            launch_smooth_only(d_lanes_, n_lanes_, step_info(queue_.front().index), stream_);
+            VS_TRY(setup_slot_guard());
+            launch_smooth_only(d_lanes_, n_lanes_, step_info(queue_.front().index), sm());
             launches_ += 1;
+            VS_TRY(setup_ready());
         }
+    }
+    return VS_OK;
+}
+
+// The warp set-up of output n_out_ lives in LaneDev::wpb[n_out_ & 1]: its writer (motion stream) waits for the
+// warp of output n_out_ - 2 (public stream), and the warp waits for the writer.
+vs_status Engine::setup_slot_guard() {
+    if (multi_ && evW_set_[n_out_ & 1]) CUDA_TRY(cudaStreamWaitEvent(sm(), evW_[n_out_ & 1], 0));
+    return VS_OK;
+}
+vs_status Engine::setup_ready() {
+    if (multi_) {
+        CUDA_TRY(cudaEventRecord(evS_[n_out_ & 1], sm()));
+        CUDA_TRY(cudaStreamWaitEvent(stream_, evS_[n_out_ & 1], 0));
     }
     return VS_OK;
 }
@@ -509,6 +538,7 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         g.mode = mode; g.border = b; g.border_mode = border_mode_;
         g.out_w = w; g.out_h = h; g.out_stride = dstride;
         g.d_tmaps = d_tmaps_;
+        g.wp_slot = n_out_ & 1;
         int m2 = mode;
         if (mode == 2 && (W_ - 2 * b <= 0 || H_ - 2 * b <= 0)) m2 = 0;                // border larger than image
         g.mode = m2;
@@ -518,6 +548,7 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
           launch_warp(d_lanes_, n_lanes_, src, dst, g, scratch.data(), stream_); }
         launches_ += (m2 == 2) ? 1 + n_lanes_ : 1;
     }
+    if (multi_) { CUDA_TRY(cudaEventRecord(evW_[n_out_ & 1], stream_)); evW_set_[n_out_ & 1] = true; }
     if (pipe) {
         CUDA_TRY(cudaEventRecord(evRing_[e.slot], stream_));            // the ring slot of this frame may be refilled
         ring_ev_set_[e.slot] = true;
@@ -605,8 +636,10 @@ vs_status Engine::flush(uint8_t* const* outs, size_t out_stride, size_t out_capa
     *produced = 0;
     if (queue_.empty()) return VS_OK;
     CUDA_TRY(cudaSetDevice(device_));
-    launch_smooth_only(d_lanes_, n_lanes_, step_info(queue_.front().index), stream_);
+    VS_TRY(setup_slot_guard());
+    launch_smooth_only(d_lanes_, n_lanes_, step_info(queue_.front().index), sm());
     launches_ += 1;
+    VS_TRY(setup_ready());
     VS_TRY(emit(outs, out_stride, out_capacity, io, ow, oh));
     *produced = 1;
     return VS_OK;
@@ -757,7 +790,7 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
     if (n_out) *n_out = n;
     if (n > 0 && out_host)
         CUDA_TRY(cudaMemcpyAsync(out_host, h_lanes_[0].transforms + 3 * (size_t)(first_tr - 1), sizeof(float) * 3 * n,
-                                 cudaMemcpyDeviceToHost, stream_));
+                                 cudaMemcpyDeviceToHost, sm()));
     VS_TRY(sync());
     return VS_OK;
 }

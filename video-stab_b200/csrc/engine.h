@@ -84,6 +84,9 @@ private:
     vs_status redetect(int cur, int frame_no, int record_frame_no);
     cudaStream_t sa() const { return multi_ ? sA_ : stream_; }
     cudaStream_t sp() const { return multi_ ? sP_ : stream_; }
+    cudaStream_t sm() const { return multi_ ? sM_ : stream_; }
+    vs_status setup_slot_guard();
+    vs_status setup_ready();
     cudaStream_t sc() const { return multi_ ? sC_ : stream_; }
     vs_status emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, int io, int* ow, int* oh);
     StepInfo step_info(int pop_index) const;
@@ -91,11 +94,12 @@ private:
 
     vs_params p_{};
     int device_ = 0, n_lanes_ = 0;
-    cudaStream_t stream_ = nullptr;           // public stream: motion + output stage
+    cudaStream_t stream_ = nullptr;           // public stream: output stage (warp, copies out)
+    cudaStream_t sM_ = nullptr;               // motion: RANSAC, trajectory, smoothing, warp set-up
     cudaStream_t sA_ = nullptr, sC_ = nullptr, sP_ = nullptr; // tracking (LK), corner detection, pyramid build
     bool multi_ = false;
-    cudaEvent_t evA_[4] = {}, evB_[4] = {}, evP_[4] = {}, evJ_[3] = {}, evG_ = nullptr, evC_ = nullptr;
-    bool evB_set_[4] = {}, evA_set_[4] = {};
+    cudaEvent_t evA_[4] = {}, evB_[4] = {}, evP_[4] = {}, evJ_[4] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_ = nullptr;
+    bool evB_set_[4] = {}, evA_set_[4] = {}, evW_set_[2] = {};
     int last_detect_frame_ = -100;
     bool c_pending_ = false;
     cudaStream_t sH_ = nullptr, sO_ = nullptr; // copy-in / copy-out streams of the pipelined host path

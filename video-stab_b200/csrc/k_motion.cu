@@ -281,14 +281,18 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
 
 __global__ void __launch_bounds__(32) k_smooth_only(const LaneDev* __restrict__ lanes, StepInfo info) {
     __shared__ float gk[512];
-    const LaneDev& L = lanes[blockIdx.z];
+    LaneDev Lm = lanes[blockIdx.z];
+    Lm.wp = Lm.wpb[info.wp_slot];
+    const LaneDev& L = Lm;
     if (threadIdx.x == 0) smooth_and_setup(L, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
 }
 
 __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict__ lanes, StepInfo info) {
     extern __shared__ unsigned char mo_raw[];
     MoSmem& S = *reinterpret_cast<MoSmem*>(mo_raw);
-    const LaneDev& L = lanes[blockIdx.z];
+    LaneDev Lm = lanes[blockIdx.z];
+    Lm.wp = Lm.wpb[info.wp_slot];
+    const LaneDev& L = Lm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const int n_prev = min(min(*L.kpc[info.kp_slot], L.kp_capacity), MO_MAXP);

@@ -386,7 +386,7 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
            const LaneDev* __restrict__ lanes, const WarpParams* __restrict__ wps,
            PtrPack srcp, const uint8_t* __restrict__ src0, size_t sframe, size_t sstride, int sw, int sh,
            MutPtrPack dstp, uint8_t* __restrict__ dst0, size_t dframe, int dw, int dh, size_t dstride,
-           int rows_per_cta, int dst_vec) {
+           int rows_per_cta, int dst_vec, int wp_slot) {
     extern __shared__ __align__(1024) unsigned char wt_smem[];
     uint32_t* const S_src = reinterpret_cast<uint32_t*>(wt_smem);
     unsigned char* const S_raw = wt_smem + WT_ROWS * WT_TPITCH;
@@ -396,7 +396,7 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
     unsigned long long* const S_mbar = reinterpret_cast<unsigned long long*>(S_box + 2);
 
     const int z = blockIdx.z;
-    const double* __restrict__ m = lanes_mode ? lanes[z].wp->m : wps[z].m;
+    const double* __restrict__ m = lanes_mode ? lanes[z].wpb[wp_slot]->m : wps[z].m;
     uint8_t* __restrict__ dst = lanes_mode ? dstp.p[z] : dst0 + (size_t)z * dframe;
     const CUtensorMap* tmap = dmaps ? dmaps + (lanes_mode ? z : 0) : &pack.m[lanes_mode ? z : 0];
     const int zc = lanes_mode ? 0 : z;
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(WT_THREADS, 4) k_warp_tiled_lanes(const LaneDe
                                                                   WarpGeom g, int rows_per_cta, int src_vec, int dst_vec) {
     __shared__ __align__(16) WarpTileSmem S;
     warp_strip(S, src.p[blockIdx.z], g.src_w, g.src_h, g.src_stride, dst.p[blockIdx.z], g.out_w, g.out_h, g.out_stride,
-               lanes[blockIdx.z].wp->m, rows_per_cta, src_vec != 0, dst_vec != 0);
+               lanes[blockIdx.z].wpb[g.wp_slot]->m, rows_per_cta, src_vec != 0, dst_vec != 0);
 }
 
 __global__ void __launch_bounds__(WT_THREADS, 4) k_warp_tiled_frames(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride,
@@ -593,7 +593,7 @@ static inline bool vec_ok(const void* p, size_t stride, int a) { return ((uintpt
 
 template <bool BORDER>
 __global__ void __launch_bounds__(256) k_warp_lanes(const LaneDev* __restrict__ lanes, PtrPack src, MutPtrPack dst, WarpGeom g) {
-    const WarpParams* wp = lanes[blockIdx.z].wp;
+    const WarpParams* wp = lanes[blockIdx.z].wpb[g.wp_slot];
     int x = blockIdx.x * 64 + (threadIdx.x & 63);
     int y = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (x >= g.out_w || y >= g.out_h) return;
@@ -679,7 +679,7 @@ static void launch_warp_plain(const LaneDev* lanes, int n_lanes, const PtrPack& 
             }
             k_warp_tma<<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, dmaps, 1, lanes, nullptr, src, nullptr, 0, g.src_stride,
                                                                g.src_w, g.src_h, dst, nullptr, 0, g.out_w, g.out_h, g.out_stride,
-                                                               rows, dv ? 1 : 0);
+                                                               rows, dv ? 1 : 0, g.wp_slot);
             return;
         }
     }
@@ -724,7 +724,7 @@ void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, si
             PtrPack sp{};
             MutPtrPack dp{};
             k_warp_tma<<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, nullptr, 0, nullptr, d_wp, sp, src, sframe, sstride, sw, sh, dp,
-                                                               dst, dframe, dw, dh, dstride, rows, dv ? 1 : 0);
+                                                               dst, dframe, dw, dh, dstride, rows, dv ? 1 : 0, 0);
             return;
         }
     }

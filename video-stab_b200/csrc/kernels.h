@@ -57,6 +57,7 @@ struct WarpGeom {
     int border, border_mode;
     int out_w, out_h;
     size_t out_stride;
+    int wp_slot;            // LaneDev::wpb index holding the warp set-up of this output
     void* d_tmaps;          // device scratch for VS_MAX_GROUP tensor maps (batches of more than 8 lanes), or nullptr
 };
 void launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, WarpGeom g,
