@@ -22,6 +22,11 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# A handle overlaps its stages on six CUDA streams (eight with the pipelined host path); the default of 8 hardware
+# queues would alias them with the other streams of this process and add false dependencies.  Must be set before
+# the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading

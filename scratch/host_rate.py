@@ -1,4 +1,5 @@
 import os, sys, time
+if len(sys.argv) > 1: os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] = sys.argv[1]
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__; __graft_entry__.build()

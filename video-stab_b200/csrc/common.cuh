@@ -48,6 +48,12 @@ struct LaneDev {
     unsigned long long* cand;       // corner candidates: (float bits << 32) | linear address
     int* cand_count;
     unsigned int* grid;             // min-distance grid: per cell [count, slot0..slot3]
+    // second set of detection scratch (generation 1): two detections can be in flight on two streams
+    float* eig2;
+    unsigned int* eig_max2;
+    unsigned long long* cand2;
+    int* cand_count2;
+    unsigned int* grid2;
     float2* kp;                     // "prevKeypointsCPU_"  (slot 0; the single-kernel entry points use these four)
     int* kp_count;
     float2* lk_next;
@@ -98,6 +104,29 @@ struct StepInfo {
     int will_detect;       // corners are re-detected on this frame (the detector writes n_detected itself)
     int wp_slot;           // warp set-up buffer of the output produced by this step (LaneDev::wpb)
 };
+
+// Detection scratch / key-point buffers of generation `gen` (0 / 1).  Plain selects on the lane record in global
+// memory: a by-value copy of LaneDev with run-time indexed members would live on the local-memory stack.
+struct DetView {
+    float* eig;
+    unsigned int* eig_max;
+    unsigned long long* cand;
+    int* cand_count;
+    unsigned int* grid;
+    float2* kp;
+    int* kp_count;
+};
+static __device__ __forceinline__ DetView det_view(const LaneDev& L, int gen) {
+    DetView v;
+    v.eig = gen ? L.eig2 : L.eig;
+    v.eig_max = gen ? L.eig_max2 : L.eig_max;
+    v.cand = gen ? L.cand2 : L.cand;
+    v.cand_count = gen ? L.cand_count2 : L.cand_count;
+    v.grid = gen ? L.grid2 : L.grid;
+    v.kp = gen ? L.kpb[1] : L.kpb[0];
+    v.kp_count = gen ? L.kpc[1] : L.kpc[0];
+    return v;
+}
 
 static __device__ __forceinline__ int reflect101(int p, int len) {
     // cv::borderInterpolate(BORDER_REFLECT_101) for |overshoot| < len

@@ -123,7 +123,7 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     multi_ = !p.adaptive_smoothing;
     if (multi_) {
         CUDA_TRY(cudaStreamCreateWithFlags(&sA_, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&sC_, cudaStreamNonBlocking));
+        for (auto& st : sC_) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&sP_, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&sM_, cudaStreamNonBlocking));
         for (auto& ev : evS_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -133,10 +133,10 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
         for (auto& ev : evB_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evJ_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&evG_, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&evC_, cudaEventDisableTiming));
-        // pipelined host I/O (push_many / flush_many): copy-in and copy-out streams
-        CUDA_TRY(cudaStreamCreateWithFlags(&sH_, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&sO_, cudaStreamNonBlocking));
+        for (auto& ev : evC_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        // pipelined host I/O (push_many / flush_many): the copy-in and copy-out streams are created on first use
+        // (a handle that never calls push_many stays at six streams: the default number of hardware queues is 8,
+        // CUDA_DEVICE_MAX_CONNECTIONS, and streams beyond it pick up false dependencies)
         for (auto& ev : evH_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evRing_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evOutReady_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -160,7 +160,7 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
 vs_status Engine::alloc_fixed() {
     h_lanes_.assign(n_lanes_, LaneDev{});
     VS_TRY(dalloc(allocs_, &d_lanes_, (size_t)n_lanes_));
-    VS_TRY(dalloc(allocs_, &d_detect_counters_, (size_t)n_lanes_ * 2));
+    VS_TRY(dalloc(allocs_, &d_detect_counters_, (size_t)n_lanes_ * 4));      // [generation][lane][eig_max, cand_count]
     int* small_counters = nullptr;
     VS_TRY(dalloc(allocs_, &small_counters, (size_t)n_lanes_ * 3));
     size_t gw = gftt_grid_words(VS_FW, VS_FH, p_.min_distance);
@@ -185,6 +185,11 @@ vs_status Engine::alloc_fixed() {
         VS_TRY(dalloc(allocs_, &L.grid, gw));
         L.eig_max = d_detect_counters_ + 2 * l;
         L.cand_count = (int*)(d_detect_counters_ + 2 * l + 1);
+        VS_TRY(dalloc(allocs_, &L.eig2, (size_t)VS_AW * VS_AH));
+        VS_TRY(dalloc(allocs_, &L.cand2, (size_t)VS_AW * VS_AH));
+        VS_TRY(dalloc(allocs_, &L.grid2, gw));
+        L.eig_max2 = d_detect_counters_ + 2 * n_lanes_ + 2 * l;
+        L.cand_count2 = (int*)(d_detect_counters_ + 2 * n_lanes_ + 2 * l + 1);
         L.kp_count = small_counters + 3 * l;
         L.first_count = small_counters + 3 * l + 1;
         L.kpc[0] = L.kp_count;
@@ -260,13 +265,13 @@ void Engine::free_all() {
     for (auto& ev : evB_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evJ_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     if (evG_) { cudaEventDestroy(evG_); evG_ = nullptr; }
-    if (evC_) { cudaEventDestroy(evC_); evC_ = nullptr; }
+    for (auto& ev : evC_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evH_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evRing_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evOutReady_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evOutFree_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     if (sA_) { cudaStreamDestroy(sA_); sA_ = nullptr; }
-    if (sC_) { cudaStreamDestroy(sC_); sC_ = nullptr; }
+    for (auto& st : sC_) if (st) { cudaStreamDestroy(st); st = nullptr; }
     if (sH_) { cudaStreamDestroy(sH_); sH_ = nullptr; }
     if (sO_) { cudaStreamDestroy(sO_); sO_ = nullptr; }
     for (cudaEvent_t ev : event_pool_) cudaEventDestroy(ev);
@@ -297,7 +302,7 @@ vs_status Engine::sync() {
     if (sP_) CUDA_TRY(cudaStreamSynchronize(sP_));
     if (sM_) CUDA_TRY(cudaStreamSynchronize(sM_));
     if (sA_) CUDA_TRY(cudaStreamSynchronize(sA_));
-    if (sC_) CUDA_TRY(cudaStreamSynchronize(sC_));
+    for (auto& st : sC_) if (st) CUDA_TRY(cudaStreamSynchronize(st));
     if (stream_) CUDA_TRY(cudaStreamSynchronize(stream_));
     if (sO_) CUDA_TRY(cudaStreamSynchronize(sO_));
     return VS_OK;
@@ -307,7 +312,8 @@ vs_status Engine::sync() {
 vs_status Engine::join() {
     if (!multi_) return VS_OK;
     CUDA_TRY(cudaEventRecord(evJ_[0], sA_));
-    CUDA_TRY(cudaEventRecord(evJ_[1], sC_));
+    CUDA_TRY(cudaEventRecord(evJ_[1], sC_[0]));
+    CUDA_TRY(cudaEventRecord(evJ_[4], sC_[1]));
     CUDA_TRY(cudaEventRecord(evJ_[2], sP_));
     CUDA_TRY(cudaEventRecord(evJ_[3], sM_));
     for (auto& ev : evJ_) CUDA_TRY(cudaStreamWaitEvent(stream_, ev, 0));
@@ -323,7 +329,7 @@ vs_status Engine::clean() {
     last_detect_frame_ = -100;
     for (bool& b : ring_ev_set_) b = false;
     for (bool& b : out_free_set_) b = false;
-    c_pending_ = false;
+    c_pending_[0] = c_pending_[1] = false;
     queue_.clear();
     first_ = true;
     next_index_ = 0;
@@ -378,10 +384,10 @@ StepInfo Engine::step_info(int pop_index) const {
 // First-frame analysis (Stabilizer.cpp:271-368): 480x270 gray + GFTT with the user's parameters -> key-point slot 0
 vs_status Engine::first_frame_detect(const PtrPack& src, int w, int h, size_t stride) {
     launch_gray_resize(d_lanes_, n_lanes_, src, w, h, stride, -1, sp());                  // :304-305
-    if (multi_) { CUDA_TRY(cudaEventRecord(evG_, sp())); CUDA_TRY(cudaStreamWaitEvent(sc(), evG_, 0)); }
-    CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc()));
-    launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, 0, sc());  // :355-357
-    if (multi_) { CUDA_TRY(cudaEventRecord(evC_, sc())); c_pending_ = true; }
+    if (multi_) { CUDA_TRY(cudaEventRecord(evG_, sp())); CUDA_TRY(cudaStreamWaitEvent(sc(0), evG_, 0)); }
+    CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc(0)));
+    launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, 0, sc(0));  // :355-357
+    if (multi_) { CUDA_TRY(cudaEventRecord(evC_[0], sc(0))); c_pending_[0] = true; }
     launches_ += 4;
     return VS_OK;
 }
@@ -390,15 +396,16 @@ vs_status Engine::first_frame_detect(const PtrPack& src, int w, int h, size_t st
 // detection stream.  It reads level 0 of the frame (ready at evG_) and overwrites the key points last read by
 // the motion kernel of frame_no - 2.
 vs_status Engine::redetect(int cur, int frame_no, int record_frame_no) {
+    const int gen = (frame_no / 2) & 1;               // detection generation: scratch set, key-point slot, stream, event
     if (multi_) {
-        CUDA_TRY(cudaStreamWaitEvent(sc(), evG_, 0));
-        if (frame_no >= 2 && evB_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sc(), evB_[(frame_no - 2) & 3], 0));
+        CUDA_TRY(cudaStreamWaitEvent(sc(gen), evG_, 0));
+        if (frame_no >= 2 && evB_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sc(gen), evB_[(frame_no - 2) & 3], 0));
     }
-    StageScope t(this, VS_STAGE_GFTT, sc());
-    CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc()));
+    StageScope t(this, VS_STAGE_GFTT, sc(gen));
+    CUDA_TRY(cudaMemsetAsync(d_detect_counters_ + (size_t)gen * 2 * n_lanes_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc(gen)));
     int mc = p_.max_corners < 200 ? p_.max_corners : 200;
-    launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, record_frame_no, (frame_no / 2) & 1, sc());   // :740-744
-    if (multi_) { CUDA_TRY(cudaEventRecord(evC_, sc())); c_pending_ = true; last_detect_frame_ = frame_no; }
+    launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, record_frame_no, gen, sc(gen));   // :740-744
+    if (multi_) { CUDA_TRY(cudaEventRecord(evC_[gen], sc(gen))); c_pending_[gen] = true; last_detect_frame_ = frame_no; }
     launches_ += 3;
     return VS_OK;
 }
@@ -429,7 +436,7 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         // slot `cur` was last read by LK(frame_no - 2) (as its previous frame) and, if frame_no - 3 re-detected,
         // by that detection
         if (frame_no >= 3 && evA_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sp(), evA_[(frame_no - 2) & 3], 0));
-        if (frame_no - last_detect_frame_ == 3) CUDA_TRY(cudaStreamWaitEvent(sp(), evC_, 0));
+        if (frame_no - last_detect_frame_ == 3) CUDA_TRY(cudaStreamWaitEvent(sp(), evC_[(last_detect_frame_ / 2) & 1], 0));
     }
     { StageScope t(this, VS_STAGE_GRAY, sp());
       launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sp()); }       // :449-450
@@ -441,7 +448,7 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         CUDA_TRY(cudaStreamWaitEvent(sa(), evP_[frame_no & 3], 0));
         // LK writes tracker slot lk_slot (last read by the motion kernel of frame_no - 2) and reads key points
         if (frame_no >= 3 && evB_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sa(), evB_[(frame_no - 2) & 3], 0));
-        if (c_pending_) { CUDA_TRY(cudaStreamWaitEvent(sa(), evC_, 0)); c_pending_ = false; }
+        if (c_pending_[kp_slot]) { CUDA_TRY(cudaStreamWaitEvent(sa(), evC_[kp_slot], 0)); c_pending_[kp_slot] = false; }
     }
     { StageScope t(this, VS_STAGE_LK, sa());
       launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa()); }   // :611-619
@@ -506,6 +513,10 @@ vs_status Engine::setup_ready() {
 // the warp half of applyNextSmoothTransform, Stabilizer.cpp:979-1137
 vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, int io, int* ow, int* oh) {
     const bool host_io = io != VS_IO_DEVICE, pipe = io == VS_IO_HOST_PIPE && multi_;
+    if (pipe && !sO_) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&sH_, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sO_, cudaStreamNonBlocking));
+    }
     QueueEntry e = queue_.front();
     queue_.pop_front();
     const bool passthrough = e.index >= n_frames_;                                    // :774-780
@@ -572,6 +583,10 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
                        size_t out_capacity, unsigned flags, int io, int* ow, int* oh, int* produced) {
     const bool host_io = io != VS_IO_DEVICE, pipe = io == VS_IO_HOST_PIPE && multi_;
     *produced = 0;
+    if (pipe && !sH_) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&sH_, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sO_, cudaStreamNonBlocking));
+    }
     if (!frames || w <= 0 || h <= 0) return VS_OK;                                    // frame.empty() -> empty Mat (:263)
     if (w < 4 || h < 4) return vs_set_error(VS_ERR_INVALID_ARG, "frame too small");
     if (stride == 0) stride = (size_t)w * 3;

@@ -87,7 +87,7 @@ private:
     cudaStream_t sm() const { return multi_ ? sM_ : stream_; }
     vs_status setup_slot_guard();
     vs_status setup_ready();
-    cudaStream_t sc() const { return multi_ ? sC_ : stream_; }
+    cudaStream_t sc(int gen) const { return multi_ ? sC_[gen & 1] : stream_; }
     vs_status emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, int io, int* ow, int* oh);
     StepInfo step_info(int pop_index) const;
     void free_all();
@@ -96,12 +96,12 @@ private:
     int device_ = 0, n_lanes_ = 0;
     cudaStream_t stream_ = nullptr;           // public stream: output stage (warp, copies out)
     cudaStream_t sM_ = nullptr;               // motion: RANSAC, trajectory, smoothing, warp set-up
-    cudaStream_t sA_ = nullptr, sC_ = nullptr, sP_ = nullptr; // tracking (LK), corner detection, pyramid build
+    cudaStream_t sA_ = nullptr, sC_[2] = {}, sP_ = nullptr;   // tracking (LK), corner detection (two generations), pyramid build
     bool multi_ = false;
-    cudaEvent_t evA_[4] = {}, evB_[4] = {}, evP_[4] = {}, evJ_[4] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_ = nullptr;
+    cudaEvent_t evA_[4] = {}, evB_[4] = {}, evP_[4] = {}, evJ_[5] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[2] = {};
     bool evB_set_[4] = {}, evA_set_[4] = {}, evW_set_[2] = {};
     int last_detect_frame_ = -100;
-    bool c_pending_ = false;
+    bool c_pending_[2] = {};
     cudaStream_t sH_ = nullptr, sO_ = nullptr; // copy-in / copy-out streams of the pipelined host path
     cudaEvent_t evH_[8] = {}, evRing_[36] = {}, evOutReady_[VS_OUT_SLOTS] = {}, evOutFree_[VS_OUT_SLOTS] = {};
     bool ring_ev_set_[36] = {}, out_free_set_[VS_OUT_SLOTS] = {};

@@ -22,12 +22,13 @@ static __device__ __forceinline__ GrayLevel gftt_src(const LaneDev& L, int slot)
 }
 
 // ------------------------------------------------------------------------------------ k_min_eig
-__global__ void __launch_bounds__(256) k_min_eig(const LaneDev* __restrict__ lanes, int slot) {
+__global__ void __launch_bounds__(256) k_min_eig(const LaneDev* __restrict__ lanes, int slot, int gen) {
     __shared__ float sxx[EIG_TH + 2][EIG_TW + 2];
     __shared__ float sxy[EIG_TH + 2][EIG_TW + 2];
     __shared__ float syy[EIG_TH + 2][EIG_TW + 2];
     __shared__ unsigned int smax;
     const LaneDev& L = lanes[blockIdx.z];
+    const DetView D = det_view(L, gen);
     const GrayLevel G = gftt_src(L, slot);
     const int x0 = blockIdx.x * EIG_TW, y0 = blockIdx.y * EIG_TH;
     const float f1 = (float)(1.0 / (4.0 * 3.0 * 255.0));
@@ -75,34 +76,35 @@ __global__ void __launch_bounds__(256) k_min_eig(const LaneDev* __restrict__ lan
         float a = __fmul_rn((float)bxx, 0.5f), b = (float)bxy, cc = __fmul_rn((float)byy, 0.5f);
         float d = __fsub_rn(a, cc);
         float e = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
-        L.eig[(size_t)y * G.w + x] = e;
+        D.eig[(size_t)y * G.w + x] = e;
         if (e > 0.f) lmax = max(lmax, __float_as_uint(e));
     }
     lmax = __reduce_max_sync(0xffffffffu, lmax);
     if ((threadIdx.x & 31) == 0 && lmax) atomicMax(&smax, lmax);
     __syncthreads();
-    if (threadIdx.x == 0 && smax) atomicMax(L.eig_max, smax);
+    if (threadIdx.x == 0 && smax) atomicMax(D.eig_max, smax);
 }
 
 // --------------------------------------------------------------------------------- k_candidates
 // threshold + 3x3 non-max suppression; compaction is warp-ballot -> CTA-level prefix in shared memory
 // -> one global atomic per CTA.
-__global__ void __launch_bounds__(256) k_candidates(const LaneDev* __restrict__ lanes, int slot, double quality) {
+__global__ void __launch_bounds__(256) k_candidates(const LaneDev* __restrict__ lanes, int slot, double quality, int gen) {
     __shared__ int s_count, s_base;
     __shared__ int s_warp_off[8];
     const LaneDev& L = lanes[blockIdx.z];
+    const DetView D = det_view(L, gen);
     const GrayLevel G = gftt_src(L, slot);
     const int w = G.w, h = G.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int x = blockIdx.x * 64 + (threadIdx.x & 63);
     int y = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (threadIdx.x == 0) s_count = 0;
-    const float mx = __uint_as_float(*L.eig_max);
+    const float mx = __uint_as_float(*D.eig_max);
     const float thr = (float)((double)mx * quality);
     bool is = false;
     float e = 0.f;
     if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
-        const float* p = L.eig + (size_t)y * w + x;
+        const float* p = D.eig + (size_t)y * w + x;
         e = p[0];
         if (e > thr) {
             is = e >= p[-1] && e >= p[1] && e >= p[-w - 1] && e >= p[-w] && e >= p[-w + 1] &&
@@ -113,11 +115,11 @@ __global__ void __launch_bounds__(256) k_candidates(const LaneDev* __restrict__ 
     const unsigned m = __ballot_sync(0xffffffffu, is);
     if (lane == 0 && m) s_warp_off[warp] = atomicAdd(&s_count, __popc(m));
     __syncthreads();
-    if (threadIdx.x == 0 && s_count) s_base = atomicAdd(L.cand_count, s_count);
+    if (threadIdx.x == 0 && s_count) s_base = atomicAdd(D.cand_count, s_count);
     __syncthreads();
     if (is) {
         int pos = s_base + s_warp_off[warp] + __popc(m & ((1u << lane) - 1u));
-        L.cand[pos] = ((unsigned long long)__float_as_uint(e) << 32) | (unsigned)(y * w + x);
+        D.cand[pos] = ((unsigned long long)__float_as_uint(e) << 32) | (unsigned)(y * w + x);
     }
 }
 
@@ -193,7 +195,7 @@ static __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
 // parallel by the whole CTA beforehand (all integer divisions live there).
 #define GRID_EMPTY 0x40004000u      // sentinel slot: x = y = 16384, never within minDistance of a real pixel (no int overflow)
 template <bool SMEM_GRID>
-static __device__ bool greedy_pass(const LaneDev& L, const unsigned* sxy, const int* scell, int m, int gw, int gh,
+static __device__ bool greedy_pass(float2* kp_out, const unsigned* sxy, const int* scell, int m, int gw, int gh,
                                    bool use_grid, int imd2, int cap, unsigned int* gcount, unsigned int* gslot,
                                    int& accepted_io) {
     const unsigned FULL = 0xffffffffu;
@@ -254,7 +256,7 @@ static __device__ bool greedy_pass(const LaneDev& L, const unsigned* sxy, const 
         int rank = __popc(acc & lt);
         const bool mine = ((acc >> lane) & 1u) && rank < room;
         if (mine) {
-            L.kp[accepted + rank] = make_float2((float)x, (float)y);
+            kp_out[accepted + rank] = make_float2((float)x, (float)y);
             if (use_grid) {
                 unsigned slot = atomicAdd(&gcount[ci], 1u);
                 if (slot < VS_GRID_SLOTS) {
@@ -286,14 +288,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     unsigned int* sxy = sgrid + SEL_GRID_CELLS * (1 + VS_GRID_SLOTS);           // SEL_CHUNK_MAX packed (x | y << 16)
     int* scell = reinterpret_cast<int*>(sxy + SEL_CHUNK_MAX);                   // SEL_CHUNK_MAX grid cell indices
     __shared__ SelSmem S;
-    LaneDev Lm = lanes[blockIdx.z];
-    Lm.kp = Lm.kpb[kp_slot];                       // key-point generation this detection writes (engine.cu)
-    Lm.kp_count = Lm.kpc[kp_slot];
-    const LaneDev& L = Lm;
+    const LaneDev& L = lanes[blockIdx.z];
+    const DetView D = det_view(L, kp_slot);          // generation this detection reads and writes (engine.cu)
     const GrayLevel G = gftt_src(L, slot);
     const int w = G.w, h = G.h;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = min(*L.cand_count, w * h);
+    const int N = min(*D.cand_count, w * h);
     const int cap = (max_corners > 0) ? min(max_corners, L.kp_capacity) : L.kp_capacity;
     const bool use_grid = min_dist >= 1.0;
     const int cell = use_grid ? (int)rint(min_dist) : 1;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     const double md2 = min_dist * min_dist;
     const bool smem_grid = gw * gh <= SEL_GRID_CELLS;
     // grid layout: [slots: cells x 4 (16-byte aligned)] [counts: cells]
-    unsigned int* gslot = smem_grid ? sgrid : L.grid;
+    unsigned int* gslot = smem_grid ? sgrid : D.grid;
     unsigned int* gcount = gslot + (size_t)(smem_grid ? SEL_GRID_CELLS : gw * gh) * VS_GRID_SLOTS;
     const int imd2 = (int)ceil(md2);             // integer d2 < md2  <=>  d2 < ceil(md2)
     if (use_grid)
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     if (tid == 0) { S.accepted = 0; S.done = 0; }
 
     // bin = (float bits - bits(threshold)) >> shift, top bin holds the maximum
-    const float mxv = __uint_as_float(*L.eig_max);
+    const float mxv = __uint_as_float(*D.eig_max);
     const unsigned lo = __float_as_uint((float)((double)mxv * quality));
     const unsigned range = __float_as_uint(mxv) - lo;
     int shift = 0;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     for (int i0 = tid; i0 < N; i0 += 4 * SEL_THREADS) {          // four independent loads in flight per thread
         unsigned long long kk[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) kk[u] = (i0 + u * SEL_THREADS < N) ? __ldcg(L.cand + i0 + u * SEL_THREADS) : 0ull;
+        for (int u = 0; u < 4; ++u) kk[u] = (i0 + u * SEL_THREADS < N) ? __ldcg(D.cand + i0 + u * SEL_THREADS) : 0ull;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
             if (i0 + u * SEL_THREADS < N) atomicAdd(&hist[((unsigned)(kk[u] >> 32) - lo) >> shift], 1u);
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
         if (m > SEL_CHUNK_MAX) {
             // one bin overflows the sort buffer (massive ties): split it exactly by key
             m = SEL_CHUNK_MAX;
-            T = radix_select(L.cand, N, U, m, S);
+            T = radix_select(D.cand, N, U, m, S);
         }
         int npad = 32;
         while (npad < m) npad <<= 1;
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
         for (int i0 = tid; i0 < N; i0 += 4 * SEL_THREADS) {
             unsigned long long kk[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) kk[u] = (i0 + u * SEL_THREADS < N) ? __ldcg(L.cand + i0 + u * SEL_THREADS) : 0ull;
+            for (int u = 0; u < 4; ++u) kk[u] = (i0 + u * SEL_THREADS < N) ? __ldcg(D.cand + i0 + u * SEL_THREADS) : 0ull;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if (i0 + u * SEL_THREADS < N && kk[u] < U && kk[u] >= T) skeys[atomicAdd(&S.count, 1)] = kk[u];
@@ -407,8 +407,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
         __syncthreads();
         if (tid < 32) {
             int accepted = S.accepted;
-            bool stop = smem_grid ? greedy_pass<true>(L, sxy, scell, m, gw, gh, use_grid, imd2, cap, gcount, gslot, accepted)
-                                  : greedy_pass<false>(L, sxy, scell, m, gw, gh, use_grid, imd2, cap, gcount, gslot, accepted);
+            bool stop = smem_grid ? greedy_pass<true>(D.kp, sxy, scell, m, gw, gh, use_grid, imd2, cap, gcount, gslot, accepted)
+                                  : greedy_pass<false>(D.kp, sxy, scell, m, gw, gh, use_grid, imd2, cap, gcount, gslot, accepted);
             if (lane == 0) { S.accepted = accepted; S.done = stop ? 1 : 0; }
         }
         __syncthreads();
@@ -419,16 +419,16 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     }
     __syncthreads();
     const int n = S.accepted;
-    if (tid == 0) *L.kp_count = n;
+    if (tid == 0) *D.kp_count = n;
     if (slot < 0) {
-        for (int i = tid; i < n; i += SEL_THREADS) L.first_corners[i] = L.kp[i];
+        for (int i = tid; i < n; i += SEL_THREADS) L.first_corners[i] = D.kp[i];
         if (tid == 0) *L.first_count = n;
     }
     if (record_frame_no > 0) {
         if (tid == 0 && record_frame_no <= L.record_capacity) L.frec[record_frame_no - 1].n_detected = n;
         if (L.log_depth > 0) {
             float2* dst = L.log_detected + (size_t)((record_frame_no - 1) % L.log_depth) * L.kp_capacity;
-            for (int i = tid; i < n; i += SEL_THREADS) dst[i] = L.kp[i];
+            for (int i = tid; i < n; i += SEL_THREADS) dst[i] = D.kp[i];
         }
     }
 }
@@ -452,9 +452,9 @@ void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_c
         attr_set = true;
     }
     dim3 g1((w + EIG_TW - 1) / EIG_TW, (h + EIG_TH - 1) / EIG_TH, n_lanes);
-    k_min_eig<<<g1, 256, 0, st>>>(lanes, slot);
+    k_min_eig<<<g1, 256, 0, st>>>(lanes, slot, kp_slot);
     dim3 g2((w + 63) / 64, (h + 3) / 4, n_lanes);
-    k_candidates<<<g2, 256, 0, st>>>(lanes, slot, quality);
+    k_candidates<<<g2, 256, 0, st>>>(lanes, slot, quality, kp_slot);
     k_select<<<dim3(1, 1, n_lanes), SEL_THREADS, SEL_DYN_BYTES, st>>>(
         lanes, slot, max_corners, quality, min_dist, record_frame_no, kp_slot);
 }

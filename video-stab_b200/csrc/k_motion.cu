@@ -180,7 +180,7 @@ void warp_params_from_T(const float* T, WarpParams* wp) {
 
 // Smoothing + intent + matrix for the frame being emitted.  Runs on one thread (sequential float32
 // arithmetic in the reference's order); S.gk is scratch for the gaussian taps.
-static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, float* gk, Traj path, Traj trf, Traj aux) {
+static __device__ void smooth_and_setup(const LaneDev& L, WarpParams* wp_out, const StepInfo& info, float* gk, Traj path, Traj trf, Traj aux) {
     const int i = info.pop_index, n = info.path_len_at_pop;
     vs_output_record rec;
     rec.index = i; rec.passthrough = 0; rec.path_len = n; rec.radius = 0; rec.intent = 0;
@@ -191,7 +191,7 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
         rec.passthrough = 1;
         wp.passthrough = 1; wp.pad = 0;
         for (int k = 0; k < 6; ++k) { wp.m[k] = (k == 0 || k == 4) ? 1. : 0.; wp.T[k] = (k == 0 || k == 4) ? 1.f : 0.f; }
-        *L.wp = wp;
+        *wp_out = wp;
         if (info.n_out < L.record_capacity) L.orec[info.n_out] = rec;
         return;
     }
@@ -275,27 +275,25 @@ static __device__ void smooth_and_setup(const LaneDev& L, const StepInfo& info, 
     invert_affine(T, wp.m);
     for (int k = 0; k < 6; ++k) { wp.T[k] = T[k]; rec.T[k] = T[k]; }
     wp.passthrough = 0; wp.pad = 0;
-    *L.wp = wp;
+    *wp_out = wp;
     if (info.n_out < L.record_capacity) L.orec[info.n_out] = rec;
 }
 
 __global__ void __launch_bounds__(32) k_smooth_only(const LaneDev* __restrict__ lanes, StepInfo info) {
     __shared__ float gk[512];
-    LaneDev Lm = lanes[blockIdx.z];
-    Lm.wp = Lm.wpb[info.wp_slot];
-    const LaneDev& L = Lm;
-    if (threadIdx.x == 0) smooth_and_setup(L, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
+    const LaneDev& L = lanes[blockIdx.z];
+    if (threadIdx.x == 0)
+        smooth_and_setup(L, info.wp_slot ? L.wpb[1] : L.wpb[0], info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
 }
 
 __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict__ lanes, StepInfo info) {
     extern __shared__ unsigned char mo_raw[];
     MoSmem& S = *reinterpret_cast<MoSmem*>(mo_raw);
-    LaneDev Lm = lanes[blockIdx.z];
-    Lm.wp = Lm.wpb[info.wp_slot];
-    const LaneDev& L = Lm;
+    const LaneDev& L = lanes[blockIdx.z];
+    WarpParams* const wp_out = info.wp_slot ? L.wpb[1] : L.wpb[0];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
-    const int n_prev = min(min(*L.kpc[info.kp_slot], L.kp_capacity), MO_MAXP);
+    const int n_prev = min(min(*(info.kp_slot ? L.kpc[1] : L.kpc[0]), L.kp_capacity), MO_MAXP);
     const int fidx = info.frame_no - 1;
     float2* lprev = nullptr; float2* lnext = nullptr; uint8_t* lstat = nullptr; uint8_t* lmask = nullptr;
     if (L.log_depth > 0) {
@@ -317,8 +315,8 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         bool ok = false;
         float2 a = make_float2(0.f, 0.f), b = a;
         if (i < n_prev) {
-            a = L.kpb[info.kp_slot][i]; b = L.lkn[info.lk_slot][i];
-            uint8_t s = L.lks[info.lk_slot][i];
+            a = (info.kp_slot ? L.kpb[1] : L.kpb[0])[i]; b = (info.lk_slot ? L.lkn[1] : L.lkn[0])[i];
+            uint8_t s = (info.lk_slot ? L.lks[1] : L.lks[0])[i];
             ok = s != 0;
             if (lprev) { lprev[i] = a; lnext[i] = b; lstat[i] = s; }
         }
@@ -498,8 +496,8 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         __threadfence_block();
         if (info.pop_index >= 0) {
             const bool in_tail = info.pop_index - 20 >= tail_base || tail_base == 0;
-            if (in_tail) smooth_and_setup(L, info, S.gk, Traj{S.tail_path, tail_base}, Traj{S.tail_trf, tail_base}, Traj{S.tail_aux, tail_base});
-            else smooth_and_setup(L, info, S.gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
+            if (in_tail) smooth_and_setup(L, wp_out, info, S.gk, Traj{S.tail_path, tail_base}, Traj{S.tail_trf, tail_base}, Traj{S.tail_aux, tail_base});
+            else smooth_and_setup(L, wp_out, info, S.gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
         }
     }
 }
@@ -557,7 +555,7 @@ __global__ void __launch_bounds__(128) k_smooth_batch(const LaneDev* __restrict_
                 info.pop_index = i;
                 info.path_len_at_pop = min(i + gate - 1, n_tr);
                 info.n_out = max(i - first, 0);
-                smooth_and_setup(L, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
+                smooth_and_setup(L, L.wp, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
                 if (i >= first) wps[i - first] = *L.wp;
             }
         }
@@ -571,9 +569,7 @@ __global__ void __launch_bounds__(128) k_smooth_batch(const LaneDev* __restrict_
     info.path_len_at_pop = min(i + gate - 1, n_tr);
     info.n_out = k;
     // box smoothing touches no shared scratch; every thread writes its own record and warp set-up
-    LaneDev Lk = L;
-    Lk.wp = wps + k;
-    smooth_and_setup(Lk, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
+    smooth_and_setup(L, wps + k, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
 }
 
 void launch_traj_build(const LaneDev* lanes, int n_lanes, int n_tr, cudaStream_t st) {
