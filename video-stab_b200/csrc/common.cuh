@@ -10,6 +10,7 @@
 
 #define VS_PAD 16            // reflect-101 border kept around every gray pyramid level
 #define VS_WIN 15            // LK window (Stabilizer.cpp:616)
+#define VS_PYR_SLOTS 6       // pyramids kept per lane (frames n-1, n for LK + 4 frames of run-ahead)
 #define VS_LEVELS 3          // maxLevel 2 (Stabilizer.cpp:617)
 #define VS_AW 960            // analysis size (Stabilizer.cpp:410)
 #define VS_AH 540
@@ -41,7 +42,7 @@ struct WarpParams {
 
 // Per-lane device state.  An array of these lives in HBM; kernels index it with blockIdx.z.
 struct LaneDev {
-    Pyramid pyr[3];                 // analysis pyramids of frames n, n-1 and the one being built (slot = frame % 3)
+    Pyramid pyr[VS_PYR_SLOTS];      // analysis pyramids, slot = frame % VS_PYR_SLOTS: the pyramid stream can run ahead of tracking
     GrayLevel small0;               // 480x270 gray of the very first frame
     float* eig;                     // min-eigenvalue map, VS_AW*VS_AH floats
     unsigned int* eig_max;          // max(eig) as float bits (non-negative => orderable)

@@ -172,7 +172,7 @@ vs_status Engine::alloc_fixed() {
     if (n_lanes_ > 8) VS_TRY(dalloc(allocs_, &d_tmaps_, (size_t)VS_MAX_GROUP * 128));
     for (int l = 0; l < n_lanes_; ++l) {
         LaneDev& L = h_lanes_[l];
-        for (int s = 0; s < 3; ++s) {
+        for (int s = 0; s < VS_PYR_SLOTS; ++s) {
             int w = VS_AW, h = VS_AH;
             for (int k = 0; k < VS_LEVELS; ++k) {
                 VS_TRY(alloc_level(allocs_, w, h, &L.pyr[s].lv[k]));
@@ -363,7 +363,7 @@ vs_status Engine::ensure_geometry(int w, int h, bool need_ring, bool need_out, b
 StepInfo Engine::step_info(int pop_index) const {
     StepInfo s{};
     s.frame_no = n_frames_;
-    s.cur = n_frames_ % 3;
+    s.cur = n_frames_ % VS_PYR_SLOTS;
     s.pop_index = pop_index;
     s.path_len_at_pop = n_frames_;
     s.smoothing_radius = smoothing_radius_;
@@ -415,13 +415,13 @@ vs_status Engine::redetect(int cur, int frame_no, int record_frame_no) {
 //   A (tracking)  LK                               needs: pyramid(n) (evP_), key points of the last detection (evC_)
 //   B (public)    motion [-> warp, in emit()]      needs: LK of this frame (evA_)
 //   C (detection) min-eig -> candidates -> select  needs: gray of this frame (evG_)
-// Pyramids live in three slots (frame % 3), tracker output is double-buffered by frame parity and key points by
+// Pyramids live in VS_PYR_SLOTS slots (frame % 6), tracker output is double-buffered by frame parity and key points by
 // detection generation, so the pyramid (and with it the detection) of frame n+1 is built while frame n is still
 // being tracked: the detection -> tracking dependency no longer stalls the stream that feeds the detector.
 vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     if (n_frames_ + 1 >= traj_cap_) VS_TRY(grow_trajectory());
     const int frame_no = ++n_frames_;
-    const int cur = frame_no % 3, prev = (frame_no - 1) % 3;
+    const int cur = frame_no % VS_PYR_SLOTS, prev = (frame_no - 1) % VS_PYR_SLOTS;
     const int kp_slot = ((frame_no - 1) / 2) & 1, lk_slot = frame_no & 1;
     const bool detect = ((detect_counter_ + 1) % 2) == 0;                             // :696-697
     PtrPack src;
@@ -433,10 +433,10 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         launches_ += 2;
     }
     if (multi_) {
-        // slot `cur` was last read by LK(frame_no - 2) (as its previous frame) and, if frame_no - 3 re-detected,
-        // by that detection
-        if (frame_no >= 3 && evA_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sp(), evA_[(frame_no - 2) & 3], 0));
-        if (frame_no - last_detect_frame_ == 3) CUDA_TRY(cudaStreamWaitEvent(sp(), evC_[(last_detect_frame_ / 2) & 1], 0));
+        // slot `cur` was last read by LK(frame_no - VS_PYR_SLOTS + 1) (as its previous frame); the detection that read
+        // it (frame_no - VS_PYR_SLOTS, if even) finished before that LK started (it produced its key points)
+        const int last_reader = frame_no - VS_PYR_SLOTS + 1;
+        if (last_reader >= 1 && evA_set_[last_reader & 7]) CUDA_TRY(cudaStreamWaitEvent(sp(), evA_[last_reader & 7], 0));
     }
     { StageScope t(this, VS_STAGE_GRAY, sp());
       launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sp()); }       // :449-450
@@ -444,8 +444,8 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     { StageScope t(this, VS_STAGE_PYRDOWN, sp());
       launch_pyrdown(d_lanes_, n_lanes_, cur, sp()); }
     if (multi_) {
-        CUDA_TRY(cudaEventRecord(evP_[frame_no & 3], sp()));
-        CUDA_TRY(cudaStreamWaitEvent(sa(), evP_[frame_no & 3], 0));
+        CUDA_TRY(cudaEventRecord(evP_[frame_no & 7], sp()));
+        CUDA_TRY(cudaStreamWaitEvent(sa(), evP_[frame_no & 7], 0));
         // LK writes tracker slot lk_slot (last read by the motion kernel of frame_no - 2) and reads key points
         if (frame_no >= 3 && evB_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sa(), evB_[(frame_no - 2) & 3], 0));
         if (c_pending_[kp_slot]) { CUDA_TRY(cudaStreamWaitEvent(sa(), evC_[kp_slot], 0)); c_pending_[kp_slot] = false; }
@@ -454,9 +454,9 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
       launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa()); }   // :611-619
     launches_ += 3;
     if (multi_) {
-        CUDA_TRY(cudaEventRecord(evA_[frame_no & 3], sa()));
-        evA_set_[frame_no & 3] = true;
-        CUDA_TRY(cudaStreamWaitEvent(sm(), evA_[frame_no & 3], 0));
+        CUDA_TRY(cudaEventRecord(evA_[frame_no & 7], sa()));
+        evA_set_[frame_no & 7] = true;
+        CUDA_TRY(cudaStreamWaitEvent(sm(), evA_[frame_no & 7], 0));
     }
 
     const bool adaptive = p_.adaptive_smoothing != 0;
@@ -780,15 +780,15 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
         // halo: corners from the even frame m, pyramid of frame first-1
         const int m = f;
         PtrPack src; src.p[0] = entry(m).frames[0];
-        launch_gray_resize(d_lanes_, 1, src, w, h, tight, m % 3, sp());
+        launch_gray_resize(d_lanes_, 1, src, w, h, tight, m % VS_PYR_SLOTS, sp());
         if (multi_) CUDA_TRY(cudaEventRecord(evG_, sp()));
-        launch_pyrdown(d_lanes_, 1, m % 3, sp());
+        launch_pyrdown(d_lanes_, 1, m % VS_PYR_SLOTS, sp());
         launches_ += 2;
-        VS_TRY(redetect(m % 3, m, 0));
+        VS_TRY(redetect(m % VS_PYR_SLOTS, m, 0));
         if (first - 1 > m) {
             PtrPack s2; s2.p[0] = entry(first - 1).frames[0];
-            launch_gray_resize(d_lanes_, 1, s2, w, h, tight, (first - 1) % 3, sp());
-            launch_pyrdown(d_lanes_, 1, (first - 1) % 3, sp());
+            launch_gray_resize(d_lanes_, 1, s2, w, h, tight, (first - 1) % VS_PYR_SLOTS, sp());
+            launch_pyrdown(d_lanes_, 1, (first - 1) % VS_PYR_SLOTS, sp());
             launches_ += 2;
         }
         first_ = false;

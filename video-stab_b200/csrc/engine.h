@@ -98,8 +98,8 @@ private:
     cudaStream_t sM_ = nullptr;               // motion: RANSAC, trajectory, smoothing, warp set-up
     cudaStream_t sA_ = nullptr, sC_[2] = {}, sP_ = nullptr;   // tracking (LK), corner detection (two generations), pyramid build
     bool multi_ = false;
-    cudaEvent_t evA_[4] = {}, evB_[4] = {}, evP_[4] = {}, evJ_[5] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[2] = {};
-    bool evB_set_[4] = {}, evA_set_[4] = {}, evW_set_[2] = {};
+    cudaEvent_t evA_[8] = {}, evB_[4] = {}, evP_[8] = {}, evJ_[5] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[2] = {};
+    bool evB_set_[4] = {}, evA_set_[8] = {}, evW_set_[2] = {};
     int last_detect_frame_ = -100;
     bool c_pending_[2] = {};
     cudaStream_t sH_ = nullptr, sO_ = nullptr; // copy-in / copy-out streams of the pipelined host path
