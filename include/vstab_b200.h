@@ -72,8 +72,8 @@ typedef struct vs_params {
     int32_t stage_two_radius;         /* inert */
     int32_t use_temporal_filtering;   /* inert */
     int32_t temporal_window_size;     /* inert */
-    float   fade_alpha;               /* fadeAlpha — only with border_type "fade" (unsupported) */
-    int32_t fade_duration;            /* fadeDuration                                        */
+    float   fade_alpha;               /* fadeAlpha (0.1) live with border_type "fade"        */
+    int32_t fade_duration;            /* fadeDuration (30) live with border_type "fade"      */
     float   motion_threshold_low;     /* inert */
     float   motion_threshold_high;    /* inert */
     float   border_scale_factor;      /* inert */

@@ -18,8 +18,13 @@ arithmetic the reference does in `float` is done in numpy float32 scalars in the
 order; `std::cos/sin/atan2/sqrt/exp(float)` go to glibc's `cosf/sinf/atan2f/sqrtf/expf`
 through ctypes, exactly what the C++ would call on this box.
 
-Out of scope here (non-default flags): `border_type: fade`,
-`drone_high_freq_mode`, `enable_virtual_canvas`.
+`border_type: fade` (:914-978, :1070-1106) is restated too, including the reference's mask quirk (the second
+cv::rectangle paints the WHOLE mask 255, so the history is blended into and updated from the whole frame, not just
+the border band).  cv::addWeighted is the real library call with optimisations ON (its SIMD path fuses
+`src1*alpha + (src2*beta)`; the plain path differs by <= 1 LSB); the history update `(1-0.1f)*h + 0.1f*s` is
+evaluated in float32 without contraction.
+
+Out of scope here (non-default flags): `drone_high_freq_mode`, `enable_virtual_canvas`.
 
 The two process-global `static` counters of the reference (`frameTicker` :260,
 `featureDetectionCounter` :696) are per-instance here: parity is defined per stream
@@ -71,6 +76,8 @@ class Parameters:
     adaptiveSmoothing: bool = False
     minSmoothingRadius: int = 5
     maxSmoothingRadius: int = 50
+    fadeAlpha: float = 0.1
+    fadeDuration: int = 30
 
 
 _BORDER = {"reflect": 2, "reflect_101": 4, "replicate": 1, "wrap": 3}     # mapBorderMode :31-38
@@ -111,8 +118,8 @@ class StabilizerRef:
         self.border_mode = _BORDER.get(self.p.borderType, 0)
         if self.p.cropNZoom and self.p.borderType != "black":
             self.border_mode = 0
-        if self.p.borderType == "fade":
-            raise NotImplementedError("fade border: SURVEY.md §8f rank 4")
+        self.border_history = None                               # borderHistory_ / fadeFrameCount_ (:73-77): NOT reset by clean()
+        self.fade_count = 0
         self.frame_records: list[FrameRecord] = []
         self.output_records: list[OutputRecord] = []
         self.clean()
@@ -418,11 +425,36 @@ class StabilizerRef:
         T = np.array([[cosf(da), -sinf(da), dx], [sinf(da), cosf(da), dy]], f32)
         self.output_records.append(OutputRecord(idx, len(self.path), radius, intent, sm, T))
         src = frame
-        if self.p.borderSize > 0 and not self.p.cropNZoom:         # :981-990
+        fade = self.p.borderType == "fade"
+        if fade:                                                   # :914-978
+            if self.p.borderSize > 0 and not self.p.cropNZoom:
+                b = self.p.borderSize
+                if self.border_history is None:
+                    self.border_history = cv2.copyMakeBorder(frame, b, b, b, b, cv2.BORDER_CONSTANT, value=(0, 0, 0))
+                    self.fade_count = 0
+                src = cv2.copyMakeBorder(frame, b, b, b, b, cv2.BORDER_CONSTANT, value=(0, 0, 0))
+                alpha = f32(self.p.fadeAlpha)
+                if self.fade_count < self.p.fadeDuration:
+                    alpha = f32(alpha * f32(f32(self.fade_count) / f32(self.p.fadeDuration)))
+                    self.fade_count += 1
+                beta = f32(f32(1.0) - alpha)
+                if self.border_history.shape == src.shape:
+                    opt = cv2.useOptimized()
+                    cv2.setUseOptimized(True)
+                    src = cv2.addWeighted(self.border_history, float(alpha), src, float(beta), 0.0)   # mask is all 255
+                    cv2.setUseOptimized(opt)
+        elif self.p.borderSize > 0 and not self.p.cropNZoom:       # :981-990
             b = self.p.borderSize
             src = cv2.copyMakeBorder(frame, b, b, b, b, self.border_mode, value=(0, 0, 0))
         out = cv2.warpAffine(src, T, (src.shape[1], src.shape[0]), flags=cv2.INTER_LINEAR,
                              borderMode=cv2.BORDER_CONSTANT)
+        if fade and self.p.borderSize > 0:                         # :1070-1106
+            if self.border_history is not None and self.border_history.shape == out.shape:
+                h = self.border_history.astype(f32)
+                upd = (f32(f32(1.0) - f32(0.1)) * h).astype(f32) + (f32(0.1) * out.astype(f32)).astype(f32)
+                self.border_history = upd.astype(f32).astype(np.uint8)      # static_cast<uchar>: truncation
+            else:
+                self.border_history = out.copy()
         if self.p.cropNZoom and self.p.borderSize > 0:             # :1108-1124
             b = self.p.borderSize
             w, h = out.shape[1] - 2 * b, out.shape[0] - 2 * b

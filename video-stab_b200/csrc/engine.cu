@@ -68,8 +68,6 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 vs_status Engine::create(const vs_params& p, int device, int n_lanes, Engine** out) {
     *out = nullptr;
     if (n_lanes < 1 || n_lanes > VS_MAX_GROUP) return vs_set_error(VS_ERR_INVALID_ARG, "n_streams must be 1..64");
-    if (!strcmp(p.border_type, "fade"))
-        return vs_set_error(VS_ERR_UNSUPPORTED, "border_type \"fade\" is not built yet (SURVEY.md 8f rank 4)");
     if (p.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode is not built yet");
     if (p.enable_virtual_canvas) return vs_set_error(VS_ERR_UNSUPPORTED, "enable_virtual_canvas is not built yet");
     if (p.block_size != 3) return vs_set_error(VS_ERR_UNSUPPORTED, "only block_size 3 (the reference default) is supported");
@@ -146,6 +144,7 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     border_mode_ = !strcmp(p.border_type, "reflect") ? 2 : !strcmp(p.border_type, "reflect_101") ? 4
                  : !strcmp(p.border_type, "replicate") ? 1 : !strcmp(p.border_type, "wrap") ? 3 : 0;
     if (p.crop_n_zoom) border_mode_ = 0;
+    fade_ = !strcmp(p.border_type, "fade") && p.border_size > 0 && !p.crop_n_zoom;     // :914-916
     method_ = !strcmp(p.smoothing_method, "gaussian") ? 1 : !strcmp(p.smoothing_method, "kalman") ? 2 : 0;
     smoothing_radius_ = p.smoothing_radius;
     cap_first_ = p.max_corners > 0 ? (p.max_corners < MO_MAXP_HOST ? p.max_corners : MO_MAXP_HOST) : MO_MAXP_HOST;
@@ -285,6 +284,8 @@ void Engine::free_all() {
     if (d_ring_) cudaFree(d_ring_);
     if (d_out_) cudaFree(d_out_);
     if (d_scratch_) cudaFree(d_scratch_);
+    if (d_fade_) cudaFree(d_fade_);
+    d_fade_ = nullptr;
     if (d_wp_batch_) cudaFree(d_wp_batch_);
     d_wp_batch_ = nullptr; wp_batch_cap_ = 0;
     d_ring_ = d_out_ = d_scratch_ = nullptr;
@@ -351,12 +352,17 @@ vs_status Engine::ensure_geometry(int w, int h, bool need_ring, bool need_out, b
         if (d_ring_) { cudaFree(d_ring_); d_ring_ = nullptr; }
         if (d_out_) { cudaFree(d_out_); d_out_ = nullptr; }
         if (d_scratch_) { cudaFree(d_scratch_); d_scratch_ = nullptr; }
+        // borderHistory_ / fadeFrameCount_ survive clean() in the reference (Stabilizer.cpp:221-256 does not touch them):
+        // keep them unless the geometry changed
+        if (d_fade_ && (w != fade_w_ || h != fade_h_)) { cudaFree(d_fade_); d_fade_ = nullptr; fade_hist_valid_ = false; fade_count_ = 0; }
+        fade_w_ = w; fade_h_ = h;
     } else if (w != W_ || h != H_) {
         return vs_set_error(VS_ERR_INVALID_ARG, "frame size changed mid-stream (call clean() first)");
     }
     if (need_ring && !d_ring_) CUDA_TRY(cudaMalloc((void**)&d_ring_, frame_bytes_ * ring_slots_ * n_lanes_));
     if (need_out && !d_out_) CUDA_TRY(cudaMalloc((void**)&d_out_, out_bytes_ * n_lanes_ * VS_OUT_SLOTS));
     if (need_scratch && !d_scratch_) CUDA_TRY(cudaMalloc((void**)&d_scratch_, frame_bytes_ * n_lanes_));
+    if (fade_ && !d_fade_) CUDA_TRY(cudaMalloc((void**)&d_fade_, out_bytes_ * n_lanes_ * 2));     // history + blended source
     return VS_OK;
 }
 
@@ -547,10 +553,27 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         WarpGeom g{};
         g.src_w = W_; g.src_h = H_; g.src_stride = e.stride;
         g.mode = mode; g.border = b; g.border_mode = border_mode_;
+        if (fade_) {
+            // the source of the warp is the history-blended bordered frame (Stabilizer.cpp:914-978)
+            float alpha = p_.fade_alpha;
+            if (fade_count_ < p_.fade_duration) {
+                alpha = alpha * ((float)fade_count_ / p_.fade_duration);
+                ++fade_count_;
+            }
+            const float beta = 1.0f - alpha;
+            uint8_t* hist = d_fade_;
+            uint8_t* blend = d_fade_ + out_bytes_ * n_lanes_;
+            launch_fade_blend(src, n_lanes_, W_, H_, e.stride, b, hist, blend, alpha, beta, !fade_hist_valid_, stream_);
+            fade_hist_valid_ = true;
+            for (int l = 0; l < n_lanes_; ++l) src.p[l] = blend + out_bytes_ * l;
+            g.src_w = w; g.src_h = h; g.src_stride = tight;
+            g.mode = 0;
+            launches_ += 1;
+        }
         g.out_w = w; g.out_h = h; g.out_stride = dstride;
         g.d_tmaps = d_tmaps_;
         g.wp_slot = n_out_ & 1;
-        int m2 = mode;
+        int m2 = fade_ ? 0 : mode;
         if (mode == 2 && (W_ - 2 * b <= 0 || H_ - 2 * b <= 0)) m2 = 0;                // border larger than image
         g.mode = m2;
         std::vector<uint8_t*> scratch(n_lanes_);
@@ -558,6 +581,10 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         { StageScope t(this, VS_STAGE_WARP, stream_);
           launch_warp(d_lanes_, n_lanes_, src, dst, g, scratch.data(), stream_); }
         launches_ += (m2 == 2) ? 1 + n_lanes_ : 1;
+        if (fade_) {                                                                  // :1070-1106
+            launch_fade_update(d_fade_, dst, dstride, n_lanes_, W_, H_, b, stream_);
+            launches_ += 1;
+        }
     }
     if (multi_) { CUDA_TRY(cudaEventRecord(evW_[n_out_ & 1], stream_)); evW_set_[n_out_ & 1] = true; }
     if (pipe) {

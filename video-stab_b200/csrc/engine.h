@@ -129,6 +129,10 @@ private:
     uint8_t* d_ring_ = nullptr;       // [lane][slot][frame]
     uint8_t* d_out_ = nullptr;        // [lane][out frame]  (host-io staging)
     uint8_t* d_scratch_ = nullptr;    // [lane][frame]      (crop+zoom first pass)
+    uint8_t* d_fade_ = nullptr;       // border_type "fade": [lane][history] then [lane][blended source], bordered size
+    bool fade_ = false, fade_hist_valid_ = false;
+    int fade_count_ = 0;              // fadeFrameCount_
+    int fade_w_ = 0, fade_h_ = 0;
     unsigned char* d_tmaps_ = nullptr;   // tensor-map scratch for the warp kernel (batches of more than 8 lanes)
     WarpParams* d_wp_batch_ = nullptr;
     int wp_batch_cap_ = 0;

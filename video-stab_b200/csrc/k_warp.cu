@@ -765,3 +765,47 @@ void launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride,
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// border_type "fade" (Stabilizer.cpp:914-978, 1070-1106).  The reference's border mask ends up all 255 (its second
+// cv::rectangle repaints the whole mask), so the history frame is blended into, and updated from, the WHOLE bordered
+// frame.  Three byte-wise passes around the plain warp; `bordered(x, y)` is the frame with a constant-0 margin.
+//   init   : history = bordered                                   (first output only)
+//   blend  : src     = cv::addWeighted(history, alpha, bordered, 1-alpha)   (SIMD path: rint(fma(h, alpha, s*beta)))
+//   update : history = (uchar)((1.0f-0.1f)*history + 0.1f*stabilized)        (float32, truncation)
+static __device__ __forceinline__ uint8_t bordered_byte(const uint8_t* __restrict__ f, int w, int h, size_t stride, int b, int xb, int y) {
+    const int x3 = xb - 3 * b, yy = y - b;          // xb: byte column of the bordered row
+    return (x3 >= 0 && x3 < 3 * w && yy >= 0 && yy < h) ? f[(size_t)yy * stride + x3] : (uint8_t)0;
+}
+__global__ void __launch_bounds__(256) k_fade_blend(PtrPack frames, int w, int h, size_t stride, int b, uint8_t* __restrict__ hist,
+                                                     uint8_t* __restrict__ blend, size_t lane_bytes, float alpha, float beta, int init) {
+    const int bw3 = 3 * (w + 2 * b), bh = h + 2 * b;
+    const int xb = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (xb >= bw3 || y >= bh) return;
+    const size_t o = blockIdx.z * lane_bytes + (size_t)y * bw3 + xb;
+    const uint8_t s = bordered_byte(frames.p[blockIdx.z], w, h, stride, b, xb, y);
+    uint8_t hv = hist[o];
+    if (init) { hv = s; hist[o] = s; }
+    const float t = __fmaf_rn((float)hv, alpha, __fmul_rn((float)s, beta));
+    blend[o] = (uint8_t)min(max(__float2int_rn(t), 0), 255);
+}
+__global__ void __launch_bounds__(256) k_fade_update(uint8_t* __restrict__ hist, size_t lane_bytes, MutPtrPack outs, size_t out_stride,
+                                                      int bw3, int bh) {
+    const int xb = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (xb >= bw3 || y >= bh) return;
+    const size_t o = blockIdx.z * lane_bytes + (size_t)y * bw3 + xb;
+    const float hv = (float)hist[o], sv = (float)outs.p[blockIdx.z][(size_t)y * out_stride + xb];
+    const float keep = __fsub_rn(1.0f, 0.1f);
+    hist[o] = (uint8_t)(int)__fadd_rn(__fmul_rn(keep, hv), __fmul_rn(0.1f, sv));
+}
+void launch_fade_blend(const PtrPack& frames, int n_lanes, int w, int h, size_t stride, int b, uint8_t* hist, uint8_t* blend,
+                       float alpha, float beta, bool init, cudaStream_t st) {
+    const int bw3 = 3 * (w + 2 * b), bh = h + 2 * b;
+    dim3 grid((bw3 + 255) / 256, bh, n_lanes);
+    k_fade_blend<<<grid, 256, 0, st>>>(frames, w, h, stride, b, hist, blend, (size_t)bw3 * bh, alpha, beta, init ? 1 : 0);
+}
+void launch_fade_update(uint8_t* hist, const MutPtrPack& outs, size_t out_stride, int n_lanes, int w, int h, int b, cudaStream_t st) {
+    const int bw3 = 3 * (w + 2 * b), bh = h + 2 * b;
+    dim3 grid((bw3 + 255) / 256, bh, n_lanes);
+    k_fade_update<<<grid, 256, 0, st>>>(hist, (size_t)bw3 * bh, outs, out_stride, bw3, bh);
+}

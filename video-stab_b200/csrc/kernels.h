@@ -71,3 +71,8 @@ void warp_params_from_T(const float* T, WarpParams* wp);   // host: cv::warpAffi
 void launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe, uint8_t* dst,
                              size_t dstride, size_t dframe, const WarpParams* d_wp, int n_frames, int mode, int border,
                              int border_mode, uint8_t* scratch, cudaStream_t st);
+
+// border_type "fade" (Stabilizer.cpp:914-978, 1070-1106): history blend before the warp, history update after it
+void launch_fade_blend(const PtrPack& frames, int n_lanes, int w, int h, size_t stride, int b, uint8_t* hist, uint8_t* blend,
+                       float alpha, float beta, bool init, cudaStream_t st);
+void launch_fade_update(uint8_t* hist, const MutPtrPack& outs, size_t out_stride, int n_lanes, int w, int h, int b, cudaStream_t st);
