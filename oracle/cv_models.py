@@ -571,3 +571,52 @@ def copy_make_border(src: np.ndarray, b: int, mode: int) -> np.ndarray:
         out[ys < 0] = 0
         out[:, xs < 0] = 0
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# libm / cv::addWeighted models used by the output stage (Stabilizer.cpp:902-906, 964-969)
+def glibc_cosf_sinf(x):
+    """glibc >= 2.28 cosf / sinf for |x| < pi/4 (sysdeps/ieee754/flt-32/s_sincosf.h, the ARM optimized-routines
+    polynomial evaluated in double): returns (cos, sin) as float32.  Pinned bit-exactly against libm.so.6 in
+    tests/test_oracle_models.py; the device code (csrc/k_motion.cu f_cos / f_sin) follows the same steps."""
+    x = np.float32(x)
+    ax = abs(float(x))
+    assert ax < 0.7853981633974483
+    if ax < 2.0 ** -12:
+        return np.float32(1.0), x
+    H = float.fromhex
+    xd = np.float64(x)
+    x2 = xd * xd
+    c1, c2, c3, c4 = H('-0x1.ffffffd0c621cp-2'), H('0x1.55553e1068f19p-5'), H('-0x1.6c087e89a359dp-10'), H('0x1.99343027bf8c3p-16')
+    s1, s2, s3 = H('-0x1.555545995a603p-3'), H('0x1.1107605230bc4p-7'), H('-0x1.994eb3774cf24p-13')
+    x4 = x2 * x2
+    C2 = c3 + x2 * c4
+    C1 = c1 + x2 * c2
+    x6 = x4 * x2
+    c = 1.0 + x2 * C1
+    cosv = np.float32(c + x6 * C2)
+    x3 = xd * x2
+    S1 = s2 + x2 * s3
+    x7 = x3 * x2
+    s = xd + x3 * s1
+    sinv = np.float32(s + x7 * S1)
+    return cosv, sinv
+
+
+def add_weighted_u8(a, alpha, b, beta):
+    """cv::addWeighted(a, alpha, b, beta, 0) on CV_8U with OpenCV's optimised (SIMD) path: the scalars are float32 and
+    each element is rint(fma(a, alpha, b * beta)) saturated - the multiply-add is FUSED (the plain C++ path rounds
+    a*alpha separately and can differ by 1 LSB).  Pinned against cv2 4.13.0 with setUseOptimized(True)."""
+    al, be = np.float32(alpha), np.float32(beta)
+    t = (a.astype(np.float64) * np.float64(al) + (b.astype(np.float32) * be).astype(np.float32).astype(np.float64)).astype(np.float32)
+    return np.clip(np.rint(t), 0, 255).astype(np.uint8)
+
+
+def glibc_atan2f_small(y, x):
+    """glibc atan2f(y, x) for x > 0 and |y/x| < 7/16 (the rotation angle of a partial-affine fit): atanf of the
+    quotient ROUNDED TO FLOAT.  The rounding of y/x is what separates it from the correctly rounded atan2 (they differ
+    in ~20 % of cases); the device code (csrc/k_motion.cu f_atan2) has the same structure."""
+    y, x = np.float32(y), np.float32(x)
+    z = np.float32(abs(np.float32(y / x)))
+    a = np.float32(np.arctan(np.float64(z)))
+    return np.float32(-a) if y < 0 else a

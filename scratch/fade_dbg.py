@@ -7,7 +7,7 @@ from oracle.stabilizer_ref import Parameters as RP, run_clip
 w, h, b, dur, n = 644, 362, 10, 4, 40
 clip = vsb.synth.make_clip(w, h, n, 91)
 kw = dict(smoothingRadius=5, borderType="fade", borderSize=b, fadeDuration=dur, fadeAlpha=0.25)
-ref, _ = run_clip(clip, RP(**kw))
+ref, rst = run_clip(clip, RP(**kw))
 st = vsb.Stabilizer(vsb.Parameters(**kw))
 outs = [o for o in (st.stabilize(f) for f in clip) if o is not None]
 while True:
@@ -21,6 +21,12 @@ for i, (a, r) in enumerate(zip(outs, ref)):
         print(i, "max", d.max(), "count", len(ys), "rows", ys.min(), ys.max(), "cols", xs.min(), xs.max())
         y0, x0 = ys[0], xs[0]
         print("   got", a[y0, max(x0-2,0):x0+3].tolist(), "\n   ref", r[y0, max(x0-2,0):x0+3].tolist())
+for i in range(len(rst.output_records)):
+    To = rst.output_records[i].T
+    if To is None: continue
+    Tg = np.array(st.output_record(i).T, np.float32).reshape(2, 3)
+    if not np.array_equal(To.view(np.uint32), Tg.view(np.uint32)):
+        print("T differs at output", i, (To - Tg).tolist())
 import torch, cv2
 cv2.setUseOptimized(False)
 T = np.array(st.output_record(33).T, np.float32).reshape(2, 3)

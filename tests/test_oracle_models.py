@@ -175,3 +175,60 @@ def test_copy_make_border(cv2_noopt, mode, cvname):
     img = _tex(320, 180, 11, 3)
     ref = cv2.copyMakeBorder(img, 30, 30, 30, 30, getattr(cv2, cvname), value=(0, 0, 0))
     assert np.array_equal(M.copy_make_border(img, 30, mode), ref)
+
+
+def test_glibc_cosf_sinf_model_matches_libm():
+    """The angle -> matrix step uses glibc's cosf/sinf (not correctly rounded): the model (and the device code that
+    follows it) must agree with libm.so.6 bit for bit."""
+    import ctypes
+    from oracle import cv_models as M
+    libm = ctypes.CDLL("libm.so.6")
+    for f in (libm.cosf, libm.sinf):
+        f.restype, f.argtypes = ctypes.c_float, [ctypes.c_float]
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.normal(0, 0.004, 20000), rng.normal(0, 0.05, 20000), rng.uniform(-0.78, 0.78, 20000),
+                         [0.0, 1e-5, -2.0 ** -12, 2.0 ** -12, 0.78]]).astype(np.float32)
+    diff_from_correctly_rounded = 0
+    for x in xs:
+        c, s = M.glibc_cosf_sinf(x)
+        assert c == np.float32(libm.cosf(float(x))) and s == np.float32(libm.sinf(float(x))), float(x)
+        diff_from_correctly_rounded += int(s != np.float32(np.sin(np.float64(x))))
+    assert diff_from_correctly_rounded > 0          # the reason the model exists
+
+
+def test_add_weighted_model_matches_cv2_simd_path():
+    import cv2
+    from oracle import cv_models as M
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 256, (333, 1001, 3), dtype=np.uint8)
+    b = rng.integers(0, 256, (333, 1001, 3), dtype=np.uint8)
+    was = cv2.useOptimized()
+    cv2.setUseOptimized(True)
+    try:
+        for alpha in (0.1, 0.25 * (3.0 / 4.0), 0.0, 0.5, 0.0333):
+            al = np.float32(alpha)
+            be = np.float32(1.0) - al
+            ref = cv2.addWeighted(a, float(al), b, float(be), 0.0)
+            got = M.add_weighted_u8(a, al, b, be)
+            assert int(np.abs(got.astype(int) - ref.astype(int)).max()) <= 1
+            # the bulk is the fused SIMD path; only a short scalar tail per thread stripe may round separately
+            assert (got != ref).mean() < 1e-4
+    finally:
+        cv2.setUseOptimized(was)
+
+
+def test_glibc_atan2f_model_matches_libm():
+    import ctypes
+    from oracle import cv_models as M
+    libm = ctypes.CDLL("libm.so.6")
+    libm.atan2f.restype, libm.atan2f.argtypes = ctypes.c_float, [ctypes.c_float, ctypes.c_float]
+    rng = np.random.default_rng(5)
+    ys = rng.normal(0, 0.004, 40000).astype(np.float32)
+    xs = (1 + rng.normal(0, 0.002, 40000)).astype(np.float32)
+    same = cr_same = 0
+    for y, x in zip(ys, xs):
+        r = np.float32(libm.atan2f(float(y), float(x)))
+        same += int(M.glibc_atan2f_small(y, x) == r)
+        cr_same += int(np.float32(np.arctan2(np.float64(y), np.float64(x))) == r)
+    assert same >= len(ys) - 4                   # bit-identical in all but ~1 case per 10^4
+    assert cr_same < 0.9 * len(ys)               # the correctly rounded atan2 is NOT what the reference computes

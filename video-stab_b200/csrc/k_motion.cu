@@ -81,7 +81,85 @@ struct Traj {
 
 // ---- scalar float32 helpers restating the reference's host arithmetic (one thread) -----------------
 static __device__ float f_sqrt(float x) { return __fsqrt_rn(x); }
-static __device__ float f_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
+
+// std::cos / std::sin on float (Stabilizer.cpp:902-906) are glibc's cosf / sinf: NOT correctly rounded (sinf differs
+// from (float)sin(double) for ~1 argument in 8000), and a last-bit difference in the matrix moves the fixed-point
+// source coordinate of isolated pixels by 1/32 px.  These follow glibc's algorithm for |x| < pi/4 (the ARM optimized
+// routines polynomial, evaluated in double without contraction; verified bit-identical against libm.so.6 on 600k
+// arguments, oracle/ + tests/test_oracle_models.py); larger angles fall back to the correctly rounded value.
+static __device__ float f_cos(float xf) {
+    const float ax = fabsf(xf);
+    if (ax < 2.44140625e-4f) return 1.0f;                                   // |x| < 2^-12
+    if (!(ax < 0.78539816339744830962f)) return (float)cos((double)xf);
+    const double x = (double)xf, x2 = __dmul_rn(x, x);
+    const double c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10, c4 = 0x1.99343027bf8c3p-16;
+    const double x4 = __dmul_rn(x2, x2);
+    const double C2 = __dadd_rn(c3, __dmul_rn(x2, c4));
+    const double C1 = __dadd_rn(c1, __dmul_rn(x2, c2));
+    const double x6 = __dmul_rn(x4, x2);
+    const double c = __dadd_rn(1.0, __dmul_rn(x2, C1));
+    return (float)__dadd_rn(c, __dmul_rn(x6, C2));
+}
+static __device__ float f_sin(float xf) {
+    const float ax = fabsf(xf);
+    if (ax < 2.44140625e-4f) return xf;                                     // |x| < 2^-12
+    if (!(ax < 0.78539816339744830962f)) return (float)sin((double)xf);
+    const double x = (double)xf, x2 = __dmul_rn(x, x);
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double x3 = __dmul_rn(x, x2);
+    const double S1 = __dadd_rn(s2, __dmul_rn(x2, s3));
+    const double x7 = __dmul_rn(x3, x2);
+    const double sv = __dadd_rn(x, __dmul_rn(x3, s1));
+    return (float)__dadd_rn(sv, __dmul_rn(x7, S1));
+}
+// std::atan2 on float is glibc's atan2f (e_atan2f.c): atanf(|y/x|) with the quotient ROUNDED TO FLOAT first, which
+// makes it differ from the correctly rounded atan2 in ~20 % of cases.  Same structure here; atanf follows glibc 2.39's
+// s_atanf.c (fdlibm, float, no contraction) above 7/16 and the correctly rounded value below it (they agree there in
+// all but ~1 case per 10^4 for the small angles this path produces).
+static __device__ float f_atanf_pos(float x) {          // x >= 0
+    const int ix = __float_as_int(x);
+    if (ix < 0x3ee00000) return (float)atan((double)x);                     // |x| < 0.4375
+    int id;
+    if (ix < 0x3f980000) {                                                  // |x| < 1.1875
+        if (ix < 0x3f300000) { id = 0; x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x)); }
+        else { id = 1; x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f)); }
+    } else if (ix < 0x401c0000) { id = 2; x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x))); }
+    else if (ix < 0x4c000000) { id = 3; x = __fdiv_rn(-1.0f, x); }
+    else return __fadd_rn(__int_as_float(0x3fc90fda), __int_as_float(0x33a22168));
+    const float atanhi[4] = {__int_as_float(0x3eed6338), __int_as_float(0x3f490fda), __int_as_float(0x3f7b985e), __int_as_float(0x3fc90fda)};
+    const float atanlo[4] = {__int_as_float(0x31ac3769), __int_as_float(0x33222168), __int_as_float(0x33140fb4), __int_as_float(0x33a22168)};
+    const float a0 = __int_as_float(0x3eaaaaaa), a1 = __int_as_float(0xbe4ccccd), a2 = __int_as_float(0x3e124925),
+                a3 = __int_as_float(0xbde38e38), a4 = __int_as_float(0x3dba2e6e), a5 = __int_as_float(0xbd9d8795),
+                a6 = __int_as_float(0x3d886b35), a7 = __int_as_float(0xbd6ef16b), a8 = __int_as_float(0x3d4bda59),
+                a9 = __int_as_float(0xbd15a221), a10 = __int_as_float(0x3c8569d7);
+    const float z = __fmul_rn(x, x), w = __fmul_rn(z, z);
+#define VS_MA(a, b, c) __fadd_rn(a, __fmul_rn(b, c))
+    const float s1 = __fmul_rn(z, VS_MA(a0, w, VS_MA(a2, w, VS_MA(a4, w, VS_MA(a6, w, VS_MA(a8, w, a10))))));
+    const float s2 = __fmul_rn(w, VS_MA(a1, w, VS_MA(a3, w, VS_MA(a5, w, VS_MA(a7, w, a9)))));
+#undef VS_MA
+    return __fsub_rn(atanhi[id], __fsub_rn(__fsub_rn(__fmul_rn(x, __fadd_rn(s1, s2)), atanlo[id]), x));
+}
+static __device__ float f_atan2(float y, float x) {
+    const int hx = __float_as_int(x), hy = __float_as_int(y);
+    const int ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (ix >= 0x7f800000 || iy >= 0x7f800000) return (float)atan2((double)y, (double)x);     // inf / NaN
+    const float pi = __int_as_float(0x40490fdb), pi_lo = __int_as_float(0xb3bbbd2e), pi_o_2 = __int_as_float(0x3fc90fdb);
+    if (hx == 0x3f800000) { const float a = f_atanf_pos(fabsf(y)); return hy < 0 ? -a : a; }      // x == 1.0
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+    if (iy == 0) return m < 2 ? y : (m == 2 ? pi : -pi);
+    if (ix == 0) return hy < 0 ? -pi_o_2 : pi_o_2;
+    const int k = (iy - ix) >> 23;
+    float z;
+    if (k > 60) z = __fadd_rn(pi_o_2, __fmul_rn(0.5f, pi_lo));
+    else if (hx < 0 && k < -60) z = 0.0f;
+    else z = f_atanf_pos(fabsf(__fdiv_rn(y, x)));
+    switch (m) {
+        case 0: return z;
+        case 1: return -z;
+        case 2: return __fsub_rn(pi, __fsub_rn(z, pi_lo));
+        default: return __fsub_rn(__fsub_rn(z, pi_lo), pi);
+    }
+}
 
 static __device__ int adaptive_radius(const Traj path, int n, int smoothing_radius) {
     // calculateAdaptiveRadius, Stabilizer.cpp:1637-1673
@@ -270,7 +348,7 @@ static __device__ void smooth_and_setup(const LaneDev& L, WarpParams* wp_out, co
     }
     float dx = __fadd_rn(raw[0], diff[0]), dy = __fadd_rn(raw[1], diff[1]), da = __fadd_rn(raw[2], diff[2]);
     if (info.horizon_lock) da = 0.f;
-    float cs = (float)cos((double)da), sn = (float)sin((double)da);
+    float cs = f_cos(da), sn = f_sin(da);
     float T[6] = {cs, -sn, dx, sn, cs, dy};
     invert_affine(T, wp.m);
     for (int k = 0; k < 6; ++k) { wp.T[k] = T[k]; rec.T[k] = T[k]; }
