@@ -44,13 +44,11 @@ struct WarpParams {
 struct LaneDev {
     Pyramid pyr[VS_PYR_SLOTS];      // analysis pyramids, slot = frame % VS_PYR_SLOTS: the pyramid stream can run ahead of tracking
     GrayLevel small0;               // 480x270 gray of the very first frame
-    float* eig;                     // min-eigenvalue map, VS_AW*VS_AH floats
     unsigned int* eig_max;          // max(eig) as float bits (non-negative => orderable)
     unsigned long long* cand;       // corner candidates: (float bits << 32) | linear address
     int* cand_count;
     unsigned int* grid;             // min-distance grid: per cell [count, slot0..slot3]
     // second set of detection scratch (generation 1): two detections can be in flight on two streams
-    float* eig2;
     unsigned int* eig_max2;
     unsigned long long* cand2;
     int* cand_count2;
@@ -109,7 +107,6 @@ struct StepInfo {
 // Detection scratch / key-point buffers of generation `gen` (0 / 1).  Plain selects on the lane record in global
 // memory: a by-value copy of LaneDev with run-time indexed members would live on the local-memory stack.
 struct DetView {
-    float* eig;
     unsigned int* eig_max;
     unsigned long long* cand;
     int* cand_count;
@@ -119,7 +116,6 @@ struct DetView {
 };
 static __device__ __forceinline__ DetView det_view(const LaneDev& L, int gen) {
     DetView v;
-    v.eig = gen ? L.eig2 : L.eig;
     v.eig_max = gen ? L.eig_max2 : L.eig_max;
     v.cand = gen ? L.cand2 : L.cand;
     v.cand_count = gen ? L.cand_count2 : L.cand_count;

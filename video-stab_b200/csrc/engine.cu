@@ -179,12 +179,10 @@ vs_status Engine::alloc_fixed() {
             }
         }
         VS_TRY(alloc_level(allocs_, VS_FW, VS_FH, &L.small0));
-        VS_TRY(dalloc(allocs_, &L.eig, (size_t)VS_AW * VS_AH));
         VS_TRY(dalloc(allocs_, &L.cand, (size_t)VS_AW * VS_AH));
         VS_TRY(dalloc(allocs_, &L.grid, gw));
         L.eig_max = d_detect_counters_ + 2 * l;
         L.cand_count = (int*)(d_detect_counters_ + 2 * l + 1);
-        VS_TRY(dalloc(allocs_, &L.eig2, (size_t)VS_AW * VS_AH));
         VS_TRY(dalloc(allocs_, &L.cand2, (size_t)VS_AW * VS_AH));
         VS_TRY(dalloc(allocs_, &L.grid2, gw));
         L.eig_max2 = d_detect_counters_ + 2 * n_lanes_ + 2 * l;
@@ -394,7 +392,7 @@ vs_status Engine::first_frame_detect(const PtrPack& src, int w, int h, size_t st
     CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc(0)));
     launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, 0, sc(0));  // :355-357
     if (multi_) { CUDA_TRY(cudaEventRecord(evC_[0], sc(0))); c_pending_[0] = true; }
-    launches_ += 4;
+    launches_ += 3;
     return VS_OK;
 }
 
@@ -412,7 +410,7 @@ vs_status Engine::redetect(int cur, int frame_no, int record_frame_no) {
     int mc = p_.max_corners < 200 ? p_.max_corners : 200;
     launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, record_frame_no, gen, sc(gen));   // :740-744
     if (multi_) { CUDA_TRY(cudaEventRecord(evC_[gen], sc(gen))); c_pending_[gen] = true; last_detect_frame_ = frame_no; }
-    launches_ += 3;
+    launches_ += 2;
     return VS_OK;
 }
 

@@ -21,31 +21,67 @@ static __device__ __forceinline__ GrayLevel gftt_src(const LaneDev& L, int slot)
     return slot < 0 ? L.small0 : L.pyr[slot].lv[0];
 }
 
-// ------------------------------------------------------------------------------------ k_min_eig
-__global__ void __launch_bounds__(256) k_min_eig(const LaneDev* __restrict__ lanes, int slot, int gen) {
-    __shared__ float sxx[EIG_TH + 2][EIG_TW + 2];
-    __shared__ float sxy[EIG_TH + 2][EIG_TW + 2];
-    __shared__ float syy[EIG_TH + 2][EIG_TW + 2];
+// ------------------------------------------------------------------------------------ k_eig_nms
+// Sobel -> products -> 3x3 box -> min eigenvalue -> 3x3 non-max suppression -> candidate keys, one launch, the
+// eigenvalue map never leaves shared memory.  One CTA = 64x16 candidate positions; it needs eigenvalues on 66x18,
+// product maps on 68x20 and gray on 70x22 (staged with two aligned word loads per thread from the padded level).
+// The box filter's BORDER_REFLECT_101 acts on the PRODUCT maps, so a product position outside the image takes the
+// value computed AT its reflected coordinate (the cross term changes sign under reflection of the gray image, so the
+// level's gray frame cannot stand in for it).  The quality threshold needs the global maximum, which is only known
+// after this kernel: every strict-positive local maximum is emitted and k_select drops keys <= threshold
+// ("zero everything <= thr, then dilate" and "dilate, then require > thr" select the same pixels).
+#define EN_GW 72                       // staged gray row: x0-4 .. x0+67 (18 aligned words)
+#define EN_GH (EIG_TH + 6)             // y0-3 .. y0+18
+#define EN_PW (EIG_TW + 4)             // products: x0-2 .. x0+65
+#define EN_PH (EIG_TH + 4)
+#define EN_EW (EIG_TW + 2)             // eigenvalues: x0-1 .. x0+64
+#define EN_EH (EIG_TH + 2)
+
+__global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lanes, int slot, int gen) {
+    __shared__ uint32_t sgw[EN_GH][EN_GW / 4];
+    __shared__ float sxx[EN_PH][EN_PW], sxy[EN_PH][EN_PW], syy[EN_PH][EN_PW];
+    __shared__ float se[EN_EH][EN_EW];
     __shared__ unsigned int smax;
+    __shared__ int s_count, s_base;
+    __shared__ int s_warp_off[8];
     const LaneDev& L = lanes[blockIdx.z];
     const DetView D = det_view(L, gen);
     const GrayLevel G = gftt_src(L, slot);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * EIG_TW, y0 = blockIdx.y * EIG_TH;
     const float f1 = (float)(1.0 / (4.0 * 3.0 * 255.0));
     const float f0 = 2.f * f1;
-    if (threadIdx.x == 0) smax = 0u;
+    if (tid == 0) { smax = 0u; s_count = 0; }
 
-    // products at the tile + 1 halo; the box filter's BORDER_REFLECT_101 acts on the PRODUCT maps,
-    // so a halo position outside the image takes the product computed AT its reflected coordinate
-    for (int i = threadIdx.x; i < (EIG_TH + 2) * (EIG_TW + 2); i += 256) {
-        int r = i / (EIG_TW + 2), c = i - r * (EIG_TW + 2);
-        int gx = min(max(reflect101(x0 - 1 + c, G.w), 0), G.w - 1);
-        int gy = min(max(reflect101(y0 - 1 + r, G.h), 0), G.h - 1);
-        const uint8_t* p = G.base + (ptrdiff_t)gy * G.pitch + gx;
-        const uint8_t* pu = p - G.pitch;
-        const uint8_t* pd = p + G.pitch;
+    // 1. gray (rows clamped into the padded plane: rows that far out are never used)
+    {
+        constexpr int NW = EN_GH * (EN_GW / 4);
+        uint32_t v[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = min(tid + 256 * k, NW - 1);
+            const int r = i / (EN_GW / 4), cw = i - r * (EN_GW / 4);
+            const int gy = min(max(y0 - 3 + r, -VS_PAD), G.h + VS_PAD - 1);
+            v[k] = __ldg(reinterpret_cast<const uint32_t*>(G.base + (ptrdiff_t)gy * G.pitch + (x0 - 4)) + cw);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = tid + 256 * k;
+            if (i < NW) sgw[i / (EN_GW / 4)][i - (i / (EN_GW / 4)) * (EN_GW / 4)] = v[k];
+        }
+    }
+    const uint8_t (*sg)[EN_GW] = reinterpret_cast<const uint8_t (*)[EN_GW]>(&sgw[0][0]);
+    __syncthreads();
+    // 2. products at in-image positions (x = x0-2+c, y = y0-2+r); gray(x, y) = sg[r+1+dy][c+2+dx]
+    for (int i = tid; i < EN_PH * EN_PW; i += 256) {
+        const int r = i / EN_PW, c = i - r * EN_PW;
+        const int x = x0 - 2 + c, y = y0 - 2 + r;
+        if ((unsigned)x >= (unsigned)G.w || (unsigned)y >= (unsigned)G.h) continue;
+        const uint8_t* pu = &sg[r][c + 2];
+        const uint8_t* p = pu + EN_GW;
+        const uint8_t* pd = p + EN_GW;
         float a00 = pu[-1], a01 = pu[0], a02 = pu[1];
-        float a10 = p[-1], a11 = p[0], a12 = p[1];
+        float a10 = p[-1], a12 = p[1];
         float a20 = pd[-1], a21 = pd[0], a22 = pd[1];
         // Dx: row pass [-1 0 1] (exact), column pass [1 2 1]*scale as (S0+S2)*f1 + S1*f0
         float r0 = a02 - a00, r1 = a12 - a10, r2 = a22 - a20;
@@ -59,67 +95,85 @@ __global__ void __launch_bounds__(256) k_min_eig(const LaneDev* __restrict__ lan
         syy[r][c] = __fmul_rn(dy, dy);
     }
     __syncthreads();
-    unsigned int lmax = 0u;
-    for (int i = threadIdx.x; i < EIG_TH * EIG_TW; i += 256) {
-        int r = i / EIG_TW, c = i - r * EIG_TW;
-        int x = x0 + c, y = y0 + r;
-        if (x >= G.w || y >= G.h) continue;
-        double bxx = 0, bxy = 0, byy = 0;        // OpenCV's box filter sums float in double: exact here
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                bxx += (double)sxx[r + dy][c + dx];
-                bxy += (double)sxy[r + dy][c + dx];
-                byy += (double)syy[r + dy][c + dx];
+    // 2b. positions outside the image: BORDER_REFLECT_101 of the product maps (the source lies inside this tile)
+    if (x0 == 0 || y0 == 0 || x0 + EIG_TW + 2 > G.w || y0 + EIG_TH + 2 > G.h) {
+        for (int i = tid; i < EN_PH * EN_PW; i += 256) {
+            const int r = i / EN_PW, c = i - r * EN_PW;
+            const int x = x0 - 2 + c, y = y0 - 2 + r;
+            if ((unsigned)x < (unsigned)G.w && (unsigned)y < (unsigned)G.h) continue;
+            const int rc = reflect101(x, G.w) - (x0 - 2), rr = reflect101(y, G.h) - (y0 - 2);
+            if ((unsigned)rc < EN_PW && (unsigned)rr < EN_PH) {
+                sxx[r][c] = sxx[rr][rc]; sxy[r][c] = sxy[rr][rc]; syy[r][c] = syy[rr][rc];
             }
-        float a = __fmul_rn((float)bxx, 0.5f), b = (float)bxy, cc = __fmul_rn((float)byy, 0.5f);
-        float d = __fsub_rn(a, cc);
-        float e = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
-        D.eig[(size_t)y * G.w + x] = e;
-        if (e > 0.f) lmax = max(lmax, __float_as_uint(e));
+        }
+        __syncthreads();
+    }
+    // 3. eigenvalues on the tile + 1 (x = x0-1+c, y = y0-1+r); outside the image: -1 (never a maximum, never >= a candidate)
+    unsigned int lmax = 0u;
+    for (int i = tid; i < EN_EH * EN_EW; i += 256) {
+        const int r = i / EN_EW, c = i - r * EN_EW;
+        const int x = x0 - 1 + c, y = y0 - 1 + r;
+        float e = -1.f;
+        if ((unsigned)x < (unsigned)G.w && (unsigned)y < (unsigned)G.h) {
+            double bxx = 0, bxy = 0, byy = 0;        // OpenCV's box filter sums float in double: exact here
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    bxx += (double)sxx[r + dy][c + dx];
+                    bxy += (double)sxy[r + dy][c + dx];
+                    byy += (double)syy[r + dy][c + dx];
+                }
+            float a = __fmul_rn((float)bxx, 0.5f), b = (float)bxy, cc = __fmul_rn((float)byy, 0.5f);
+            float d = __fsub_rn(a, cc);
+            e = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+            if (e > 0.f) lmax = max(lmax, __float_as_uint(e));
+        }
+        se[r][c] = e;
     }
     lmax = __reduce_max_sync(0xffffffffu, lmax);
-    if ((threadIdx.x & 31) == 0 && lmax) atomicMax(&smax, lmax);
+    if (lane == 0 && lmax) atomicMax(&smax, lmax);
     __syncthreads();
-    if (threadIdx.x == 0 && smax) atomicMax(D.eig_max, smax);
-}
-
-// --------------------------------------------------------------------------------- k_candidates
-// threshold + 3x3 non-max suppression; compaction is warp-ballot -> CTA-level prefix in shared memory
-// -> one global atomic per CTA.
-__global__ void __launch_bounds__(256) k_candidates(const LaneDev* __restrict__ lanes, int slot, double quality, int gen) {
-    __shared__ int s_count, s_base;
-    __shared__ int s_warp_off[8];
-    const LaneDev& L = lanes[blockIdx.z];
-    const DetView D = det_view(L, gen);
-    const GrayLevel G = gftt_src(L, slot);
-    const int w = G.w, h = G.h;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (threadIdx.x == 0) s_count = 0;
-    const float mx = __uint_as_float(*D.eig_max);
-    const float thr = (float)((double)mx * quality);
-    bool is = false;
-    float e = 0.f;
-    if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
-        const float* p = D.eig + (size_t)y * w + x;
-        e = p[0];
-        if (e > thr) {
-            is = e >= p[-1] && e >= p[1] && e >= p[-w - 1] && e >= p[-w] && e >= p[-w + 1] &&
-                 e >= p[w - 1] && e >= p[w] && e >= p[w + 1];
+    if (tid == 0 && smax) atomicMax(D.eig_max, smax);
+    // 4. 3x3 non-max suppression on the tile (4 positions per thread), warp-ballot compaction, one global atomic per CTA
+    bool is[4];
+    float ev[4];
+    int npos = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + 256 * k;
+        const int r = i / EIG_TW, c = i - r * EIG_TW;
+        const int x = x0 + c, y = y0 + r;
+        const float e = se[r + 1][c + 1];
+        ev[k] = e;
+        is[k] = false;
+        if (x >= 1 && x < G.w - 1 && y >= 1 && y < G.h - 1 && e > 0.f) {
+            is[k] = e >= se[r + 1][c] && e >= se[r + 1][c + 2] && e >= se[r][c] && e >= se[r][c + 1] && e >= se[r][c + 2] &&
+                    e >= se[r + 2][c] && e >= se[r + 2][c + 1] && e >= se[r + 2][c + 2];
         }
+        npos += is[k] ? 1 : 0;
     }
+    // exclusive prefix of npos inside the warp, then across warps
+    int incl = npos;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31 && incl) s_warp_off[warp] = atomicAdd(&s_count, incl);
     __syncthreads();
-    const unsigned m = __ballot_sync(0xffffffffu, is);
-    if (lane == 0 && m) s_warp_off[warp] = atomicAdd(&s_count, __popc(m));
+    if (tid == 0 && s_count) s_base = atomicAdd(D.cand_count, s_count);
     __syncthreads();
-    if (threadIdx.x == 0 && s_count) s_base = atomicAdd(D.cand_count, s_count);
-    __syncthreads();
-    if (is) {
-        int pos = s_base + s_warp_off[warp] + __popc(m & ((1u << lane) - 1u));
-        D.cand[pos] = ((unsigned long long)__float_as_uint(e) << 32) | (unsigned)(y * w + x);
+    if (npos) {
+        int pos = s_base + s_warp_off[warp] + incl - npos;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (is[k]) {
+                const int i = tid + 256 * k;
+                const int r = i / EIG_TW, c = i - r * EIG_TW;
+                D.cand[pos++] = ((unsigned long long)__float_as_uint(ev[k]) << 32) | (unsigned)((y0 + r) * G.w + x0 + c);
+            }
+        }
     }
 }
 
@@ -132,7 +186,7 @@ struct SelSmem {
     unsigned long long prefix, mask, T;
     int k, count, accepted, done;
     int warp_sum[32];
-    int lo_bin, chunk_count;
+    int lo_bin, chunk_count, n_valid;
 };
 
 // K-th largest key strictly below U (keys are unique): MSD radix select, 8 bits per pass.
@@ -325,8 +379,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
 #pragma unroll
         for (int u = 0; u < 4; ++u) kk[u] = (i0 + u * SEL_THREADS < N) ? __ldcg(D.cand + i0 + u * SEL_THREADS) : 0ull;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (i0 + u * SEL_THREADS < N) atomicAdd(&hist[((unsigned)(kk[u] >> 32) - lo) >> shift], 1u);
+        for (int u = 0; u < 4; ++u)                               // keys <= threshold are not candidates (k_eig_nms emits all maxima)
+            if (i0 + u * SEL_THREADS < N && (unsigned)(kk[u] >> 32) > lo) atomicAdd(&hist[((unsigned)(kk[u] >> 32) - lo) >> shift], 1u);
     }
     __syncthreads();
     // suffix scan (from the top bin down): thread r owns bins 4095-4r .. 4092-4r
@@ -353,12 +407,15 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     }
     __syncthreads();
     const int before = S.warp_sum[warp] + incl - local;    // candidates in bins above this thread's four
+    if (tid == SEL_THREADS - 1) S.n_valid = before + local;  // all keys above the quality threshold
+    __syncthreads();
+    const int Nv = S.n_valid;
 
     int taken = 0;               // candidates already handed to the greedy pass (exactly those with key >= U)
     unsigned long long U = ~0ull;
     bool first = true;
-    while (taken < N) {
-        const int target = min(first ? SEL_CHUNK_FIRST : SEL_CHUNK_MAX / 2, N - taken);
+    while (taken < Nv) {
+        const int target = min(first ? SEL_CHUNK_FIRST : SEL_CHUNK_MAX / 2, Nv - taken);
         first = false;
         // lowest bin such that the not-yet-taken candidates in bins >= lo_bin number >= target
         {
@@ -394,7 +451,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
             for (int u = 0; u < 4; ++u) kk[u] = (i0 + u * SEL_THREADS < N) ? __ldcg(D.cand + i0 + u * SEL_THREADS) : 0ull;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (i0 + u * SEL_THREADS < N && kk[u] < U && kk[u] >= T) skeys[atomicAdd(&S.count, 1)] = kk[u];
+                if (i0 + u * SEL_THREADS < N && kk[u] < U && kk[u] >= T && (unsigned)(kk[u] >> 32) > lo)
+                    skeys[atomicAdd(&S.count, 1)] = kk[u];
         }
         __syncthreads();
         bitonic_sort_desc(skeys, npad);
@@ -452,9 +510,7 @@ void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_c
         attr_set = true;
     }
     dim3 g1((w + EIG_TW - 1) / EIG_TW, (h + EIG_TH - 1) / EIG_TH, n_lanes);
-    k_min_eig<<<g1, 256, 0, st>>>(lanes, slot, kp_slot);
-    dim3 g2((w + 63) / 64, (h + 3) / 4, n_lanes);
-    k_candidates<<<g2, 256, 0, st>>>(lanes, slot, quality, kp_slot);
+    k_eig_nms<<<g1, 256, 0, st>>>(lanes, slot, kp_slot);
     k_select<<<dim3(1, 1, n_lanes), SEL_THREADS, SEL_DYN_BYTES, st>>>(
         lanes, slot, max_corners, quality, min_dist, record_frame_no, kp_slot);
 }
