@@ -9,7 +9,9 @@
 // Specification: oracle/cv_models.py estimate_affine_partial_2d + oracle/stabilizer_ref.py.
 #include "kernels.h"
 
-#define MO_THREADS 1024
+#define MO_THREADS 256                 // 8 warps: a 1024-thread CTA claims a whole SM (register file), which delays its
+                                       // start while other streams' kernels occupy the SMs; the first RANSAC round has
+                                       // 8 hypotheses (one per warp) and usually is the only one
 #define MO_MAXP 2048                 // key-point capacity handled in shared memory
 #define MO_BATCH 32                  // hypotheses per round
 #define MO_TAIL 128                  // trajectory entries staged in shared memory for the sequential part
@@ -435,10 +437,10 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
             S.rng = r;
         }
         __syncthreads();
-        if (warp < batch) {
+        for (int hyp = warp; hyp < batch; hyp += MO_THREADS / 32) {
             double M[6];
             float F[6];
-            int i0 = S.idx[warp][0], i1 = S.idx[warp][1];
+            int i0 = S.idx[hyp][0], i1 = S.idx[hyp][1];
             model_from_pair(S.from[i0], S.from[i1], S.to[i0], S.to[i1], M);
 #pragma unroll
             for (int k = 0; k < 6; ++k) F[k] = (float)M[k];
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
                 bool in = i < n && is_inlier(F, S.from[i], S.to[i]);
                 cnt += __popc(__ballot_sync(FULL, in));
             }
-            if (lane == 0) S.good[warp] = cnt;
+            if (lane == 0) S.good[hyp] = cnt;
         }
         __syncthreads();
         if (tid == 0) {
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         __syncthreads();
         if (warp == 0) {
             for (int k = 0; k < nvals; ++k) {
-                double v = S.red[k][lane];
+                double v = lane < MO_THREADS / 32 ? S.red[k][lane] : 0.;
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
                 if (lane == 0) S.red[k][0] = v;
             }
