@@ -1,7 +1,7 @@
 import os, sys, time
 if len(sys.argv) > 1: os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] = sys.argv[1]
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import __graft_entry__; __graft_entry__.build()
 import video_stab_b200 as vsb
 W, H, n = 1920, 1080, 64

@@ -1,6 +1,6 @@
 """Extract one function's SASS from the built library: python scratch/sass_fn.py <substr> [start end]"""
-import re, subprocess, sys
-txt = subprocess.run(["cuobjdump", "-sass", "video-stab_b200/libvstab_b200.so"], capture_output=True, text=True).stdout
+import os, re, subprocess, sys
+txt = subprocess.run(["cuobjdump", "-sass", os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "video-stab_b200", "libvstab_b200.so")], capture_output=True, text=True).stdout
 i = txt.index("Function : " + [m for m in re.findall(r"Function : (\S+)", txt) if sys.argv[1] in m][0])
 j = txt.find("Function :", i + 10)
 body = txt[i:j if j > 0 else None]

@@ -202,26 +202,6 @@ void launch_upsample_small(const LaneDev* lanes, int n_lanes, int slot, cudaStre
 // ---------------------------------------------------------------- cv::pyrDown
 // out(x,y) = (sum_{i,j} k_i k_j src(2x+i-2, 2y+j-2) + 128) >> 8, k = [1 4 6 4 1]; the source level's
 // materialised reflect-101 frame supplies the out-of-image taps.  Padded output domain again.
-__global__ void __launch_bounds__(128) k_pyrdown(const LaneDev* __restrict__ lanes, int slot, int level) {
-    const LaneDev& L = lanes[blockIdx.z];
-    const GrayLevel s = L.pyr[slot].lv[level - 1];
-    const GrayLevel d = L.pyr[slot].lv[level];
-    int px = blockIdx.x * blockDim.x + threadIdx.x - VS_PAD;
-    int py = blockIdx.y - VS_PAD;
-    if (px >= d.w + VS_PAD) return;
-    int ox = reflect101(px, d.w), oy = reflect101(py, d.h);
-    const uint8_t* c = s.base + (ptrdiff_t)(2 * oy) * s.pitch + 2 * ox;
-    int acc = 0;
-#pragma unroll
-    for (int j = -2; j <= 2; ++j) {
-        const uint8_t* r = c + (ptrdiff_t)j * s.pitch;
-        int row = r[-2] + 4 * r[-1] + 6 * r[0] + 4 * r[1] + r[2];
-        const int kj = (j == 0) ? 6 : ((j == -1 || j == 1) ? 4 : 1);
-        acc += kj * row;
-    }
-    d.base[(ptrdiff_t)py * d.pitch + px] = (uint8_t)((acc + 128) >> 8);
-}
-
 // Both pyrDown levels in one launch.  One CTA = one 16x16 tile of level 2; it needs a 36x36 region of level 1
 // (recomputed per CTA, 27 % redundancy) and that a 76x76 region of level 0, read once from the padded level-0
 // plane into shared memory.  Both passes are separable ([1 4 6 4 1] rows then columns, exact integers).  The CTA

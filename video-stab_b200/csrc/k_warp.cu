@@ -601,16 +601,6 @@ __global__ void __launch_bounds__(256) k_warp_lanes(const LaneDev* __restrict__ 
     warp_pixel<BORDER>(src.p[blockIdx.z], g.src_w, g.src_h, g.src_stride, wp->m, g.border, g.border_mode, x, y, o);
 }
 
-__global__ void __launch_bounds__(256) k_warp_frames(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride, size_t sframe,
-                                                      uint8_t* __restrict__ dst, int dw, int dh, size_t dstride, size_t dframe,
-                                                      const WarpParams* __restrict__ wps) {
-    int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= dw || y >= dh) return;
-    uint8_t* o = dst + blockIdx.z * dframe + (size_t)y * dstride + 3 * x;
-    warp_pixel<false>(src + blockIdx.z * sframe, sw, sh, sstride, wps[blockIdx.z].m, 0, 0, x, y, o);
-}
-
 // ---- host side of the TMA path ------------------------------------------------------------------------
 typedef CUresult (*TmaEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
