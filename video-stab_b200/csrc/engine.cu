@@ -584,10 +584,14 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
             launches_ += 1;
         }
     }
-    if (multi_) { CUDA_TRY(cudaEventRecord(evW_[n_out_ & 1], stream_)); evW_set_[n_out_ & 1] = true; }
+    if (multi_) {
+        CUDA_TRY(cudaEventRecord(evW_[n_out_ & 1], stream_)); evW_set_[n_out_ & 1] = true;
+        if (e.in_ring) {
+            CUDA_TRY(cudaEventRecord(evRing_[e.slot], stream_));        // the ring slot of this frame may be refilled
+            ring_ev_set_[e.slot] = true;
+        }
+    }
     if (pipe) {
-        CUDA_TRY(cudaEventRecord(evRing_[e.slot], stream_));            // the ring slot of this frame may be refilled
-        ring_ev_set_[e.slot] = true;
         CUDA_TRY(cudaEventRecord(evOutReady_[oslot], stream_));
         CUDA_TRY(cudaStreamWaitEvent(sO_, evOutReady_[oslot], 0));
         for (int l = 0; l < n_lanes_; ++l)
@@ -630,8 +634,9 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
     } else {
         const size_t tight = (size_t)w * 3;
         // pipelined host I/O: copy in on the copy-in stream, after the warp that last read this ring slot
+        // the ring slot is refilled only after the warp that last read it (another stream) has finished
         cudaStream_t cs = pipe ? sH_ : sp();
-        if (pipe && ring_ev_set_[e.slot]) CUDA_TRY(cudaStreamWaitEvent(sH_, evRing_[e.slot], 0));
+        if (multi_ && ring_ev_set_[e.slot]) CUDA_TRY(cudaStreamWaitEvent(cs, evRing_[e.slot], 0));
         for (int l = 0; l < n_lanes_; ++l) {
             uint8_t* dst = d_ring_ + ((size_t)l * ring_slots_ + e.slot) * frame_bytes_;
             CUDA_TRY(cudaMemcpy2DAsync(dst, tight, frames[l], stride, tight, h,
@@ -639,6 +644,7 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
             e.frames[l] = dst;
         }
         e.stride = tight;
+        e.in_ring = true;
         if (pipe) {
             cudaEvent_t ev = evH_[h_seq_++ & 7];
             CUDA_TRY(cudaEventRecord(ev, sH_));

@@ -16,6 +16,7 @@ enum { VS_STAGE_GRAY = 0, VS_STAGE_PYRDOWN, VS_STAGE_LK, VS_STAGE_MOTION, VS_STA
 struct QueueEntry {
     int index;                               // frameIndexQueue_
     int slot;                                // ring slot (copy mode)
+    bool in_ring = false;                    // the frame lives in the device ring (not borrowed)
     std::vector<const uint8_t*> frames;      // per-lane device pointer of the queued frame
     size_t stride;
 };
