@@ -322,6 +322,25 @@ def run_gpu(args, rank, world, local_rank):
     peak, peak_src = _peaks()
     achieved = alg_bytes / (warp_ms * 1e-3) / 1e9
 
+    # ---- pyramid build (north-star kernel 1): gray + both pyrDown levels of 64 frames in one lock-step launch pair,
+    #      timed alone.  Algorithmic bytes per frame: 3*W*H read + 960*540*(1 + 1/4 + 1/16) written = 6 901 200.
+    sb = vsb.StabilizerBatch(params, FRAMES_PER_STEP, device=local_rank)
+    sb_ext = torch.cuda.ExternalStream(sb.stream, device=dev)
+    ptrs = [clip_d[i].data_ptr() for i in range(FRAMES_PER_STEP)]
+    for _ in range(3):
+        sb.build_pyramids(ptrs, W, H, W * 3)
+    sb.sync()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(sb_ext)
+    for _ in range(reps):
+        sb.build_pyramids(ptrs, W, H, W * 3)
+    p1.record(sb_ext)
+    sb.sync()
+    pyr_ms = p0.elapsed_time(p1) / reps
+    pyr_bytes = (3 * W * H + 960 * 540 + 480 * 270 + 240 * 135) * FRAMES_PER_STEP
+    pyr_gbs = pyr_bytes / (pyr_ms * 1e-3) / 1e9
+    del sb
+
     # max over ranks
     t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -355,6 +374,10 @@ def run_gpu(args, rank, world, local_rank):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "ms_per_launch": warp_ms, "frac_of_nominal_8000": achieved / 8000.0},
+            "roofline_pyramid": {"bound": "hbm", "kernel": "k_gray_half + k_pyrdown2 (resize + gray + 2 pyrDown levels, 64 frames "
+                                                           "per launch pair, timed alone)",
+                                 "achieved": pyr_gbs, "peak": peak, "unit": "GB/s", "frac": pyr_gbs / peak,
+                                 "algorithmic_bytes_per_launch": pyr_bytes, "ms_per_launch": pyr_ms},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()

@@ -240,6 +240,9 @@ void*     vs_batch_stream(vs_batch* b);
 vs_status vs_batch_launch_count(vs_batch* b, uint64_t* n);
 vs_status vs_batch_set_timing(vs_batch* b, int enable);
 vs_status vs_batch_stage_time(vs_batch* b, int stage, double* total_ms, long long* count);
+/* cv::resize + cvtColor + both pyrDown levels (Stabilizer.cpp:449-450, the pyramid of :611) for every stream of the
+ * batch, nothing else: the analysis-image build timed alone (pyramid roofline in bench.py). */
+vs_status vs_batch_build_pyramids(vs_batch* b, const uint8_t* const* d_frames, int width, int height, size_t stride);
 vs_status vs_batch_stream_counts(vs_batch* b, int stream, int* n_frame_records, int* n_output_records);
 vs_status vs_batch_frame_record(vs_batch* b, int stream, int i, vs_frame_record* rec);
 vs_status vs_batch_output_record(vs_batch* b, int stream, int i, vs_output_record* rec);

@@ -356,6 +356,11 @@ class StabilizerBatch:
         check(lib.vs_batch_flush_device(self._h, oa, out_stride, out_capacity, C.byref(ow), C.byref(oh), C.byref(produced)))
         return (ow.value, oh.value) if produced.value else None
 
+    def build_pyramids(self, d_frames, w, h, stride):
+        """Analysis-image build alone (gray + pyramid) for every stream: profiling / roofline."""
+        fa = (C.c_void_p * self.n)(*d_frames)
+        check(lib.vs_batch_build_pyramids(self._h, fa, w, h, stride))
+
     def sync(self):
         check(lib.vs_batch_sync(self._h))
 
