@@ -24,7 +24,13 @@ the border band).  cv::addWeighted is the real library call with optimisations O
 `src1*alpha + (src2*beta)`; the plain path differs by <= 1 LSB); the history update `(1-0.1f)*h + 0.1f*s` is
 evaluated in float32 without contraction.
 
-Out of scope here (non-default flags): `drone_high_freq_mode`, `enable_virtual_canvas`.
+`drone_high_freq_mode` (:2447-2686) is restated for the case its analysis size comes out as 960x540 (the default
+`hfAnalysisMaxWidth` = 960 on any 16:9 frame): dead-zone freeze, micro-shake suppression, rotation low-pass (only with
+`horizonLock`), the 10-sample translation history, and the [10,50] box-radius clamp.  Conditional CLAHE never fires in
+the reference (both call sites pass -1 to shouldApplyConditionalCLAHE, which then always returns false).  The HF state is
+set in the constructor only; clean() does not reset it.
+
+Out of scope here (non-default flags): `enable_virtual_canvas`.
 
 The two process-global `static` counters of the reference (`frameTicker` :260,
 `featureDetectionCounter` :696) are per-instance here: parity is defined per stream
@@ -78,6 +84,14 @@ class Parameters:
     maxSmoothingRadius: int = 50
     fadeAlpha: float = 0.1
     fadeDuration: int = 30
+    droneHighFreqMode: bool = False
+    hfShakePx: float = 1.5
+    hfAnalysisMaxWidth: int = 960
+    hfRotLPAlpha: float = 0.2
+    enableConditionalCLAHE: bool = True
+    hfDeadZoneThreshold: float = 2.0
+    hfFreezeDuration: int = 10
+    hfMotionAccumulatorDecay: float = 0.9
 
 
 _BORDER = {"reflect": 2, "reflect_101": 4, "replicate": 1, "wrap": 3}     # mapBorderMode :31-38
@@ -120,6 +134,13 @@ class StabilizerRef:
             self.border_mode = 0
         self.border_history = None                               # borderHistory_ / fadeFrameCount_ (:73-77): NOT reset by clean()
         self.fade_count = 0
+        # drone high-frequency state (:143-153), constructor only
+        self.hf_hist: list = []
+        self.hf_median = np.zeros(2, f32)
+        self.hf_rot_lp = f32(0)
+        self.hf_in_dead_zone = False
+        self.hf_freeze_counter = 0
+        self.hf_accumulator = f32(0)
         self.frame_records: list[FrameRecord] = []
         self.output_records: list[OutputRecord] = []
         self.clean()
@@ -202,6 +223,8 @@ class StabilizerRef:
             dx, dy = t[0, 2], t[1, 2]
             da = atan2f(t[1, 0], t[0, 0])
             tr = np.array([dx, dy, da], f32)
+            if self.p.droneHighFreqMode:                           # :666-671
+                tr = self._hf_filters(tr)
         else:
             tr = np.zeros(3, f32)                                  # :675-677
         self.transforms.append(tr)
@@ -218,6 +241,56 @@ class StabilizerRef:
         self.frame_records.append(FrameRecord(len(self.transforms), rec_prev, nxt, status, mask, affine,
                                               tr, self.path[-1].copy(), detected))
 
+    # --------------------------------------------------------- :2468-2686 (drone high-frequency chain)
+    def _hf_filters(self, raw):
+        p = self.p
+        dx, dy, da = f32(raw[0]), f32(raw[1]), f32(raw[2])
+        thr = f32(p.hfDeadZoneThreshold)
+        # applyDeadZoneFreeze :2605-2655 (updateMotionAccumulator :2668-2681 first)
+        mag = sqrtf(f32(f32(dx * dx) + f32(dy * dy)) + f32(f32(da * da) * f32(100.0)))
+        acc = max(f32(self.hf_accumulator * f32(p.hfMotionAccumulatorDecay)), mag)
+        acc = min(acc, f32(thr * f32(5.0)))
+        acc = max(f32(0), min(acc, f32(100.0)))
+        self.hf_accumulator = f32(acc)
+        out = np.array([dx, dy, da], f32)
+        if not self.hf_in_dead_zone and mag < thr:
+            self.hf_in_dead_zone = True
+            self.hf_freeze_counter = p.hfFreezeDuration
+        if self.hf_in_dead_zone:
+            self.hf_freeze_counter -= 1
+            if (self.hf_freeze_counter <= 0 or mag > f32(thr * f32(1.5)) or self.hf_accumulator > f32(thr * f32(1.2))):
+                self.hf_in_dead_zone = False
+                self.hf_freeze_counter = 0
+                self.hf_accumulator = f32(0)
+            else:
+                out = np.zeros(3, f32)
+        # applyMicroShakeSuppression :2468-2503
+        if len(self.hf_hist) >= 5:
+            xs = sorted(f32(t[0]) for t in self.hf_hist)
+            ys = sorted(f32(t[1]) for t in self.hf_hist)
+            mid = len(xs) // 2
+            if len(xs) % 2 == 0:
+                self.hf_median = np.array([f32(f32(xs[mid - 1] + xs[mid]) / f32(2)), f32(f32(ys[mid - 1] + ys[mid]) / f32(2))], f32)
+            else:
+                self.hf_median = np.array([xs[mid], ys[mid]], f32)
+        dev = (out[:2] - self.hf_median).astype(f32)
+        m2 = sqrtf(f32(f32(dev[0] * dev[0]) + f32(dev[1] * dev[1])))
+        shake = f32(p.hfShakePx)
+        if m2 < shake:
+            out[:2] = (self.hf_median + (dev * f32(0.01)).astype(f32)).astype(f32)
+        elif m2 < f32(shake * f32(2.0)):
+            out[:2] = (self.hf_median + (dev * f32(0.05)).astype(f32)).astype(f32)
+        # applyRotationLowPass :2505-2520
+        if p.horizonLock:
+            a = f32(p.hfRotLPAlpha)
+            self.hf_rot_lp = f32(f32(f32(f32(1.0) - a) * self.hf_rot_lp) + f32(a * out[2]))
+            out[2] = self.hf_rot_lp
+        # updateTranslationHistory :2522-2529
+        self.hf_hist.append(out[:2].copy())
+        if len(self.hf_hist) > 10:
+            self.hf_hist.pop(0)
+        return out
+
     # --------------------------------------------------------- :1461-1492,1562-1574
     def _update_adaptive(self):
         if len(self.transforms) < 3:
@@ -232,8 +305,8 @@ class StabilizerRef:
 
     # --------------------------------------------------------------- :1139-1172
     @staticmethod
-    def _box(path: np.ndarray, radius: int) -> np.ndarray:
-        r = max(2, min(radius, 8))
+    def _box(path: np.ndarray, radius: int, drone: bool = False) -> np.ndarray:
+        r = max(10, min(radius, 50)) if drone else max(2, min(radius, 8))
         n = len(path)
         if n <= r:
             return path.copy()
@@ -247,9 +320,9 @@ class StabilizerRef:
         return out
 
     @staticmethod
-    def box_at(path: np.ndarray, radius: int, i: int) -> np.float32:
+    def box_at(path: np.ndarray, radius: int, i: int, drone: bool = False) -> np.float32:
         """smoothed[i] only (what the reference actually consumes)."""
-        r = max(2, min(radius, 8))
+        r = max(10, min(radius, 50)) if drone else max(2, min(radius, 8))
         n = len(path)
         if n <= r:
             return path[i]
@@ -404,7 +477,7 @@ class StabilizerRef:
             sm = np.array([self._kalman(c)[idx] for c in (px, py, pa)], f32)
         if sm is None:
             radius = self._adaptive_radius(px, py, pa)
-            sm = np.array([self.box_at(c, radius, idx) for c in (px, py, pa)], f32)
+            sm = np.array([self.box_at(c, radius, idx, self.p.droneHighFreqMode) for c in (px, py, pa)], f32)
         raw = self.transforms[idx]
         diff = (sm - arr[idx]).astype(f32)
         intent = INTENT_NORMAL

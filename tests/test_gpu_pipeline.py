@@ -260,6 +260,67 @@ def test_fade_border_vs_live_oracle(vsb, w, h, b, dur):
     assert len(again) > 0 and not np.array_equal(again[0], outs[0])
 
 
+def _calm_clip(vsb, w, h, n, seed):
+    """A hovering-drone clip: sub-pixel to few-pixel vibration with calm stretches, so that every branch of the
+    high-frequency chain (dead-zone entry / timed exit / motion exit, 1 % and 5 % shake residuals, median) runs."""
+    rng = np.random.default_rng(seed)
+    base = vsb.synth.base_texture(w, h, seed)
+    amp = np.where((np.arange(n) // 12) % 2 == 0, 0.4, 2.5)
+    poses = np.stack([np.cumsum(rng.normal(0, 0.15, n)) + rng.normal(0, 1, n) * amp,
+                      np.cumsum(rng.normal(0, 0.15, n)) + rng.normal(0, 1, n) * amp,
+                      rng.normal(0, 0.002, n)], axis=1)
+    return np.stack([vsb.synth.render_frame(base, poses[k], w, h) for k in range(n)])
+
+
+@pytest.mark.parametrize("case", ["shaky", "calm", "calm_lock"])
+def test_drone_high_freq_mode_vs_live_oracle(vsb, cv2_noopt, case):
+    """drone_high_freq_mode (Stabilizer.cpp:666-671, 2468-2529, 2605-2681, box radius clamp :1144-1146) at the
+    960x540 analysis size: filtered transforms equal to the oracle's float for float, frames within 1 LSB."""
+    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    n = 60
+    if case == "shaky":
+        clip = vsb.synth.make_clip(1280, 720, n, 17)
+        kw = dict(smoothingRadius=12, droneHighFreqMode=True)
+    else:
+        clip = _calm_clip(vsb, 1280, 720, n, 23)
+        kw = dict(smoothingRadius=30, droneHighFreqMode=True, hfFreezeDuration=4, horizonLock=(case == "calm_lock"))
+    ref_outs, ref = run_clip(clip, RP(**kw))
+    plain_outs, plain = run_clip(clip[:20], RP(**{**kw, "droneHighFreqMode": False}), flush=False)
+    outs, st = _run(vsb, clip, vsb.Parameters(**kw))
+    assert len(outs) == len(ref_outs) == n
+    nf, no = st.counts()
+    assert nf == len(ref.frame_records)
+    changed = 0
+    for i, fr in enumerate(ref.frame_records):
+        rec = st.frame_record(i)
+        d = np.abs(np.asarray(rec.transform, np.float32) - fr.transform)
+        assert d[0] < 1e-3 and d[1] < 1e-3 and d[2] * HALF_DIAG < 1e-3, f"frame {i}: {rec.transform} vs {fr.transform}"
+        if i < len(plain.frame_records):
+            changed += int(not np.array_equal(fr.transform, plain.frame_records[i].transform))
+    assert changed > 0, "the clip never exercised the high-frequency filters"
+    for k, orec in enumerate(ref.output_records):
+        r = st.output_record(k)
+        assert r.index == orec.index and bool(r.passthrough) == (orec.T is None)
+        if not r.passthrough:
+            assert r.radius == orec.radius and r.intent == orec.intent
+    band = 40
+    for k, (a, b) in enumerate(zip(outs, ref_outs)):
+        assert a.shape == b.shape
+        d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+        assert d[band:-band, band:-band].max() <= 1, f"output {k}: {d[band:-band, band:-band].max()} LSB"
+        assert d.max() <= 12 and (d > 1).mean() < 1e-3
+
+
+def test_drone_mode_other_analysis_sizes_are_refused(vsb):
+    st = vsb.Stabilizer(vsb.Parameters(droneHighFreqMode=True))
+    with pytest.raises(vsb.VsError) as ei:
+        st.stabilize(np.zeros((480, 640, 3), np.uint8))           # 4:3 -> 640x480 analysis size in the reference
+    assert ei.value.status == 7
+    st2 = vsb.Stabilizer(vsb.Parameters(droneHighFreqMode=True, hfAnalysisMaxWidth=1280))
+    with pytest.raises(vsb.VsError):
+        st2.stabilize(np.zeros((1080, 1920, 3), np.uint8))
+
+
 @pytest.mark.parametrize("borrow", [True, False])
 def test_async_device_pipeline_is_deterministic(vsb, borrow):
     """The asynchronous device-pointer path keeps five streams busy (pyramid of frame n+1 while frame n is tracked,

@@ -232,3 +232,38 @@ def test_glibc_atan2f_model_matches_libm():
         cr_same += int(np.float32(np.arctan2(np.float64(y), np.float64(x))) == r)
     assert same >= len(ys) - 4                   # bit-identical in all but ~1 case per 10^4
     assert cr_same < 0.9 * len(ys)               # the correctly rounded atan2 is NOT what the reference computes
+
+
+def test_drone_high_freq_chain_known_answers():
+    """Hand-traced walk through applyDeadZoneFreeze / applyMicroShakeSuppression / updateTranslationHistory
+    (Stabilizer.cpp:2468-2529, 2605-2681) with the default thresholds (2.0 px, 10 frames, 0.9 decay, 1.5 px)."""
+    from oracle.stabilizer_ref import Parameters, StabilizerRef
+    f32 = np.float32
+    st = StabilizerRef(Parameters(droneHighFreqMode=True))
+    # 0.5 px: enters the dead zone at once, frozen to zero
+    assert np.array_equal(st._hf_filters(np.array([0.5, 0, 0], f32)), np.zeros(3, f32))
+    assert st.hf_in_dead_zone and st.hf_freeze_counter == 9
+    # 5 px > 1.5 x threshold: leaves the dead zone, accumulator reset, raw motion returned (history too short for a median)
+    assert np.array_equal(st._hf_filters(np.array([5, 0, 0], f32)), np.array([5, 0, 0], f32))
+    assert not st.hf_in_dead_zone and st.hf_accumulator == 0
+    # 2.5 px: outside the dead zone, between shake and 2 x shake of the (zero) median -> 5 % residual
+    out = st._hf_filters(np.array([2.5, 0, 0], f32))
+    assert out[0] == f32(2.5) * f32(0.05) and out[1] == 0
+    assert len(st.hf_hist) == 3
+
+    st = StabilizerRef(Parameters(droneHighFreqMode=True))
+    outs = [st._hf_filters(np.array([0.5, 0.25, 0.001], f32)) for _ in range(11)]
+    assert all(np.array_equal(o, np.zeros(3, f32)) for o in outs[:9])
+    # 10th call: freeze duration over -> raw motion, pulled to 1 % of its distance from the median (0 after nine zeros)
+    assert outs[9][0] == f32(0.5) * f32(0.01) and outs[9][1] == f32(0.25) * f32(0.01) and outs[9][2] == f32(0.001)
+    # 11th call: still calm -> frozen again
+    assert np.array_equal(outs[10], np.zeros(3, f32)) and st.hf_in_dead_zone
+    assert len(st.hf_hist) == 10
+    # rotation low-pass only with horizonLock
+    st = StabilizerRef(Parameters(droneHighFreqMode=True, horizonLock=True))
+    o = st._hf_filters(np.array([9, 9, 0.01], f32))
+    assert o[2] == f32(f32(0.2) * f32(0.01))
+    # box radius clamp [10, 50] in drone mode
+    p = np.arange(40, dtype=f32)
+    assert StabilizerRef.box_at(p, 30, 20, True) == f32(19.5) and StabilizerRef.box_at(p, 3, 0, True) == f32(5)
+    assert StabilizerRef.box_at(p, 3, 0, False) == f32(1.5)

@@ -68,6 +68,7 @@ struct LaneDev {
     float* path;                    // 3 floats per frame  (path_)
     float* aux;                     // 2 floats per frame: |t| and atan2(ty,tx) of each transform (motion-intent terms)
     float* kalman;                  // 3 x {x0,x1,P00,P01,P10,P11} incremental Kalman state
+    float* hf;                      // drone high-frequency state (VS_HF_* slots), set at creation only
     vs_frame_record* frec;
     vs_output_record* orec;
     float2* log_prev;               // ring of per-frame point logs (tests)
@@ -86,6 +87,16 @@ struct LaneDev {
 };
 
 // Host-known scalars of one lock-step frame step, passed by value to the motion kernel.
+// LaneDev::hf layout: translation history (x,y) x 10 oldest first, then the scalars of Stabilizer.cpp:143-153
+#define VS_HF_HIST 0
+#define VS_HF_COUNT 20
+#define VS_HF_MEDIAN 21
+#define VS_HF_ROT_LP 23
+#define VS_HF_IN_DEAD_ZONE 24
+#define VS_HF_FREEZE_COUNTER 25
+#define VS_HF_ACCUMULATOR 26
+#define VS_HF_FLOATS 32
+
 struct StepInfo {
     int frame_no;          // n >= 1: this is the n-th generateTransform() call (frame n)
     int cur;               // pyramid slot holding the current frame
@@ -102,6 +113,9 @@ struct StepInfo {
     int lk_slot;           // tracker output buffer of this frame (LaneDev::lkn / lks)
     int will_detect;       // corners are re-detected on this frame (the detector writes n_detected itself)
     int wp_slot;           // warp set-up buffer of the output produced by this step (LaneDev::wpb)
+    int drone;             // droneHighFreqMode (Stabilizer.cpp:666-671, :1144-1146)
+    float hf_shake_px, hf_rot_lp_alpha, hf_dead_zone_threshold, hf_accumulator_decay;
+    int hf_freeze_duration;
 };
 
 // Detection scratch / key-point buffers of generation `gen` (0 / 1).  Plain selects on the lane record in global

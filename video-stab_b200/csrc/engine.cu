@@ -68,7 +68,6 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 vs_status Engine::create(const vs_params& p, int device, int n_lanes, Engine** out) {
     *out = nullptr;
     if (n_lanes < 1 || n_lanes > VS_MAX_GROUP) return vs_set_error(VS_ERR_INVALID_ARG, "n_streams must be 1..64");
-    if (p.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode is not built yet");
     if (p.enable_virtual_canvas) return vs_set_error(VS_ERR_UNSUPPORTED, "enable_virtual_canvas is not built yet");
     if (p.block_size != 3) return vs_set_error(VS_ERR_UNSUPPORTED, "only block_size 3 (the reference default) is supported");
     if (p.adaptive_smoothing && n_lanes > 1)
@@ -201,6 +200,7 @@ vs_status Engine::alloc_fixed() {
         VS_TRY(dalloc(allocs_, &L.lks[1], (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.first_corners, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.kalman, (size_t)VS_KAL_FLOATS));
+        VS_TRY(dalloc(allocs_, &L.hf, (size_t)VS_HF_FLOATS));
         VS_TRY(dalloc(allocs_, &L.wp, (size_t)2));
         L.wpb[0] = L.wp; L.wpb[1] = L.wp + 1;
         size_t ln = (size_t)log_depth_ * kp_cap_;
@@ -341,6 +341,15 @@ vs_status Engine::clean() {
 }
 
 vs_status Engine::ensure_geometry(int w, int h, bool need_ring, bool need_out, bool need_scratch) {
+    if (p_.drone_high_freq_mode) {
+        // calculateDroneAnalysisSize (Stabilizer.cpp:2447-2466): the analysis kernels are built for 960x540
+        const int mw = p_.hf_analysis_max_width < w ? p_.hf_analysis_max_width : w;
+        const float aspect = (float)h / (float)w;
+        const int ah = (int)((float)mw * aspect);
+        if ((mw / 2) * 2 != VS_AW || (ah / 2) * 2 != VS_AH)
+            return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode: only frames whose drone analysis size is 960x540 "
+                                                    "(hf_analysis_max_width 960, 16:9 input at least 960 wide) are supported");
+    }
     if (W_ == 0) {
         W_ = w; H_ = h;
         frame_bytes_ = (size_t)w * 3 * h;
@@ -382,6 +391,12 @@ StepInfo Engine::step_info(int pop_index) const {
     s.lk_slot = n_frames_ & 1;
     s.will_detect = ((detect_counter_ + 1) % 2) == 0;            // (++featureDetectionCounter % 2) == 0, Stabilizer.cpp:696-697
     s.wp_slot = n_out_ & 1;
+    s.drone = p_.drone_high_freq_mode;
+    s.hf_shake_px = p_.hf_shake_px;
+    s.hf_rot_lp_alpha = p_.hf_rot_lp_alpha;
+    s.hf_dead_zone_threshold = p_.hf_dead_zone_threshold;
+    s.hf_accumulator_decay = p_.hf_motion_accumulator_decay;
+    s.hf_freeze_duration = p_.hf_freeze_duration;
     return s;
 }
 
@@ -785,6 +800,7 @@ int Engine::chunk_halo(int first) {
 vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first, int count, float* out_host, int* n_out) {
     if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "clip mode uses single-lane handles");
     if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
+    if (p_.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode filters carry state from frame to frame; not available in clip mode");
     if (!d_frames || first < 0 || count <= 0) return vs_set_error(VS_ERR_INVALID_ARG, "bad chunk");
     CUDA_TRY(cudaSetDevice(device_));
     VS_TRY(clean());
@@ -845,6 +861,7 @@ vs_status Engine::render_chunk(const float* all_tr_host, int n_total, const uint
                                int count, uint8_t* d_out, int* ow, int* oh) {
     if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "clip mode uses single-lane handles");
     if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
+    if (p_.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode filters carry state from frame to frame; not available in clip mode");
     if (!all_tr_host || !d_frames || !d_out || n_total < 1 || first < 0 || count <= 0 || first + count > n_total)
         return vs_set_error(VS_ERR_INVALID_ARG, "bad chunk");
     CUDA_TRY(cudaSetDevice(device_));

@@ -183,14 +183,77 @@ static __device__ int adaptive_radius(const Traj path, int n, int smoothing_radi
     return (int)fmaxf(5.0f, fminf(25.0f, __fmul_rn(total, 2.0f)));
 }
 
-static __device__ float box_at(const Traj path, int comp, int n, int radius, int i) {
-    // boxFilterConvolve (normal mode), Stabilizer.cpp:1139-1172 — only element i is ever consumed
-    int r = max(2, min(radius, 8));
+static __device__ float box_at(const Traj path, int comp, int n, int radius, int i, int drone) {
+    // boxFilterConvolve, Stabilizer.cpp:1139-1172 — only element i is ever consumed
+    int r = drone ? max(10, min(radius, 50)) : max(2, min(radius, 8));
     if (n <= r) return path.at(i, comp);
     int lo = max(0, i - r), hi = min(n - 1, i + r);
     float s = 0.f;
     for (int j = lo; j <= hi; ++j) s = __fadd_rn(s, path.at(j, comp));
     return __fdiv_rn(s, (float)(hi - lo + 1));
+}
+
+static __device__ float hf_median(const float* hist, int cnt, int comp) {
+    // calculateMedianTranslation, Stabilizer.cpp:2531-2555 (cnt is 5..10)
+    float v[10];
+    for (int i = 0; i < 10; ++i) v[i] = i < cnt ? hist[2 * i + comp] : 0.f;
+    for (int i = 1; i < 10; ++i) {
+        if (i >= cnt) break;
+        float x = v[i];
+        int j = i - 1;
+        while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
+        v[j + 1] = x;
+    }
+    const int mid = cnt / 2;
+    float lo = 0.f, hi = 0.f;
+    for (int i = 0; i < 10; ++i) { if (i == mid - 1) lo = v[i]; if (i == mid) hi = v[i]; }
+    return (cnt & 1) ? hi : __fdiv_rn(__fadd_rn(lo, hi), 2.0f);
+}
+
+static __device__ void hf_filters(float* hf, const StepInfo& info, float* t) {
+    // applyDeadZoneFreeze -> applyMicroShakeSuppression -> applyRotationLowPass -> updateTranslationHistory,
+    // Stabilizer.cpp:666-671 with :2468-2529 and :2605-2681; float32 step for step
+    const float dx = t[0], dy = t[1], da = t[2];
+    const float thr = info.hf_dead_zone_threshold;
+    const float mag = f_sqrt(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(__fmul_rn(da, da), 100.0f)));
+    float acc = fmaxf(__fmul_rn(hf[VS_HF_ACCUMULATOR], info.hf_accumulator_decay), mag);
+    acc = fminf(acc, __fmul_rn(thr, 5.0f));
+    acc = fmaxf(0.0f, fminf(acc, 100.0f));
+    int in_dz = __float_as_int(hf[VS_HF_IN_DEAD_ZONE]);
+    int counter = __float_as_int(hf[VS_HF_FREEZE_COUNTER]);
+    if (!in_dz && mag < thr) { in_dz = 1; counter = info.hf_freeze_duration; }
+    if (in_dz) {
+        --counter;
+        if (counter <= 0 || mag > __fmul_rn(thr, 1.5f) || acc > __fmul_rn(thr, 1.2f)) { in_dz = 0; counter = 0; acc = 0.f; }
+        else { t[0] = 0.f; t[1] = 0.f; t[2] = 0.f; }
+    }
+    hf[VS_HF_ACCUMULATOR] = acc;
+    hf[VS_HF_IN_DEAD_ZONE] = __int_as_float(in_dz);
+    hf[VS_HF_FREEZE_COUNTER] = __int_as_float(counter);
+
+    int cnt = __float_as_int(hf[VS_HF_COUNT]);
+    float* hist = hf + VS_HF_HIST;
+    if (cnt >= 5) { hf[VS_HF_MEDIAN] = hf_median(hist, cnt, 0); hf[VS_HF_MEDIAN + 1] = hf_median(hist, cnt, 1); }
+    const float mx = hf[VS_HF_MEDIAN], my = hf[VS_HF_MEDIAN + 1];
+    const float ex = __fsub_rn(t[0], mx), ey = __fsub_rn(t[1], my);
+    const float m2 = f_sqrt(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+    if (m2 < info.hf_shake_px) {
+        t[0] = __fadd_rn(mx, __fmul_rn(ex, 0.01f)); t[1] = __fadd_rn(my, __fmul_rn(ey, 0.01f));
+    } else if (m2 < __fmul_rn(info.hf_shake_px, 2.0f)) {
+        t[0] = __fadd_rn(mx, __fmul_rn(ex, 0.05f)); t[1] = __fadd_rn(my, __fmul_rn(ey, 0.05f));
+    }
+    if (info.horizon_lock) {
+        const float a = info.hf_rot_lp_alpha;
+        const float lp = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, a), hf[VS_HF_ROT_LP]), __fmul_rn(a, t[2]));
+        hf[VS_HF_ROT_LP] = lp;
+        t[2] = lp;
+    }
+    if (cnt == 10) {
+        for (int i = 0; i < 18; ++i) hist[i] = hist[i + 2];
+        cnt = 9;
+    }
+    hist[2 * cnt] = t[0]; hist[2 * cnt + 1] = t[1];
+    hf[VS_HF_COUNT] = __int_as_float(cnt + 1);
 }
 
 static __device__ float variance_f(const float* v, int n) {
@@ -335,7 +398,7 @@ static __device__ void smooth_and_setup(const LaneDev& L, WarpParams* wp_out, co
     }
     if (!have) {                                            // box with adaptive radius :808-823
         rec.radius = adaptive_radius(path, n, info.smoothing_radius);
-        for (int comp = 0; comp < 3; ++comp) sm[comp] = box_at(path, comp, n, rec.radius, i);
+        for (int comp = 0; comp < 3; ++comp) sm[comp] = box_at(path, comp, n, rec.radius, i, info.drone);
     }
     float raw[3], diff[3];
     for (int k = 0; k < 3; ++k) {
@@ -543,6 +606,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
             t[0] = (float)TX; t[1] = (float)TY;
             t[2] = f_atan2(T10, T00);
         }
+        if (info.drone && n_prev > 0) hf_filters(L.hf, info, t);
         float* tr = L.transforms + 3 * fidx;
         float* pa = L.path + 3 * fidx;
         for (int k = 0; k < 3; ++k) {
@@ -575,7 +639,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         }
         __threadfence_block();
         if (info.pop_index >= 0) {
-            const bool in_tail = info.pop_index - 20 >= tail_base || tail_base == 0;
+            const bool in_tail = info.pop_index - (info.drone ? 50 : 20) >= tail_base || tail_base == 0;
             if (in_tail) smooth_and_setup(L, wp_out, info, S.gk, Traj{S.tail_path, tail_base}, Traj{S.tail_trf, tail_base}, Traj{S.tail_aux, tail_base});
             else smooth_and_setup(L, wp_out, info, S.gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
         }
