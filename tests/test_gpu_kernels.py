@@ -118,15 +118,25 @@ def test_border_then_warp(vsb, cv2_noopt, mode, bmode, cvname):
     assert np.array_equal(out, ref)
 
 
-@pytest.mark.parametrize("w,h,b", [(1280, 720, 30), (1920, 1080, 50)])
+@pytest.mark.parametrize("w,h,b", [(1280, 720, 30), (1920, 1080, 50), (3840, 2160, 30), (1920, 1080, 1), (1920, 1080, 300),
+                                   (1000, 562, 17), (640, 360, 8), (136, 64, 2)])
 def test_warp_crop_zoom(vsb, cv2_noopt, w, h, b):
+    """cropNZoom output stage (Stabilizer.cpp:1056-1060, 1108-1124) = warpAffine, crop by b, cv::resize back.  Frames
+    whose rows are 16-byte aligned take the fused single-pass kernel, (1000, 562) the two-pass fallback; the matrices
+    cover the identity, typical jitter, a shift that leaves a zero band, and a 25 degree rotation (per-tile generic
+    path inside the fused kernel)."""
     cv2 = cv2_noopt
     f = _tex(vsb, w, h, 43)
-    T = _matrices(3, 11)[1]
-    out = vsb.kernels.warp_output(_dev(f), T, 2, b, 0).cpu().numpy()
-    wr = cv2.warpAffine(f, T, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
-    ref = cv2.resize(wr[b:h - b, b:w - b].copy(), (w, h))
-    assert np.array_equal(out, ref)
+    Ts = list(_matrices(3, 11))
+    Ts.append(np.array([[1, 0, -37.25], [0, 1, 21.5]], np.float32))
+    a = np.deg2rad(25.0)
+    Ts.append(np.array([[np.cos(a), -np.sin(a), 0.1 * w], [np.sin(a), np.cos(a), -0.2 * h]], np.float32))
+    Ts.append(np.array([[1.07, 0.02, 3.5], [-0.03, 0.95, -2.25]], np.float32))
+    for k, T in enumerate(Ts):
+        out = vsb.kernels.warp_output(_dev(f), T, 2, b, 0).cpu().numpy()
+        wr = cv2.warpAffine(f, T, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+        ref = cv2.resize(wr[b:h - b, b:w - b].copy(), (w, h))
+        assert np.array_equal(out, ref), f"matrix {k}: {int((out != ref).sum())} bytes differ, max {np.abs(out.astype(int) - ref).max()}"
 
 
 @pytest.mark.parametrize("w,h", [(1920, 1080), (1280, 720), (3840, 2160), (1000, 562)])

@@ -149,6 +149,42 @@ static __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
+// ---------------------------------------------------------------- cv::resize INTER_LINEAR tables
+struct AxisTap {
+    int s0, s1;      // tap indices (already clamped)
+    int a0, a1;      // 11-bit coefficients
+};
+
+// horizontal semantics: index clamped AND fraction zeroed at both ends
+static __device__ __forceinline__ AxisTap tap_h(int d, int src, double scale) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= src - 1) { s = src - 1; f = 0.f; }
+    AxisTap t;
+    t.s0 = s;
+    t.s1 = min(s + 1, src - 1);
+    t.a0 = __float2int_rn((1.f - f) * 2048.f);
+    t.a1 = __float2int_rn(f * 2048.f);
+    return t;
+}
+// vertical semantics: coefficients from the unclamped fraction, row indices clipped
+static __device__ __forceinline__ AxisTap tap_v(int d, int src, double scale) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    AxisTap t;
+    t.s0 = min(max(s, 0), src - 1);
+    t.s1 = min(max(s + 1, 0), src - 1);
+    t.a0 = __float2int_rn((1.f - f) * 2048.f);
+    t.a1 = __float2int_rn(f * 2048.f);
+    return t;
+}
+static __device__ __forceinline__ int vres(int h0, int h1, int b0, int b1) {
+    return (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+}
+
 #define CUDA_TRY(x)                                                                   \
     do {                                                                              \
         cudaError_t e__ = (x);                                                        \

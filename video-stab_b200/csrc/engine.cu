@@ -592,8 +592,7 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         std::vector<uint8_t*> scratch(n_lanes_);
         for (int l = 0; l < n_lanes_; ++l) scratch[l] = d_scratch_ ? d_scratch_ + frame_bytes_ * l : nullptr;
         { StageScope t(this, VS_STAGE_WARP, stream_);
-          launch_warp(d_lanes_, n_lanes_, src, dst, g, scratch.data(), stream_); }
-        launches_ += (m2 == 2) ? 1 + n_lanes_ : 1;
+          launches_ += launch_warp(d_lanes_, n_lanes_, src, dst, g, scratch.data(), stream_); }
         if (fade_) {                                                                  // :1070-1106
             launch_fade_update(d_fade_, dst, dstride, n_lanes_, W_, H_, b, stream_);
             launches_ += 1;
@@ -892,9 +891,8 @@ vs_status Engine::render_chunk(const float* all_tr_host, int n_total, const uint
     if (n_warp > 0) {
         StepInfo base = step_info(0);
         launch_smooth_batch(d_lanes_, 1, base, first, n_warp, n_total, gate, d_wp_batch_, stream_);
-        launch_warp_frames_mode(d_frames, w, h, tight_in, frame_bytes_, d_out, tight_out, oframe, d_wp_batch_, n_warp, mode, b,
-                                border_mode_, d_scratch_, stream_);
-        launches_ += 2 + (mode == 2 ? 2 * n_warp - 1 : 0);
+        launches_ += 1 + launch_warp_frames_mode(d_frames, w, h, tight_in, frame_bytes_, d_out, tight_out, oframe, d_wp_batch_, n_warp,
+                                                 mode, b, border_mode_, d_scratch_, stream_);
     }
     if (n_warp < count) {
         // un-warped original frame, written at the top-left of its output slot (smaller than a bordered frame)

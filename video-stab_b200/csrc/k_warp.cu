@@ -50,11 +50,10 @@ static __device__ __forceinline__ int border_map(int p, int len, int mode) {
     return p;
 }
 
-// One output pixel (3 channels).  BORDER: the source is the virtual (w+2b)x(h+2b) bordered frame.
+// One output pixel (3 channels) as a word [B G R 0].  BORDER: the source is the virtual (w+2b)x(h+2b) bordered frame.
 template <bool BORDER>
-static __device__ __forceinline__ void warp_pixel(const uint8_t* __restrict__ src, int w, int h, size_t stride,
-                                                  const double* __restrict__ m, int b, int bmode, int x, int y,
-                                                  uint8_t* __restrict__ out) {
+static __device__ __forceinline__ uint32_t warp_pixel_word(const uint8_t* __restrict__ src, int w, int h, size_t stride,
+                                                           const double* __restrict__ m, int b, int bmode, int x, int y) {
     FixedCoord c = warp_coord(m, x, y);
     const int vw = BORDER ? w + 2 * b : w, vh = BORDER ? h + 2 * b : h;
     const int w00 = (32 - c.ax) * (32 - c.ay), w01 = c.ax * (32 - c.ay), w10 = (32 - c.ax) * c.ay, w11 = c.ax * c.ay;
@@ -75,9 +74,14 @@ static __device__ __forceinline__ void warp_pixel(const uint8_t* __restrict__ sr
         acc2 += wt * p[2];
     }
     // weights are (..)*32 with sum 32768: (acc*32 + 16384) >> 15 == (acc + 512) >> 10
-    out[0] = (uint8_t)((acc0 + 512) >> 10);
-    out[1] = (uint8_t)((acc1 + 512) >> 10);
-    out[2] = (uint8_t)((acc2 + 512) >> 10);
+    return (uint32_t)((acc0 + 512) >> 10) | ((uint32_t)((acc1 + 512) >> 10) << 8) | ((uint32_t)((acc2 + 512) >> 10) << 16);
+}
+template <bool BORDER>
+static __device__ __forceinline__ void warp_pixel(const uint8_t* __restrict__ src, int w, int h, size_t stride,
+                                                  const double* __restrict__ m, int b, int bmode, int x, int y,
+                                                  uint8_t* __restrict__ out) {
+    const uint32_t v = warp_pixel_word<BORDER>(src, w, h, stride, m, b, bmode, x, y);
+    out[0] = (uint8_t)v; out[1] = (uint8_t)(v >> 8); out[2] = (uint8_t)(v >> 16);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -564,6 +568,268 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Crop-and-zoom fused into the warp (Stabilizer.cpp:1056-1060 + :1108-1124): cv::warpAffine, the (b, b, W-2b, H-2b)
+// crop and cv::resize back to W x H, reading the source once and writing the output once.  One CTA walks a strip
+// of 120x30 OUTPUT tiles.  The resize taps of such a tile cover at most 122x32 pixels of the warped image (the
+// zoom factor is > 1), so per tile
+//   A. the 128x32 warped tile that contains them is produced exactly like a k_warp_tma tile (same TMA box, same
+//      re-pack, same fixed-point inner loop) but lands in shared memory as [B G R -] words, and
+//   B. the output tile is cv::resize's 11-bit bilinear of that shared tile: horizontal pass as IDP.2A with the
+//      coefficient pair (a0 | a1 << 16), vertical pass ((b * (h >> 4)) >> 16 as IMAD.HI with b << 16), rounding
+//      (v + 2) >> 2 — term for term VResizeLinear / HResizeLinear of OpenCV (oracle/cv_models.py resize_linear).
+// The warped frame never exists in HBM.
+#define ZT_W 120
+#define ZT_H 30
+#define ZT_MAXT 4
+#define ZT_SMEM (WT_ROWS * WT_TPITCH + WT_ROWS * WT_RAW_PITCH + WT_H * WT_W * 4 + (WT_THREADS / 32) * WT_W * 4 + \
+                 2 * WT_H * 8 + 2 * WT_H * 16 + 64 + 16)
+
+__global__ void __launch_bounds__(WT_THREADS, 3)
+k_warp_zoom_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict__ dmaps, int lanes_mode,
+                const LaneDev* __restrict__ lanes, const WarpParams* __restrict__ wps,
+                PtrPack srcp, const uint8_t* __restrict__ src0, size_t sframe, size_t sstride, int sw, int sh,
+                MutPtrPack dstp, uint8_t* __restrict__ dst0, size_t dframe, size_t dstride,
+                int rows_per_cta, int dst_vec, int wp_slot, int border, double zsx, double zsy) {
+    extern __shared__ __align__(1024) unsigned char wt_smem[];
+    uint32_t* const S_src = reinterpret_cast<uint32_t*>(wt_smem);
+    unsigned char* const S_raw = wt_smem + WT_ROWS * WT_TPITCH;
+    uint32_t* const S_w = reinterpret_cast<uint32_t*>(S_raw + WT_ROWS * WT_RAW_PITCH);       // warped tile, 128 words x 32 rows
+    uint32_t* const S_out = S_w + WT_H * WT_W;
+    int2* const S_rowXY = reinterpret_cast<int2*>(S_out + (WT_THREADS / 32) * WT_W);         // [2][WT_H]
+    int4* const S_vtap = reinterpret_cast<int4*>(S_rowXY + 2 * WT_H);                        // [2][WT_H]
+    int (*S_box)[8] = reinterpret_cast<int (*)[8]>(S_vtap + 2 * WT_H);
+    unsigned long long* const S_mbar = reinterpret_cast<unsigned long long*>(S_box + 2);
+
+    const int z = blockIdx.z;
+    const double* __restrict__ m = lanes_mode ? lanes[z].wpb[wp_slot]->m : wps[z].m;
+    uint8_t* __restrict__ dst = lanes_mode ? dstp.p[z] : dst0 + (size_t)z * dframe;
+    const CUtensorMap* tmap = dmaps ? dmaps + (lanes_mode ? z : 0) : &pack.m[lanes_mode ? z : 0];
+    const int zc = lanes_mode ? 0 : z;
+    const int dw = sw, dh = sh, cw = sw - 2 * border, ch = sh - 2 * border;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * ZT_W, ys = blockIdx.y * rows_per_cta;
+    const int ye = min(ys + rows_per_cta, dh);
+    int2* const colAB = reinterpret_cast<int2*>(S_out);              // 128 entries (1 KB)
+    int2* const colTap = colAB + WT_W;                               // 120 entries
+    const uint32_t s_src = (uint32_t)__cvta_generic_to_shared(S_src);
+    const uint32_t s_raw = (uint32_t)__cvta_generic_to_shared(S_raw);
+    const uint32_t s_w = (uint32_t)__cvta_generic_to_shared(S_w);
+    const uint32_t s_mbar = (uint32_t)__cvta_generic_to_shared(S_mbar);
+
+    // first crop column any tap of this tile column range touches; warped column of tile column c is wx0 + c
+    const int c0 = tap_h(x0, cw, zsx).s0;
+    const int wx0 = border + c0;
+
+    // row terms of the 32 warped rows and vertical taps of the 30 output rows of the tile starting at output row y0
+    auto prep_tile = [&](int y0, int b, int i) {
+        const int r0 = tap_v(y0, ch, zsy).s0;
+        if (i < WT_H) {
+            const double yd = (double)min(border + r0 + i, sh - 1);
+            S_rowXY[b * WT_H + i] = make_int2(sat_int((m[1] * yd + m[2]) * 1024.0) + 16, sat_int((m[4] * yd + m[5]) * 1024.0) + 16);
+        } else if (i < WT_H + ZT_H) {
+            const int k = i - WT_H;
+            const AxisTap t = tap_v(min(y0 + k, dh - 1), ch, zsy);
+            S_vtap[b * WT_H + k] = make_int4((t.s0 - r0) * (WT_W * 4), (t.s1 - r0) * (WT_W * 4), t.a0 << 16, t.a1 << 16);
+        }
+    };
+
+    // ---- 0. strip prologue
+    if (tid < WT_W) {
+        const double xd = (double)min(wx0 + tid, sw - 1);
+        colAB[tid] = make_int2(sat_int(m[0] * xd * 1024.0), sat_int(m[3] * xd * 1024.0));
+        if (tid < ZT_W) {
+            const AxisTap t = tap_h(min(x0 + tid, dw - 1), cw, zsx);
+            colTap[tid] = make_int2(4 * (t.s0 - c0), t.a0 | (t.a1 << 16));
+        }
+    } else if (tid < WT_W + WT_H + ZT_H) {
+        prep_tile(ys, 0, tid - WT_W);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(s_mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (dmaps) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(tmap) : "memory");
+    }
+    __syncthreads();
+    uint32_t adT[4], bd[4], colS[4], colW[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int2 c = colAB[lane + 32 * j];
+        adT[j] = (uint32_t)c.x * 16u;
+        bd[j] = (uint32_t)c.y;
+        const int2 t = colTap[min(lane + 32 * j, ZT_W - 1)];
+        colS[j] = (uint32_t)t.x;
+        colW[j] = (uint32_t)t.y;
+    }
+    const int tw = min(ZT_W, dw - x0);
+    const int2 cA = colAB[0], cB = colAB[WT_W - 1];
+    const bool col_ok = max(max(abs(cA.x), abs(cB.x)), max(abs(cA.y), abs(cB.y))) < (1 << 26);
+    const bool vec_out = dst_vec && tw == ZT_W;
+    const uint32_t s_px = (uint32_t)__cvta_generic_to_shared(S_out + warp * WT_W + lane);
+    const uint32_t s_v4 = (uint32_t)__cvta_generic_to_shared(S_out + warp * WT_W + 4 * lane);
+    const uint32_t s_wpx = s_w + 4u * (uint32_t)lane;
+    const int r7 = tid / WT_TGRPS, q = tid - r7 * WT_TGRPS;
+    const uint32_t s_stage = s_src + (uint32_t)(r7 * WT_TPITCH + 16 * q);
+    const uint32_t s_rawt = s_raw + (uint32_t)(r7 * WT_RAW_PITCH + 12 * q);
+
+    // source box of the warped tile whose row terms are (rA, rB) -> S_box[b]; issues its fetch when the box fits
+    auto box_and_fetch = [&](int2 rA, int2 rB, int b) {
+        int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int2 cc = (c & 1) ? cB : cA, rr = (c & 2) ? rB : rA;
+            const int X = (rr.x + cc.x) >> 10, Y = (rr.y + cc.y) >> 10;
+            minx = min(minx, X); maxx = max(maxx, X); miny = min(miny, Y); maxy = max(maxy, Y);
+        }
+        const int ax0 = minx & ~3;
+        const int ngrp = (maxx + 1 - ax0) / 4 + 1;
+        const int nrows = maxy + 2 - miny;
+        const bool row_ok = max(max(abs(rA.x), abs(rB.x)), max(abs(rA.y), abs(rB.y))) < (1 << 26);
+        const bool ok = col_ok && row_ok && minx > -30000 && maxx < 30000 && miny > -30000 && maxy < 30000 &&
+                        ngrp <= WT_GRPS && nrows <= WT_ROWS && ngrp > 0 && nrows > 0;
+        const int axT = minx & ~15;
+        int* bx = S_box[b];
+        bx[0] = ax0; bx[1] = miny; bx[2] = ngrp; bx[3] = nrows; bx[4] = ok ? 1 : 0; bx[5] = 3 * (ax0 - axT);
+        if (ok) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s_mbar), "r"(WT_ROWS * WT_RAW_PITCH) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         :: "r"(s_raw), "l"(tmap), "r"(s_mbar), "r"(3 * (axT >> 2)), "r"(miny), "r"(zc) : "memory");
+        }
+    };
+    // the row terms of a tile's first and last warped row, recomputed by the issuing thread (the table entries of
+    // the NEXT tile are being written by other threads at that moment)
+    auto row_terms = [&](int y0, int i) {
+        const int r0 = tap_v(y0, ch, zsy).s0;
+        const double yd = (double)min(border + r0 + i, sh - 1);
+        return make_int2(sat_int((m[1] * yd + m[2]) * 1024.0) + 16, sat_int((m[4] * yd + m[5]) * 1024.0) + 16);
+    };
+    if (tid == 0) box_and_fetch(S_rowXY[0], S_rowXY[WT_H - 1], 0);
+    __syncthreads();
+
+    int buf = 0;
+    uint32_t phase = 0;
+    for (int y0 = ys; y0 < ye; y0 += ZT_H, buf ^= 1) {
+        const int ax0 = S_box[buf][0], by0 = S_box[buf][1], ngrp = S_box[buf][2], nrows = S_box[buf][3];
+        const bool ok = S_box[buf][4] != 0;
+        const bool more = y0 + ZT_H < ye;
+        const int orows = min(ZT_H, ye - y0);                                   // output rows of this tile
+        const int wrows = (S_vtap[buf * WT_H + orows - 1].y >> 9) + 1;          // warped rows its taps touch
+        if (ok) {
+            mbar_wait(s_mbar, phase);
+            phase ^= 1;
+            const bool colok = q < ngrp && r7 < WT_TSROWS;
+            const uint32_t s_rawq = s_rawt + (uint32_t)S_box[buf][5];
+#define WT_REPACK(k)                                                                                           \
+            if ((k) * WT_TSROWS < nrows) {                               /* CTA-uniform */                      \
+                if (colok && r7 + (k) * WT_TSROWS < nrows) {                                                    \
+                    const uint32_t w0 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH>(s_rawq);                          \
+                    const uint32_t w1 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 4>(s_rawq);                      \
+                    const uint32_t w2 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 8>(s_rawq);                      \
+                    const uint32_t w3 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 12>(s_rawq);                     \
+                    const uint4 o = repack_bgrr(w0, w1, w2, w3);                                               \
+                    sts128<(k) * WT_TSROWS * WT_TPITCH>(s_stage, o.x, o.y, o.z, o.w);                       \
+                }                                                                                              \
+            }
+            WT_REPACK(0) WT_REPACK(1) WT_REPACK(2) WT_REPACK(3) WT_REPACK(4) WT_REPACK(5) WT_REPACK(6)
+#undef WT_REPACK
+        }
+        __syncthreads();                                   // S_src ready, raw box free, previous tile's stage B done
+        if (more) {
+            if (tid == 0) box_and_fetch(row_terms(y0 + ZT_H, 0), row_terms(y0 + ZT_H, WT_H - 1), buf ^ 1);
+            else if (tid >= WT_W && tid < WT_W + WT_H + ZT_H) prep_tile(y0 + ZT_H, buf ^ 1, tid - WT_W);
+        }
+        // ---- A. the warped tile -> S_w
+        if (!ok) {
+            const uint8_t* sp = lanes_mode ? srcp.p[z] : src0 + (size_t)z * sframe;
+            const int r0 = tap_v(y0, ch, zsy).s0;
+            for (int i = tid; i < WT_W * wrows; i += WT_THREADS) {
+                const int c = i & (WT_W - 1), r = i / WT_W;
+                S_w[r * WT_W + c] = warp_pixel_word<false>(sp, sw, sh, sstride, m, 0, 0, min(wx0 + c, sw - 1), min(border + r0 + r, sh - 1));
+            }
+        } else {
+            const uint32_t bx14 = (uint32_t)ax0 << 14, by10 = (uint32_t)by0 << 10;
+#pragma unroll
+            for (int rr = warp; rr < WT_H; rr += WT_THREADS / 32) {
+                if (rr >= wrows) break;
+                const int2 xy = S_rowXY[buf * WT_H + rr];
+                const uint32_t rxT = (uint32_t)xy.x * 16u - bx14;
+                const uint32_t ryS = (uint32_t)xy.y - by10;
+                const uint32_t s_row = s_wpx + (uint32_t)rr * (WT_W * 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t T1 = rxT + adT[j];
+                    const uint32_t t2 = ryS + bd[j];
+                    const uint32_t a = s_src + 4u * ((t2 >> 10) * (WT_TPITCH / 4) + (T1 >> 14));
+                    const uint32_t A16 = T1 & 0x3E00u;
+                    const uint32_t W16 = A16 * 0xFFFFu + 16384u;
+                    const uint32_t B = t2 & 0x3E0u, Bc = 1024u - B;
+                    const uint32_t t00 = lds32<0>(a), t01 = lds32<4>(a), t10 = lds32<WT_TPITCH>(a), t11 = lds32<WT_TPITCH + 4>(a);
+                    const uint32_t u0 = __byte_perm(t00, t01, 0x5140);
+                    const uint32_t l0 = __byte_perm(t10, t11, 0x5140);
+                    const uint32_t hb0 = __dp2a_lo(W16, u0, 0u), hg0 = __dp2a_hi(W16, u0, 0u), hr0 = __dp2a_hi(W16, t00, 0u);
+                    const uint32_t hb1 = __dp2a_lo(W16, l0, 0u), hg1 = __dp2a_hi(W16, l0, 0u), hr1 = __dp2a_hi(W16, t10, 0u);
+                    const uint32_t vb = hb0 * Bc + (hb1 * B + 0x800000u);
+                    const uint32_t vg = hg0 * Bc + (hg1 * B + 0x800000u);
+                    const uint32_t vr = hr0 * Bc + (hr1 * B + 0x800000u);
+                    const uint32_t px = __byte_perm(__byte_perm(vb, vg, 0x0073), vr, 0x0710);
+                    if (j == 0) sts32<0>(s_row, px);
+                    else if (j == 1) sts32<128>(s_row, px);
+                    else if (j == 2) sts32<256>(s_row, px);
+                    else sts32<384>(s_row, px);
+                }
+            }
+        }
+        __syncthreads();                                   // S_w complete (and S_src free for the next re-pack)
+        // ---- B. cv::resize of the shared warped tile: warp -> output rows, lane -> pixels x0 + lane + 32 j
+        uint8_t* grow = dst + (size_t)(y0 + warp) * dstride + (size_t)x0 * 3 + (vec_out ? 12 * lane : 0);
+#pragma unroll
+        for (int rr = warp; rr < ZT_H; rr += WT_THREADS / 32) {
+            if (rr >= orows) break;
+            const int4 vt = S_vtap[buf * WT_H + rr];
+            const uint32_t B0 = (uint32_t)vt.z, B1 = (uint32_t)vt.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j == 3 && lane >= ZT_W - 96) break;
+                const uint32_t a0 = s_w + colS[j] + (uint32_t)vt.x, a1 = s_w + colS[j] + (uint32_t)vt.y;
+                const uint32_t t00 = lds32<0>(a0), t01 = lds32<4>(a0), t10 = lds32<0>(a1), t11 = lds32<4>(a1);
+                const uint32_t W = colW[j];
+                const uint32_t u0 = __byte_perm(t00, t01, 0x5140), r0p = __byte_perm(t00, t01, 0x0062);
+                const uint32_t u1 = __byte_perm(t10, t11, 0x5140), r1p = __byte_perm(t10, t11, 0x0062);
+                const uint32_t hb0 = __dp2a_lo(W, u0, 0u) >> 4, hg0 = __dp2a_hi(W, u0, 0u) >> 4, hr0 = __dp2a_lo(W, r0p, 0u) >> 4;
+                const uint32_t hb1 = __dp2a_lo(W, u1, 0u) >> 4, hg1 = __dp2a_hi(W, u1, 0u) >> 4, hr1 = __dp2a_lo(W, r1p, 0u) >> 4;
+                const uint32_t vb = __umulhi(B1, hb1) + (__umulhi(B0, hb0) + 2u);
+                const uint32_t vg = __umulhi(B1, hg1) + (__umulhi(B0, hg0) + 2u);
+                const uint32_t vr = __umulhi(B1, hr1) + (__umulhi(B0, hr0) + 2u);
+                const uint32_t px = (vb >> 2) | ((vg << 6) & 0xFF00u) | ((vr << 14) & 0xFF0000u);
+                if (j == 0) sts32<0>(s_px, px);
+                else if (j == 1) sts32<128>(s_px, px);
+                else if (j == 2) sts32<256>(s_px, px);
+                else sts32<384>(s_px, px);
+            }
+            __syncwarp();
+            if (vec_out) {
+                if (lane < ZT_W / 4) {
+                    uint32_t vx, vy, vz, vw;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(vx), "=r"(vy), "=r"(vz), "=r"(vw) : "r"(s_v4));
+                    uint32_t* g = reinterpret_cast<uint32_t*>(grow);
+                    g[0] = __byte_perm(vx, vy, 0x4210);
+                    g[1] = __byte_perm(vy, vz, 0x5421);
+                    g[2] = __byte_perm(vz, vw, 0x6542);
+                }
+            } else {
+                const uint32_t* orow = S_out + warp * WT_W;
+                for (int c = lane; c < tw; c += 32) {
+                    const uint32_t v = orow[c];
+                    grow[3 * c] = (uint8_t)v; grow[3 * c + 1] = (uint8_t)(v >> 8); grow[3 * c + 2] = (uint8_t)(v >> 16);
+                }
+            }
+            grow += (size_t)(WT_THREADS / 32) * dstride;
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(WT_THREADS, 4) k_warp_tiled_lanes(const LaneDev* __restrict__ lanes, PtrPack src, MutPtrPack dst,
                                                                   WarpGeom g, int rows_per_cta, int src_vec, int dst_vec) {
     __shared__ __align__(16) WarpTileSmem S;
@@ -678,10 +944,82 @@ static void launch_warp_plain(const LaneDev* lanes, int n_lanes, const PtrPack& 
     k_warp_tiled_lanes<<<grid, WT_THREADS, 0, st>>>(lanes, src, dst, g, rows, sv ? 1 : 0, dv ? 1 : 0);
 }
 
-void launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, WarpGeom g,
-                 uint8_t* const* scratch, cudaStream_t st) {
+static bool zoom_kernel_ready() {
+    static int state[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    if (state[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(k_warp_zoom_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, ZT_SMEM);
+        state[dev] = (e == cudaSuccess && tma_encode_fn()) ? 1 : -1;
+        cudaGetLastError();
+    }
+    return state[dev] == 1;
+}
+static inline int zoom_strip_rows(int dw, int dh, int n_frames) {
+    const long tiles = (long)((dw + ZT_W - 1) / ZT_W) * ((dh + ZT_H - 1) / ZT_H) * n_frames;
+    int t = 1;
+    while (t < ZT_MAXT && tiles / (t * 2) >= 148L * 3 * 4) t *= 2;
+    return t * ZT_H;
+}
+// cv::resize's inverse scale factors for the (w-2b, h-2b) -> (w, h) zoom, as launch_resize_linear forms them
+static inline void zoom_scales(int w, int h, int b, double* sx, double* sy) {
+    *sx = 1.0 / ((double)w / (double)(w - 2 * b));
+    *sy = 1.0 / ((double)h / (double)(h - 2 * b));
+}
+
+// fused crop+zoom for per-lane frames; false when the TMA path is not available for this geometry
+static bool launch_warp_zoom_lanes(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, const WarpGeom& g,
+                                   cudaStream_t st) {
+    if (!zoom_kernel_ready() || !(n_lanes <= WT_TMA_MAXPACK || g.d_tmaps != nullptr)) return false;
+    if (g.out_w != g.src_w || g.out_h != g.src_h || g.src_w - 2 * g.border <= 0 || g.src_h - 2 * g.border <= 0) return false;
+    bool dv = true;
+    for (int i = 0; i < n_lanes; ++i) {
+        if (!tma_geometry_ok(src.p[i], g.src_w, g.src_stride, 0, 1)) return false;
+        dv = dv && vec_ok(dst.p[i], g.out_stride, 4);
+    }
+    TmapPack pack;
+    CUtensorMap big[VS_MAX_GROUP];
+    CUtensorMap* maps = n_lanes <= WT_TMA_MAXPACK ? pack.m : big;
+    for (int i = 0; i < n_lanes; ++i)
+        if (!tma_make_map(maps + i, src.p[i], g.src_w, g.src_h, g.src_stride, 0, 1)) return false;
+    const CUtensorMap* dmaps = nullptr;
+    if (n_lanes > WT_TMA_MAXPACK) {
+        cudaMemcpyAsync(g.d_tmaps, big, sizeof(CUtensorMap) * n_lanes, cudaMemcpyHostToDevice, st);
+        dmaps = (const CUtensorMap*)g.d_tmaps;
+    }
+    const int rows = zoom_strip_rows(g.out_w, g.out_h, n_lanes);
+    dim3 grid((g.out_w + ZT_W - 1) / ZT_W, (g.out_h + rows - 1) / rows, n_lanes);
+    double zsx, zsy;
+    zoom_scales(g.src_w, g.src_h, g.border, &zsx, &zsy);
+    k_warp_zoom_tma<<<grid, WT_THREADS, ZT_SMEM, st>>>(pack, dmaps, 1, lanes, nullptr, src, nullptr, 0, g.src_stride, g.src_w, g.src_h,
+                                                       dst, nullptr, 0, g.out_stride, rows, dv ? 1 : 0, g.wp_slot, g.border, zsx, zsy);
+    return true;
+}
+
+// fused crop+zoom for contiguous frames with device-resident warp set-ups
+static bool launch_warp_zoom_frames(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe, uint8_t* dst, size_t dstride,
+                                    size_t dframe, const WarpParams* d_wp, int n_frames, int border, cudaStream_t st) {
+    if (!zoom_kernel_ready() || sw - 2 * border <= 0 || sh - 2 * border <= 0) return false;
+    if (!tma_geometry_ok(src, sw, sstride, sframe, n_frames)) return false;
+    TmapPack pack;
+    if (!tma_make_map(pack.m, src, sw, sh, sstride, sframe, n_frames)) return false;
+    const bool dv = vec_ok(dst, dstride, 4) && dframe % 4 == 0;
+    const int rows = zoom_strip_rows(sw, sh, n_frames);
+    dim3 grid((sw + ZT_W - 1) / ZT_W, (sh + rows - 1) / rows, n_frames);
+    double zsx, zsy;
+    zoom_scales(sw, sh, border, &zsx, &zsy);
+    PtrPack sp{};
+    MutPtrPack dp{};
+    k_warp_zoom_tma<<<grid, WT_THREADS, ZT_SMEM, st>>>(pack, nullptr, 0, nullptr, d_wp, sp, src, sframe, sstride, sw, sh, dp, dst, dframe,
+                                                       dstride, rows, dv ? 1 : 0, 0, border, zsx, zsy);
+    return true;
+}
+
+int launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, WarpGeom g,
+                uint8_t* const* scratch, cudaStream_t st) {
     if (g.mode == 2) {
-        // crop+zoom, two passes for now: warp into the lane's scratch frame, then cv::resize the
+        if (launch_warp_zoom_lanes(lanes, n_lanes, src, dst, g, st)) return 1;
+        // no TMA for this geometry: two passes — warp into the lane's scratch frame, then cv::resize the
         // (b,b,w-2b,h-2b) crop back to w x h.
         MutPtrPack tmp;
         for (int i = 0; i < n_lanes; ++i) tmp.p[i] = scratch[i];
@@ -692,7 +1030,7 @@ void launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const Mu
         for (int i = 0; i < n_lanes; ++i)
             launch_resize_linear(scratch[i] + (size_t)b * g1.out_stride + 3 * b, cw, ch, g1.out_stride, 3,
                                  dst.p[i], g.out_w, g.out_h, g.out_stride, st);
-        return;
+        return 1 + n_lanes;
     }
     if (g.mode == 1) {
         dim3 grid((g.out_w + 63) / 64, (g.out_h + 3) / 4, n_lanes);
@@ -700,6 +1038,7 @@ void launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const Mu
     } else {
         launch_warp_plain(lanes, n_lanes, src, dst, g, st);
     }
+    return 1;
 }
 
 void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe,
@@ -735,10 +1074,10 @@ __global__ void __launch_bounds__(256) k_warp_frames_border(const uint8_t* __res
     warp_pixel<true>(src + blockIdx.z * sframe, sw, sh, sstride, wps[blockIdx.z].m, border, border_mode, x, y, o);
 }
 
-void launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe, uint8_t* dst,
-                             size_t dstride, size_t dframe, const WarpParams* d_wp, int n_frames, int mode, int border,
-                             int border_mode, uint8_t* scratch, cudaStream_t st) {
-    if (n_frames <= 0) return;
+int launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe, uint8_t* dst,
+                            size_t dstride, size_t dframe, const WarpParams* d_wp, int n_frames, int mode, int border,
+                            int border_mode, uint8_t* scratch, cudaStream_t st) {
+    if (n_frames <= 0) return 0;
     if (mode == 0) {
         launch_warp_matrices(src, sw, sh, sstride, sframe, dst, sw, sh, dstride, dframe, d_wp, n_frames, st);
     } else if (mode == 1) {
@@ -746,14 +1085,17 @@ void launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride,
         dim3 grid((dw + 63) / 64, (dh + 3) / 4, n_frames);
         k_warp_frames_border<<<grid, 256, 0, st>>>(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp, border, border_mode);
     } else {
-        // crop+zoom: warp each frame into the scratch frame, then cv::resize the (b,b,w-2b,h-2b) crop
+        if (launch_warp_zoom_frames(src, sw, sh, sstride, sframe, dst, dstride, dframe, d_wp, n_frames, border, st)) return 1;
+        // no TMA for this geometry: warp each frame into the scratch frame, then cv::resize the (b,b,w-2b,h-2b) crop
         const size_t tight = (size_t)sw * 3;
         for (int i = 0; i < n_frames; ++i) {
             launch_warp_matrices(src + i * sframe, sw, sh, sstride, sframe, scratch, sw, sh, tight, tight * sh, d_wp + i, 1, st);
             launch_resize_linear(scratch + (size_t)border * tight + 3 * border, sw - 2 * border, sh - 2 * border, tight, 3,
                                  dst + i * dframe, sw, sh, dstride, st);
         }
+        return 2 * n_frames;
     }
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -60,17 +60,18 @@ struct WarpGeom {
     int wp_slot;            // LaneDev::wpb index holding the warp set-up of this output
     void* d_tmaps;          // device scratch for VS_MAX_GROUP tensor maps (batches of more than 8 lanes), or nullptr
 };
-void launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, WarpGeom g,
-                 uint8_t* const* scratch, cudaStream_t st);
+// both output-stage launchers return the number of kernels they launched
+int launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, WarpGeom g,
+                uint8_t* const* scratch, cudaStream_t st);
 // stand-alone batched warp with host-supplied matrices (tests + roofline bench)
 void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe,
                           uint8_t* dst, int dw, int dh, size_t dstride, size_t dframe,
                           const WarpParams* d_wp, int n_frames, cudaStream_t st);
 void warp_params_from_T(const float* T, WarpParams* wp);   // host: cv::warpAffine's matrix inversion
 // batched output stage for contiguous frames with device-resident warp set-ups (offline clip mode)
-void launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe, uint8_t* dst,
-                             size_t dstride, size_t dframe, const WarpParams* d_wp, int n_frames, int mode, int border,
-                             int border_mode, uint8_t* scratch, cudaStream_t st);
+int launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe, uint8_t* dst,
+                            size_t dstride, size_t dframe, const WarpParams* d_wp, int n_frames, int mode, int border,
+                            int border_mode, uint8_t* scratch, cudaStream_t st);
 
 // border_type "fade" (Stabilizer.cpp:914-978, 1070-1106): history blend before the warp, history update after it
 void launch_fade_blend(const PtrPack& frames, int n_lanes, int w, int h, size_t stride, int b, uint8_t* hist, uint8_t* blend,
