@@ -108,14 +108,20 @@ def test_warp_affine_4k_and_linearity_property(vsb, cv2_noopt):
                                               (1, 2, "BORDER_REFLECT"), (1, 3, "BORDER_WRAP"),
                                               (1, 4, "BORDER_REFLECT_101")])
 def test_border_then_warp(vsb, cv2_noopt, mode, bmode, cvname):
+    """copyMakeBorder + warpAffine (Stabilizer.cpp:981-990, 1056-1060).  (640, 360) and (1920, 1080) take the tiled
+    TMA kernel (interior tiles staged, margin tiles per pixel unless the margin is constant 0), (642, 360) the
+    per-pixel kernel (row pitch not a multiple of 16 bytes)."""
     cv2 = cv2_noopt
-    w, h, b = 640, 360, 24
-    f = _tex(vsb, w, h, 41)
-    T = _matrices(3, 9)[2]
-    out = vsb.kernels.warp_output(_dev(f), T, mode, b, bmode).cpu().numpy()
-    src = cv2.copyMakeBorder(f, b, b, b, b, getattr(cv2, cvname), value=(0, 0, 0))
-    ref = cv2.warpAffine(src, T, (w + 2 * b, h + 2 * b), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
-    assert np.array_equal(out, ref)
+    for w, h, b in ((640, 360, 24), (642, 360, 24), (1920, 1080, 100)):
+        f = _tex(vsb, w, h, 41)
+        Ts = [_matrices(3, 9)[2], np.array([[1, 0, 0], [0, 1, 0]], np.float32)]
+        a = np.deg2rad(12.0)
+        Ts.append(np.array([[np.cos(a), -np.sin(a), 40.5], [np.sin(a), np.cos(a), -60.25]], np.float32))
+        for k, T in enumerate(Ts[:2] if w == 1920 else Ts):
+            out = vsb.kernels.warp_output(_dev(f), T, mode, b, bmode).cpu().numpy()
+            src = cv2.copyMakeBorder(f, b, b, b, b, getattr(cv2, cvname), value=(0, 0, 0))
+            ref = cv2.warpAffine(src, T, (w + 2 * b, h + 2 * b), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+            assert np.array_equal(out, ref), f"{w}x{h} matrix {k}: {int((out != ref).sum())} bytes differ"
 
 
 @pytest.mark.parametrize("w,h,b", [(1280, 720, 30), (1920, 1080, 50), (3840, 2160, 30), (1920, 1080, 1), (1920, 1080, 300),

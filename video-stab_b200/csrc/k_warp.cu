@@ -385,12 +385,15 @@ static __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
 }
 
 // lanes_mode: one 2-D-like map per lane (maps[z], frame coordinate 0); else one map, frame coordinate z
+// BORDER: the source is the virtual cv::copyMakeBorder frame (border_ pixels of margin, mode bmode_)
+template <bool BORDER>
 __global__ void __launch_bounds__(WT_THREADS, 4)
 k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict__ dmaps, int lanes_mode,
            const LaneDev* __restrict__ lanes, const WarpParams* __restrict__ wps,
            PtrPack srcp, const uint8_t* __restrict__ src0, size_t sframe, size_t sstride, int sw, int sh,
            MutPtrPack dstp, uint8_t* __restrict__ dst0, size_t dframe, int dw, int dh, size_t dstride,
-           int rows_per_cta, int dst_vec, int wp_slot) {
+           int rows_per_cta, int dst_vec, int wp_slot, int border_, int bmode_) {
+    const int border = BORDER ? border_ : 0, bmode = BORDER ? bmode_ : 0;
     extern __shared__ __align__(1024) unsigned char wt_smem[];
     uint32_t* const S_src = reinterpret_cast<uint32_t*>(wt_smem);
     unsigned char* const S_raw = wt_smem + WT_ROWS * WT_TPITCH;
@@ -460,19 +463,24 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
             const int X = (rr.x + cc.x) >> 10, Y = (rr.y + cc.y) >> 10;
             minx = min(minx, X); maxx = max(maxx, X); miny = min(miny, Y); maxy = max(maxy, Y);
         }
-        const int ax0 = minx & ~3;
-        const int ngrp = (maxx + 1 - ax0) / 4 + 1;
+        // (minx..maxx, miny..maxy) are coordinates in the bordered frame (cv::copyMakeBorder, Stabilizer.cpp:981-990);
+        // the frame itself starts at (border, border).  A zero margin is what TMA fills in anyway; for the other
+        // border modes only tiles whose taps all lie inside the frame take the staged path.
+        const int rminx = minx - border, rmaxx = maxx - border, rminy = miny - border, rmaxy = maxy - border;
+        const bool inside = border == 0 || bmode == 0 || (rminx >= 0 && rmaxx + 1 < sw && rminy >= 0 && rmaxy + 1 < sh);
+        const int ax0 = rminx & ~3;
+        const int ngrp = (rmaxx + 1 - ax0) / 4 + 1;
         const int nrows = maxy + 2 - miny;
         const bool row_ok = max(max(abs(rA.x), abs(rB.x)), max(abs(rA.y), abs(rB.y))) < (1 << 26);
-        const bool ok = col_ok && row_ok && minx > -30000 && maxx < 30000 && miny > -30000 && maxy < 30000 &&
+        const bool ok = col_ok && row_ok && inside && minx > -30000 && maxx < 30000 && miny > -30000 && maxy < 30000 &&
                         ngrp <= WT_GRPS && nrows <= WT_ROWS && ngrp > 0 && nrows > 0;
-        const int axT = minx & ~15;                          // TMA box origin: 16 pixels = 48 bytes = 12 words
+        const int axT = rminx & ~15;                         // TMA box origin: 16 pixels = 48 bytes = 12 words
         int* bx = S_box[b];
-        bx[0] = ax0; bx[1] = miny; bx[2] = ngrp; bx[3] = nrows; bx[4] = ok ? 1 : 0; bx[5] = 3 * (ax0 - axT);
+        bx[0] = ax0 + border; bx[1] = miny; bx[2] = ngrp; bx[3] = nrows; bx[4] = ok ? 1 : 0; bx[5] = 3 * (ax0 - axT);
         if (ok) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s_mbar), "r"(WT_ROWS * WT_RAW_PITCH) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                         :: "r"(s_raw), "l"(tmap), "r"(s_mbar), "r"(3 * (axT >> 2)), "r"(miny), "r"(zc) : "memory");
+                         :: "r"(s_raw), "l"(tmap), "r"(s_mbar), "r"(3 * (axT >> 2)), "r"(rminy), "r"(zc) : "memory");
         }
     };
     if (tid == 0) box_and_fetch(ys, 0);
@@ -510,7 +518,10 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
             // generic per-pixel path for this tile
             for (int i = tid; i < WT_W * WT_H; i += WT_THREADS) {
                 const int x = x0 + (i & (WT_W - 1)), y = y0 + i / WT_W;
-                if (x < dw && y < ye) warp_pixel<false>(lanes_mode ? srcp.p[z] : src0 + (size_t)z * sframe, sw, sh, sstride, m, 0, 0, x, y, dst + (size_t)y * dstride + 3 * x);
+                if (x < dw && y < ye) {
+                    const uint8_t* sp = lanes_mode ? srcp.p[z] : src0 + (size_t)z * sframe;
+                    warp_pixel<BORDER>(sp, sw, sh, sstride, m, border, bmode, x, y, dst + (size_t)y * dstride + 3 * x);
+                }
             }
         } else {
             // ---- 3. compute: warp -> rows, lane -> pixels x0 + lane + 32 j
@@ -905,7 +916,8 @@ static bool tma_kernel_ready() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
     if (state[dev] == 0) {
-        cudaError_t e = cudaFuncSetAttribute(k_warp_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_TMA_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_warp_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_TMA_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_TMA_SMEM);
         state[dev] = (e == cudaSuccess && tma_encode_fn()) ? 1 : -1;
         cudaGetLastError();
     }
@@ -933,11 +945,21 @@ static void launch_warp_plain(const LaneDev* lanes, int n_lanes, const PtrPack& 
                 cudaMemcpyAsync(g.d_tmaps, big, sizeof(CUtensorMap) * n_lanes, cudaMemcpyHostToDevice, st);
                 dmaps = (const CUtensorMap*)g.d_tmaps;
             }
-            k_warp_tma<<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, dmaps, 1, lanes, nullptr, src, nullptr, 0, g.src_stride,
-                                                               g.src_w, g.src_h, dst, nullptr, 0, g.out_w, g.out_h, g.out_stride,
-                                                               rows, dv ? 1 : 0, g.wp_slot);
+            if (g.mode == 1 && g.border > 0)
+                k_warp_tma<true><<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, dmaps, 1, lanes, nullptr, src, nullptr, 0, g.src_stride,
+                                                                         g.src_w, g.src_h, dst, nullptr, 0, g.out_w, g.out_h, g.out_stride,
+                                                                         rows, dv ? 1 : 0, g.wp_slot, g.border, g.border_mode);
+            else
+                k_warp_tma<false><<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, dmaps, 1, lanes, nullptr, src, nullptr, 0, g.src_stride,
+                                                                          g.src_w, g.src_h, dst, nullptr, 0, g.out_w, g.out_h, g.out_stride,
+                                                                          rows, dv ? 1 : 0, g.wp_slot, 0, 0);
             return;
         }
+    }
+    if (g.mode == 1) {                                    // no TMA for this geometry: per-pixel kernel
+        dim3 grid((g.out_w + 63) / 64, (g.out_h + 3) / 4, n_lanes);
+        k_warp_lanes<true><<<grid, 256, 0, st>>>(lanes, src, dst, g);
+        return;
     }
     const int rows = strip_rows(g.out_w, g.out_h, n_lanes, WT_MAXT_F);
     dim3 grid((g.out_w + WT_W - 1) / WT_W, (g.out_h + rows - 1) / rows, n_lanes);
@@ -1032,31 +1054,37 @@ int launch_warp(const LaneDev* lanes, int n_lanes, const PtrPack& src, const Mut
                                  dst.p[i], g.out_w, g.out_h, g.out_stride, st);
         return 1 + n_lanes;
     }
-    if (g.mode == 1) {
-        dim3 grid((g.out_w + 63) / 64, (g.out_h + 3) / 4, n_lanes);
-        k_warp_lanes<true><<<grid, 256, 0, st>>>(lanes, src, dst, g);
-    } else {
-        launch_warp_plain(lanes, n_lanes, src, dst, g, st);
-    }
+    launch_warp_plain(lanes, n_lanes, src, dst, g, st);      // mode 0, or mode 1 (copyMakeBorder folded into the source box)
     return 1;
+}
+
+// border > 0: the source is the virtual copyMakeBorder frame (dw, dh = sw + 2 border, sh + 2 border); false when the
+// TMA path is not available (the caller then uses the per-pixel border kernel)
+static bool launch_warp_matrices_border(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe,
+                                        uint8_t* dst, int dw, int dh, size_t dstride, size_t dframe,
+                                        const WarpParams* d_wp, int n_frames, int border, int bmode, cudaStream_t st) {
+    const bool dv = vec_ok(dst, dstride, 4) && dframe % 4 == 0;
+    if (!(tma_kernel_ready() && tma_geometry_ok(src, sw, sstride, sframe, n_frames))) return false;
+    const int rows = strip_rows(dw, dh, n_frames, WT_MAXT);
+    dim3 grid((dw + WT_W - 1) / WT_W, (dh + rows - 1) / rows, n_frames);
+    TmapPack pack;
+    if (!tma_make_map(pack.m, src, sw, sh, sstride, sframe, n_frames)) return false;
+    PtrPack sp{};
+    MutPtrPack dp{};
+    if (border > 0)
+        k_warp_tma<true><<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, nullptr, 0, nullptr, d_wp, sp, src, sframe, sstride, sw, sh, dp,
+                                                                 dst, dframe, dw, dh, dstride, rows, dv ? 1 : 0, 0, border, bmode);
+    else
+        k_warp_tma<false><<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, nullptr, 0, nullptr, d_wp, sp, src, sframe, sstride, sw, sh, dp,
+                                                                  dst, dframe, dw, dh, dstride, rows, dv ? 1 : 0, 0, 0, 0);
+    return true;
 }
 
 void launch_warp_matrices(const uint8_t* src, int sw, int sh, size_t sstride, size_t sframe,
                           uint8_t* dst, int dw, int dh, size_t dstride, size_t dframe,
                           const WarpParams* d_wp, int n_frames, cudaStream_t st) {
     const bool sv = vec_ok(src, sstride, 4) && sframe % 4 == 0, dv = vec_ok(dst, dstride, 4) && dframe % 4 == 0;
-    if (tma_kernel_ready() && tma_geometry_ok(src, sw, sstride, sframe, n_frames)) {
-        const int rows = strip_rows(dw, dh, n_frames, WT_MAXT);
-        dim3 grid((dw + WT_W - 1) / WT_W, (dh + rows - 1) / rows, n_frames);
-        TmapPack pack;
-        if (tma_make_map(pack.m, src, sw, sh, sstride, sframe, n_frames)) {
-            PtrPack sp{};
-            MutPtrPack dp{};
-            k_warp_tma<<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, nullptr, 0, nullptr, d_wp, sp, src, sframe, sstride, sw, sh, dp,
-                                                               dst, dframe, dw, dh, dstride, rows, dv ? 1 : 0, 0);
-            return;
-        }
-    }
+    if (launch_warp_matrices_border(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp, n_frames, 0, 0, st)) return;
     const int rows = strip_rows(dw, dh, n_frames, WT_MAXT_F);
     dim3 grid((dw + WT_W - 1) / WT_W, (dh + rows - 1) / rows, n_frames);
     k_warp_tiled_frames<<<grid, WT_THREADS, 0, st>>>(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp, rows,
@@ -1082,6 +1110,8 @@ int launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride, 
         launch_warp_matrices(src, sw, sh, sstride, sframe, dst, sw, sh, dstride, dframe, d_wp, n_frames, st);
     } else if (mode == 1) {
         const int dw = sw + 2 * border, dh = sh + 2 * border;
+        if (launch_warp_matrices_border(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp, n_frames, border, border_mode, st))
+            return 1;
         dim3 grid((dw + 63) / 64, (dh + 3) / 4, n_frames);
         k_warp_frames_border<<<grid, 256, 0, st>>>(src, sw, sh, sstride, sframe, dst, dw, dh, dstride, dframe, d_wp, border, border_mode);
     } else {
