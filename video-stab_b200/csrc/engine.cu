@@ -119,10 +119,15 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     // corner detection.  adaptive_smoothing reads one int back per frame, so that mode stays on one stream.
     multi_ = !p.adaptive_smoothing;
     if (multi_) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&sA_, cudaStreamNonBlocking));
-        for (auto& st : sC_) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&sP_, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&sM_, cudaStreamNonBlocking));
+        // The analysis kernels are small and latency-critical (a single CTA for k_motion / k_select), the warp is one
+        // machine-filling grid: the analysis streams get the higher priority so their CTAs are placed first whenever
+        // a warp CTA retires, instead of queueing behind the rest of the warp grid.
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&sA_, cudaStreamNonBlocking, prio_hi));
+        for (auto& st : sC_) CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&sP_, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&sM_, cudaStreamNonBlocking, prio_hi));
         for (auto& ev : evS_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evW_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : evP_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));

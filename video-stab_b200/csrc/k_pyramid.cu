@@ -71,6 +71,32 @@ static __device__ __forceinline__ uint32_t gray4_from_sums(const uint32_t* sb, c
     return out;
 }
 
+// four horizontally adjacent level-0 pixels (x % 4 == 0) as one 32-bit store, plus their BORDER_REFLECT_101 images in the
+// level's materialised frame (rows: whole words; columns: bytes)
+static __device__ __forceinline__ void store4_with_mirrors(const GrayLevel& lv, int x, int y, uint32_t v) {
+    uint8_t* row_ptr = lv.base + (ptrdiff_t)y * lv.pitch;
+    *reinterpret_cast<uint32_t*>(row_ptr + x) = v;
+    int ym = INT_MIN;
+    if (y >= 1 && y <= VS_PAD) ym = -y;
+    else if (y >= lv.h - 1 - VS_PAD && y <= lv.h - 2) ym = 2 * (lv.h - 1) - y;
+    uint8_t* mrow_ptr = lv.base + (ptrdiff_t)(ym == INT_MIN ? y : ym) * lv.pitch;
+    if (ym != INT_MIN) *reinterpret_cast<uint32_t*>(mrow_ptr + x) = v;
+    if (x <= VS_PAD || x + 3 >= lv.w - 1 - VS_PAD) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xx = x + k;
+            int xm = INT_MIN;
+            if (xx >= 1 && xx <= VS_PAD) xm = -xx;
+            else if (xx >= lv.w - 1 - VS_PAD && xx <= lv.w - 2) xm = 2 * (lv.w - 1) - xx;
+            if (xm != INT_MIN) {
+                const uint8_t b = (uint8_t)(v >> (8 * k));
+                row_ptr[xm] = b;
+                if (ym != INT_MIN) mrow_ptr[xm] = b;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_gray_half(const LaneDev* __restrict__ lanes, PtrPack src, size_t stride, int slot) {
     const LaneDev& L = lanes[blockIdx.z];
     const GrayLevel lv = L.pyr[slot].lv[0];
@@ -101,29 +127,43 @@ __global__ void __launch_bounds__(256) k_gray_half(const LaneDev* __restrict__ l
             sr[2 * g + 1] = __dp4a(w2, 0x01000001u, sr[2 * g + 1]);                           // R2 + R3
         }
     }
-    const uint32_t v = gray4_from_sums(sb, sg, sr);
-    uint8_t* row_ptr = lv.base + (ptrdiff_t)y * lv.pitch;
-    *reinterpret_cast<uint32_t*>(row_ptr + x) = v;
-    // reflect-101 frame: mirror rows ym (at most one per pixel row), mirror columns xm
-    int ym = INT_MIN;
-    if (y >= 1 && y <= VS_PAD) ym = -y;
-    else if (y >= lv.h - 1 - VS_PAD && y <= lv.h - 2) ym = 2 * (lv.h - 1) - y;
-    uint8_t* mrow_ptr = lv.base + (ptrdiff_t)(ym == INT_MIN ? y : ym) * lv.pitch;
-    if (ym != INT_MIN) *reinterpret_cast<uint32_t*>(mrow_ptr + x) = v;
-    if (x <= VS_PAD || x + 3 >= lv.w - 1 - VS_PAD) {
+    store4_with_mirrors(lv, x, y, gray4_from_sums(sb, sg, sr));
+}
+
+// ---------------------------------------------------------------- exact-4x fast path (2160p -> 960x540)
+// cv::resize INTER_LINEAR at scale 4 samples at 4 x + 1.5: coefficients (1024, 1024) on source pixels 4x+1, 4x+2 of rows
+// 4y+1, 4y+2, i.e. the rounded mean of the centre 2x2 of every 4x4 block (oracle/cv_models.py resize_linear; the
+// >>4, >>16 truncations of the vertical pass are exact for these coefficients).  One thread = 4 output pixels = 48
+// source bytes x 2 rows as three 128-bit loads per row (a warp reads 1536 contiguous bytes per row); the channel
+// sums come off the packed words with DP4A byte-select masks as in k_gray_half.
+__global__ void __launch_bounds__(256) k_gray_quarter(const LaneDev* __restrict__ lanes, PtrPack src, size_t stride, int slot) {
+    const LaneDev& L = lanes[blockIdx.z];
+    const GrayLevel lv = L.pyr[slot].lv[0];
+    const int per_row = lv.w >> 2;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= per_row * lv.h) return;
+    const int y = id / per_row, x = (id - y * per_row) << 2;
+    const uint4* r0 = reinterpret_cast<const uint4*>(src.p[blockIdx.z] + (size_t)(4 * y + 1) * stride + 12 * x);
+    const uint4* r1 = reinterpret_cast<const uint4*>(src.p[blockIdx.z] + (size_t)(4 * y + 2) * stride + 12 * x);
+    uint4 a[3], b[3];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int xx = x + k;
-            int xm = INT_MIN;
-            if (xx >= 1 && xx <= VS_PAD) xm = -xx;
-            else if (xx >= lv.w - 1 - VS_PAD && xx <= lv.w - 2) xm = 2 * (lv.w - 1) - xx;
-            if (xm != INT_MIN) {
-                const uint8_t b = (uint8_t)(v >> (8 * k));
-                row_ptr[xm] = b;
-                if (ym != INT_MIN) mrow_ptr[xm] = b;
-            }
+    for (int k = 0; k < 3; ++k) { a[k] = __ldg(r0 + k); b[k] = __ldg(r1 + k); }
+    uint32_t sb[4], sg[4], sr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // output pixel k = 12 bytes = words 3k .. 3k+2 of the 12-word row segment: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+        uint32_t w0[2], w1[2], w2[2];
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+            const uint4* v = row ? b : a;
+            const uint32_t words[12] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w, v[2].x, v[2].y, v[2].z, v[2].w};
+            w0[row] = words[3 * k]; w1[row] = words[3 * k + 1]; w2[row] = words[3 * k + 2];
         }
+        sb[k] = __dp4a(w1[1], 0x00010000u, __dp4a(w0[1], 0x01000000u, __dp4a(w1[0], 0x00010000u, __dp4a(w0[0], 0x01000000u, 0u))));   // B1 + B2
+        sg[k] = __dp4a(w1[1], 0x01000001u, __dp4a(w1[0], 0x01000001u, 0u));                                                             // G1 + G2
+        sr[k] = __dp4a(w2[1], 0x00000001u, __dp4a(w1[1], 0x00000100u, __dp4a(w2[0], 0x00000001u, __dp4a(w1[0], 0x00000100u, 0u))));   // R1 + R2
     }
+    store4_with_mirrors(lv, x, y, gray4_from_sums(sb, sg, sr));
 }
 
 void launch_gray_resize(const LaneDev* lanes, int n_lanes, const PtrPack& src, int w, int h, size_t stride,
@@ -133,9 +173,14 @@ void launch_gray_resize(const LaneDev* lanes, int n_lanes, const PtrPack& src, i
     double sx = 1.0 / ((double)aw / (double)w), sy = 1.0 / ((double)ah / (double)h);
     bool aligned = slot >= 0 && stride % 8 == 0 && aw % 4 == 0;
     for (int i = 0; i < n_lanes; ++i) aligned = aligned && ((uintptr_t)src.p[i] % 8 == 0);
+    bool aligned16 = aligned && stride % 16 == 0;
+    for (int i = 0; i < n_lanes; ++i) aligned16 = aligned16 && ((uintptr_t)src.p[i] % 16 == 0);
     if (w == 2 * aw && h == 2 * ah && aligned) {
         dim3 g2(((aw / 4) * ah + 255) / 256, 1, n_lanes);
         k_gray_half<<<g2, 256, 0, st>>>(lanes, src, stride, slot);
+    } else if (w == 4 * aw && h == 4 * ah && aligned16) {
+        dim3 g2(((aw / 4) * ah + 255) / 256, 1, n_lanes);
+        k_gray_quarter<<<g2, 256, 0, st>>>(lanes, src, stride, slot);
     } else if (w == 2 * aw && h == 2 * ah)
         k_gray_resize<0><<<grid, 128, 0, st>>>(lanes, src, w, h, stride, slot, sx, sy);
     else

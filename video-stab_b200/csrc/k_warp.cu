@@ -489,28 +489,29 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
     int buf = 0;
     uint32_t phase = 0;
     for (int y0 = ys; y0 < ye; y0 += WT_H, buf ^= 1) {
-        const int ax0 = S_box[buf][0], by0 = S_box[buf][1], ngrp = S_box[buf][2], nrows = S_box[buf][3];
+        const int ax0 = S_box[buf][0], by0 = S_box[buf][1], nrows = S_box[buf][3];
         const bool ok = S_box[buf][4] != 0;
         const bool more = y0 + WT_H < ye;
         if (ok) {
             // ---- 2. wait for the raw box, re-pack it: one task = 16 raw bytes -> 4 words [B G R R']
             mbar_wait(s_mbar, phase);
             phase ^= 1;
-            const bool colok = q < ngrp && r7 < WT_TSROWS;
+            // No per-thread row / column test: TMA always delivers the full 42 x 480-byte box, so rows beyond nrows
+            // and column groups beyond ngrp are re-packed too (never read as taps) — cheaper than the predicates.
             const uint32_t s_rawq = s_rawt + (uint32_t)S_box[buf][5];
+            if (tid < WT_TGRPS * WT_TSROWS) {
 #define WT_REPACK(k)                                                                                           \
-            if ((k) * WT_TSROWS < nrows) {                               /* CTA-uniform */                      \
-                if (colok && r7 + (k) * WT_TSROWS < nrows) {                                                    \
+                if ((k) * WT_TSROWS < nrows) {                           /* CTA-uniform */                      \
                     const uint32_t w0 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH>(s_rawq);                          \
                     const uint32_t w1 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 4>(s_rawq);                      \
                     const uint32_t w2 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 8>(s_rawq);                      \
                     const uint32_t w3 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 12>(s_rawq);                     \
                     const uint4 o = repack_bgrr(w0, w1, w2, w3);                                               \
                     sts128<(k) * WT_TSROWS * WT_TPITCH>(s_stage, o.x, o.y, o.z, o.w);                       \
-                }                                                                                              \
-            }
-            WT_REPACK(0) WT_REPACK(1) WT_REPACK(2) WT_REPACK(3) WT_REPACK(4) WT_REPACK(5) WT_REPACK(6)
+                }
+                WT_REPACK(0) WT_REPACK(1) WT_REPACK(2) WT_REPACK(3) WT_REPACK(4) WT_REPACK(5) WT_REPACK(6)
 #undef WT_REPACK
+            }
         }
         __syncthreads();                                   // S_src ready, raw box free
         if (tid == 0 && more) box_and_fetch(y0 + WT_H, buf ^ 1);      // overlaps this tile's compute
@@ -721,7 +722,7 @@ k_warp_zoom_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __rest
     int buf = 0;
     uint32_t phase = 0;
     for (int y0 = ys; y0 < ye; y0 += ZT_H, buf ^= 1) {
-        const int ax0 = S_box[buf][0], by0 = S_box[buf][1], ngrp = S_box[buf][2], nrows = S_box[buf][3];
+        const int ax0 = S_box[buf][0], by0 = S_box[buf][1], nrows = S_box[buf][3];
         const bool ok = S_box[buf][4] != 0;
         const bool more = y0 + ZT_H < ye;
         const int orows = min(ZT_H, ye - y0);                                   // output rows of this tile
@@ -729,21 +730,22 @@ k_warp_zoom_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __rest
         if (ok) {
             mbar_wait(s_mbar, phase);
             phase ^= 1;
-            const bool colok = q < ngrp && r7 < WT_TSROWS;
+            // No per-thread row / column test: TMA always delivers the full 42 x 480-byte box, so rows beyond nrows
+            // and column groups beyond ngrp are re-packed too (never read as taps) — cheaper than the predicates.
             const uint32_t s_rawq = s_rawt + (uint32_t)S_box[buf][5];
+            if (tid < WT_TGRPS * WT_TSROWS) {
 #define WT_REPACK(k)                                                                                           \
-            if ((k) * WT_TSROWS < nrows) {                               /* CTA-uniform */                      \
-                if (colok && r7 + (k) * WT_TSROWS < nrows) {                                                    \
+                if ((k) * WT_TSROWS < nrows) {                           /* CTA-uniform */                      \
                     const uint32_t w0 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH>(s_rawq);                          \
                     const uint32_t w1 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 4>(s_rawq);                      \
                     const uint32_t w2 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 8>(s_rawq);                      \
                     const uint32_t w3 = lds32<(k) * WT_TSROWS * WT_RAW_PITCH + 12>(s_rawq);                     \
                     const uint4 o = repack_bgrr(w0, w1, w2, w3);                                               \
                     sts128<(k) * WT_TSROWS * WT_TPITCH>(s_stage, o.x, o.y, o.z, o.w);                       \
-                }                                                                                              \
-            }
-            WT_REPACK(0) WT_REPACK(1) WT_REPACK(2) WT_REPACK(3) WT_REPACK(4) WT_REPACK(5) WT_REPACK(6)
+                }
+                WT_REPACK(0) WT_REPACK(1) WT_REPACK(2) WT_REPACK(3) WT_REPACK(4) WT_REPACK(5) WT_REPACK(6)
 #undef WT_REPACK
+            }
         }
         __syncthreads();                                   // S_src ready, raw box free, previous tile's stage B done
         if (more) {
