@@ -205,6 +205,9 @@ vs_status vs_stabilizer_launch_count(vs_stabilizer* s, uint64_t* n);
  * vs_*_stage_time synchronises and returns the summed duration and launch-group count since enabling. */
 vs_status vs_stabilizer_set_timing(vs_stabilizer* s, int enable);
 vs_status vs_stabilizer_stage_time(vs_stabilizer* s, int stage, double* total_ms, long long* count);
+/* Diagnostics: the timeline of the stage launches timed since the previous query, as (stage, start us, end us) float
+ * triples relative to the first of them; *n = number of triples available (at most `capacity` are written). */
+vs_status vs_stabilizer_trace(vs_stabilizer* s, float* out, int capacity, int* n);
 
 /* ---- offline clip mode: one temporal chunk of a long clip per handle / GPU (BASELINE config 5) -----------
  * The reference has no such mode (it is single-stream, single-process); results are defined as "identical to

@@ -257,6 +257,14 @@ vs_status vs_stabilizer_stage_time(vs_stabilizer* s, int stage, double* total_ms
     s->eng->stage_time(stage, total_ms, count);
     return VS_OK;
 }
+vs_status vs_stabilizer_trace(vs_stabilizer* s, float* out, int capacity, int* n) {
+    if (!s || !n) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    const std::vector<float>& t = s->eng->trace();
+    const int m = (int)(t.size() / 3);
+    *n = m;
+    if (out) memcpy(out, t.data(), sizeof(float) * 3 * (size_t)(m < capacity ? m : capacity));
+    return VS_OK;
+}
 vs_status vs_batch_set_timing(vs_batch* b, int enable) {
     if (!b) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
     b->eng->set_timing(enable != 0);

@@ -42,11 +42,16 @@ void Engine::add_pending(int stage, cudaEvent_t a, cudaEvent_t b) {
 void Engine::collect_timing() {
     if (pending_.empty()) return;
     sync();
+    trace_.clear();
     for (auto& p : pending_) {
-        float ms = 0.f;
+        float ms = 0.f, t0 = 0.f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { stage_ms_[p.stage] += ms; stage_n_[p.stage] += 1; }
-        event_pool_.push_back(p.a); event_pool_.push_back(p.b);
+        // timeline of the last collected batch, relative to its first event (diagnostics: vs_stabilizer_trace)
+        if (cudaEventElapsedTime(&t0, pending_.front().a, p.a) == cudaSuccess) {
+            trace_.push_back((float)p.stage); trace_.push_back(t0 * 1e3f); trace_.push_back((t0 + ms) * 1e3f);
+        }
     }
+    for (auto& p : pending_) { event_pool_.push_back(p.a); event_pool_.push_back(p.b); }
     pending_.clear();
 }
 void Engine::set_timing(bool on) {

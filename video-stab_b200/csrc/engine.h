@@ -67,6 +67,7 @@ public:
     cudaEvent_t take_event();
     void add_pending(int stage, cudaEvent_t a, cudaEvent_t b);
     void collect_timing();
+    const std::vector<float>& trace() { collect_timing(); return trace_; }
 
     // single-op helpers behind the vs_k_* entry points (lane 0 scratch)
     const LaneDev* d_lanes() const { return d_lanes_; }
@@ -144,6 +145,7 @@ private:
     bool timing_ = false;
     std::vector<cudaEvent_t> event_pool_;
     std::vector<Pending> pending_;
+    std::vector<float> trace_;           // (stage, start us, end us) of the last collected timing batch
     double stage_ms_[VS_N_STAGES] = {};
     long long stage_n_[VS_N_STAGES] = {};
 };

@@ -312,6 +312,14 @@ class Stabilizer:
     def stage_times(self) -> dict:
         return _stage_times(None, lib.vs_stabilizer_stage_time, self._h)
 
+    def trace(self, capacity: int = 65536):
+        """(n, 3) float32 array of (stage, start us, end us) for the stage launches timed since the last query."""
+        import ctypes as C
+        buf = (C.c_float * (3 * capacity))()
+        n = C.c_int()
+        check(lib.vs_stabilizer_trace(self._h, buf, capacity, C.byref(n)))
+        return np.frombuffer(buf, np.float32, 3 * min(n.value, capacity)).reshape(-1, 3).copy()
+
 
 STAGES = ("resize_gray", "pyrdown", "pyr_lk", "motion", "gftt", "warp")
 
