@@ -171,7 +171,10 @@ vs_status vs_stabilizer_clean(vs_stabilizer* s);
  * handle's device.  Asynchronous on the handle's stream; call vs_stabilizer_sync() before reading
  * d_out.  flags: VS_PUSH_BORROW — the caller keeps d_bgr alive and unmodified until the output of
  * that frame has been produced (the reference itself queues frames without cloning them,
- * Stabilizer.cpp:376); without it the frame is copied into an internal ring. */
+ * Stabilizer.cpp:376); without it the frame is copied into an internal ring.
+ * The handle's streams are non-blocking: they do NOT order against the caller's streams.  d_bgr must be complete
+ * when the call is made — either synchronise its producer, or record a cudaEvent_t after the producer and hand it
+ * to vs_stabilizer_wait_event() first (stream-ordered hand-off from a decoder, no host synchronisation). */
 #define VS_PUSH_BORROW 1u
 vs_status vs_stabilizer_push_device(vs_stabilizer* s, const uint8_t* d_bgr, int width, int height, size_t stride,
                                     uint8_t* d_out, size_t out_stride, size_t out_capacity, unsigned flags,
@@ -179,6 +182,8 @@ vs_status vs_stabilizer_push_device(vs_stabilizer* s, const uint8_t* d_bgr, int 
 vs_status vs_stabilizer_flush_device(vs_stabilizer* s, uint8_t* d_out, size_t out_stride, size_t out_capacity,
                                      int* out_width, int* out_height, int* produced);
 vs_status vs_stabilizer_sync(vs_stabilizer* s);
+/* Everything pushed after this call waits (on the device) for `cuda_event` (a cudaEvent_t as void*). */
+vs_status vs_stabilizer_wait_event(vs_stabilizer* s, void* cuda_event);
 /* cudaStream_t of the handle (as void*), so callers can time/order work on it.  A handle runs its analysis and
  * corner-detection kernels on two further internal streams; every OUTPUT frame is produced on this public
  * stream.  vs_stabilizer_join() makes the public stream wait for everything enqueued so far on the internal

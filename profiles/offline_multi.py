@@ -40,6 +40,7 @@ first, count = offline.chunk_bounds(n, world, rank)
 hl = offline.halo(first)
 mine = frames(first - hl, first + count)
 out = torch.empty((count, H, W, 3), dtype=torch.uint8, device=dev)
+torch.cuda.synchronize()        # the handle's streams do not order against torch's stream: the frames must be complete
 st = vsb.Stabilizer(params, device=local)
 
 
@@ -71,8 +72,14 @@ if rank == 0:
     # reference: the whole clip on this GPU in one chunk
     st1 = vsb.Stabilizer(params, device=local)
     full = frames(0, n)
+    torch.cuda.synchronize()
     tr1 = offline.analyze_chunk(st1, full.data_ptr(), W, H, 0, n)
     ok_tr = bool(np.array_equal(tr1.view(np.uint32), tr.view(np.uint32)))
+    if not ok_tr:
+        bad = np.nonzero((tr1.view(np.uint32) != tr.view(np.uint32)).any(axis=1))[0]
+        print("transform rows that differ:", bad[:16], "of", len(bad), "chunk size", offline.chunk_bounds(n, world, 0)[1], file=sys.stderr)
+        for i in bad[:4]:
+            print(i, tr1[i], tr[i], file=sys.stderr)
     ref_out = torch.empty_like(full)
     offline.render_chunk(st1, tr1, n, full.data_ptr(), W, H, 0, n, ref_out.data_ptr())
     ok_frames = True

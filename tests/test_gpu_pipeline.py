@@ -347,3 +347,37 @@ def test_async_device_pipeline_is_deterministic(vsb, borrow):
         assert k == n
         got = [zlib.crc32(f.tobytes()) for f in d_out.cpu().numpy()]
         assert got == want, f"rep {rep}: frames {[i for i in range(n) if got[i] != want[i]][:8]} differ"
+
+
+def test_wait_event_orders_frames_produced_on_another_stream(vsb):
+    """Stream-ordered hand-off (vs_stabilizer_wait_event): frames written by a slow producer on another CUDA stream
+    are pushed without any host synchronisation; the handle's streams wait for the producer's event."""
+    w, h, n = 640, 360, 24
+    clip = vsb.synth.make_clip(w, h, n, 77)
+    params = vsb.Parameters(smoothingRadius=5)
+    ref, _ = _run(vsb, clip, params)
+    d_clip = torch.from_numpy(clip).cuda()
+    fb = h * w * 3
+    prod = torch.cuda.Stream()
+    ballast = torch.randn((4096, 4096), device="cuda")
+    staged = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    st = vsb.Stabilizer(params)
+    k = 0
+    for i in range(n):
+        with torch.cuda.stream(prod):
+            ballast = ballast @ ballast * 1e-4            # a few hundred microseconds ahead of the frame copy
+            staged[i].copy_(d_clip[i], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(prod)
+        st.wait_event(ev.cuda_event)
+        if st.push_device(staged[i].data_ptr(), w, h, w * 3, d_out[k].data_ptr(), w * 3, fb, borrow=True) is not None:
+            k += 1
+    while st.flush_device(d_out[min(k, n - 1)].data_ptr(), w * 3, fb) is not None:
+        k += 1
+    st.sync()
+    assert k == n == len(ref)
+    got = d_out.cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(got[i], ref[i]), f"frame {i}"

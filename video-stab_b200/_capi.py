@@ -77,6 +77,7 @@ SYMBOLS = {
     "vs_stabilizer_set_timing": (_I, [_P, _I]),
     "vs_stabilizer_stage_time": (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "vs_batch_set_timing": (_I, [_P, _I]),
+    "vs_stabilizer_wait_event": (_I, [_P, _P]),
     "vs_stabilizer_trace": (_I, [_P, C.POINTER(C.c_float), _I, C.POINTER(C.c_int)]),
     "vs_batch_stage_time": (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "vs_clip_halo": (_I, [_I]),

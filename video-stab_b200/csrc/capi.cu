@@ -219,6 +219,10 @@ vs_status vs_stabilizer_flush_device(vs_stabilizer* s, uint8_t* d_out, size_t ou
     API_END
 }
 vs_status vs_stabilizer_sync(vs_stabilizer* s) { return s ? s->eng->sync() : vs_set_error(VS_ERR_INVALID_ARG, "null handle"); }
+vs_status vs_stabilizer_wait_event(vs_stabilizer* s, void* cuda_event) {
+    if (!s || !cuda_event) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    return s->eng->wait_external((cudaEvent_t)cuda_event);
+}
 vs_status vs_stabilizer_join(vs_stabilizer* s) { return s ? s->eng->join() : vs_set_error(VS_ERR_INVALID_ARG, "null handle"); }
 void* vs_stabilizer_stream(vs_stabilizer* s) { return s ? (void*)s->eng->stream() : nullptr; }
 vs_status vs_stabilizer_counts(vs_stabilizer* s, int* nf, int* no) {

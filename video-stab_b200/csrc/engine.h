@@ -69,6 +69,14 @@ public:
     void collect_timing();
     const std::vector<float>& trace() { collect_timing(); return trace_; }
 
+    // every stream that reads caller frames (pyramid, warp, ring / host copy-in) waits for a caller event
+    vs_status wait_external(cudaEvent_t ev) {
+        if (cudaStreamWaitEvent(stream_, ev, 0) != cudaSuccess) return vs_set_cuda_error(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+        if (multi_ && cudaStreamWaitEvent(sP_, ev, 0) != cudaSuccess) return vs_set_cuda_error(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+        if (sH_ && cudaStreamWaitEvent(sH_, ev, 0) != cudaSuccess) return vs_set_cuda_error(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+        return VS_OK;
+    }
+
     // single-op helpers behind the vs_k_* entry points (lane 0 scratch)
     const LaneDev* d_lanes() const { return d_lanes_; }
     const LaneDev& h_lane(int i) const { return h_lanes_[i]; }

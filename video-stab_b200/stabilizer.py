@@ -312,6 +312,11 @@ class Stabilizer:
     def stage_times(self) -> dict:
         return _stage_times(None, lib.vs_stabilizer_stage_time, self._h)
 
+    def wait_event(self, cuda_event: int) -> None:
+        """Frames pushed after this call wait on the device for `cuda_event` (a cudaEvent_t handle, e.g.
+        torch.cuda.Event().cuda_event): stream-ordered hand-off of frames produced on another stream."""
+        check(lib.vs_stabilizer_wait_event(self._h, C.c_void_p(cuda_event)))
+
     def trace(self, capacity: int = 65536):
         """(n, 3) float32 array of (stage, start us, end us) for the stage launches timed since the last query."""
         import ctypes as C
