@@ -53,17 +53,33 @@ def _peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs: NVML from a thread (a sample every ~2 ms,
+    so even a 30 ms region at N = 8 is covered), nvidia-smi -lms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
         self.rows = []
         self.proc = None
         self.index = index
+        self.nvml = None
+        self.stop_flag = False
+        self.sm, self.mask, self.sm_max = [], 0, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
@@ -73,11 +89,28 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(reasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max,
+                    "reasons": [n for n, b in self.BITS if self.mask & b], "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -91,7 +124,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 def _pingpong(n):
@@ -165,8 +198,38 @@ def cpu_baseline_sample(seconds_budget=12.0):
                       f"{cv2.__version__}, optimized paths on, {cores} threads), wall clock"}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the host cores of the NUMA node the GPU hangs off (sysfs; no numactl in the image), so the
+    page-locked frame buffers allocated afterwards are first-touched on that node and the enqueue thread stays near the
+    GPU.  Matters for the host-buffer (e2e) leg at N > 1, where every rank streams ~2 x 40 GB/s over PCIe."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                               # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        before = os.sched_getaffinity(0)
+        allowed = sorted(set(cpus) & set(before))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed), "_restore": sorted(before)}
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_gpu(args, rank, world, local_rank):
+    numa = bind_to_gpu_numa_node(local_rank)
+    all_cpus = numa.pop("_restore") if numa else None
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -359,7 +422,8 @@ def run_gpu(args, rank, world, local_rank):
                                    "at N>1 one independent stream per GPU (configs[3] sharding, no collective)",
                        "frames_per_step": FRAMES_PER_STEP, "gftt": "200 pts every 2nd frame", "lk": "15x15, 3 levels",
                        "l2_policy": "inputs larger than L2 (64-frame clip = 398 MB, frames read in place)",
-                       "api": "vs_stabilizer_push_device (borrowed device frames), one frame per call"},
+                       "api": "vs_stabilizer_push_device (borrowed device frames), one frame per call",
+                       "host_numa_binding": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": frame_bytes * FRAMES_PER_STEP,
                     "d2h_bytes_per_step": frame_bytes * FRAMES_PER_STEP,
                     "api": "vs_stabilizer_push_many: 64 page-locked host frames in, 64 host frames out per call "
@@ -380,6 +444,12 @@ def run_gpu(args, rank, world, local_rank):
                                  "algorithmic_bytes_per_launch": pyr_bytes, "ms_per_launch": pyr_ms},
         }
         if world == 1 and not args.no_cpu_baseline:
+            if all_cpus:                                   # the CPU baseline gets every host core back (all threads)
+                for tid in os.listdir("/proc/self/task"):
+                    try:
+                        os.sched_setaffinity(int(tid), all_cpus)
+                    except OSError:
+                        pass
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)
     if world > 1:
