@@ -19,13 +19,17 @@ def step(k):
         pos += 1
 step(200); st.sync()
 st.set_timing(True)
-step(40)
+step(int(os.environ.get("TL_FRAMES", "40")))
 tr = st.trace()
 names = ["gray", "pyrdown", "lk", "motion", "gftt", "warp"]
 t0 = tr[len(tr) // 2, 1]
-for s, a, b in tr[len(tr) // 2: len(tr) // 2 + 40]:
-    print(f"{names[int(s)]:8s} {a - t0:8.1f} -> {b - t0:8.1f}  ({b - a:5.1f} us)")
+if not os.environ.get("VS_TRACE_STAGE"):
+    for s, a, b in tr[len(tr) // 2: len(tr) // 2 + 40]:
+        print(f"{names[int(s)]:8s} {a - t0:8.1f} -> {b - t0:8.1f}  ({b - a:5.1f} us)")
 for k, nm in enumerate(names):
     sel = tr[tr[:, 0] == k]
     if len(sel) > 2:
-        print(f"{nm:8s} n={len(sel):3d} mean {np.mean(sel[:, 2] - sel[:, 1]):6.1f} us, period {np.mean(np.diff(sel[:, 1])):6.1f} us")
+        d = sel[:, 2] - sel[:, 1]
+        gap = sel[1:, 1] - sel[:-1, 2]
+        print(f"{nm:8s} n={len(sel):3d} duration mean {d.mean():6.1f} min {d.min():6.1f} max {d.max():6.1f} us, period {np.mean(np.diff(sel[:, 1])):6.1f} us, "
+              f"idle gap before next mean {gap.mean():6.1f} us")

@@ -451,7 +451,7 @@ vs_status vs_k_good_features(const uint8_t* d_gray, int w, int h, int max_corner
     const int slot = (w == VS_FW) ? -1 : 0;
     launch_pack_level(d_gray, slot < 0 ? L.small0 : L.pyr[0].lv[0], st);
     e->reset_detect_counters();
-    launch_good_features(e->d_lanes(), 1, slot, max_corners, quality, min_dist, 0, 0, st);
+    launch_good_features(e->d_lanes(), 1, slot, max_corners, quality, min_dist, 0, 0, 0, st);
     int n = 0;
     cudaError_t ce = cudaMemcpyAsync(&n, L.kp_count, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);

@@ -12,6 +12,8 @@
 #define VS_WIN 15            // LK window (Stabilizer.cpp:616)
 #define VS_PYR_SLOTS 6       // pyramids kept per lane (frames n-1, n for LK + 4 frames of run-ahead)
 #define VS_LEVELS 3          // maxLevel 2 (Stabilizer.cpp:617)
+#define VS_KP_SLOTS 4        // key-point buffers (LaneDev::kpb / kpc), by (detection frame / 2) % VS_KP_SLOTS
+#define VS_LK_SLOTS 4        // tracker output buffers (LaneDev::lkn / lks), by frame % VS_LK_SLOTS
 #define VS_AW 960            // analysis size (Stabilizer.cpp:410)
 #define VS_AH 540
 #define VS_FW 480            // first-frame analysis size (Stabilizer.cpp:277)
@@ -59,10 +61,10 @@ struct LaneDev {
     uint8_t* lk_status;
     // double-buffered copies so that detection / tracking / motion of neighbouring frames can overlap on
     // different CUDA streams (engine.cu): key points by detection generation, tracker output by frame parity
-    float2* kpb[2];
-    int* kpc[2];
-    float2* lkn[2];
-    uint8_t* lks[2];
+    float2* kpb[VS_KP_SLOTS];       // key points by detection index % VS_KP_SLOTS: a detection may finish while the motion
+    int* kpc[VS_KP_SLOTS];          // kernel two detections back still reads its slot
+    float2* lkn[VS_LK_SLOTS];       // tracker output by frame % VS_LK_SLOTS: LK(n) may run while motion(n-3) still reads its slot
+    uint8_t* lks[VS_LK_SLOTS];
     uint8_t* inlier_mask;
     float* transforms;              // 3 floats per frame  (transforms_)
     float* path;                    // 3 floats per frame  (path_)
@@ -128,14 +130,14 @@ struct DetView {
     float2* kp;
     int* kp_count;
 };
-static __device__ __forceinline__ DetView det_view(const LaneDev& L, int gen) {
+static __device__ __forceinline__ DetView det_view(const LaneDev& L, int gen, int kp_slot) {
     DetView v;
     v.eig_max = gen ? L.eig_max2 : L.eig_max;
     v.cand = gen ? L.cand2 : L.cand;
     v.cand_count = gen ? L.cand_count2 : L.cand_count;
     v.grid = gen ? L.grid2 : L.grid;
-    v.kp = gen ? L.kpb[1] : L.kpb[0];
-    v.kp_count = gen ? L.kpc[1] : L.kpc[0];
+    v.kp = L.kpb[kp_slot];
+    v.kp_count = L.kpc[kp_slot];
     return v;
 }
 

@@ -25,7 +25,14 @@ extern "C" const char* vs_last_error(void) { return g_err; }
 // ---- optional per-stage CUDA-event timing (bench / profiles); off by default
 struct StageScope {
     Engine* e; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
-    StageScope(Engine* e_, int s, cudaStream_t st_) : e(e_), stage(s), st(st_) { if (e->timing_on()) { a = e->take_event(); b = e->take_event(); cudaEventRecord(a, st); } }
+    StageScope(Engine* e_, int s, cudaStream_t st_) : e(e_), stage(s), st(st_) {
+        if (e->timing_on() && (only_stage() < 0 || only_stage() == s)) { a = e->take_event(); b = e->take_event(); cudaEventRecord(a, st); }
+    }
+    // VS_TRACE_STAGE=<stage>: time only that stage (two events per frame instead of twelve: an almost unperturbed pipeline)
+    static int only_stage() {
+        static int v = [] { const char* e = getenv("VS_TRACE_STAGE"); return e ? atoi(e) : -1; }();
+        return v;
+    }
     ~StageScope() { if (a) { cudaEventRecord(b, st); e->add_pending(stage, a, b); } }
 };
 
@@ -170,7 +177,7 @@ vs_status Engine::alloc_fixed() {
     VS_TRY(dalloc(allocs_, &d_lanes_, (size_t)n_lanes_));
     VS_TRY(dalloc(allocs_, &d_detect_counters_, (size_t)n_lanes_ * 4));      // [generation][lane][eig_max, cand_count]
     int* small_counters = nullptr;
-    VS_TRY(dalloc(allocs_, &small_counters, (size_t)n_lanes_ * 3));
+    VS_TRY(dalloc(allocs_, &small_counters, (size_t)n_lanes_ * (1 + VS_KP_SLOTS)));
     size_t gw = gftt_grid_words(VS_FW, VS_FH, p_.min_distance);
     size_t gw2 = gftt_grid_words(VS_AW, VS_AH, 15.0);
     if (gw2 > gw) gw = gw2;
@@ -196,18 +203,20 @@ vs_status Engine::alloc_fixed() {
         VS_TRY(dalloc(allocs_, &L.grid2, gw));
         L.eig_max2 = d_detect_counters_ + 2 * n_lanes_ + 2 * l;
         L.cand_count2 = (int*)(d_detect_counters_ + 2 * n_lanes_ + 2 * l + 1);
-        L.kp_count = small_counters + 3 * l;
-        L.first_count = small_counters + 3 * l + 1;
+        L.kp_count = small_counters + (1 + VS_KP_SLOTS) * l;
+        L.first_count = small_counters + (1 + VS_KP_SLOTS) * l + 1;
         L.kpc[0] = L.kp_count;
-        L.kpc[1] = small_counters + 3 * l + 2;
+        for (int k = 1; k < VS_KP_SLOTS; ++k) L.kpc[k] = small_counters + (1 + VS_KP_SLOTS) * l + 1 + k;
         VS_TRY(dalloc(allocs_, &L.kp, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.lk_next, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.lk_status, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.inlier_mask, (size_t)kp_cap_));
         L.kpb[0] = L.kp; L.lkn[0] = L.lk_next; L.lks[0] = L.lk_status;
-        VS_TRY(dalloc(allocs_, &L.kpb[1], (size_t)kp_cap_));
-        VS_TRY(dalloc(allocs_, &L.lkn[1], (size_t)kp_cap_));
-        VS_TRY(dalloc(allocs_, &L.lks[1], (size_t)kp_cap_));
+        for (int k = 1; k < VS_KP_SLOTS; ++k) VS_TRY(dalloc(allocs_, &L.kpb[k], (size_t)kp_cap_));
+        for (int k = 1; k < VS_LK_SLOTS; ++k) {
+            VS_TRY(dalloc(allocs_, &L.lkn[k], (size_t)kp_cap_));
+            VS_TRY(dalloc(allocs_, &L.lks[k], (size_t)kp_cap_));
+        }
         VS_TRY(dalloc(allocs_, &L.first_corners, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.kalman, (size_t)VS_KAL_FLOATS));
         VS_TRY(dalloc(allocs_, &L.hf, (size_t)VS_HF_FLOATS));
@@ -338,7 +347,7 @@ vs_status Engine::clean() {
     last_detect_frame_ = -100;
     for (bool& b : ring_ev_set_) b = false;
     for (bool& b : out_free_set_) b = false;
-    c_pending_[0] = c_pending_[1] = false;
+    for (bool& b : c_pending_) b = false;
     queue_.clear();
     first_ = true;
     next_index_ = 0;
@@ -397,8 +406,8 @@ StepInfo Engine::step_info(int pop_index) const {
     s.adaptive = p_.adaptive_smoothing;
     s.min_radius = p_.min_smoothing_radius;
     s.max_radius = p_.max_smoothing_radius;
-    s.kp_slot = ((n_frames_ - 1) / 2) & 1;
-    s.lk_slot = n_frames_ & 1;
+    s.kp_slot = ((n_frames_ - 1) / 2) % VS_KP_SLOTS;
+    s.lk_slot = n_frames_ % VS_LK_SLOTS;
     s.will_detect = ((detect_counter_ + 1) % 2) == 0;            // (++featureDetectionCounter % 2) == 0, Stabilizer.cpp:696-697
     s.wp_slot = n_out_ & 1;
     s.drone = p_.drone_high_freq_mode;
@@ -415,7 +424,7 @@ vs_status Engine::first_frame_detect(const PtrPack& src, int w, int h, size_t st
     launch_gray_resize(d_lanes_, n_lanes_, src, w, h, stride, -1, sp());                  // :304-305
     if (multi_) { CUDA_TRY(cudaEventRecord(evG_, sp())); CUDA_TRY(cudaStreamWaitEvent(sc(0), evG_, 0)); }
     CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc(0)));
-    launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, 0, sc(0));  // :355-357
+    launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, 0, 0, sc(0));  // :355-357
     if (multi_) { CUDA_TRY(cudaEventRecord(evC_[0], sc(0))); c_pending_[0] = true; }
     launches_ += 3;
     return VS_OK;
@@ -424,17 +433,21 @@ vs_status Engine::first_frame_detect(const PtrPack& src, int w, int h, size_t st
 // Corner re-detection on analysis frame `frame_no` (pyramid slot `cur`) -> key-point slot (frame_no / 2) & 1, on the
 // detection stream.  It reads level 0 of the frame (ready at evG_) and overwrites the key points last read by
 // the motion kernel of frame_no - 2.
-vs_status Engine::redetect(int cur, int frame_no, int record_frame_no) {
-    const int gen = (frame_no / 2) & 1;               // detection generation: scratch set, key-point slot, stream, event
+vs_status Engine::redetect(int cur, int frame_no, int record_frame_no, cudaEvent_t level0_ready) {
+    const int gen = (frame_no / 2) & 1;               // detection generation: scratch set and stream
+    const int ks = (frame_no / 2) % VS_KP_SLOTS;      // key-point slot written (LK / motion of frame_no + 1, + 2 read it)
     if (multi_) {
-        CUDA_TRY(cudaStreamWaitEvent(sc(gen), evG_, 0));
-        if (frame_no >= 2 && evB_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sc(gen), evB_[(frame_no - 2) & 3], 0));
+        CUDA_TRY(cudaStreamWaitEvent(sc(gen), level0_ready, 0));
+        // slot ks was last read by the motion kernel of frame_no - 2 (VS_KP_SLOTS - 1).  With two slots this wait closed
+        // a loop detect(n-2) -> LK(n-1) -> LK(n) -> motion(n) -> detect(n+2) that set the pipeline period.
+        const int last = frame_no - 2 * (VS_KP_SLOTS - 1);
+        if (last >= 1 && evB_set_[last & 7]) CUDA_TRY(cudaStreamWaitEvent(sc(gen), evB_[last & 7], 0));
     }
     StageScope t(this, VS_STAGE_GFTT, sc(gen));
     CUDA_TRY(cudaMemsetAsync(d_detect_counters_ + (size_t)gen * 2 * n_lanes_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc(gen)));
     int mc = p_.max_corners < 200 ? p_.max_corners : 200;
-    launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, record_frame_no, gen, sc(gen));   // :740-744
-    if (multi_) { CUDA_TRY(cudaEventRecord(evC_[gen], sc(gen))); c_pending_[gen] = true; last_detect_frame_ = frame_no; }
+    launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, record_frame_no, gen, ks, sc(gen));   // :740-744
+    if (multi_) { CUDA_TRY(cudaEventRecord(evC_[ks], sc(gen))); c_pending_[ks] = true; last_detect_frame_ = frame_no; }
     launches_ += 2;
     return VS_OK;
 }
@@ -451,7 +464,7 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     if (n_frames_ + 1 >= traj_cap_) VS_TRY(grow_trajectory());
     const int frame_no = ++n_frames_;
     const int cur = frame_no % VS_PYR_SLOTS, prev = (frame_no - 1) % VS_PYR_SLOTS;
-    const int kp_slot = ((frame_no - 1) / 2) & 1, lk_slot = frame_no & 1;
+    const int kp_slot = ((frame_no - 1) / 2) % VS_KP_SLOTS, lk_slot = frame_no % VS_LK_SLOTS;
     const bool detect = ((detect_counter_ + 1) % 2) == 0;                             // :696-697
     PtrPack src;
     for (int l = 0; l < n_lanes_; ++l) src.p[l] = e.frames[l];
@@ -469,14 +482,14 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     }
     { StageScope t(this, VS_STAGE_GRAY, sp());
       launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sp()); }       // :449-450
-    if (multi_ && detect) CUDA_TRY(cudaEventRecord(evG_, sp()));
     { StageScope t(this, VS_STAGE_PYRDOWN, sp());
       launch_pyrdown(d_lanes_, n_lanes_, cur, sp()); }
     if (multi_) {
         CUDA_TRY(cudaEventRecord(evP_[frame_no & 7], sp()));
         CUDA_TRY(cudaStreamWaitEvent(sa(), evP_[frame_no & 7], 0));
-        // LK writes tracker slot lk_slot (last read by the motion kernel of frame_no - 2) and reads key points
-        if (frame_no >= 3 && evB_set_[(frame_no - 2) & 3]) CUDA_TRY(cudaStreamWaitEvent(sa(), evB_[(frame_no - 2) & 3], 0));
+        // LK writes tracker slot lk_slot (last read by the motion kernel of frame_no - VS_LK_SLOTS) and reads key points
+        if (frame_no > VS_LK_SLOTS && evB_set_[(frame_no - VS_LK_SLOTS) & 7])
+            CUDA_TRY(cudaStreamWaitEvent(sa(), evB_[(frame_no - VS_LK_SLOTS) & 7], 0));
         if (c_pending_[kp_slot]) { CUDA_TRY(cudaStreamWaitEvent(sa(), evC_[kp_slot], 0)); c_pending_[kp_slot] = false; }
     }
     { StageScope t(this, VS_STAGE_LK, sa());
@@ -499,11 +512,15 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     { StageScope t(this, VS_STAGE_MOTION, sm());
       launch_motion(d_lanes_, n_lanes_, step_info(pop_index), sm()); }                 // :629-688 (+ :783-908)
     launches_ += 1;
-    if (multi_) { CUDA_TRY(cudaEventRecord(evB_[frame_no & 3], sm())); evB_set_[frame_no & 3] = true; }
-    if (pop_index >= 0) VS_TRY(setup_ready());
+    if (multi_) {
+        // one event serves both consumers of this kernel: the tracker-slot guard of LK(frame_no + VS_LK_SLOTS) and the
+        // warp of the output this step set up (fewer stream-semaphore operations per frame)
+        CUDA_TRY(cudaEventRecord(evB_[frame_no & 7], sm())); evB_set_[frame_no & 7] = true;
+        if (pop_index >= 0) CUDA_TRY(cudaStreamWaitEvent(stream_, evB_[frame_no & 7], 0));
+    }
 
     ++detect_counter_;
-    if (detect) VS_TRY(redetect(cur, frame_no, frame_no));
+    if (detect) VS_TRY(redetect(cur, frame_no, frame_no, evP_[frame_no & 7]));   // pyramid-complete event: one record fewer
     if (adaptive) {
         // updateAdaptiveParameters (:691-693, :1562-1574) changes params_.smoothingRadius, which moves the
         // latency gate: the one data-dependent host decision of the path, so this mode reads it back.
@@ -840,7 +857,7 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
         if (multi_) CUDA_TRY(cudaEventRecord(evG_, sp()));
         launch_pyrdown(d_lanes_, 1, m % VS_PYR_SLOTS, sp());
         launches_ += 2;
-        VS_TRY(redetect(m % VS_PYR_SLOTS, m, 0));
+        VS_TRY(redetect(m % VS_PYR_SLOTS, m, 0, evG_));
         if (first - 1 > m) {
             PtrPack s2; s2.p[0] = entry(first - 1).frames[0];
             launch_gray_resize(d_lanes_, 1, s2, w, h, tight, (first - 1) % VS_PYR_SLOTS, sp());

@@ -91,7 +91,7 @@ private:
     vs_status grow_trajectory();
     vs_status generate_transform(const QueueEntry& e, bool* will_pop);
     vs_status first_frame_detect(const PtrPack& src, int w, int h, size_t stride);
-    vs_status redetect(int cur, int frame_no, int record_frame_no);
+    vs_status redetect(int cur, int frame_no, int record_frame_no, cudaEvent_t level0_ready);
     cudaStream_t sa() const { return multi_ ? sA_ : stream_; }
     cudaStream_t sp() const { return multi_ ? sP_ : stream_; }
     cudaStream_t sm() const { return multi_ ? sM_ : stream_; }
@@ -108,10 +108,10 @@ private:
     cudaStream_t sM_ = nullptr;               // motion: RANSAC, trajectory, smoothing, warp set-up
     cudaStream_t sA_ = nullptr, sC_[2] = {}, sP_ = nullptr;   // tracking (LK), corner detection (two generations), pyramid build
     bool multi_ = false;
-    cudaEvent_t evA_[8] = {}, evB_[4] = {}, evP_[8] = {}, evJ_[5] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[2] = {};
-    bool evB_set_[4] = {}, evA_set_[8] = {}, evW_set_[2] = {};
+    cudaEvent_t evA_[8] = {}, evB_[8] = {}, evP_[8] = {}, evJ_[5] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[VS_KP_SLOTS] = {};
+    bool evB_set_[8] = {}, evA_set_[8] = {}, evW_set_[2] = {};
     int last_detect_frame_ = -100;
-    bool c_pending_[2] = {};
+    bool c_pending_[VS_KP_SLOTS] = {};
     cudaStream_t sH_ = nullptr, sO_ = nullptr; // copy-in / copy-out streams of the pipelined host path
     cudaEvent_t evH_[8] = {}, evRing_[36] = {}, evOutReady_[VS_OUT_SLOTS] = {}, evOutFree_[VS_OUT_SLOTS] = {};
     bool ring_ev_set_[36] = {}, out_free_set_[VS_OUT_SLOTS] = {};

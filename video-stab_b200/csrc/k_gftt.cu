@@ -37,7 +37,7 @@ static __device__ __forceinline__ GrayLevel gftt_src(const LaneDev& L, int slot)
 #define EN_EW (EIG_TW + 2)             // eigenvalues: x0-1 .. x0+64
 #define EN_EH (EIG_TH + 2)
 
-__global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lanes, int slot, int gen) {
+__global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lanes, int slot, int gen) {   // gen: scratch set
     __shared__ uint32_t sgw[EN_GH][EN_GW / 4];
     __shared__ float sxx[EN_PH][EN_PW], sxy[EN_PH][EN_PW], syy[EN_PH][EN_PW];
     __shared__ float se[EN_EH][EN_EW];
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lan
     __shared__ int s_count, s_base;
     __shared__ int s_warp_off[8];
     const LaneDev& L = lanes[blockIdx.z];
-    const DetView D = det_view(L, gen);
+    const DetView D = det_view(L, gen, 0);
     const GrayLevel G = gftt_src(L, slot);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * EIG_TW, y0 = blockIdx.y * EIG_TH;
@@ -334,7 +334,7 @@ static __device__ bool greedy_pass(float2* kp_out, const unsigned* sxy, const in
 // boundary that holds the next >= `target` candidates, a gather + shared-memory bitonic sort of just
 // those, then the greedy pass.  Bins are value-ordered, so chunk order == global order.
 __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restrict__ lanes, int slot, int max_corners,
-                                                         double quality, double min_dist, int record_frame_no, int kp_slot) {
+                                                         double quality, double min_dist, int record_frame_no, int gen, int kp_slot) {
     extern __shared__ unsigned long long sel_dyn[];
     unsigned long long* skeys = sel_dyn;                                        // SEL_CHUNK_MAX keys
     unsigned int* hist = reinterpret_cast<unsigned int*>(sel_dyn + SEL_CHUNK_MAX);   // SEL_BINS
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     int* scell = reinterpret_cast<int*>(sxy + SEL_CHUNK_MAX);                   // SEL_CHUNK_MAX grid cell indices
     __shared__ SelSmem S;
     const LaneDev& L = lanes[blockIdx.z];
-    const DetView D = det_view(L, kp_slot);          // generation this detection reads and writes (engine.cu)
+    const DetView D = det_view(L, gen, kp_slot);     // scratch generation read, key-point slot written (engine.cu)
     const GrayLevel G = gftt_src(L, slot);
     const int w = G.w, h = G.h;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -502,7 +502,7 @@ size_t gftt_grid_words(int w, int h, double min_dist) {
 }
 
 void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_corners, double quality,
-                          double min_dist, int record_frame_no, int kp_slot, cudaStream_t st) {
+                          double min_dist, int record_frame_no, int gen, int kp_slot, cudaStream_t st) {
     const int w = slot < 0 ? VS_FW : VS_AW, h = slot < 0 ? VS_FH : VS_AH;
     static bool attr_set = false;
     if (!attr_set) {
@@ -510,7 +510,7 @@ void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_c
         attr_set = true;
     }
     dim3 g1((w + EIG_TW - 1) / EIG_TW, (h + EIG_TH - 1) / EIG_TH, n_lanes);
-    k_eig_nms<<<g1, 256, 0, st>>>(lanes, slot, kp_slot);
+    k_eig_nms<<<g1, 256, 0, st>>>(lanes, slot, gen);
     k_select<<<dim3(1, 1, n_lanes), SEL_THREADS, SEL_DYN_BYTES, st>>>(
-        lanes, slot, max_corners, quality, min_dist, record_frame_no, kp_slot);
+        lanes, slot, max_corners, quality, min_dist, record_frame_no, gen, kp_slot);
 }

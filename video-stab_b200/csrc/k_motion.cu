@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
     WarpParams* const wp_out = info.wp_slot ? L.wpb[1] : L.wpb[0];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
-    const int n_prev = min(min(*(info.kp_slot ? L.kpc[1] : L.kpc[0]), L.kp_capacity), MO_MAXP);
+    const int n_prev = min(min(*L.kpc[info.kp_slot], L.kp_capacity), MO_MAXP);
     const int fidx = info.frame_no - 1;
     float2* lprev = nullptr; float2* lnext = nullptr; uint8_t* lstat = nullptr; uint8_t* lmask = nullptr;
     if (L.log_depth > 0) {
@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         bool ok = false;
         float2 a = make_float2(0.f, 0.f), b = a;
         if (i < n_prev) {
-            a = (info.kp_slot ? L.kpb[1] : L.kpb[0])[i]; b = (info.lk_slot ? L.lkn[1] : L.lkn[0])[i];
-            uint8_t s = (info.lk_slot ? L.lks[1] : L.lks[0])[i];
+            a = L.kpb[info.kp_slot][i]; b = L.lkn[info.lk_slot][i];
+            uint8_t s = L.lks[info.lk_slot][i];
             ok = s != 0;
             if (lprev) { lprev[i] = a; lnext[i] = b; lstat[i] = s; }
         }
