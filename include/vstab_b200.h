@@ -179,6 +179,11 @@ vs_status vs_stabilizer_clean(vs_stabilizer* s);
 vs_status vs_stabilizer_push_device(vs_stabilizer* s, const uint8_t* d_bgr, int width, int height, size_t stride,
                                     uint8_t* d_out, size_t out_stride, size_t out_capacity, unsigned flags,
                                     int* out_width, int* out_height, int* produced);
+/* The stabilize() loop over n_frames device-resident frames (frame k at d_bgr + k * frame_step) as one call; outputs are
+ * written consecutively from d_out, out_frame_capacity bytes apart.  Asynchronous like vs_stabilizer_push_device. */
+vs_status vs_stabilizer_push_many_device(vs_stabilizer* s, const uint8_t* d_bgr, size_t frame_step, int n_frames, int width, int height,
+                                         size_t stride, uint8_t* d_out, size_t out_stride, size_t out_frame_capacity, unsigned flags,
+                                         int* out_width, int* out_height, int* n_produced);
 vs_status vs_stabilizer_flush_device(vs_stabilizer* s, uint8_t* d_out, size_t out_stride, size_t out_capacity,
                                      int* out_width, int* out_height, int* produced);
 vs_status vs_stabilizer_sync(vs_stabilizer* s);

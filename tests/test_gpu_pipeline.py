@@ -381,3 +381,28 @@ def test_wait_event_orders_frames_produced_on_another_stream(vsb):
     got = d_out.cpu().numpy()
     for i in range(n):
         assert np.array_equal(got[i], ref[i]), f"frame {i}"
+
+
+@pytest.mark.parametrize("borrow", [True, False])
+def test_push_many_device_equals_per_frame_push(vsb, borrow):
+    """vs_stabilizer_push_many_device is the per-frame loop moved inside the library: same frames, same records."""
+    w, h, n = 640, 360, 50
+    clip = vsb.synth.make_clip(w, h, n, 99)
+    params = vsb.Parameters(smoothingRadius=6)
+    ref, st0 = _run(vsb, clip, params)
+    d_clip = torch.from_numpy(clip).cuda()
+    fb = h * w * 3
+    d_out = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    st = vsb.Stabilizer(params)
+    k = st.push_many_device(d_clip.data_ptr(), fb, 20, w, h, w * 3, d_out.data_ptr(), w * 3, fb, borrow=borrow)
+    k += st.push_many_device(d_clip[20].data_ptr(), fb, n - 20, w, h, w * 3, d_out[k].data_ptr(), w * 3, fb, borrow=borrow)
+    while st.flush_device(d_out[min(k, n - 1)].data_ptr(), w * 3, fb) is not None:
+        k += 1
+    st.sync()
+    assert k == n == len(ref)
+    got = d_out.cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(got[i], ref[i]), f"frame {i}"
+    for i in range(st.counts()[0]):
+        assert list(st.frame_record(i).transform) == list(st0.frame_record(i).transform)

@@ -64,6 +64,7 @@ SYMBOLS = {
     "vs_stabilizer_push_device": (_I, [_P, _U8P, _I, _I, _SZ, _U8P, _SZ, _SZ, C.c_uint, _IP, _IP, _IP]),
     "vs_stabilizer_flush_device": (_I, [_P, _U8P, _SZ, _SZ, _IP, _IP, _IP]),
     "vs_stabilizer_push_many": (_I, [_P, _U8P, _SZ, _I, _I, _I, _SZ, _U8P, _SZ, _SZ, _IP, _IP, _IP]),
+    "vs_stabilizer_push_many_device": (_I, [_P, _U8P, _SZ, _I, _I, _I, _SZ, _U8P, _SZ, _SZ, C.c_uint, _IP, _IP, _IP]),
     "vs_stabilizer_flush_many": (_I, [_P, _U8P, _SZ, _SZ, _I, _IP, _IP, _IP]),
     "vs_stabilizer_sync": (_I, [_P]),
     "vs_stabilizer_join": (_I, [_P]),

@@ -189,6 +189,16 @@ vs_status vs_stabilizer_push_many(vs_stabilizer* s, const uint8_t* bgr, size_t f
                              out_width, out_height, n_produced);
     API_END
 }
+vs_status vs_stabilizer_push_many_device(vs_stabilizer* s, const uint8_t* d_bgr, size_t frame_step, int n_frames, int width, int height,
+                                         size_t stride, uint8_t* d_out, size_t out_stride, size_t out_frame_capacity, unsigned flags,
+                                         int* out_width, int* out_height, int* n_produced) {
+    if (!s || !n_produced || !out_width || !out_height || !d_bgr || !d_out || n_frames < 0)
+        return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    return s->eng->push_many_device(d_bgr, frame_step, n_frames, width, height, stride, d_out, out_stride, out_frame_capacity, flags,
+                                    out_width, out_height, n_produced);
+    API_END
+}
 vs_status vs_stabilizer_flush_many(vs_stabilizer* s, uint8_t* out, size_t out_stride, size_t out_frame_capacity, int max_frames,
                                    int* out_width, int* out_height, int* n_produced) {
     if (!s || !n_produced || !out_width || !out_height || !out) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");

@@ -751,6 +751,22 @@ vs_status Engine::push_many(const uint8_t* frames, size_t frame_step, int n, int
     return rc != VS_OK ? rc : rs;
 }
 
+// the same loop over device-resident frames; asynchronous like push_device (no synchronisation at the end)
+vs_status Engine::push_many_device(const uint8_t* d_frames, size_t frame_step, int n, int w, int h, size_t stride, uint8_t* d_outs,
+                                   size_t out_stride, size_t out_frame_capacity, unsigned flags, int* ow, int* oh, int* n_produced) {
+    *n_produced = 0;
+    if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "push_many_device is a single-stream call");
+    vs_status rc = VS_OK;
+    for (int k = 0; k < n && rc == VS_OK; ++k) {
+        const uint8_t* f = d_frames + (size_t)k * frame_step;
+        uint8_t* o = d_outs + (size_t)(*n_produced) * out_frame_capacity;
+        int produced = 0;
+        rc = push(&f, w, h, stride, &o, out_stride, out_frame_capacity, flags, VS_IO_DEVICE, ow, oh, &produced);
+        *n_produced += produced;
+    }
+    return rc;
+}
+
 vs_status Engine::flush_many(uint8_t* outs, size_t out_stride, size_t out_frame_capacity, int max_frames, int* ow, int* oh,
                              int* n_produced) {
     *n_produced = 0;

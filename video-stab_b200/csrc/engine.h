@@ -34,6 +34,8 @@ public:
                     int* produced);
     vs_status push_many(const uint8_t* frames, size_t frame_step, int n, int w, int h, size_t stride, uint8_t* outs,
                         size_t out_stride, size_t out_frame_capacity, int* ow, int* oh, int* n_produced);
+    vs_status push_many_device(const uint8_t* d_frames, size_t frame_step, int n, int w, int h, size_t stride, uint8_t* d_outs,
+                               size_t out_stride, size_t out_frame_capacity, unsigned flags, int* ow, int* oh, int* n_produced);
     vs_status flush_many(uint8_t* outs, size_t out_stride, size_t out_frame_capacity, int max_frames, int* ow, int* oh,
                          int* n_produced);
     vs_status clean();

@@ -249,6 +249,15 @@ class Stabilizer:
                                             1 if borrow else 0, C.byref(ow), C.byref(oh), C.byref(produced)))
         return (ow.value, oh.value) if produced.value else None
 
+    def push_many_device(self, d_frames: int, frame_step: int, n: int, w: int, h: int, stride: int, d_out: int,
+                         out_stride: int, out_frame_capacity: int, borrow: bool = False) -> int:
+        """stabilize() over n device frames (frame k at d_frames + k * frame_step) in one call; returns the number of
+        outputs written consecutively from d_out.  Asynchronous: sync() before reading them."""
+        ow, oh, produced = C.c_int(), C.c_int(), C.c_int()
+        check(lib.vs_stabilizer_push_many_device(self._h, d_frames, frame_step, n, w, h, stride, d_out, out_stride,
+                                                 out_frame_capacity, 1 if borrow else 0, C.byref(ow), C.byref(oh), C.byref(produced)))
+        return produced.value
+
     def flush_device(self, d_out: int, out_stride: int, out_capacity: int):
         ow, oh, produced = C.c_int(), C.c_int(), C.c_int()
         check(lib.vs_stabilizer_flush_device(self._h, d_out, out_stride, out_capacity,
