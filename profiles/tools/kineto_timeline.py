@@ -12,15 +12,19 @@ frames = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 clip = torch.from_numpy(vsb.synth.make_clip(W, H, n, 2000)).cuda()
 out = torch.empty_like(clip)
 order = list(range(n)) + list(range(n - 2, 0, -1))
+seq = clip[torch.tensor(order, device="cuda")].contiguous()
+torch.cuda.synchronize()
 st = vsb.Stabilizer(vsb.Parameters(smoothingRadius=15))
 pos = 0
-def step(k):
+fb = W * H * 3
+def step(k):                      # the loop runs inside the library (vs_stabilizer_push_many_device): no Python per frame
     global pos
-    for _ in range(k):
-        i = order[pos % len(order)]
-        st.push_device(clip[i].data_ptr(), W, H, W * 3, out[pos % n].data_ptr(), W * 3, H * W * 3, borrow=True)
-        pos += 1
-step(200); st.sync()
+    while k > 0:
+        a = pos % len(order)
+        m = min(k, len(order) - a, n)
+        st.push_many_device(seq[a].data_ptr(), fb, m, W, H, W * 3, out.data_ptr(), W * 3, fb, borrow=True)
+        pos += m; k -= m
+step(252); st.sync()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(frames); st.sync()
 path = os.path.join(tempfile.mkdtemp(), "trace.json")

@@ -136,7 +136,7 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
         // a warp CTA retires, instead of queueing behind the rest of the warp grid.
         int prio_lo = 0, prio_hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&sA_, cudaStreamNonBlocking, prio_hi));
+        for (auto& st : sA_) CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
         for (auto& st : sC_) CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&sP_, cudaStreamNonBlocking, prio_hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&sM_, cudaStreamNonBlocking, prio_hi));
@@ -286,7 +286,7 @@ void Engine::free_all() {
     for (auto& ev : evRing_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evOutReady_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : evOutFree_) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
-    if (sA_) { cudaStreamDestroy(sA_); sA_ = nullptr; }
+    for (auto& st : sA_) if (st) { cudaStreamDestroy(st); st = nullptr; }
     for (auto& st : sC_) if (st) { cudaStreamDestroy(st); st = nullptr; }
     if (sH_) { cudaStreamDestroy(sH_); sH_ = nullptr; }
     if (sO_) { cudaStreamDestroy(sO_); sO_ = nullptr; }
@@ -319,7 +319,7 @@ vs_status Engine::sync() {
     if (sH_) CUDA_TRY(cudaStreamSynchronize(sH_));
     if (sP_) CUDA_TRY(cudaStreamSynchronize(sP_));
     if (sM_) CUDA_TRY(cudaStreamSynchronize(sM_));
-    if (sA_) CUDA_TRY(cudaStreamSynchronize(sA_));
+    for (auto& st : sA_) if (st) CUDA_TRY(cudaStreamSynchronize(st));
     for (auto& st : sC_) if (st) CUDA_TRY(cudaStreamSynchronize(st));
     if (stream_) CUDA_TRY(cudaStreamSynchronize(stream_));
     if (sO_) CUDA_TRY(cudaStreamSynchronize(sO_));
@@ -329,7 +329,8 @@ vs_status Engine::sync() {
 // Orders everything enqueued so far (on all three streams) before whatever is enqueued on the public stream next.
 vs_status Engine::join() {
     if (!multi_) return VS_OK;
-    CUDA_TRY(cudaEventRecord(evJ_[0], sA_));
+    CUDA_TRY(cudaEventRecord(evJ_[0], sA_[0]));
+    CUDA_TRY(cudaEventRecord(evJ_[5], sA_[1]));
     CUDA_TRY(cudaEventRecord(evJ_[1], sC_[0]));
     CUDA_TRY(cudaEventRecord(evJ_[4], sC_[1]));
     CUDA_TRY(cudaEventRecord(evJ_[2], sP_));
@@ -479,6 +480,8 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         // it (frame_no - VS_PYR_SLOTS, if even) finished before that LK started (it produced its key points)
         const int last_reader = frame_no - VS_PYR_SLOTS + 1;
         if (last_reader >= 1 && evA_set_[last_reader & 7]) CUDA_TRY(cudaStreamWaitEvent(sp(), evA_[last_reader & 7], 0));
+        // ... and as its current frame by LK(frame_no - VS_PYR_SLOTS), which runs on the other tracking stream
+        if (last_reader - 1 >= 1 && evA_set_[(last_reader - 1) & 7]) CUDA_TRY(cudaStreamWaitEvent(sp(), evA_[(last_reader - 1) & 7], 0));
     }
     { StageScope t(this, VS_STAGE_GRAY, sp());
       launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sp()); }       // :449-450
@@ -486,17 +489,19 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
       launch_pyrdown(d_lanes_, n_lanes_, cur, sp()); }
     if (multi_) {
         CUDA_TRY(cudaEventRecord(evP_[frame_no & 7], sp()));
-        CUDA_TRY(cudaStreamWaitEvent(sa(), evP_[frame_no & 7], 0));
+        // LK(n) and LK(n+1) are independent (key points are not advanced between detections, Appendix B Q4): they
+        // alternate between two tracking streams, so the tracker is not a serial chain
+        CUDA_TRY(cudaStreamWaitEvent(sa(frame_no), evP_[frame_no & 7], 0));
         // LK writes tracker slot lk_slot (last read by the motion kernel of frame_no - VS_LK_SLOTS) and reads key points
         if (frame_no > VS_LK_SLOTS && evB_set_[(frame_no - VS_LK_SLOTS) & 7])
-            CUDA_TRY(cudaStreamWaitEvent(sa(), evB_[(frame_no - VS_LK_SLOTS) & 7], 0));
-        if (c_pending_[kp_slot]) { CUDA_TRY(cudaStreamWaitEvent(sa(), evC_[kp_slot], 0)); c_pending_[kp_slot] = false; }
+            CUDA_TRY(cudaStreamWaitEvent(sa(frame_no), evB_[(frame_no - VS_LK_SLOTS) & 7], 0));
+        if (c_pending_[kp_slot]) CUDA_TRY(cudaStreamWaitEvent(sa(frame_no), evC_[kp_slot], 0));   // both frames after a detection
     }
-    { StageScope t(this, VS_STAGE_LK, sa());
-      launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa()); }   // :611-619
+    { StageScope t(this, VS_STAGE_LK, sa(frame_no));
+      launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa(frame_no)); }   // :611-619
     launches_ += 3;
     if (multi_) {
-        CUDA_TRY(cudaEventRecord(evA_[frame_no & 7], sa()));
+        CUDA_TRY(cudaEventRecord(evA_[frame_no & 7], sa(frame_no)));
         evA_set_[frame_no & 7] = true;
         CUDA_TRY(cudaStreamWaitEvent(sm(), evA_[frame_no & 7], 0));
     }

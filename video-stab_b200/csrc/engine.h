@@ -94,7 +94,7 @@ private:
     vs_status generate_transform(const QueueEntry& e, bool* will_pop);
     vs_status first_frame_detect(const PtrPack& src, int w, int h, size_t stride);
     vs_status redetect(int cur, int frame_no, int record_frame_no, cudaEvent_t level0_ready);
-    cudaStream_t sa() const { return multi_ ? sA_ : stream_; }
+    cudaStream_t sa(int frame_no) const { return multi_ ? sA_[frame_no & 1] : stream_; }
     cudaStream_t sp() const { return multi_ ? sP_ : stream_; }
     cudaStream_t sm() const { return multi_ ? sM_ : stream_; }
     vs_status setup_slot_guard();
@@ -108,9 +108,9 @@ private:
     int device_ = 0, n_lanes_ = 0;
     cudaStream_t stream_ = nullptr;           // public stream: output stage (warp, copies out)
     cudaStream_t sM_ = nullptr;               // motion: RANSAC, trajectory, smoothing, warp set-up
-    cudaStream_t sA_ = nullptr, sC_[2] = {}, sP_ = nullptr;   // tracking (LK), corner detection (two generations), pyramid build
+    cudaStream_t sA_[2] = {}, sC_[2] = {}, sP_ = nullptr;   // tracking (LK, by frame parity), corner detection (two generations), pyramid build
     bool multi_ = false;
-    cudaEvent_t evA_[8] = {}, evB_[8] = {}, evP_[8] = {}, evJ_[5] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[VS_KP_SLOTS] = {};
+    cudaEvent_t evA_[8] = {}, evB_[8] = {}, evP_[8] = {}, evJ_[6] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[VS_KP_SLOTS] = {};
     bool evB_set_[8] = {}, evA_set_[8] = {}, evW_set_[2] = {};
     int last_detect_frame_ = -100;
     bool c_pending_[VS_KP_SLOTS] = {};
