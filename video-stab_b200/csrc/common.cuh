@@ -13,7 +13,7 @@
 #define VS_PYR_SLOTS 6       // pyramids kept per lane (frames n-1, n for LK + 4 frames of run-ahead)
 #define VS_LEVELS 3          // maxLevel 2 (Stabilizer.cpp:617)
 #define VS_KP_SLOTS 4        // key-point buffers (LaneDev::kpb / kpc), by (detection frame / 2) % VS_KP_SLOTS
-#define VS_LK_SLOTS 4        // tracker output buffers (LaneDev::lkn / lks), by frame % VS_LK_SLOTS
+#define VS_LK_SLOTS 8        // tracker output buffers (LaneDev::lkn / lks), by frame % VS_LK_SLOTS
 #define VS_AW 960            // analysis size (Stabilizer.cpp:410)
 #define VS_AH 540
 #define VS_FW 480            // first-frame analysis size (Stabilizer.cpp:277)

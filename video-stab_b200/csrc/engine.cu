@@ -439,14 +439,12 @@ vs_status Engine::redetect(int cur, int frame_no, int record_frame_no, cudaEvent
     const int ks = (frame_no / 2) % VS_KP_SLOTS;      // key-point slot written (LK / motion of frame_no + 1, + 2 read it)
     if (multi_) {
         CUDA_TRY(cudaStreamWaitEvent(sc(gen), level0_ready, 0));
-        // slot ks was last read by the motion kernel of frame_no - 2 (VS_KP_SLOTS - 1).  With two slots this wait closed
-        // a loop detect(n-2) -> LK(n-1) -> LK(n) -> motion(n) -> detect(n+2) that set the pipeline period.
-        const int last = frame_no - 2 * (VS_KP_SLOTS - 1);
-        if (last >= 1 && evB_set_[last & 7]) CUDA_TRY(cudaStreamWaitEvent(sc(gen), evB_[last & 7], 0));
+        // slot ks was last read by the motion kernel of frame_no - 6: complete, see the guard in generate_transform
+        // (with two slots the explicit wait on motion(frame_no - 2) closed a loop detect(n-2) -> LK(n-1) -> LK(n) ->
+        // motion(n) -> detect(n+2) that set the pipeline period)
     }
     StageScope t(this, VS_STAGE_GFTT, sc(gen));
-    CUDA_TRY(cudaMemsetAsync(d_detect_counters_ + (size_t)gen * 2 * n_lanes_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc(gen)));
-    int mc = p_.max_corners < 200 ? p_.max_corners : 200;
+    int mc = p_.max_corners < 200 ? p_.max_corners : 200;       // (the counters were left zeroed by the previous k_select)
     launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, record_frame_no, gen, ks, sc(gen));   // :740-744
     if (multi_) { CUDA_TRY(cudaEventRecord(evC_[ks], sc(gen))); c_pending_[ks] = true; last_detect_frame_ = frame_no; }
     launches_ += 2;
@@ -476,12 +474,14 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         launches_ += 2;
     }
     if (multi_) {
-        // slot `cur` was last read by LK(frame_no - VS_PYR_SLOTS + 1) (as its previous frame); the detection that read
-        // it (frame_no - VS_PYR_SLOTS, if even) finished before that LK started (it produced its key points)
-        const int last_reader = frame_no - VS_PYR_SLOTS + 1;
-        if (last_reader >= 1 && evA_set_[last_reader & 7]) CUDA_TRY(cudaStreamWaitEvent(sp(), evA_[last_reader & 7], 0));
-        // ... and as its current frame by LK(frame_no - VS_PYR_SLOTS), which runs on the other tracking stream
-        if (last_reader - 1 >= 1 && evA_set_[(last_reader - 1) & 7]) CUDA_TRY(cudaStreamWaitEvent(sp(), evA_[(last_reader - 1) & 7], 0));
+        // Slot `cur` was last read by LK(frame_no - 5) (as its previous frame) and LK(frame_no - 6) (as its current
+        // frame), and by the detection of frame_no - 6.  ONE wait covers them and more: motion(frame_no - 5) complete
+        // means LK(frame_no - 5) complete (it consumed its output), hence the detection whose key points that LK used,
+        // and - the motion stream being in order - motion and LK of every earlier frame.  The tracker-output slots
+        // (VS_LK_SLOTS = 8 > 5) and key-point slots (2 * VS_KP_SLOTS = 8 > 5 frames) are guarded by the same wait,
+        // because LK(n) and the detection of frame n both start after pyramid(n).
+        const int guard = frame_no - VS_PYR_SLOTS + 1;
+        if (guard >= 1 && evB_set_[guard & 7]) CUDA_TRY(cudaStreamWaitEvent(sp(), evB_[guard & 7], 0));
     }
     { StageScope t(this, VS_STAGE_GRAY, sp());
       launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sp()); }       // :449-450
@@ -492,9 +492,6 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         // LK(n) and LK(n+1) are independent (key points are not advanced between detections, Appendix B Q4): they
         // alternate between two tracking streams, so the tracker is not a serial chain
         CUDA_TRY(cudaStreamWaitEvent(sa(frame_no), evP_[frame_no & 7], 0));
-        // LK writes tracker slot lk_slot (last read by the motion kernel of frame_no - VS_LK_SLOTS) and reads key points
-        if (frame_no > VS_LK_SLOTS && evB_set_[(frame_no - VS_LK_SLOTS) & 7])
-            CUDA_TRY(cudaStreamWaitEvent(sa(frame_no), evB_[(frame_no - VS_LK_SLOTS) & 7], 0));
         if (c_pending_[kp_slot]) CUDA_TRY(cudaStreamWaitEvent(sa(frame_no), evC_[kp_slot], 0));   // both frames after a detection
     }
     { StageScope t(this, VS_STAGE_LK, sa(frame_no));

@@ -374,6 +374,9 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
     int shift = 0;
     while ((range >> shift) >= (unsigned)SEL_BINS) ++shift;
     __syncthreads();
+    // every thread holds N and the maximum in registers now: leave this generation's counters zeroed for its next
+    // detection (same stream, so ordered) — the engine needs no memset node per detection
+    if (tid == 0) { *D.eig_max = 0u; *D.cand_count = 0; }
     for (int i0 = tid; i0 < N; i0 += 4 * SEL_THREADS) {          // four independent loads in flight per thread
         unsigned long long kk[4];
 #pragma unroll
