@@ -39,7 +39,7 @@ static __device__ __forceinline__ GrayLevel gftt_src(const LaneDev& L, int slot)
 
 __global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lanes, int slot, int gen) {   // gen: scratch set
     __shared__ uint32_t sgw[EN_GH][EN_GW / 4];
-    __shared__ float sxx[EN_PH][EN_PW], sxy[EN_PH][EN_PW], syy[EN_PH][EN_PW];
+    __shared__ double sxx[EN_PH][EN_PW], sxy[EN_PH][EN_PW], syy[EN_PH][EN_PW];   // products, already widened: OpenCV's box filter sums them in double
     __shared__ float se[EN_EH][EN_EW];
     __shared__ unsigned int smax;
     __shared__ int s_count, s_base;
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lan
         float t0 = __fadd_rn(__fadd_rn(__fmul_rn(a00, f1), __fmul_rn(a01, f0)), __fmul_rn(a02, f1));
         float t2 = __fadd_rn(__fadd_rn(__fmul_rn(a20, f1), __fmul_rn(a21, f0)), __fmul_rn(a22, f1));
         float dy = __fsub_rn(t2, t0);
-        sxx[r][c] = __fmul_rn(dx, dx);
-        sxy[r][c] = __fmul_rn(dx, dy);
-        syy[r][c] = __fmul_rn(dy, dy);
+        sxx[r][c] = (double)__fmul_rn(dx, dx);
+        sxy[r][c] = (double)__fmul_rn(dx, dy);
+        syy[r][c] = (double)__fmul_rn(dy, dy);
     }
     __syncthreads();
     // 2b. positions outside the image: BORDER_REFLECT_101 of the product maps (the source lies inside this tile)
@@ -108,28 +108,40 @@ __global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lan
         }
         __syncthreads();
     }
-    // 3. eigenvalues on the tile + 1 (x = x0-1+c, y = y0-1+r); outside the image: -1 (never a maximum, never >= a candidate)
+    // 3. eigenvalues on the tile + 1 (x = x0-1+c, y = y0-1+r); outside the image: -1 (never a maximum, never >= a candidate).
+    //    The 3x3 box sum is separable and exact in double (the sum of nine floats of similar magnitude), so any
+    //    association gives OpenCV's value: one thread walks a column segment of EN_SEG rows with a sliding window of
+    //    three row sums - 12 double adds per position instead of 27, and no float->double conversion here.
     unsigned int lmax = 0u;
-    for (int i = tid; i < EN_EH * EN_EW; i += 256) {
-        const int r = i / EN_EW, c = i - r * EN_EW;
-        const int x = x0 - 1 + c, y = y0 - 1 + r;
-        float e = -1.f;
-        if ((unsigned)x < (unsigned)G.w && (unsigned)y < (unsigned)G.h) {
-            double bxx = 0, bxy = 0, byy = 0;        // OpenCV's box filter sums float in double: exact here
+    {
+        constexpr int EN_SEG = 6, NSEG = EN_EH / EN_SEG;          // 18 rows = 3 segments; 66 columns x 3 = 198 threads
+        static_assert(NSEG * EN_SEG == EN_EH && NSEG * EN_EW <= 256, "segment map");
+        const int seg = tid / EN_EW, c = tid - seg * EN_EW;
+        if (seg < NSEG) {
+            const int x = x0 - 1 + c;
+            double w0x = 0, w0y = 0, w0z = 0, w1x = 0, w1y = 0, w1z = 0;
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    bxx += (double)sxx[r + dy][c + dx];
-                    bxy += (double)sxy[r + dy][c + dx];
-                    byy += (double)syy[r + dy][c + dx];
+            for (int rr = 0; rr < EN_SEG + 2; ++rr) {
+                const int pr = seg * EN_SEG + rr;                 // product row
+                const double rx = (sxx[pr][c] + sxx[pr][c + 1]) + sxx[pr][c + 2];
+                const double ry = (sxy[pr][c] + sxy[pr][c + 1]) + sxy[pr][c + 2];
+                const double rz = (syy[pr][c] + syy[pr][c + 1]) + syy[pr][c + 2];
+                if (rr >= 2) {
+                    const int r = pr - 2, y = y0 - 1 + r;
+                    float e = -1.f;
+                    if ((unsigned)x < (unsigned)G.w && (unsigned)y < (unsigned)G.h) {
+                        const double bxx = (w0x + w1x) + rx, bxy = (w0y + w1y) + ry, byy = (w0z + w1z) + rz;
+                        float a = __fmul_rn((float)bxx, 0.5f), b = (float)bxy, cc = __fmul_rn((float)byy, 0.5f);
+                        float d = __fsub_rn(a, cc);
+                        e = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+                        if (e > 0.f) lmax = max(lmax, __float_as_uint(e));
+                    }
+                    se[r][c] = e;
                 }
-            float a = __fmul_rn((float)bxx, 0.5f), b = (float)bxy, cc = __fmul_rn((float)byy, 0.5f);
-            float d = __fsub_rn(a, cc);
-            e = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
-            if (e > 0.f) lmax = max(lmax, __float_as_uint(e));
+                w0x = w1x; w0y = w1y; w0z = w1z;
+                w1x = rx; w1y = ry; w1z = rz;
+            }
         }
-        se[r][c] = e;
     }
     lmax = __reduce_max_sync(0xffffffffu, lmax);
     if (lane == 0 && lmax) atomicMax(&smax, lmax);
