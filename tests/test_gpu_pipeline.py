@@ -406,3 +406,36 @@ def test_push_many_device_equals_per_frame_push(vsb, borrow):
         assert np.array_equal(got[i], ref[i]), f"frame {i}"
     for i in range(st.counts()[0]):
         assert list(st.frame_record(i).transform) == list(st0.frame_record(i).transform)
+
+
+@pytest.mark.parametrize("w,h,n,kw", [(1920, 1080, 150, dict(smoothingRadius=15)),
+                                      (1280, 720, 120, dict(smoothingRadius=6, cropNZoom=True, borderSize=24))])
+def test_multi_stream_engine_equals_single_stream(vsb, monkeypatch, w, h, n, kw):
+    """The seven-stream engine (slot rings + one transitive guard per frame) against the same calls with every kernel
+    serialised on one stream (VS_SINGLE_STREAM=1): frames and transforms must be identical, on every repetition."""
+    clip = torch.from_numpy(vsb.synth.make_clip(w, h, 40, 31)).cuda()
+    order = list(range(40)) + list(range(38, 0, -1))
+    seq = clip[torch.tensor([order[k % len(order)] for k in range(n)], device="cuda")].contiguous()
+    fb = w * h * 3
+    torch.cuda.synchronize()
+    want = None
+    for rep in range(4):
+        if rep == 0:
+            monkeypatch.setenv("VS_SINGLE_STREAM", "1")
+        else:
+            monkeypatch.delenv("VS_SINGLE_STREAM", raising=False)
+        out = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        st = vsb.Stabilizer(vsb.Parameters(**kw))
+        k = st.push_many_device(seq.data_ptr(), fb, n, w, h, w * 3, out.data_ptr(), w * 3, fb, borrow=True)
+        while k < n and st.flush_device(out[k].data_ptr(), w * 3, fb) is not None:
+            k += 1
+        st.sync()
+        assert k == n
+        got = [zlib.crc32(f.tobytes()) for f in out.cpu().numpy()]
+        recs = [tuple(st.frame_record(i).transform) for i in range(st.counts()[0])]
+        if want is None:
+            want = (got, recs)
+        else:
+            assert got == want[0], f"rep {rep}: frames {[i for i in range(n) if got[i] != want[0][i]][:8]} differ"
+            assert recs == want[1], f"rep {rep}: transforms differ"

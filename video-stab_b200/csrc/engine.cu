@@ -129,7 +129,8 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     // Three streams per handle (engine.h): analysis (gray, pyramid, LK), motion + output (the public stream), and
     // corner detection.  adaptive_smoothing reads one int back per frame, so that mode stays on one stream.
-    multi_ = !p.adaptive_smoothing;
+    // VS_SINGLE_STREAM=1 runs everything on the public stream (verification: the multi-stream engine must reproduce it)
+    multi_ = !p.adaptive_smoothing && !getenv("VS_SINGLE_STREAM");
     if (multi_) {
         // The analysis kernels are small and latency-critical (a single CTA for k_motion / k_select), the warp is one
         // machine-filling grid: the analysis streams get the higher priority so their CTAs are placed first whenever
