@@ -12,6 +12,7 @@
 #define VS_WIN 15            // LK window (Stabilizer.cpp:616)
 #define VS_PYR_SLOTS 6       // pyramids kept per lane (frames n-1, n for LK + 4 frames of run-ahead)
 #define VS_LEVELS 3          // maxLevel 2 (Stabilizer.cpp:617)
+#define VS_WP_SLOTS 8        // warp set-up buffers (LaneDev::wpb), by output index % VS_WP_SLOTS
 #define VS_KP_SLOTS 4        // key-point buffers (LaneDev::kpb / kpc), by (detection frame / 2) % VS_KP_SLOTS
 #define VS_LK_SLOTS 8        // tracker output buffers (LaneDev::lkn / lks), by frame % VS_LK_SLOTS
 #define VS_AW 960            // analysis size (Stabilizer.cpp:410)
@@ -81,7 +82,7 @@ struct LaneDev {
     float2* first_corners;
     int* first_count;
     WarpParams* wp;                 // == wpb[0] (single-kernel entry points, clip mode scratch)
-    WarpParams* wpb[2];             // warp set-ups by output parity: motion of frame n+1 may run while output n is warped
+    WarpParams* wpb[VS_WP_SLOTS];   // warp set-ups by output % VS_WP_SLOTS: the motion kernel runs ahead of the warps
     int kp_capacity;
     int log_depth;
     int record_capacity;

@@ -221,8 +221,8 @@ vs_status Engine::alloc_fixed() {
         VS_TRY(dalloc(allocs_, &L.first_corners, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.kalman, (size_t)VS_KAL_FLOATS));
         VS_TRY(dalloc(allocs_, &L.hf, (size_t)VS_HF_FLOATS));
-        VS_TRY(dalloc(allocs_, &L.wp, (size_t)2));
-        L.wpb[0] = L.wp; L.wpb[1] = L.wp + 1;
+        VS_TRY(dalloc(allocs_, &L.wp, (size_t)VS_WP_SLOTS));
+        for (int k = 0; k < VS_WP_SLOTS; ++k) L.wpb[k] = L.wp + k;
         size_t ln = (size_t)log_depth_ * kp_cap_;
         VS_TRY(dalloc(allocs_, &L.log_prev, ln));
         VS_TRY(dalloc(allocs_, &L.log_next, ln));
@@ -411,7 +411,7 @@ StepInfo Engine::step_info(int pop_index) const {
     s.kp_slot = ((n_frames_ - 1) / 2) % VS_KP_SLOTS;
     s.lk_slot = n_frames_ % VS_LK_SLOTS;
     s.will_detect = ((detect_counter_ + 1) % 2) == 0;            // (++featureDetectionCounter % 2) == 0, Stabilizer.cpp:696-697
-    s.wp_slot = n_out_ & 1;
+    s.wp_slot = n_out_ % VS_WP_SLOTS;
     s.drone = p_.drone_high_freq_mode;
     s.hf_shake_px = p_.hf_shake_px;
     s.hf_rot_lp_alpha = p_.hf_rot_lp_alpha;
@@ -545,10 +545,13 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     return VS_OK;
 }
 
-// The warp set-up of output n_out_ lives in LaneDev::wpb[n_out_ & 1]: its writer (motion stream) waits for the
-// warp of output n_out_ - 2 (public stream), and the warp waits for the writer.
+// The warp set-up of output k lives in LaneDev::wpb[k % 8]; its writer (motion stream) must not overtake the warp of
+// output k - 8 (public stream).  Outputs are guarded in groups of four: the public stream records evW_[g & 1] after the
+// last warp of group g = k / 4, and the motion stream waits for group g - 2 before the first set-up of group g - one
+// record and one wait per four frames.
 vs_status Engine::setup_slot_guard() {
-    if (multi_ && evW_set_[n_out_ & 1]) CUDA_TRY(cudaStreamWaitEvent(sm(), evW_[n_out_ & 1], 0));
+    const int g = n_out_ >> 2;
+    if (multi_ && (n_out_ & 3) == 0 && g >= 2 && evW_set_[g & 1]) CUDA_TRY(cudaStreamWaitEvent(sm(), evW_[g & 1], 0));
     return VS_OK;
 }
 vs_status Engine::setup_ready() {
@@ -615,7 +618,7 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         }
         g.out_w = w; g.out_h = h; g.out_stride = dstride;
         g.d_tmaps = d_tmaps_;
-        g.wp_slot = n_out_ & 1;
+        g.wp_slot = n_out_ % VS_WP_SLOTS;
         int m2 = fade_ ? 0 : mode;
         if (mode == 2 && (W_ - 2 * b <= 0 || H_ - 2 * b <= 0)) m2 = 0;                // border larger than image
         g.mode = m2;
@@ -629,7 +632,7 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         }
     }
     if (multi_) {
-        CUDA_TRY(cudaEventRecord(evW_[n_out_ & 1], stream_)); evW_set_[n_out_ & 1] = true;
+        if ((n_out_ & 3) == 3) { CUDA_TRY(cudaEventRecord(evW_[(n_out_ >> 2) & 1], stream_)); evW_set_[(n_out_ >> 2) & 1] = true; }
         if (e.in_ring) {
             CUDA_TRY(cudaEventRecord(evRing_[e.slot], stream_));        // the ring slot of this frame may be refilled
             ring_ev_set_[e.slot] = true;

@@ -40,7 +40,12 @@ static __device__ __forceinline__ GrayLevel gftt_src(const LaneDev& L, int slot)
 __global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lanes, int slot, int gen) {   // gen: scratch set
     __shared__ uint32_t sgw[EN_GH][EN_GW / 4];
     __shared__ double sxx[EN_PH][EN_PW], sxy[EN_PH][EN_PW], syy[EN_PH][EN_PW];   // products, already widened: OpenCV's box filter sums them in double
-    __shared__ float se[EN_EH][EN_EW];
+    // horizontal Sobel passes (stage 2a) and the eigenvalue tile (stage 3 on) share storage: the former are dead by then
+    __shared__ __align__(16) unsigned char s_u[EN_GH * EN_PW * 6];
+    float (*const sT)[EN_PW] = reinterpret_cast<float (*)[EN_PW]>(s_u);                                   // [1 2 1] * scale row pass
+    short (*const sD)[EN_PW] = reinterpret_cast<short (*)[EN_PW]>(s_u + EN_GH * EN_PW * 4);               // [-1 0 1] row pass
+    float (*const se)[EN_EW] = reinterpret_cast<float (*)[EN_EW]>(s_u);
+    static_assert(EN_EH * EN_EW * 4 <= EN_GH * EN_PW * 6 && EN_PW % 4 == 0, "shared eigenvalue tile");
     __shared__ unsigned int smax;
     __shared__ int s_count, s_base;
     __shared__ int s_warp_off[8];
@@ -70,32 +75,44 @@ __global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lan
             if (i < NW) sgw[i / (EN_GW / 4)][i - (i / (EN_GW / 4)) * (EN_GW / 4)] = v[k];
         }
     }
-    const uint8_t (*sg)[EN_GW] = reinterpret_cast<const uint8_t (*)[EN_GW]>(&sgw[0][0]);
     __syncthreads();
-    // 2. products at in-image positions (x = x0-2+c, y = y0-2+r); gray(x, y) = sg[r+1+dy][c+2+dx]
+    // 2a. separable Sobel, row passes on every staged gray row (gray column of product column c is c + 2):
+    //       sD = a[c+3] - a[c+1] (exact integer), sT = (a[c+1]*f1 + a[c+2]*f0) + a[c+3]*f1 (OpenCV's order, left to right).
+    //     One task = 4 columns of one row from two aligned words; 8 int->float conversions instead of 12 per 4 pixels,
+    //     and each row pass is computed once instead of once per vertical neighbour.
+    for (int i = tid; i < EN_GH * (EN_PW / 4); i += 256) {
+        const int r = i / (EN_PW / 4), g4 = i - r * (EN_PW / 4);
+        const uint32_t w0 = sgw[r][g4], w1 = sgw[r][g4 + 1];
+        const int b1 = (w0 >> 8) & 255, b2 = (w0 >> 16) & 255, b3 = w0 >> 24, b4 = w1 & 255, b5 = (w1 >> 8) & 255, b6 = (w1 >> 16) & 255;
+        const float a1 = __fmul_rn((float)b1, f1), a3 = __fmul_rn((float)b3, f1), a4 = __fmul_rn((float)b4, f1), a6 = __fmul_rn((float)b6, f1);
+        const float a2 = __fmul_rn((float)b2, f1), a5 = __fmul_rn((float)b5, f1);
+        const float c2 = __fmul_rn((float)b2, f0), c3 = __fmul_rn((float)b3, f0), c4 = __fmul_rn((float)b4, f0), c5 = __fmul_rn((float)b5, f0);
+        float4 t;
+        t.x = __fadd_rn(__fadd_rn(a1, c2), a3);
+        t.y = __fadd_rn(__fadd_rn(a2, c3), a4);
+        t.z = __fadd_rn(__fadd_rn(a3, c4), a5);
+        t.w = __fadd_rn(__fadd_rn(a4, c5), a6);
+        *reinterpret_cast<float4*>(&sT[r][4 * g4]) = t;
+        short4 d;
+        d.x = (short)(b3 - b1); d.y = (short)(b4 - b2); d.z = (short)(b5 - b3); d.w = (short)(b6 - b4);
+        *reinterpret_cast<short4*>(&sD[r][4 * g4]) = d;
+    }
+    __syncthreads();
+    // 2b. products at in-image positions (x = x0-2+c, y = y0-2+r): column passes over rows r, r+1, r+2
     for (int i = tid; i < EN_PH * EN_PW; i += 256) {
         const int r = i / EN_PW, c = i - r * EN_PW;
         const int x = x0 - 2 + c, y = y0 - 2 + r;
         if ((unsigned)x >= (unsigned)G.w || (unsigned)y >= (unsigned)G.h) continue;
-        const uint8_t* pu = &sg[r][c + 2];
-        const uint8_t* p = pu + EN_GW;
-        const uint8_t* pd = p + EN_GW;
-        float a00 = pu[-1], a01 = pu[0], a02 = pu[1];
-        float a10 = p[-1], a12 = p[1];
-        float a20 = pd[-1], a21 = pd[0], a22 = pd[1];
-        // Dx: row pass [-1 0 1] (exact), column pass [1 2 1]*scale as (S0+S2)*f1 + S1*f0
-        float r0 = a02 - a00, r1 = a12 - a10, r2 = a22 - a20;
-        float dx = __fadd_rn(__fmul_rn(__fadd_rn(r0, r2), f1), __fmul_rn(r1, f0));
-        // Dy: row pass [1 2 1]*scale left-to-right, column pass [-1 0 1] (exact difference of floats)
-        float t0 = __fadd_rn(__fadd_rn(__fmul_rn(a00, f1), __fmul_rn(a01, f0)), __fmul_rn(a02, f1));
-        float t2 = __fadd_rn(__fadd_rn(__fmul_rn(a20, f1), __fmul_rn(a21, f0)), __fmul_rn(a22, f1));
-        float dy = __fsub_rn(t2, t0);
+        // Dx: column pass [1 2 1]*scale as (S0+S2)*f1 + S1*f0 (S0+S2 is an exact small integer either way)
+        const float dx = __fadd_rn(__fmul_rn((float)((int)sD[r][c] + (int)sD[r + 2][c]), f1), __fmul_rn((float)sD[r + 1][c], f0));
+        // Dy: column pass [-1 0 1]
+        const float dy = __fsub_rn(sT[r + 2][c], sT[r][c]);
         sxx[r][c] = (double)__fmul_rn(dx, dx);
         sxy[r][c] = (double)__fmul_rn(dx, dy);
         syy[r][c] = (double)__fmul_rn(dy, dy);
     }
     __syncthreads();
-    // 2b. positions outside the image: BORDER_REFLECT_101 of the product maps (the source lies inside this tile)
+    // 2c. positions outside the image: BORDER_REFLECT_101 of the product maps (the source lies inside this tile)
     if (x0 == 0 || y0 == 0 || x0 + EIG_TW + 2 > G.w || y0 + EIG_TH + 2 > G.h) {
         for (int i = tid; i < EN_PH * EN_PW; i += 256) {
             const int r = i / EN_PW, c = i - r * EN_PW;
@@ -147,23 +164,31 @@ __global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lan
     if (lane == 0 && lmax) atomicMax(&smax, lmax);
     __syncthreads();
     if (tid == 0 && smax) atomicMax(D.eig_max, smax);
-    // 4. 3x3 non-max suppression on the tile (4 positions per thread), warp-ballot compaction, one global atomic per CTA
+    // 4. 3x3 non-max suppression on the tile, warp-ballot compaction, one global atomic per CTA.  A thread owns four
+    //    vertically adjacent positions (column c, rows 4q..4q+3): six rows of three eigenvalues give the row-wise maxima
+    //    once, "e >= all eight neighbours" becomes e >= max(row above, row below, left, right) - no branches.
     bool is[4];
     float ev[4];
     int npos = 0;
+    const int nc = tid & (EIG_TW - 1), nq = tid / EIG_TW;
+    {
+        float hm[6], side[6], ctr[6];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = tid + 256 * k;
-        const int r = i / EIG_TW, c = i - r * EIG_TW;
-        const int x = x0 + c, y = y0 + r;
-        const float e = se[r + 1][c + 1];
-        ev[k] = e;
-        is[k] = false;
-        if (x >= 1 && x < G.w - 1 && y >= 1 && y < G.h - 1 && e > 0.f) {
-            is[k] = e >= se[r + 1][c] && e >= se[r + 1][c + 2] && e >= se[r][c] && e >= se[r][c + 1] && e >= se[r][c + 2] &&
-                    e >= se[r + 2][c] && e >= se[r + 2][c + 1] && e >= se[r + 2][c + 2];
+        for (int j = 0; j < 6; ++j) {
+            const float l = se[4 * nq + j][nc], m = se[4 * nq + j][nc + 1], rr = se[4 * nq + j][nc + 2];
+            side[j] = fmaxf(l, rr);
+            hm[j] = fmaxf(side[j], m);
+            ctr[j] = m;
         }
-        npos += is[k] ? 1 : 0;
+        const int x = x0 + nc;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int y = y0 + 4 * nq + k;
+            const float e = ctr[k + 1];
+            ev[k] = e;
+            is[k] = x >= 1 && x < G.w - 1 && y >= 1 && y < G.h - 1 && e > 0.f && e >= fmaxf(fmaxf(hm[k], hm[k + 2]), side[k + 1]);
+            npos += is[k] ? 1 : 0;
+        }
     }
     // exclusive prefix of npos inside the warp, then across warps
     int incl = npos;
@@ -180,11 +205,8 @@ __global__ void __launch_bounds__(256) k_eig_nms(const LaneDev* __restrict__ lan
         int pos = s_base + s_warp_off[warp] + incl - npos;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (is[k]) {
-                const int i = tid + 256 * k;
-                const int r = i / EIG_TW, c = i - r * EIG_TW;
-                D.cand[pos++] = ((unsigned long long)__float_as_uint(ev[k]) << 32) | (unsigned)((y0 + r) * G.w + x0 + c);
-            }
+            if (is[k])
+                D.cand[pos++] = ((unsigned long long)__float_as_uint(ev[k]) << 32) | (unsigned)((y0 + 4 * nq + k) * G.w + x0 + nc);
         }
     }
 }

@@ -426,14 +426,14 @@ __global__ void __launch_bounds__(32) k_smooth_only(const LaneDev* __restrict__ 
     __shared__ float gk[512];
     const LaneDev& L = lanes[blockIdx.z];
     if (threadIdx.x == 0)
-        smooth_and_setup(L, info.wp_slot ? L.wpb[1] : L.wpb[0], info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
+        smooth_and_setup(L, L.wpb[info.wp_slot], info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
 }
 
 __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict__ lanes, StepInfo info) {
     extern __shared__ unsigned char mo_raw[];
     MoSmem& S = *reinterpret_cast<MoSmem*>(mo_raw);
     const LaneDev& L = lanes[blockIdx.z];
-    WarpParams* const wp_out = info.wp_slot ? L.wpb[1] : L.wpb[0];
+    WarpParams* const wp_out = L.wpb[info.wp_slot];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const int n_prev = min(min(*L.kpc[info.kp_slot], L.kp_capacity), MO_MAXP);
