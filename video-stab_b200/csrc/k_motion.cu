@@ -301,6 +301,81 @@ static __device__ int motion_intent(const Traj aux, int n_tr, const float* motio
     return 0;
 }
 
+// ---- warp-cooperative versions of the sequential float32 smoothing arithmetic ---------------------------------------
+// The reference sums in a fixed order in float32, so the ORDER cannot change - but the loads can run in parallel and the
+// ordered sum can be fed from registers: lane k holds sample k, every lane replays the same chain
+// s = (...((0 + v0) + v1) ...) + v_{cnt-1} from broadcast shuffles.  The shuffles are independent of the adds, so they
+// pipeline; one thread walking shared memory paid a load latency per term (6.6 us -> about 2 us for the whole section).
+template <int MAXN>
+static __device__ __forceinline__ float warp_seq_sum(float v, int cnt, float s = 0.f) {
+#pragma unroll
+    for (int k = 0; k < MAXN; ++k) {
+        const float t = __shfl_sync(0xffffffffu, v, k);
+        if (k < cnt) s = __fadd_rn(s, t);
+    }
+    return s;
+}
+
+static __device__ int adaptive_radius_warp(const Traj path, int n, int smoothing_radius, int lane) {
+    // calculateAdaptiveRadius, Stabilizer.cpp:1637-1673 (same operations as adaptive_radius above)
+    if (n < 10) return smoothing_radius;
+    const int start = max(0, n - 20), c = n - start;
+    const float cnt = (float)c;
+    const bool on = lane < c;
+    const float v0 = on ? path.at(start + lane, 0) : 0.f, v1 = on ? path.at(start + lane, 1) : 0.f, v2 = on ? path.at(start + lane, 2) : 0.f;
+    const float mx = __fdiv_rn(warp_seq_sum<20>(v0, c), cnt), my = __fdiv_rn(warp_seq_sum<20>(v1, c), cnt), ma = __fdiv_rn(warp_seq_sum<20>(v2, c), cnt);
+    const float dx = __fsub_rn(v0, mx), dy = __fsub_rn(v1, my), da = __fsub_rn(v2, ma);
+    const float vx = __fdiv_rn(warp_seq_sum<20>(__fmul_rn(dx, dx), c), cnt), vy = __fdiv_rn(warp_seq_sum<20>(__fmul_rn(dy, dy), c), cnt),
+                va = __fdiv_rn(warp_seq_sum<20>(__fmul_rn(da, da), c), cnt);
+    const float total = f_sqrt(__fadd_rn(__fadd_rn(vx, vy), __fmul_rn(va, 1000.f)));
+    return (int)fmaxf(5.0f, fminf(25.0f, __fmul_rn(total, 2.0f)));
+}
+
+static __device__ void box_at_warp(const Traj path, int n, int radius, int i, int drone, int lane, float* sm) {
+    // boxFilterConvolve, Stabilizer.cpp:1139-1172, element i of all three components
+    const int r = drone ? max(10, min(radius, 50)) : max(2, min(radius, 8));
+    if (n <= r) { sm[0] = path.at(i, 0); sm[1] = path.at(i, 1); sm[2] = path.at(i, 2); return; }
+    const int lo = max(0, i - r), hi = min(n - 1, i + r);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int base = lo; base <= hi; base += 32) {               // one pass unless drone mode widens the window
+        const int c = min(32, hi - base + 1);
+        const bool on = lane < c;
+        const float v0 = on ? path.at(base + lane, 0) : 0.f, v1 = on ? path.at(base + lane, 1) : 0.f, v2 = on ? path.at(base + lane, 2) : 0.f;
+        s0 = warp_seq_sum<32>(v0, c, s0); s1 = warp_seq_sum<32>(v1, c, s1); s2 = warp_seq_sum<32>(v2, c, s2);
+    }
+    const float w = (float)(hi - lo + 1);
+    sm[0] = __fdiv_rn(s0, w); sm[1] = __fdiv_rn(s1, w); sm[2] = __fdiv_rn(s2, w);
+}
+
+static __device__ int motion_intent_warp(const Traj aux, int n_tr, float motion_da, int idx, int lane) {
+    // analyzeMotionIntent, Stabilizer.cpp:1676-1719 (same operations as motion_intent above)
+    const float mag = aux.at2(idx, 0);
+    const float ang = (float)((double)__fmul_rn(fabsf(motion_da), 180.0f) / 3.14159265358979323846 * (double)30.0f);
+    if (n_tr < 15) return 0;
+    const int i0 = max(0, idx - 15);
+    const int c = max(0, min(idx, n_tr) - i0);                  // the valid samples are a prefix of [i0, idx)
+    if (c == 0) return 0;
+    const bool on = lane < c;
+    const float mg = on ? aux.at2(i0 + lane, 0) : 0.f, dr = on ? aux.at2(i0 + lane, 1) : 0.f;
+    const float fc = (float)c;
+    // variance_f(dirs)
+    const float dm = __fdiv_rn(warp_seq_sum<15>(dr, c), fc);
+    const float dd = __fsub_rn(dr, dm);
+    const float dv = __fdiv_rn(warp_seq_sum<15>(__fmul_rn(dd, dd), c), fc);
+    // consistency_f(mags)
+    float mc = 0.f;
+    if (c >= 2) {
+        const float mm = __fdiv_rn(warp_seq_sum<15>(mg, c), fc);
+        const float md = __fsub_rn(mg, mm);
+        const float var = __fdiv_rn(warp_seq_sum<15>(__fmul_rn(md, md), c), fc);
+        if (mm != 0.f) mc = fmaxf(0.f, fminf(1.f, __fdiv_rn(1.f, __fadd_rn(1.f, __fdiv_rn(var, __fmul_rn(mm, mm))))));
+    }
+    if (dv < 0.5f && mc > 0.7f && mag > 5.0f) return 1;
+    if (mag < 3.0f && mc < 0.3f && ang > 10.0f) return 2;
+    if (mag > 3.0f && mag < 15.0f && dv > 0.5f) return 3;
+    return 0;
+}
+
 // cv::warpAffine's inversion of the float32 matrix promoted to double (imgwarp.cpp)
 static __host__ __device__ void invert_affine(const float* T, double* m) {
     double M[6];
@@ -422,11 +497,49 @@ static __device__ void smooth_and_setup(const LaneDev& L, WarpParams* wp_out, co
     if (info.n_out < L.record_capacity) L.orec[info.n_out] = rec;
 }
 
+// The same, executed by all 32 lanes of one warp (box smoothing; the gaussian / Kalman variants stay on lane 0).
+static __device__ void smooth_and_setup_warp(const LaneDev& L, WarpParams* wp_out, const StepInfo& info, float* gk, Traj path, Traj trf,
+                                             Traj aux, int lane) {
+    const int i = info.pop_index, n = info.path_len_at_pop;
+    if (i >= n || info.method != 0) {                       // pass-through frame, or a smoother with shared scratch
+        if (lane == 0) smooth_and_setup(L, wp_out, info, gk, path, trf, aux);
+        return;
+    }
+    vs_output_record rec;
+    rec.index = i; rec.passthrough = 0; rec.path_len = n;
+    float sm[3];
+    rec.radius = adaptive_radius_warp(path, n, info.smoothing_radius, lane);       // :808-823
+    box_at_warp(path, n, rec.radius, i, info.drone, lane, sm);
+    float raw[3], diff[3];
+    for (int k = 0; k < 3; ++k) {
+        raw[k] = trf.at(i, k);
+        diff[k] = __fsub_rn(sm[k], path.at(i, k));
+        rec.smoothed[k] = sm[k];
+    }
+    rec.intent = 0;
+    if (i > 0) {                                            // :854-888
+        rec.intent = motion_intent_warp(aux, n, raw[2], i, lane);
+        const float sc = rec.intent == 1 ? 0.5f : rec.intent == 2 ? 1.0f : rec.intent == 3 ? 0.8f : 0.7f;
+        for (int k = 0; k < 3; ++k) diff[k] = __fmul_rn(diff[k], sc);
+    }
+    if (lane != 0) return;
+    const float dx = __fadd_rn(raw[0], diff[0]), dy = __fadd_rn(raw[1], diff[1]);
+    float da = __fadd_rn(raw[2], diff[2]);
+    if (info.horizon_lock) da = 0.f;
+    const float cs = f_cos(da), sn = f_sin(da);
+    const float T[6] = {cs, -sn, dx, sn, cs, dy};
+    WarpParams wp;
+    invert_affine(T, wp.m);
+    for (int k = 0; k < 6; ++k) { wp.T[k] = T[k]; rec.T[k] = T[k]; }
+    wp.passthrough = 0; wp.pad = 0;
+    *wp_out = wp;
+    if (info.n_out < L.record_capacity) L.orec[info.n_out] = rec;
+}
+
 __global__ void __launch_bounds__(32) k_smooth_only(const LaneDev* __restrict__ lanes, StepInfo info) {
     __shared__ float gk[512];
     const LaneDev& L = lanes[blockIdx.z];
-    if (threadIdx.x == 0)
-        smooth_and_setup(L, L.wpb[info.wp_slot], info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
+    smooth_and_setup_warp(L, L.wpb[info.wp_slot], info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0}, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict__ lanes, StepInfo info) {
@@ -637,12 +750,14 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
             int nr = info.min_radius + (int)__fmul_rn(sc, (float)(info.max_radius - info.min_radius));
             L.kalman[VS_KAL_RADIUS_SLOT] = __int_as_float(nr);   // adaptive radius hand-off to the host
         }
-        __threadfence_block();
-        if (info.pop_index >= 0) {
-            const bool in_tail = info.pop_index - (info.drone ? 50 : 20) >= tail_base || tail_base == 0;
-            if (in_tail) smooth_and_setup(L, wp_out, info, S.gk, Traj{S.tail_path, tail_base}, Traj{S.tail_trf, tail_base}, Traj{S.tail_aux, tail_base});
-            else smooth_and_setup(L, wp_out, info, S.gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
-        }
+        __threadfence();                                    // trajectory entries of this frame, for the global-memory view below
+    }
+    // ---- smoothing, intent and warp set-up of the frame being emitted: warp 0, ordered float32 sums fed by shuffles
+    if (warp == 0 && info.pop_index >= 0) {
+        __syncwarp();                                       // lane 0's tail entries are visible to the warp
+        const bool in_tail = info.pop_index - (info.drone ? 50 : 20) >= tail_base || tail_base == 0;
+        if (in_tail) smooth_and_setup_warp(L, wp_out, info, S.gk, Traj{S.tail_path, tail_base}, Traj{S.tail_trf, tail_base}, Traj{S.tail_aux, tail_base}, lane);
+        else smooth_and_setup_warp(L, wp_out, info, S.gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0}, lane);
     }
 }
 
