@@ -193,9 +193,21 @@ def cpu_baseline_sample(seconds_budget=12.0):
         st.stabilize(clip[order[(20 + n) % len(order)]])
         n += 1
     dt = time.perf_counter() - t0
+    # the same path on ONE host thread (SURVEY.md section 8d asks for both), a shorter sample
+    cv2.setNumThreads(1)
+    st1 = StabilizerRef(Parameters(smoothingRadius=SMOOTHING_RADIUS), use_optimized=True)
+    for k in range(5):
+        st1.stabilize(clip[order[k % len(order)]])
+    n1, t1 = 0, time.perf_counter()
+    while n1 < 400 and time.perf_counter() - t1 < 4.0:
+        st1.stabilize(clip[order[(5 + n1) % len(order)]])
+        n1 += 1
+    dt1 = time.perf_counter() - t1
+    cv2.setNumThreads(cores)
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} frames 1080p (~{dt:.0f} s) after 20 warm-up frames, oracle (Stabilizer.cpp host logic restated over cv2 "
-                      f"{cv2.__version__}, optimized paths on, {cores} threads), wall clock"}
+                      f"{cv2.__version__}, optimized paths on, {cores} threads), wall clock",
+            "single_thread": {"value": n1 / dt1, "unit": UNIT, "cores": 1, "sample": f"{n1} frames (~{dt1:.0f} s), cv2.setNumThreads(1)"}}
 
 
 def bind_to_gpu_numa_node(index: int):
