@@ -412,15 +412,21 @@ def run_gpu(args, rank, world, local_rank):
     for _ in range(3):
         sb.build_pyramids(ptrs, W, H, W * 3)
     sb.sync()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record(sb_ext)
-    for _ in range(reps):
-        sb.build_pyramids(ptrs, W, H, W * 3)
-    p1.record(sb_ext)
-    sb.sync()
-    pyr_ms = p0.elapsed_time(p1) / reps
+    def timed_levels(parts):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(sb_ext)
+        for _ in range(reps):
+            sb.build_levels(ptrs, W, H, W * 3, parts)
+        b.record(sb_ext)
+        sb.sync()
+        return a.elapsed_time(b) / reps
+    pyr_ms = timed_levels(3)
+    gray_ms = timed_levels(1)
+    down_ms = timed_levels(2)
     pyr_bytes = (3 * W * H + 960 * 540 + 480 * 270 + 240 * 135) * FRAMES_PER_STEP
+    gray_bytes = (3 * W * H + 960 * 540) * FRAMES_PER_STEP
     pyr_gbs = pyr_bytes / (pyr_ms * 1e-3) / 1e9
+    gray_gbs = gray_bytes / (gray_ms * 1e-3) / 1e9
     del sb
 
     # max over ranks
@@ -461,7 +467,12 @@ def run_gpu(args, rank, world, local_rank):
             "roofline_pyramid": {"bound": "hbm", "kernel": "k_gray_half + k_pyrdown2 (resize + gray + 2 pyrDown levels, 64 frames "
                                                            "per launch pair, timed alone)",
                                  "achieved": pyr_gbs, "peak": peak, "unit": "GB/s", "frac": pyr_gbs / peak,
-                                 "algorithmic_bytes_per_launch": pyr_bytes, "ms_per_launch": pyr_ms},
+                                 "algorithmic_bytes_per_launch": pyr_bytes, "ms_per_launch": pyr_ms,
+                                 "level0": {"kernel": "k_gray_half alone (resize + gray: the HBM-bound half, 3*W*H read + 518 400 written "
+                                                      "per frame)", "achieved": gray_gbs, "frac": gray_gbs / peak,
+                                            "algorithmic_bytes_per_launch": gray_bytes, "ms_per_launch": gray_ms},
+                                 "pyrdown": {"kernel": "k_pyrdown2 alone (level 0 -> levels 1, 2: 0.69 MB per frame, L2-resident, "
+                                                       "latency / issue bound)", "ms_per_launch": down_ms}},
         }
         if world == 1 and not args.no_cpu_baseline:
             if all_cpus:                                   # the CPU baseline gets every host core back (all threads)

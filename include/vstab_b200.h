@@ -256,6 +256,8 @@ vs_status vs_batch_stage_time(vs_batch* b, int stage, double* total_ms, long lon
 /* cv::resize + cvtColor + both pyrDown levels (Stabilizer.cpp:449-450, the pyramid of :611) for every stream of the
  * batch, nothing else: the analysis-image build timed alone (pyramid roofline in bench.py). */
 vs_status vs_batch_build_pyramids(vs_batch* b, const uint8_t* const* d_frames, int width, int height, size_t stride);
+/* The two halves separately: parts & 1 = level 0 (resize + gray, the HBM-bound kernel), parts & 2 = both pyrDown levels. */
+vs_status vs_batch_build_levels(vs_batch* b, const uint8_t* const* d_frames, int width, int height, size_t stride, int parts);
 vs_status vs_batch_stream_counts(vs_batch* b, int stream, int* n_frame_records, int* n_output_records);
 vs_status vs_batch_frame_record(vs_batch* b, int stream, int i, vs_frame_record* rec);
 vs_status vs_batch_output_record(vs_batch* b, int stream, int i, vs_output_record* rec);

@@ -89,6 +89,7 @@ SYMBOLS = {
     "vs_batch_push_device": (_I, [_P, C.POINTER(_P), _I, _I, _SZ, C.POINTER(_P), _SZ, _SZ, C.c_uint, _IP, _IP, _IP]),
     "vs_batch_flush_device": (_I, [_P, C.POINTER(_P), _SZ, _SZ, _IP, _IP, _IP]),
     "vs_batch_build_pyramids": (_I, [_P, C.POINTER(_P), _I, _I, _SZ]),
+    "vs_batch_build_levels": (_I, [_P, C.POINTER(_P), _I, _I, _SZ, _I]),
     "vs_batch_sync": (_I, [_P]),
     "vs_batch_join": (_I, [_P]),
     "vs_batch_stream": (_P, [_P]),

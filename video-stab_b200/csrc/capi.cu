@@ -331,18 +331,21 @@ vs_status vs_batch_launch_count(vs_batch* b, uint64_t* n) {
 }
 // analysis-image build alone (cv::resize + cvtColor + both pyrDown levels) for every stream of the batch, into pyramid
 // slot 0, on the batch's public stream: the launch bench.py times for the pyramid roofline
-vs_status vs_batch_build_pyramids(vs_batch* b, const uint8_t* const* d_frames, int width, int height, size_t stride) {
+vs_status vs_batch_build_levels(vs_batch* b, const uint8_t* const* d_frames, int width, int height, size_t stride, int parts) {
     if (!b || !d_frames) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
     API_BEGIN
     Engine* e = b->eng;
     PtrPack src;
     for (int l = 0; l < e->n_lanes(); ++l) src.p[l] = d_frames[l];
-    launch_gray_resize(e->d_lanes(), e->n_lanes(), src, width, height, stride ? stride : (size_t)width * 3, 0, e->stream());
-    launch_pyrdown(e->d_lanes(), e->n_lanes(), 0, e->stream());
+    if (parts & 1) launch_gray_resize(e->d_lanes(), e->n_lanes(), src, width, height, stride ? stride : (size_t)width * 3, 0, e->stream());
+    if (parts & 2) launch_pyrdown(e->d_lanes(), e->n_lanes(), 0, e->stream());
     cudaError_t ce = cudaGetLastError();
-    if (ce != cudaSuccess) return vs_set_cuda_error(ce, "vs_batch_build_pyramids", __FILE__, __LINE__);
+    if (ce != cudaSuccess) return vs_set_cuda_error(ce, "vs_batch_build_levels", __FILE__, __LINE__);
     return VS_OK;
     API_END
+}
+vs_status vs_batch_build_pyramids(vs_batch* b, const uint8_t* const* d_frames, int width, int height, size_t stride) {
+    return vs_batch_build_levels(b, d_frames, width, height, stride, 3);
 }
 vs_status vs_batch_stream_counts(vs_batch* b, int stream, int* nf, int* no) {
     if (!b || stream < 0 || stream >= b->eng->n_lanes()) return vs_set_error(VS_ERR_INVALID_ARG, "bad stream");

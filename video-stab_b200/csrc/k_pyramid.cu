@@ -221,27 +221,36 @@ void launch_upsample_small(const LaneDev* lanes, int n_lanes, int slot, cudaStre
 #define PD_R1 36
 #define PD_R0 76
 
-static __device__ __forceinline__ void store_with_mirrors(const GrayLevel& lv, int x, int y, uint8_t v) {
-    int xm = INT_MIN, ym = INT_MIN;
-    if (x >= 1 && x <= VS_PAD) xm = -x;
-    else if (x >= lv.w - 1 - VS_PAD && x <= lv.w - 2) xm = 2 * (lv.w - 1) - x;
+// two horizontally adjacent pixels (x even, both inside the level) as one 16-bit store, plus their reflect-101 images
+static __device__ __forceinline__ void store2_with_mirrors(const GrayLevel& lv, int x, int y, unsigned short v2) {
+    uint8_t* r = lv.base + (ptrdiff_t)y * lv.pitch;
+    *reinterpret_cast<unsigned short*>(r + x) = v2;
+    int ym = INT_MIN;
     if (y >= 1 && y <= VS_PAD) ym = -y;
     else if (y >= lv.h - 1 - VS_PAD && y <= lv.h - 2) ym = 2 * (lv.h - 1) - y;
-    uint8_t* r = lv.base + (ptrdiff_t)y * lv.pitch;
-    r[x] = v;
-    if (xm != INT_MIN) r[xm] = v;
-    if (ym != INT_MIN) {
-        uint8_t* rm = lv.base + (ptrdiff_t)ym * lv.pitch;
-        rm[x] = v;
-        if (xm != INT_MIN) rm[xm] = v;
+    uint8_t* rm = lv.base + (ptrdiff_t)(ym == INT_MIN ? y : ym) * lv.pitch;
+    if (ym != INT_MIN) *reinterpret_cast<unsigned short*>(rm + x) = v2;
+    if (x <= VS_PAD || x + 1 >= lv.w - 1 - VS_PAD) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int xx = x + k;
+            int xm = INT_MIN;
+            if (xx >= 1 && xx <= VS_PAD) xm = -xx;
+            else if (xx >= lv.w - 1 - VS_PAD && xx <= lv.w - 2) xm = 2 * (lv.w - 1) - xx;
+            if (xm != INT_MIN) {
+                const uint8_t b = (uint8_t)(v2 >> (8 * k));
+                r[xm] = b;
+                if (ym != INT_MIN) rm[xm] = b;
+            }
+        }
     }
 }
 
 __global__ void __launch_bounds__(256) k_pyrdown2(const LaneDev* __restrict__ lanes, int slot) {
     __shared__ uint32_t L0w[PD_R0][PD_R0 / 4 + 1];    // 80-byte rows: columns x0o-2 .. x0o+77 (word aligned)
-    __shared__ unsigned short H1[PD_R0][PD_R1];
-    __shared__ uint8_t L1[PD_R1][PD_R1];
-    __shared__ unsigned short H2[PD_R1][PD_T2];
+    __shared__ uint32_t H1w[PD_R0][PD_R1 / 2];        // row-pass sums of two adjacent columns per word (each <= 16 * 255)
+    __shared__ __align__(4) uint8_t L1[PD_R1][PD_R1];
+    __shared__ uint32_t H2w[PD_R1][PD_T2 / 2];
     const LaneDev& L = lanes[blockIdx.z];
     const GrayLevel g0 = L.pyr[slot].lv[0], g1 = L.pyr[slot].lv[1], g2 = L.pyr[slot].lv[2];
     const int tid = threadIdx.x;
@@ -267,24 +276,30 @@ __global__ void __launch_bounds__(256) k_pyrdown2(const LaneDev* __restrict__ la
             if (i < NW) L0w[i / RW][i - (i / RW) * RW] = v[k];
         }
     }
-    const uint8_t (*L0)[(PD_R0 / 4 + 1) * 4] = reinterpret_cast<const uint8_t (*)[(PD_R0 / 4 + 1) * 4]>(&L0w[0][0]);
     __syncthreads();
-    // 2. level 1, row pass: H1[r][c] = sum_i k_i L0[r][2c+i]
-    for (int i = tid; i < PD_R0 * PD_R1; i += 256) {
-        const int r = i / PD_R1, c = i - r * PD_R1;
-        const uint8_t* p = &L0[r][2 * c + 2];
-        H1[r][c] = (unsigned short)(p[0] + 4 * p[1] + 6 * p[2] + 4 * p[3] + p[4]);
+    // Both passes work on PAIRS of adjacent output columns.  Row pass: the five taps of column 2m and of column 2m+1 sit in
+    // three aligned words, so each sum is two DP4A with the [1 4 6 4 1] weights as byte masks.  Column pass: the two
+    // 16-bit sums of a pair share a word and 1+4+6+4+1 = 16 row sums of <= 4080 stay below 65536, so one word-wide
+    // multiply-add chain filters both columns; (acc + 128) >> 8 per half with one add, one shift and one mask.
+    // 2. level 1, row pass: H1[r][c] = sum_i k_i L0[r][2c+2+i]   (pair m = columns 2m, 2m+1 = bytes 4m+2 .. 4m+8)
+    for (int i = tid; i < PD_R0 * (PD_R1 / 2); i += 256) {
+        const int r = i / (PD_R1 / 2), m = i - r * (PD_R1 / 2);
+        const uint32_t wa = L0w[r][m], wb = L0w[r][m + 1], wc = L0w[r][m + 2];
+        const uint32_t h0 = __dp4a(wa, 0x04010000u, __dp4a(wb, 0x00010406u, 0u));
+        const uint32_t h1 = __dp4a(wb, 0x04060401u, wc & 255u);
+        H1w[r][m] = h0 | (h1 << 16);
     }
     __syncthreads();
     // 3. level 1, column pass (in-image positions), stored by the owner
-    for (int i = tid; i < PD_R1 * PD_R1; i += 256) {
-        const int r = i / PD_R1, c = i - r * PD_R1;
-        const int x1 = x1o + c, y1 = y1o + r;
+    for (int i = tid; i < PD_R1 * (PD_R1 / 2); i += 256) {
+        const int r = i / (PD_R1 / 2), m = i - r * (PD_R1 / 2), c = 2 * m;
+        const int x1 = x1o + c, y1 = y1o + r;                 // x1 is even and the level width is even: a pair is inside or outside together
         if ((unsigned)x1 < (unsigned)g1.w && (unsigned)y1 < (unsigned)g1.h) {
-            const int acc = H1[2 * r][c] + 4 * H1[2 * r + 1][c] + 6 * H1[2 * r + 2][c] + 4 * H1[2 * r + 3][c] + H1[2 * r + 4][c];
-            const uint8_t v = (uint8_t)((acc + 128) >> 8);
-            L1[r][c] = v;
-            if (r >= 2 && r < 2 + 2 * PD_T2 && c >= 2 && c < 2 + 2 * PD_T2) store_with_mirrors(g1, x1, y1, v);
+            const uint32_t acc = H1w[2 * r][m] + 4u * H1w[2 * r + 1][m] + 6u * H1w[2 * r + 2][m] + 4u * H1w[2 * r + 3][m] + H1w[2 * r + 4][m];
+            const uint32_t v = ((acc + 0x00800080u) >> 8) & 0x00FF00FFu;
+            const unsigned short v2 = (unsigned short)(v | (v >> 8));           // [v(2m), v(2m+1)]
+            *reinterpret_cast<unsigned short*>(&L1[r][c]) = v2;
+            if (r >= 2 && r < 2 + 2 * PD_T2 && c >= 2 && c < 2 + 2 * PD_T2) store2_with_mirrors(g1, x1, y1, v2);
         }
     }
     __syncthreads();
@@ -298,19 +313,23 @@ __global__ void __launch_bounds__(256) k_pyrdown2(const LaneDev* __restrict__ la
         }
     }
     __syncthreads();
-    // 4. level 2: row pass over the 36 region rows, then column pass
-    for (int i = tid; i < PD_R1 * PD_T2; i += 256) {
-        const int r = i / PD_T2, c = i - r * PD_T2;
-        const uint8_t* p = &L1[r][2 * c];
-        H2[r][c] = (unsigned short)(p[0] + 4 * p[1] + 6 * p[2] + 4 * p[3] + p[4]);
+    // 4. level 2: row pass over the 36 region rows (pair m = columns 2m, 2m+1 = bytes 4m .. 4m+6 of the L1 row), then column pass
+    const uint32_t (*L1w)[PD_R1 / 4] = reinterpret_cast<const uint32_t (*)[PD_R1 / 4]>(&L1[0][0]);
+    for (int i = tid; i < PD_R1 * (PD_T2 / 2); i += 256) {
+        const int r = i / (PD_T2 / 2), m = i - r * (PD_T2 / 2);
+        const uint32_t wa = L1w[r][m], wb = L1w[r][m + 1];
+        const uint32_t h0 = __dp4a(wa, 0x04060401u, wb & 255u);
+        const uint32_t h1 = __dp4a(wa, 0x04010000u, __dp4a(wb, 0x00010406u, 0u));
+        H2w[r][m] = h0 | (h1 << 16);
     }
     __syncthreads();
-    {
-        const int r = tid / PD_T2, c = tid - r * PD_T2;
-        const int x2 = x2o + c, y2 = y2o + r;
+    if (tid < PD_T2 * (PD_T2 / 2)) {
+        const int r = tid / (PD_T2 / 2), m = tid - r * (PD_T2 / 2);
+        const int x2 = x2o + 2 * m, y2 = y2o + r;
         if (x2 < g2.w && y2 < g2.h) {
-            const int acc = H2[2 * r][c] + 4 * H2[2 * r + 1][c] + 6 * H2[2 * r + 2][c] + 4 * H2[2 * r + 3][c] + H2[2 * r + 4][c];
-            store_with_mirrors(g2, x2, y2, (uint8_t)((acc + 128) >> 8));
+            const uint32_t acc = H2w[2 * r][m] + 4u * H2w[2 * r + 1][m] + 6u * H2w[2 * r + 2][m] + 4u * H2w[2 * r + 3][m] + H2w[2 * r + 4][m];
+            const uint32_t v = ((acc + 0x00800080u) >> 8) & 0x00FF00FFu;
+            store2_with_mirrors(g2, x2, y2, (unsigned short)(v | (v >> 8)));
         }
     }
 }

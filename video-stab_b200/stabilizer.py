@@ -383,6 +383,11 @@ class StabilizerBatch:
         fa = (C.c_void_p * self.n)(*d_frames)
         check(lib.vs_batch_build_pyramids(self._h, fa, w, h, stride))
 
+    def build_levels(self, d_frames, w, h, stride, parts: int):
+        """parts & 1: level 0 (resize + gray); parts & 2: both pyrDown levels."""
+        fa = (C.c_void_p * self.n)(*d_frames)
+        check(lib.vs_batch_build_levels(self._h, fa, w, h, stride, parts))
+
     def sync(self):
         check(lib.vs_batch_sync(self._h))
 
