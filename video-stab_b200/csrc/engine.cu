@@ -127,8 +127,8 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     n_lanes_ = n_lanes;
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    // Three streams per handle (engine.h): analysis (gray, pyramid, LK), motion + output (the public stream), and
-    // corner detection.  adaptive_smoothing reads one int back per frame, so that mode stays on one stream.
+    // Seven streams per handle (engine.h): pyramid, two tracking, motion, two detection, and the public stream for the
+    // warp.  adaptive_smoothing reads one int back per frame, so that mode stays on one stream.
     // VS_SINGLE_STREAM=1 runs everything on the public stream (verification: the multi-stream engine must reproduce it)
     multi_ = !p.adaptive_smoothing && !getenv("VS_SINGLE_STREAM");
     if (multi_) {

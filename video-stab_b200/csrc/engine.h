@@ -1,6 +1,7 @@
 // engine.h — host side of the stabilizer: the reference's stabilize()/flush()/clean() control flow
-// (Stabilizer.cpp:258-400) re-expressed as an asynchronous launch sequence on three CUDA streams per handle
-// (analysis / motion+output / detection) joined by events; see Engine::generate_transform.
+// (Stabilizer.cpp:258-400) re-expressed as an asynchronous launch sequence on seven CUDA streams per handle
+// (pyramid, two tracking, motion, two detection, output) joined by events and slot rings; see
+// Engine::generate_transform and DESIGN.md section 5.
 // One Engine advances n_lanes independent streams in lock-step (n_lanes == 1 is vs::Stabilizer).
 #pragma once
 #include <deque>

@@ -3,11 +3,13 @@
 // at Stabilizer.cpp:355-357 (first frame, user parameters) and :740-744 (every 2nd frame,
 // hard-coded 200 / 0.02 / 15.0 / 3).
 // Specification: oracle/cv_models.py min_eigen_map + gftt (ordered corner list bit-exact vs cv2 4.13
-// on its baseline code path).  Three kernels:
-//   k_min_eig   Sobel -> products -> 3x3 box -> min eigenvalue, shared-memory tiled, + global max
-//   k_candidates threshold + 3x3 non-max suppression, warp-ballot compaction into 64-bit sort keys
-//   k_select    per lane: radix-select of the strongest chunk, shared-memory bitonic sort, and the
-//               order-dependent min-distance greedy pass done 32 candidates at a time by one warp
+// on its baseline code path).  Two kernels:
+//   k_eig_nms   Sobel -> products -> 3x3 box -> min eigenvalue -> 3x3 non-max suppression -> warp-ballot compaction
+//               into 64-bit sort keys + global max, one launch, shared-memory tiled (the eigenvalue map never
+//               reaches HBM)
+//   k_select    per lane: keys <= quality * max dropped, radix-select of the strongest chunk, shared-memory bitonic
+//               sort, and the order-dependent min-distance greedy pass done 32 candidates at a time by one warp;
+//               leaves the detection counters zeroed for the next detection
 // The float map must match OpenCV's op order exactly (no FMA contraction: explicit _rn intrinsics).
 #include "kernels.h"
 
