@@ -234,6 +234,29 @@ def test_pyr_lk_bit_exact(vsb, cv2_noopt, seed, ang, shift):
         f"max diff {np.abs(got[ok] - ref.reshape(-1, 2)[ok]).max()}"
 
 
+@pytest.mark.parametrize("seed,ang,shift", [(81, 0.1, (14.5, 12.25)), (82, 0.0, (20.0, 18.0)), (83, -0.2, (-16.0, -13.5))])
+def test_pyr_lk_points_leaving_the_frame(vsb, cv2_noopt, seed, ang, shift):
+    """Points along the four borders with a motion that carries many of them out of the frame: OpenCV drops the status
+    of a point whose FINAL window origin lies outside level 0 (the re-check it makes when it computes `err`, which the
+    reference requests), besides the checks inside the iteration loop."""
+    cv2 = cv2_noopt
+    prev, nxt = _moved_pair(vsb, cv2, seed, ang, shift)
+    xs = np.arange(8, 960, 37, dtype=np.float32)
+    ys = np.arange(10, 540, 38, dtype=np.float32)
+    pts = np.concatenate([np.stack([xs, np.full_like(xs, 536.0)], 1), np.stack([xs, np.full_like(xs, 2.0)], 1),
+                          np.stack([np.full_like(ys, 956.0), ys], 1), np.stack([np.full_like(ys, 3.0), ys], 1)]).astype(np.float32)
+    ref, st, _ = cv2.calcOpticalFlowPyrLK(prev, nxt, pts, None, winSize=(15, 15), maxLevel=2,
+                                          criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 20, 0.03))
+    ref, st = ref.reshape(-1, 2), st.ravel()
+    org = np.floor(ref - 7)
+    left = (org[:, 0] < -15) | (org[:, 0] >= 960) | (org[:, 1] < -15) | (org[:, 1] >= 540)
+    assert int((left & (st == 0)).sum()) >= 5, "the case no longer exercises points that end outside the frame"
+    got, gst = vsb.kernels.pyr_lk(_dev(prev), _dev(nxt), pts)
+    assert np.array_equal(gst, st), f"status differs at {np.nonzero(gst != st)[0]}"
+    ok = st == 1
+    assert np.array_equal(got[ok].view(np.uint32), ref[ok].view(np.uint32))
+
+
 @pytest.mark.parametrize("n,outl,noise", [(200, 0.0, 0.05), (200, 0.3, 0.2), (60, 0.5, 0.5), (12, 0.25, 0.1),
                                           (4, 0.0, 0.01), (150, 0.7, 0.3), (1500, 0.4, 0.3), (3, 0.0, 0.0), (0, 0, 0)])
 def test_ransac_partial_affine(vsb, cv2_noopt, n, outl, noise):

@@ -439,3 +439,62 @@ def test_multi_stream_engine_equals_single_stream(vsb, monkeypatch, w, h, n, kw)
         else:
             assert got == want[0], f"rep {rep}: frames {[i for i in range(n) if got[i] != want[0][i]][:8]} differ"
             assert recs == want[1], f"rep {rep}: transforms differ"
+
+
+def _sweep_case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    w, h = [(640, 360), (644, 362), (960, 540), (1280, 720), (1000, 562)][int(rng.integers(0, 5))]
+    kw = dict(smoothingRadius=int(rng.integers(5, 36)),
+              smoothingMethod=["box", "box", "gaussian", "kalman"][int(rng.integers(0, 4))],
+              gaussianSigma=float(rng.choice([1.0, 2.0, 3.5])),
+              horizonLock=bool(rng.integers(0, 2)),
+              maxCorners=int(rng.choice([40, 200, 600])),
+              qualityLevel=float(rng.choice([0.01, 0.05])),
+              minDistance=float(rng.choice([8.0, 15.0, 30.0])))
+    border = int(rng.choice([0, 0, 9, 24]))
+    if border:
+        kw["borderSize"] = border
+        mode = int(rng.integers(0, 6))
+        if mode == 5:
+            kw["cropNZoom"] = True
+        else:
+            kw["borderType"] = ["black", "reflect", "replicate", "wrap", "fade"][mode]
+    if (w * 9 == h * 16) and w >= 960 and rng.integers(0, 3) == 0:
+        kw["droneHighFreqMode"] = True
+    return w, h, kw
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_parameter_sweep_vs_live_oracle(vsb, cv2_noopt, seed):
+    """Random points of the configuration space (smoother, radius, corner parameters, border mode, crop-zoom, fade,
+    drone mode, frame sizes that do and do not take the aligned fast paths) against the oracle run live: corner lists
+    and LK status bit-exact, transforms within 1e-3 px, frames within 1 LSB away from the border band."""
+    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    w, h, kw = _sweep_case(seed)
+    n = 44
+    clip = vsb.synth.make_clip(w, h, n, 600 + seed)
+    ref_outs, ref = run_clip(clip, RP(**kw))
+    outs, st = _run(vsb, clip, vsb.Parameters(**kw))
+    assert len(outs) == len(ref_outs) == n, kw
+    nf, no = st.counts()
+    assert nf == len(ref.frame_records)
+    assert np.array_equal(st.first_corners(), ref.first_corners), kw
+    for i, fr in enumerate(ref.frame_records):
+        rec = st.frame_record(i)
+        pts = st.frame_points(i)
+        assert np.array_equal(pts["status"], fr.status), f"{kw} frame {i}: LK status"
+        if fr.detected is not None:
+            assert np.array_equal(pts["detected"], fr.detected), f"{kw} frame {i}: corner list"
+        d = np.abs(np.asarray(rec.transform, np.float32) - fr.transform)
+        assert d[0] < 1e-3 and d[1] < 1e-3 and d[2] * HALF_DIAG < 1e-3, f"{kw} frame {i}: {rec.transform} vs {fr.transform}"
+    band = 48
+    fade = kw.get("borderType") == "fade"
+    for k, (a, b) in enumerate(zip(outs, ref_outs)):
+        assert a.shape == b.shape, f"{kw} output {k}"
+        d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+        inner = d[band:-band, band:-band]
+        if fade:
+            assert (inner > 1).mean() < 1e-4 and d.max() <= 12, f"{kw} output {k}"
+        else:
+            assert inner.max() <= 1, f"{kw} output {k}: {inner.max()} LSB"
+            assert d.max() <= 12 and (d > 1).mean() < 1e-3, f"{kw} output {k}"

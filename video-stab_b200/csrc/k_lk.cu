@@ -334,6 +334,14 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restr
             pdx = ddx; pdy = ddy;
         }
     }
+    // OpenCV re-checks the FINAL position when it computes the error measure (err is requested at Stabilizer.cpp:611-619):
+    // a point whose window origin floor(nextPts - halfWin) left the level-0 image keeps its coordinates but loses its
+    // status (lkpyramid.cpp, "if (status[ptidx] && err && level == 0 ...)").
+    if (status) {
+        const GrayLevel J0 = L.pyr[cur].lv[0];
+        const int fx = (int)floorf(__fsub_rn(nx, 7.f)), fy = (int)floorf(__fsub_rn(ny, 7.f));
+        if (fx < -VS_WIN || fx >= J0.w || fy < -VS_WIN || fy >= J0.h) status = 0;
+    }
     if (lane == 0) {
         L.lkn[lk_slot][pidx] = make_float2(nx, ny);
         L.lks[lk_slot][pidx] = (uint8_t)status;
