@@ -464,7 +464,7 @@ def _sweep_case(seed):
     return w, h, kw
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("VS_SWEEP_SEEDS", "12"))))
 def test_random_parameter_sweep_vs_live_oracle(vsb, cv2_noopt, seed):
     """Random points of the configuration space (smoother, radius, corner parameters, border mode, crop-zoom, fade,
     drone mode, frame sizes that do and do not take the aligned fast paths) against the oracle run live: corner lists
