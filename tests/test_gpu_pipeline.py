@@ -498,3 +498,44 @@ def test_random_parameter_sweep_vs_live_oracle(vsb, cv2_noopt, seed):
         else:
             assert inner.max() <= 1, f"{kw} output {k}: {inner.max()} LSB"
             assert d.max() <= 12 and (d > 1).mean() < 1e-3, f"{kw} output {k}"
+
+
+def test_degenerate_inputs_vs_live_oracle(vsb, cv2_noopt):
+    """Inputs that push the path through its fallbacks: flat frames (no corners: the no-key-points branch pushes a zero
+    transform, Stabilizer.cpp:676-678), the return of texture (re-detection), a scene cut (tracking / RANSAC failure:
+    identity transform, :646-659), a very dark stretch and heavy noise."""
+    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    w, h = 960, 540
+    a = vsb.synth.make_clip(w, h, 12, 71)
+    b = vsb.synth.make_clip(w, h, 10, 72)                       # unrelated texture: scene cut
+    rng = np.random.default_rng(9)
+    flat = np.full((6, h, w, 3), 127, np.uint8)
+    dark = (a[:6].astype(np.float32) * 0.04).astype(np.uint8)
+    noisy = np.clip(b[:6].astype(np.int16) + rng.normal(0, 40, (6, h, w, 3)), 0, 255).astype(np.uint8)
+    clip = np.concatenate([a, flat, a[::-1][:8], b, dark, noisy, b[:6]])
+    kw = dict(smoothingRadius=6)
+    ref_outs, ref = run_clip(clip, RP(**kw))
+    outs, st = _run(vsb, clip, vsb.Parameters(**kw))
+    n = len(clip)
+    assert len(outs) == len(ref_outs) == n
+    assert st.counts()[0] == len(ref.frame_records)
+    zero_tr = ident = 0
+    for i, fr in enumerate(ref.frame_records):
+        rec = st.frame_record(i)
+        pts = st.frame_points(i)
+        assert rec.n_prev_pts == len(fr.prev_pts), f"frame {i}: {rec.n_prev_pts} key points vs {len(fr.prev_pts)}"
+        assert np.array_equal(pts["status"], fr.status), f"frame {i}: LK status"
+        if fr.detected is not None:
+            assert np.array_equal(pts["detected"], fr.detected), f"frame {i}: corner list"
+        if fr.inlier_mask is not None:
+            assert np.array_equal(pts["inlier_mask"], fr.inlier_mask), f"frame {i}: inlier mask"
+        else:
+            assert pts["inlier_mask"] is None, f"frame {i}: the oracle found no model"
+            ident += 1
+        d = np.abs(np.asarray(rec.transform, np.float32) - fr.transform)
+        assert d[0] < 1e-3 and d[1] < 1e-3 and d[2] * HALF_DIAG < 1e-3, f"frame {i}: {rec.transform} vs {fr.transform}"
+        zero_tr += int(len(fr.prev_pts) == 0)
+    assert zero_tr >= 2 and ident >= 1, f"the clip no longer reaches the fallbacks ({zero_tr} empty, {ident} identity)"
+    for k, (x, y) in enumerate(zip(outs, ref_outs)):
+        dd = np.abs(x.astype(np.int16) - y.astype(np.int16))
+        assert dd[40:-40, 40:-40].max() <= 1 and (dd > 1).mean() < 1e-3, f"output {k}"
