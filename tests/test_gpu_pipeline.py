@@ -539,3 +539,31 @@ def test_degenerate_inputs_vs_live_oracle(vsb, cv2_noopt):
     for k, (x, y) in enumerate(zip(outs, ref_outs)):
         dd = np.abs(x.astype(np.int16) - y.astype(np.int16))
         assert dd[40:-40, 40:-40].max() <= 1 and (dd > 1).mean() < 1e-3, f"output {k}"
+
+
+@pytest.mark.parametrize("w,h", [(320, 240), (100, 60), (1366, 768), (2560, 1440), (1922, 1082), (3840, 2160)])
+def test_unusual_frame_sizes_vs_live_oracle(vsb, cv2_noopt, w, h):
+    """4:3, tiny, not-a-multiple-of-4, 1440p and 4K frames: the analysis image is always 960x540 (up- or down-scaled with
+    cv::resize's arithmetic), the output stage takes the aligned TMA kernels or the fallbacks depending on the row pitch."""
+    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    n = 16
+    clip = vsb.synth.make_clip(w, h, n, 4000 + w)
+    kw = dict(smoothingRadius=5, borderSize=6 if w < 2000 else 0, cropNZoom=(w == 1366))
+    ref_outs, ref = run_clip(clip, RP(**kw))
+    outs, st = _run(vsb, clip, vsb.Parameters(**kw))
+    assert len(outs) == len(ref_outs) == n
+    assert np.array_equal(st.first_corners(), ref.first_corners)
+    for i, fr in enumerate(ref.frame_records):
+        rec = st.frame_record(i)
+        pts = st.frame_points(i)
+        assert np.array_equal(pts["status"], fr.status), f"frame {i}: LK status"
+        if fr.detected is not None:
+            assert np.array_equal(pts["detected"], fr.detected), f"frame {i}: corner list"
+        d = np.abs(np.asarray(rec.transform, np.float32) - fr.transform)
+        assert d[0] < 1e-3 and d[1] < 1e-3 and d[2] * HALF_DIAG < 1e-3, f"frame {i}: {rec.transform} vs {fr.transform}"
+    band = max(8, min(40, h // 8))
+    for k, (a, b) in enumerate(zip(outs, ref_outs)):
+        assert a.shape == b.shape, f"output {k}: {a.shape} vs {b.shape}"
+        d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+        assert d[band:-band, band:-band].max() <= 1, f"output {k}: {d[band:-band, band:-band].max()} LSB"
+        assert (d > 1).mean() < 2e-3, f"output {k}"
