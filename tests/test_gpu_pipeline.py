@@ -567,3 +567,28 @@ def test_unusual_frame_sizes_vs_live_oracle(vsb, cv2_noopt, w, h):
         d = np.abs(a.astype(np.int16) - b.astype(np.int16))
         assert d[band:-band, band:-band].max() <= 1, f"output {k}: {d[band:-band, band:-band].max()} LSB"
         assert (d > 1).mean() < 2e-3, f"output {k}"
+
+
+def test_adaptive_smoothing_frames_vs_live_oracle(vsb, cv2_noopt):
+    """adaptive_smoothing (Stabilizer.cpp:691-693, 1461-1492, 1562-1574): the radius follows the last motion, moves the
+    latency gate, and the run stays on one stream with one int read back per frame - frames and records as the oracle's."""
+    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    w, h, n = 960, 540, 60
+    clip = vsb.synth.make_clip(w, h, n, 91)
+    kw = dict(smoothingRadius=12, adaptiveSmoothing=True, minSmoothingRadius=6, maxSmoothingRadius=20)
+    ref_outs, ref = run_clip(clip, RP(**kw))
+    outs, st = _run(vsb, clip, vsb.Parameters(**kw))
+    assert len(outs) == len(ref_outs)
+    assert st.counts()[0] == len(ref.frame_records)
+    for i, fr in enumerate(ref.frame_records):
+        d = np.abs(np.asarray(st.frame_record(i).transform, np.float32) - fr.transform)
+        assert d[0] < 1e-3 and d[1] < 1e-3 and d[2] * HALF_DIAG < 1e-3, f"frame {i}"
+    for k, orec in enumerate(ref.output_records):
+        r = st.output_record(k)
+        assert r.index == orec.index and bool(r.passthrough) == (orec.T is None), f"output {k}"
+        if orec.T is not None:
+            assert r.radius == orec.radius and r.intent == orec.intent, f"output {k}: radius {r.radius} vs {orec.radius}"
+    for k, (a, b) in enumerate(zip(outs, ref_outs)):
+        assert a.shape == b.shape
+        d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+        assert d[40:-40, 40:-40].max() <= 1 and (d > 1).mean() < 1e-3, f"output {k}"
