@@ -6,6 +6,7 @@
 #include "engine.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 static thread_local char g_err[512] = "";
@@ -84,6 +85,9 @@ vs_status Engine::create(const vs_params& p, int device, int n_lanes, Engine** o
     if (p.block_size != 3) return vs_set_error(VS_ERR_UNSUPPORTED, "only block_size 3 (the reference default) is supported");
     if (p.adaptive_smoothing && n_lanes > 1)
         return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing makes the latency gate data dependent; single-stream handles only");
+    // A handle uses up to nine streams (seven + two copy streams); the default of eight hardware queues would make two of
+    // them share one.  Only effective when the process has not initialised CUDA yet, never overrides the user's value.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) {
