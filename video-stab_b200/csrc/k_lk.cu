@@ -111,7 +111,7 @@ static __device__ __forceinline__ float ordered_sum_b(const int* t, int lane) {
     return __fadd_rn(tl, __fadd_rn(__fadd_rn(p0, p2), __fadd_rn(p1, p3)));
 }
 
-__global__ void __launch_bounds__(LK_WARPS * 32) k_pyr_lk(const LaneDev* __restrict__ lanes, int prev, int cur, int kp_slot, int lk_slot) {
+__global__ void __launch_bounds__(LK_WARPS * 32, 5) k_pyr_lk(const LaneDev* __restrict__ lanes, int prev, int cur, int kp_slot, int lk_slot) {
     __shared__ LkSmem smem[LK_WARPS];
     const LaneDev& L = lanes[blockIdx.z];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
