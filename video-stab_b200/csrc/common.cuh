@@ -10,11 +10,12 @@
 
 #define VS_PAD 16            // reflect-101 border kept around every gray pyramid level
 #define VS_WIN 15            // LK window (Stabilizer.cpp:616)
-#define VS_PYR_SLOTS 6       // pyramids kept per lane (frames n-1, n for LK + 4 frames of run-ahead)
+#define VS_PYR_SLOTS 12      // pyramids kept per lane (frames n-1, n for LK + the run-ahead of the pyramid stream)
+#define VS_EV_RING 16        // per-frame event rings (must exceed VS_PYR_SLOTS - 1, the distance of the slot guard)
 #define VS_LEVELS 3          // maxLevel 2 (Stabilizer.cpp:617)
 #define VS_WP_SLOTS 8        // warp set-up buffers (LaneDev::wpb), by output index % VS_WP_SLOTS
-#define VS_KP_SLOTS 4        // key-point buffers (LaneDev::kpb / kpc), by (detection frame / 2) % VS_KP_SLOTS
-#define VS_LK_SLOTS 8        // tracker output buffers (LaneDev::lkn / lks), by frame % VS_LK_SLOTS
+#define VS_KP_SLOTS 8        // key-point buffers (LaneDev::kpb / kpc), by (detection frame / 2) % VS_KP_SLOTS
+#define VS_LK_SLOTS 16       // tracker output buffers (LaneDev::lkn / lks), by frame % VS_LK_SLOTS
 #define VS_AW 960            // analysis size (Stabilizer.cpp:410)
 #define VS_AH 540
 #define VS_FW 480            // first-frame analysis size (Stabilizer.cpp:277)
@@ -99,6 +100,12 @@ struct LaneDev {
 #define VS_HF_FREEZE_COUNTER 25
 #define VS_HF_ACCUMULATOR 26
 #define VS_HF_FLOATS 32
+
+// One wait guards every slot ring: before gray(n) overwrites pyramid slot n % VS_PYR_SLOTS the pyramid stream waits for
+// motion(n - VS_PYR_SLOTS + 1).  The other rings must not be reused any sooner than that:
+static_assert(VS_LK_SLOTS >= VS_PYR_SLOTS - 1, "tracker-output slot n % VS_LK_SLOTS is last read by motion(n - VS_LK_SLOTS)");
+static_assert(2 * VS_KP_SLOTS - 2 >= VS_PYR_SLOTS - 1, "key-point slot of detect(n) is last read by motion(n - 2 * VS_KP_SLOTS + 2)");
+static_assert(VS_EV_RING > VS_PYR_SLOTS - 1 && (VS_EV_RING & (VS_EV_RING - 1)) == 0, "event ring");
 
 struct StepInfo {
     int frame_no;          // n >= 1: this is the n-th generateTransform() call (frame n)

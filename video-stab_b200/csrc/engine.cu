@@ -480,33 +480,34 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         launches_ += 2;
     }
     if (multi_) {
-        // Slot `cur` was last read by LK(frame_no - 5) (as its previous frame) and LK(frame_no - 6) (as its current
-        // frame), and by the detection of frame_no - 6.  ONE wait covers them and more: motion(frame_no - 5) complete
-        // means LK(frame_no - 5) complete (it consumed its output), hence the detection whose key points that LK used,
-        // and - the motion stream being in order - motion and LK of every earlier frame.  The tracker-output slots
-        // (VS_LK_SLOTS = 8 > 5) and key-point slots (2 * VS_KP_SLOTS = 8 > 5 frames) are guarded by the same wait,
-        // because LK(n) and the detection of frame n both start after pyramid(n).
+        // Slot `cur` was last read by LK(frame_no - VS_PYR_SLOTS + 1) (as its previous frame), LK(frame_no - VS_PYR_SLOTS)
+        // (as its current frame) and the detection of frame_no - VS_PYR_SLOTS.  ONE wait covers them and more:
+        // motion(guard) complete means LK(guard) complete (it consumed its output), hence the detection whose key points
+        // that LK used, and - the motion stream being in order - motion and LK of every earlier frame.  The tracker-
+        // output and key-point rings are at least as deep (static_asserts in common.cuh), and LK(n) and the detection
+        // of frame n both start after pyramid(n), so the same wait guards them.  The rings are deeper than the
+        // pipeline is long (gray -> motion takes ~150 us, 5 - 6 frame periods), so the wait never binds.
         const int guard = frame_no - VS_PYR_SLOTS + 1;
-        if (guard >= 1 && evB_set_[guard & 7]) CUDA_TRY(cudaStreamWaitEvent(sp(), evB_[guard & 7], 0));
+        if (guard >= 1 && evB_set_[guard & (VS_EV_RING - 1)]) CUDA_TRY(cudaStreamWaitEvent(sp(), evB_[guard & (VS_EV_RING - 1)], 0));
     }
     { StageScope t(this, VS_STAGE_GRAY, sp());
       launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sp()); }       // :449-450
     { StageScope t(this, VS_STAGE_PYRDOWN, sp());
       launch_pyrdown(d_lanes_, n_lanes_, cur, sp()); }
     if (multi_) {
-        CUDA_TRY(cudaEventRecord(evP_[frame_no & 7], sp()));
+        CUDA_TRY(cudaEventRecord(evP_[frame_no & (VS_EV_RING - 1)], sp()));
         // LK(n) and LK(n+1) are independent (key points are not advanced between detections, Appendix B Q4): they
         // alternate between two tracking streams, so the tracker is not a serial chain
-        CUDA_TRY(cudaStreamWaitEvent(sa(frame_no), evP_[frame_no & 7], 0));
+        CUDA_TRY(cudaStreamWaitEvent(sa(frame_no), evP_[frame_no & (VS_EV_RING - 1)], 0));
         if (c_pending_[kp_slot]) CUDA_TRY(cudaStreamWaitEvent(sa(frame_no), evC_[kp_slot], 0));   // both frames after a detection
     }
     { StageScope t(this, VS_STAGE_LK, sa(frame_no));
       launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa(frame_no)); }   // :611-619
     launches_ += 3;
     if (multi_) {
-        CUDA_TRY(cudaEventRecord(evA_[frame_no & 7], sa(frame_no)));
-        evA_set_[frame_no & 7] = true;
-        CUDA_TRY(cudaStreamWaitEvent(sm(), evA_[frame_no & 7], 0));
+        CUDA_TRY(cudaEventRecord(evA_[frame_no & (VS_EV_RING - 1)], sa(frame_no)));
+        evA_set_[frame_no & (VS_EV_RING - 1)] = true;
+        CUDA_TRY(cudaStreamWaitEvent(sm(), evA_[frame_no & (VS_EV_RING - 1)], 0));
     }
 
     const bool adaptive = p_.adaptive_smoothing != 0;
@@ -523,12 +524,12 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     if (multi_) {
         // one event serves both consumers of this kernel: the tracker-slot guard of LK(frame_no + VS_LK_SLOTS) and the
         // warp of the output this step set up (fewer stream-semaphore operations per frame)
-        CUDA_TRY(cudaEventRecord(evB_[frame_no & 7], sm())); evB_set_[frame_no & 7] = true;
-        if (pop_index >= 0) CUDA_TRY(cudaStreamWaitEvent(stream_, evB_[frame_no & 7], 0));
+        CUDA_TRY(cudaEventRecord(evB_[frame_no & (VS_EV_RING - 1)], sm())); evB_set_[frame_no & (VS_EV_RING - 1)] = true;
+        if (pop_index >= 0) CUDA_TRY(cudaStreamWaitEvent(stream_, evB_[frame_no & (VS_EV_RING - 1)], 0));
     }
 
     ++detect_counter_;
-    if (detect) VS_TRY(redetect(cur, frame_no, frame_no, evP_[frame_no & 7]));   // pyramid-complete event: one record fewer
+    if (detect) VS_TRY(redetect(cur, frame_no, frame_no, evP_[frame_no & (VS_EV_RING - 1)]));   // pyramid-complete event: one record fewer
     if (adaptive) {
         // updateAdaptiveParameters (:691-693, :1562-1574) changes params_.smoothingRadius, which moves the
         // latency gate: the one data-dependent host decision of the path, so this mode reads it back.

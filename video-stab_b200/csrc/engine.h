@@ -111,8 +111,8 @@ private:
     cudaStream_t sM_ = nullptr;               // motion: RANSAC, trajectory, smoothing, warp set-up
     cudaStream_t sA_[2] = {}, sC_[2] = {}, sP_ = nullptr;   // tracking (LK, by frame parity), corner detection (two generations), pyramid build
     bool multi_ = false;
-    cudaEvent_t evA_[8] = {}, evB_[8] = {}, evP_[8] = {}, evJ_[6] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[VS_KP_SLOTS] = {};
-    bool evB_set_[8] = {}, evA_set_[8] = {}, evW_set_[2] = {};
+    cudaEvent_t evA_[VS_EV_RING] = {}, evB_[VS_EV_RING] = {}, evP_[VS_EV_RING] = {}, evJ_[6] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[VS_KP_SLOTS] = {};
+    bool evB_set_[VS_EV_RING] = {}, evA_set_[VS_EV_RING] = {}, evW_set_[2] = {};
     int last_detect_frame_ = -100;
     bool c_pending_[VS_KP_SLOTS] = {};
     cudaStream_t sH_ = nullptr, sO_ = nullptr; // copy-in / copy-out streams of the pipelined host path
