@@ -528,7 +528,7 @@ vs_status vs_k_estimate_affine_partial(const float* from_xy_host, const float* t
     if (ce == cudaSuccess) {
         StepInfo info{};
         info.frame_no = 1; info.cur = 1; info.pop_index = -1; info.smoothing_radius = 30;
-        launch_motion(e->d_lanes(), 1, info, st);
+        launch_motion(e->d_lanes(), 1, info, 0, st);
         ce = cudaStreamSynchronize(st);
     }
     if (ce == cudaSuccess) ce = cudaMemcpy(&rec, L.frec, sizeof(rec), cudaMemcpyDeviceToHost);

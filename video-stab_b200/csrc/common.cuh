@@ -45,6 +45,12 @@ struct WarpParams {
 };
 
 // Per-lane device state.  An array of these lives in HBM; kernels index it with blockIdx.z.
+// result of the frame-independent half of the motion step (k_motion phase 1), consumed by the sequential half (phase 2)
+struct MotionFit {
+    double A, B, TX, TY;
+    int found, n_inl, n, n_prev, iters, pad;
+};
+
 struct LaneDev {
     Pyramid pyr[VS_PYR_SLOTS];      // analysis pyramids, slot = frame % VS_PYR_SLOTS: the pyramid stream can run ahead of tracking
     GrayLevel small0;               // 480x270 gray of the very first frame
@@ -72,6 +78,7 @@ struct LaneDev {
     float* path;                    // 3 floats per frame  (path_)
     float* aux;                     // 2 floats per frame: |t| and atan2(ty,tx) of each transform (motion-intent terms)
     float* kalman;                  // 3 x {x0,x1,P00,P01,P10,P11} incremental Kalman state
+    MotionFit* fit;                 // VS_EV_RING fit records, by frame % VS_EV_RING
     float* hf;                      // drone high-frequency state (VS_HF_* slots), set at creation only
     vs_frame_record* frec;
     vs_output_record* orec;

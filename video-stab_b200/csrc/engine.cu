@@ -225,6 +225,7 @@ vs_status Engine::alloc_fixed() {
         VS_TRY(dalloc(allocs_, &L.first_corners, (size_t)kp_cap_));
         VS_TRY(dalloc(allocs_, &L.kalman, (size_t)VS_KAL_FLOATS));
         VS_TRY(dalloc(allocs_, &L.hf, (size_t)VS_HF_FLOATS));
+        VS_TRY(dalloc(allocs_, &L.fit, (size_t)VS_EV_RING));
         VS_TRY(dalloc(allocs_, &L.wp, (size_t)VS_WP_SLOTS));
         for (int k = 0; k < VS_WP_SLOTS; ++k) L.wpb[k] = L.wp + k;
         size_t ln = (size_t)log_depth_ * kp_cap_;
@@ -505,6 +506,11 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
       launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa(frame_no)); }   // :611-619
     launches_ += 3;
     if (multi_) {
+        // the frame-independent half of the motion step (status filter, RANSAC, refit) runs right behind LK on the
+        // tracking stream; only trajectory + smoothing + set-up stay on the sequential motion stream
+        { StageScope t(this, VS_STAGE_MOTION, sa(frame_no));
+          launch_motion(d_lanes_, n_lanes_, step_info(-1), 1, sa(frame_no)); }
+        launches_ += 1;
         CUDA_TRY(cudaEventRecord(evA_[frame_no & (VS_EV_RING - 1)], sa(frame_no)));
         evA_set_[frame_no & (VS_EV_RING - 1)] = true;
         CUDA_TRY(cudaStreamWaitEvent(sm(), evA_[frame_no & (VS_EV_RING - 1)], 0));
@@ -519,7 +525,7 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     }
     if (pop_index >= 0) VS_TRY(setup_slot_guard());
     { StageScope t(this, VS_STAGE_MOTION, sm());
-      launch_motion(d_lanes_, n_lanes_, step_info(pop_index), sm()); }                 // :629-688 (+ :783-908)
+      launch_motion(d_lanes_, n_lanes_, step_info(pop_index), multi_ ? 2 : 0, sm()); }  // :629-688 (+ :783-908)
     launches_ += 1;
     if (multi_) {
         // one event serves both consumers of this kernel: the tracker-slot guard of LK(frame_no + VS_LK_SLOTS) and the

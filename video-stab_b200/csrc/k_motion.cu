@@ -542,14 +542,19 @@ __global__ void __launch_bounds__(32) k_smooth_only(const LaneDev* __restrict__ 
     smooth_and_setup_warp(L, L.wpb[info.wp_slot], info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0}, threadIdx.x);
 }
 
-__global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict__ lanes, StepInfo info) {
+// phase 0: the whole step in one launch (single-stream engine, batch of one kernel).  The multi-stream engine splits it:
+//   phase 1 (tracking stream, right behind LK, independent from frame to frame): status filter, RANSAC, refit -> L.fit[n]
+//   phase 2 (motion stream, the sequential chain): decomposition, trajectory, records, smoothing, warp set-up
+// so that only the short second half sits on the chain every frame has to wait for.
+__global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict__ lanes, StepInfo info, int phase) {
     extern __shared__ unsigned char mo_raw[];
     MoSmem& S = *reinterpret_cast<MoSmem*>(mo_raw);
     const LaneDev& L = lanes[blockIdx.z];
     WarpParams* const wp_out = L.wpb[info.wp_slot];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
-    const int n_prev = min(min(*L.kpc[info.kp_slot], L.kp_capacity), MO_MAXP);
+    MotionFit* const fit_slot = L.fit + (info.frame_no & (VS_EV_RING - 1));
+    int n_prev = phase == 2 ? fit_slot->n_prev : min(min(*L.kpc[info.kp_slot], L.kp_capacity), MO_MAXP);
     const int fidx = info.frame_no - 1;
     float2* lprev = nullptr; float2* lnext = nullptr; uint8_t* lstat = nullptr; uint8_t* lmask = nullptr;
     if (L.log_depth > 0) {
@@ -559,11 +564,20 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
 
     // ---- stage the tail of the trajectory (entries written by earlier steps) for the sequential part
     const int tail_base = max(0, fidx + 1 - MO_TAIL);
-    for (int i = tid; i < 3 * (fidx - tail_base); i += MO_THREADS) {
-        S.tail_path[i] = L.path[3 * tail_base + i];
-        S.tail_trf[i] = L.transforms[3 * tail_base + i];
+    if (phase != 1) {
+        for (int i = tid; i < 3 * (fidx - tail_base); i += MO_THREADS) {
+            S.tail_path[i] = L.path[3 * tail_base + i];
+            S.tail_trf[i] = L.transforms[3 * tail_base + i];
+        }
+        for (int i = tid; i < 2 * (fidx - tail_base); i += MO_THREADS) S.tail_aux[i] = L.aux[2 * tail_base + i];
     }
-    for (int i = tid; i < 2 * (fidx - tail_base); i += MO_THREADS) S.tail_aux[i] = L.aux[2 * tail_base + i];
+    bool found = false;
+    double A = 1., B = 0., TX = 0., TY = 0.;
+    int n_inl = -1, n = 0, iters = 0;
+    if (phase == 2) {
+        const MotionFit f = *fit_slot;
+        found = f.found != 0; A = f.A; B = f.B; TX = f.TX; TY = f.TY; n_inl = f.n_inl; n = f.n; iters = f.iters;
+    } else {
     // ---- order-preserving compaction of the tracked pairs (status != 0)
     int running = 0;
     for (int base = 0; base < n_prev; base += MO_THREADS) {
@@ -590,7 +604,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         running += tot;
         __syncthreads();
     }
-    const int n = running;
+    n = running;
 
     if (tid == 0) {
         S.n = n; S.niters = VS_RANSAC_MAX_ITERS; S.iter = 0; S.max_good = 0; S.best_found = 0;
@@ -654,7 +668,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
     }
 
     // ---- inlier mask of the winning hypothesis + least-squares similarity refit (double)
-    const bool found = S.best_found != 0;
+    found = S.best_found != 0;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     if (found) {
         float F[6];
@@ -686,8 +700,6 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         }
         __syncthreads();
     };
-    double A = 1., B = 0., TX = 0., TY = 0.;
-    int n_inl = -1;
     if (found) {                                            // uniform across the CTA
         block_reduce(5);
         double cnt = S.red[4][0];
@@ -695,8 +707,11 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         n_inl = (int)cnt;
         __syncthreads();
         for (int k = 0; k < 7; ++k) acc[k] = 0;
+        float F2[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) F2[k] = S.bestF[k];
         for (int i = tid; i < n; i += MO_THREADS) {
-            if (L.inlier_mask[i]) {
+            if (is_inlier(F2, S.from[i], S.to[i])) {    // recomputed: the global mask is shared scratch, two fits may be in flight
                 double xc = S.from[i].x - mx, yc = S.from[i].y - my, uc = S.to[i].x - mu, vc = S.to[i].y - mv;
                 acc[0] += xc * xc + yc * yc;
                 acc[1] += xc * uc + yc * vc;
@@ -709,6 +724,16 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         TX = mu - (A * mx - B * my);
         TY = mv - (B * mx + A * my);
     }
+    iters = S.iter;
+    if (phase == 1) {                                       // hand the fit to the motion stream and stop here
+        if (tid == 0) {
+            MotionFit f;
+            f.A = A; f.B = B; f.TX = TX; f.TY = TY; f.found = found ? 1 : 0; f.n_inl = n_inl; f.n = n; f.n_prev = n_prev; f.iters = iters; f.pad = 0;
+            *fit_slot = f;
+        }
+        return;
+    }
+    }   // phase != 2
     __syncthreads();
 
     // ---- decomposition, trajectory, record, smoothing (one thread; sequential float32 semantics)
@@ -737,7 +762,7 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
         if (fidx < L.record_capacity) {
             vs_frame_record& r = L.frec[fidx];
             r.frame_index = info.frame_no; r.n_prev_pts = n_prev; r.n_tracked = n;
-            r.n_inliers = found ? n_inl : -1; r.ransac_iters = S.iter;
+            r.n_inliers = found ? n_inl : -1; r.ransac_iters = iters;
             if (!info.will_detect) r.n_detected = -1;          // else the detector (another stream) writes it
             for (int k = 0; k < 3; ++k) { r.transform[k] = t[k]; r.path[k] = pa[k]; }
             r.affine[0] = found ? A : 1.; r.affine[1] = found ? -B : 0.; r.affine[2] = found ? TX : 0.;
@@ -761,13 +786,13 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
     }
 }
 
-void launch_motion(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_t st) {
+void launch_motion(const LaneDev* lanes, int n_lanes, StepInfo info, int phase, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_motion, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoSmem));
         attr_set = true;
     }
-    k_motion<<<dim3(1, 1, n_lanes), MO_THREADS, sizeof(MoSmem), st>>>(lanes, info);
+    k_motion<<<dim3(1, 1, n_lanes), MO_THREADS, sizeof(MoSmem), st>>>(lanes, info, phase);
 }
 
 void launch_smooth_only(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_t st) {

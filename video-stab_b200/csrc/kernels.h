@@ -40,7 +40,8 @@ void launch_pyr_lk(const LaneDev* lanes, int n_lanes, int prev, int cur, int max
 
 // ---- k_motion.cu : status filter + estimateAffinePartial2D + decomposition + trajectory +
 //                    smoothing + warp set-up (Stabilizer.cpp:629-688, 783-908, 1139-1172, 1364-1458, 1637-1780)
-void launch_motion(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_t st);
+// phase 0: whole step; 1: status filter + RANSAC + refit -> LaneDev::fit; 2: trajectory, smoothing, set-up from LaneDev::fit
+void launch_motion(const LaneDev* lanes, int n_lanes, StepInfo info, int phase, cudaStream_t st);
 // flush-time variant: no new frame, only the smoothing + warp set-up for `info.pop_index`
 void launch_smooth_only(const LaneDev* lanes, int n_lanes, StepInfo info, cudaStream_t st);
 
