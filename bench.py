@@ -53,7 +53,7 @@ def _peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks and throttle reasons while the timed region runs: NVML from a thread (a sample every ~2 ms,
+    """Samples SM clocks and throttle reasons while the timed region runs: NVML from a thread (a sample every ~4 ms,
     so even a 30 ms region at N = 8 is covered), nvidia-smi -lms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -98,7 +98,7 @@ class ClockSampler:
                 self.mask |= int(reasons(self.h))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -293,7 +293,8 @@ def run_gpu(args, rank, world, local_rank):
     st.sync()
     barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not os.environ.get("VS_BENCH_NO_SAMPLER"):
+        sampler.start()
     l0 = st.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)

@@ -135,6 +135,10 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     // warp.  adaptive_smoothing reads one int back per frame, so that mode stays on one stream.
     // VS_SINGLE_STREAM=1 runs everything on the public stream (verification: the multi-stream engine must reproduce it)
     multi_ = !p.adaptive_smoothing && !getenv("VS_SINGLE_STREAM");
+    // VS_SPLIT_MOTION=1: run the frame-independent half of the motion step behind LK on the tracking streams.  It
+    // shortens the sequential chain (27.2 -> 24.5 us device-side) but costs one more launch per frame, and the loop is
+    // host-bound: measured 5 - 10 % SLOWER end to end in bench.py, so it is off by default.
+    split_motion_ = getenv("VS_SPLIT_MOTION") != nullptr;
     if (multi_) {
         // The analysis kernels are small and latency-critical (a single CTA for k_motion / k_select), the warp is one
         // machine-filling grid: the analysis streams get the higher priority so their CTAs are placed first whenever
@@ -335,12 +339,11 @@ vs_status Engine::sync() {
 // Orders everything enqueued so far (on all three streams) before whatever is enqueued on the public stream next.
 vs_status Engine::join() {
     if (!multi_) return VS_OK;
-    CUDA_TRY(cudaEventRecord(evJ_[0], sA_[0]));
-    CUDA_TRY(cudaEventRecord(evJ_[5], sA_[1]));
-    CUDA_TRY(cudaEventRecord(evJ_[1], sC_[0]));
-    CUDA_TRY(cudaEventRecord(evJ_[4], sC_[1]));
-    CUDA_TRY(cudaEventRecord(evJ_[2], sP_));
-    CUDA_TRY(cudaEventRecord(evJ_[3], sM_));
+    for (int k = 0; k < VS_TRACK_STREAMS; ++k) CUDA_TRY(cudaEventRecord(evJ_[k], sA_[k]));
+    CUDA_TRY(cudaEventRecord(evJ_[VS_TRACK_STREAMS], sC_[0]));
+    CUDA_TRY(cudaEventRecord(evJ_[VS_TRACK_STREAMS + 1], sC_[1]));
+    CUDA_TRY(cudaEventRecord(evJ_[VS_TRACK_STREAMS + 2], sP_));
+    CUDA_TRY(cudaEventRecord(evJ_[VS_TRACK_STREAMS + 3], sM_));
     for (auto& ev : evJ_) CUDA_TRY(cudaStreamWaitEvent(stream_, ev, 0));
     return VS_OK;
 }
@@ -505,12 +508,14 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     { StageScope t(this, VS_STAGE_LK, sa(frame_no));
       launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa(frame_no)); }   // :611-619
     launches_ += 3;
-    if (multi_) {
+    if (multi_ && split_motion_) {
         // the frame-independent half of the motion step (status filter, RANSAC, refit) runs right behind LK on the
         // tracking stream; only trajectory + smoothing + set-up stay on the sequential motion stream
         { StageScope t(this, VS_STAGE_MOTION, sa(frame_no));
           launch_motion(d_lanes_, n_lanes_, step_info(-1), 1, sa(frame_no)); }
         launches_ += 1;
+    }
+    if (multi_) {
         CUDA_TRY(cudaEventRecord(evA_[frame_no & (VS_EV_RING - 1)], sa(frame_no)));
         evA_set_[frame_no & (VS_EV_RING - 1)] = true;
         CUDA_TRY(cudaStreamWaitEvent(sm(), evA_[frame_no & (VS_EV_RING - 1)], 0));
@@ -525,7 +530,7 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     }
     if (pop_index >= 0) VS_TRY(setup_slot_guard());
     { StageScope t(this, VS_STAGE_MOTION, sm());
-      launch_motion(d_lanes_, n_lanes_, step_info(pop_index), multi_ ? 2 : 0, sm()); }  // :629-688 (+ :783-908)
+      launch_motion(d_lanes_, n_lanes_, step_info(pop_index), (multi_ && split_motion_) ? 2 : 0, sm()); }  // :629-688 (+ :783-908)
     launches_ += 1;
     if (multi_) {
         // one event serves both consumers of this kernel: the tracker-slot guard of LK(frame_no + VS_LK_SLOTS) and the

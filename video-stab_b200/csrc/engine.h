@@ -11,6 +11,7 @@
 #include "kernels.h"
 
 enum { VS_IO_DEVICE = 0, VS_IO_HOST_SYNC = 1, VS_IO_HOST_PIPE = 2 };   // where push()/flush() frames live
+#define VS_TRACK_STREAMS 2                // LK of frame n runs on tracking stream n % 2 (four measured no faster)
 #define VS_OUT_SLOTS 3                    // output staging frames of the pipelined host path
 enum { VS_STAGE_GRAY = 0, VS_STAGE_PYRDOWN, VS_STAGE_LK, VS_STAGE_MOTION, VS_STAGE_GFTT, VS_STAGE_WARP, VS_N_STAGES };
 
@@ -95,7 +96,7 @@ private:
     vs_status generate_transform(const QueueEntry& e, bool* will_pop);
     vs_status first_frame_detect(const PtrPack& src, int w, int h, size_t stride);
     vs_status redetect(int cur, int frame_no, int record_frame_no, cudaEvent_t level0_ready);
-    cudaStream_t sa(int frame_no) const { return multi_ ? sA_[frame_no & 1] : stream_; }
+    cudaStream_t sa(int frame_no) const { return multi_ ? sA_[frame_no % VS_TRACK_STREAMS] : stream_; }
     cudaStream_t sp() const { return multi_ ? sP_ : stream_; }
     cudaStream_t sm() const { return multi_ ? sM_ : stream_; }
     vs_status setup_slot_guard();
@@ -109,12 +110,13 @@ private:
     int device_ = 0, n_lanes_ = 0;
     cudaStream_t stream_ = nullptr;           // public stream: output stage (warp, copies out)
     cudaStream_t sM_ = nullptr;               // motion: RANSAC, trajectory, smoothing, warp set-up
-    cudaStream_t sA_[2] = {}, sC_[2] = {}, sP_ = nullptr;   // tracking (LK, by frame parity), corner detection (two generations), pyramid build
+    cudaStream_t sA_[VS_TRACK_STREAMS] = {}, sC_[2] = {}, sP_ = nullptr;   // tracking (LK + motion fit, round-robin), corner detection (two generations), pyramid build
     bool multi_ = false;
-    cudaEvent_t evA_[VS_EV_RING] = {}, evB_[VS_EV_RING] = {}, evP_[VS_EV_RING] = {}, evJ_[6] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[VS_KP_SLOTS] = {};
+    cudaEvent_t evA_[VS_EV_RING] = {}, evB_[VS_EV_RING] = {}, evP_[VS_EV_RING] = {}, evJ_[VS_TRACK_STREAMS + 4] = {}, evS_[2] = {}, evW_[2] = {}, evG_ = nullptr, evC_[VS_KP_SLOTS] = {};
     bool evB_set_[VS_EV_RING] = {}, evA_set_[VS_EV_RING] = {}, evW_set_[2] = {};
     int last_detect_frame_ = -100;
     bool c_pending_[VS_KP_SLOTS] = {};
+    bool split_motion_ = false;
     cudaStream_t sH_ = nullptr, sO_ = nullptr; // copy-in / copy-out streams of the pipelined host path
     cudaEvent_t evH_[8] = {}, evRing_[36] = {}, evOutReady_[VS_OUT_SLOTS] = {}, evOutFree_[VS_OUT_SLOTS] = {};
     bool ring_ev_set_[36] = {}, out_free_set_[VS_OUT_SLOTS] = {};
