@@ -18,12 +18,15 @@ for mode in ("multi", "single"):
     else:
         os.environ.pop("VS_SINGLE_STREAM", None)
     st = vsb.Stabilizer(vsb.Parameters(smoothingRadius=15))
-    def run(k):
+    pos = 0
+    def run(k):                       # walks the ping-pong sequence without a jump, like bench.py
+        global pos
         done = 0
         while done < k:
-            m = min(k - done, len(order), n)
-            st.push_many_device(seq.data_ptr(), fb, m, W, H, W * 3, out.data_ptr(), W * 3, fb, borrow=True)
-            done += m
+            a = pos % len(order)
+            m = min(k - done, len(order) - a, n)
+            st.push_many_device(seq[a].data_ptr(), fb, m, W, H, W * 3, out.data_ptr(), W * 3, fb, borrow=True)
+            done += m; pos += m
     run(256); st.sync()
     for rep in range(3):
         t0 = time.perf_counter(); run(1024); t1 = time.perf_counter(); st.sync(); t2 = time.perf_counter()
