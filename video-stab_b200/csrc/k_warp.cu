@@ -903,7 +903,22 @@ static inline bool tma_geometry_ok(const void* base, int w, size_t stride, size_
            (size_t)w * 3 <= stride && w >= 16;
 }
 // tensor map over {row words (u32), rows, frames}; box = one raw source box (WT_RAW_WORDS x WT_ROWS x 1)
+static bool tma_encode_map(CUtensorMap* m, const uint8_t* base, int w, int h, size_t stride, size_t frame_bytes, int n);
+// Frames come from a ring or from a handful of decoder surfaces, so the same (address, geometry) recurs every few frames:
+// a small direct-mapped, per-thread cache saves the driver's encode call on the per-frame enqueue path.
 static bool tma_make_map(CUtensorMap* m, const uint8_t* base, int w, int h, size_t stride, size_t frame_bytes, int n) {
+    struct Entry { const uint8_t* base; int w, h, n; size_t stride, frame_bytes; CUtensorMap map; };
+    static thread_local Entry cache[256] = {};
+    Entry& e = cache[((uintptr_t)base >> 12) * 2654435761u >> 24 & 255];
+    if (e.base == base && e.w == w && e.h == h && e.n == n && e.stride == stride && e.frame_bytes == frame_bytes) {
+        *m = e.map;
+        return true;
+    }
+    if (!tma_encode_map(m, base, w, h, stride, frame_bytes, n)) return false;
+    e.base = base; e.w = w; e.h = h; e.n = n; e.stride = stride; e.frame_bytes = frame_bytes; e.map = *m;
+    return true;
+}
+static bool tma_encode_map(CUtensorMap* m, const uint8_t* base, int w, int h, size_t stride, size_t frame_bytes, int n) {
     TmaEncodeFn enc = tma_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)w * 3 / 4, (cuuint64_t)h, (cuuint64_t)(n > 0 ? n : 1)};
