@@ -293,8 +293,7 @@ def run_gpu(args, rank, world, local_rank):
     st.sync()
     barrier()
     sampler = ClockSampler(local_rank)
-    if not os.environ.get("VS_BENCH_NO_SAMPLER"):
-        sampler.start()
+    sampler.start()
     l0 = st.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
