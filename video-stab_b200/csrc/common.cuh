@@ -11,6 +11,7 @@
 #define VS_PAD 16            // reflect-101 border kept around every gray pyramid level
 #define VS_WIN 15            // LK window (Stabilizer.cpp:616)
 #define VS_PYR_SLOTS 12      // pyramids kept per lane (frames n-1, n for LK + the run-ahead of the pyramid stream)
+#define VS_GUARD_GROUP 4     // the slot guard is taken once per this many frames
 #define VS_EV_RING 16        // per-frame event rings (must exceed VS_PYR_SLOTS - 1, the distance of the slot guard)
 #define VS_LEVELS 3          // maxLevel 2 (Stabilizer.cpp:617)
 #define VS_WP_SLOTS 8        // warp set-up buffers (LaneDev::wpb), by output index % VS_WP_SLOTS
@@ -108,11 +109,14 @@ struct LaneDev {
 #define VS_HF_ACCUMULATOR 26
 #define VS_HF_FLOATS 32
 
-// One wait guards every slot ring: before gray(n) overwrites pyramid slot n % VS_PYR_SLOTS the pyramid stream waits for
-// motion(n - VS_PYR_SLOTS + 1).  The other rings must not be reused any sooner than that:
+// One wait guards every slot ring: before gray(n) overwrites pyramid slot n % VS_PYR_SLOTS, motion(n - VS_PYR_SLOTS + 1) must
+// be complete.  The pyramid stream takes the wait once per VS_GUARD_GROUP frames, on motion(n - VS_PYR_SLOTS +
+// VS_GUARD_GROUP) at the first frame n of a group, which covers the whole group (the motion stream is in order).  The other
+// rings must not be reused any sooner than the pyramid ring:
 static_assert(VS_LK_SLOTS >= VS_PYR_SLOTS - 1, "tracker-output slot n % VS_LK_SLOTS is last read by motion(n - VS_LK_SLOTS)");
 static_assert(2 * VS_KP_SLOTS - 2 >= VS_PYR_SLOTS - 1, "key-point slot of detect(n) is last read by motion(n - 2 * VS_KP_SLOTS + 2)");
 static_assert(VS_EV_RING > VS_PYR_SLOTS - 1 && (VS_EV_RING & (VS_EV_RING - 1)) == 0, "event ring");
+static_assert(VS_GUARD_GROUP >= 1 && VS_GUARD_GROUP < VS_PYR_SLOTS - 2, "guard group");
 
 struct StepInfo {
     int frame_no;          // n >= 1: this is the n-th generateTransform() call (frame n)

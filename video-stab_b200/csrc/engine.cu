@@ -491,8 +491,11 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         // output and key-point rings are at least as deep (static_asserts in common.cuh), and LK(n) and the detection
         // of frame n both start after pyramid(n), so the same wait guards them.  The rings are deeper than the
         // pipeline is long (gray -> motion takes ~150 us, 5 - 6 frame periods), so the wait never binds.
-        const int guard = frame_no - VS_PYR_SLOTS + 1;
-        if (guard >= 1 && evB_set_[guard & (VS_EV_RING - 1)]) CUDA_TRY(cudaStreamWaitEvent(sp(), evB_[guard & (VS_EV_RING - 1)], 0));
+        // Taken at the first frame of each group of VS_GUARD_GROUP, on the motion kernel the LAST frame of the group
+        // needs (one stream-wait call per four frames instead of one per frame: the enqueue loop is host-bound).
+        const int guard = frame_no - VS_PYR_SLOTS + VS_GUARD_GROUP;
+        if (frame_no % VS_GUARD_GROUP == 0 && guard >= 1 && evB_set_[guard & (VS_EV_RING - 1)])
+            CUDA_TRY(cudaStreamWaitEvent(sp(), evB_[guard & (VS_EV_RING - 1)], 0));
     }
     { StageScope t(this, VS_STAGE_GRAY, sp());
       launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sp()); }       // :449-450
