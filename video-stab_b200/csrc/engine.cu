@@ -461,14 +461,14 @@ vs_status Engine::redetect(int cur, int frame_no, int record_frame_no, cudaEvent
 }
 
 // generateTransform, Stabilizer.cpp:402-761 (CPU branch) as a launch sequence over the handle's streams:
-//   P  (pyramid)    gray -> pyramid               needs: motion(n-5) complete - the one slot guard (below)
+//   P  (pyramid)    gray -> pyramid               needs: motion(n-8) complete, checked every 4th frame - the one slot guard (below)
 //   A0/A1 (tracking) LK(n) on stream n & 1        needs: pyramid(n) (evP_), key points of the last detection (evC_)
 //   M  (motion)     RANSAC .. smoothing, set-up   needs: LK of this frame (evA_), warp set-up slot (evW_, every 4th output)
 //   O  (public)     warp, in emit()               needs: motion of this step (evB_)
 //   C0/C1 (detection) eig+NMS -> select           needs: pyramid of this frame (evP_)
-// Pyramids live in 6 slots, tracker output in 8, key points in 4, warp set-ups in 8, detection scratch in 2; every
-// kernel of frame n-6 and older is complete once motion(n-5) is (the motion stream is in order and consumes LK, which
-// consumes the detection), and LK(n) / detect(n) start after pyramid(n), so that single wait guards all of them.
+// Pyramids live in 12 slots, tracker output in 16, key points in 8, warp set-ups in 8, detection scratch in 2; every
+// kernel of frame n-8 and older is complete once motion(n-8) is (the motion stream is in order and consumes LK, which
+// consumes the detection), and LK(n) / detect(n) start after pyramid(n), so one wait per four frames guards all of them.
 vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     if (n_frames_ + 1 >= traj_cap_) VS_TRY(grow_trajectory());
     const int frame_no = ++n_frames_;
