@@ -141,7 +141,7 @@ def run_reference(args, rank, world):
     import cv2
     import numpy as np
     from oracle.stabilizer_ref import Parameters, StabilizerRef
-    from video_stab_b200 import synth
+    import synthclip as synth
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
     sample = 16                                    # frames per step (bounded sample of the 64-frame step)
@@ -180,7 +180,7 @@ def run_reference(args, rank, world):
 def cpu_baseline_sample(seconds_budget=12.0):
     import cv2
     from oracle.stabilizer_ref import Parameters, StabilizerRef
-    from video_stab_b200 import synth
+    import synthclip as synth
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
     clip = synth.make_clip(W, H, 32, seed=2000)
@@ -248,6 +248,7 @@ def run_gpu(args, rank, world, local_rank):
 
     import __graft_entry__
     __graft_entry__.build()
+    import synthclip
     import video_stab_b200 as vsb
     from video_stab_b200._capi import lib
 
@@ -263,7 +264,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # synthetic clip, resident in HBM: the 64 generated frames laid out in ping-pong order (126 frames = 784 MB > L2), so a
     # step is a run of consecutive frames and the sequence loops without a jump
-    clip_h = vsb.synth.make_clip(W, H, FRAMES_PER_STEP, seed=2000 + rank)
+    clip_h = synthclip.make_clip(W, H, FRAMES_PER_STEP, seed=2000 + rank)
     order = _pingpong(FRAMES_PER_STEP)
     clip_d = torch.from_numpy(clip_h).to(dev)
     seq_d = clip_d[torch.tensor(order, device=dev)].contiguous()

@@ -22,13 +22,48 @@ therefore has two layers:
   CUDA kernels are specified against, and they are *pinned* against `cv2` itself
   by `tests/test_oracle_models.py` (bit-exact on every op).
 
-Parity pinning status
----------------------
-The reference ships **no tests, golden vectors or fixtures** for this path
-(SURVEY.md §4, §8c), so parity cannot be pinned on reference-held vectors.  It is
-pinned instead on outputs of the reference's own dependency run here: `cv2` 4.13.0
-with `cv2.setUseOptimized(False)` (OpenCV's portable baseline code path — the
-IPP/AVX2-dispatched path differs in float rounding of the Shi-Tomasi map by <=1e-8
-and is not bit-stable across CPUs).  Golden fixtures generated from that run are
-committed under `tests/golden/` with the generating script `oracle/make_golden.py`.
+* `oracle/_ref/libvideostab_ref.so` — **the reference itself**: `/root/reference/src/Stabilizer.cpp`,
+  all 2688 lines, unmodified and read in place, compiled by `oracle/build_ref.py` against
+  `oracle/mini_cv/` (a stand-in for the OpenCV *headers*; its image operations call back into the
+  real OpenCV of the cv2 wheel, `oracle/ref_lib.py`).  `oracle.ref_lib.RefStabilizer` drives it.
+
+Parity pinning status: PINNED ON THE REFERENCE'S OWN CODE
+---------------------------------------------------------
+The reference ships **no tests, golden vectors or fixtures** for this path, so
+there are no reference-held vectors to pin on.  The pin is instead the strongest one available:
+outputs of the reference itself, run here.  `tests/test_ref_pin.py` runs the compiled reference
+(`oracle/_ref`) and the Python restatement on the same seeded clips — 19 configurations covering every
+live flag (box / gaussian / kalman, horizon lock, the five border modes, crop-n-zoom, fade, drone mode,
+adaptive smoothing, custom corner parameters, 720p / 1080p / odd sizes), degenerate inputs, and clips
+built to reach every motion intent — and requires bit equality of every transform, path sample,
+corner list, LK status, RANSAC mask, smoothed sample, adaptive radius, motion intent, warp matrix and
+output pixel.  The pure host functions are also driven on their own with random inputs, and the
+committed goldens (`tests/golden/*.npz`, generator `oracle/make_golden.py`) are re-derived from the
+compiled reference and must match field for field.
+
+OpenCV itself is taken from the cv2 4.13.0 wheel with `cv2.setUseOptimized(False)` (OpenCV's portable
+baseline code path — the IPP/AVX2-dispatched path differs in float rounding of the Shi-Tomasi map by
+<=1e-8 and is not bit-stable across CPUs).  Residual risk: the OpenCV version on the author's Jetson is
+unknown (the reference does not pin one).
 """
+
+
+def reference_available() -> bool:
+    """True when the compiled reference (oracle/_ref) can be used on this machine."""
+    from . import ref_lib
+    return ref_lib.available()
+
+
+def oracle_kind() -> str:
+    return "reference" if reference_available() else "port"
+
+
+def run_clip(frames, params, flush: bool = True, use_optimized: bool = False):
+    """Push every frame, then flush — through the compiled reference when oracle/_ref is present (it travels to
+    the GPU box with the snapshot), else through the Python restatement (bit-identical, tests/test_ref_pin.py).
+    Returns (outputs, stabilizer) with `.frame_records`, `.output_records`, `.first_corners` on either."""
+    if reference_available():
+        from . import ref_lib
+        return ref_lib.run_clip(frames, params, flush=flush, use_optimized=use_optimized)
+    from . import stabilizer_ref
+    return stabilizer_ref.run_clip(frames, params, flush=flush, use_optimized=use_optimized)

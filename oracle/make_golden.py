@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle.stabilizer_ref import Parameters, run_clip  # noqa: E402
-from video_stab_b200 import synth  # noqa: E402
+import synthclip as synth  # noqa: E402
 
 CASES = {
     # BASELINE.json configs[0]: 1280x720, 300 frames, defaults (GFTT 200, LK 3 lvls, smooth win 30)

@@ -7,6 +7,7 @@ import sys
 import time
 
 import numpy as np
+
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,6 +15,7 @@ import __graft_entry__  # noqa: E402
 
 __graft_entry__.build()
 import video_stab_b200 as vsb  # noqa: E402
+import synthclip
 
 dev = torch.device("cuda", 0)
 which = set(sys.argv[1:]) or {"cfg3", "cfg4", "cfg5", "pcie"}
@@ -56,7 +58,7 @@ if "pcie" in which:
 
 if "cfg3" in which:
     W, H, n = 3840, 2160, 24
-    clip = torch.from_numpy(vsb.synth.make_clip(W, H, n, 3000)).to(dev)
+    clip = torch.from_numpy(synthclip.make_clip(W, H, n, 3000)).to(dev)
     out = torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev)
     order = pingpong(n)
     st = vsb.Stabilizer(vsb.Parameters(smoothingRadius=15, cropNZoom=True, borderSize=30))
@@ -76,7 +78,7 @@ if "cfg3" in which:
 
 if "cfg4" in which:
     W, H, n, S = 1920, 1080, 12, 64
-    clips = [torch.from_numpy(vsb.synth.make_clip(W, H, n, 2000 + s)).to(dev) for s in range(S)]
+    clips = [torch.from_numpy(synthclip.make_clip(W, H, n, 2000 + s)).to(dev) for s in range(S)]
     outs = torch.empty((S, H, W, 3), dtype=torch.uint8, device=dev)
     order = pingpong(n)
     sb = vsb.StabilizerBatch(vsb.Parameters(smoothingRadius=15), S)
@@ -97,7 +99,7 @@ if "cfg4" in which:
 
 if "cfg5" in which:
     W, H, n = 1920, 1080, 768
-    base = vsb.synth.make_clip(W, H, 64, 5000)
+    base = synthclip.make_clip(W, H, 64, 5000)
     idx = [pingpong(64)[k % 126] for k in range(n)]
     clip = torch.from_numpy(base).to(dev)[torch.tensor(idx, device=dev)]
     out = torch.empty_like(clip)

@@ -9,6 +9,7 @@ import sys
 import time
 
 import numpy as np
+
 import torch
 import torch.distributed as dist
 
@@ -17,6 +18,7 @@ import __graft_entry__  # noqa: E402
 
 __graft_entry__.build()
 import video_stab_b200 as vsb  # noqa: E402
+import synthclip
 from video_stab_b200 import offline  # noqa: E402
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -27,7 +29,7 @@ if world > 1:
 W, H = 1920, 1080
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 fb = W * H * 3
-base = torch.from_numpy(vsb.synth.make_clip(W, H, 64, 5000)).to(dev)
+base = torch.from_numpy(synthclip.make_clip(W, H, 64, 5000)).to(dev)
 pp = list(range(64)) + list(range(62, 0, -1))
 
 

@@ -9,11 +9,12 @@ import __graft_entry__  # noqa: E402
 
 __graft_entry__.build()
 import video_stab_b200 as vsb  # noqa: E402
+import synthclip
 
 W, H, n, S = 1920, 1080, 8, 64
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 dev = torch.device("cuda", 0)
-clips = [torch.from_numpy(vsb.synth.make_clip(W, H, n, 2000 + s)).to(dev) for s in range(S)]
+clips = [torch.from_numpy(synthclip.make_clip(W, H, n, 2000 + s)).to(dev) for s in range(S)]
 outs = torch.empty((S, H, W, 3), dtype=torch.uint8, device=dev)
 order = list(range(n)) + list(range(n - 2, 0, -1))
 sb = vsb.StabilizerBatch(vsb.Parameters(smoothingRadius=15), S)

@@ -9,11 +9,12 @@ import __graft_entry__  # noqa: E402
 
 __graft_entry__.build()
 import video_stab_b200 as vsb  # noqa: E402
+import synthclip
 
 W, H, n = 3840, 2160, 12
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 dev = torch.device("cuda", 0)
-clip = torch.from_numpy(vsb.synth.make_clip(W, H, n, 3000)).to(dev)
+clip = torch.from_numpy(synthclip.make_clip(W, H, n, 3000)).to(dev)
 out = torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev)
 st = vsb.Stabilizer(vsb.Parameters(smoothingRadius=5, cropNZoom=True, borderSize=30))
 order = list(range(n)) + list(range(n - 2, 0, -1))

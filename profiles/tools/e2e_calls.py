@@ -2,13 +2,15 @@
 pipeline latency: the last input's copy, analysis, warp and copy-out cannot overlap anything)."""
 import os, sys, time, ctypes as C
 import numpy as np, torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import __graft_entry__; __graft_entry__.build()
 import video_stab_b200 as vsb
+import synthclip
 from video_stab_b200._capi import lib
 W, H = 1920, 1080
 fb = W * H * 3
-base = vsb.synth.make_clip(W, H, 64, 2000)
+base = synthclip.make_clip(W, H, 64, 2000)
 order = list(range(64)) + list(range(62, 0, -1))
 N = 512
 seq = torch.from_numpy(np.stack([base[order[k % len(order)]] for k in range(N)])).pin_memory()

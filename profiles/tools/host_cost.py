@@ -2,12 +2,14 @@
 single-stream verification mode (no events), enqueue time vs total time."""
 import os, sys, time
 import numpy as np, torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import __graft_entry__; __graft_entry__.build()
 import video_stab_b200 as vsb
+import synthclip
 W, H, n = 1920, 1080, 64
 fb = W * H * 3
-clip = torch.from_numpy(vsb.synth.make_clip(W, H, n, 2000)).cuda()
+clip = torch.from_numpy(synthclip.make_clip(W, H, n, 2000)).cuda()
 order = list(range(n)) + list(range(n - 2, 0, -1))
 seq = clip[torch.tensor(order, device="cuda")].contiguous()
 out = torch.empty_like(clip)

@@ -1,14 +1,16 @@
 """Copy / kernel timeline of the host-buffer path (vs_stabilizer_push_many) from CUPTI through torch.profiler."""
 import json, os, sys, tempfile, ctypes as C
 import numpy as np, torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import __graft_entry__; __graft_entry__.build()
 import video_stab_b200 as vsb
+import synthclip
 from video_stab_b200._capi import lib
 from torch.profiler import profile, ProfilerActivity
 W, H, n = 1920, 1080, 64
 fb = W * H * 3
-clip = torch.from_numpy(vsb.synth.make_clip(W, H, n, 2000)).pin_memory()
+clip = torch.from_numpy(synthclip.make_clip(W, H, n, 2000)).pin_memory()
 outs = torch.empty((n, H, W, 3), dtype=torch.uint8).pin_memory()
 st = vsb.Stabilizer(vsb.Parameters(smoothingRadius=15))
 ow, oh, pr = C.c_int(), C.c_int(), C.c_int()

@@ -3,13 +3,15 @@ process, ours included): per-kernel duration in situ, per-stream busy time, and 
     python profiles/tools/kineto_timeline.py [frames] > gpurun_out/timeline.txt"""
 import json, os, sys, tempfile
 import numpy as np, torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import __graft_entry__; __graft_entry__.build()
 import video_stab_b200 as vsb
+import synthclip
 from torch.profiler import profile, ProfilerActivity
 W, H, n = 1920, 1080, 64
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 120
-clip = torch.from_numpy(vsb.synth.make_clip(W, H, n, 2000)).cuda()
+clip = torch.from_numpy(synthclip.make_clip(W, H, n, 2000)).cuda()
 out = torch.empty_like(clip)
 order = list(range(n)) + list(range(n - 2, 0, -1))
 seq = clip[torch.tensor(order, device="cuda")].contiguous()

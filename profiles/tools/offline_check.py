@@ -1,12 +1,14 @@
 import os, sys
 import numpy as np, torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import __graft_entry__; __graft_entry__.build()
 import video_stab_b200 as vsb
+import synthclip
 from video_stab_b200 import offline
 W, H = 1920, 1080
 dev = torch.device("cuda", 0)
-base = torch.from_numpy(vsb.synth.make_clip(W, H, 64, 5000)).to(dev)
+base = torch.from_numpy(synthclip.make_clip(W, H, 64, 5000)).to(dev)
 pp = list(range(64)) + list(range(62, 0, -1))
 for n in (256, 1024, 2048):
     clip = base[torch.tensor([pp[k % 126] for k in range(n)], device=dev)]

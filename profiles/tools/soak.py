@@ -4,15 +4,17 @@ transform with a pass in which every kernel is serialised on ONE stream (VS_SING
 between the handle's streams would show up as a difference."""
 import os, sys, zlib
 import numpy as np, torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import __graft_entry__; __graft_entry__.build()
 import video_stab_b200 as vsb
+import synthclip
 
 def crcs(t):
     return [zlib.crc32(f.tobytes()) for f in t.cpu().numpy()]
 
 def run(W, H, n, params, reps, mode):
-    clip = torch.from_numpy(vsb.synth.make_clip(W, H, 48, 777)).cuda()
+    clip = torch.from_numpy(synthclip.make_clip(W, H, 48, 777)).cuda()
     order = list(range(48)) + list(range(46, 0, -1))
     seq = clip[torch.tensor([order[k % len(order)] for k in range(n)], device="cuda")].contiguous()
     torch.cuda.synchronize()

@@ -2,11 +2,13 @@
 Note: the event records themselves add host and device overhead, so the period is longer than in the untimed loop."""
 import os, sys
 import numpy as np, torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import __graft_entry__; __graft_entry__.build()
 import video_stab_b200 as vsb
+import synthclip
 W, H, n = 1920, 1080, 64
-clip = torch.from_numpy(vsb.synth.make_clip(W, H, n, 2000)).cuda()
+clip = torch.from_numpy(synthclip.make_clip(W, H, n, 2000)).cuda()
 out = torch.empty_like(clip)
 order = list(range(n)) + list(range(n - 2, 0, -1))
 st = vsb.Stabilizer(vsb.Parameters(smoothingRadius=15))

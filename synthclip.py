@@ -56,3 +56,27 @@ def make_clip(width: int, height: int, n_frames: int, seed: int) -> np.ndarray:
     for k in range(n_frames):
         out[k] = render_frame(base, poses[k], width, height)
     return out
+
+
+def shake_clip(width: int, height: int, n_frames: int, seed: int, theta: float = 0.008, jump: float = 8.0, every: int = 7) -> np.ndarray:
+    """A clip built to reach the reference's SHAKE_REMOVAL / FOLLOW_ACTION motion intents (Stabilizer.cpp:1676-1719):
+    an alternating roll of +-theta about the frame ORIGIN (so the translation part of the fitted similarity stays
+    near zero while |da| is large) with a translation jump every `every` frames (erratic magnitudes: low consistency)."""
+    import cv2  # data tooling only
+    base = base_texture(width + 4 * MARGIN, height, seed)
+    out = np.empty((n_frames, height, width, 3), np.uint8)
+    for k in range(n_frames):
+        th = theta * (1.0 if k % 2 == 0 else -1.0)
+        offx = MARGIN + jump * (k // every)
+        offy = float(MARGIN)
+        c, s = np.cos(th), np.sin(th)
+        m = np.array([[c, -s, -(c * offx - s * offy)], [s, c, -(s * offx + c * offy)]], np.float64)
+        out[k] = cv2.warpAffine(base, m, (width, height), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+    return out
+
+
+def pan_clip(width: int, height: int, n_frames: int, seed: int, speed: float = 14.0) -> np.ndarray:
+    """A steady horizontal pan (constant direction, consistent magnitude): reaches DELIBERATE_PAN."""
+    base = base_texture(width + int(speed * n_frames) + 2 * MARGIN, height, seed)
+    cx = (base.shape[1] - width) / 2.0 - MARGIN
+    return np.stack([render_frame(base, (-cx + speed * k, 0.0, 0.0), width, height) for k in range(n_frames)])

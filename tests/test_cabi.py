@@ -126,6 +126,54 @@ def test_yaml_reader_understands_reference_config(vsb, tmp_path):
     assert ei.value.status == 6
 
 
+def test_yaml_reader_parses_the_reference_config_file(vsb):
+    """The reference's own examples/config.yaml (read in place; present in the build container only): every
+    `stabilizer:` key the canonical reader (examples/vsg.cpp:1003-1114) consumes lands in the right field."""
+    path = "/root/reference/examples/config.yaml"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present on this machine")
+    p = vsb.Parameters.from_yaml(path)
+    # expected values: the file's stabilizer: section, parsed here independently (key: scalar lines)
+    sect, inside = {}, False
+    for line in open(path):
+        if re.match(r"^stabilizer:\s*$", line):
+            inside = True
+            continue
+        if inside and re.match(r"^\S", line):
+            break
+        m = re.match(r"^\s+([A-Za-z_0-9]+):\s*(\"[^\"]*\"|[^#\s]+)", line) if inside else None
+        if m:
+            sect[m.group(1)] = m.group(2).strip('"')
+    assert len(sect) >= 60, len(sect)
+    want = {"smoothing_radius": ("smoothingRadius", int), "border_type": ("borderType", str), "border_size": ("borderSize", int),
+            "crop_n_zoom": ("cropNZoom", "b"), "logging": ("logging", "b"), "use_cuda": ("useCuda", "b"),
+            "max_corners": ("maxCorners", int), "quality_level": ("qualityLevel", float), "min_distance": ("minDistance", float),
+            "block_size": ("blockSize", int), "smoothing_method": ("smoothingMethod", str), "gaussian_sigma": ("gaussianSigma", float),
+            "stage_one_radius": ("stageOneRadius", int), "stage_two_radius": ("stageTwoRadius", int),
+            "use_temporal_filtering": ("useTemporalFiltering", "b"), "temporal_window_size": ("temporalWindowSize", int),
+            "adaptive_smoothing": ("adaptiveSmoothing", "b"), "min_smoothing_radius": ("minSmoothingRadius", int),
+            "max_smoothing_radius": ("maxSmoothingRadius", int), "outlier_threshold": ("outlierThreshold", float),
+            "motion_prediction": ("motionPrediction", "b"), "intentional_motion_threshold": ("intentionalMotionThreshold", float),
+            "horizon_lock": ("horizonLock", "b"), "fadeDuration": ("fadeDuration", int), "fadeAlpha": ("fadeAlpha", float),
+            "enable_virtual_canvas": ("enableVirtualCanvas", "b"), "canvas_scale_factor": ("canvasScaleFactor", float),
+            "temporal_buffer_size": ("temporalBufferSize", int), "edge_blend_radius": ("edgeBlendRadius", int),
+            "drone_high_freq_mode": ("droneHighFreqMode", "b"), "hf_shake_px": ("hfShakePx", float),
+            "hf_analysis_max_width": ("hfAnalysisMaxWidth", int), "hf_rot_lp_alpha": ("hfRotLPAlpha", float),
+            "hf_dead_zone_threshold": ("hfDeadZoneThreshold", float), "hf_freeze_duration": ("hfFreezeDuration", int),
+            "hf_motion_accumulator_decay": ("hfMotionAccumulatorDecay", float), "roll_compensation_factor": ("rollCompensationFactor", float),
+            "fast_threshold": ("fastThreshold", int), "orb_features": ("orbFeatures", int)}
+    for key, (field, kind) in want.items():
+        assert key in sect, key
+        got = getattr(p, field)
+        if kind == "b":
+            assert bool(got) == (sect[key] == "true"), key
+        elif kind is str:
+            assert got == sect[key], key
+        else:
+            assert abs(float(got) - float(sect[key])) < 1e-6, (key, got, sect[key])
+    assert p.smoothingMethod == "gausian"          # the sample's typo => the box smoother (SURVEY.md 5.6)
+
+
 def test_no_cpu_fallback(vsb):
     """Without a GPU the product path must fail loudly, never route to a CPU implementation."""
     import torch

@@ -6,6 +6,8 @@ import subprocess
 import zlib
 
 import numpy as np
+
+import synthclip
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -40,7 +42,7 @@ def test_shim_compiles_and_fails_loudly_without_gpu(shim_exe, tmp_path):
 def test_shim_matches_python_mirror(shim_exe, tmp_path):
     import video_stab_b200 as vsb
     w, h, n = 640, 360, 12
-    clip = vsb.synth.make_clip(w, h, n, 31)
+    clip = synthclip.make_clip(w, h, n, 31)
     p = tmp_path / "clip.raw"
     clip.tofile(p)
     r = subprocess.run([shim_exe, str(p), str(w), str(h), str(n), "5"], capture_output=True, text=True, check=True)

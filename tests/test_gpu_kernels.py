@@ -1,6 +1,8 @@
 """Per-kernel parity through the C-ABI (vs_k_*) against the oracle (cv2 4.13 on its baseline
 path + oracle/cv_models.py), on seeded inputs.  Integer/byte/index work is compared bit-exactly."""
 import numpy as np
+
+import synthclip
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -18,8 +20,8 @@ def vsb():
 
 
 def _tex(vsb, w, h, seed, ch=3):
-    m = vsb.synth.MARGIN
-    img = vsb.synth.base_texture(w, h, seed)[m:-m, m:-m]
+    m = synthclip.MARGIN
+    img = synthclip.base_texture(w, h, seed)[m:-m, m:-m]
     return np.ascontiguousarray(img if ch == 3 else img[..., 1])
 
 
@@ -210,11 +212,11 @@ def test_good_features_massive_ties(vsb, cv2_noopt):
 
 
 def _moved_pair(vsb, cv2, seed, ang, shift, w=960, h=540):
-    big = vsb.synth.base_texture(w, h, seed)[..., 1].copy()
+    big = synthclip.base_texture(w, h, seed)[..., 1].copy()
     m = cv2.getRotationMatrix2D((big.shape[1] / 2, big.shape[0] / 2), ang, 1.0)
     m[:, 2] += shift
     moved = cv2.warpAffine(big, m, (big.shape[1], big.shape[0]))
-    s = vsb.synth.MARGIN
+    s = synthclip.MARGIN
     return np.ascontiguousarray(big[s:-s, s:-s]), np.ascontiguousarray(moved[s:-s, s:-s])
 
 

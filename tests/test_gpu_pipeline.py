@@ -5,6 +5,8 @@ import os
 import zlib
 
 import numpy as np
+
+import synthclip
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -45,7 +47,7 @@ def _crc(a):
 
 def _check_against_golden(vsb, name, w, h, n, seed, params, frame_tol=1):
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    clip = vsb.synth.make_clip(w, h, n, seed)
+    clip = synthclip.make_clip(w, h, n, seed)
     assert np.array_equal(np.array([_crc(f) for f in clip], np.uint32), g["input_crc"]), \
         "synthetic clip differs from the one the goldens were made from"
     outs, st = _run(vsb, clip, params)
@@ -127,8 +129,9 @@ def test_kalman_horizon_lock_vs_golden(vsb):
 
 def test_live_oracle_full_frames(vsb, cv2_noopt):
     """Full-frame comparison against the oracle run on this box (not just the golden row slices)."""
-    from oracle.stabilizer_ref import Parameters, run_clip
-    clip = vsb.synth.make_clip(1280, 720, 24, 555)
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters
+    clip = synthclip.make_clip(1280, 720, 24, 555)
     outs, st = _run(vsb, clip, vsb.Parameters(smoothingRadius=8))
     ref_outs, ref = run_clip(clip, Parameters(smoothingRadius=8))
     assert len(outs) == len(ref_outs) == 24
@@ -145,8 +148,9 @@ def test_live_oracle_full_frames(vsb, cv2_noopt):
 
 
 def test_adaptive_smoothing_gate(vsb, cv2_noopt):
-    from oracle.stabilizer_ref import Parameters, run_clip
-    clip = vsb.synth.make_clip(640, 360, 40, 91)
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters
+    clip = synthclip.make_clip(640, 360, 40, 91)
     kw = dict(smoothingRadius=12, adaptiveSmoothing=True, minSmoothingRadius=6, maxSmoothingRadius=20)
     ref_outs, ref = run_clip(clip, Parameters(**kw), flush=False)
     st = vsb.Stabilizer(vsb.Parameters(**kw))
@@ -160,7 +164,7 @@ def test_empty_frame_and_clean(vsb):
     st = vsb.Stabilizer(vsb.Parameters(smoothingRadius=5))
     assert st.stabilize(None) is None
     assert st.flush() is None
-    clip = vsb.synth.make_clip(640, 360, 8, 3)
+    clip = synthclip.make_clip(640, 360, 8, 3)
     a = [st.stabilize(f) for f in clip]
     st.clean()
     b = [st.stabilize(f) for f in clip]
@@ -173,7 +177,7 @@ def test_empty_frame_and_clean(vsb):
 def test_device_api_and_batch_equal_single(vsb):
     """Config 4 in miniature: 3 streams in one lock-step batch == 3 independent stabilizers."""
     w, h, n, S = 640, 360, 14, 3
-    clips = [vsb.synth.make_clip(w, h, n, 2000 + s) for s in range(S)]
+    clips = [synthclip.make_clip(w, h, n, 2000 + s) for s in range(S)]
     params = vsb.Parameters(smoothingRadius=6)
     singles = [_run(vsb, c, params)[0] for c in clips]
     d_clips = [torch.from_numpy(c).cuda() for c in clips]
@@ -207,7 +211,7 @@ def test_push_many_equals_per_frame_push(vsb, kw):
     of n stabilize() calls + flush(), for ragged chunk sizes, page-locked and pageable buffers, more frames than the
     36-slot device ring, and the single-stream adaptive mode."""
     w, h, n = 640, 360, 90
-    clip = vsb.synth.make_clip(w, h, n, 77)
+    clip = synthclip.make_clip(w, h, n, 77)
     ref, st0 = _run(vsb, clip, vsb.Parameters(**kw))
     for pinned in (True, False):
         st = vsb.Stabilizer(vsb.Parameters(**kw))
@@ -235,9 +239,10 @@ def test_fade_border_vs_live_oracle(vsb, w, h, b, dur):
     """border_type "fade" (Stabilizer.cpp:914-978, 1070-1106): history blend before the warp, history update after
     it, whole-frame mask quirk included.  Bit-exact against the oracle (cv::addWeighted on its SIMD/FMA path);
     the last frame comes back un-warped and un-bordered."""
-    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters as RP
     n = 40
-    clip = vsb.synth.make_clip(w, h, n, 91)
+    clip = synthclip.make_clip(w, h, n, 91)
     kw = dict(smoothingRadius=5, borderType="fade", borderSize=b, fadeDuration=dur, fadeAlpha=0.25)
     ref, _ = run_clip(clip, RP(**kw))
     outs, st = _run(vsb, clip, vsb.Parameters(**kw))
@@ -264,22 +269,23 @@ def _calm_clip(vsb, w, h, n, seed):
     """A hovering-drone clip: sub-pixel to few-pixel vibration with calm stretches, so that every branch of the
     high-frequency chain (dead-zone entry / timed exit / motion exit, 1 % and 5 % shake residuals, median) runs."""
     rng = np.random.default_rng(seed)
-    base = vsb.synth.base_texture(w, h, seed)
+    base = synthclip.base_texture(w, h, seed)
     amp = np.where((np.arange(n) // 12) % 2 == 0, 0.4, 2.5)
     poses = np.stack([np.cumsum(rng.normal(0, 0.15, n)) + rng.normal(0, 1, n) * amp,
                       np.cumsum(rng.normal(0, 0.15, n)) + rng.normal(0, 1, n) * amp,
                       rng.normal(0, 0.002, n)], axis=1)
-    return np.stack([vsb.synth.render_frame(base, poses[k], w, h) for k in range(n)])
+    return np.stack([synthclip.render_frame(base, poses[k], w, h) for k in range(n)])
 
 
 @pytest.mark.parametrize("case", ["shaky", "calm", "calm_lock"])
 def test_drone_high_freq_mode_vs_live_oracle(vsb, cv2_noopt, case):
     """drone_high_freq_mode (Stabilizer.cpp:666-671, 2468-2529, 2605-2681, box radius clamp :1144-1146) at the
     960x540 analysis size: filtered transforms equal to the oracle's float for float, frames within 1 LSB."""
-    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters as RP
     n = 60
     if case == "shaky":
-        clip = vsb.synth.make_clip(1280, 720, n, 17)
+        clip = synthclip.make_clip(1280, 720, n, 17)
         kw = dict(smoothingRadius=12, droneHighFreqMode=True)
     else:
         clip = _calm_clip(vsb, 1280, 720, n, 23)
@@ -328,7 +334,7 @@ def test_async_device_pipeline_is_deterministic(vsb, borrow):
     path - which serialises everything - on every repetition, with more frames than ring slots / event slots, and
     with the internal ring copy (borrow=False) as well as frames read in place."""
     w, h, n = 1280, 720, 100
-    clip = vsb.synth.make_clip(w, h, n, 4321)
+    clip = synthclip.make_clip(w, h, n, 4321)
     params = vsb.Parameters(smoothingRadius=7)
     ref, _ = _run(vsb, clip, params)
     want = [zlib.crc32(o.tobytes()) for o in ref]
@@ -353,7 +359,7 @@ def test_wait_event_orders_frames_produced_on_another_stream(vsb):
     """Stream-ordered hand-off (vs_stabilizer_wait_event): frames written by a slow producer on another CUDA stream
     are pushed without any host synchronisation; the handle's streams wait for the producer's event."""
     w, h, n = 640, 360, 24
-    clip = vsb.synth.make_clip(w, h, n, 77)
+    clip = synthclip.make_clip(w, h, n, 77)
     params = vsb.Parameters(smoothingRadius=5)
     ref, _ = _run(vsb, clip, params)
     d_clip = torch.from_numpy(clip).cuda()
@@ -387,7 +393,7 @@ def test_wait_event_orders_frames_produced_on_another_stream(vsb):
 def test_push_many_device_equals_per_frame_push(vsb, borrow):
     """vs_stabilizer_push_many_device is the per-frame loop moved inside the library: same frames, same records."""
     w, h, n = 640, 360, 50
-    clip = vsb.synth.make_clip(w, h, n, 99)
+    clip = synthclip.make_clip(w, h, n, 99)
     params = vsb.Parameters(smoothingRadius=6)
     ref, st0 = _run(vsb, clip, params)
     d_clip = torch.from_numpy(clip).cuda()
@@ -413,7 +419,7 @@ def test_push_many_device_equals_per_frame_push(vsb, borrow):
 def test_multi_stream_engine_equals_single_stream(vsb, monkeypatch, w, h, n, kw):
     """The seven-stream engine (slot rings + one transitive guard per frame) against the same calls with every kernel
     serialised on one stream (VS_SINGLE_STREAM=1): frames and transforms must be identical, on every repetition."""
-    clip = torch.from_numpy(vsb.synth.make_clip(w, h, 40, 31)).cuda()
+    clip = torch.from_numpy(synthclip.make_clip(w, h, 40, 31)).cuda()
     order = list(range(40)) + list(range(38, 0, -1))
     seq = clip[torch.tensor([order[k % len(order)] for k in range(n)], device="cuda")].contiguous()
     fb = w * h * 3
@@ -471,10 +477,11 @@ def test_random_parameter_sweep_vs_live_oracle(vsb, cv2_noopt, seed):
     """Random points of the configuration space (smoother, radius, corner parameters, border mode, crop-zoom, fade,
     drone mode, frame sizes that do and do not take the aligned fast paths) against the oracle run live: corner lists
     and LK status bit-exact, transforms within 1e-3 px, frames within 1 LSB away from the border band."""
-    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters as RP
     w, h, kw = _sweep_case(seed)
     n = 44
-    clip = vsb.synth.make_clip(w, h, n, 600 + seed)
+    clip = synthclip.make_clip(w, h, n, 600 + seed)
     ref_outs, ref = run_clip(clip, RP(**kw))
     outs, st = _run(vsb, clip, vsb.Parameters(**kw))
     assert len(outs) == len(ref_outs) == n, kw
@@ -506,10 +513,11 @@ def test_degenerate_inputs_vs_live_oracle(vsb, cv2_noopt):
     """Inputs that push the path through its fallbacks: flat frames (no corners: the no-key-points branch pushes a zero
     transform, Stabilizer.cpp:676-678), the return of texture (re-detection), a scene cut (tracking / RANSAC failure:
     identity transform, :646-659), a very dark stretch and heavy noise."""
-    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters as RP
     w, h = 960, 540
-    a = vsb.synth.make_clip(w, h, 12, 71)
-    b = vsb.synth.make_clip(w, h, 10, 72)                       # unrelated texture: scene cut
+    a = synthclip.make_clip(w, h, 12, 71)
+    b = synthclip.make_clip(w, h, 10, 72)                       # unrelated texture: scene cut
     rng = np.random.default_rng(9)
     flat = np.full((6, h, w, 3), 127, np.uint8)
     dark = (a[:6].astype(np.float32) * 0.04).astype(np.uint8)
@@ -547,9 +555,10 @@ def test_degenerate_inputs_vs_live_oracle(vsb, cv2_noopt):
 def test_unusual_frame_sizes_vs_live_oracle(vsb, cv2_noopt, w, h):
     """4:3, tiny, not-a-multiple-of-4, 1440p and 4K frames: the analysis image is always 960x540 (up- or down-scaled with
     cv::resize's arithmetic), the output stage takes the aligned TMA kernels or the fallbacks depending on the row pitch."""
-    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters as RP
     n = 16
-    clip = vsb.synth.make_clip(w, h, n, 4000 + w)
+    clip = synthclip.make_clip(w, h, n, 4000 + w)
     kw = dict(smoothingRadius=5, borderSize=6 if w < 2000 else 0, cropNZoom=(w == 1366))
     ref_outs, ref = run_clip(clip, RP(**kw))
     outs, st = _run(vsb, clip, vsb.Parameters(**kw))
@@ -574,9 +583,10 @@ def test_unusual_frame_sizes_vs_live_oracle(vsb, cv2_noopt, w, h):
 def test_adaptive_smoothing_frames_vs_live_oracle(vsb, cv2_noopt):
     """adaptive_smoothing (Stabilizer.cpp:691-693, 1461-1492, 1562-1574): the radius follows the last motion, moves the
     latency gate, and the run stays on one stream with one int read back per frame - frames and records as the oracle's."""
-    from oracle.stabilizer_ref import Parameters as RP, run_clip
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters as RP
     w, h, n = 960, 540, 60
-    clip = vsb.synth.make_clip(w, h, n, 91)
+    clip = synthclip.make_clip(w, h, n, 91)
     kw = dict(smoothingRadius=12, adaptiveSmoothing=True, minSmoothingRadius=6, maxSmoothingRadius=20)
     ref_outs, ref = run_clip(clip, RP(**kw))
     outs, st = _run(vsb, clip, vsb.Parameters(**kw))

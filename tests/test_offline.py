@@ -3,6 +3,8 @@ import os
 import sys
 
 import numpy as np
+
+import synthclip
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -66,7 +68,7 @@ def test_chunked_clip_equals_streamed(kw):
     import torch
     import video_stab_b200 as vsb
     w, h, n = 640, 360, 41
-    clip = vsb.synth.make_clip(w, h, n, 321)
+    clip = synthclip.make_clip(w, h, n, 321)
     params = vsb.Parameters(**kw)
     st = vsb.Stabilizer(params)
     outs = [o for o in (st.stabilize(f) for f in clip) if o is not None]

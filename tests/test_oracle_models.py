@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import cv_models as M
-from video_stab_b200 import synth
+import synthclip as synth
 
 
 def _tex(w, h, seed, channels=3):

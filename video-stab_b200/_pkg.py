@@ -1,8 +1,7 @@
 """video-stab_b200: B200-native drop-in for the reference's per-frame stabilization hot path."""
-from . import synth  # noqa: F401
 from ._capi import LIB_PATH, VsError, lib  # noqa: F401  (raises ImportError if the CUDA library is missing)
 from .stabilizer import Parameters, Stabilizer, StabilizerBatch  # noqa: F401
 from . import kernels  # noqa: F401
 from . import offline  # noqa: F401
 
-__all__ = ["synth", "lib", "LIB_PATH", "VsError", "Parameters", "Stabilizer", "StabilizerBatch", "kernels", "offline"]
+__all__ = ["lib", "LIB_PATH", "VsError", "Parameters", "Stabilizer", "StabilizerBatch", "kernels", "offline"]
