@@ -47,7 +47,7 @@ typedef struct vs_params {
     int32_t use_cuda;                 /* useCuda — accepted, ignored (always GPU)           */
     int32_t logging;                  /* logging                                             */
     int32_t smoothing_radius;         /* smoothingRadius (30) live                           */
-    int32_t max_corners;              /* maxCorners (200) live, first frame                  */
+    int32_t max_corners;              /* maxCorners (200) live, first frame; 1..2048 (else UNSUPPORTED) */
     double  quality_level;            /* qualityLevel (0.01) live, first frame               */
     double  min_distance;             /* minDistance (30.0) live, first frame                */
     int32_t block_size;               /* blockSize (3) — only 3 is supported (the default)   */
@@ -235,6 +235,14 @@ vs_status vs_clip_analyze(vs_stabilizer* s, const uint8_t* d_frames, int width, 
                           float* transforms_out_host, int* n_out);
 vs_status vs_clip_render(vs_stabilizer* s, const float* all_transforms_host, int n_total, const uint8_t* d_frames,
                          int width, int height, int first, int count, uint8_t* d_out, int* out_width, int* out_height);
+/* Device-resident variants: the transforms stay in device memory, so the exchange step (an NCCL all-gather of
+ * 12 bytes per frame) reads and writes them in place and nothing on the path blocks the host.  Both calls are
+ * asynchronous on vs_stabilizer_stream(): order the collective after vs_clip_analyze_device and
+ * vs_clip_render_device after the collective with events on that stream (or vs_stabilizer_wait_event). */
+vs_status vs_clip_analyze_device(vs_stabilizer* s, const uint8_t* d_frames, int width, int height, int first, int count,
+                                 float* d_transforms_out, int* n_out);
+vs_status vs_clip_render_device(vs_stabilizer* s, const float* d_all_transforms, int n_total, const uint8_t* d_frames,
+                                int width, int height, int first, int count, uint8_t* d_out, int* out_width, int* out_height);
 
 /* ---- multi-stream batch: N independent streams advanced in lock-step, one kernel launch per
  * stage for the whole batch (BASELINE config 4).  Semantically N vs_stabilizers. -------------- */

@@ -604,3 +604,167 @@ def test_adaptive_smoothing_frames_vs_live_oracle(vsb, cv2_noopt):
         assert a.shape == b.shape
         d = np.abs(a.astype(np.int16) - b.astype(np.int16))
         assert d[40:-40, 40:-40].max() <= 1 and (d > 1).mean() < 1e-3, f"output {k}"
+
+
+# ------------------------------------------------------------------------ BASELINE configs at their stated sizes
+def test_oracle_on_this_box_is_the_compiled_reference():
+    """The live-oracle tests of this module compare against the REFERENCE'S OWN Stabilizer.cpp (oracle/_ref, built in
+    the build container by oracle/build_ref.py; the .so travels with the snapshot).  If it did not travel they fall
+    back to the bit-identical Python restatement (tests/test_ref_pin.py); this test says which one ran."""
+    import oracle
+    if not oracle.reference_available():
+        pytest.skip("oracle/_ref not present on this box: live-oracle tests used the Python restatement")
+    assert oracle.oracle_kind() == "reference"
+
+
+def test_config2_1080p_r15_live_oracle_full_frames(vsb, cv2_noopt):
+    """BASELINE config 2 (the bench workload): 1920x1080, smoothing radius 15, 150 frames, EVERY output pixel of every
+    frame against the oracle run live on this box.  Tolerances are the north star's: corner lists / status / inlier
+    masks bit-exact, transforms within 1e-3 px of corner displacement, frames within 1 LSB outside the border band —
+    and the fraction of bit-exact frames is asserted, not just reported."""
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters
+    w, h, n = 1920, 1080, 150
+    clip = synthclip.make_clip(w, h, n, 2000)
+    outs, st = _run(vsb, clip, vsb.Parameters(smoothingRadius=15))
+    ref_outs, ref = run_clip(clip, Parameters(smoothingRadius=15))
+    assert len(outs) == len(ref_outs) == n
+    assert np.array_equal(st.first_corners(), ref.first_corners)
+    for i, r in enumerate(ref.frame_records):
+        rec, pts = st.frame_record(i), st.frame_points(i)
+        assert np.array_equal(pts["status"], r.status), f"frame {i}: LK status"
+        if r.inlier_mask is not None:
+            assert np.array_equal(pts["inlier_mask"], r.inlier_mask), f"frame {i}: inlier mask"
+        if r.detected is not None:
+            assert np.array_equal(pts["detected"], r.detected), f"frame {i}: corner list"
+        d = np.abs(np.asarray(rec.transform) - r.transform)
+        assert d[0] < 1e-3 and d[1] < 1e-3 and d[2] * HALF_DIAG < 1e-3, f"frame {i}: transform {d}"
+    for k, r in enumerate(ref.output_records):
+        o = st.output_record(k)
+        assert o.index == r.index and bool(o.passthrough) == (r.T is None)
+        if r.T is not None:
+            assert (o.radius, o.intent) == (r.radius, r.intent), f"output {k}"
+    band, exact, worst = 40, 0, 0
+    for k, (a, b) in enumerate(zip(outs, ref_outs)):
+        assert a.shape == b.shape
+        d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+        inner = int(d[band:-band, band:-band].max())
+        worst = max(worst, inner)
+        assert inner <= 1, f"output {k}: {inner} LSB inside the border band"
+        assert (d > 1).mean() < 1e-3
+        exact += int(d.max() == 0)
+    print(f"config 2: bit-exact output frames {exact}/{n}, worst interior difference {worst} LSB")
+    assert exact >= int(0.9 * n), f"only {exact}/{n} output frames are bit-exact"
+
+
+def test_config4_64_streams_batch_equals_singles(vsb):
+    """BASELINE config 4 at its stated width: 64 concurrent 1080p streams in one lock-step batch == 64 independent
+    stabilizers, every output frame compared on the device (40 frames per stream, radius 15).  The 64 streams are
+    8 seeded clips x 8 start offsets (distinct content and phase per stream)."""
+    w, h, n, S = 1920, 1080, 40, 64
+    fb = h * w * 3
+    params = vsb.Parameters(smoothingRadius=15)
+    bases = [torch.from_numpy(synthclip.make_clip(w, h, n + 8, 2000 + s)).cuda() for s in range(8)]
+    lane_clip = [bases[s % 8][s // 8: s // 8 + n] for s in range(S)]
+    out_b = torch.zeros((S, n, h, w, 3), dtype=torch.uint8, device="cuda")
+    batch = vsb.StabilizerBatch(params, S)
+    k = 0
+    for i in range(n):
+        r = batch.push_device([lane_clip[s][i].data_ptr() for s in range(S)], w, h, w * 3,
+                              [out_b[s, k].data_ptr() for s in range(S)], w * 3, fb, borrow=True)
+        k += r is not None
+    while True:
+        r = batch.flush_device([out_b[s, min(k, n - 1)].data_ptr() for s in range(S)], w * 3, fb)
+        if r is None:
+            break
+        k += 1
+    batch.sync()
+    assert k == n
+    out_s = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    for s in range(S):
+        st = vsb.Stabilizer(params)
+        m = st.push_many_device(lane_clip[s].data_ptr(), fb, n, w, h, w * 3, out_s.data_ptr(), w * 3, fb, borrow=True)
+        while st.flush_device(out_s[m].data_ptr(), w * 3, fb) is not None:
+            m += 1
+        st.sync()
+        assert m == n
+        same = (out_b[s] == out_s).reshape(n, -1).all(1)
+        assert bool(same.all()), f"stream {s}: frames {(~same).nonzero().flatten().tolist()[:5]} differ"
+        for i in (0, n // 2, n - 2):
+            assert list(batch.frame_record(s, i).transform) == list(st.frame_record(i).transform)
+        del st
+
+
+@pytest.mark.parametrize("kind", ["pan", "shake"])
+def test_motion_intents_vs_live_oracle(vsb, cv2_noopt, kind):
+    """Clips that leave MotionIntent::NORMAL (Stabilizer.cpp:1676-1719): a steady pan reaches DELIBERATE_PAN, an alternating
+    roll about the frame origin with translation jumps reaches SHAKE_REMOVAL and FOLLOW_ACTION.  The device takes the same
+    branch as the oracle on every output."""
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters
+    w, h = 640, 360
+    clip = synthclip.pan_clip(w, h, 50, 123) if kind == "pan" else synthclip.shake_clip(w, h, 60, 5)
+    outs, st = _run(vsb, clip, vsb.Parameters(smoothingRadius=5))
+    ref_outs, ref = run_clip(clip, Parameters(smoothingRadius=5))
+    intents = [r.intent for r in ref.output_records]
+    if kind == "pan":
+        assert 1 in intents
+    else:
+        assert intents.count(2) >= 20 and 3 in intents
+    for k, r in enumerate(ref.output_records):
+        o = st.output_record(k)
+        if r.T is not None:
+            assert o.intent == r.intent and o.radius == r.radius, f"output {k}: intent {o.intent} vs {r.intent}"
+            dT = np.abs(np.asarray(o.T).reshape(2, 3) - r.T)
+            assert dT[:, 2].max() < 1e-3 and dT[:, :2].max() * HALF_DIAG < 1e-3
+    for i, r in enumerate(ref.frame_records):
+        assert np.array_equal(st.frame_points(i)["status"], r.status)
+    for k, (a, b) in enumerate(zip(outs, ref_outs)):
+        d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+        assert d[40:-40, 40:-40].max() <= 1, f"output {k}"
+
+
+@pytest.mark.parametrize("kw", [dict(smoothingRadius=6), dict(smoothingRadius=5, borderType="reflect", borderSize=12)])
+def test_too_small_output_buffer_is_recoverable(vsb, kw):
+    """A too-small output buffer is reported BEFORE anything is queued or launched (VS_ERR_BUFFER_TOO_SMALL = 4): repeating
+    the call with a large enough buffer continues the stream as if nothing had happened (same frames as a clean run)."""
+    import ctypes as C
+    from video_stab_b200._capi import lib
+    w, h, n = 640, 360, 20
+    clip = synthclip.make_clip(w, h, n, 12)
+    ref, st0 = _run(vsb, clip, vsb.Parameters(**kw))
+    st = vsb.Stabilizer(vsb.Parameters(**kw))
+    b = kw.get("borderSize", 0)
+    cap = (w + 2 * b) * (h + 2 * b) * 3
+    big, small = np.empty(cap, np.uint8), np.empty(cap - 1, np.uint8)
+    ow, oh, produced = C.c_int(), C.c_int(), C.c_int()
+    got, failures = [], 0
+    for i, f in enumerate(clip):
+        f = np.ascontiguousarray(f)
+        if i % 3 == 0:      # first try with a buffer one byte short
+            rc = lib.vs_stabilizer_push(st._h, f.ctypes.data, w, h, w * 3, small.ctypes.data, 0, small.size, C.byref(ow), C.byref(oh), C.byref(produced))
+            if rc != 0:
+                assert rc == 4 and not produced.value
+                failures += 1
+            elif produced.value:
+                raise AssertionError("a frame fitted into a too-small buffer")
+            else:
+                continue    # no output was due: the frame was accepted
+        rc = lib.vs_stabilizer_push(st._h, f.ctypes.data, w, h, w * 3, big.ctypes.data, 0, big.size, C.byref(ow), C.byref(oh), C.byref(produced))
+        assert rc == 0
+        if produced.value:
+            got.append(big[: ow.value * oh.value * 3].reshape(oh.value, ow.value, 3).copy())
+    while True:
+        rc = lib.vs_stabilizer_flush(st._h, small.ctypes.data, 0, w * h * 3 - 1, C.byref(ow), C.byref(oh), C.byref(produced))
+        if rc == 0 and not produced.value:
+            break
+        assert rc == 4, "flush into a too-small buffer must be refused"
+        rc = lib.vs_stabilizer_flush(st._h, big.ctypes.data, 0, big.size, C.byref(ow), C.byref(oh), C.byref(produced))
+        assert rc == 0 and produced.value
+        got.append(big[: ow.value * oh.value * 3].reshape(oh.value, ow.value, 3).copy())
+    assert failures >= 3
+    assert len(got) == len(ref) == n
+    for i, (a, c) in enumerate(zip(got, ref)):
+        assert a.shape == c.shape and np.array_equal(a, c), f"frame {i} differs after a refused call"
+    for i in range(n - 1):
+        assert list(st.frame_record(i).transform) == list(st0.frame_record(i).transform)

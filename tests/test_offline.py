@@ -36,7 +36,13 @@ def _stitch_worker(rank, world, port, n_total, q):
     lo, hi = max(f, 1) - 1, f + c - 1
     local = full[lo:hi] if c > 0 else full[:0]
     got = offline.stitch_transforms(local, f, c, n_total)
-    q.put((rank, bool(np.array_equal(got, full))))
+    # the tensor variant (what the device-resident path uses; here on CPU tensors over gloo)
+    import torch
+    per, _ = offline.stitch_index(n_total, world)
+    buf = torch.full((per, 3), -1.0)
+    buf[: len(local)] = torch.from_numpy(np.ascontiguousarray(local))
+    got2 = offline.stitch_transforms_tensor(buf, n_total).numpy()
+    q.put((rank, bool(np.array_equal(got, full)) and bool(np.array_equal(got2, full))))
     dist.destroy_process_group()
 
 
@@ -86,3 +92,114 @@ def test_chunked_clip_equals_streamed(kw):
         for i in range(n):
             oh, ow = outs[i].shape[:2]
             assert np.array_equal(g[i, :oh, :ow], outs[i]), f"{chunks} chunks: frame {i} differs"
+
+
+def _synthetic_long_clip(torch, w, h, n, seed, dev):
+    """n frames generated ON THE DEVICE from the seed (a 10-minute 1080p clip is 112 GB raw): integer-offset crops of a
+    few pre-rotated copies of one texture, following a smooth pan + seeded jitter.  Returns a function that
+    materialises frames [a, b) as a (b-a, h, w, 3) uint8 tensor."""
+    import cv2
+    m = 96
+    base = synthclip.base_texture(w + 2 * m - 2 * synthclip.MARGIN, h + 2 * m - 2 * synthclip.MARGIN, seed)
+    rots = []
+    for a in (-0.004, -0.002, 0.0, 0.002, 0.004):
+        c, s_ = np.cos(a), np.sin(a)
+        cx, cy = base.shape[1] / 2.0, base.shape[0] / 2.0
+        M = np.array([[c, -s_, cx - c * cx + s_ * cy], [s_, c, cy - s_ * cx - c * cy]])
+        rots.append(torch.from_numpy(cv2.warpAffine(base, M, (base.shape[1], base.shape[0]))).to(dev))
+    rng = np.random.default_rng(seed + 1)
+    k = np.arange(n)
+    xs = np.clip(np.rint(m + 40 * np.sin(2 * np.pi * k / 240.0) + rng.normal(0, 3, n)), 0, 2 * m).astype(int)
+    ys = np.clip(np.rint(m + 20 * np.sin(2 * np.pi * k / 180.0 + 1.0) + rng.normal(0, 3, n)), 0, 2 * m).astype(int)
+    rs = rng.integers(0, len(rots), n)
+
+    def frames(a, b):
+        out = torch.empty((b - a, h, w, 3), dtype=torch.uint8, device=dev)
+        for i in range(a, b):
+            out[i - a] = rots[rs[i]][ys[i]:ys[i] + h, xs[i]:xs[i] + w]
+        return out
+    return frames
+
+
+def _frame_checksums(torch, frames):
+    """per-frame 64-bit checksum on the device (position-weighted sum of the 32-bit words)"""
+    n = frames.shape[0]
+    words = frames.reshape(n, -1).view(torch.int32).to(torch.int64)
+    wts = (torch.arange(words.shape[1], device=frames.device, dtype=torch.int64) % 65521) + 1
+    return (words * wts).sum(1)
+
+
+@pytest.mark.gpu
+def test_config5_long_clip_chunked_equals_streamed(monkeypatch):
+    """BASELINE config 5 at its full length: an 18 000-frame 1080p clip (10 min @ 30 fps), generated on the device.
+    8 temporal chunks through the device-resident clip calls (analyse -> stitch -> rebuild path -> smooth -> warp) must
+    equal the streamed stabilize() + flush() of the whole clip: transforms bit for bit, every output frame by checksum.
+    The trajectory arrays start at 4096 entries (VS_TRAJ_CAP), so grow_trajectory() runs three times on the way."""
+    import torch
+    import video_stab_b200 as vsb
+    from video_stab_b200 import offline
+    monkeypatch.setenv("VS_TRAJ_CAP", "4096")
+    w, h, n, chunks = 1920, 1080, 18000, 8
+    dev = torch.device("cuda", 0)
+    gen = _synthetic_long_clip(torch, w, h, n, 5000, dev)
+    params = vsb.Parameters(smoothingRadius=15)
+    fb = h * w * 3
+
+    # ---- streamed: push_device frame by frame, outputs into a 512-frame ring, checksummed block by block
+    st = vsb.Stabilizer(params)
+    blk = 500
+    ring = torch.empty((blk + 40, h, w, 3), dtype=torch.uint8, device=dev)
+    sums = []
+    produced = 0
+    for a in range(0, n, blk):
+        fr = gen(a, min(a + blk, n))
+        torch.cuda.synchronize()
+        k = st.push_many_device(fr.data_ptr(), fb, fr.shape[0], w, h, w * 3, ring.data_ptr(), w * 3, fb, borrow=False)
+        st.sync()
+        sums.append(_frame_checksums(torch, ring[:k]).cpu())
+        produced += k
+    while True:
+        got = st.flush_device(ring.data_ptr(), w * 3, fb)
+        if got is None:
+            break
+        st.sync()
+        sums.append(_frame_checksums(torch, ring[:1]).cpu())
+        produced += 1
+    assert produced == n
+    streamed = torch.cat(sums)
+    nf, no = st.counts()
+    assert nf == n - 1 and no == n
+    ref_tr = np.array([list(st.frame_record(i).transform) for i in range(0, n - 1, 97)], np.float32)
+    last = st.output_record(n - 2)
+    del st
+
+    # ---- chunked: 8 chunks on this one GPU, one after the other, exactly as 8 ranks would run them
+    st = vsb.Stabilizer(params)
+    per, idx = offline.stitch_index(n, chunks)
+    gathered = torch.zeros((chunks * per, 3), dtype=torch.float32, device=dev)
+    for r in range(chunks):
+        first, count = offline.chunk_bounds(n, chunks, r)
+        hl = offline.halo(first)
+        fr = gen(first - hl, first + count)
+        torch.cuda.synchronize()
+        offline.analyze_chunk_device(st, fr.data_ptr(), w, h, first, count, gathered[r * per].data_ptr())
+        st.sync()
+        del fr
+    full = gathered.index_select(0, torch.from_numpy(idx).to(dev)).contiguous()
+    tr = full.cpu().numpy()
+    assert np.array_equal(tr[::97].view(np.uint32), ref_tr.view(np.uint32)), "chunked transforms differ from streamed"
+    chunked = []
+    for r in range(chunks):
+        first, count = offline.chunk_bounds(n, chunks, r)
+        fr = gen(first, first + count)
+        out = torch.empty((count, h, w, 3), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        offline.render_chunk_device(st, full.data_ptr(), n, fr.data_ptr(), w, h, first, count, out.data_ptr())
+        st.sync()
+        for a in range(0, count, 250):
+            chunked.append(_frame_checksums(torch, out[a:a + 250]).cpu())
+        del fr, out
+    chunked = torch.cat(chunked)
+    bad = (chunked != streamed).nonzero().flatten().tolist()
+    assert not bad, f"{len(bad)} of {n} output frames differ, first at {bad[:5]}"
+    assert last.index == n - 2

@@ -84,6 +84,8 @@ SYMBOLS = {
     "vs_clip_halo": (_I, [_I]),
     "vs_clip_analyze": (_I, [_P, _U8P, _I, _I, _I, _I, _P, _IP]),
     "vs_clip_render": (_I, [_P, _P, _I, _U8P, _I, _I, _I, _I, _U8P, _IP, _IP]),
+    "vs_clip_analyze_device": (_I, [_P, _U8P, _I, _I, _I, _I, _P, _IP]),
+    "vs_clip_render_device": (_I, [_P, _P, _I, _U8P, _I, _I, _I, _I, _U8P, _IP, _IP]),
     "vs_batch_create": (_I, [C.POINTER(VsParams), _I, _I, C.POINTER(_P)]),
     "vs_batch_destroy": (None, [_P]),
     "vs_batch_push_device": (_I, [_P, C.POINTER(_P), _I, _I, _SZ, C.POINTER(_P), _SZ, _SZ, C.c_uint, _IP, _IP, _IP]),

@@ -366,14 +366,28 @@ vs_status vs_clip_analyze(vs_stabilizer* s, const uint8_t* d_frames, int width, 
                           float* transforms_out_host, int* n_out) {
     if (!s) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
     API_BEGIN
-    return s->eng->analyze_chunk(d_frames, width, height, first, count, transforms_out_host, n_out);
+    return s->eng->analyze_chunk(d_frames, width, height, first, count, transforms_out_host, false, n_out);
+    API_END
+}
+vs_status vs_clip_analyze_device(vs_stabilizer* s, const uint8_t* d_frames, int width, int height, int first, int count,
+                                 float* d_transforms_out, int* n_out) {
+    if (!s) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
+    API_BEGIN
+    return s->eng->analyze_chunk(d_frames, width, height, first, count, d_transforms_out, true, n_out);
     API_END
 }
 vs_status vs_clip_render(vs_stabilizer* s, const float* all_transforms_host, int n_total, const uint8_t* d_frames,
                          int width, int height, int first, int count, uint8_t* d_out, int* out_width, int* out_height) {
     if (!s || !out_width || !out_height) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
     API_BEGIN
-    return s->eng->render_chunk(all_transforms_host, n_total, d_frames, width, height, first, count, d_out, out_width, out_height);
+    return s->eng->render_chunk(all_transforms_host, false, n_total, d_frames, width, height, first, count, d_out, out_width, out_height);
+    API_END
+}
+vs_status vs_clip_render_device(vs_stabilizer* s, const float* d_all_transforms, int n_total, const uint8_t* d_frames,
+                                int width, int height, int first, int count, uint8_t* d_out, int* out_width, int* out_height) {
+    if (!s || !out_width || !out_height) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    return s->eng->render_chunk(d_all_transforms, true, n_total, d_frames, width, height, first, count, d_out, out_width, out_height);
     API_END
 }
 

@@ -83,6 +83,8 @@ vs_status Engine::create(const vs_params& p, int device, int n_lanes, Engine** o
     if (n_lanes < 1 || n_lanes > VS_MAX_GROUP) return vs_set_error(VS_ERR_INVALID_ARG, "n_streams must be 1..64");
     if (p.enable_virtual_canvas) return vs_set_error(VS_ERR_UNSUPPORTED, "enable_virtual_canvas is not built yet");
     if (p.block_size != 3) return vs_set_error(VS_ERR_UNSUPPORTED, "only block_size 3 (the reference default) is supported");
+    if (p.max_corners <= 0 || p.max_corners > MO_MAXP_HOST)
+        return vs_set_error(VS_ERR_UNSUPPORTED, "max_corners must be 1..2048 (<= 0 means 'unlimited' to cv::goodFeaturesToTrack; the corner buffers are fixed-size)");
     if (p.adaptive_smoothing && n_lanes > 1)
         return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing makes the latency gate data dependent; single-stream handles only");
     // A handle uses up to nine streams (seven + two copy streams); the default of eight hardware queues would make two of
@@ -178,6 +180,9 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     kp_cap_ = cap_first_ > cap_redetect_ ? cap_first_ : cap_redetect_;
     log_depth_ = n_lanes == 1 ? 512 : 8;
     traj_cap_ = 1 << 15;
+    // VS_TRAJ_CAP=<frames>: initial capacity of the growable trajectory / record arrays (tests use a small value to
+    // exercise grow_trajectory() without a 20-minute clip)
+    if (const char* tc = getenv("VS_TRAJ_CAP")) { int v = atoi(tc); if (v >= 64) traj_cap_ = v; }
     return alloc_fixed();
 }
 
@@ -582,6 +587,23 @@ vs_status Engine::setup_ready() {
     return VS_OK;
 }
 
+// Output geometry of the frame at the head of the queue, and whether the caller's buffer can take it.  Called at the top of
+// push()/flush(), BEFORE anything is queued, launched or popped: a too-small buffer is a recoverable caller error and
+// must leave the handle exactly as it was (the call can simply be repeated with a larger buffer).
+vs_status Engine::check_out_buffer(bool passthrough, uint8_t* const* outs, size_t out_stride, size_t out_capacity) const {
+    const int b = p_.border_size;
+    const bool grows = !passthrough && b > 0 && !p_.crop_n_zoom;                      // copyMakeBorder path, :981-990
+    const int w = grows ? W_ + 2 * b : W_, h = grows ? H_ + 2 * b : H_;
+    const size_t tight = (size_t)w * 3;
+    if (out_stride == 0) out_stride = tight;
+    if (!outs) return vs_set_error(VS_ERR_INVALID_ARG, "no output buffer");
+    for (int l = 0; l < n_lanes_; ++l)
+        if (!outs[l]) return vs_set_error(VS_ERR_INVALID_ARG, "no output buffer");
+    if (out_stride < tight || out_stride * (size_t)(h - 1) + tight > out_capacity)
+        return vs_set_error(VS_ERR_BUFFER_TOO_SMALL, "output buffer too small for the stabilized frame");
+    return VS_OK;
+}
+
 // the warp half of applyNextSmoothTransform, Stabilizer.cpp:979-1137
 vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, int io, int* ow, int* oh) {
     const bool host_io = io != VS_IO_DEVICE, pipe = io == VS_IO_HOST_PIPE && multi_;
@@ -690,6 +712,12 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
     CUDA_TRY(cudaSetDevice(device_));
     const bool borrow = !host_io && (flags & VS_PUSH_BORROW);
     VS_TRY(ensure_geometry(w, h, !borrow, false, false));
+    if (!first_) {
+        // will this call emit a frame?  Known from counts alone (:383), except with adaptive_smoothing, where the gate
+        // moves with the data: there the buffer must be good whenever the smallest possible gate (5) could open.
+        const int gate = p_.adaptive_smoothing ? 5 : clampi(smoothing_radius_, 5, 35);
+        if ((int)queue_.size() + 1 >= gate) VS_TRY(check_out_buffer(false, outs, out_stride, out_capacity));
+    }
 
     QueueEntry e;
     e.index = next_index_;
@@ -749,6 +777,7 @@ vs_status Engine::flush(uint8_t* const* outs, size_t out_stride, size_t out_capa
     *produced = 0;
     if (queue_.empty()) return VS_OK;
     CUDA_TRY(cudaSetDevice(device_));
+    VS_TRY(check_out_buffer(queue_.front().index >= n_frames_, outs, out_stride, out_capacity));
     VS_TRY(setup_slot_guard());
     launch_smooth_only(d_lanes_, n_lanes_, step_info(queue_.front().index), sm());
     launches_ += 1;
@@ -865,7 +894,7 @@ int Engine::chunk_halo(int first) {
     return first - m;                                // 1 or 2
 }
 
-vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first, int count, float* out_host, int* n_out) {
+vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first, int count, float* out, bool device_out, int* n_out) {
     if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "clip mode uses single-lane handles");
     if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
     if (p_.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode filters carry state from frame to frame; not available in clip mode");
@@ -918,22 +947,36 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
     }
     const int n = first + count - first_tr;
     if (n_out) *n_out = n;
-    if (n > 0 && out_host)
-        CUDA_TRY(cudaMemcpyAsync(out_host, h_lanes_[0].transforms + 3 * (size_t)(first_tr - 1), sizeof(float) * 3 * n,
-                                 cudaMemcpyDeviceToHost, sm()));
+    if (n > 0 && out)
+        CUDA_TRY(cudaMemcpyAsync(out, h_lanes_[0].transforms + 3 * (size_t)(first_tr - 1), sizeof(float) * 3 * n,
+                                 device_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sm()));
+    if (device_out) return join();                   // asynchronous: ordered on the public stream, no host block
     VS_TRY(sync());
     return VS_OK;
 }
 
-vs_status Engine::render_chunk(const float* all_tr_host, int n_total, const uint8_t* d_frames, int w, int h, int first,
+vs_status Engine::render_chunk(const float* all_tr, bool device_in, int n_total, const uint8_t* d_frames, int w, int h, int first,
                                int count, uint8_t* d_out, int* ow, int* oh) {
     if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "clip mode uses single-lane handles");
     if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
     if (p_.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode filters carry state from frame to frame; not available in clip mode");
-    if (!all_tr_host || !d_frames || !d_out || n_total < 1 || first < 0 || count <= 0 || first + count > n_total)
+    if (!all_tr || !d_frames || !d_out || n_total < 1 || first < 0 || count <= 0 || first + count > n_total)
         return vs_set_error(VS_ERR_INVALID_ARG, "bad chunk");
     CUDA_TRY(cudaSetDevice(device_));
-    VS_TRY(clean());
+    if (device_in) {
+        // asynchronous variant: everything below is enqueued on the public stream behind whatever the handle still has
+        // in flight (the analysis of this chunk); the host state is reset without the blocking sync of clean()
+        VS_TRY(join());
+        queue_.clear();
+        for (bool& bb : evB_set_) bb = false;
+        for (bool& bb : evA_set_) bb = false;
+        for (bool& bb : evW_set_) bb = false;
+        for (bool& bb : c_pending_) bb = false;
+        last_detect_frame_ = -100;
+        first_ = true; next_index_ = 0; n_frames_ = 0; n_out_ = 0; detect_counter_ = 0;
+    } else {
+        VS_TRY(clean());
+    }
     const int b = p_.border_size;
     const int mode = b <= 0 ? 0 : (p_.crop_n_zoom ? ((w - 2 * b > 0 && h - 2 * b > 0) ? 2 : 0) : 1);
     VS_TRY(ensure_geometry(w, h, false, false, mode == 2));
@@ -945,7 +988,8 @@ vs_status Engine::render_chunk(const float* all_tr_host, int n_total, const uint
         wp_batch_cap_ = count;
     }
     if (n_tr > 0) {
-        CUDA_TRY(cudaMemcpyAsync(h_lanes_[0].transforms, all_tr_host, sizeof(float) * 3 * n_tr, cudaMemcpyHostToDevice, stream_));
+        CUDA_TRY(cudaMemcpyAsync(h_lanes_[0].transforms, all_tr, sizeof(float) * 3 * n_tr,
+                                 device_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
         launch_traj_build(d_lanes_, 1, n_tr, stream_);
         launches_ += 1;
     }
@@ -969,6 +1013,6 @@ vs_status Engine::render_chunk(const float* all_tr_host, int n_total, const uint
                                    cudaMemcpyDeviceToDevice, stream_));
     }
     n_out_ = n_warp;
-    CUDA_TRY(cudaStreamSynchronize(stream_));
+    if (!device_in) CUDA_TRY(cudaStreamSynchronize(stream_));
     return VS_OK;
 }

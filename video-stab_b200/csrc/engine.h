@@ -59,9 +59,12 @@ public:
     static int chunk_halo(int first);
     // d_frames: frames [first - chunk_halo(first), first + count), tight rows.  Writes transforms_[n-1] for
     // the generateTransform calls n = max(first,1) .. first+count-1 to out_host (3 floats each).
-    vs_status analyze_chunk(const uint8_t* d_frames, int w, int h, int first, int count, float* out_host, int* n_out);
+    // `out` is host memory (the call returns when it is filled) or, with device_out, device memory (asynchronous: the
+    // copy is ordered on the public stream, see join()).
+    vs_status analyze_chunk(const uint8_t* d_frames, int w, int h, int first, int count, float* out, bool device_out, int* n_out);
     // all_tr_host: the n_total-1 transforms of the whole clip.  d_frames: frames [first, first+count).
-    vs_status render_chunk(const float* all_tr_host, int n_total, const uint8_t* d_frames, int w, int h, int first,
+    // all_tr is host memory (synchronous call) or, with device_in, device memory (asynchronous on the public stream)
+    vs_status render_chunk(const float* all_tr, bool device_in, int n_total, const uint8_t* d_frames, int w, int h, int first,
                            int count, uint8_t* d_out, int* ow, int* oh);
 
     // per-stage CUDA-event timing (off by default; used by bench.py and the profiles)
@@ -102,6 +105,7 @@ private:
     vs_status setup_slot_guard();
     vs_status setup_ready();
     cudaStream_t sc(int gen) const { return multi_ ? sC_[gen & 1] : stream_; }
+    vs_status check_out_buffer(bool passthrough, uint8_t* const* outs, size_t out_stride, size_t out_capacity) const;
     vs_status emit(uint8_t* const* outs, size_t out_stride, size_t out_capacity, int io, int* ow, int* oh);
     StepInfo step_info(int pop_index) const;
     void free_all();

@@ -75,6 +75,86 @@ def stitch_transforms(local: np.ndarray, first: int, count: int, n_total: int, g
     return out
 
 
+# ------------------------------------------------------------------------------------------ device-resident path
+# The transforms never leave the device: vs_clip_analyze_device writes them to a device buffer, the all-gather (NCCL
+# over NVLink) exchanges that buffer in place, vs_clip_render_device consumes the stitched list.  Nothing blocks the host.
+def stitch_index(n_total: int, world: int):
+    """Row indices into the (world * per, 3) all-gather result that give the clip's n_total-1 transforms in order
+    (rank r contributed its k_r = first+count-max(first,1) transforms at rows r*per ..)."""
+    per = max(chunk_bounds(n_total, world, r)[1] for r in range(world))
+    idx = []
+    for r in range(world):
+        f, c = chunk_bounds(n_total, world, r)
+        k = f + c - max(f, 1) if c > 0 else 0
+        idx.extend(range(r * per, r * per + k))
+    assert len(idx) == n_total - 1, (len(idx), n_total)
+    return per, np.asarray(idx, np.int64)
+
+
+def stitch_transforms_tensor(local, n_total: int, group=None):
+    """`local`: (per, 3) float32 tensor on the rank's device (rows beyond the rank's own transforms are ignored).
+    Returns the (n_total-1, 3) transform list of the whole clip on the same device.  One all-gather of 12 bytes per
+    frame (NCCL on GPUs, gloo in the CPU tests); no host round trip."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    per, idx = stitch_index(n_total, world)
+    assert tuple(local.shape) == (per, 3) and local.dtype == torch.float32
+    if world == 1:
+        gathered = local
+    elif dist.get_backend(group) == "nccl":
+        gathered = torch.empty((world * per, 3), dtype=torch.float32, device=local.device)
+        dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)
+    else:
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local.contiguous(), group=group)
+        gathered = torch.cat(parts, 0)
+    return gathered.index_select(0, torch.from_numpy(idx).to(local.device))
+
+
+def analyze_chunk_device(st: Stabilizer, d_frames_ptr: int, w: int, h: int, first: int, count: int, d_out_ptr: int) -> int:
+    """Asynchronous vs_clip_analyze: transforms land in device memory at d_out_ptr, ordered on st.stream."""
+    n = C.c_int()
+    check(lib.vs_clip_analyze_device(st._h, d_frames_ptr, w, h, first, count, d_out_ptr, C.byref(n)))
+    return n.value
+
+
+def render_chunk_device(st: Stabilizer, d_all_transforms_ptr: int, n_total: int, d_frames_ptr: int, w: int, h: int,
+                        first: int, count: int, d_out_ptr: int) -> tuple[int, int]:
+    ow, oh = C.c_int(), C.c_int()
+    check(lib.vs_clip_render_device(st._h, d_all_transforms_ptr, n_total, d_frames_ptr, w, h, first, count, d_out_ptr,
+                                    C.byref(ow), C.byref(oh)))
+    return ow.value, oh.value
+
+
+def stabilize_chunk_distributed(st: Stabilizer, frames, halo_frames: int, n_total: int, first: int, count: int, out, group=None):
+    """One rank's share of a long clip, end to end on the device: analyse -> all-gather -> rebuild path -> smooth -> warp.
+    `frames`: (halo_frames + count, H, W, 3) uint8 CUDA tensor holding frames [first - halo_frames, first + count);
+    `out`: (count, H', W', 3) uint8 CUDA tensor.  Asynchronous; returns the stitched (n_total-1, 3) transform tensor."""
+    import torch
+    import torch.distributed as dist
+    assert halo_frames == halo(first)
+    h, w = int(frames.shape[1]), int(frames.shape[2])
+    fb = h * w * 3
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    per, _ = stitch_index(n_total, world)
+    local = torch.zeros((per, 3), dtype=torch.float32, device=frames.device)
+    ext = torch.cuda.ExternalStream(st.stream, device=frames.device)
+    cur = torch.cuda.current_stream(frames.device)
+    if count > 0:
+        analyze_chunk_device(st, frames.data_ptr(), w, h, first, count, local.data_ptr())
+    ev = torch.cuda.Event()
+    ev.record(ext)
+    cur.wait_event(ev)
+    full = stitch_transforms_tensor(local, n_total, group)
+    ev2 = torch.cuda.Event()
+    ev2.record(cur)
+    st.wait_event(ev2.cuda_event)
+    if count > 0:
+        render_chunk_device(st, full.data_ptr(), n_total, frames.data_ptr() + halo_frames * fb, w, h, first, count, out.data_ptr())
+    return full
+
+
 def stabilize_clip(frames, params: Parameters | None = None, out=None, n_chunks: int = 1, device: int = 0):
     """Single-process driver: `frames` is a (N,H,W,3) uint8 CUDA tensor.  With n_chunks > 1 the clip is
     processed chunk by chunk exactly as n_chunks ranks would (used to test the chunked path on one GPU)."""
