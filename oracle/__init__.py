@@ -58,11 +58,31 @@ def oracle_kind() -> str:
     return "reference" if reference_available() else "port"
 
 
+def gaussian_reads_out_of_bounds(params) -> bool:
+    """Quirk B-Q8: `gaussianFilterConvolve` pads with `path[center - i]` and
+    `path[size - 1 - i]` without checking `size > center` (Stabilizer.cpp:1392-1401).  The first frame is popped when
+    the path holds gate-1 samples, so with `clamp(smoothingRadius,5,35) - 1 <= center` the reference reads outside
+    the vector — undefined behaviour, whatever the heap holds (observed: 164 LSB of garbage on the first outputs).
+    The drop-in DEFINES that case (box filter until the path is longer than `center`), which is what the Python
+    restatement implements; the compiled reference cannot be an oracle there."""
+    import math
+    import numpy as np
+    if getattr(params, "smoothingMethod", "box") != "gaussian":
+        return False
+    if getattr(params, "adaptiveSmoothing", False):
+        return True                                   # the gate moves with the data: be conservative
+    sigma = np.float32(params.gaussianSigma)
+    k = max(3, int(math.ceil(np.float32(6) * sigma)))
+    k += k % 2 == 0
+    gate = max(5, min(int(params.smoothingRadius), 35))
+    return gate - 1 <= k // 2
+
+
 def run_clip(frames, params, flush: bool = True, use_optimized: bool = False):
     """Push every frame, then flush — through the compiled reference when oracle/_ref is present (it travels to
     the GPU box with the snapshot), else through the Python restatement (bit-identical, tests/test_ref_pin.py).
     Returns (outputs, stabilizer) with `.frame_records`, `.output_records`, `.first_corners` on either."""
-    if reference_available():
+    if reference_available() and not gaussian_reads_out_of_bounds(params):
         from . import ref_lib
         return ref_lib.run_clip(frames, params, flush=flush, use_optimized=use_optimized)
     from . import stabilizer_ref

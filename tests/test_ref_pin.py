@@ -116,6 +116,27 @@ def test_reference_intents_are_reached():
     assert intents.count(2) >= 20 and 3 in intents, f"SHAKE_REMOVAL / FOLLOW_ACTION not reached: {intents}"
 
 
+def test_gaussian_short_path_is_undefined_in_the_reference_and_defined_here():
+    """Quirk B-Q8: with gate-1 <= centre the reference's gaussianFilterConvolve reads outside the path vector
+    (Stabilizer.cpp:1392-1401) — undefined behaviour.  The restatement (and the CUDA path) fall back to the box filter until
+    the path is longer than the kernel centre.  Everything that does not depend on those out-of-bounds reads still agrees
+    bit for bit: all transforms, and every output popped once the path is long enough."""
+    import oracle
+    params = Parameters(smoothingRadius=7, smoothingMethod="gaussian", gaussianSigma=3.5)      # centre 10, first pop at 6 samples
+    assert oracle.gaussian_reads_out_of_bounds(params)
+    assert not oracle.gaussian_reads_out_of_bounds(Parameters(smoothingRadius=10, smoothingMethod="gaussian", gaussianSigma=2.0))
+    clip = synthclip.make_clip(640, 360, 40, 607)
+    o_port, port = run_clip(clip, params)
+    o_ref, ref = ref_lib.run_clip(clip, params)
+    assert np.array_equal(bits(np.array(port.transforms).reshape(-1, 3)), bits(ref.transforms()))
+    centre, checked = 10, 0
+    for a, b, x, y in zip(port.output_records, ref.output_records, o_port, o_ref):
+        if a.T is not None and a.path_len > centre + 1:
+            assert np.array_equal(bits(a.smoothed), bits(b.smoothed)) and np.array_equal(x, y), f"output {a.index}"
+            checked += 1
+    assert checked >= 20
+
+
 # ----------------------------------------------------------------------------- pure host functions, on their own
 @pytest.fixture(scope="module")
 def ref_box():

@@ -395,7 +395,7 @@ vs_status vs_clip_render_device(vs_stabilizer* s, const float* d_all_transforms,
 static vs_status scratch_engine(Engine** e, int max_corners = 200, double min_dist = 1.0) {
     vs_params p;
     vs_params_default(&p);
-    p.max_corners = max_corners;
+    p.max_corners = (max_corners <= 0 || max_corners > 2048) ? 2048 : max_corners;   // sizes the key-point buffers only
     p.min_distance = min_dist;
     int dev = 0;
     cudaGetDevice(&dev);
