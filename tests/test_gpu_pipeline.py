@@ -684,7 +684,7 @@ def test_config4_64_streams_batch_equals_singles(vsb):
     for s in range(S):
         st = vsb.Stabilizer(params)
         m = st.push_many_device(lane_clip[s].data_ptr(), fb, n, w, h, w * 3, out_s.data_ptr(), w * 3, fb, borrow=True)
-        while st.flush_device(out_s[m].data_ptr(), w * 3, fb) is not None:
+        while st.flush_device(out_s[min(m, n - 1)].data_ptr(), w * 3, fb) is not None:
             m += 1
         st.sync()
         assert m == n
@@ -726,7 +726,7 @@ def test_motion_intents_vs_live_oracle(vsb, cv2_noopt, kind):
 
 @pytest.mark.parametrize("kw", [dict(smoothingRadius=6), dict(smoothingRadius=5, borderType="reflect", borderSize=12)])
 def test_too_small_output_buffer_is_recoverable(vsb, kw):
-    """A too-small output buffer is reported BEFORE anything is queued or launched (VS_ERR_BUFFER_TOO_SMALL = 4): repeating
+    """A too-small output buffer is reported BEFORE anything is queued or launched (VS_ERR_BUFFER_TOO_SMALL = 5): repeating
     the call with a large enough buffer continues the stream as if nothing had happened (same frames as a clean run)."""
     import ctypes as C
     from video_stab_b200._capi import lib
@@ -744,7 +744,7 @@ def test_too_small_output_buffer_is_recoverable(vsb, kw):
         if i % 3 == 0:      # first try with a buffer one byte short
             rc = lib.vs_stabilizer_push(st._h, f.ctypes.data, w, h, w * 3, small.ctypes.data, 0, small.size, C.byref(ow), C.byref(oh), C.byref(produced))
             if rc != 0:
-                assert rc == 4 and not produced.value
+                assert rc == 5 and not produced.value
                 failures += 1
             elif produced.value:
                 raise AssertionError("a frame fitted into a too-small buffer")
@@ -758,7 +758,7 @@ def test_too_small_output_buffer_is_recoverable(vsb, kw):
         rc = lib.vs_stabilizer_flush(st._h, small.ctypes.data, 0, w * h * 3 - 1, C.byref(ow), C.byref(oh), C.byref(produced))
         if rc == 0 and not produced.value:
             break
-        assert rc == 4, "flush into a too-small buffer must be refused"
+        assert rc == 5, "flush into a too-small buffer must be refused"
         rc = lib.vs_stabilizer_flush(st._h, big.ctypes.data, 0, big.size, C.byref(ow), C.byref(oh), C.byref(produced))
         assert rc == 0 and produced.value
         got.append(big[: ow.value * oh.value * 3].reshape(oh.value, ow.value, 3).copy())
