@@ -80,3 +80,38 @@ def pan_clip(width: int, height: int, n_frames: int, seed: int, speed: float = 1
     base = base_texture(width + int(speed * n_frames) + 2 * MARGIN, height, seed)
     cx = (base.shape[1] - width) / 2.0 - MARGIN
     return np.stack([render_frame(base, (-cx + speed * k, 0.0, 0.0), width, height) for k in range(n_frames)])
+
+
+class DeviceClip:
+    """An arbitrarily long clip generated ON THE DEVICE from a seed (a 10-minute 1080p clip is 112 GB raw, so it cannot
+    be built on the host): integer-offset crops of five pre-rotated copies of one seeded texture, following a slow
+    sinusoidal pan plus seeded per-frame jitter (N(0, 3^2) px, rotation from {0, +-0.002, +-0.004} rad).  Every rank of a
+    multi-GPU run builds the same clip from the same seed and materialises only its own frames.  Needs torch + CUDA."""
+
+    PAD = 96
+
+    def __init__(self, width: int, height: int, n_frames: int, seed: int, device):
+        import cv2  # data tooling only
+        import torch
+        self.torch, self.w, self.h, self.n, self.device = torch, width, height, n_frames, device
+        m = self.PAD
+        base = base_texture(width + 2 * m - 2 * MARGIN, height + 2 * m - 2 * MARGIN, seed)
+        cx, cy = base.shape[1] / 2.0, base.shape[0] / 2.0
+        self.rots = []
+        for a in (-0.004, -0.002, 0.0, 0.002, 0.004):
+            c, s = np.cos(a), np.sin(a)
+            mat = np.array([[c, -s, cx - c * cx + s * cy], [s, c, cy - s * cx - c * cy]])
+            self.rots.append(torch.from_numpy(cv2.warpAffine(base, mat, (base.shape[1], base.shape[0]))).to(device))
+        rng = np.random.default_rng(seed + 1)
+        k = np.arange(n_frames)
+        self.xs = np.clip(np.rint(m + 40 * np.sin(2 * np.pi * k / 240.0) + rng.normal(0, 3, n_frames)), 0, 2 * m).astype(int)
+        self.ys = np.clip(np.rint(m + 20 * np.sin(2 * np.pi * k / 180.0 + 1.0) + rng.normal(0, 3, n_frames)), 0, 2 * m).astype(int)
+        self.rs = rng.integers(0, len(self.rots), n_frames)
+
+    def frames(self, a: int, b: int, out=None):
+        """frames [a, b) as a contiguous (b-a, H, W, 3) uint8 tensor on the device"""
+        if out is None:
+            out = self.torch.empty((b - a, self.h, self.w, 3), dtype=self.torch.uint8, device=self.device)
+        for i in range(a, b):
+            out[i - a] = self.rots[self.rs[i]][self.ys[i]:self.ys[i] + self.h, self.xs[i]:self.xs[i] + self.w]
+        return out

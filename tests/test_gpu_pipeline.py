@@ -654,7 +654,7 @@ def test_config2_1080p_r15_live_oracle_full_frames(vsb, cv2_noopt):
         assert (d > 1).mean() < 1e-3
         exact += int(d.max() == 0)
     print(f"config 2: bit-exact output frames {exact}/{n}, worst interior difference {worst} LSB")
-    assert exact >= int(0.9 * n), f"only {exact}/{n} output frames are bit-exact"
+    assert exact >= int(0.98 * n), f"only {exact}/{n} output frames are bit-exact"
 
 
 def test_config4_64_streams_batch_equals_singles(vsb):

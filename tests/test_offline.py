@@ -95,30 +95,8 @@ def test_chunked_clip_equals_streamed(kw):
 
 
 def _synthetic_long_clip(torch, w, h, n, seed, dev):
-    """n frames generated ON THE DEVICE from the seed (a 10-minute 1080p clip is 112 GB raw): integer-offset crops of a
-    few pre-rotated copies of one texture, following a smooth pan + seeded jitter.  Returns a function that
-    materialises frames [a, b) as a (b-a, h, w, 3) uint8 tensor."""
-    import cv2
-    m = 96
-    base = synthclip.base_texture(w + 2 * m - 2 * synthclip.MARGIN, h + 2 * m - 2 * synthclip.MARGIN, seed)
-    rots = []
-    for a in (-0.004, -0.002, 0.0, 0.002, 0.004):
-        c, s_ = np.cos(a), np.sin(a)
-        cx, cy = base.shape[1] / 2.0, base.shape[0] / 2.0
-        M = np.array([[c, -s_, cx - c * cx + s_ * cy], [s_, c, cy - s_ * cx - c * cy]])
-        rots.append(torch.from_numpy(cv2.warpAffine(base, M, (base.shape[1], base.shape[0]))).to(dev))
-    rng = np.random.default_rng(seed + 1)
-    k = np.arange(n)
-    xs = np.clip(np.rint(m + 40 * np.sin(2 * np.pi * k / 240.0) + rng.normal(0, 3, n)), 0, 2 * m).astype(int)
-    ys = np.clip(np.rint(m + 20 * np.sin(2 * np.pi * k / 180.0 + 1.0) + rng.normal(0, 3, n)), 0, 2 * m).astype(int)
-    rs = rng.integers(0, len(rots), n)
-
-    def frames(a, b):
-        out = torch.empty((b - a, h, w, 3), dtype=torch.uint8, device=dev)
-        for i in range(a, b):
-            out[i - a] = rots[rs[i]][ys[i]:ys[i] + h, xs[i]:xs[i] + w]
-        return out
-    return frames
+    """n frames generated on the device from the seed (synthclip.DeviceClip); returns frames(a, b)."""
+    return synthclip.DeviceClip(w, h, n, seed, dev).frames
 
 
 def _frame_checksums(torch, frames):

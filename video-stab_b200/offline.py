@@ -155,6 +155,51 @@ def stabilize_chunk_distributed(st: Stabilizer, frames, halo_frames: int, n_tota
     return full
 
 
+def stabilize_rank_chunks(st: Stabilizer, chunk_frames: dict, n_total: int, n_chunks: int, my_chunks, out_ring, group=None):
+    """One rank's share of a long clip cut into `n_chunks` temporal chunks (n_chunks a multiple of the world size; rank r
+    owns the contiguous block `my_chunks`).  chunk_frames[c]: (halo + count, H, W, 3) uint8 CUDA tensor of frames
+    [first_c - halo_c, first_c + count_c).  Every chunk is analysed, ONE all-gather stitches the transforms of the whole
+    clip (device to device), then every chunk is smoothed and warped into `out_ring` ((max count, H', W', 3); reused chunk
+    after chunk when a rank owns several).  Asynchronous on the handle's streams and torch's current stream; returns the
+    stitched (n_total-1, 3) transform tensor."""
+    import torch
+    import torch.distributed as dist
+    my_chunks = list(my_chunks)
+    per, idx = stitch_index(n_total, n_chunks)
+    some = chunk_frames[my_chunks[0]]
+    dev, h, w = some.device, int(some.shape[1]), int(some.shape[2])
+    fb = h * w * 3
+    local = torch.zeros((len(my_chunks) * per, 3), dtype=torch.float32, device=dev)
+    ext = torch.cuda.ExternalStream(st.stream, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    ev0 = torch.cuda.Event()
+    ev0.record(cur)
+    st.wait_event(ev0.cuda_event)                      # `local` was zeroed on torch's stream
+    for k, c in enumerate(my_chunks):
+        first, count = chunk_bounds(n_total, n_chunks, c)
+        if count > 0:
+            analyze_chunk_device(st, chunk_frames[c].data_ptr(), w, h, first, count, local[k * per].data_ptr())
+    ev = torch.cuda.Event()
+    ev.record(ext)
+    cur.wait_event(ev)
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world > 1:
+        gathered = torch.empty((n_chunks * per, 3), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gathered, local, group=group)
+    else:
+        gathered = local
+    full = gathered.index_select(0, torch.from_numpy(idx).to(dev))
+    ev2 = torch.cuda.Event()
+    ev2.record(cur)
+    st.wait_event(ev2.cuda_event)
+    for c in my_chunks:
+        first, count = chunk_bounds(n_total, n_chunks, c)
+        if count > 0:
+            hl = halo(first)
+            render_chunk_device(st, full.data_ptr(), n_total, chunk_frames[c].data_ptr() + hl * fb, w, h, first, count, out_ring.data_ptr())
+    return full
+
+
 def stabilize_clip(frames, params: Parameters | None = None, out=None, n_chunks: int = 1, device: int = 0):
     """Single-process driver: `frames` is a (N,H,W,3) uint8 CUDA tensor.  With n_chunks > 1 the clip is
     processed chunk by chunk exactly as n_chunks ranks would (used to test the chunked path on one GPU)."""
