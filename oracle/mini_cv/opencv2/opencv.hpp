@@ -271,8 +271,8 @@ public:
         if (data && r == rows && c == cols && type == type_ && isContinuous()) return;
         rows = r; cols = c; type_ = type;
         step.v = (size_t)c * elemSize();
-        buf_ = std::make_shared<std::vector<uchar>>((size_t)r * step.v + 64);
-        data = buf_->data();
+        buf_ = std::shared_ptr<uchar>(new uchar[(size_t)r * step.v + 64], std::default_delete<uchar[]>());   // uninitialised, like cv::Mat::create
+        data = buf_.get();
     }
     void create(Size s, int type) { create(s.height, s.width, type); }
     void release() { rows = cols = 0; data = nullptr; buf_.reset(); step.v = 0; }
@@ -374,7 +374,7 @@ public:
 
 protected:
     int type_ = 0;
-    std::shared_ptr<std::vector<uchar>> buf_;
+    std::shared_ptr<uchar> buf_;
 };
 
 // Mat_<T> with the `(Mat_<float>(2,2) << a, b, c, d)` comma initialiser

@@ -72,7 +72,14 @@ def _put(dst, arr):
         arr = arr[:, :, None]
     if out.shape != arr.shape:
         raise ValueError(f"mini_cv: destination {out.shape} != result {arr.shape}")
-    out[...] = arr
+    if arr.ctypes.data != out.ctypes.data:        # cv2 was handed `out` as dst= and wrote in place: nothing to copy
+        out[...] = arr
+
+
+def _dst(m):
+    """the destination Mat as a cv2 `dst=` argument (cv2 writes in place when shape, type and contiguity fit)"""
+    out = _np(m)
+    return out if out.flags.c_contiguous else None
 
 
 _SIG = [
@@ -141,10 +148,10 @@ class CvOps:
     # ---- the operations on the stabilize() path
     def _resize(self, src, dst, interp):
         d = _np(dst)
-        _put(dst, self.cv2.resize(_np(src), (d.shape[1], d.shape[0]), interpolation=interp))
+        _put(dst, self.cv2.resize(_np(src), (d.shape[1], d.shape[0]), dst=_dst(dst), interpolation=interp))
 
     def _cvt_color(self, src, dst, code):
-        _put(dst, self.cv2.cvtColor(_np(src), code))
+        _put(dst, self.cv2.cvtColor(_np(src), code, dst=_dst(dst)))
 
     def _gftt(self, img, mask, max_corners, quality, min_dist, block, harris, k, xy, cap, n):
         m = _np(mask) if mask else None
@@ -187,12 +194,12 @@ class CvOps:
             M = M.astype(f32)
         d = _np(dst)
         bv = tuple(border_value[i] for i in range(4))
-        _put(dst, self.cv2.warpAffine(_np(src), M, (d.shape[1], d.shape[0]), flags=flags, borderMode=border_mode, borderValue=bv))
+        _put(dst, self.cv2.warpAffine(_np(src), M, (d.shape[1], d.shape[0]), dst=_dst(dst), flags=flags, borderMode=border_mode, borderValue=bv))
         self._emit("warp", T=M.copy())
 
     def _copy_make_border(self, src, dst, top, bottom, left, right, btype, value):
         bv = tuple(value[i] for i in range(4))
-        _put(dst, self.cv2.copyMakeBorder(_np(src), top, bottom, left, right, btype, value=bv))
+        _put(dst, self.cv2.copyMakeBorder(_np(src), top, bottom, left, right, btype, dst=_dst(dst), value=bv))
 
     def _add_weighted(self, a, alpha, b, beta, gamma, dst):
         # the Python restatement documents that cv::addWeighted is taken with optimisations ON (its SIMD path fuses
@@ -301,6 +308,7 @@ def _declare(lib):
         "vsref_new": (vp, [vp]), "vsref_delete": (None, [vp]), "vsref_clean": (None, [vp]),
         "vsref_stabilize": (ci, [vp, vp, ci, ci, cz, vp, cz, PI, PI]),
         "vsref_flush": (ci, [vp, vp, cz, PI, PI]),
+        "vsref_stabilize_nocopy": (ci, [vp, vp, ci, ci, cz, PI, PI]),
         "vsref_n_transforms": (ci, [vp]), "vsref_queue_size": (ci, [vp]), "vsref_smoothing_radius": (ci, [vp]),
         "vsref_get_transforms": (None, [vp, vp, ci]), "vsref_get_path": (None, [vp, vp, ci]),
         "vsref_n_smoothed": (ci, [vp]), "vsref_get_smoothed": (None, [vp, vp, ci]),
@@ -450,6 +458,15 @@ class RefStabilizer:
         if rc == 0:
             return None
         return out[: ow.value * oh.value * 3].reshape(oh.value, ow.value, 3).copy()
+
+    def stabilize_nocopy(self, frame: np.ndarray) -> bool:
+        """Timing path: no input copy (the caller keeps `frame` alive and unchanged while it is queued), no output copy,
+        no records.  Returns whether a stabilized frame was produced."""
+        ow, oh = C.c_int(), C.c_int()
+        rc = self.lib.vsref_stabilize_nocopy(self.h, _fp(frame), frame.shape[1], frame.shape[0], frame.strides[0], C.byref(ow), C.byref(oh))
+        if rc < 0:
+            raise RuntimeError(f"reference stabilize failed rc={rc}: {self.ops.errors[-3:]}")
+        return rc == 1
 
     def flush(self):
         if self.lib.vsref_queue_size(self.h) == 0:

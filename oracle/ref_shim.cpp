@@ -108,6 +108,22 @@ int vsref_stabilize(void *s, const unsigned char *bgr, int w, int h, size_t stri
         return -1;
     }
 }
+// Timing variant (bench.py's CPU arm): the frame is a cv::Mat HEADER over the caller's buffer (no input copy: the reference
+// queues the Mat it is given, Stabilizer.cpp:376, so the caller keeps the buffer alive) and the stabilized cv::Mat is only
+// inspected, not copied out.  1 = produced, 0 = empty, < 0 = error.
+int vsref_stabilize_nocopy(void *s, unsigned char *bgr, int w, int h, size_t stride, int *ow, int *oh) {
+    try {
+        cv::Mat frame(h, w, CV_8UC3, bgr, stride);
+        cv::Mat out = static_cast<Stabilizer *>(s)->stabilize(frame);
+        if (out.empty()) return 0;
+        *ow = out.cols;
+        *oh = out.rows;
+        return 1;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "vsref_stabilize_nocopy: %s\n", e.what());
+        return -1;
+    }
+}
 int vsref_flush(void *s, unsigned char *dst, size_t cap, int *ow, int *oh) {
     try {
         return emit(static_cast<Stabilizer *>(s)->flush(), dst, cap, ow, oh);
