@@ -103,8 +103,16 @@ public:
 
     // Returns the stabilized frame, or an empty Mat while the reference would (first frame, latency gate).
     // Like the reference it never throws on the hot path: on an internal error the input frame is returned.
+    // A frame that is not CV_8UC3 is refused (empty Mat, lastStatus() == VS_ERR_INVALID_ARG): the reference would raise a
+    // cv::Exception inside cvtColor for anything but 3-channel input, and reading e.g. a BGRA or 16-bit Mat as packed BGR would
+    // run past its rows.
     cv::Mat stabilize(const cv::Mat& frame) {
         if (frame.empty()) return cv::Mat();
+        if (frame.type() != CV_8UC3) {
+            status_ = VS_ERR_INVALID_ARG;
+            error_ = "vs::Stabilizer::stabilize: frame must be CV_8UC3 (BGR)";
+            return cv::Mat();
+        }
         const int b = (params_.borderSize > 0 && !params_.cropNZoom) ? params_.borderSize : 0;
         cols_hint_ = frame.cols + 2 * b;
         rows_hint_ = frame.rows + 2 * b;
@@ -112,6 +120,7 @@ public:
         int ow = 0, oh = 0, produced = 0;
         vs_status st = vs_stabilizer_push(h_, frame.data, frame.cols, frame.rows, (size_t)frame.step, out.data,
                                           (size_t)out.step, (size_t)out.step * out.rows, &ow, &oh, &produced);
+        note(st);
         if (st != VS_OK) return frame;
         if (!produced) return cv::Mat();
         if (ow != out.cols || oh != out.rows) return out(cv::Rect(0, 0, ow, oh));   // pass-through of the last frame
@@ -122,11 +131,17 @@ public:
         cv::Mat out(rows_hint_, cols_hint_, CV_8UC3);
         int ow = 0, oh = 0, produced = 0;
         vs_status st = vs_stabilizer_flush(h_, out.data, (size_t)out.step, (size_t)out.step * out.rows, &ow, &oh, &produced);
+        note(st);
         if (st != VS_OK || !produced) return cv::Mat();
         if (ow != out.cols || oh != out.rows) return out(cv::Rect(0, 0, ow, oh));
         return out;
     }
-    void clean() { vs_stabilizer_clean(h_); }
+    void clean() { note(vs_stabilizer_clean(h_)); }
+
+    // Not part of the reference's interface: the reference swallows every failure (it returns the input frame or an empty
+    // Mat), which hides real errors; these two let a caller see the status of the last call.
+    vs_status lastStatus() const { return status_; }
+    const std::string& lastError() const { return error_; }
 
     static void to_c(const Parameters& s, vs_params* p) {
         vs_params_default(p);
@@ -161,7 +176,13 @@ public:
     }
 
 private:
+    void note(vs_status st) {
+        status_ = st;
+        if (st != VS_OK) error_ = vs_last_error();
+    }
     Parameters params_;
+    vs_status status_ = VS_OK;
+    std::string error_;
     vs_stabilizer* h_ = nullptr;
     int cols_hint_ = 0, rows_hint_ = 0;      // output geometry remembered for flush()
 };

@@ -768,3 +768,43 @@ def test_too_small_output_buffer_is_recoverable(vsb, kw):
         assert a.shape == c.shape and np.array_equal(a, c), f"frame {i} differs after a refused call"
     for i in range(n - 1):
         assert list(st.frame_record(i).transform) == list(st0.frame_record(i).transform)
+
+
+def test_lone_first_frame_flushed_from_the_device_ring(vsb):
+    """push_device (copy mode) of ONE frame, then flush: the pass-through read on the public stream must be ordered behind
+    the ring copy on the pyramid stream (there is no analysis chain between them for a lone frame).  Repeated to give a
+    missing dependency a chance to show."""
+    w, h = 1920, 1080
+    fb = h * w * 3
+    for rep in range(20):
+        frame = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device="cuda")
+        out = torch.zeros_like(frame)
+        torch.cuda.synchronize()
+        st = vsb.Stabilizer(vsb.Parameters(smoothingRadius=5))
+        assert st.push_device(frame.data_ptr(), w, h, w * 3, out.data_ptr(), w * 3, fb, borrow=False) is None
+        assert st.flush_device(out.data_ptr(), w * 3, fb) == (w, h)
+        st.sync()
+        assert torch.equal(out, frame), f"repetition {rep}"
+        del st
+
+
+def test_handles_on_two_devices_in_one_process(vsb):
+    """Per-device kernel attributes (k_select / k_motion opt in to > 48 KB of dynamic shared memory, and that opt-in is per
+    device): handles on cuda:0 and cuda:1 in one process produce the same frames as each other."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w, h, n = 640, 360, 16
+    clip = synthclip.make_clip(w, h, n, 808)
+    outs = []
+    for dev in (0, 1, 0):
+        st = vsb.Stabilizer(vsb.Parameters(smoothingRadius=6), device=dev)
+        got = [o for o in (st.stabilize(f) for f in clip) if o is not None]
+        while True:
+            o = st.flush()
+            if o is None:
+                break
+            got.append(o)
+        assert len(got) == n
+        outs.append(got)
+    for a, b, c in zip(*outs):
+        assert np.array_equal(a, b) and np.array_equal(a, c)

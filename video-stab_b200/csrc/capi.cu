@@ -168,7 +168,18 @@ vs_status vs_stabilizer_push(vs_stabilizer* s, const uint8_t* bgr, int width, in
     API_BEGIN
     const uint8_t* f[1] = {bgr};
     uint8_t* o[1] = {out};
-    return s->eng->push(bgr ? f : nullptr, width, height, stride, o, out_stride, out_capacity, 0, true, out_width, out_height, produced);
+    vs_status rc = s->eng->push(bgr ? f : nullptr, width, height, stride, o, out_stride, out_capacity, 0, true, out_width, out_height, produced);
+    if ((rc == VS_ERR_CUDA || rc == VS_ERR_OUT_OF_MEMORY) && bgr && out && width > 0 && height > 0) {
+        // The reference never throws on this path: every cv::Exception degrades to the un-warped frame (Stabilizer.cpp:609-626,
+        // :1049-1066).  There is no CPU fallback here, so a device failure is REPORTED (status + vs_last_error()) and the
+        // input frame is handed back unchanged when the caller's buffer can take it.
+        const size_t tight = (size_t)width * 3, is = stride ? stride : tight, os = out_stride ? out_stride : tight;
+        if (is >= tight && os >= tight && os * (size_t)(height - 1) + tight <= out_capacity) {
+            for (int y = 0; y < height; ++y) memcpy(out + (size_t)y * os, bgr + (size_t)y * is, tight);
+            *out_width = width; *out_height = height; *produced = 1;
+        }
+    }
+    return rc;
     API_END
 }
 vs_status vs_stabilizer_flush(vs_stabilizer* s, uint8_t* out, size_t out_stride, size_t out_capacity, int* out_width,
@@ -408,19 +419,20 @@ vs_status vs_k_warp_affine_bgr8(const uint8_t* d_src, int src_w, int src_h, size
     if (!d_src || !d_dst || !T_host || n_frames < 1) return vs_set_error(VS_ERR_INVALID_ARG, "bad argument");
     API_BEGIN
     cudaStream_t st = (cudaStream_t)stream;
-    static thread_local WarpParams* d_wp = nullptr;
-    static thread_local int d_wp_cap = 0;
-    if (n_frames > d_wp_cap) {
-        if (d_wp) cudaFree(d_wp);
-        CUDA_TRY(cudaMalloc((void**)&d_wp, sizeof(WarpParams) * n_frames));
-        d_wp_cap = n_frames;
-    }
+    // The set-up block lives exactly as long as this call's work on `st`: stream-ordered allocation on the caller's stream and
+    // current device (calls on different streams or devices never share it; nothing is kept between calls).
+    WarpParams* d_wp = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d_wp, sizeof(WarpParams) * n_frames, st));
     std::vector<WarpParams> h(n_frames);
     for (int i = 0; i < n_frames; ++i) warp_params_from_T(T_host + 6 * i, &h[i]);
-    CUDA_TRY(cudaMemcpyAsync(d_wp, h.data(), sizeof(WarpParams) * n_frames, cudaMemcpyHostToDevice, st));
-    launch_warp_matrices(d_src, src_w, src_h, src_stride, src_frame_bytes, d_dst, dst_w, dst_h, dst_stride,
-                         dst_frame_bytes, d_wp, n_frames, st);
-    CUDA_TRY(cudaGetLastError());
+    cudaError_t ce = cudaMemcpyAsync(d_wp, h.data(), sizeof(WarpParams) * n_frames, cudaMemcpyHostToDevice, st);   // pageable source: staged before return
+    if (ce == cudaSuccess) {
+        launch_warp_matrices(d_src, src_w, src_h, src_stride, src_frame_bytes, d_dst, dst_w, dst_h, dst_stride,
+                             dst_frame_bytes, d_wp, n_frames, st);
+        ce = cudaGetLastError();
+    }
+    cudaFreeAsync(d_wp, st);
+    CUDA_TRY(ce);
     return VS_OK;
     API_END
 }

@@ -633,6 +633,17 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
     for (int l = 0; l < n_lanes_; ++l) dst.p[l] = host_io ? d_out_ + out_bytes_ * ((size_t)l * VS_OUT_SLOTS + oslot) : outs[l];
     const size_t dstride = host_io ? tight : out_stride;
     if (passthrough) {
+        if (multi_ && e.in_ring) {
+            // A passed-through frame has no transform, hence no pyramid -> LK -> motion chain that would order its ring copy
+            // (enqueued on the pyramid or copy-in stream) before this read on the public stream: order it explicitly.  An
+            // event recorded now is behind that copy.  Happens once per clip (the last frame), or for a lone first frame.
+            CUDA_TRY(cudaEventRecord(evJ_[VS_TRACK_STREAMS + 2], sP_));
+            CUDA_TRY(cudaStreamWaitEvent(stream_, evJ_[VS_TRACK_STREAMS + 2], 0));
+            if (sH_) {
+                CUDA_TRY(cudaEventRecord(evJ_[VS_TRACK_STREAMS + 3], sH_));
+                CUDA_TRY(cudaStreamWaitEvent(stream_, evJ_[VS_TRACK_STREAMS + 3], 0));
+            }
+        }
         for (int l = 0; l < n_lanes_; ++l)
             CUDA_TRY(cudaMemcpy2DAsync(dst.p[l], dstride, e.frames[l], e.stride, tight, h, cudaMemcpyDeviceToDevice, stream_));
     } else {

@@ -543,10 +543,13 @@ size_t gftt_grid_words(int w, int h, double min_dist) {
 void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_corners, double quality,
                           double min_dist, int record_frame_no, int gen, int kp_slot, cudaStream_t st) {
     const int w = slot < 0 ? VS_FW : VS_AW, h = slot < 0 ? VS_FH : VS_AH;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per DEVICE (a process may hold handles on several GPUs): once per device, not once per process
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_DYN_BYTES);
-        attr_set = true;
+        attr_set[dev] = true;
     }
     dim3 g1((w + EIG_TW - 1) / EIG_TW, (h + EIG_TH - 1) / EIG_TH, n_lanes);
     k_eig_nms<<<g1, 256, 0, st>>>(lanes, slot, gen);

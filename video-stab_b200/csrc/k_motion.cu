@@ -787,10 +787,13 @@ __global__ void __launch_bounds__(MO_THREADS) k_motion(const LaneDev* __restrict
 }
 
 void launch_motion(const LaneDev* lanes, int n_lanes, StepInfo info, int phase, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // per DEVICE, not per process (see launch_good_features)
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         cudaFuncSetAttribute(k_motion, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoSmem));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     k_motion<<<dim3(1, 1, n_lanes), MO_THREADS, sizeof(MoSmem), st>>>(lanes, info, phase);
 }
