@@ -28,7 +28,8 @@ OUT = os.path.join(HERE, "_ref")
 TARGETS = {
     # output                     reference TUs (read in place)         shim
     "libvideostab_ref.so": (["src/Stabilizer.cpp"], "ref_shim.cpp"),
-    "libstages_ref.so": (["src/RollCorrection.cpp", "src/AutoZoomCrop.cpp"], "ref_stages_shim.cpp"),
+    # the shim #includes src/RollCorrection.cpp and src/AutoZoomCrop.cpp (one TU, so their file-scope statics can be read back)
+    "libstages_ref.so": ([], "ref_stages_shim.cpp"),
 }
 
 CXXFLAGS = ["-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w"]
@@ -56,9 +57,11 @@ def build(force: bool = False, verbose: bool = False) -> list[str]:
         shim_path = os.path.join(HERE, shim)
         srcs = [os.path.join(REF, t) for t in tus]
         if reference_present() and os.path.exists(shim_path) and all(os.path.exists(s) for s in srcs):
-            if force or _stale(out, srcs + [shim_path] + hdrs + [os.path.join(REF, "include", "video", "Stabilizer.h")]):
+            deps = srcs + [shim_path] + hdrs + [os.path.join(REF, "include", "video", "Stabilizer.h"),
+                                                os.path.join(REF, "src", "RollCorrection.cpp"), os.path.join(REF, "src", "AutoZoomCrop.cpp")]
+            if force or _stale(out, deps):
                 cmd = ["g++"] + CXXFLAGS + ["-I", os.path.join(HERE, "mini_cv"), "-I", os.path.join(REF, "include"),
-                                            "-o", out] + srcs + [shim_path]
+                                            "-I", os.path.join(REF, "src"), "-o", out] + srcs + [shim_path]
                 res = subprocess.run(cmd, capture_output=True, text=True)
                 if verbose or res.returncode != 0:
                     sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -39,10 +39,12 @@ typedef struct mini_cv_ops {
     int (*kalman_release)(int handle);
     /* RollCorrection / AutoZoomCrop (cv::cuda:: in the reference; the CPU equivalents of the same OpenCV build) */
     int (*canny)(const mini_cv_mat *src, mini_cv_mat *dst, double low, double high, int aperture, int l2);
-    int (*hough_lines)(const mini_cv_mat *edges, double rho, double theta, int threshold, int max_lines, float *rho_theta, int cap, int *n);
+    int (*hough_lines)(const mini_cv_mat *edges, double rho, double theta, int threshold, int max_lines, float *rho_theta, int *votes, int cap, int *n);
     int (*gaussian_blur)(const mini_cv_mat *src, mini_cv_mat *dst, int kw, int kh, double sx, double sy);
     int (*remap)(const mini_cv_mat *src, mini_cv_mat *dst, const mini_cv_mat *mapx, const mini_cv_mat *mapy, int interp, int border_mode);
-    int (*morphology)(const mini_cv_mat *src, mini_cv_mat *dst, int op, int shape, int kw, int kh);
+    int (*morphology)(const mini_cv_mat *src, mini_cv_mat *dst, int op, const mini_cv_mat *kernel);
+    int (*structuring_element)(int shape, mini_cv_mat *dst);
+    int (*draw_contours)(mini_cv_mat *img, const int *pts_xy, const int *lens, int ncont, int idx, const double *color, int thickness);
     int (*rotation_matrix)(double cx, double cy, double angle, double scale, double *m6);
     int (*sobel)(const mini_cv_mat *src, mini_cv_mat *dst, int dx, int dy, int ksize);
 } mini_cv_ops;

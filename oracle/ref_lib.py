@@ -98,10 +98,12 @@ _SIG = [
     ("kalman_correct", [C.c_int, PM, PM]),
     ("kalman_release", [C.c_int]),
     ("canny", [PM, PM, C.c_double, C.c_double, C.c_int, C.c_int]),
-    ("hough_lines", [PM, C.c_double, C.c_double, C.c_int, C.c_int, PF, C.c_int, PI]),
+    ("hough_lines", [PM, C.c_double, C.c_double, C.c_int, C.c_int, PF, PI, C.c_int, PI]),
     ("gaussian_blur", [PM, PM, C.c_int, C.c_int, C.c_double, C.c_double]),
     ("remap", [PM, PM, PM, PM, C.c_int, C.c_int]),
-    ("morphology", [PM, PM, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("morphology", [PM, PM, C.c_int, PM]),
+    ("structuring_element", [C.c_int, PM]),
+    ("draw_contours", [PM, PI, PI, C.c_int, C.c_int, PD, C.c_int]),
     ("rotation_matrix", [C.c_double, C.c_double, C.c_double, C.c_double, PD]),
     ("sobel", [PM, PM, C.c_int, C.c_int, C.c_int]),
 ]
@@ -262,18 +264,21 @@ class CvOps:
 
     # ---- RollCorrection / AutoZoomCrop operations (cv::cuda:: in the reference -> the CPU functions of the same library)
     def _canny(self, src, dst, low, high, aperture, l2):
-        _put(dst, self.cv2.Canny(_np(src), low, high, apertureSize=aperture, L2gradient=bool(l2)))
+        g = np.ascontiguousarray(_np(src))
+        _put(dst, self.cv2.Canny(g, low, high, apertureSize=aperture, L2gradient=bool(l2)))
+        self._emit("canny", gray=g.copy(), edges=_np(dst).copy())
 
-    def _hough_lines(self, edges, rho, theta, threshold, max_lines, out, cap, n):
-        lines = self.cv2.HoughLines(_np(edges), rho, theta, threshold)
-        lines = np.zeros((0, 2), f32) if lines is None else lines.reshape(-1, 2).astype(f32)
+    def _hough_lines(self, edges, rho, theta, threshold, max_lines, out, votes, cap, n):
+        lv = self.cv2.HoughLinesWithAccumulator(np.ascontiguousarray(_np(edges)), rho, theta, threshold)
+        lv = np.zeros((0, 3), f32) if lv is None else lv.reshape(-1, 3).astype(f32)
         if max_lines > 0:
-            lines = lines[:max_lines]
-        lines = lines[:cap]
-        n[0] = len(lines)
-        if len(lines):
-            np.ctypeslib.as_array(out, shape=(len(lines) * 2,))[:] = lines.ravel()
-        self._emit("hough", lines=lines.copy())
+            lv = lv[:max_lines]
+        lv = lv[:cap]
+        n[0] = len(lv)
+        if len(lv):
+            np.ctypeslib.as_array(out, shape=(len(lv) * 2,))[:] = np.ascontiguousarray(lv[:, :2]).ravel()
+            np.ctypeslib.as_array(votes, shape=(len(lv),))[:] = lv[:, 2].astype(np.int32)
+        self._emit("hough", lines=lv[:, :2].copy(), votes=lv[:, 2].astype(np.int32), edges=_np(edges).copy())
 
     def _gaussian_blur(self, src, dst, kw, kh, sx, sy):
         _put(dst, self.cv2.GaussianBlur(_np(src), (kw, kh), sx, sigmaY=sy))
@@ -281,9 +286,21 @@ class CvOps:
     def _remap(self, src, dst, mapx, mapy, interp, border):
         _put(dst, self.cv2.remap(_np(src), _np(mapx), _np(mapy), interp, borderMode=border))
 
-    def _morphology(self, src, dst, op, shape, kw, kh):
-        k = self.cv2.getStructuringElement(shape, (kw, kh))
-        _put(dst, self.cv2.morphologyEx(_np(src), op, k))
+    def _morphology(self, src, dst, op, kernel):
+        _put(dst, self.cv2.morphologyEx(_np(src), op, np.ascontiguousarray(_np(kernel))))
+
+    def _structuring_element(self, shape, dst):
+        d = _np(dst)
+        _put(dst, self.cv2.getStructuringElement(shape, (d.shape[1], d.shape[0])))
+
+    def _draw_contours(self, img, pts, lens, ncont, idx, color, thickness):
+        cs, k = [], 0
+        for i in range(ncont):
+            c = np.array([[pts[2 * (k + j)], pts[2 * (k + j) + 1]] for j in range(lens[i])], np.int32).reshape(-1, 1, 2)
+            cs.append(c)
+            k += lens[i]
+        im = _np(img)
+        self.cv2.drawContours(im, cs, idx, tuple(color[i] for i in range(4)), thickness)
 
     def _rotation_matrix(self, cx, cy, angle, scale, m6):
         M = self.cv2.getRotationMatrix2D((cx, cy), angle, scale)

@@ -115,3 +115,30 @@ class DeviceClip:
         for i in range(a, b):
             out[i - a] = self.rots[self.rs[i]][self.ys[i]:self.ys[i] + self.h, self.xs[i]:self.xs[i] + self.w]
         return out
+
+
+def horizon_clip(width: int, height: int, n_frames: int, seed: int, roll_deg=None) -> np.ndarray:
+    """Frames with a strong straight horizon (bright sky over textured ground plus a few long straight structures) seen
+    through a slowly varying camera ROLL: input for RollCorrection (Canny + Hough find the horizon lines)."""
+    import cv2  # data tooling only
+    rng = np.random.default_rng(seed)
+    big_w, big_h = width + 4 * MARGIN, height + 4 * MARGIN
+    tex = base_texture(big_w - 2 * MARGIN, big_h - 2 * MARGIN, seed)
+    scene = (tex // 4 + 40).astype(np.uint8)
+    hy = big_h // 2
+    scene[:hy] = (scene[:hy] // 2 + 150).astype(np.uint8)                      # sky
+    cv2.line(scene, (0, hy), (big_w - 1, hy), (250, 250, 250), 3)
+    for k in range(3):
+        y = hy + 60 + 70 * k
+        cv2.line(scene, (0, y), (big_w - 1, y), (int(rng.integers(0, 80)),) * 3, 2)
+    if roll_deg is None:
+        k = np.arange(n_frames)
+        roll_deg = 3.0 * np.sin(2 * np.pi * k / 40.0) + rng.normal(0, 0.2, n_frames)
+    out = np.empty((n_frames, height, width, 3), np.uint8)
+    cx, cy = big_w / 2.0, big_h / 2.0
+    for i in range(n_frames):
+        M = cv2.getRotationMatrix2D((cx, cy), float(roll_deg[i]), 1.0)
+        M[0, 2] -= (big_w - width) / 2.0
+        M[1, 2] -= (big_h - height) / 2.0
+        out[i] = cv2.warpAffine(scene, M, (width, height), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+    return out
