@@ -244,6 +244,45 @@ vs_status vs_clip_analyze_device(vs_stabilizer* s, const uint8_t* d_frames, int 
 vs_status vs_clip_render_device(vs_stabilizer* s, const float* d_all_transforms, int n_total, const uint8_t* d_frames,
                                 int width, int height, int first, int count, uint8_t* d_out, int* out_width, int* out_height);
 
+/* ---- roll correction ------------------------------------------------------------
+ * Replaces vs::RollCorrection::autoCorrectRoll(input, params) (reference include/video/RollCorrection.h:16-51,
+ * src/RollCorrection.cpp:16-155), the stage that runs immediately before stabilize() in the reference's pipeline
+ * (examples/vsg.cpp:1272-1285): downscale -> gray -> Canny -> Hough lines -> mean angle in the filter band ->
+ * exponential smoothing with a per-frame clamp (decay when no line qualifies) -> rotate the full frame about its centre
+ * (INTER_LINEAR, BORDER_REPLICATE).  The reference keeps the smoothed angle in two process-global statics; here it is
+ * per handle and lives on the device.  Output size == input size.  Fields mirror RollCorrection::Parameters; YAML keys are
+ * those of the `roll_correction:` section (examples/vsg.cpp:988-1000). */
+typedef struct vs_roll_params {
+    double  scale_factor;            /* scaleFactor (0.25)          */
+    double  canny_threshold_low;     /* cannyThresholdLow (50)      */
+    double  canny_threshold_high;    /* cannyThresholdHigh (150)    */
+    int32_t canny_aperture;          /* cannyAperture (3); only 3   */
+    float   hough_rho;               /* houghRho (1)                */
+    float   hough_theta;             /* houghTheta (pi/180)         */
+    int32_t hough_threshold;         /* houghThreshold (100)        */
+    double  angle_filter_min;        /* angleFilterMin (-10)        */
+    double  angle_filter_max;        /* angleFilterMax (+10)        */
+    double  angle_smoothing_alpha;   /* angleSmoothingAlpha (0.1)   */
+    double  angle_decay;             /* angleDecay (0.995)          */
+    double  max_angle_change_deg;    /* maxAngleChangeDeg (0.5)     */
+} vs_roll_params;
+typedef struct vs_roll vs_roll;
+vs_status vs_roll_params_default(vs_roll_params* p);
+vs_status vs_roll_params_from_yaml(const char* path, vs_roll_params* p);
+vs_status vs_roll_params_from_yaml_string(const char* text, vs_roll_params* p);
+vs_status vs_roll_create(const vs_roll_params* params, int device, vs_roll** out);
+void      vs_roll_destroy(vs_roll* r);
+/* host frame in, host frame out (synchronous), like the reference's cv::Mat -> cv::Mat call */
+vs_status vs_roll_correct(vs_roll* r, const uint8_t* bgr, int width, int height, size_t stride, uint8_t* out, size_t out_stride);
+/* device frame in, device frame out, asynchronous on `stream` (a cudaStream_t; NULL = the default stream) */
+vs_status vs_roll_correct_device(vs_roll* r, const uint8_t* d_bgr, int width, int height, size_t stride, uint8_t* d_out,
+                                 size_t out_stride, void* stream);
+vs_status vs_roll_reset(vs_roll* r);                                   /* sFirstFrame = true */
+/* diagnostics (synchronise): smoothed angle in degrees, lines / edge pixels found on the last frame, kernels launched */
+vs_status vs_roll_state(vs_roll* r, double* smoothed_angle_deg, int* n_lines, int* n_edges, uint64_t* launches);
+/* analysis image of the last frame: size, gray and edge planes (small_w * small_h bytes each), lines as (rho, theta, votes) */
+vs_status vs_roll_debug(vs_roll* r, int* small_w, int* small_h, uint8_t* gray_out, uint8_t* edges_out, float* lines_out, int lines_capacity);
+
 /* ---- multi-stream batch: N independent streams advanced in lock-step, one kernel launch per
  * stage for the whole batch (BASELINE config 4).  Semantically N vs_stabilizers. -------------- */
 typedef struct vs_batch vs_batch;

@@ -10,6 +10,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvstab_b200.so")
 
 
+class VsRollParams(C.Structure):
+    """vs_roll_params (include/vstab_b200.h) == vs::RollCorrection::Parameters"""
+    _fields_ = [
+        ("scale_factor", C.c_double), ("canny_threshold_low", C.c_double), ("canny_threshold_high", C.c_double),
+        ("canny_aperture", C.c_int32), ("hough_rho", C.c_float), ("hough_theta", C.c_float), ("hough_threshold", C.c_int32),
+        ("angle_filter_min", C.c_double), ("angle_filter_max", C.c_double), ("angle_smoothing_alpha", C.c_double),
+        ("angle_decay", C.c_double), ("max_angle_change_deg", C.c_double),
+    ]
+
+
 class VsParams(C.Structure):
     _fields_ = [
         ("use_cuda", C.c_int32), ("logging", C.c_int32), ("smoothing_radius", C.c_int32), ("max_corners", C.c_int32),
@@ -86,6 +96,16 @@ SYMBOLS = {
     "vs_clip_render": (_I, [_P, _P, _I, _U8P, _I, _I, _I, _I, _U8P, _IP, _IP]),
     "vs_clip_analyze_device": (_I, [_P, _U8P, _I, _I, _I, _I, _P, _IP]),
     "vs_clip_render_device": (_I, [_P, _P, _I, _U8P, _I, _I, _I, _I, _U8P, _IP, _IP]),
+    "vs_roll_params_default": (_I, [C.POINTER(VsRollParams)]),
+    "vs_roll_params_from_yaml": (_I, [C.c_char_p, C.POINTER(VsRollParams)]),
+    "vs_roll_params_from_yaml_string": (_I, [C.c_char_p, C.POINTER(VsRollParams)]),
+    "vs_roll_create": (_I, [C.POINTER(VsRollParams), _I, C.POINTER(_P)]),
+    "vs_roll_destroy": (None, [_P]),
+    "vs_roll_correct": (_I, [_P, _U8P, _I, _I, _SZ, _U8P, _SZ]),
+    "vs_roll_correct_device": (_I, [_P, _U8P, _I, _I, _SZ, _U8P, _SZ, _P]),
+    "vs_roll_reset": (_I, [_P]),
+    "vs_roll_state": (_I, [_P, C.POINTER(C.c_double), _IP, _IP, C.POINTER(C.c_uint64)]),
+    "vs_roll_debug": (_I, [_P, _IP, _IP, _P, _P, _P, _I]),
     "vs_batch_create": (_I, [C.POINTER(VsParams), _I, _I, C.POINTER(_P)]),
     "vs_batch_destroy": (None, [_P]),
     "vs_batch_push_device": (_I, [_P, C.POINTER(_P), _I, _I, _SZ, C.POINTER(_P), _SZ, _SZ, C.c_uint, _IP, _IP, _IP]),

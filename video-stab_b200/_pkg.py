@@ -3,5 +3,6 @@ from ._capi import LIB_PATH, VsError, lib  # noqa: F401  (raises ImportError if 
 from .stabilizer import Parameters, Stabilizer, StabilizerBatch  # noqa: F401
 from . import kernels  # noqa: F401
 from . import offline  # noqa: F401
+from .roll import RollCorrection, RollParameters  # noqa: F401
 
-__all__ = ["lib", "LIB_PATH", "VsError", "Parameters", "Stabilizer", "StabilizerBatch", "kernels", "offline"]
+__all__ = ["lib", "LIB_PATH", "VsError", "Parameters", "Stabilizer", "StabilizerBatch", "kernels", "offline", "RollCorrection", "RollParameters"]

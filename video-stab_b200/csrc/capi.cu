@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "roll.h"
 
 struct vs_stabilizer { Engine* eng; };
 struct vs_batch { Engine* eng; };
@@ -400,6 +401,108 @@ vs_status vs_clip_render_device(vs_stabilizer* s, const float* d_all_transforms,
     API_BEGIN
     return s->eng->render_chunk(d_all_transforms, true, n_total, d_frames, width, height, first, count, d_out, out_width, out_height);
     API_END
+}
+
+// ------------------------------------------------------------------------------------ roll correction
+struct vs_roll { RollCorrector* rc; };
+
+vs_status vs_roll_params_default(vs_roll_params* p) {
+    if (!p) return vs_set_error(VS_ERR_INVALID_ARG, "null params");
+    // RollCorrection.h:16-38
+    p->scale_factor = 0.25; p->canny_threshold_low = 50.0; p->canny_threshold_high = 150.0; p->canny_aperture = 3;
+    p->hough_rho = 1.0f; p->hough_theta = (float)(3.1415926535897932384626433832795 / 180.0f); p->hough_threshold = 100;
+    p->angle_filter_min = -10.0; p->angle_filter_max = 10.0; p->angle_smoothing_alpha = 0.1; p->angle_decay = 0.995;
+    p->max_angle_change_deg = 0.5;
+    return VS_OK;
+}
+vs_status vs_roll_params_from_yaml_string(const char* text, vs_roll_params* p) {
+    if (!text || !p) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    std::istringstream in(text);
+    std::string line;
+    bool in_section = false;
+    while (std::getline(in, line)) {                         // the `roll_correction:` section, keys of examples/vsg.cpp:988-1000
+        size_t hash = line.find('#');
+        if (hash != std::string::npos) line = line.substr(0, hash);
+        if (trim(line).empty() || line[0] == '%' || trim(line) == "---") continue;
+        const bool indented = line[0] == ' ' || line[0] == '\t';
+        size_t colon = line.find(':');
+        if (colon == std::string::npos) continue;
+        std::string key = trim(line.substr(0, colon)), val = trim(line.substr(colon + 1));
+        if (!indented) { in_section = (key == "roll_correction"); continue; }
+        if (!in_section || val.empty()) continue;
+        const double v = atof(val.c_str());
+        if (key == "scale_factor") p->scale_factor = v;
+        else if (key == "canny_threshold_low") p->canny_threshold_low = v;
+        else if (key == "canny_threshold_high") p->canny_threshold_high = v;
+        else if (key == "canny_aperture") p->canny_aperture = (int)v;
+        else if (key == "hough_rho") p->hough_rho = (float)v;
+        else if (key == "hough_theta") p->hough_theta = (float)v;
+        else if (key == "hough_threshold") p->hough_threshold = (int)v;
+        else if (key == "angle_smoothing_alpha") p->angle_smoothing_alpha = v;
+        else if (key == "angle_decay") p->angle_decay = v;
+        else if (key == "angle_filter_min") p->angle_filter_min = v;
+        else if (key == "angle_filter_max") p->angle_filter_max = v;
+        else if (key == "max_angle_change_deg") p->max_angle_change_deg = v;   // not read by vsg.cpp; accepted
+    }
+    return VS_OK;
+    API_END
+}
+vs_status vs_roll_params_from_yaml(const char* path, vs_roll_params* p) {
+    if (!path || !p) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    std::ifstream f(path);
+    if (!f) return vs_set_error(VS_ERR_IO, "cannot open config file");
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return vs_roll_params_from_yaml_string(ss.str().c_str(), p);
+    API_END
+}
+vs_status vs_roll_create(const vs_roll_params* params, int device, vs_roll** out) {
+    if (!params || !out) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    RollCorrector* rc = nullptr;
+    vs_status st = RollCorrector::create(*params, device, &rc);
+    if (st != VS_OK) { *out = nullptr; return st; }
+    *out = new vs_roll{rc};
+    return VS_OK;
+    API_END
+}
+void vs_roll_destroy(vs_roll* r) {
+    if (!r) return;
+    delete r->rc;
+    delete r;
+}
+vs_status vs_roll_correct(vs_roll* r, const uint8_t* bgr, int width, int height, size_t stride, uint8_t* out, size_t out_stride) {
+    if (!r) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
+    API_BEGIN
+    return r->rc->correct_host(bgr, width, height, stride, out, out_stride);
+    API_END
+}
+vs_status vs_roll_correct_device(vs_roll* r, const uint8_t* d_bgr, int width, int height, size_t stride, uint8_t* d_out,
+                                 size_t out_stride, void* stream) {
+    if (!r) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
+    API_BEGIN
+    return r->rc->correct_device(d_bgr, width, height, stride, d_out, out_stride, (cudaStream_t)stream);
+    API_END
+}
+vs_status vs_roll_reset(vs_roll* r) { return r ? r->rc->reset() : vs_set_error(VS_ERR_INVALID_ARG, "null handle"); }
+vs_status vs_roll_state(vs_roll* r, double* smoothed_angle_deg, int* n_lines, int* n_edges, uint64_t* launches) {
+    if (!r) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
+    RollState s{};
+    vs_status st = r->rc->state(&s, n_edges);
+    if (st != VS_OK) return st;
+    if (smoothed_angle_deg) *smoothed_angle_deg = s.smoothed_angle;
+    if (n_lines) *n_lines = s.n_lines;
+    if (launches) *launches = r->rc->launches();
+    return VS_OK;
+}
+vs_status vs_roll_debug(vs_roll* r, int* small_w, int* small_h, uint8_t* gray_out, uint8_t* edges_out, float* lines_out, int lines_capacity) {
+    if (!r) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
+    if (small_w) *small_w = r->rc->small_w();
+    if (small_h) *small_h = r->rc->small_h();
+    if (!gray_out && !edges_out && !lines_out) return VS_OK;
+    return r->rc->debug(gray_out, edges_out, lines_out, lines_capacity);
 }
 
 // ------------------------------------------------------------------------------------ single kernels
