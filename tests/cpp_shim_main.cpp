@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "video/RollCorrection.h"
 #include "video/Stabilizer.h"
 
 static uint32_t crc32(const uint8_t* p, size_t n, uint32_t c) {
@@ -26,6 +27,7 @@ int main(int argc, char** argv) {
     const int w = std::atoi(argv[2]), h = std::atoi(argv[3]), n = std::atoi(argv[4]);
     vs::Stabilizer::Parameters params;
     params.smoothingRadius = argc > 5 ? std::atoi(argv[5]) : 5;
+    const bool roll = argc > 6 && !std::strcmp(argv[6], "roll");     // the reference's pipeline order: roll correction, then stabilize (vsg.cpp:1272-1285)
     try {
         vs::Stabilizer stab(params);
         FILE* f = std::fopen(argv[1], "rb");
@@ -33,6 +35,7 @@ int main(int argc, char** argv) {
         for (int i = 0; i < n; ++i) {
             cv::Mat frame(h, w, CV_8UC3);
             if (std::fread(frame.data, 1, (size_t)w * h * 3, f) != (size_t)w * h * 3) return 2;
+            if (roll) frame = vs::RollCorrection::autoCorrectRoll(frame);
             cv::Mat out = stab.stabilize(frame);
             if (!out.empty()) std::printf("%08x %d %d\n", mat_crc(out), out.cols, out.rows);
         }

@@ -19,9 +19,10 @@ public:
     uint8_t* data = nullptr;
     size_t step = 0;
     Mat() = default;
-    Mat(int r, int c, int /*type*/) : rows(r), cols(c), step((size_t)c * 3), buf_(std::make_shared<std::vector<uint8_t>>((size_t)r * c * 3)) {
+    Mat(int r, int c, int type) : rows(r), cols(c), step((size_t)c * 3), type_(type), buf_(std::make_shared<std::vector<uint8_t>>((size_t)r * c * 3)) {
         data = buf_->data();
     }
+    int type() const { return type_; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     Mat operator()(const Rect& r) const {
         Mat m = *this;
@@ -30,6 +31,7 @@ public:
         return m;
     }
 private:
+    int type_ = CV_8UC3;
     std::shared_ptr<std::vector<uint8_t>> buf_;
 };
 }  // namespace cv
