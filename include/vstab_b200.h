@@ -283,6 +283,29 @@ vs_status vs_roll_state(vs_roll* r, double* smoothed_angle_deg, int* n_lines, in
 /* analysis image of the last frame: size, gray and edge planes (small_w * small_h bytes each), lines as (rho, theta, votes) */
 vs_status vs_roll_debug(vs_roll* r, int* small_w, int* small_h, uint8_t* gray_out, uint8_t* edges_out, float* lines_out, int lines_capacity);
 
+/* ---- auto zoom-crop ------------------------------------------------------------
+ * Replaces vs::AutoZoomCrop::autoZoomCrop(corrected, marginPercent) (reference include/video/AutoZoomCrop.h:8-16,
+ * src/AutoZoomCrop.cpp:102-283): finds the largest axis-aligned rectangle of the frame's aspect ratio inside the non-black
+ * content (the black corners a rotation leaves), crops it and scales it to the reference's hard-coded 640 x 360
+ * (AutoZoomCrop.cpp:246-261; marginPercent is ignored there and here).  Device: gray, threshold, 5x5 elliptic close, crop +
+ * warpAffine scale.  Host (as in the reference, which downloads the mask and calls cv::findContours): border following of the
+ * content region and the greedy rectangle-shrinking loop.  Output is out_width x out_height (640 x 360, or the input size when
+ * the reference would hand the frame back unchanged). */
+vs_status vs_auto_zoom_crop(const uint8_t* bgr, int width, int height, size_t stride, double margin_percent, int device,
+                            uint8_t* out, size_t out_stride, size_t out_capacity, int* out_width, int* out_height);
+vs_status vs_auto_zoom_crop_device(const uint8_t* d_bgr, int width, int height, size_t stride, double margin_percent,
+                                   uint8_t* d_out, size_t out_stride, size_t out_capacity, int* out_width, int* out_height,
+                                   void* stream);
+/* the host half on its own: crop rectangle from a (closed) content mask in host memory.  found = 0: no contour (frame unchanged) */
+vs_status vs_auto_zoom_rect_from_mask(const uint8_t* mask, int width, int height, size_t stride, int* x, int* y, int* w, int* h,
+                                      int* found);
+/* cv::findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) of a host mask: points_xy (2 ints per point, contours back to back) and the
+ * length of every contour, in cv::findContours order (tests) */
+vs_status vs_k_find_external_contours(const uint8_t* mask, int width, int height, size_t stride, int* points_xy, int points_capacity,
+                                      int* lengths, int lengths_capacity, int* n_contours);
+/* the content mask of a device frame (gray > 1, then the 5x5 elliptic close), device -> device; `stream` as above */
+vs_status vs_k_content_mask(const uint8_t* d_bgr, int width, int height, size_t stride, uint8_t* d_mask, uint8_t* d_scratch, void* stream);
+
 /* ---- multi-stream batch: N independent streams advanced in lock-step, one kernel launch per
  * stage for the whole batch (BASELINE config 4).  Semantically N vs_stabilizers. -------------- */
 typedef struct vs_batch vs_batch;

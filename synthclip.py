@@ -142,3 +142,17 @@ def horizon_clip(width: int, height: int, n_frames: int, seed: int, roll_deg=Non
         M[1, 2] -= (big_h - height) / 2.0
         out[i] = cv2.warpAffine(scene, M, (width, height), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
     return out
+
+
+def black_corner_frame(width: int, height: int, seed: int, angle_deg: float, shift=(0.0, 0.0), hole: bool = False) -> np.ndarray:
+    """A frame as a roll correction / stabilizer with BORDER_CONSTANT leaves it: never-black content rotated about the centre and
+    shifted, black where nothing maps (input for AutoZoomCrop).  `hole` paints a black object inside the content."""
+    import cv2  # data tooling only
+    img = np.maximum(base_texture(width, height, seed)[MARGIN:-MARGIN, MARGIN:-MARGIN], 8)
+    M = cv2.getRotationMatrix2D((width / 2.0, height / 2.0), float(angle_deg), 1.0)
+    M[0, 2] += shift[0]
+    M[1, 2] += shift[1]
+    fr = cv2.warpAffine(img, M, (width, height), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+    if hole:
+        fr[height // 3: height // 3 + 40, width // 2: width // 2 + 60] = 0
+    return fr

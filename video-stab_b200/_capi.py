@@ -106,6 +106,11 @@ SYMBOLS = {
     "vs_roll_reset": (_I, [_P]),
     "vs_roll_state": (_I, [_P, C.POINTER(C.c_double), _IP, _IP, C.POINTER(C.c_uint64)]),
     "vs_roll_debug": (_I, [_P, _IP, _IP, _P, _P, _P, _I]),
+    "vs_auto_zoom_crop": (_I, [_U8P, _I, _I, _SZ, C.c_double, _I, _U8P, _SZ, _SZ, _IP, _IP]),
+    "vs_auto_zoom_crop_device": (_I, [_U8P, _I, _I, _SZ, C.c_double, _U8P, _SZ, _SZ, _IP, _IP, _P]),
+    "vs_auto_zoom_rect_from_mask": (_I, [_U8P, _I, _I, _SZ, _IP, _IP, _IP, _IP, _IP]),
+    "vs_k_find_external_contours": (_I, [_U8P, _I, _I, _SZ, _IP, _I, _IP, _I, _IP]),
+    "vs_k_content_mask": (_I, [_U8P, _I, _I, _SZ, _U8P, _U8P, _P]),
     "vs_batch_create": (_I, [C.POINTER(VsParams), _I, _I, C.POINTER(_P)]),
     "vs_batch_destroy": (None, [_P]),
     "vs_batch_push_device": (_I, [_P, C.POINTER(_P), _I, _I, _SZ, C.POINTER(_P), _SZ, _SZ, C.c_uint, _IP, _IP, _IP]),

@@ -4,5 +4,6 @@ from .stabilizer import Parameters, Stabilizer, StabilizerBatch  # noqa: F401
 from . import kernels  # noqa: F401
 from . import offline  # noqa: F401
 from .roll import RollCorrection, RollParameters  # noqa: F401
+from .autozoom import AutoZoomCrop  # noqa: F401
 
-__all__ = ["lib", "LIB_PATH", "VsError", "Parameters", "Stabilizer", "StabilizerBatch", "kernels", "offline", "RollCorrection", "RollParameters"]
+__all__ = ["lib", "LIB_PATH", "VsError", "Parameters", "Stabilizer", "StabilizerBatch", "kernels", "offline", "RollCorrection", "RollParameters", "AutoZoomCrop"]

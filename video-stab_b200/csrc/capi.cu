@@ -1,4 +1,5 @@
 // capi.cu — the extern "C" boundary declared in include/vstab_b200.h.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -8,6 +9,7 @@
 
 #include "engine.h"
 #include "roll.h"
+#include "autozoom_host.h"
 
 struct vs_stabilizer { Engine* eng; };
 struct vs_batch { Engine* eng; };
@@ -503,6 +505,82 @@ vs_status vs_roll_debug(vs_roll* r, int* small_w, int* small_h, uint8_t* gray_ou
     if (small_h) *small_h = r->rc->small_h();
     if (!gray_out && !edges_out && !lines_out) return VS_OK;
     return r->rc->debug(gray_out, edges_out, lines_out, lines_capacity);
+}
+
+// ------------------------------------------------------------------------------------ auto zoom-crop
+vs_status vs_auto_zoom_crop_device(const uint8_t* d_bgr, int width, int height, size_t stride, double /*margin_percent*/,
+                                   uint8_t* d_out, size_t out_stride, size_t out_capacity, int* out_width, int* out_height, void* stream) {
+    API_BEGIN
+    return auto_zoom_crop_device(d_bgr, width, height, stride, d_out, out_stride, out_capacity, out_width, out_height, (cudaStream_t)stream);
+    API_END
+}
+vs_status vs_auto_zoom_crop(const uint8_t* bgr, int width, int height, size_t stride, double /*margin_percent*/, int device,
+                            uint8_t* out, size_t out_stride, size_t out_capacity, int* out_width, int* out_height) {
+    if (!bgr || !out || !out_width || !out_height || width < 4 || height < 4) return vs_set_error(VS_ERR_INVALID_ARG, "auto zoom-crop: bad argument");
+    API_BEGIN
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return vs_set_error(VS_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return vs_set_error(VS_ERR_INVALID_ARG, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+    if (stride == 0) stride = (size_t)width * 3;
+    const size_t tight = (size_t)width * 3;
+    const size_t ocap = std::max(tight * height, (size_t)640 * 360 * 3);
+    uint8_t *d_in = nullptr, *d_o = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_in, tight * height));
+    cudaError_t e = cudaMalloc((void**)&d_o, ocap);
+    vs_status rc = VS_OK;
+    if (e == cudaSuccess) e = cudaMemcpy2D(d_in, tight, bgr, stride, tight, height, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = auto_zoom_crop_device(d_in, width, height, tight, d_o, 0, ocap, out_width, out_height, 0);
+        if (rc == VS_OK) {
+            const size_t ot = (size_t)*out_width * 3;
+            if (out_stride == 0) out_stride = ot;
+            if (out_stride < ot || out_stride * (size_t)(*out_height - 1) + ot > out_capacity)
+                rc = vs_set_error(VS_ERR_BUFFER_TOO_SMALL, "auto zoom-crop: output buffer too small");
+            else e = cudaMemcpy2D(out, out_stride, d_o, ot, ot, *out_height, cudaMemcpyDeviceToHost);
+        }
+    }
+    cudaFree(d_in);
+    if (d_o) cudaFree(d_o);
+    CUDA_TRY(e);
+    return rc;
+    API_END
+}
+vs_status vs_auto_zoom_rect_from_mask(const uint8_t* mask, int width, int height, size_t stride, int* x, int* y, int* w, int* h, int* found) {
+    if (!mask || !x || !y || !w || !h || !found || width < 1 || height < 1) return vs_set_error(VS_ERR_INVALID_ARG, "bad argument");
+    API_BEGIN
+    azc::Rect r;
+    *found = azc::crop_rect_from_mask(mask, width, height, stride ? stride : (size_t)width, &r) ? 1 : 0;
+    *x = r.x; *y = r.y; *w = r.width; *h = r.height;
+    return VS_OK;
+    API_END
+}
+vs_status vs_k_find_external_contours(const uint8_t* mask, int width, int height, size_t stride, int* points_xy, int points_capacity,
+                                      int* lengths, int lengths_capacity, int* n_contours) {
+    if (!mask || !points_xy || !lengths || !n_contours || width < 1 || height < 1) return vs_set_error(VS_ERR_INVALID_ARG, "bad argument");
+    API_BEGIN
+    std::vector<std::vector<azc::Pt>> cs;
+    std::vector<signed char> work;
+    azc::find_external_contours(mask, width, height, stride ? stride : (size_t)width, cs, work);
+    *n_contours = (int)cs.size();
+    if ((int)cs.size() > lengths_capacity) return vs_set_error(VS_ERR_BUFFER_TOO_SMALL, "too many contours");
+    int k = 0;
+    for (size_t i = 0; i < cs.size(); ++i) {
+        lengths[i] = (int)cs[i].size();
+        if (k + (int)cs[i].size() > points_capacity) return vs_set_error(VS_ERR_BUFFER_TOO_SMALL, "too many contour points");
+        for (auto& p : cs[i]) { points_xy[2 * k] = p.x; points_xy[2 * k + 1] = p.y; ++k; }
+    }
+    return VS_OK;
+    API_END
+}
+vs_status vs_k_content_mask(const uint8_t* d_bgr, int width, int height, size_t stride, uint8_t* d_mask, uint8_t* d_scratch, void* stream) {
+    if (!d_bgr || !d_mask || !d_scratch || width < 1 || height < 1) return vs_set_error(VS_ERR_INVALID_ARG, "bad argument");
+    launch_content_mask(d_bgr, width, height, stride ? stride : (size_t)width * 3, d_mask, d_scratch, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return VS_OK;
 }
 
 // ------------------------------------------------------------------------------------ single kernels

@@ -78,3 +78,8 @@ int launch_warp_frames_mode(const uint8_t* src, int sw, int sh, size_t sstride, 
 void launch_fade_blend(const PtrPack& frames, int n_lanes, int w, int h, size_t stride, int b, uint8_t* hist, uint8_t* blend,
                        float alpha, float beta, bool init, cudaStream_t st);
 void launch_fade_update(uint8_t* hist, const MutPtrPack& outs, size_t out_stride, int n_lanes, int w, int h, int b, cudaStream_t st);
+
+// vs::AutoZoomCrop (k_autozoom.cu): content mask on the device; the whole call on a device frame
+void launch_content_mask(const uint8_t* d_bgr, int w, int h, size_t stride, uint8_t* d_mask, uint8_t* d_scratch, cudaStream_t st);
+vs_status auto_zoom_crop_device(const uint8_t* d_bgr, int w, int h, size_t stride, uint8_t* d_out, size_t out_stride, size_t out_capacity,
+                                int* ow, int* oh, cudaStream_t st);
