@@ -10,7 +10,8 @@
 //     pixels marked 2, or -126 when the pixel to their right is background; a vertex is emitted whenever the step direction
 //     changes); contours are returned last-found first;
 //   * cv::drawContours(FILLED) of one external contour: its border pixels plus everything they enclose.  Computed as the
-//     complement of what a 4-connected flood from outside the image can reach without crossing the contour's border pixels.
+//     complement of what a 4-connected flood from outside the image can reach without crossing the contour's border pixels
+//     (in place, in the same padded image: the flood only ever touches the free corners).
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -67,27 +68,20 @@ static inline void fetch_contour(signed char* img, int step, int x, int y, std::
     }
 }
 
-// mask: h x w, nonzero = foreground.  Returns the external contours in cv::findContours order and leaves the marked image in `work`
-// ((h+2) x (w+2): 0 background, 1 untouched foreground, 2 / -126 traced border pixels).
-static inline void find_external_contours(const uint8_t* mask, int w, int h, size_t stride, std::vector<std::vector<Pt>>& contours,
-                                          std::vector<signed char>& work) {
+// work: (h+2) x (w+2) signed bytes, 0 / 1 with a zero frame.  Returns the external contours in cv::findContours order and leaves
+// the traced border pixels marked (2, or -126 where the pixel to the right is background).
+static inline void find_external_contours_padded(signed char* work, int w, int h, std::vector<std::vector<Pt>>& contours) {
     const int step = w + 2;
-    work.assign((size_t)step * (h + 2), 0);
-    for (int y = 0; y < h; ++y) {
-        const uint8_t* m = mask + (size_t)y * stride;
-        signed char* d = work.data() + (size_t)(y + 1) * step + 1;
-        for (int x = 0; x < w; ++x) d[x] = m[x] ? 1 : 0;
-    }
     std::vector<std::vector<Pt>> found;
     for (int y = 1; y <= h; ++y) {
-        signed char* row = work.data() + (size_t)y * step;
+        signed char* row = work + (size_t)y * step;
         int prev = 0, lnbd_x = 0;
         for (int x = 1; x <= w + 1; ++x) {
             const int p = row[x];
             if (p == prev) continue;
             if (prev == 0 && p == 1 && !(row[lnbd_x] > 0)) {      // start of an outer border that no traced border encloses
                 found.emplace_back();
-                fetch_contour(work.data(), step, x, y, found.back());
+                fetch_contour(work, step, x, y, found.back());
             }
             prev = row[x];                                        // (possibly just marked)
             if (prev & -2) lnbd_x = x;
@@ -95,16 +89,59 @@ static inline void find_external_contours(const uint8_t* mask, int w, int h, siz
     }
     contours.assign(found.rbegin(), found.rend());                // last found first
 }
+static inline void pad_mask(const uint8_t* mask, int w, int h, size_t stride, std::vector<signed char>& work) {
+    const int step = w + 2;
+    work.assign((size_t)step * (h + 2), 0);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* m = mask + (size_t)y * stride;
+        signed char* d = work.data() + (size_t)(y + 1) * step + 1;
+        for (int x = 0; x < w; ++x) d[x] = m[x] ? 1 : 0;
+    }
+}
+static inline void find_external_contours(const uint8_t* mask, int w, int h, size_t stride, std::vector<std::vector<Pt>>& contours,
+                                          std::vector<signed char>& work) {
+    pad_mask(mask, w, h, stride, work);
+    find_external_contours_padded(work.data(), w, h, contours);
+}
 
-// AutoZoomCrop.cpp:9-84
-static inline bool check_interior_exterior(const std::vector<uint8_t>& filled, int w, const Rect& bb, int& top, int& bottom, int& left, int& right) {
-    bool ok = true;
+// AutoZoomCrop.cpp:9-84.  `work` doubles as the filled contour mask: a pixel is OUTSIDE the drawn contour iff it is marked EXT.
+// The reference recounts the zeros on all four border lines of the rectangle in every iteration of its shrinking loop; the
+// rectangle only ever shrinks, so the same four counts are maintained incrementally here (a side is recounted when it moves, the
+// two perpendicular sides give up the pixels they lose) - identical counts, a fraction of the pixel visits.
+enum : signed char { AZ_BORDER = 3, AZ_EXT = 4 };
+struct BorderCounts {
+    const signed char* work;
+    int step;
+    bool have = false;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;                   // inclusive corners of the last rectangle (x1 = x0 + width - 1 ...)
     unsigned cTop = 0, cBottom = 0, cLeft = 0, cRight = 0;
-    auto at = [&](int y, int x) { return filled[(size_t)(bb.y + y) * w + bb.x + x]; };
-    for (int x = 0; x < bb.width; ++x) if (at(0, x) == 0) { ok = false; ++cTop; }
-    for (int x = 0; x < bb.width; ++x) if (at(bb.height - 1, x) == 0) { ok = false; ++cBottom; }
-    for (int y = 0; y < bb.height; ++y) if (at(y, 0) == 0) { ok = false; ++cLeft; }
-    for (int y = 0; y < bb.height; ++y) if (at(y, bb.width - 1) == 0) { ok = false; ++cRight; }
+    bool zero(int y, int x) const { return work[(size_t)(y + 1) * step + x + 1] == AZ_EXT; }
+    unsigned row(int y, int xa, int xb) const { unsigned c = 0; for (int x = xa; x <= xb; ++x) c += zero(y, x); return c; }
+    unsigned col(int x, int ya, int yb) const { unsigned c = 0; for (int y = ya; y <= yb; ++y) c += zero(y, x); return c; }
+    void update(const Rect& bb) {
+        const int nx0 = bb.x, ny0 = bb.y, nx1 = bb.x + bb.width - 1, ny1 = bb.y + bb.height - 1;
+        const bool shrink = have && nx0 >= x0 && ny0 >= y0 && nx1 <= x1 && ny1 <= y1 && nx0 <= nx1 && ny0 <= ny1;
+        if (!shrink) {
+            cTop = row(ny0, nx0, nx1); cBottom = row(ny1, nx0, nx1); cLeft = col(nx0, ny0, ny1); cRight = col(nx1, ny0, ny1);
+        } else {
+            if (ny0 != y0) cTop = row(ny0, nx0, nx1); else cTop -= row(y0, x0, nx0 - 1) + row(y0, nx1 + 1, x1);
+            if (ny1 != y1) cBottom = row(ny1, nx0, nx1); else cBottom -= row(y1, x0, nx0 - 1) + row(y1, nx1 + 1, x1);
+            if (nx0 != x0) cLeft = col(nx0, ny0, ny1); else cLeft -= col(x0, y0, ny0 - 1) + col(x0, ny1 + 1, y1);
+            if (nx1 != x1) cRight = col(nx1, ny0, ny1); else cRight -= col(x1, y0, ny0 - 1) + col(x1, ny1 + 1, y1);
+        }
+        have = true; x0 = nx0; y0 = ny0; x1 = nx1; y1 = ny1;
+    }
+};
+static inline bool check_interior_exterior(BorderCounts& bc, const Rect& bb, int& top, int& bottom, int& left, int& right) {
+    if (bb.width <= 0 || bb.height <= 0) {
+        // degenerate rectangle: the reference's four loops read (at most) one line of an empty ROI; count it the plain way
+        bc.have = false;
+        bc.cTop = bc.cBottom = bc.cLeft = bc.cRight = 0;
+        for (int x = 0; x < bb.width; ++x) { bc.cTop += bc.zero(bb.y, bb.x + x); bc.cBottom += bc.zero(bb.y + bb.height - 1, bb.x + x); }
+        for (int y = 0; y < bb.height; ++y) { bc.cLeft += bc.zero(bb.y + y, bb.x); bc.cRight += bc.zero(bb.y + y, bb.x + bb.width - 1); }
+    } else bc.update(bb);
+    const unsigned cTop = bc.cTop, cBottom = bc.cBottom, cLeft = bc.cLeft, cRight = bc.cRight;
+    const bool ok = !(cTop | cBottom | cLeft | cRight);
     if (cTop > cBottom) {
         if (cTop > cLeft && cTop > cRight) top = 1;
     } else if (cBottom > cLeft && cBottom > cRight) bottom = 1;
@@ -114,52 +151,45 @@ static inline bool check_interior_exterior(const std::vector<uint8_t>& filled, i
     return ok;
 }
 
-// The crop rectangle of AutoZoomCrop.cpp:141-223 from the (closed) content mask.  Returns false when there is no contour (the
-// reference then returns the frame unchanged).  An empty rectangle (width or height <= 0) also means "return the frame".
-static inline bool crop_rect_from_mask(const uint8_t* mask, int w, int h, size_t stride, Rect* out) {
+// The crop rectangle of AutoZoomCrop.cpp:141-223 from the padded 0/1 content image (modified in place).  Returns false when
+// there is no contour (the reference then returns the frame unchanged).  An empty rectangle also means "return the frame".
+static inline bool crop_rect_from_padded(signed char* work, int w, int h, Rect* out) {
     std::vector<std::vector<Pt>> contours;
-    std::vector<signed char> work;
-    find_external_contours(mask, w, h, stride, contours, work);
+    find_external_contours_padded(work, w, h, contours);
     if (contours.empty()) return false;
     size_t id = 0, max_size = 0;
     for (size_t i = 0; i < contours.size(); ++i)
         if (contours[i].size() > max_size) { max_size = contours[i].size(); id = i; }
     const std::vector<Pt>& c = contours[id];
-    // ---- cv::drawContours(contourMask, contours, id, 255, FILLED): border + enclosed pixels.  Re-trace only this contour on a
-    //      clean copy so that `border` holds exactly its border pixels, then flood the outside.
     const int step = w + 2;
-    std::vector<uint8_t> border((size_t)step * (h + 2), 0);
-    {
-        // walk the polygon: consecutive vertices are joined by horizontal, vertical or 45-degree runs of border pixels
-        for (size_t i = 0; i < c.size(); ++i) {
-            Pt a = c[i], b = c[(i + 1) % c.size()];
-            const int sx = (b.x > a.x) - (b.x < a.x), sy = (b.y > a.y) - (b.y < a.y);
-            int x = a.x, y = a.y;
-            for (;;) {
-                border[(size_t)(y + 1) * step + x + 1] = 1;
-                if (x == b.x && y == b.y) break;
-                x += sx; y += sy;
-            }
+    // ---- cv::drawContours(contourMask, contours, id, 255, FILLED) = this contour's border pixels plus everything they enclose.
+    //      Its border: consecutive vertices are joined by horizontal, vertical or 45-degree runs of border pixels.
+    for (size_t i = 0; i < c.size(); ++i) {
+        const Pt a = c[i], b = c[(i + 1) % c.size()];
+        const int sx = (b.x > a.x) - (b.x < a.x), sy = (b.y > a.y) - (b.y < a.y);
+        int x = a.x, y = a.y;
+        for (;;) {
+            work[(size_t)(y + 1) * step + x + 1] = AZ_BORDER;
+            if (x == b.x && y == b.y) break;
+            x += sx; y += sy;
         }
     }
-    std::vector<uint8_t> filled((size_t)w * h, 255);
+    //      Everything else: a 4-connected flood from the frame that never enters a border pixel marks the OUTSIDE (it only
+    //      ever visits the corners the content leaves free, other components included: they are not part of the drawn contour).
     {
-        // 4-connected flood of everything reachable from the frame without entering a border pixel
-        std::vector<uint8_t> seen((size_t)step * (h + 2), 0);
         std::vector<int> stack;
         stack.push_back(0);
-        seen[0] = 1;
+        work[0] = AZ_EXT;
         while (!stack.empty()) {
             const int p = stack.back();
             stack.pop_back();
             const int y = p / step, x = p - y * step;
-            if (x >= 1 && x <= w && y >= 1 && y <= h) filled[(size_t)(y - 1) * w + (x - 1)] = 0;
             const int nx[4] = {x + 1, x - 1, x, x}, ny[4] = {y, y, y + 1, y - 1};
             for (int k = 0; k < 4; ++k) {
                 if (nx[k] < 0 || nx[k] > w + 1 || ny[k] < 0 || ny[k] > h + 1) continue;
                 const int q = ny[k] * step + nx[k];
-                if (seen[q] || border[q]) continue;
-                seen[q] = 1;
+                if (work[q] == AZ_BORDER || work[q] == AZ_EXT) continue;
+                work[q] = AZ_EXT;
                 stack.push_back(q);
             }
         }
@@ -171,11 +201,11 @@ static inline bool crop_rect_from_mask(const uint8_t* mask, int w, int h, size_t
     std::sort(ys.begin(), ys.end());
     unsigned minX = 0, maxX = (unsigned)(xs.size() - 1), minY = 0, maxY = (unsigned)(ys.size() - 1);
     Rect bb;
+    BorderCounts bc{work, step};
     while (minX < maxX && minY < maxY) {
         bb.x = xs[minX]; bb.y = ys[minY]; bb.width = xs[maxX] - xs[minX]; bb.height = ys[maxY] - ys[minY];
         int t = 0, b = 0, l = 0, r = 0;
-        // cv::Mat::operator()(Rect) of an empty ROI is still valid; a zero-sized one makes the loops of the check empty
-        if (check_interior_exterior(filled, w, bb, t, b, l, r)) break;
+        if (check_interior_exterior(bc, bb, t, b, l, r)) break;
         if (l) ++minX;
         if (r) --maxX;
         if (t) ++minY;
@@ -189,12 +219,16 @@ static inline bool crop_rect_from_mask(const uint8_t* mask, int w, int h, size_t
     bb.x = cx - new_w / 2;
     if (bb.x < 0) bb.x = 0;
     if (bb.x + bb.width > w) bb.x = w - bb.width;
-    // interiorBB &= Rect(0, 0, cols, rows)
     const int x1 = std::max(bb.x, 0), y1 = std::max(bb.y, 0), x2 = std::min(bb.x + bb.width, w), y2 = std::min(bb.y + bb.height, h);
     Rect v;
     if (x2 > x1 && y2 > y1) { v.x = x1; v.y = y1; v.width = x2 - x1; v.height = y2 - y1; }
     *out = v;
     return true;
+}
+static inline bool crop_rect_from_mask(const uint8_t* mask, int w, int h, size_t stride, Rect* out) {
+    std::vector<signed char> work;
+    pad_mask(mask, w, h, stride, work);
+    return crop_rect_from_padded(work.data(), w, h, out);
 }
 
 }  // namespace azc

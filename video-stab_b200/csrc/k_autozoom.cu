@@ -39,6 +39,14 @@ __global__ void __launch_bounds__(256) k_az_morph(const uint8_t* __restrict__ in
     out[(size_t)y * w + x] = r ? 255 : 0;
 }
 
+// mask (0 / 255, w x h) -> the padded 0 / 1 image ((h + 2) x (w + 2), zero frame) the border follower works on
+__global__ void __launch_bounds__(256) k_az_pad01(const uint8_t* __restrict__ mask, int w, int h, signed char* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w + 2) return;
+    const bool in = x >= 1 && x <= w && y >= 1 && y <= h;
+    out[(size_t)y * (w + 2) + x] = (in && mask[(size_t)(y - 1) * w + (x - 1)]) ? 1 : 0;
+}
+
 void launch_content_mask(const uint8_t* d_bgr, int w, int h, size_t stride, uint8_t* d_mask, uint8_t* d_scratch, cudaStream_t st) {
     const dim3 g((w + 255) / 256, h);
     k_az_threshold<<<g, 256, 0, st>>>(d_bgr, w, h, stride, d_mask);
@@ -54,19 +62,29 @@ vs_status auto_zoom_crop_device(const uint8_t* d_bgr, int w, int h, size_t strid
     if (stride == 0) stride = (size_t)w * 3;
     uint8_t *d_mask = nullptr, *d_scratch = nullptr;
     WarpParams* d_wp = nullptr;
-    std::vector<uint8_t> mask((size_t)w * h);
+    const size_t padded = (size_t)(w + 2) * (h + 2);
+    // page-locked landing buffer for the padded 0/1 image, kept per host thread
+    static thread_local signed char* h_work = nullptr;
+    static thread_local size_t h_work_cap = 0;
+    if (padded > h_work_cap) {
+        if (h_work) cudaFreeHost(h_work);
+        h_work = nullptr; h_work_cap = 0;
+        if (cudaMallocHost((void**)&h_work, padded) != cudaSuccess) return vs_set_cuda_error(cudaGetLastError(), "cudaMallocHost", __FILE__, __LINE__);
+        h_work_cap = padded;
+    }
     cudaError_t e = cudaMallocAsync((void**)&d_mask, (size_t)w * h, st);
-    if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_scratch, (size_t)w * h, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_scratch, padded > (size_t)w * h ? padded : (size_t)w * h, st);
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_wp, sizeof(WarpParams), st);
     vs_status rc = VS_OK;
     if (e == cudaSuccess) {
         launch_content_mask(d_bgr, w, h, stride, d_mask, d_scratch, st);
-        e = cudaMemcpyAsync(mask.data(), d_mask, (size_t)w * h, cudaMemcpyDeviceToHost, st);
+        k_az_pad01<<<dim3((w + 2 + 255) / 256, h + 2), 256, 0, st>>>(d_mask, w, h, reinterpret_cast<signed char*>(d_scratch));
+        e = cudaMemcpyAsync(h_work, d_scratch, padded, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
     if (e == cudaSuccess) {
         azc::Rect r;
-        const bool found = azc::crop_rect_from_mask(mask.data(), w, h, (size_t)w, &r);
+        const bool found = azc::crop_rect_from_padded(h_work, w, h, &r);
         // no contour, or an empty crop: the reference returns the frame itself (AutoZoomCrop.cpp:149-152, 233-245)
         const bool unchanged = !found || r.width <= 0 || r.height <= 0;
         const int dw = unchanged ? w : AZ_OUT_W, dh = unchanged ? h : AZ_OUT_H;
