@@ -645,6 +645,67 @@ def run_gpu(args, rank, world, local_rank):
         del sbp, clip_d, out_d, clip_r
         torch.cuda.empty_cache()
 
+    # ============================================================ config 3: one 4K stream, RollCorrection -> Stabilizer (crop-n-zoom) -> AutoZoomCrop
+    c3 = None
+    if "config3" in parts and world == 1:
+        W3, H3, n3, ring3 = 3840, 2160, 24, 24
+        fb3 = H3 * W3 * 3
+        clip3 = torch.from_numpy(synthclip.horizon_clip(W3, H3, n3, 3000)).to(dev)
+        loop3 = _pingpong(n3)
+        rolled = torch.empty((ring3, H3, W3, 3), dtype=torch.uint8, device=dev)
+        out3 = torch.empty((ring3, H3, W3, 3), dtype=torch.uint8, device=dev)
+        zoomed = torch.empty((360, 640, 3), dtype=torch.uint8, device=dev)
+        rp = vsb.RollParameters(angleFilterMin=-70.0, angleFilterMax=70.0, angleDecay=0.98)       # examples/config.yaml roll_correction:
+        sp3 = vsb.Parameters(smoothingRadius=SMOOTHING_RADIUS, cropNZoom=True, borderSize=30)
+        s_roll = torch.cuda.Stream(dev)
+
+        def run3(frames, with_roll, with_stab, with_zoom):
+            roll = vsb.RollCorrection(rp, device=local_rank)
+            st3 = vsb.Stabilizer(sp3, device=local_rank)
+            ext3 = torch.cuda.ExternalStream(st3.stream, device=dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            produced = 0
+            for k in range(frames):
+                src = clip3[loop3[k % len(loop3)]]
+                cur_in = src
+                if with_roll:
+                    dst = rolled[k % ring3]
+                    roll.correct_device(src.data_ptr(), W3, H3, W3 * 3, dst.data_ptr(), W3 * 3, s_roll.cuda_stream)
+                    cur_in = dst
+                if with_stab:
+                    if with_roll:
+                        ev = torch.cuda.Event()
+                        ev.record(s_roll)
+                        st3.wait_event(ev.cuda_event)
+                    got = st3.push_device(cur_in.data_ptr(), W3, H3, W3 * 3, out3[k % ring3].data_ptr(), W3 * 3, fb3, borrow=True)
+                    if got is not None:
+                        produced += 1
+                        if with_zoom:
+                            st3.join()
+                            ev2 = torch.cuda.Event()
+                            ev2.record(ext3)
+                            s_roll.wait_event(ev2)
+                            vsb.AutoZoomCrop.crop_device(out3[k % ring3].data_ptr(), W3, H3, W3 * 3, zoomed.data_ptr(), 640 * 3, 640 * 360 * 3, s_roll.cuda_stream)
+                elif with_zoom:
+                    vsb.AutoZoomCrop.crop_device(cur_in.data_ptr(), W3, H3, W3 * 3, zoomed.data_ptr(), 640 * 3, 640 * 360 * 3, s_roll.cuda_stream)
+            st3.sync()
+            torch.cuda.synchronize()
+            return frames / (time.perf_counter() - t0)
+        run3(24, True, True, True)                         # warm-up (allocations, first-use set-up)
+        nfr = 96
+        c3 = {"workload": "3840x2160 single stream (BASELINE configs[2]): RollCorrection (roll_correction: of examples/config.yaml) -> Stabilizer "
+                          "(radius 15, crop_n_zoom, border 30) -> AutoZoomCrop (640x360 out, as the reference hard-codes); device frames",
+              "frames": nfr, "unit": UNIT,
+              "stabilizer_only": run3(nfr, False, True, False),
+              "roll_only": run3(nfr, True, False, False),
+              "roll_then_stabilizer": run3(nfr, True, True, False),
+              "roll_stabilizer_autozoom": run3(nfr, True, True, True),
+              "autozoom_only": run3(nfr, False, False, True),
+              "note": "AutoZoomCrop makes one device->host trip per frame for the contour / rectangle logic, like the reference (AutoZoomCrop.cpp:141-147)"}
+        del clip3, rolled, out3, zoomed
+        torch.cuda.empty_cache()
+
     # ============================================================ config 5: one long clip, temporal chunks + all-gather
     c5 = None
     if "config5" in parts:
@@ -734,7 +795,7 @@ def run_gpu(args, rank, world, local_rank):
             "notes": {"api": (c2 or {}).get("api") if world == 1 else "vs_batch_push_device (borrowed device frames, one call per lock-step frame)",
                       "l2_policy": head.get("l2_policy"), "host_cpu_binding": numa},
             "e2e": e2e, "gpu_launches": int(head.get("launches", 0)), "clocks": clocks,
-            "roofline": roof, "roofline_pyramid": roof_pyr, "config4": c4, "config5": c5,
+            "roofline": roof, "roofline_pyramid": roof_pyr, "config3": c3, "config4": c4, "config5": c5,
         }
         if c2 is not None:
             line["stage_us_per_launch_group"] = c2["stage_us_per_launch_group"]
@@ -761,8 +822,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parts", default="config2,config4,e2e,roofline,config5",
-                    help="comma list of config2, config4, e2e, roofline, config5 (profiling runs select one)")
+    ap.add_argument("--parts", default="config2,config4,e2e,roofline,config3,config5",
+                    help="comma list of config2, config4, e2e, roofline, config3, config5 (profiling runs select one)")
     ap.add_argument("--clip-frames", type=int, default=C5_FRAMES)
     ap.add_argument("--config2-at-all-n", action="store_true")
     args = ap.parse_args()
