@@ -600,20 +600,26 @@ vs_status vs_k_warp_affine_bgr8(const uint8_t* d_src, int src_w, int src_h, size
     if (!d_src || !d_dst || !T_host || n_frames < 1) return vs_set_error(VS_ERR_INVALID_ARG, "bad argument");
     API_BEGIN
     cudaStream_t st = (cudaStream_t)stream;
-    // The set-up block lives exactly as long as this call's work on `st`: stream-ordered allocation on the caller's stream and
-    // current device (calls on different streams or devices never share it; nothing is kept between calls).
-    WarpParams* d_wp = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&d_wp, sizeof(WarpParams) * n_frames, st));
+    // One set-up block per (host thread, device, stream): calls on the same stream are ordered by the stream itself (the copy
+    // below queues behind the previous launch), calls on different streams or devices never share a block.
+    struct WpBlock { int dev; cudaStream_t st; WarpParams* p; int cap; };
+    static thread_local std::vector<WpBlock> blocks;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    WpBlock* blk = nullptr;
+    for (auto& b : blocks) if (b.dev == dev && b.st == st) blk = &b;
+    if (!blk) { blocks.push_back({dev, st, nullptr, 0}); blk = &blocks.back(); }
+    if (n_frames > blk->cap) {
+        if (blk->p) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(blk->p); blk->p = nullptr; blk->cap = 0; }
+        CUDA_TRY(cudaMalloc((void**)&blk->p, sizeof(WarpParams) * n_frames));
+        blk->cap = n_frames;
+    }
     std::vector<WarpParams> h(n_frames);
     for (int i = 0; i < n_frames; ++i) warp_params_from_T(T_host + 6 * i, &h[i]);
-    cudaError_t ce = cudaMemcpyAsync(d_wp, h.data(), sizeof(WarpParams) * n_frames, cudaMemcpyHostToDevice, st);   // pageable source: staged before return
-    if (ce == cudaSuccess) {
-        launch_warp_matrices(d_src, src_w, src_h, src_stride, src_frame_bytes, d_dst, dst_w, dst_h, dst_stride,
-                             dst_frame_bytes, d_wp, n_frames, st);
-        ce = cudaGetLastError();
-    }
-    cudaFreeAsync(d_wp, st);
-    CUDA_TRY(ce);
+    CUDA_TRY(cudaMemcpyAsync(blk->p, h.data(), sizeof(WarpParams) * n_frames, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    launch_warp_matrices(d_src, src_w, src_h, src_stride, src_frame_bytes, d_dst, dst_w, dst_h, dst_stride,
+                         dst_frame_bytes, blk->p, n_frames, st);
+    CUDA_TRY(cudaGetLastError());
     return VS_OK;
     API_END
 }

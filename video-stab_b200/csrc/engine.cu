@@ -694,13 +694,17 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
     if (pipe) {
         CUDA_TRY(cudaEventRecord(evOutReady_[oslot], stream_));
         CUDA_TRY(cudaStreamWaitEvent(sO_, evOutReady_[oslot], 0));
-        for (int l = 0; l < n_lanes_; ++l)
-            CUDA_TRY(cudaMemcpy2DAsync(outs[l], out_stride, dst.p[l], dstride, tight, h, cudaMemcpyDeviceToHost, sO_));
+        for (int l = 0; l < n_lanes_; ++l) {
+            if (out_stride == tight && dstride == tight) CUDA_TRY(cudaMemcpyAsync(outs[l], dst.p[l], tight * (size_t)h, cudaMemcpyDeviceToHost, sO_));
+            else CUDA_TRY(cudaMemcpy2DAsync(outs[l], out_stride, dst.p[l], dstride, tight, h, cudaMemcpyDeviceToHost, sO_));
+        }
         CUDA_TRY(cudaEventRecord(evOutFree_[oslot], sO_));
         out_free_set_[oslot] = true;
     } else if (host_io) {
-        for (int l = 0; l < n_lanes_; ++l)
-            CUDA_TRY(cudaMemcpy2DAsync(outs[l], out_stride, dst.p[l], dstride, tight, h, cudaMemcpyDeviceToHost, stream_));
+        for (int l = 0; l < n_lanes_; ++l) {
+            if (out_stride == tight && dstride == tight) CUDA_TRY(cudaMemcpyAsync(outs[l], dst.p[l], tight * (size_t)h, cudaMemcpyDeviceToHost, stream_));
+            else CUDA_TRY(cudaMemcpy2DAsync(outs[l], out_stride, dst.p[l], dstride, tight, h, cudaMemcpyDeviceToHost, stream_));
+        }
         CUDA_TRY(cudaStreamSynchronize(stream_));
     }
     ++n_out_;
@@ -745,8 +749,9 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
         if (multi_ && ring_ev_set_[e.slot]) CUDA_TRY(cudaStreamWaitEvent(cs, evRing_[e.slot], 0));
         for (int l = 0; l < n_lanes_; ++l) {
             uint8_t* dst = d_ring_ + ((size_t)l * ring_slots_ + e.slot) * frame_bytes_;
-            CUDA_TRY(cudaMemcpy2DAsync(dst, tight, frames[l], stride, tight, h,
-                                       host_io ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cs));
+            const cudaMemcpyKind kind = host_io ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+            if (stride == tight) CUDA_TRY(cudaMemcpyAsync(dst, frames[l], frame_bytes_, kind, cs));      // one flat transfer, not 1080 rows
+            else CUDA_TRY(cudaMemcpy2DAsync(dst, tight, frames[l], stride, tight, h, kind, cs));
             e.frames[l] = dst;
         }
         e.stride = tight;
