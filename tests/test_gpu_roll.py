@@ -61,7 +61,7 @@ def test_roll_correction_vs_reference(vsb, name):
         exact += int(d.max() == 0)
     assert exact >= n - 1, f"only {exact}/{n} rotated frames are bit-exact"
     st = rc.state()
-    assert st["launches"] == 7 * n
+    assert st["launches"] == 9 * n
 
 
 def test_roll_no_lines_decays_and_first_frame_resets(vsb):

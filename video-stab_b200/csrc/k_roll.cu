@@ -108,46 +108,64 @@ __global__ void __launch_bounds__(CN_TX * CN_TY) k_roll_canny_nms(const uint8_t*
 // compare-and-swap (each pixel is claimed exactly once, so the final map does not depend on the order).  Threads that find the
 // queue momentarily empty wait only for items produced by threads that are running; the kernel ends when every produced item is
 // complete.
+// head, reservation cursor and seed count all start at the number of strong pixels the NMS kernel queued
+__global__ void k_roll_seed_counters(int* __restrict__ counters) {
+    if (threadIdx.x == 0) { const int n0 = counters[0]; counters[1] = n0; counters[3] = n0; counters[6] = n0; }
+}
 #define HY_STACK 24
+// counters: [0] tail (items published), [1] head (next spilled item to claim), [2] items completed, [3] slot reservation cursor,
+//           [6] number of strong seeds.  [1], [3], [6] start at the seed count (copied on the stream after the NMS kernel).
+static __device__ __forceinline__ void hyst_walk(unsigned int* __restrict__ map, int w, int h, int* __restrict__ queue, int* __restrict__ counters, int seed) {
+    int stack[HY_STACK];
+    int sp = 0;
+    stack[sp++] = seed;
+    while (sp) {
+        const int q = stack[--sp];
+        const int y = q / w, x = q - y * w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int dx = (k == 0 || k == 3 || k == 5) ? -1 : (k == 1 || k == 6) ? 0 : 1;
+            const int dy = k < 3 ? -1 : (k < 5 ? 0 : 1);
+            const int nx = x + dx, ny = y + dy;
+            if ((unsigned)nx >= (unsigned)w || (unsigned)ny >= (unsigned)h) continue;
+            const int n = ny * w + nx;
+            if (map[n] == 0u && atomicCAS(&map[n], 0u, 2u) == 0u) {
+                if (sp < HY_STACK) stack[sp++] = n;
+                else {
+                    const int t = atomicAdd(&counters[3], 1);                  // reserve a slot, fill it, then extend the tail in order
+                    ((volatile int*)queue)[t] = n;
+                    __threadfence();
+                    while (atomicCAS(&counters[0], t, t + 1) != t) {}
+                }
+            }
+        }
+    }
+}
 __global__ void __launch_bounds__(128) k_roll_hysteresis(unsigned int* __restrict__ map, int w, int h, int* __restrict__ queue,
                                                           int* __restrict__ counters, int capacity) {
     volatile int* vc = counters;
+    // phase 1: the strong seeds, statically shared out
+    const int n0 = counters[6];
+    int mine = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += gridDim.x * blockDim.x) {
+        hyst_walk(map, w, h, queue, counters, queue[i]);
+        ++mine;
+    }
+    if (mine) { __threadfence(); atomicAdd(&counters[2], mine); }
+    // phase 2: items spilled by walks whose stack overflowed (rare), claimed dynamically until every published item is complete
     while (true) {
         const int idx = atomicAdd(&counters[1], 1);
         if (idx >= capacity) return;
-        while (true) {                                            // wait until item idx exists, or until none ever will
+        while (true) {
             const int done = vc[2];
             __threadfence();
             const int tail = vc[0];
             if (idx < tail) break;
             if (done == tail) return;
-            __nanosleep(200);
+            __nanosleep(500);
         }
         __threadfence();
-        int stack[HY_STACK];
-        int sp = 0;
-        stack[sp++] = ((volatile int*)queue)[idx];
-        while (sp) {
-            const int q = stack[--sp];
-            const int y = q / w, x = q - y * w;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int dx = (k == 0 || k == 3 || k == 5) ? -1 : (k == 1 || k == 6) ? 0 : 1;
-                const int dy = k < 3 ? -1 : (k < 5 ? 0 : 1);
-                const int nx = x + dx, ny = y + dy;
-                if ((unsigned)nx >= (unsigned)w || (unsigned)ny >= (unsigned)h) continue;
-                const int n = ny * w + nx;
-                if (map[n] == 0u && atomicCAS(&map[n], 0u, 2u) == 0u) {
-                    if (sp < HY_STACK) stack[sp++] = n;
-                    else {
-                        const int t = atomicAdd(&counters[3], 1);                  // reserve a slot, publish it, then extend the tail in order
-                        ((volatile int*)queue)[t] = n;
-                        __threadfence();
-                        while (atomicCAS(&counters[0], t, t + 1) != t) {}
-                    }
-                }
-            }
-        }
+        hyst_walk(map, w, h, queue, counters, ((volatile int*)queue)[idx]);
         __threadfence();
         atomicAdd(&counters[2], 1);
     }
@@ -194,25 +212,32 @@ __global__ void __launch_bounds__(256) k_roll_hough(const unsigned int* __restri
 }
 
 // ---------------------------------------------------------------------------------------------- 6. lines, angle, rotation set-up
-// Local maxima of the accumulator -> lines ordered like cv::HoughLines -> the reference's angle statistics and exponential
-// smoothing (RollCorrection.cpp:92-140, double arithmetic in source order) -> rotation matrix, its inverse, float coefficients.
-__global__ void __launch_bounds__(1024) k_roll_lines(const int* __restrict__ accum, int numangle, int numrho, int threshold, float rho,
+// 6a. local maxima of the accumulator above the threshold, one CTA per angle (rows n - 1 and n + 1 come from L2): keys
+//     (votes << 32) | ~accumulator-index, so that one descending sort gives cv::HoughLines' order (votes desc, index asc)
+__global__ void __launch_bounds__(256) k_roll_maxima(const int* __restrict__ accum, int numrho, int threshold,
+                                                     unsigned long long* __restrict__ cand, int* __restrict__ counters) {
+    const int n = blockIdx.x, pitch = numrho + 2;
+    const int* row = accum + (size_t)(n + 1) * pitch;
+    for (int r = threadIdx.x; r < numrho; r += blockDim.x) {
+        const int v = row[r + 1];
+        if (v > threshold && v > row[r] && v >= row[r + 2] && v > row[r + 1 - pitch] && v >= row[r + 1 + pitch]) {
+            const int k = atomicAdd(&counters[5], 1);
+            const unsigned base = (unsigned)((n + 1) * pitch + r + 1);
+            if (k < RL_MAX_LINES) cand[k] = ((unsigned long long)(unsigned)v << 32) | (unsigned)(0xFFFFFFFFu - base);
+        }
+    }
+}
+
+// 6b. lines ordered like cv::HoughLines -> the reference's angle statistics and exponential smoothing (RollCorrection.cpp:92-140,
+//     double arithmetic in source order) -> rotation matrix, its inverse, float coefficients.  One CTA.
+__global__ void __launch_bounds__(1024) k_roll_lines(const unsigned long long* __restrict__ cand, const int* __restrict__ counters,
+                                                     int numangle, int numrho, int threshold, float rho,
                                                      float theta, RollParamsDev prm, int w, int h, RollState* __restrict__ st,
                                                      float* __restrict__ lines_out) {
     __shared__ unsigned long long keys[RL_MAX_LINES];
-    __shared__ int n_found;
-    if (threadIdx.x == 0) n_found = 0;
-    __syncthreads();
     const int pitch = numrho + 2;
-    for (int i = threadIdx.x; i < numangle * numrho; i += blockDim.x) {
-        const int n = i / numrho, r = i - n * numrho;
-        const int base = (n + 1) * pitch + r + 1;
-        const int v = accum[base];
-        if (v > threshold && v > accum[base - 1] && v >= accum[base + 1] && v > accum[base - pitch] && v >= accum[base + pitch]) {
-            const int k = atomicAdd(&n_found, 1);
-            if (k < RL_MAX_LINES) keys[k] = ((unsigned long long)(unsigned)v << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)base);
-        }
-    }
+    const int n_found = counters[5];
+    for (int i = threadIdx.x; i < min(n_found, RL_MAX_LINES); i += blockDim.x) keys[i] = cand[i];
     __syncthreads();
     const int found = n_found;
     const int nl = min(found, RL_MAX_LINES);
@@ -369,6 +394,7 @@ vs_status RollCorrector::create(const vs_roll_params& p, int device, RollCorrect
     if (e == cudaSuccess) e = cudaMemcpy(r->d_tab_ + numangle, tc.data(), sizeof(float) * numangle, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_state_, sizeof(RollState));
     if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_lines_, sizeof(float) * 3 * RL_MAX_LINES);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_cand_, sizeof(unsigned long long) * RL_MAX_LINES);
     RollState init{};
     init.first = 1;
     if (e == cudaSuccess) e = cudaMemcpy(r->d_state_, &init, sizeof(init), cudaMemcpyHostToDevice);
@@ -380,7 +406,7 @@ vs_status RollCorrector::create(const vs_roll_params& p, int device, RollCorrect
 RollCorrector::~RollCorrector() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
-    for (void* p : {(void*)d_tab_, (void*)d_state_, (void*)d_lines_, (void*)d_gray_, (void*)d_map_, (void*)d_queue_, (void*)d_list_,
+    for (void* p : {(void*)d_tab_, (void*)d_state_, (void*)d_lines_, (void*)d_cand_, (void*)d_gray_, (void*)d_map_, (void*)d_queue_, (void*)d_list_,
                     (void*)d_edges_, (void*)d_counters_, (void*)d_accum_, (void*)d_in_, (void*)d_out_})
         if (p) cudaFree(p);
 }
@@ -430,17 +456,17 @@ vs_status RollCorrector::correct_device(const uint8_t* d_src, int w, int h, size
     const int low = (int)std::floor(std::min(p_.canny_threshold_low, p_.canny_threshold_high));
     const int high = (int)std::floor(std::max(p_.canny_threshold_low, p_.canny_threshold_high));
     k_roll_canny_nms<<<dim3((sw_ + CN_TX - 1) / CN_TX, (sh_ + CN_TY - 1) / CN_TY), dim3(CN_TX, CN_TY), 0, st>>>(d_gray_, sw_, sh_, low, high, d_map_, d_queue_, d_counters_);
-    // counters[3] (slot reservation for spilled items) starts where the strong list ends
-    RCUDA(cudaMemcpyAsync(d_counters_ + 3, d_counters_, sizeof(int), cudaMemcpyDeviceToDevice, st));
-    k_roll_hysteresis<<<64, 128, 0, st>>>(d_map_, sw_, sh_, d_queue_, d_counters_, n);
+    k_roll_seed_counters<<<1, 32, 0, st>>>(d_counters_);
+    k_roll_hysteresis<<<32, 128, 0, st>>>(d_map_, sw_, sh_, d_queue_, d_counters_, n);
     k_roll_edge_list<<<(n + 255) / 256, 256, 0, st>>>(d_map_, n, sw_, d_edges_, d_list_, d_counters_);
     k_roll_hough<<<numangle_, 256, (numrho_ + 2) * sizeof(int), st>>>(d_list_, d_counters_, d_tab_, d_tab_ + numangle_, numrho_, d_accum_);
     RollParamsDev prm{p_.angle_filter_min, p_.angle_filter_max, p_.angle_smoothing_alpha, p_.angle_decay, p_.max_angle_change_deg};
-    k_roll_lines<<<1, 1024, 0, st>>>(d_accum_, numangle_, numrho_, p_.hough_threshold, p_.hough_rho, p_.hough_theta, prm, w, h, d_state_, d_lines_);
+    k_roll_maxima<<<numangle_, 256, 0, st>>>(d_accum_, numrho_, p_.hough_threshold, d_cand_, d_counters_);
+    k_roll_lines<<<1, 1024, 0, st>>>(d_cand_, d_counters_, numangle_, numrho_, p_.hough_threshold, p_.hough_rho, p_.hough_theta, prm, w, h, d_state_, d_lines_);
     const int vec = ((uintptr_t)d_dst % 4 == 0 && dstride % 4 == 0) ? 1 : 0;
     k_roll_remap<<<dim3(((w + 3) / 4 + 255) / 256, h), 256, 0, st>>>(d_src, w, h, stride, d_dst, dstride, d_state_, vec);
     RCUDA(cudaGetLastError());
-    launches_ += 7;
+    launches_ += 9;
     return VS_OK;
 }
 

@@ -36,6 +36,7 @@ private:
     float* d_tab_ = nullptr;          // tabSin[numangle] then tabCos[numangle]
     RollState* d_state_ = nullptr;
     float* d_lines_ = nullptr;        // (rho, theta, votes) of the last frame, in cv::HoughLines order
+    unsigned long long* d_cand_ = nullptr;   // local maxima of the accumulator, unsorted keys
     uint8_t *d_gray_ = nullptr, *d_edges_ = nullptr, *d_in_ = nullptr, *d_out_ = nullptr;
     unsigned int *d_map_ = nullptr, *d_list_ = nullptr;
     int *d_queue_ = nullptr, *d_counters_ = nullptr, *d_accum_ = nullptr;
