@@ -50,7 +50,7 @@ typedef struct vs_params {
     int32_t max_corners;              /* maxCorners (200) live, first frame; 1..2048 (else UNSUPPORTED) */
     double  quality_level;            /* qualityLevel (0.01) live, first frame               */
     double  min_distance;             /* minDistance (30.0) live, first frame                */
-    int32_t block_size;               /* blockSize (3) — only 3 is supported (the default)   */
+    int32_t block_size;               /* blockSize (3) live, first frame only; 1..23          */
     char    border_type[32];          /* borderType ("black") live                           */
     int32_t border_size;              /* borderSize (0) live                                 */
     int32_t crop_n_zoom;              /* cropNZoom (false) live                              */
@@ -351,6 +351,9 @@ vs_status vs_k_resize_linear_u8(const uint8_t* d_src, int sw, int sh, size_t sst
  * d_gray tightly packed w x h.  Writes up to capacity (x,y) pairs to host xy_out. */
 vs_status vs_k_good_features(const uint8_t* d_gray, int w, int h, int max_corners, double quality, double min_dist,
                              float* xy_out_host, int capacity, int* n_out, void* stream);
+/* the same with cv::goodFeaturesToTrack's blockSize argument (1..23; the first-frame detection passes params.blockSize) */
+vs_status vs_k_good_features_block(const uint8_t* d_gray, int w, int h, int max_corners, double quality, double min_dist,
+                                   int block_size, float* xy_out_host, int capacity, int* n_out, void* stream);
 /* cv::calcOpticalFlowPyrLK(prev, next, pts, 15x15, maxLevel 2, COUNT+EPS 20/0.03) — Stabilizer.cpp:611-619.
  * d_prev/d_next tightly packed w x h gray. */
 vs_status vs_k_pyr_lk(const uint8_t* d_prev, const uint8_t* d_next, int w, int h, const float* pts_xy_host, int n,

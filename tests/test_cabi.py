@@ -195,7 +195,7 @@ def test_unsupported_flags_are_reported(vsb):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("needs a device to get past the device check")
-    for kw in ({"enableVirtualCanvas": True}, {"blockSize": 5}, {"maxCorners": 0}, {"maxCorners": 5000}):
+    for kw in ({"enableVirtualCanvas": True}, {"blockSize": 0}, {"blockSize": 31}, {"maxCorners": 0}, {"maxCorners": 5000}):
         with pytest.raises(vsb.VsError) as ei:
             vsb.Stabilizer(vsb.Parameters(**kw))
         assert ei.value.status == 7

@@ -286,3 +286,17 @@ def test_ransac_partial_affine(vsb, cv2_noopt, n, outl, noise):
         assert np.array_equal(gmask, mask.ravel()), "inlier mask differs"
         # 1e-3 px of corner displacement (north star); the fit itself agrees to ~1e-9
         assert np.abs(got - ref).max() < 1e-8
+
+
+@pytest.mark.parametrize("w,h,block,q,md", [(480, 270, 5, 0.01, 30.0), (480, 270, 7, 0.02, 10.0), (480, 270, 2, 0.01, 15.0),
+                                            (960, 540, 5, 0.05, 12.0), (480, 270, 9, 0.01, 8.0), (480, 270, 1, 0.03, 20.0)])
+def test_good_features_other_block_sizes(vsb, cv2_noopt, w, h, block, q, md):
+    """cv::goodFeaturesToTrack with blockSize != 3 (the first-frame detection passes params.blockSize, Stabilizer.cpp:355-357):
+    ordered corner list bit-exact against cv2, odd and even window sizes."""
+    cv2 = cv2_noopt
+    g = _texture(w, h, 40 + block)[..., 1].copy()
+    ref = cv2.goodFeaturesToTrack(g, 200, q, md, None, blockSize=block)
+    ref = np.zeros((0, 2), np.float32) if ref is None else ref.reshape(-1, 2)
+    got = vsb.kernels.good_features(_dev(g), 200, q, md, block_size=block)
+    assert len(ref) > 20
+    assert np.array_equal(got, ref), f"first difference at {next((i for i in range(min(len(got), len(ref))) if not np.array_equal(got[i], ref[i])), None)} of {len(ref)} / {len(got)}"

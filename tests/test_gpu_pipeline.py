@@ -808,3 +808,22 @@ def test_handles_on_two_devices_in_one_process(vsb):
         outs.append(got)
     for a, b, c in zip(*outs):
         assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+@pytest.mark.parametrize("block", [5, 2])
+def test_block_size_of_the_first_frame_detection_vs_live_oracle(vsb, cv2_noopt, block):
+    """params.blockSize reaches only the first-frame goodFeaturesToTrack (Stabilizer.cpp:355-357); re-detections hard-code 3."""
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters
+    clip = synthclip.make_clip(1280, 720, 16, 990 + block)
+    kw = dict(smoothingRadius=5, blockSize=block, minDistance=12.0)
+    outs, st = _run(vsb, clip, vsb.Parameters(**kw))
+    ref_outs, ref = run_clip(clip, Parameters(**kw))
+    assert np.array_equal(st.first_corners(), ref.first_corners)
+    for i, r in enumerate(ref.frame_records):
+        pts = st.frame_points(i)
+        assert np.array_equal(pts["status"], r.status)
+        if r.detected is not None:
+            assert np.array_equal(pts["detected"], r.detected)
+    for k, (a, b) in enumerate(zip(outs, ref_outs)):
+        assert np.abs(a.astype(np.int16) - b.astype(np.int16))[40:-40, 40:-40].max() <= 1, f"output {k}"

@@ -128,6 +128,7 @@ SYMBOLS = {
     "vs_k_gray_pyramid": (_I, [_U8P, _I, _I, _SZ, _I, _I, _U8P, _U8P, _U8P, _P]),
     "vs_k_resize_linear_u8": (_I, [_U8P, _I, _I, _SZ, _I, _U8P, _I, _I, _SZ, _P]),
     "vs_k_good_features": (_I, [_U8P, _I, _I, _I, C.c_double, C.c_double, _P, _I, _IP, _P]),
+    "vs_k_good_features_block": (_I, [_U8P, _I, _I, _I, C.c_double, C.c_double, _I, _P, _I, _IP, _P]),
     "vs_k_pyr_lk": (_I, [_U8P, _U8P, _I, _I, _P, _I, _P, _P, _P]),
     "vs_k_estimate_affine_partial": (_I, [_P, _P, _I, _P, _P, _IP, _IP, _P]),
     "vs_k_warp_output": (_I, [_U8P, _I, _I, _SZ, _P, _I, _I, _I, _U8P, _SZ, _IP, _IP, _P]),

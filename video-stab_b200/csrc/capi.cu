@@ -663,9 +663,9 @@ vs_status vs_k_gray_pyramid(const uint8_t* d_bgr, int w, int h, size_t stride, i
     API_END
 }
 
-vs_status vs_k_good_features(const uint8_t* d_gray, int w, int h, int max_corners, double quality, double min_dist,
-                             float* xy_out_host, int capacity, int* n_out, void* stream) {
-    if (!d_gray || !n_out) return vs_set_error(VS_ERR_INVALID_ARG, "bad argument");
+vs_status vs_k_good_features_block(const uint8_t* d_gray, int w, int h, int max_corners, double quality, double min_dist,
+                                   int block_size, float* xy_out_host, int capacity, int* n_out, void* stream) {
+    if (!d_gray || !n_out || block_size < 1 || block_size > 23) return vs_set_error(VS_ERR_INVALID_ARG, "bad argument");
     if (!((w == VS_AW && h == VS_AH) || (w == VS_FW && h == VS_FH)))
         return vs_set_error(VS_ERR_INVALID_ARG, "gray size must be 960x540 or 480x270");
     API_BEGIN
@@ -677,18 +677,25 @@ vs_status vs_k_good_features(const uint8_t* d_gray, int w, int h, int max_corner
     const int slot = (w == VS_FW) ? -1 : 0;
     launch_pack_level(d_gray, slot < 0 ? L.small0 : L.pyr[0].lv[0], st);
     e->reset_detect_counters();
-    launch_good_features(e->d_lanes(), 1, slot, max_corners, quality, min_dist, 0, 0, 0, st);
+    float* eig = nullptr;
+    if (block_size != 3 && cudaMalloc((void**)&eig, sizeof(float) * (size_t)w * h) != cudaSuccess) { delete e; return vs_set_cuda_error(cudaGetLastError(), "cudaMalloc", __FILE__, __LINE__); }
+    launch_good_features(e->d_lanes(), 1, slot, max_corners, quality, min_dist, 0, 0, 0, st, block_size, eig);
     int n = 0;
     cudaError_t ce = cudaMemcpyAsync(&n, L.kp_count, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
     if (ce == cudaSuccess && xy_out_host && n > 0)
         ce = cudaMemcpy(xy_out_host, L.kp, sizeof(float2) * (n < capacity ? n : capacity), cudaMemcpyDeviceToHost);
     delete e;
+    if (eig) cudaFree(eig);
     if (ce != cudaSuccess) return vs_set_cuda_error(ce, "vs_k_good_features", __FILE__, __LINE__);
     *n_out = n;
     (void)stream;
     return VS_OK;
     API_END
+}
+vs_status vs_k_good_features(const uint8_t* d_gray, int w, int h, int max_corners, double quality, double min_dist,
+                             float* xy_out_host, int capacity, int* n_out, void* stream) {
+    return vs_k_good_features_block(d_gray, w, h, max_corners, quality, min_dist, 3, xy_out_host, capacity, n_out, stream);
 }
 
 vs_status vs_k_pyr_lk(const uint8_t* d_prev, const uint8_t* d_next, int w, int h, const float* pts_xy_host, int n,

@@ -82,7 +82,9 @@ vs_status Engine::create(const vs_params& p, int device, int n_lanes, Engine** o
     *out = nullptr;
     if (n_lanes < 1 || n_lanes > VS_MAX_GROUP) return vs_set_error(VS_ERR_INVALID_ARG, "n_streams must be 1..64");
     if (p.enable_virtual_canvas) return vs_set_error(VS_ERR_UNSUPPORTED, "enable_virtual_canvas is not built yet");
-    if (p.block_size != 3) return vs_set_error(VS_ERR_UNSUPPORTED, "only block_size 3 (the reference default) is supported");
+    // block_size applies to the first-frame detection only (Stabilizer.cpp:355-357); the window must stay inside the 16-pixel
+    // reflect frame kept around every gray level
+    if (p.block_size < 1 || p.block_size > 23) return vs_set_error(VS_ERR_UNSUPPORTED, "block_size must be 1..23");
     if (p.max_corners <= 0 || p.max_corners > MO_MAXP_HOST)
         return vs_set_error(VS_ERR_UNSUPPORTED, "max_corners must be 1..2048 (<= 0 means 'unlimited' to cv::goodFeaturesToTrack; the corner buffers are fixed-size)");
     if (p.adaptive_smoothing && n_lanes > 1)
@@ -439,7 +441,11 @@ vs_status Engine::first_frame_detect(const PtrPack& src, int w, int h, size_t st
     launch_gray_resize(d_lanes_, n_lanes_, src, w, h, stride, -1, sp());                  // :304-305
     if (multi_) { CUDA_TRY(cudaEventRecord(evG_, sp())); CUDA_TRY(cudaStreamWaitEvent(sc(0), evG_, 0)); }
     CUDA_TRY(cudaMemsetAsync(d_detect_counters_, 0, sizeof(unsigned int) * 2 * n_lanes_, sc(0)));
-    launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, 0, 0, sc(0));  // :355-357
+    if (p_.block_size != 3 && !d_eig_generic_) {
+        CUDA_TRY(cudaMalloc((void**)&d_eig_generic_, sizeof(float) * VS_FW * VS_FH * n_lanes_));
+        allocs_.push_back(d_eig_generic_);
+    }
+    launch_good_features(d_lanes_, n_lanes_, -1, p_.max_corners, p_.quality_level, p_.min_distance, 0, 0, 0, sc(0), p_.block_size, d_eig_generic_);  // :355-357
     if (multi_) { CUDA_TRY(cudaEventRecord(evC_[0], sc(0))); c_pending_[0] = true; }
     launches_ += 3;
     return VS_OK;

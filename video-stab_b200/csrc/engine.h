@@ -142,6 +142,7 @@ private:
     std::vector<LaneDev> h_lanes_;
     LaneDev* d_lanes_ = nullptr;
     unsigned int* d_detect_counters_ = nullptr;   // [lane][2] = eig_max, cand_count
+    float* d_eig_generic_ = nullptr;              // eigenvalue map of the first-frame detection when block_size != 3
     int kp_cap_ = 0, cap_first_ = 0, cap_redetect_ = 0, log_depth_ = 0, traj_cap_ = 0;
     int ring_slots_ = 0;
     size_t frame_bytes_ = 0, out_bytes_ = 0;

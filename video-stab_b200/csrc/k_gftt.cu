@@ -533,6 +533,62 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const LaneDev* __restric
 #define SEL_DYN_BYTES (SEL_CHUNK_MAX * sizeof(unsigned long long) + SEL_BINS * sizeof(unsigned int) + \
                        SEL_GRID_CELLS * (1 + VS_GRID_SLOTS) * sizeof(unsigned int) + SEL_CHUNK_MAX * 2 * sizeof(unsigned int))
 
+// ------------------------------------------------------------------------------------ any block size (first frame only)
+// cv::goodFeaturesToTrack is called with params_.blockSize only on the very first frame (Stabilizer.cpp:355-357); every re-detection
+// hard-codes 3 (:744).  For blockSize != 3 the eigenvalue map is computed per pixel, once per stream, by the two plain kernels below
+// (the tiled k_eig_nms is specialised for 3x3): Sobel 3x3 scaled by 1 / (4 * blockSize * 255), products in float, the
+// blockSize x blockSize box sum in double over BORDER_REFLECT_101 of the PRODUCT maps (window anchored at blockSize / 2), then
+// (a + c) - sqrt((a - c)^2 + b^2) exactly as k_eig_nms, 3x3 non-max suppression and the same sort keys for k_select.
+__global__ void __launch_bounds__(128) k_eig_generic(const LaneDev* __restrict__ lanes, int slot, int block, float* __restrict__ eig_all) {
+    const LaneDev& L = lanes[blockIdx.z];
+    const GrayLevel G = gftt_src(L, slot);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= G.w) return;
+    const float f1 = (float)(1.0 / (4.0 * (double)block * 255.0));
+    const float f0 = 2.f * f1;
+    const int a0 = block / 2;
+    double sxx = 0, sxy = 0, syy = 0;
+    for (int j = 0; j < block; ++j) {
+        const int py = reflect101(y - a0 + j, G.h);
+        double rx = 0, ry = 0, rz = 0;
+        for (int i = 0; i < block; ++i) {
+            const int px = reflect101(x - a0 + i, G.w);
+            const uint8_t* r0 = G.base + (ptrdiff_t)(py - 1) * G.pitch + px;      // the level's materialised reflect frame supplies Sobel's border
+            const uint8_t* r1 = r0 + G.pitch;
+            const uint8_t* r2 = r1 + G.pitch;
+            // row passes then column passes, in k_eig_nms's (= OpenCV's) operation order
+            const float t0 = __fadd_rn(__fadd_rn(__fmul_rn((float)r0[-1], f1), __fmul_rn((float)r0[0], f0)), __fmul_rn((float)r0[1], f1));
+            const float t2 = __fadd_rn(__fadd_rn(__fmul_rn((float)r2[-1], f1), __fmul_rn((float)r2[0], f0)), __fmul_rn((float)r2[1], f1));
+            const int d0 = (int)r0[1] - (int)r0[-1], d1 = (int)r1[1] - (int)r1[-1], d2 = (int)r2[1] - (int)r2[-1];
+            const float dx = __fadd_rn(__fmul_rn((float)(d0 + d2), f1), __fmul_rn((float)d1, f0));
+            const float dy = __fsub_rn(t2, t0);
+            rx += (double)__fmul_rn(dx, dx);
+            ry += (double)__fmul_rn(dx, dy);
+            rz += (double)__fmul_rn(dy, dy);
+        }
+        sxx += rx; sxy += ry; syy += rz;
+    }
+    const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
+    const float d = __fsub_rn(a, c);
+    const float e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+    eig_all[(size_t)blockIdx.z * G.w * G.h + (size_t)y * G.w + x] = e;
+}
+__global__ void __launch_bounds__(128) k_nms_generic(const LaneDev* __restrict__ lanes, int slot, int gen, const float* __restrict__ eig_all) {
+    const LaneDev& L = lanes[blockIdx.z];
+    const DetView D = det_view(L, gen, 0);
+    const GrayLevel G = gftt_src(L, slot);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= G.w) return;
+    const float* eig = eig_all + (size_t)blockIdx.z * G.w * G.h;
+    const float e = eig[(size_t)y * G.w + x];
+    if (e > 0.f) atomicMax(D.eig_max, __float_as_uint(e));
+    if (x < 1 || x >= G.w - 1 || y < 1 || y >= G.h - 1 || !(e > 0.f)) return;
+    bool is = true;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) is = is && e >= eig[(size_t)(y + dy) * G.w + x + dx];
+    if (is) D.cand[atomicAdd(D.cand_count, 1)] = ((unsigned long long)__float_as_uint(e) << 32) | (unsigned)(y * G.w + x);
+}
+
 size_t gftt_grid_words(int w, int h, double min_dist) {
     if (min_dist < 1.0) return 8;
     int cell = (int)rint(min_dist);
@@ -541,7 +597,7 @@ size_t gftt_grid_words(int w, int h, double min_dist) {
 }
 
 void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_corners, double quality,
-                          double min_dist, int record_frame_no, int gen, int kp_slot, cudaStream_t st) {
+                          double min_dist, int record_frame_no, int gen, int kp_slot, cudaStream_t st, int block_size, float* eig_scratch) {
     const int w = slot < 0 ? VS_FW : VS_AW, h = slot < 0 ? VS_FH : VS_AH;
     // the attribute is per DEVICE (a process may hold handles on several GPUs): once per device, not once per process
     static bool attr_set[64] = {};
@@ -551,8 +607,14 @@ void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_c
         cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_DYN_BYTES);
         attr_set[dev] = true;
     }
-    dim3 g1((w + EIG_TW - 1) / EIG_TW, (h + EIG_TH - 1) / EIG_TH, n_lanes);
-    k_eig_nms<<<g1, 256, 0, st>>>(lanes, slot, gen);
+    if (block_size != 3 && eig_scratch) {
+        const dim3 gg((w + 127) / 128, h, n_lanes);
+        k_eig_generic<<<gg, 128, 0, st>>>(lanes, slot, block_size, eig_scratch);
+        k_nms_generic<<<gg, 128, 0, st>>>(lanes, slot, gen, eig_scratch);
+    } else {
+        dim3 g1((w + EIG_TW - 1) / EIG_TW, (h + EIG_TH - 1) / EIG_TH, n_lanes);
+        k_eig_nms<<<g1, 256, 0, st>>>(lanes, slot, gen);
+    }
     k_select<<<dim3(1, 1, n_lanes), SEL_THREADS, SEL_DYN_BYTES, st>>>(
         lanes, slot, max_corners, quality, min_dist, record_frame_no, gen, kp_slot);
 }

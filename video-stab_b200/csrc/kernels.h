@@ -31,7 +31,8 @@ void launch_unpack_level(GrayLevel src, uint8_t* dst, cudaStream_t st);
 // source = pyramid slot `slot` level 0 (slot >= 0) or small0 (slot < 0); result -> lanes[].kp / kp_count
 // (and first_corners when slot < 0).  record_frame_no > 0: also log into the frame record ring.
 void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_corners, double quality,
-                          double min_dist, int record_frame_no, int gen, int kp_slot, cudaStream_t st);
+                          double min_dist, int record_frame_no, int gen, int kp_slot, cudaStream_t st, int block_size = 3,
+                          float* eig_scratch = nullptr);   // block_size != 3: per-pixel eigenvalue map in eig_scratch (n_lanes * w * h floats)
 size_t gftt_grid_words(int w, int h, double min_dist);
 
 // ---- k_lk.cu : cv::calcOpticalFlowPyrLK (Stabilizer.cpp:611-619)

@@ -55,12 +55,12 @@ def resize_linear(src, dsize):
     return dst
 
 
-def good_features(gray, max_corners: int, quality: float, min_dist: float) -> np.ndarray:
+def good_features(gray, max_corners: int, quality: float, min_dist: float, block_size: int = 3) -> np.ndarray:
     h, w = gray.shape
     cap = max_corners if max_corners > 0 else 2048
     out = np.zeros((cap, 2), np.float32)
     n = C.c_int()
-    check(lib.vs_k_good_features(gray.data_ptr(), w, h, max_corners, quality, min_dist, out.ctypes.data, cap, C.byref(n), None))
+    check(lib.vs_k_good_features_block(gray.data_ptr(), w, h, max_corners, quality, min_dist, block_size, out.ctypes.data, cap, C.byref(n), None))
     return out[: min(n.value, cap)].copy()
 
 
