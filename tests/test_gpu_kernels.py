@@ -294,7 +294,7 @@ def test_good_features_other_block_sizes(vsb, cv2_noopt, w, h, block, q, md):
     """cv::goodFeaturesToTrack with blockSize != 3 (the first-frame detection passes params.blockSize, Stabilizer.cpp:355-357):
     ordered corner list bit-exact against cv2, odd and even window sizes."""
     cv2 = cv2_noopt
-    g = _texture(w, h, 40 + block)[..., 1].copy()
+    g = _tex(vsb, w, h, 40 + block, 1)
     ref = cv2.goodFeaturesToTrack(g, 200, q, md, None, blockSize=block)
     ref = np.zeros((0, 2), np.float32) if ref is None else ref.reshape(-1, 2)
     got = vsb.kernels.good_features(_dev(g), 200, q, md, block_size=block)
