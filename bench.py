@@ -407,9 +407,23 @@ def run_gpu(args, rank, world, local_rank):
         stages = st.stage_times()
         st.set_timing(False)
         stage_us = {k: (v["ms"] / v["count"] * 1e3 if v["count"] else None) for k, v in stages.items()}
+        # per-frame latency of a LIVE stream: one frame pushed, then waited for - the whole
+        # gray -> pyramid -> LK -> motion -> warp chain with nothing to overlap with
+        lat = []
+        for i in range(48):
+            a = (pos + i) % len(order)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            st.push_device(seq_d[a].data_ptr(), W, H, W * 3, out_d[0].data_ptr(), W * 3, frame_bytes, borrow=True)
+            st.sync()
+            lat.append((time.perf_counter() - t0) * 1e6)
+        pos += 48
+        lat.sort()
         ms_max, = allmax(ms)
         c2 = {"value": args.steps * FRAMES_PER_STEP * world / (ms_max * 1e-3), "ms_per_step": ms_max / args.steps,
               "launches": int(launches), "stage_us_per_launch_group": stage_us,
+              "latency_us_push_to_frame": {"median": lat[len(lat) // 2], "p90": lat[int(len(lat) * 0.9)],
+                                           "what": "vs_stabilizer_push_device of ONE frame followed by a host wait, device frames (no copies)"},
               "api": "vs_stabilizer_push_many_device (borrowed device frames; the per-frame stabilize() loop runs inside the library)",
               "l2_policy": "inputs larger than L2 (126-frame sequence = 784 MB, frames read in place)"}
         del st, out_d, seq_d
@@ -799,6 +813,7 @@ def run_gpu(args, rank, world, local_rank):
         }
         if c2 is not None:
             line["stage_us_per_launch_group"] = c2["stage_us_per_launch_group"]
+            line["latency_us_push_to_frame"] = c2["latency_us_push_to_frame"]
             if world > 1:
                 line["config2_per_gpu"] = c2
         if world == 1 and not args.no_cpu_baseline:
