@@ -431,7 +431,7 @@ def run_gpu(args, rank, world, local_rank):
     # ============================================================ config 4: 64 streams sharded s mod N, lock-step batches
     c4 = None
     if "config4" in parts:
-        my_streams = [s for s in range(C4_STREAMS) if s % world == rank]
+        my_streams = [s for s in range(args.c4_streams) if s % world == rank]
         S = len(my_streams)
         loop = _pingpong(C4_CLIP)
         lanes = []
@@ -442,50 +442,72 @@ def run_gpu(args, rank, world, local_rank):
             del gen, fr
         out4 = torch.empty((S, C4_FRAMES, H, W, 3), dtype=torch.uint8, device=dev)
         torch.cuda.synchronize()
-        sb = vsb.StabilizerBatch(params, S, device=local_rank)
-        ext4 = torch.cuda.ExternalStream(sb.stream, device=dev)
-        # pointer tables built once: the timed loop is one C call per lock-step frame
-        PA = C.c_void_p * S
-        in_tab = [PA(*[lanes[i][f].data_ptr() for i in range(S)]) for f in range(len(loop))]
-        out_tab = [PA(*[out4[i, k].data_ptr() for i in range(S)]) for k in range(C4_FRAMES)]
+        # The rank's streams advance in lock-step GROUPS, one StabilizerBatch (one launch per stage) per group.  With few streams per
+        # GPU (N = 8: eight) two groups of four interleaved from the one host thread keep the SMs busier than one group of eight
+        # (profiles/tools/batch_groups.py: 84.7 k -> 90.2 k frames/s on one GPU); from 16 streams per GPU up one group is as good.
+        n_groups = 2 if (S <= 8 and S % 2 == 0 and S >= 4) else 1
+        per = S // n_groups
+        groups = []
+        for g in range(n_groups):
+            sbg = vsb.StabilizerBatch(params, per, device=local_rank)
+            PA = C.c_void_p * per
+            idx = range(g * per, (g + 1) * per)
+            in_tab = [PA(*[lanes[i][f].data_ptr() for i in idx]) for f in range(len(loop))]       # pointer tables built once: the timed
+            out_tab = [PA(*[out4[i, k].data_ptr() for i in idx]) for k in range(C4_FRAMES)]       # loop is one C call per lock-step frame
+            groups.append((sbg, in_tab, out_tab))
+        ext4 = torch.cuda.ExternalStream(groups[0][0].stream, device=dev)
         pos4 = 0
 
         def step4():
             nonlocal pos4
             for k in range(C4_FRAMES):
-                rc = lib.vs_batch_push_device(sb._h, in_tab[pos4 % len(loop)], W, H, W * 3, out_tab[k], W * 3, frame_bytes, 1,
-                                              C.byref(ow), C.byref(oh), C.byref(produced))
-                assert rc == 0, lib.vs_last_error()
+                for sbg, in_tab, out_tab in groups:
+                    rc = lib.vs_batch_push_device(sbg._h, in_tab[pos4 % len(loop)], W, H, W * 3, out_tab[k], W * 3, frame_bytes, 1,
+                                                  C.byref(ow), C.byref(oh), C.byref(produced))
+                    assert rc == 0, lib.vs_last_error()
                 pos4 += 1
+
+        def join4():
+            # every group's work ordered before the timing event on the first group's public stream
+            for sbg, _, _ in groups:
+                sbg.join()
+            for sbg, _, _ in groups[1:]:
+                evj = torch.cuda.Event()
+                evj.record(torch.cuda.ExternalStream(sbg.stream, device=dev))
+                ext4.wait_event(evj)
 
         for _ in range(max(args.warmup, 3)):
             step4()
-        sb.sync()
+        for sbg, _, _ in groups:
+            sbg.sync()
         barrier()
         sampler4 = ClockSampler(local_rank)
         sampler4.start()
-        l0 = sb.launch_count()
+        l0 = sum(g[0].launch_count() for g in groups)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        join4()
         e0.record(ext4)
         for _ in range(args.steps):
             step4()
-        sb.join()
+        join4()
         e1.record(ext4)
-        sb.sync()
+        for sbg, _, _ in groups:
+            sbg.sync()
         barrier()
         ms4 = e0.elapsed_time(e1)
-        launches4 = sb.launch_count() - l0
+        launches4 = sum(g[0].launch_count() for g in groups) - l0
         clocks4 = sampler4.stop()
         ms4_max, = allmax(ms4)
         l4_sum, = allsum(launches4)
-        c4 = {"value": args.steps * C4_STREAMS * C4_FRAMES / (ms4_max * 1e-3), "unit": UNIT, "ms_per_step": ms4_max / args.steps,
-              "streams": C4_STREAMS, "streams_per_gpu": S, "frames_per_step": C4_STREAMS * C4_FRAMES, "n_gpus": world,
+        c4 = {"value": args.steps * args.c4_streams * C4_FRAMES / (ms4_max * 1e-3), "unit": UNIT, "ms_per_step": ms4_max / args.steps,
+              "streams": args.c4_streams, "streams_per_gpu": S, "frames_per_step": args.c4_streams * C4_FRAMES, "n_gpus": world,
               "launches": int(l4_sum), "clocks": clocks4, "scaling": "strong",
-              "sharding": "stream s on GPU s mod N; one StabilizerBatch per rank, one launch per stage for all its streams",
+              "sharding": f"stream s on GPU s mod N; {n_groups} lock-step group(s) of {per} streams per rank (one StabilizerBatch each, one launch per stage per group)",
+              "groups_per_gpu": n_groups,
               "l2_policy": f"inputs larger than L2 ({S} streams x 46-frame loop = {S * 46 * frame_bytes / 1e9:.1f} GB per GPU, frames read in place)"}
         if world > 1:
             clocks = clocks4
-        del sb, out4, lanes, in_tab, out_tab
+        del groups, out4, lanes
         torch.cuda.empty_cache()
 
     # ============================================================ e2e: host frames in / host frames out, copies timed
@@ -840,6 +862,7 @@ def main():
     ap.add_argument("--parts", default="config2,config4,e2e,roofline,config3,config5",
                     help="comma list of config2, config4, e2e, roofline, config3, config5 (profiling runs select one)")
     ap.add_argument("--clip-frames", type=int, default=C5_FRAMES)
+    ap.add_argument("--c4-streams", type=int, default=C4_STREAMS, help="profiling only: total streams of config 4 (default 64)")
     ap.add_argument("--config2-at-all-n", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
