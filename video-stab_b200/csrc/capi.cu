@@ -716,7 +716,7 @@ vs_status vs_k_pyr_lk(const uint8_t* d_prev, const uint8_t* d_next, int w, int h
     cudaError_t ce = cudaMemcpyAsync(L.kp, pts_xy_host, sizeof(float2) * n, cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(L.kp_count, &n, sizeof(int), cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess) {
-        launch_pyr_lk(e->d_lanes(), 1, 0, 1, n, 0, 0, st);
+        launch_pyr_lk(e->d_lanes(), 1, 0, 1, n, 0, 0, st, e->tracker_uses_tma());
         ce = cudaStreamSynchronize(st);
     }
     if (ce == cudaSuccess && n > 0) {

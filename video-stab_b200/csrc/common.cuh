@@ -96,6 +96,8 @@ struct LaneDev {
     int log_depth;
     int record_capacity;
     int pad0;
+    const void* lk_maps;            // device array of CUtensorMap, [pyramid slot][level][0: 48x18 template box, 1: 48x32 search box] over
+                                    // the PADDED gray plane of that level (k_lk.cu); null = the tracker stages with plain loads
 };
 
 // Host-known scalars of one lock-step frame step, passed by value to the motion kernel.

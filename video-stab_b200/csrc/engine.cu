@@ -254,7 +254,21 @@ vs_status Engine::alloc_fixed() {
         L.kp_capacity = kp_cap_;
         L.log_depth = log_depth_;
         L.record_capacity = traj_cap_;
+        // tensor maps of this lane's pyramid planes (TMA-staged tracker, k_lk.cu); without them the tracker uses plain loads
+        L.lk_maps = nullptr;
+        if (l == 0 || lk_tma_) {
+            std::vector<unsigned char> hm((size_t)VS_PYR_SLOTS * VS_LEVELS * 2 * 128 + 64);
+            unsigned char* aligned = reinterpret_cast<unsigned char*>(((uintptr_t)hm.data() + 63) & ~(uintptr_t)63);
+            if (lk_encode_maps(L, aligned)) {
+                unsigned char* dm = nullptr;
+                VS_TRY(dalloc(allocs_, &dm, (size_t)VS_PYR_SLOTS * VS_LEVELS * 2 * 128));
+                CUDA_TRY(cudaMemcpy(dm, aligned, (size_t)VS_PYR_SLOTS * VS_LEVELS * 2 * 128, cudaMemcpyHostToDevice));
+                L.lk_maps = dm;
+                lk_tma_ = true;
+            } else lk_tma_ = false;
+        }
     }
+    if (!lk_tma_) for (auto& L : h_lanes_) L.lk_maps = nullptr;
     CUDA_TRY(cudaMemcpy(d_lanes_, h_lanes_.data(), sizeof(LaneDev) * n_lanes_, cudaMemcpyHostToDevice));
     return VS_OK;
 }
@@ -520,7 +534,7 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
         if (c_pending_[kp_slot]) CUDA_TRY(cudaStreamWaitEvent(sa(frame_no), evC_[kp_slot], 0));   // both frames after a detection
     }
     { StageScope t(this, VS_STAGE_LK, sa(frame_no));
-      launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa(frame_no)); }   // :611-619
+      launch_pyr_lk(d_lanes_, n_lanes_, prev, cur, frame_no <= 2 ? cap_first_ : cap_redetect_, kp_slot, lk_slot, sa(frame_no), lk_tma_); }   // :611-619
     launches_ += 3;
     if (multi_ && split_motion_) {
         // the frame-independent half of the motion step (status filter, RANSAC, refit) runs right behind LK on the

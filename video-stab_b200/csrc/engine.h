@@ -89,6 +89,7 @@ public:
     const LaneDev& h_lane(int i) const { return h_lanes_[i]; }
     vs_status reset_detect_counters();
     int kp_capacity() const { return kp_cap_; }
+    bool tracker_uses_tma() const { return lk_tma_; }
 
 private:
     Engine() = default;
@@ -121,6 +122,8 @@ private:
     int last_detect_frame_ = -100;
     bool c_pending_[VS_KP_SLOTS] = {};
     bool split_motion_ = false;
+    bool lk_tma_ = false;                     // the tracker stages its patches with TMA (tensor maps built for every lane)
+    bool lk_tma() const { return lk_tma_; }
     cudaStream_t sH_ = nullptr, sO_ = nullptr; // copy-in / copy-out streams of the pipelined host path
     cudaEvent_t evH_[8] = {}, evRing_[36] = {}, evOutReady_[VS_OUT_SLOTS] = {}, evOutFree_[VS_OUT_SLOTS] = {};
     bool ring_ev_set_[36] = {}, out_free_set_[VS_OUT_SLOTS] = {};

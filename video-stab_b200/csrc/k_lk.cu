@@ -17,6 +17,7 @@
 // Latency/occupancy-bound: ~200 warps per frame per lane.
 #include "kernels.h"
 #include <climits>
+#include <cstdlib>
 
 #define LK_WARPS 4
 #define LK_NPIX (VS_WIN * VS_WIN)        // 225
@@ -348,8 +349,337 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 5) k_pyr_lk(const LaneDev* __re
     }
 }
 
-void launch_pyr_lk(const LaneDev* lanes, int n_lanes, int prev, int cur, int max_pts, int kp_slot, int lk_slot, cudaStream_t st) {
+// ------------------------------------------------------------------------------------------------
+// TMA variant (the default): the template patch of EVERY level is fetched at the start of the kernel (they depend only on the
+// key point) and the search region of a level is fetched when the level starts, each by ONE cp.async.bulk.tensor.2d issued by
+// lane 0 on the padded gray plane of that level (box 48 bytes x 18 / 32 rows; the plane's materialised reflect-101 frame makes
+// every needed byte in-bounds, and a 16-byte aligned box origin costs at most 15 extra columns).  Completion is an mbarrier per
+// buffer.  The Scharr derivatives, the interpolated template window and the covariance sums only need the template, so they
+// run while the search region is still in flight.  Arithmetic is unchanged from k_pyr_lk above.
+#define LKT_PITCH 48
+#define LKT_PBYTES 896                   // 18 x 48 = 864, padded to a multiple of 128
+#define LKT_JBYTES (LK_JR * LKT_PITCH)   // 1536
+
+struct LkSmemT {
+    uint8_t P[VS_LEVELS][LKT_PBYTES];    // template patches, one per level; origin (pxa, ipy - 1) in plane coordinates
+    uint8_t J[LKT_JBYTES];               // search region; origin (jxa, jy0)
+    short2 D[16][16];
+    int term[3][LK_NPIX];
+    unsigned long long mbar[VS_LEVELS + 1];
+    unsigned long long pad_[10];         // keep sizeof a multiple of 128
+};
+static_assert(sizeof(LkSmemT) % 128 == 0, "per-warp block must keep 128-byte alignment of the TMA destinations");
+
+static __device__ __forceinline__ void lk_mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LKW_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LKD_%=;\n"
+        "bra LKW_%=;\n"
+        "LKD_%=:\n"
+        "}\n" :: "r"(mbar), "r"(parity) : "memory");
+}
+static __device__ __forceinline__ void lk_tma_2d(uint32_t dst, const void* tmap, uint32_t mbar, int x, int y, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(tmap), "r"(mbar), "r"(x), "r"(y) : "memory");
+}
+
+__global__ void __launch_bounds__(LK_WARPS * 32, 5) k_pyr_lk_tma(const LaneDev* __restrict__ lanes, int prev, int cur, int kp_slot, int lk_slot) {
+    __shared__ __align__(128) LkSmemT smem[LK_WARPS];
+    const LaneDev& L = lanes[blockIdx.z];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pidx = blockIdx.x * LK_WARPS + warp;
+    const int npts = min(*L.kpc[kp_slot], L.kp_capacity);
+    if (pidx >= npts) return;                         // warp-uniform
+    LkSmemT& S = smem[warp];
+    const unsigned FULL = 0xffffffffu;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const unsigned char* maps = reinterpret_cast<const unsigned char*>(L.lk_maps);
+    const uint32_t s_mbar = (uint32_t)__cvta_generic_to_shared(&S.mbar[0]);
+    const uint32_t s_J = (uint32_t)__cvta_generic_to_shared(&S.J[0]);
+
+    const float2 pt = L.kpb[kp_slot][pidx];
+    float nx = 0.f, ny = 0.f;                          // nextPts[ptidx]
+    int status = 1;
+
+    // ---- barriers, then the template patch of every level whose window origin is valid (the same test the level loop makes)
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k <= VS_LEVELS; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(s_mbar + 8 * k));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int level = 0; level < VS_LEVELS; ++level) {
+            const GrayLevel I = L.pyr[prev].lv[level];
+            const float sc = 1.f / (float)(1 << level);
+            const float px = __fmul_rn(pt.x, sc) - 7.f, py = __fmul_rn(pt.y, sc) - 7.f;
+            const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+            if (ipx < -VS_WIN || ipx >= I.w || ipy < -VS_WIN || ipy >= I.h) continue;
+            const void* mp = maps + (size_t)((prev * VS_LEVELS + level) * 2 + 0) * 128;
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(mp) : "memory");
+            const int pxa = ((ipx - 1) + VS_PAD) & ~15;
+            lk_tma_2d((uint32_t)__cvta_generic_to_shared(&S.P[level][0]), mp, s_mbar + 8 * level, pxa, ipy - 1 + VS_PAD, LK_PP * LKT_PITCH);
+        }
+    }
+    __syncwarp();
+    uint32_t j_phase = 0;
+
+    for (int level = VS_LEVELS - 1; level >= 0; --level) {
+        const GrayLevel I = L.pyr[prev].lv[level];
+        const GrayLevel Jl = L.pyr[cur].lv[level];
+        const float sc = 1.f / (float)(1 << level);
+        float px = __fmul_rn(pt.x, sc), py = __fmul_rn(pt.y, sc);
+        float qx, qy;                                  // nextPt
+        if (level == VS_LEVELS - 1) { qx = px; qy = py; }
+        else { qx = __fmul_rn(nx, 2.f); qy = __fmul_rn(ny, 2.f); }
+        nx = qx; ny = qy;
+        px -= 7.f; py -= 7.f;
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -VS_WIN || ipx >= I.w || ipy < -VS_WIN || ipy >= I.h) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        int w00, w01, w10, w11;
+        lk_weights(px - (float)ipx, py - (float)ipy, w00, w01, w10, w11);
+        qx -= 7.f; qy -= 7.f;
+
+        // ---- search region of this level: one bulk tensor copy, in flight while the template is processed
+        const void* mj = maps + (size_t)((cur * VS_LEVELS + level) * 2 + 1) * 128;
+        int jx0, jy0, jofs;
+        auto fetch_J = [&](int inx, int iny) {
+            jx0 = min(max((inx - 8) & ~3, -VS_PAD), Jl.w + VS_PAD - LK_JR);
+            jy0 = min(max(iny - 8, -VS_PAD), Jl.h + VS_PAD - LK_JR);
+            const int jxa = (jx0 + VS_PAD) & ~15;
+            jofs = jx0 + VS_PAD - jxa;
+            __syncwarp();                                             // every lane is done with the previous contents
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(mj) : "memory");
+                lk_tma_2d(s_J, mj, s_mbar + 8 * VS_LEVELS, jxa, jy0 + VS_PAD, LKT_JBYTES);
+            }
+        };
+        fetch_J((int)floorf(qx), (int)floorf(qy));
+        // ---- template: wait for its patch (fetched at kernel start)
+        lk_mbar_wait(s_mbar + 8 * level, 0);
+        const uint8_t* Pb = &S.P[level][0];
+        const int pofs = (ipx - 1 + VS_PAD) - (((ipx - 1) + VS_PAD) & ~15);        // 0..15
+        // ---- Scharr derivatives on the 16x16 support; the derivative plane is ZERO outside the image
+        for (int i = lane; i < 256; i += 32) {
+            int r = i >> 4, c = i & 15;
+            int gx = 0, gy = 0;
+            int ix = ipx + c, iy = ipy + r;
+            if (ix >= 0 && ix < I.w && iy >= 0 && iy < I.h) {
+                const uint8_t* p0 = Pb + r * LKT_PITCH + c + pofs;
+                int p00 = p0[0], p01 = p0[1], p02 = p0[2];
+                int p10 = p0[LKT_PITCH], p12 = p0[LKT_PITCH + 2];
+                int p20 = p0[2 * LKT_PITCH], p21 = p0[2 * LKT_PITCH + 1], p22 = p0[2 * LKT_PITCH + 2];
+                gx = 3 * (p02 - p00) + 10 * (p12 - p10) + 3 * (p22 - p20);
+                gy = 3 * (p20 - p00) + 10 * (p21 - p01) + 3 * (p22 - p02);
+            }
+            S.D[r][c] = make_short2((short)gx, (short)gy);
+        }
+        __syncwarp();
+        unsigned abs11 = 0, abs12 = 0, abs22 = 0;
+        int s11 = 0, s12 = 0, s22 = 0;
+        int Iw_r[LK_PER_LANE], dI_r[LK_PER_LANE];
+#pragma unroll
+        for (int k = 0; k < LK_PER_LANE; ++k) {
+            const int p = lane + 32 * k;
+            Iw_r[k] = 0; dI_r[k] = 0;
+            if (p < LK_NPIX) {
+                const int y = p / VS_WIN, x = p - y * VS_WIN;
+                const uint8_t* q0 = Pb + (y + 1) * LKT_PITCH + x + 1 + pofs;
+                const int iv = q0[0] * w00 + q0[1] * w01 + q0[LKT_PITCH] * w10 + q0[LKT_PITCH + 1] * w11;
+                const short2 d00 = S.D[y][x], d01 = S.D[y][x + 1], d10 = S.D[y + 1][x], d11 = S.D[y + 1][x + 1];
+                const int gx = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + 8192) >> 14;
+                const int gy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + 8192) >> 14;
+                Iw_r[k] = (iv + 256) >> 9;
+                dI_r[k] = (gx & 0xffff) | (gy << 16);
+                const int t11 = gx * gx, t12 = gx * gy, t22 = gy * gy;
+                s11 += t11; s12 += t12; s22 += t22;
+                abs11 += (unsigned)t11; abs12 += (unsigned)abs(t12); abs22 += (unsigned)t22;
+            }
+        }
+        float A[3];
+        {
+            const int b11 = __reduce_add_sync(FULL, clamp_abs_sum(abs11));
+            const int b12 = __reduce_add_sync(FULL, clamp_abs_sum(abs12));
+            const int b22 = __reduce_add_sync(FULL, clamp_abs_sum(abs22));
+            const int e11 = __reduce_add_sync(FULL, s11), e12 = __reduce_add_sync(FULL, s12), e22 = __reduce_add_sync(FULL, s22);
+            if (b11 <= (1 << 24) && b12 <= (1 << 24) && b22 <= (1 << 24)) {
+                A[0] = (float)e11; A[1] = (float)e12; A[2] = (float)e22;
+            } else {
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < LK_PER_LANE; ++k) {
+                    const int p = lane + 32 * k;
+                    if (p < LK_NPIX) {
+                        const int gx = (int)(short)(dI_r[k] & 0xffff), gy = dI_r[k] >> 16;
+                        const int t11 = gx * gx, t12 = gx * gy, t22 = gy * gy;
+                        const bool tail = (p - (p / VS_WIN) * VS_WIN) >= 8;
+                        S.term[0][p] = tail ? __float_as_int(__int2float_rn(t11)) : t11;
+                        S.term[1][p] = tail ? __float_as_int(__int2float_rn(t12)) : t12;
+                        S.term[2][p] = tail ? __float_as_int(__int2float_rn(t22)) : t22;
+                    }
+                }
+                __syncwarp();
+                A[0] = (b11 <= (1 << 24)) ? (float)e11 : ordered_sum<true>(S.term[0], lane);
+                A[1] = (b12 <= (1 << 24)) ? (float)e12 : ordered_sum<true>(S.term[1], lane);
+                A[2] = (b22 <= (1 << 24)) ? (float)e22 : ordered_sum<true>(S.term[2], lane);
+                __syncwarp();
+            }
+        }
+        // the search region must have landed before this level is left by any path
+        lk_mbar_wait(s_mbar + 8 * VS_LEVELS, j_phase);
+        j_phase ^= 1;
+        const uint8_t* Jb = &S.J[0];
+        const float A11 = __fmul_rn(A[0], FLT_SCALE), A12 = __fmul_rn(A[1], FLT_SCALE), A22 = __fmul_rn(A[2], FLT_SCALE);
+        float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        float dd = __fsub_rn(A11, A22);
+        float minEig = __fdiv_rn(
+            __fsub_rn(__fadd_rn(A22, A11),
+                      __fsqrt_rn(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
+            450.f);
+        if ((double)minEig < 1e-4 || Dt < 1.1920928955078125e-7f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        Dt = __fdiv_rn(1.f, Dt);
+        float pdx = 0.f, pdy = 0.f;
+        uint32_t jw[LK_PER_LANE];
+        int cur_inx = INT_MIN, cur_iny = INT_MIN;
+#pragma unroll
+        for (int k = 0; k < LK_PER_LANE; ++k) jw[k] = 0u;
+        for (int j = 0; j < 20; ++j) {
+            const int inx = (int)floorf(qx), iny = (int)floorf(qy);
+            if (inx < -VS_WIN || inx >= Jl.w || iny < -VS_WIN || iny >= Jl.h) {
+                if (level == 0) status = 0;
+                break;
+            }
+            lk_weights(qx - (float)inx, qy - (float)iny, w00, w01, w10, w11);
+            if (inx < jx0 || inx + 16 > jx0 + LK_JR || iny < jy0 || iny + 16 > jy0 + LK_JR) {
+                // the window left the staged region: re-centre it (rare)
+                fetch_J(inx, iny);
+                lk_mbar_wait(s_mbar + 8 * VS_LEVELS, j_phase);
+                j_phase ^= 1;
+                cur_inx = INT_MIN;
+            }
+            if (inx != cur_inx || iny != cur_iny) {
+                const uint8_t* jb = Jb + (iny - jy0) * LKT_PITCH + (inx - jx0) + jofs;
+#pragma unroll
+                for (int k = 0; k < LK_PER_LANE; ++k) {
+                    const int p = lane + 32 * k;
+                    if (p < LK_NPIX) {
+                        const int y = p / VS_WIN, x = p - y * VS_WIN;
+                        const uint8_t* q0 = jb + y * LKT_PITCH + x;
+                        jw[k] = (uint32_t)q0[0] | ((uint32_t)q0[1] << 8) | ((uint32_t)q0[LKT_PITCH] << 16) | ((uint32_t)q0[LKT_PITCH + 1] << 24);
+                    }
+                }
+                cur_inx = inx; cur_iny = iny;
+            }
+            const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
+            int sx = 0, sy = 0;
+            unsigned absx = 0, absy = 0;
+#pragma unroll
+            for (int k = 0; k < LK_PER_LANE; ++k) {
+                if (lane + 32 * k < LK_NPIX) {
+                    const int jv = dp2a_hi_su(Wb, jw[k], dp2a_lo_su(Wt, jw[k], 256));
+                    const int diff = (jv >> 9) - Iw_r[k];
+                    const int tx = diff * (int)(short)(dI_r[k] & 0xffff), ty = diff * (dI_r[k] >> 16);
+                    sx += tx; sy += ty;
+                    absx += (unsigned)abs(tx); absy += (unsigned)abs(ty);
+                }
+            }
+            const int bx = __reduce_add_sync(FULL, clamp_abs_sum(absx)), by = __reduce_add_sync(FULL, clamp_abs_sum(absy));
+            const int ex = __reduce_add_sync(FULL, sx), ey = __reduce_add_sync(FULL, sy);
+            float ib1, ib2;
+            if (bx <= (1 << 24) && by <= (1 << 24)) {
+                ib1 = (float)ex; ib2 = (float)ey;
+            } else {
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < LK_PER_LANE; ++k) {
+                    const int p = lane + 32 * k;
+                    if (p < LK_NPIX) {
+                        const int jv = dp2a_hi_su(Wb, jw[k], dp2a_lo_su(Wt, jw[k], 256));
+                        const int diff = (jv >> 9) - Iw_r[k];
+                        const int tx = diff * (int)(short)(dI_r[k] & 0xffff), ty = diff * (dI_r[k] >> 16);
+                        const bool tail = (p - (p / VS_WIN) * VS_WIN) >= 8;
+                        S.term[0][p] = tail ? __float_as_int(__int2float_rn(tx)) : tx;
+                        S.term[1][p] = tail ? __float_as_int(__int2float_rn(ty)) : ty;
+                    }
+                }
+                __syncwarp();
+                ib1 = ordered_sum_b(S.term[0], lane);
+                ib2 = ordered_sum_b(S.term[1], lane);
+                __syncwarp();
+            }
+            float b1 = __fmul_rn(ib1, FLT_SCALE), b2 = __fmul_rn(ib2, FLT_SCALE);
+            float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
+            float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt);
+            qx = __fadd_rn(qx, ddx); qy = __fadd_rn(qy, ddy);
+            nx = __fadd_rn(qx, 7.f); ny = __fadd_rn(qy, 7.f);
+            if ((double)ddx * (double)ddx + (double)ddy * (double)ddy <= 0.03 * 0.03) break;
+            if (j > 0 && fabs((double)__fadd_rn(ddx, pdx)) < 0.01 && fabs((double)__fadd_rn(ddy, pdy)) < 0.01) {
+                nx = __fsub_rn(nx, __fmul_rn(ddx, 0.5f));
+                ny = __fsub_rn(ny, __fmul_rn(ddy, 0.5f));
+                break;
+            }
+            pdx = ddx; pdy = ddy;
+        }
+    }
+    if (status) {
+        const GrayLevel J0 = L.pyr[cur].lv[0];
+        const int fx = (int)floorf(__fsub_rn(nx, 7.f)), fy = (int)floorf(__fsub_rn(ny, 7.f));
+        if (fx < -VS_WIN || fx >= J0.w || fy < -VS_WIN || fy >= J0.h) status = 0;
+    }
+    if (lane == 0) {
+        L.lkn[lk_slot][pidx] = make_float2(nx, ny);
+        L.lks[lk_slot][pidx] = (uint8_t)status;
+    }
+}
+
+// host: the tensor maps of one lane's pyramids, [slot][level][template box, search box], over the padded planes
+#include <cuda.h>
+typedef CUresult (*LkEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool lk_encode_maps(const LaneDev& hl, void* out_host) {
+    static LkEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (LkEncodeFn)p;
+        cudaGetLastError();
+    }
+    if (!fn || getenv("VS_LK_PLAIN")) return false;
+    CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(out_host);
+    for (int s = 0; s < VS_PYR_SLOTS; ++s)
+        for (int l = 0; l < VS_LEVELS; ++l) {
+            const GrayLevel& g = hl.pyr[s].lv[l];
+            void* plane = g.base - (ptrdiff_t)VS_PAD * g.pitch - VS_PAD;
+            if ((uintptr_t)plane % 16 != 0 || g.pitch % 16 != 0) return false;
+            cuuint64_t dims[2] = {(cuuint64_t)g.pitch, (cuuint64_t)(g.h + 2 * VS_PAD)};
+            cuuint64_t strides[1] = {(cuuint64_t)g.pitch};
+            cuuint32_t es[2] = {1, 1};
+            for (int k = 0; k < 2; ++k) {
+                cuuint32_t box[2] = {LKT_PITCH, (cuuint32_t)(k ? LK_JR : LK_PP)};
+                if (fn(&maps[(s * VS_LEVELS + l) * 2 + k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, plane, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return false;
+            }
+        }
+    return true;
+}
+
+void launch_pyr_lk(const LaneDev* lanes, int n_lanes, int prev, int cur, int max_pts, int kp_slot, int lk_slot, cudaStream_t st, bool tma) {
     if (max_pts <= 0) return;
     dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, 1, n_lanes);
-    k_pyr_lk<<<grid, LK_WARPS * 32, 0, st>>>(lanes, prev, cur, kp_slot, lk_slot);
+    if (tma) k_pyr_lk_tma<<<grid, LK_WARPS * 32, 0, st>>>(lanes, prev, cur, kp_slot, lk_slot);
+    else k_pyr_lk<<<grid, LK_WARPS * 32, 0, st>>>(lanes, prev, cur, kp_slot, lk_slot);
 }

@@ -37,7 +37,9 @@ size_t gftt_grid_words(int w, int h, double min_dist);
 
 // ---- k_lk.cu : cv::calcOpticalFlowPyrLK (Stabilizer.cpp:611-619)
 // tracks lanes[].kp from pyramid slot `prev` to slot `cur`; writes lk_next / lk_status
-void launch_pyr_lk(const LaneDev* lanes, int n_lanes, int prev, int cur, int max_pts, int kp_slot, int lk_slot, cudaStream_t st);
+void launch_pyr_lk(const LaneDev* lanes, int n_lanes, int prev, int cur, int max_pts, int kp_slot, int lk_slot, cudaStream_t st, bool tma = false);
+// tensor maps of one lane's pyramid planes for the TMA tracker: out_host = VS_PYR_SLOTS * VS_LEVELS * 2 CUtensorMap (128 bytes each)
+bool lk_encode_maps(const LaneDev& host_lane, void* out_host);
 
 // ---- k_motion.cu : status filter + estimateAffinePartial2D + decomposition + trajectory +
 //                    smoothing + warp set-up (Stabilizer.cpp:629-688, 783-908, 1139-1172, 1364-1458, 1637-1780)
