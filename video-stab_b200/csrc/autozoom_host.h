@@ -77,8 +77,20 @@ static inline void find_external_contours_padded(signed char* work, int w, int h
         signed char* row = work + (size_t)y * step;
         int prev = 0, lnbd_x = 0;
         for (int x = 1; x <= w + 1; ++x) {
-            const int p = row[x];
-            if (p == prev) continue;
+            int p = row[x];
+            if (p == prev) {
+                // runs of equal pixels (almost the whole image) are skipped eight at a time
+                const unsigned long long pat = 0x0101010101010101ull * (unsigned char)prev;
+                while (x + 8 <= w + 1) {
+                    unsigned long long v;
+                    std::memcpy(&v, row + x, 8);
+                    if (v != pat) break;
+                    x += 8;
+                }
+                if (x > w + 1) break;
+                p = row[x];
+                if (p == prev) continue;
+            }
             if (prev == 0 && p == 1 && !(row[lnbd_x] > 0)) {      // start of an outer border that no traced border encloses
                 found.emplace_back();
                 fetch_contour(work, step, x, y, found.back());

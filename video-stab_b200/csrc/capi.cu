@@ -528,9 +528,19 @@ vs_status vs_auto_zoom_crop(const uint8_t* bgr, int width, int height, size_t st
     if (stride == 0) stride = (size_t)width * 3;
     const size_t tight = (size_t)width * 3;
     const size_t ocap = std::max(tight * height, (size_t)640 * 360 * 3);
-    uint8_t *d_in = nullptr, *d_o = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d_in, tight * height));
-    cudaError_t e = cudaMalloc((void**)&d_o, ocap);
+    // device staging frames kept per host thread and device (a per-frame call must not pay for allocations)
+    struct Stage { int dev = -1; size_t in_cap = 0, out_cap = 0; uint8_t *d_in = nullptr, *d_o = nullptr; };
+    static thread_local Stage sg;
+    if (sg.dev != device || tight * height > sg.in_cap || ocap > sg.out_cap) {
+        if (sg.d_in) cudaFree(sg.d_in);
+        if (sg.d_o) cudaFree(sg.d_o);
+        sg = Stage();
+        CUDA_TRY(cudaMalloc((void**)&sg.d_in, tight * height));
+        CUDA_TRY(cudaMalloc((void**)&sg.d_o, ocap));
+        sg.dev = device; sg.in_cap = tight * height; sg.out_cap = ocap;
+    }
+    uint8_t *d_in = sg.d_in, *d_o = sg.d_o;
+    cudaError_t e = cudaSuccess;
     vs_status rc = VS_OK;
     if (e == cudaSuccess) e = cudaMemcpy2D(d_in, tight, bgr, stride, tight, height, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
@@ -543,8 +553,6 @@ vs_status vs_auto_zoom_crop(const uint8_t* bgr, int width, int height, size_t st
             else e = cudaMemcpy2D(out, out_stride, d_o, ot, ot, *out_height, cudaMemcpyDeviceToHost);
         }
     }
-    cudaFree(d_in);
-    if (d_o) cudaFree(d_o);
     CUDA_TRY(e);
     return rc;
     API_END

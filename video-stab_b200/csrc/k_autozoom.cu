@@ -60,21 +60,31 @@ vs_status auto_zoom_crop_device(const uint8_t* d_bgr, int w, int h, size_t strid
                                 int* ow, int* oh, cudaStream_t st) {
     if (!d_bgr || !d_out || w < 4 || h < 4 || !ow || !oh) return vs_set_error(VS_ERR_INVALID_ARG, "auto zoom-crop: bad argument");
     if (stride == 0) stride = (size_t)w * 3;
-    uint8_t *d_mask = nullptr, *d_scratch = nullptr;
-    WarpParams* d_wp = nullptr;
     const size_t padded = (size_t)(w + 2) * (h + 2);
-    // page-locked landing buffer for the padded 0/1 image, kept per host thread
-    static thread_local signed char* h_work = nullptr;
-    static thread_local size_t h_work_cap = 0;
-    if (padded > h_work_cap) {
-        if (h_work) cudaFreeHost(h_work);
-        h_work = nullptr; h_work_cap = 0;
-        if (cudaMallocHost((void**)&h_work, padded) != cudaSuccess) return vs_set_cuda_error(cudaGetLastError(), "cudaMallocHost", __FILE__, __LINE__);
-        h_work_cap = padded;
+    // Scratch kept per host thread and device (a call per frame must not pay for allocations): the mask, the padded 0/1 image,
+    // one warp set-up block, and the page-locked landing buffer of the padded image.  Grown on demand, never shrunk.
+    struct Scratch { int dev = -1; size_t cap = 0; uint8_t *d_mask = nullptr, *d_scratch = nullptr; WarpParams* d_wp = nullptr; signed char* h_work = nullptr; };
+    static thread_local Scratch sc;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return vs_set_cuda_error(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__);
+    if (sc.dev != dev || padded > sc.cap) {
+        if (sc.d_mask) cudaFree(sc.d_mask);
+        if (sc.d_scratch) cudaFree(sc.d_scratch);
+        if (sc.d_wp) cudaFree(sc.d_wp);
+        if (sc.h_work) cudaFreeHost(sc.h_work);
+        sc = Scratch();
+        cudaError_t ea = cudaMalloc((void**)&sc.d_mask, padded);
+        if (ea == cudaSuccess) ea = cudaMalloc((void**)&sc.d_scratch, padded);
+        if (ea == cudaSuccess) ea = cudaMalloc((void**)&sc.d_wp, sizeof(WarpParams));
+        if (ea == cudaSuccess) ea = cudaMallocHost((void**)&sc.h_work, padded);
+        if (ea != cudaSuccess) return vs_set_cuda_error(ea, "auto zoom-crop scratch", __FILE__, __LINE__);
+        sc.dev = dev;
+        sc.cap = padded;
     }
-    cudaError_t e = cudaMallocAsync((void**)&d_mask, (size_t)w * h, st);
-    if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_scratch, padded > (size_t)w * h ? padded : (size_t)w * h, st);
-    if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_wp, sizeof(WarpParams), st);
+    uint8_t *d_mask = sc.d_mask, *d_scratch = sc.d_scratch;
+    WarpParams* d_wp = sc.d_wp;
+    signed char* h_work = sc.h_work;
+    cudaError_t e = cudaSuccess;
     vs_status rc = VS_OK;
     if (e == cudaSuccess) {
         launch_content_mask(d_bgr, w, h, stride, d_mask, d_scratch, st);
@@ -109,9 +119,6 @@ vs_status auto_zoom_crop_device(const uint8_t* d_bgr, int w, int h, size_t strid
             }
         }
     }
-    if (d_mask) cudaFreeAsync(d_mask, st);
-    if (d_scratch) cudaFreeAsync(d_scratch, st);
-    if (d_wp) cudaFreeAsync(d_wp, st);
     if (e != cudaSuccess) return vs_set_cuda_error(e, "auto zoom-crop", __FILE__, __LINE__);
     return rc;
 }
