@@ -581,6 +581,338 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_warp_quad: the tiled warp without the re-pack stage.  ncu on k_warp_tma (profiles/r01_e_warp_ncu.json) shows the
+// shared-memory pipe (11.1 wavefronts per 32 output pixels) and the issue slots (48.7 instructions) saturating together;
+// a third of both goes into turning the packed 3-byte pixels of the TMA box into 4-byte words and into carrying finished
+// pixels through shared memory so that a warp can write whole rows.  Here a lane owns FOUR ADJACENT output pixels:
+//   * their taps are 15 contiguous bytes per source row (5 pixels x 3 channels), i.e. five aligned 32-bit words of the RAW
+//     box whatever the byte phase o = (3 sx) & 3; the channel pairs come out of those words with constant-selector PRMTs
+//     (one code variant per o, chosen by a warp-uniform switch), so the box is used as TMA delivers it;
+//   * the horizontal weight pair and the tap address are derived once per quad, the two middle taps of each row are shared
+//     between neighbouring pixels, and the 12 packed output bytes leave as three 32-bit stores straight from registers;
+//   * a warp covers 8 quads x 4 consecutive rows per step: raw word index 3 q + 120 row takes 32 distinct banks
+//     (120 = 24 mod 32), so the ten tap loads of a step are conflict free without any padding.
+// Per step (4 pixels per lane): 10 LDS + 16 PRMT + 24 IDP.2A + 24 IMAD + 8 PRMT (pack) + 3 PRMT + 3 STG + ~25 for the
+// coordinates, against 4 x 36 in k_warp_tma, and 2.5 + 0.75 shared-memory / store wavefronts per 32 pixels against 6 + 3.4.
+// The vertical terms are lane constants while Y0 advances by exactly 4096 per 4 rows (checked per step, recomputed when
+// not).  Exactness: every coordinate is the integer cv::warpAffine computes (X0(y) + adelta(x), Y0(y) + bdelta(x)); the
+// quad path only requires what it then uses - px 0 and px 3 give consecutive sx (so the five words are the taps of all
+// four pixels), one source row pair for the quad, one byte phase for the warp - and a warp whose step fails a test takes
+// the per-pixel path for that step (same integers, byte loads from the same box).
+#define WQ_BOXB (WT_ROWS * WT_RAW_PITCH)                 // bytes one TMA box delivers
+#define WQ_RAWB ((WQ_BOXB + 127) / 128 * 128)            // raw buffer stride: TMA destinations are 128-byte aligned
+#define WQ_SMEM (2 * WQ_RAWB + WT_W * 8 + WT_H * 8 * 8 + 2 * 32 + 2 * 8 + 8 * 4 + 64)
+
+template <int OFF>
+static __device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(a), "n"(OFF));
+    return v;
+}
+static __device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+template <int OFF>
+static __device__ __forceinline__ uint32_t lds32v(uint32_t a) {            // not volatile: free to be scheduled with its neighbours
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+
+// PRMT selectors for the pixel whose first byte sits at byte P of a run of aligned words: [b0 b1 g0 g1] and [. . r0 r1]
+template <int P> struct QuadSel {
+    static constexpr int s = P & 3, m = P >> 2;
+    static constexpr int sr = (P + 2) & 3, mr = (P + 2) >> 2;
+    static constexpr uint32_t bg = (uint32_t)(s | ((s + 3) << 4) | ((s + 1) << 8) | ((s + 4) << 12));
+    static constexpr uint32_t r = (uint32_t)(sr | ((sr + 3) << 4) | (sr << 8) | ((sr + 3) << 12));
+};
+
+template <int P>
+static __device__ __forceinline__ uint32_t quad_pixel(const uint32_t (&wt)[5], const uint32_t (&wb)[5], uint32_t W16, uint32_t B, uint32_t Bc) {
+    typedef QuadSel<P> S;
+    const uint32_t u0 = __byte_perm(wt[S::m], wt[S::m + 1], S::bg), r0 = __byte_perm(wt[S::mr], wt[S::mr + 1], S::r);
+    const uint32_t l0 = __byte_perm(wb[S::m], wb[S::m + 1], S::bg), r1 = __byte_perm(wb[S::mr], wb[S::mr + 1], S::r);
+    const uint32_t hb0 = __dp2a_lo(W16, u0, 0u), hg0 = __dp2a_hi(W16, u0, 0u), hr0 = __dp2a_hi(W16, r0, 0u);
+    const uint32_t hb1 = __dp2a_lo(W16, l0, 0u), hg1 = __dp2a_hi(W16, l0, 0u), hr1 = __dp2a_hi(W16, r1, 0u);
+    const uint32_t vb = hb0 * Bc + (hb1 * B + 0x800000u);
+    const uint32_t vg = hg0 * Bc + (hg1 * B + 0x800000u);
+    const uint32_t vr = hr0 * Bc + (hr1 * B + 0x800000u);
+    return __byte_perm(__byte_perm(vb, vg, 0x0073), vr, 0x0710);
+}
+
+// four adjacent pixels from the five words of each of the two source rows at shared address a (byte phase O)
+template <int O>
+static __device__ __forceinline__ void quad_step(uint32_t a, const uint32_t (&W)[4], const uint32_t (&B)[4], uint32_t (&px)[4]) {
+    uint32_t wt[5], wb[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) wt[i] = lds32v<0>(a + 4u * i);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) wb[i] = lds32v<0>(a + (uint32_t)WT_RAW_PITCH + 4u * i);
+    px[0] = quad_pixel<O + 0>(wt, wb, W[0], B[0], 1024u - B[0]);
+    px[1] = quad_pixel<O + 3>(wt, wb, W[1], B[1], 1024u - B[1]);
+    px[2] = quad_pixel<O + 6>(wt, wb, W[2], B[2], 1024u - B[2]);
+    px[3] = quad_pixel<O + 9>(wt, wb, W[3], B[3], 1024u - B[3]);
+}
+
+// A quad that straddles a change of source row (px 0..k-1 read rows R, R+1; px k..3 read rows R+1, R+2, or the other way
+// round): every pixel loads its own two or three words per row from its own row pair; nothing is shared, the blend is the same.
+template <int P>
+static __device__ __forceinline__ uint32_t quad_pixel_own(uint32_t a, uint32_t W16, uint32_t B) {
+    typedef QuadSel<P> S;
+    uint32_t wt[5], wb[5];
+#pragma unroll
+    for (int i = S::m; i <= S::mr + 1; ++i) {
+        wt[i] = lds32v<0>(a + 4u * i);
+        wb[i] = lds32v<0>(a + (uint32_t)WT_RAW_PITCH + 4u * i);
+    }
+    return quad_pixel<P>(wt, wb, W16, B, 1024u - B);
+}
+template <int O>
+static __device__ __forceinline__ void quad_step_split(uint32_t a, const uint32_t (&W)[4], const uint32_t (&B)[4], uint32_t smask, uint32_t (&px)[4]) {
+    px[0] = quad_pixel_own<O + 0>(a + ((smask >> 0) & 1u) * (uint32_t)WT_RAW_PITCH, W[0], B[0]);
+    px[1] = quad_pixel_own<O + 3>(a + ((smask >> 1) & 1u) * (uint32_t)WT_RAW_PITCH, W[1], B[1]);
+    px[2] = quad_pixel_own<O + 6>(a + ((smask >> 2) & 1u) * (uint32_t)WT_RAW_PITCH, W[2], B[2]);
+    px[3] = quad_pixel_own<O + 9>(a + ((smask >> 3) & 1u) * (uint32_t)WT_RAW_PITCH, W[3], B[3]);
+}
+// bitwise c ? b : a
+static __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+#define WQ_MAXT 8                         // tiles per CTA strip
+template <bool BORDER>
+__global__ void __launch_bounds__(WT_THREADS, 4)
+k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict__ dmaps, int lanes_mode,
+            const LaneDev* __restrict__ lanes, const WarpParams* __restrict__ wps,
+            PtrPack srcp, const uint8_t* __restrict__ src0, size_t sframe, size_t sstride, int sw, int sh,
+            MutPtrPack dstp, uint8_t* __restrict__ dst0, size_t dframe, int dw, int dh, size_t dstride,
+            int rows_per_cta, int dst_vec, int wp_slot, int border_, int bmode_) {
+    const int border = BORDER ? border_ : 0, bmode = BORDER ? bmode_ : 0;
+    extern __shared__ __align__(1024) unsigned char wt_smem[];
+    unsigned char* const S_raw = wt_smem;                                              // [2][WT_ROWS][WT_RAW_PITCH]
+    int2* const colAB = reinterpret_cast<int2*>(wt_smem + 2 * WQ_RAWB);               // [WT_W] (adelta, bdelta)
+    int2* const S_rowXY = colAB + WT_W;                                               // [WT_H * WQ_MAXT] (X0, Y0), rows past the frame included
+    int (*S_box)[8] = reinterpret_cast<int (*)[8]>(S_rowXY + WT_H * WQ_MAXT);          // [2]
+    unsigned long long* const S_mbar = reinterpret_cast<unsigned long long*>(S_box + 2);   // [2]
+    int* const S_misc = reinterpret_cast<int*>(S_mbar + 2);                            // [tile of the strip]: irregular-step mask
+
+    const int z = blockIdx.z;
+    const double* __restrict__ m = lanes_mode ? lanes[z].wpb[wp_slot]->m : wps[z].m;
+    uint8_t* __restrict__ dst = lanes_mode ? dstp.p[z] : dst0 + (size_t)z * dframe;
+    const CUtensorMap* tmap = dmaps ? dmaps + (lanes_mode ? z : 0) : &pack.m[lanes_mode ? z : 0];
+    const int zc = lanes_mode ? 0 : z;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * WT_W, ys = blockIdx.y * rows_per_cta;
+    const int ye = min(ys + rows_per_cta, dh);
+    const uint32_t s_raw = (uint32_t)__cvta_generic_to_shared(S_raw);
+    const uint32_t s_mbar = (uint32_t)__cvta_generic_to_shared(S_mbar);
+    const uint32_t s_rowXY = (uint32_t)__cvta_generic_to_shared(S_rowXY);
+    const uint32_t s_colAB = (uint32_t)__cvta_generic_to_shared(colAB);
+
+    // ---- 0. strip prologue: column terms and row terms of cv::warpAffine.  A row thread's warp holds the 32 rows of one
+    //         tile; it also notes which 4-row steps cannot keep the vertical terms of the step the same lane did before
+    //         (4 rows up; 20 rows up for the first step of a 16-row half): Y0 must have advanced by exactly 1024 per row.
+    if (tid < WT_W) {
+        const double xd = (double)min(x0 + tid, dw - 1);     // columns beyond the frame repeat the last one: their taps stay in the box
+        colAB[tid] = make_int2(sat_int(m[0] * xd * 1024.0), sat_int(m[3] * xd * 1024.0));
+    } else {
+        for (int r = tid - WT_W; r < rows_per_cta; r += WT_THREADS - WT_W) {      // rows past the frame are computed too, never stored
+            const int back = (r & 15) < 4 ? 20 : 4;
+            const double yd = (double)(ys + r), yp = (double)(ys + r - back);
+            const int Y0 = sat_int((m[4] * yd + m[5]) * 1024.0) + 16;
+            S_rowXY[r] = make_int2(sat_int((m[1] * yd + m[2]) * 1024.0) + 16, Y0);
+            const unsigned irr = __ballot_sync(0xFFFFFFFFu, Y0 - (sat_int((m[4] * yp + m[5]) * 1024.0) + 16) != 1024 * back);
+            if (lane == 0) {
+                unsigned steps = 0u;
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) steps |= ((irr >> (4 * s8)) & 0xFu) ? (1u << s8) : 0u;
+                S_misc[r >> 5] = (int)steps;
+            }
+        }
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(s_mbar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(s_mbar + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (dmaps) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(tmap) : "memory");
+    }
+    __syncthreads();
+    const int tw = min(WT_W, dw - x0);
+    const int2 cA = colAB[0], cB = colAB[tw - 1];
+    const bool col_ok = max(max(abs(cA.x), abs(cB.x)), max(abs(cA.y), abs(cB.y))) < (1 << 26);
+    // lane constants: quad q of segment seg; the lane walks rows 16 half + 4 t + j of every tile
+    const int seg = warp & 3, half = warp >> 2, q = lane & 7, j = lane >> 3;
+    const int c0 = 32 * seg + 4 * q;
+    const int npx = min(max(tw - c0, 0), 4);
+    const int cq = npx > 0 ? c0 : 32 * seg;                 // a quad wholly beyond the frame recomputes the segment's first quad (not stored)
+    const bool seg_on = 32 * seg < tw;
+    uint32_t adT0, dT3, M1, M2;
+    bool lane_bad;
+    {
+        const int2 k0 = colAB[cq], k1 = colAB[cq + 1], k2 = colAB[cq + 2], k3 = colAB[cq + 3];
+        adT0 = (uint32_t)k0.x * 16u;
+        // e_k - e_0 with e = adelta - 1024 x: all four equal, or one step of +-1 somewhere inside the quad
+        const int d1 = k1.x - k0.x - 1024, d2 = k2.x - k0.x - 2048, d3 = k3.x - k0.x - 3072;
+        lane_bad = !((d3 == 0 && d1 == 0 && d2 == 0) || ((d3 == 1 || d3 == -1) && (d1 == 0 || d1 == d3) && (d2 == d1 || d2 == d3)));
+        dT3 = (uint32_t)(d3 * 16);
+        M1 = (d1 != 0) ? 0xFFFFFFFFu : 0u;
+        M2 = (d2 != 0) ? 0xFFFFFFFFu : 0u;
+    }
+    const uint32_t s_bd = s_colAB + 8u * (uint32_t)cq;       // this quad's four (adelta, bdelta) entries
+
+    // source box of the tile starting at row y0 -> S_box[b]; issues its fetch into raw buffer b when the box fits
+    auto box_and_fetch = [&](int y0, int b) {
+        const int yb = min(y0 + WT_H, ye) - 1;
+        const int2 rA = S_rowXY[y0 - ys], rB = S_rowXY[yb - ys];
+        int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int2 cc = (c & 1) ? cB : cA, rr = (c & 2) ? rB : rA;
+            const int X = (rr.x + cc.x) >> 10, Y = (rr.y + cc.y) >> 10;
+            minx = min(minx, X); maxx = max(maxx, X); miny = min(miny, Y); maxy = max(maxy, Y);
+        }
+        const int rminx = minx - border, rmaxx = maxx - border, rminy = miny - border, rmaxy = maxy - border;
+        const bool inside = border == 0 || bmode == 0 || (rminx >= 0 && rmaxx + 1 < sw && rminy >= 0 && rmaxy + 1 < sh);
+        const int axT = rminx & ~15;                         // TMA box origin: 16 pixels = 48 bytes = 12 words
+        const int nrows = maxy + 2 - miny;
+        const bool row_ok = max(max(abs(rA.x), abs(rB.x)), max(abs(rA.y), abs(rB.y))) < (1 << 26);
+        const bool ok = col_ok && row_ok && inside && minx > -30000 && maxx < 30000 && miny > -30000 && maxy < 30000 &&
+                        rmaxx + 2 - axT <= WT_RAW_PITCH / 3 && nrows <= WT_ROWS && nrows > 0;
+        int* bx = S_box[b];
+        bx[0] = axT + border; bx[1] = miny; bx[4] = ok ? 1 : 0;        // box origin in the (bordered) coordinates the taps use
+        if (ok) {
+            const uint32_t mb = s_mbar + 8u * (uint32_t)b;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(WQ_BOXB) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         :: "r"(s_raw + (uint32_t)(b * WQ_RAWB)), "l"(tmap), "r"(mb), "r"(3 * (axT >> 2)), "r"(rminy), "r"(zc) : "memory");
+        }
+    };
+    if (tid == 0) {
+        box_and_fetch(ys, 0);
+        if (ys + WT_H < ye) box_and_fetch(ys + WT_H, 1);
+    }
+    __syncthreads();
+
+    // per-lane walk state, carried from step to step and from tile to tile
+    uint32_t rowp = s_rowXY + 8u * (uint32_t)(16 * half + j);                  // this lane's (X0, Y0) entry
+    // entries from rowp_endq on are rows past the frame (a quad beyond the frame's right edge stores nothing at all)
+    uint32_t rowp_endq = npx == 4 ? s_rowXY + 8u * (uint32_t)(ye - ys) : 0u;
+    asm volatile("" : "+r"(rowp_endq));                                        // (kept in a register, not re-derived every step)
+    const uint32_t rowp_endj = s_rowXY + 8u * (uint32_t)(ye - ys + j);         // the warp's step is inside the frame while rowp < rowp_endj
+    uint8_t* g = dst + (size_t)(ys + 16 * half + j) * dstride + (size_t)(x0 + c0) * 3;
+    const size_t gstep = 4 * dstride;
+    uint32_t Bk[4] = {0u, 0u, 0u, 0u}, rowA = 0u, smask = 0u;
+    bool ybad = true, anysplit = false, stale = true;        // stale: no vertical terms carried into the next tile
+    int oy_prev = 0;
+
+    int buf = 0;
+    uint32_t phase = 0;                                     // bit b: parity of raw buffer b's barrier
+    for (int y0 = ys; y0 < ye; y0 += WT_H, buf ^= 1) {
+        const int ox = S_box[buf][0], oy = S_box[buf][1];
+        const bool ok = S_box[buf][4] != 0;
+        const int yh = y0 + 16 * half;                       // first frame row of this warp's 16 rows
+        if (!ok) {
+            for (int i = tid; i < WT_W * WT_H; i += WT_THREADS) {
+                const int x = x0 + (i & (WT_W - 1)), y = y0 + i / WT_W;
+                if (x < dw && y < ye) {
+                    const uint8_t* sp = lanes_mode ? srcp.p[z] : src0 + (size_t)z * sframe;
+                    warp_pixel<BORDER>(sp, sw, sh, sstride, m, border, bmode, x, y, dst + (size_t)y * dstride + 3 * x);
+                }
+            }
+            stale = true;
+            rowp += 8u * WT_H;
+            g += 8 * gstep;
+        } else {
+            mbar_wait(s_mbar + 8u * (uint32_t)buf, (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+            if (seg_on && yh < ye) {
+                const uint32_t s_box = s_raw + (uint32_t)(buf * WQ_RAWB);
+                const uint32_t oy10 = (uint32_t)oy << 10, ox14 = (uint32_t)ox << 14;
+                const uint32_t kx = adT0 - ox14;
+                uint32_t irrbits = ((uint32_t)S_misc[(y0 - ys) >> 5] >> (4 * half)) | (stale ? 1u : 0u);   // bit t: derive the vertical terms at step t
+                // carried row address -> this tile's box (the regular step below adds the usual 4 rows)
+                rowA += (uint32_t)((buf ? WQ_RAWB : -WQ_RAWB) + (oy_prev - oy + 16) * WT_RAW_PITCH);
+                const uint32_t rowp_stop = min(rowp + 128u, rowp_endj);
+#pragma unroll 1
+                for (; rowp < rowp_stop; rowp += 32u, g += gstep, irrbits >>= 1) {
+                    const uint2 xy = lds64<0>(rowp);
+                    if (irrbits & 1u) {
+                        // vertical terms of the four columns: weights, source rows (bdelta is monotone in x, so the rows of
+                        // px 1, 2 lie between those of px 0 and px 3)
+                        uint32_t b0, b1, b2, b3, u0, u1, u2, u3;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u0), "=r"(b0), "=r"(u1), "=r"(b1) : "r"(s_bd));
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(u2), "=r"(b2), "=r"(u3), "=r"(b3) : "r"(s_bd));
+                        const uint32_t yb = xy.y - oy10;
+                        const uint32_t t20 = yb + b0, t21 = yb + b1, t22 = yb + b2, t23 = yb + b3;
+                        Bk[0] = t20 & 0x3E0u; Bk[1] = t21 & 0x3E0u; Bk[2] = t22 & 0x3E0u; Bk[3] = t23 & 0x3E0u;
+                        const uint32_t r0 = t20 >> 10, r3 = t23 >> 10, rb = min(r0, r3);
+                        smask = (r0 - rb) | (((t21 >> 10) - rb) << 1) | (((t22 >> 10) - rb) << 2) | ((r3 - rb) << 3);
+                        ybad = lane_bad || max(r0, r3) - rb > 1u;
+                        anysplit = __any_sync(0xFFFFFFFFu, r0 != r3);
+                        rowA = s_box + rb * (uint32_t)WT_RAW_PITCH;
+                    } else {
+                        rowA += 4u * (uint32_t)WT_RAW_PITCH;
+                    }
+                    // horizontal terms of px 0 and px 3 (px 1, 2 follow one of them: M1, M2)
+                    const uint32_t T0 = xy.x * 16u + kx, T3 = T0 + dT3;
+                    const uint32_t c = T0 >> 14, c3 = 3u * c;                      // px 0's column / byte in the box
+                    const uint32_t o = c3 & 3u;
+                    const uint32_t o0 = __shfl_sync(0xFFFFFFFFu, o, 0);
+                    const bool bad = ybad || (T3 >> 14) != c || o != o0;
+                    uint32_t px[4];
+                    if (!__any_sync(0xFFFFFFFFu, bad)) {
+                        const uint32_t a = rowA + (c3 & ~3u);
+                        const uint32_t W0 = (T0 & 0x3E00u) * 0xFFFFu + 16384u, W3 = (T3 & 0x3E00u) * 0xFFFFu + 16384u;
+                        const uint32_t W[4] = {W0, bitsel(W0, W3, M1), bitsel(W0, W3, M2), W3};
+                        if (!anysplit) {
+                            if (o0 < 2u) { if (o0 == 0u) quad_step<0>(a, W, Bk, px); else quad_step<1>(a, W, Bk, px); }
+                            else { if (o0 == 2u) quad_step<2>(a, W, Bk, px); else quad_step<3>(a, W, Bk, px); }
+                        } else {
+                            if (o0 < 2u) { if (o0 == 0u) quad_step_split<0>(a, W, Bk, smask, px); else quad_step_split<1>(a, W, Bk, smask, px); }
+                            else { if (o0 == 2u) quad_step_split<2>(a, W, Bk, smask, px); else quad_step_split<3>(a, W, Bk, smask, px); }
+                        }
+                    } else {
+                        // per-pixel path: the same integers, byte loads from the box
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int2 ck = colAB[cq + k];
+                            const uint32_t T1 = xy.x * 16u - ox14 + (uint32_t)ck.x * 16u;
+                            const uint32_t t2 = xy.y - oy10 + (uint32_t)ck.y;
+                            const uint32_t ab = s_box + (t2 >> 10) * (uint32_t)WT_RAW_PITCH + 3u * (T1 >> 14);
+                            const uint32_t ax = (T1 >> 9) & 31u, ay = (t2 >> 5) & 31u;
+                            const uint32_t w00 = (32u - ax) * (32u - ay), w01 = ax * (32u - ay), w10 = (32u - ax) * ay, w11 = ax * ay;
+                            uint32_t v = 0u;
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch) {
+                                const uint32_t acc = w00 * lds8(ab + ch) + w01 * lds8(ab + 3 + ch) +
+                                                     w10 * lds8(ab + WT_RAW_PITCH + ch) + w11 * lds8(ab + WT_RAW_PITCH + 3 + ch);
+                                v |= ((acc + 512u) >> 10) << (8 * ch);
+                            }
+                            px[k] = v;
+                        }
+                    }
+                    // three aligned words per quad, predicated on the row being inside the frame (and the quad inside its width)
+                    asm volatile("{\n.reg .pred p;\nsetp.lt.u32 p, %4, %5;\n@p st.global.u32 [%0], %1;\n@p st.global.u32 [%0+4], %2;\n@p st.global.u32 [%0+8], %3;\n}\n"
+                                 :: "l"(g), "r"(__byte_perm(px[0], px[1], 0x4210)), "r"(__byte_perm(px[1], px[2], 0x5421)),
+                                    "r"(__byte_perm(px[2], px[3], 0x6542)), "r"(rowp), "r"(rowp_endq) : "memory");
+                }
+                stale = false;
+                oy_prev = oy;
+                rowp += 8u * 16u;                            // on to the same rows of the next tile (a short last tile ends the strip)
+                g += 4 * gstep;
+            }
+        }
+        __syncthreads();                                   // every warp is done with raw buffer buf
+        if (tid == 0 && y0 + 2 * WT_H < ye) box_and_fetch(y0 + 2 * WT_H, buf);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Crop-and-zoom fused into the warp (Stabilizer.cpp:1056-1060 + :1108-1124): cv::warpAffine, the (b, b, W-2b, H-2b)
 // crop and cv::resize back to W x H, reading the source once and writing the output once.  One CTA walks a strip
 // of 120x30 OUTPUT tiles.  The resize taps of such a tile cover at most 122x32 pixels of the warped image (the
@@ -928,6 +1260,10 @@ static bool tma_encode_map(CUtensorMap* m, const uint8_t* base, int w, int h, si
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+static bool warp_v1() {
+    static const bool v = [] { const char* e = getenv("VS_WARP_V1"); return e && *e == '1'; }();
+    return v;
+}
 static bool tma_kernel_ready() {
     static int state[64] = {0};                   // per device: 0 unknown, 1 ready, -1 unavailable
     int dev = 0;
@@ -935,11 +1271,19 @@ static bool tma_kernel_ready() {
     if (state[dev] == 0) {
         cudaError_t e = cudaFuncSetAttribute(k_warp_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_TMA_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_TMA_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_quad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WQ_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_quad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WQ_SMEM);
         state[dev] = (e == cudaSuccess && tma_encode_fn()) ? 1 : -1;
         cudaGetLastError();
     }
     return state[dev] == 1;
 }
+
+#define WT_LAUNCH(QUAD, BORDER, ...)                                                            \
+    do {                                                                                        \
+        if (QUAD) k_warp_quad<BORDER><<<grid, WT_THREADS, WQ_SMEM, st>>>(__VA_ARGS__);           \
+        else k_warp_tma<BORDER><<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(__VA_ARGS__);             \
+    } while (0)
 
 static void launch_warp_plain(const LaneDev* lanes, int n_lanes, const PtrPack& src, const MutPtrPack& dst, const WarpGeom& g,
                               cudaStream_t st) {
@@ -950,7 +1294,8 @@ static void launch_warp_plain(const LaneDev* lanes, int n_lanes, const PtrPack& 
         tma = tma && tma_geometry_ok(src.p[i], g.src_w, g.src_stride, 0, 1);
     }
     if (tma) {
-        const int rows = strip_rows(g.out_w, g.out_h, n_lanes, WT_MAXT);
+        const bool quad = !warp_v1() && dv && g.out_w % 4 == 0;     // k_warp_quad writes packed quads with aligned 32-bit stores
+        const int rows = strip_rows(g.out_w, g.out_h, n_lanes, quad ? WQ_MAXT : WT_MAXT);
         dim3 grid((g.out_w + WT_W - 1) / WT_W, (g.out_h + rows - 1) / rows, n_lanes);
         TmapPack pack;
         CUtensorMap big[VS_MAX_GROUP];
@@ -963,13 +1308,11 @@ static void launch_warp_plain(const LaneDev* lanes, int n_lanes, const PtrPack& 
                 dmaps = (const CUtensorMap*)g.d_tmaps;
             }
             if (g.mode == 1 && g.border > 0)
-                k_warp_tma<true><<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, dmaps, 1, lanes, nullptr, src, nullptr, 0, g.src_stride,
-                                                                         g.src_w, g.src_h, dst, nullptr, 0, g.out_w, g.out_h, g.out_stride,
-                                                                         rows, dv ? 1 : 0, g.wp_slot, g.border, g.border_mode);
+                WT_LAUNCH(quad, true, pack, dmaps, 1, lanes, nullptr, src, nullptr, 0, g.src_stride, g.src_w, g.src_h, dst, nullptr, 0,
+                          g.out_w, g.out_h, g.out_stride, rows, dv ? 1 : 0, g.wp_slot, g.border, g.border_mode);
             else
-                k_warp_tma<false><<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, dmaps, 1, lanes, nullptr, src, nullptr, 0, g.src_stride,
-                                                                          g.src_w, g.src_h, dst, nullptr, 0, g.out_w, g.out_h, g.out_stride,
-                                                                          rows, dv ? 1 : 0, g.wp_slot, 0, 0);
+                WT_LAUNCH(quad, false, pack, dmaps, 1, lanes, nullptr, src, nullptr, 0, g.src_stride, g.src_w, g.src_h, dst, nullptr, 0,
+                          g.out_w, g.out_h, g.out_stride, rows, dv ? 1 : 0, g.wp_slot, 0, 0);
             return;
         }
     }
@@ -1082,18 +1425,19 @@ static bool launch_warp_matrices_border(const uint8_t* src, int sw, int sh, size
                                         const WarpParams* d_wp, int n_frames, int border, int bmode, cudaStream_t st) {
     const bool dv = vec_ok(dst, dstride, 4) && dframe % 4 == 0;
     if (!(tma_kernel_ready() && tma_geometry_ok(src, sw, sstride, sframe, n_frames))) return false;
-    const int rows = strip_rows(dw, dh, n_frames, WT_MAXT);
+    const bool quad = !warp_v1() && dv && dw % 4 == 0;
+    const int rows = strip_rows(dw, dh, n_frames, quad ? WQ_MAXT : WT_MAXT);
     dim3 grid((dw + WT_W - 1) / WT_W, (dh + rows - 1) / rows, n_frames);
     TmapPack pack;
     if (!tma_make_map(pack.m, src, sw, sh, sstride, sframe, n_frames)) return false;
     PtrPack sp{};
     MutPtrPack dp{};
     if (border > 0)
-        k_warp_tma<true><<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, nullptr, 0, nullptr, d_wp, sp, src, sframe, sstride, sw, sh, dp,
-                                                                 dst, dframe, dw, dh, dstride, rows, dv ? 1 : 0, 0, border, bmode);
+        WT_LAUNCH(quad, true, pack, nullptr, 0, nullptr, d_wp, sp, src, sframe, sstride, sw, sh, dp, dst, dframe, dw, dh, dstride, rows,
+                  dv ? 1 : 0, 0, border, bmode);
     else
-        k_warp_tma<false><<<grid, WT_THREADS, WT_TMA_SMEM, st>>>(pack, nullptr, 0, nullptr, d_wp, sp, src, sframe, sstride, sw, sh, dp,
-                                                                  dst, dframe, dw, dh, dstride, rows, dv ? 1 : 0, 0, 0, 0);
+        WT_LAUNCH(quad, false, pack, nullptr, 0, nullptr, d_wp, sp, src, sframe, sstride, sw, sh, dp, dst, dframe, dw, dh, dstride, rows,
+                  dv ? 1 : 0, 0, 0, 0);
     return true;
 }
 
