@@ -763,7 +763,8 @@ k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict
         M1 = (d1 != 0) ? 0xFFFFFFFFu : 0u;
         M2 = (d2 != 0) ? 0xFFFFFFFFu : 0u;
     }
-    const uint32_t s_bd = s_colAB + 8u * (uint32_t)cq;       // this quad's four (adelta, bdelta) entries
+    uint32_t s_bd = s_colAB + 8u * (uint32_t)cq;             // this quad's four (adelta, bdelta) entries
+    asm volatile("" : "+r"(s_bd), "+r"(adT0), "+r"(dT3), "+r"(M1), "+r"(M2));
 
     // source box of the tile starting at row y0 -> S_box[b]; issues its fetch into raw buffer b when the box fits
     auto box_and_fetch = [&](int y0, int b) {
@@ -803,7 +804,8 @@ k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict
     // entries from rowp_endq on are rows past the frame (a quad beyond the frame's right edge stores nothing at all)
     uint32_t rowp_endq = npx == 4 ? s_rowXY + 8u * (uint32_t)(ye - ys) : 0u;
     asm volatile("" : "+r"(rowp_endq));                                        // (kept in a register, not re-derived every step)
-    const uint32_t rowp_endj = s_rowXY + 8u * (uint32_t)(ye - ys + j);         // the warp's step is inside the frame while rowp < rowp_endj
+    uint32_t rowp_endj = s_rowXY + 8u * (uint32_t)(ye - ys + j);               // the warp's step is inside the frame while rowp < rowp_endj
+    asm volatile("" : "+r"(rowp_endj));
     uint8_t* g = dst + (size_t)(ys + 16 * half + j) * dstride + (size_t)(x0 + c0) * 3;
     const size_t gstep = 4 * dstride;
     uint32_t Bk[4] = {0u, 0u, 0u, 0u}, rowA = 0u, smask = 0u;
@@ -815,7 +817,6 @@ k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict
     for (int y0 = ys; y0 < ye; y0 += WT_H, buf ^= 1) {
         const int ox = S_box[buf][0], oy = S_box[buf][1];
         const bool ok = S_box[buf][4] != 0;
-        const int yh = y0 + 16 * half;                       // first frame row of this warp's 16 rows
         if (!ok) {
             for (int i = tid; i < WT_W * WT_H; i += WT_THREADS) {
                 const int x = x0 + (i & (WT_W - 1)), y = y0 + i / WT_W;
@@ -830,10 +831,9 @@ k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict
         } else {
             mbar_wait(s_mbar + 8u * (uint32_t)buf, (phase >> buf) & 1u);
             phase ^= 1u << buf;
-            if (seg_on && yh < ye) {
+            if (seg_on) {                                    // (a warp whose 16 rows lie past the frame finds rowp >= rowp_stop below)
                 const uint32_t s_box = s_raw + (uint32_t)(buf * WQ_RAWB);
-                const uint32_t oy10 = (uint32_t)oy << 10, ox14 = (uint32_t)ox << 14;
-                const uint32_t kx = adT0 - ox14;
+                const uint32_t kx = adT0 - ((uint32_t)ox << 14);
                 uint32_t irrbits = ((uint32_t)S_misc[(y0 - ys) >> 5] >> (4 * half)) | (stale ? 1u : 0u);   // bit t: derive the vertical terms at step t
                 // carried row address -> this tile's box (the regular step below adds the usual 4 rows)
                 rowA += (uint32_t)((buf ? WQ_RAWB : -WQ_RAWB) + (oy_prev - oy + 16) * WT_RAW_PITCH);
@@ -847,7 +847,7 @@ k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict
                         uint32_t b0, b1, b2, b3, u0, u1, u2, u3;
                         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u0), "=r"(b0), "=r"(u1), "=r"(b1) : "r"(s_bd));
                         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(u2), "=r"(b2), "=r"(u3), "=r"(b3) : "r"(s_bd));
-                        const uint32_t yb = xy.y - oy10;
+                        const uint32_t yb = xy.y - ((uint32_t)oy << 10);
                         const uint32_t t20 = yb + b0, t21 = yb + b1, t22 = yb + b2, t23 = yb + b3;
                         Bk[0] = t20 & 0x3E0u; Bk[1] = t21 & 0x3E0u; Bk[2] = t22 & 0x3E0u; Bk[3] = t23 & 0x3E0u;
                         const uint32_t r0 = t20 >> 10, r3 = t23 >> 10, rb = min(r0, r3);
@@ -881,8 +881,8 @@ k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const int2 ck = colAB[cq + k];
-                            const uint32_t T1 = xy.x * 16u - ox14 + (uint32_t)ck.x * 16u;
-                            const uint32_t t2 = xy.y - oy10 + (uint32_t)ck.y;
+                            const uint32_t T1 = xy.x * 16u - ((uint32_t)ox << 14) + (uint32_t)ck.x * 16u;
+                            const uint32_t t2 = xy.y - ((uint32_t)oy << 10) + (uint32_t)ck.y;
                             const uint32_t ab = s_box + (t2 >> 10) * (uint32_t)WT_RAW_PITCH + 3u * (T1 >> 14);
                             const uint32_t ax = (T1 >> 9) & 31u, ay = (t2 >> 5) & 31u;
                             const uint32_t w00 = (32u - ax) * (32u - ay), w01 = ax * (32u - ay), w10 = (32u - ax) * ay, w11 = ax * ay;
