@@ -644,16 +644,16 @@ static __device__ __forceinline__ uint32_t quad_pixel(const uint32_t (&wt)[5], c
 
 // four adjacent pixels from the five words of each of the two source rows at shared address a (byte phase O)
 template <int O>
-static __device__ __forceinline__ void quad_step(uint32_t a, const uint32_t (&W)[4], const uint32_t (&B)[4], uint32_t (&px)[4]) {
+static __device__ __forceinline__ void quad_step(uint32_t a, const uint32_t (&W)[4], const uint32_t (&B)[4], const uint32_t (&Bc)[4], uint32_t (&px)[4]) {
     uint32_t wt[5], wb[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) wt[i] = lds32v<0>(a + 4u * i);
 #pragma unroll
     for (int i = 0; i < 5; ++i) wb[i] = lds32v<0>(a + (uint32_t)WT_RAW_PITCH + 4u * i);
-    px[0] = quad_pixel<O + 0>(wt, wb, W[0], B[0], 1024u - B[0]);
-    px[1] = quad_pixel<O + 3>(wt, wb, W[1], B[1], 1024u - B[1]);
-    px[2] = quad_pixel<O + 6>(wt, wb, W[2], B[2], 1024u - B[2]);
-    px[3] = quad_pixel<O + 9>(wt, wb, W[3], B[3], 1024u - B[3]);
+    px[0] = quad_pixel<O + 0>(wt, wb, W[0], B[0], Bc[0]);
+    px[1] = quad_pixel<O + 3>(wt, wb, W[1], B[1], Bc[1]);
+    px[2] = quad_pixel<O + 6>(wt, wb, W[2], B[2], Bc[2]);
+    px[3] = quad_pixel<O + 9>(wt, wb, W[3], B[3], Bc[3]);
 }
 
 // A quad that straddles a change of source row (px 0..k-1 read rows R, R+1; px k..3 read rows R+1, R+2, or the other way
@@ -808,7 +808,7 @@ k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict
     asm volatile("" : "+r"(rowp_endj));
     uint8_t* g = dst + (size_t)(ys + 16 * half + j) * dstride + (size_t)(x0 + c0) * 3;
     const size_t gstep = 4 * dstride;
-    uint32_t Bk[4] = {0u, 0u, 0u, 0u}, rowA = 0u, smask = 0u;
+    uint32_t Bk[4] = {0u, 0u, 0u, 0u}, Bck[4] = {0u, 0u, 0u, 0u}, rowA = 0u, smask = 0u;
     bool ybad = true, anysplit = false, stale = true;        // stale: no vertical terms carried into the next tile
     int oy_prev = 0;
 
@@ -850,6 +850,7 @@ k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict
                         const uint32_t yb = xy.y - ((uint32_t)oy << 10);
                         const uint32_t t20 = yb + b0, t21 = yb + b1, t22 = yb + b2, t23 = yb + b3;
                         Bk[0] = t20 & 0x3E0u; Bk[1] = t21 & 0x3E0u; Bk[2] = t22 & 0x3E0u; Bk[3] = t23 & 0x3E0u;
+                        Bck[0] = 1024u - Bk[0]; Bck[1] = 1024u - Bk[1]; Bck[2] = 1024u - Bk[2]; Bck[3] = 1024u - Bk[3];
                         const uint32_t r0 = t20 >> 10, r3 = t23 >> 10, rb = min(r0, r3);
                         smask = (r0 - rb) | (((t21 >> 10) - rb) << 1) | (((t22 >> 10) - rb) << 2) | ((r3 - rb) << 3);
                         ybad = lane_bad || max(r0, r3) - rb > 1u;
@@ -870,8 +871,8 @@ k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict
                         const uint32_t W0 = (T0 & 0x3E00u) * 0xFFFFu + 16384u, W3 = (T3 & 0x3E00u) * 0xFFFFu + 16384u;
                         const uint32_t W[4] = {W0, bitsel(W0, W3, M1), bitsel(W0, W3, M2), W3};
                         if (!anysplit) {
-                            if (o0 < 2u) { if (o0 == 0u) quad_step<0>(a, W, Bk, px); else quad_step<1>(a, W, Bk, px); }
-                            else { if (o0 == 2u) quad_step<2>(a, W, Bk, px); else quad_step<3>(a, W, Bk, px); }
+                            if (o0 < 2u) { if (o0 == 0u) quad_step<0>(a, W, Bk, Bck, px); else quad_step<1>(a, W, Bk, Bck, px); }
+                            else { if (o0 == 2u) quad_step<2>(a, W, Bk, Bck, px); else quad_step<3>(a, W, Bk, Bck, px); }
                         } else {
                             if (o0 < 2u) { if (o0 == 0u) quad_step_split<0>(a, W, Bk, smask, px); else quad_step_split<1>(a, W, Bk, smask, px); }
                             else { if (o0 == 2u) quad_step_split<2>(a, W, Bk, smask, px); else quad_step_split<3>(a, W, Bk, smask, px); }
