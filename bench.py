@@ -646,7 +646,7 @@ def run_gpu(args, rank, world, local_rank):
         alg_bytes = 2 * 3 * W * H * WARP_BATCH
         peak, peak_src = _peaks()
         achieved = alg_bytes / (warp_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_warp_tma (cv::warpAffine, 64 frames per launch, timed alone; 796 MB per launch > L2)",
+        roof = {"bound": "hbm", "kernel": "k_warp_quad (cv::warpAffine, 64 frames per launch, timed alone; 796 MB per launch > L2)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": warp_ms,
                 "frac_of_nominal_8000": achieved / 8000.0}

@@ -592,8 +592,9 @@ k_warp_tma(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict_
 //     between neighbouring pixels, and the 12 packed output bytes leave as three 32-bit stores straight from registers;
 //   * a warp covers 8 quads x 4 consecutive rows per step: raw word index 3 q + 120 row takes 32 distinct banks
 //     (120 = 24 mod 32), so the ten tap loads of a step are conflict free without any padding.
-// Per step (4 pixels per lane): 10 LDS + 16 PRMT + 24 IDP.2A + 24 IMAD + 8 PRMT (pack) + 3 PRMT + 3 STG + ~25 for the
-// coordinates, against 4 x 36 in k_warp_tma, and 2.5 + 0.75 shared-memory / store wavefronts per 32 pixels against 6 + 3.4.
+// Per step (4 pixels per lane): 10 LDS + 16 PRMT + 24 IDP.2A + 24 IMAD + 8 PRMT (pack) + 3 PRMT + 3 STG + ~45 for the
+// coordinates, votes and loop, against 4 x 36 in k_warp_tma plus its re-pack; measured 42.1 warp-instructions and 4.3
+// shared-memory wavefronts per 32 output pixels against 48.7 and 11.1 (profiles/r02_b_warp_ncu.json).
 // The vertical terms are lane constants while Y0 advances by exactly 4096 per 4 rows (checked per step, recomputed when
 // not).  Exactness: every coordinate is the integer cv::warpAffine computes (X0(y) + adelta(x), Y0(y) + bdelta(x)); the
 // quad path only requires what it then uses - px 0 and px 3 give consecutive sx (so the five words are the taps of all
