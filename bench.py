@@ -443,9 +443,14 @@ def run_gpu(args, rank, world, local_rank):
         out4 = torch.empty((S, C4_FRAMES, H, W, 3), dtype=torch.uint8, device=dev)
         torch.cuda.synchronize()
         # The rank's streams advance in lock-step GROUPS, one StabilizerBatch (one launch per stage) per group.  With few streams per
-        # GPU (N = 8: eight) two groups of four interleaved from the one host thread keep the SMs busier than one group of eight
-        # (profiles/tools/batch_groups.py: 84.7 k -> 90.2 k frames/s on one GPU); from 16 streams per GPU up one group is as good.
+        # GPU (N = 8: eight) two groups of four keep the SMs busier than one group of eight (profiles/tools/batch_groups.py:
+        # 84.7 k -> 90.2 k frames/s on one GPU, both groups fed from one host thread); the host's enqueue time per lock-step
+        # frame (32 - 42 us) is then the limit, so each group gets its own host thread (VS_C4_GROUPS overrides the count).
         n_groups = 2 if (S <= 8 and S % 2 == 0 and S >= 4) else 1
+        if os.environ.get("VS_C4_GROUPS"):
+            n_groups = max(1, min(S, int(os.environ["VS_C4_GROUPS"])))
+            while S % n_groups:
+                n_groups -= 1
         per = S // n_groups
         groups = []
         for g in range(n_groups):
@@ -458,14 +463,30 @@ def run_gpu(args, rank, world, local_rank):
         ext4 = torch.cuda.ExternalStream(groups[0][0].stream, device=dev)
         pos4 = 0
 
-        def step4():
-            nonlocal pos4
-            for k in range(C4_FRAMES):
-                for sbg, in_tab, out_tab in groups:
-                    rc = lib.vs_batch_push_device(sbg._h, in_tab[pos4 % len(loop)], W, H, W * 3, out_tab[k], W * 3, frame_bytes, 1,
-                                                  C.byref(ow), C.byref(oh), C.byref(produced))
+        def push_group(gi, first_pos, nsteps):
+            # one host thread per lock-step group: handles are independent, the C call releases the GIL
+            sbg, in_tab, out_tab = groups[gi]
+            o_w, o_h, prod = C.c_int(), C.c_int(), C.c_int()
+            p = first_pos
+            for _ in range(nsteps):
+                for k in range(C4_FRAMES):
+                    rc = lib.vs_batch_push_device(sbg._h, in_tab[p % len(loop)], W, H, W * 3, out_tab[k], W * 3, frame_bytes, 1,
+                                                  C.byref(o_w), C.byref(o_h), C.byref(prod))
                     assert rc == 0, lib.vs_last_error()
-                pos4 += 1
+                    p += 1
+
+        def run4(nsteps):
+            nonlocal pos4
+            if n_groups == 1:
+                push_group(0, pos4, nsteps)
+            else:
+                import threading
+                th = [threading.Thread(target=push_group, args=(gi, pos4, nsteps)) for gi in range(n_groups)]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+            pos4 += nsteps * C4_FRAMES
 
         def join4():
             # every group's work ordered before the timing event on the first group's public stream
@@ -476,8 +497,7 @@ def run_gpu(args, rank, world, local_rank):
                 evj.record(torch.cuda.ExternalStream(sbg.stream, device=dev))
                 ext4.wait_event(evj)
 
-        for _ in range(max(args.warmup, 3)):
-            step4()
+        run4(max(args.warmup, 3))
         for sbg, _, _ in groups:
             sbg.sync()
         barrier()
@@ -487,8 +507,7 @@ def run_gpu(args, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         join4()
         e0.record(ext4)
-        for _ in range(args.steps):
-            step4()
+        run4(args.steps)
         join4()
         e1.record(ext4)
         for sbg, _, _ in groups:
@@ -747,6 +766,11 @@ def run_gpu(args, rank, world, local_rank):
     if "config5" in parts:
         n_total, chunks = args.clip_frames, max(C5_CHUNKS, world)
         chunks -= chunks % world
+        # lock-step analysis: as many equal, even-length chunks per rank as the clip divides into (<= 64): they advance together,
+        # one launch per stage for all of them (VS_C5_LOCKSTEP=0: the chunk-by-chunk, frame-by-frame analysis of round 1)
+        cpr = offline.lockstep_chunking(n_total, world) if os.environ.get("VS_C5_LOCKSTEP", "1") != "0" else None
+        if cpr:
+            chunks = world * cpr
         per_rank = chunks // world
         mine = list(range(rank * per_rank, (rank + 1) * per_rank))
         need = sum(offline.chunk_bounds(n_total, chunks, c)[1] + 2 for c in mine) * frame_bytes
@@ -755,6 +779,11 @@ def run_gpu(args, rank, world, local_rank):
         ok_mem, = allmax(0.0 if need + ring_frames * frame_bytes + (12 << 30) < free else 1.0)
         if ok_mem != 0.0:                                  # never drive the box out of memory: fall back to a shorter clip
             n_total = 4096
+            if cpr:
+                cpr = offline.lockstep_chunking(n_total, world)
+                chunks = world * cpr if cpr else chunks
+                per_rank = chunks // world
+                mine = list(range(rank * per_rank, (rank + 1) * per_rank))
             ring_frames = max(offline.chunk_bounds(n_total, chunks, c)[1] for c in mine)
         gen = synthclip.DeviceClip(W, H, n_total, 5000, dev)
         chunk_frames = {}
@@ -764,17 +793,19 @@ def run_gpu(args, rank, world, local_rank):
                 chunk_frames[c] = gen.frames(first - offline.halo(first), first + count)
         out_ring = torch.empty((ring_frames, H, W, 3), dtype=torch.uint8, device=dev)
         st5 = vsb.Stabilizer(params, device=local_rank)
+        n_lock = sum(1 for c in mine if offline.chunk_bounds(n_total, chunks, c)[0] >= 4) if cpr else 0
+        sb5 = vsb.StabilizerBatch(params, n_lock, device=local_rank) if n_lock >= 2 else None
         ext5 = torch.cuda.ExternalStream(st5.stream, device=dev)
         torch.cuda.synchronize()
         full = None
         times = []
         for it in range(3):                                # one warm-up pass, two timed passes (max over ranks of each)
             barrier()
-            l0 = st5.launch_count()
+            l0 = st5.launch_count() + (sb5.launch_count() if sb5 else 0)
             t0 = torch.cuda.Event(enable_timing=True)
             t1 = torch.cuda.Event(enable_timing=True)
             t0.record(torch.cuda.current_stream(dev))
-            full = offline.stabilize_rank_chunks(st5, chunk_frames, n_total, chunks, mine, out_ring)
+            full = offline.stabilize_rank_chunks(st5, chunk_frames, n_total, chunks, mine, out_ring, batch=sb5)
             st5.join()
             tail = torch.cuda.Event()
             tail.record(ext5)
@@ -785,7 +816,7 @@ def run_gpu(args, rank, world, local_rank):
             barrier()
             if it:
                 times.append(allmax(t0.elapsed_time(t1))[0])
-            l5 = st5.launch_count() - l0
+            l5 = st5.launch_count() + (sb5.launch_count() if sb5 else 0) - l0
         # bit-equality with ONE handle streaming the whole clip (rank 0; blocks generated on the fly)
         equal = None
         if rank == 0:
@@ -814,9 +845,11 @@ def run_gpu(args, rank, world, local_rank):
                              "bytes_per_rank": int(per_rank * offline.stitch_index(n_total, chunks)[0] * 12),
                              "payload": "per-chunk transforms, 12 bytes per frame, device to device"},
               "transforms_bit_equal_to_single_handle_stream": equal,
-              "what": "analyse own chunks -> one all-gather of the transforms -> rebuild path in the reference's float32 order -> smooth + warp own "
-                      "frames; inputs resident in HBM, outputs into a device ring of one chunk"}
-        del st5, chunk_frames, out_ring, gen
+              "lockstep_lanes_per_gpu": n_lock if sb5 else 0,
+              "what": "analyse own chunks (in lock-step: one launch per stage for all of a rank's chunks; the clip's first chunk frame by "
+                      "frame) -> one all-gather of the transforms -> rebuild path in the reference's float32 order once -> smooth + warp "
+                      "own frames chunk by chunk; inputs resident in HBM, outputs into a device ring of one chunk"}
+        del st5, sb5, chunk_frames, out_ring, gen
         torch.cuda.empty_cache()
 
     if rank == 0:

@@ -243,6 +243,11 @@ vs_status vs_clip_analyze_device(vs_stabilizer* s, const uint8_t* d_frames, int 
                                  float* d_transforms_out, int* n_out);
 vs_status vs_clip_render_device(vs_stabilizer* s, const float* d_all_transforms, int n_total, const uint8_t* d_frames,
                                 int width, int height, int first, int count, uint8_t* d_out, int* out_width, int* out_height);
+/* vs_clip_render_device in two steps, for a rank that renders several chunks of the same clip: the transform list is
+ * installed (and the float32 trajectory rebuilt in the reference's order) ONCE, then each chunk is smoothed and warped. */
+vs_status vs_clip_set_transforms_device(vs_stabilizer* s, const float* d_all_transforms, int n_total, int width, int height);
+vs_status vs_clip_render_prepared_device(vs_stabilizer* s, const uint8_t* d_frames, int width, int height, int first, int count,
+                                         uint8_t* d_out, int* out_width, int* out_height);
 
 /* ---- roll correction ------------------------------------------------------------
  * Replaces vs::RollCorrection::autoCorrectRoll(input, params) (reference include/video/RollCorrection.h:16-51,
@@ -317,6 +322,16 @@ vs_status vs_batch_push_device(vs_batch* b, const uint8_t* const* d_frames, int 
                                int* out_width, int* out_height, int* produced);
 vs_status vs_batch_flush_device(vs_batch* b, uint8_t* const* d_outs, size_t out_stride, size_t out_capacity,
                                 int* out_width, int* out_height, int* produced);
+/* Offline clip mode, lock-step: the batch's n_streams lanes analyse n_streams temporal chunks of a long clip at once (one
+ * launch per stage for all of them instead of one per frame and chunk).  Lane l analyses `count` frames starting at an EVEN
+ * clip frame number first_l >= 4; d_frames[l] points at frame first_l - 2 (the two-frame halo of vs_clip_halo), tight rows,
+ * count + 2 frames.  d_transforms_out[l] (device memory) receives the `count` transforms of generateTransform calls
+ * first_l .. first_l + count - 1, bit-identical to vs_clip_analyze_device on the same chunk (motion estimation is
+ * pairwise-local, Stabilizer.cpp:594-678: only the parity of the chunk start matters).  Asynchronous on the batch's stream. */
+vs_status vs_batch_clip_analyze_device(vs_batch* b, const uint8_t* const* d_frames, int width, int height, int count,
+                                       float* const* d_transforms_out);
+/* as vs_stabilizer_wait_event: everything pushed after this call waits (on the device) for `cuda_event` */
+vs_status vs_batch_wait_event(vs_batch* b, void* cuda_event);
 vs_status vs_batch_sync(vs_batch* b);
 vs_status vs_batch_join(vs_batch* b);
 void*     vs_batch_stream(vs_batch* b);

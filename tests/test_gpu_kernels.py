@@ -76,6 +76,26 @@ def test_warp_affine_general_matrices(vsb, cv2_noopt, w, h):
         assert np.array_equal(out[i], ref), f"matrix {i} {T[i].tolist()}: max diff {np.abs(out[i].astype(int) - ref).max()}"
 
 
+@pytest.mark.parametrize("w,h,n", [(1920, 1080, 24), (1284, 722, 12), (256, 301, 12), (3840, 2160, 3)])
+def test_warp_quad_paths_small_angles(vsb, cv2_noopt, w, h, n):
+    """k_warp_quad (four adjacent pixels per lane, taps straight from the raw TMA box): a sweep over the angles a stabiliser
+    applies (1e-4 .. 0.06 rad, both signs, scales a hair off 1) with sub-pixel shifts, on sizes whose last tile is short and
+    on batches long enough for 8-tile strips.  Exercises all four byte phases, quads with an adelta step inside, quads that
+    straddle a change of source row, steps where Y0 does not advance by 1024 per row, and the per-pixel step path."""
+    cv2 = cv2_noopt
+    rng = np.random.default_rng(w * 7 + h)
+    f = _tex(vsb, w, h, 91)
+    angs = np.concatenate([np.geomspace(1e-4, 0.06, n - 2), [0.0, 0.0035]]) * rng.choice([-1.0, 1.0], n)
+    T = np.zeros((n, 2, 3), np.float32)
+    for i, a in enumerate(angs):
+        sc = 1.0 + (rng.normal(0, 2e-4) if i % 3 == 0 else 0.0)
+        T[i] = [[np.cos(a) * sc, -np.sin(a) * sc, rng.normal(0, 6)], [np.sin(a) * sc, np.cos(a) * sc, rng.normal(0, 6)]]
+    out = vsb.kernels.warp_affine(_dev(np.broadcast_to(f, (n,) + f.shape)), T).cpu().numpy()
+    for i in range(n):
+        ref = cv2.warpAffine(f, T[i], (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+        assert np.array_equal(out[i], ref), f"matrix {i} {T[i].tolist()}: max diff {np.abs(out[i].astype(int) - ref).max()}"
+
+
 def test_warp_affine_unaligned_views(vsb, cv2_noopt):
     """Source / destination views whose base address or row stride is not 4-byte aligned (ROI of a larger frame)."""
     cv2 = cv2_noopt

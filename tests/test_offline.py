@@ -94,6 +94,78 @@ def test_chunked_clip_equals_streamed(kw):
             assert np.array_equal(g[i, :oh, :ow], outs[i]), f"{chunks} chunks: frame {i} differs"
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,n,world", [(640, 360, 480, 1), (1280, 720, 960, 2)])
+def test_lockstep_chunk_analysis_equals_streamed(w, h, n, world):
+    """The lock-step analysis (vs_batch_clip_analyze_device: all of a rank's chunks advance together, one launch per stage)
+    and the prepared render (vs_clip_set_transforms_device once, vs_clip_render_prepared_device per chunk) against the
+    streamed stabilize() + flush() of the whole clip: transforms bit for bit, every output frame equal.  `world` ranks are
+    played one after the other on this GPU (rank 0 owns the clip's first chunk, which goes frame by frame)."""
+    import torch
+    import video_stab_b200 as vsb
+    from video_stab_b200 import offline
+    dev = torch.device("cuda", 0)
+    gen = synthclip.DeviceClip(w, h, n, 777, dev)
+    clip = gen.frames(0, n)
+    params = vsb.Parameters(smoothingRadius=9)
+    fb = h * w * 3
+    st = vsb.Stabilizer(params)
+    ring = torch.empty((n + 1, h, w, 3), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    k = st.push_many_device(clip.data_ptr(), fb, n, w, h, w * 3, ring.data_ptr(), w * 3, fb, borrow=False)
+    while st.flush_device(ring[k].data_ptr(), w * 3, fb) is not None:
+        k += 1
+    st.sync()
+    assert k == n
+    ref_tr = np.array([list(st.frame_record(i).transform) for i in range(n - 1)], np.float32)
+    del st
+
+    import ctypes as C
+    cpr = offline.lockstep_chunking(n, world, max_lanes=12, min_frames=20)
+    assert cpr is not None
+    chunks = world * cpr
+    per, idx = offline.stitch_index(n, chunks)
+
+    def chunk_tensor(c):
+        first, count = offline.chunk_bounds(n, chunks, c)
+        return clip[first - offline.halo(first): first + count]
+
+    if world == 1:
+        mine = list(range(chunks))
+        frames = {c: chunk_tensor(c) for c in mine}
+        st = vsb.Stabilizer(params)
+        sb = vsb.StabilizerBatch(params, chunks - 1)                  # every chunk but the clip's first advances in lock-step
+        out = torch.zeros((per, h, w, 3), dtype=torch.uint8, device=dev)
+        full = offline.stabilize_rank_chunks(st, frames, n, chunks, mine, out, batch=sb)
+        st.sync(); sb.sync(); torch.cuda.synchronize()
+        assert np.array_equal(full.cpu().numpy().view(np.uint32), ref_tr.view(np.uint32)), "lock-step transforms differ from streamed"
+        last_first, last_count = offline.chunk_bounds(n, chunks, chunks - 1)
+        assert torch.equal(out[:last_count], ring[last_first:last_first + last_count]), "last chunk: frames differ"
+        # every chunk rendered against the installed transform list equals the streamed output
+        ow, oh = C.c_int(), C.c_int()
+        for c in mine:
+            first, count = offline.chunk_bounds(n, chunks, c)
+            offline.check(offline.lib.vs_clip_render_prepared_device(st._h, clip[first].data_ptr(), w, h, first, count,
+                                                                     out.data_ptr(), C.byref(ow), C.byref(oh)))
+            st.sync()
+            assert torch.equal(out[:count], ring[first:first + count]), f"chunk {c}: frames differ"
+    else:
+        # `world` ranks played in turn: each rank's lock-step rows must equal the streamed transforms of its frames
+        for rank in range(world):
+            mine = [c for c in range(rank * cpr, (rank + 1) * cpr) if offline.chunk_bounds(n, chunks, c)[0] >= 4]
+            frames = {c: chunk_tensor(c) for c in mine}
+            sb = vsb.StabilizerBatch(params, len(mine))
+            local = torch.zeros((len(mine) * per, 3), dtype=torch.float32, device=dev)
+            torch.cuda.synchronize()
+            sb.clip_analyze_device([frames[c].data_ptr() for c in mine], w, h, per, [local[k * per].data_ptr() for k in range(len(mine))])
+            sb.sync()
+            loc = local.cpu().numpy()
+            for k, c in enumerate(mine):
+                first, count = offline.chunk_bounds(n, chunks, c)
+                assert np.array_equal(loc[k * per: k * per + count].view(np.uint32), ref_tr[first - 1:first + count - 1].view(np.uint32)), \
+                    f"rank {rank} chunk {c}: lock-step transforms differ"
+
+
 def _synthetic_long_clip(torch, w, h, n, seed, dev):
     """n frames generated on the device from the seed (synthclip.DeviceClip); returns frames(a, b)."""
     return synthclip.DeviceClip(w, h, n, seed, dev).frames

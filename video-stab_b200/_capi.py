@@ -95,6 +95,8 @@ SYMBOLS = {
     "vs_clip_analyze": (_I, [_P, _U8P, _I, _I, _I, _I, _P, _IP]),
     "vs_clip_render": (_I, [_P, _P, _I, _U8P, _I, _I, _I, _I, _U8P, _IP, _IP]),
     "vs_clip_analyze_device": (_I, [_P, _U8P, _I, _I, _I, _I, _P, _IP]),
+    "vs_clip_set_transforms_device": (_I, [_P, _P, _I, _I, _I]),
+    "vs_clip_render_prepared_device": (_I, [_P, _U8P, _I, _I, _I, _I, _U8P, _IP, _IP]),
     "vs_clip_render_device": (_I, [_P, _P, _I, _U8P, _I, _I, _I, _I, _U8P, _IP, _IP]),
     "vs_roll_params_default": (_I, [C.POINTER(VsRollParams)]),
     "vs_roll_params_from_yaml": (_I, [C.c_char_p, C.POINTER(VsRollParams)]),
@@ -119,6 +121,8 @@ SYMBOLS = {
     "vs_batch_build_levels": (_I, [_P, C.POINTER(_P), _I, _I, _SZ, _I]),
     "vs_batch_sync": (_I, [_P]),
     "vs_batch_join": (_I, [_P]),
+    "vs_batch_wait_event": (_I, [_P, _P]),
+    "vs_batch_clip_analyze_device": (_I, [_P, C.POINTER(_P), _I, _I, _I, C.POINTER(_P)]),
     "vs_batch_stream": (_P, [_P]),
     "vs_batch_launch_count": (_I, [_P, C.POINTER(C.c_uint64)]),
     "vs_batch_stream_counts": (_I, [_P, _I, _IP, _IP]),

@@ -335,6 +335,17 @@ vs_status vs_batch_flush_device(vs_batch* b, uint8_t* const* d_outs, size_t out_
     return b->eng->flush(d_outs, out_stride, out_capacity, false, out_width, out_height, produced);
     API_END
 }
+vs_status vs_batch_clip_analyze_device(vs_batch* b, const uint8_t* const* d_frames, int width, int height, int count,
+                                       float* const* d_transforms_out) {
+    if (!b || !d_frames || !d_transforms_out) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    return b->eng->analyze_chunks_lockstep(d_frames, width, height, count, d_transforms_out);
+    API_END
+}
+vs_status vs_batch_wait_event(vs_batch* b, void* cuda_event) {
+    if (!b || !cuda_event) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    return b->eng->wait_external((cudaEvent_t)cuda_event);
+}
 vs_status vs_batch_sync(vs_batch* b) { return b ? b->eng->sync() : vs_set_error(VS_ERR_INVALID_ARG, "null handle"); }
 vs_status vs_batch_join(vs_batch* b) { return b ? b->eng->join() : vs_set_error(VS_ERR_INVALID_ARG, "null handle"); }
 void* vs_batch_stream(vs_batch* b) { return b ? (void*)b->eng->stream() : nullptr; }
@@ -395,6 +406,19 @@ vs_status vs_clip_render(vs_stabilizer* s, const float* all_transforms_host, int
     if (!s || !out_width || !out_height) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
     API_BEGIN
     return s->eng->render_chunk(all_transforms_host, false, n_total, d_frames, width, height, first, count, d_out, out_width, out_height);
+    API_END
+}
+vs_status vs_clip_set_transforms_device(vs_stabilizer* s, const float* d_all_transforms, int n_total, int width, int height) {
+    if (!s) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
+    API_BEGIN
+    return s->eng->set_clip_transforms(d_all_transforms, true, n_total, width, height);
+    API_END
+}
+vs_status vs_clip_render_prepared_device(vs_stabilizer* s, const uint8_t* d_frames, int width, int height, int first, int count,
+                                         uint8_t* d_out, int* out_width, int* out_height) {
+    if (!s || !out_width || !out_height) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    return s->eng->render_prepared(d_frames, width, height, first, count, d_out, out_width, out_height, false);
     API_END
 }
 vs_status vs_clip_render_device(vs_stabilizer* s, const float* d_all_transforms, int n_total, const uint8_t* d_frames,

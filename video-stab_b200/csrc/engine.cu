@@ -991,13 +991,68 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
     return VS_OK;
 }
 
+vs_status Engine::analyze_chunks_lockstep(const uint8_t* const* d_frames, int w, int h, int count, float* const* d_out) {
+    if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
+    if (p_.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode filters carry state from frame to frame; not available in clip mode");
+    if (!d_frames || !d_out || count <= 0) return vs_set_error(VS_ERR_INVALID_ARG, "bad chunk");
+    for (int l = 0; l < n_lanes_; ++l)
+        if (!d_frames[l] || !d_out[l]) return vs_set_error(VS_ERR_INVALID_ARG, "null chunk pointer");
+    CUDA_TRY(cudaSetDevice(device_));
+    VS_TRY(clean());
+    VS_TRY(ensure_geometry(w, h, false, false, false));
+    // every lane runs with the same LOCAL frame numbers: its chunk starts at `first` = 4 (even, past the first-frame
+    // quirks), so slots, detection parity and record indices coincide across lanes
+    const int first = 4, halo = 2;
+    while (first + count + 2 >= traj_cap_) VS_TRY(grow_trajectory());
+    const size_t fb = frame_bytes_, tight = (size_t)w * 3;
+    auto entry = [&](int frame_index) {
+        QueueEntry e;
+        e.index = frame_index; e.slot = 0; e.stride = tight;
+        e.frames.resize(n_lanes_);
+        for (int l = 0; l < n_lanes_; ++l) e.frames[l] = d_frames[l] + (size_t)(frame_index - (first - halo)) * fb;
+        return e;
+    };
+    {
+        // halo: corners from the even frame m = first - 2, pyramid of frame first - 1
+        const int m = first - halo;
+        QueueEntry em = entry(m), e1 = entry(first - 1);
+        PtrPack src, s2;
+        for (int l = 0; l < n_lanes_; ++l) { src.p[l] = em.frames[l]; s2.p[l] = e1.frames[l]; }
+        launch_gray_resize(d_lanes_, n_lanes_, src, w, h, tight, m % VS_PYR_SLOTS, sp());
+        if (multi_) CUDA_TRY(cudaEventRecord(evG_, sp()));
+        launch_pyrdown(d_lanes_, n_lanes_, m % VS_PYR_SLOTS, sp());
+        launches_ += 2;
+        VS_TRY(redetect(m % VS_PYR_SLOTS, m, 0, evG_));
+        launch_gray_resize(d_lanes_, n_lanes_, s2, w, h, tight, (first - 1) % VS_PYR_SLOTS, sp());
+        launch_pyrdown(d_lanes_, n_lanes_, (first - 1) % VS_PYR_SLOTS, sp());
+        launches_ += 2;
+        first_ = false;
+        n_frames_ = first - 1; detect_counter_ = first - 1;      // the counters equal the (local) frame number
+    }
+    for (int f = first; f < first + count; ++f) {
+        bool pop = false;
+        QueueEntry e = entry(f);
+        VS_TRY(generate_transform(e, &pop));         // queue_ is empty: never pops
+    }
+    for (int l = 0; l < n_lanes_; ++l)
+        CUDA_TRY(cudaMemcpyAsync(d_out[l], h_lanes_[l].transforms + 3 * (size_t)(first - 1), sizeof(float) * 3 * count,
+                                 cudaMemcpyDeviceToDevice, sm()));
+    return join();                                   // asynchronous: ordered on the public stream, no host block
+}
+
 vs_status Engine::render_chunk(const float* all_tr, bool device_in, int n_total, const uint8_t* d_frames, int w, int h, int first,
                                int count, uint8_t* d_out, int* ow, int* oh) {
+    VS_TRY(set_clip_transforms(all_tr, device_in, n_total, w, h));
+    return render_prepared(d_frames, w, h, first, count, d_out, ow, oh, !device_in);
+}
+
+// The transform list of the whole clip -> transforms_ and path_ (the reference's sequential float32 running sum) of this
+// handle.  Done once per clip; render_prepared() then smooths and warps any number of chunks against it.
+vs_status Engine::set_clip_transforms(const float* all_tr, bool device_in, int n_total, int w, int h) {
     if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "clip mode uses single-lane handles");
     if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
     if (p_.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode filters carry state from frame to frame; not available in clip mode");
-    if (!all_tr || !d_frames || !d_out || n_total < 1 || first < 0 || count <= 0 || first + count > n_total)
-        return vs_set_error(VS_ERR_INVALID_ARG, "bad chunk");
+    if (!all_tr || n_total < 1) return vs_set_error(VS_ERR_INVALID_ARG, "bad clip");
     CUDA_TRY(cudaSetDevice(device_));
     if (device_in) {
         // asynchronous variant: everything below is enqueued on the public stream behind whatever the handle still has
@@ -1018,11 +1073,6 @@ vs_status Engine::render_chunk(const float* all_tr, bool device_in, int n_total,
     VS_TRY(ensure_geometry(w, h, false, false, mode == 2));
     while (n_total + 2 >= traj_cap_) VS_TRY(grow_trajectory());
     const int n_tr = n_total - 1;
-    if (count > wp_batch_cap_) {
-        if (d_wp_batch_) cudaFree(d_wp_batch_);
-        CUDA_TRY(cudaMalloc((void**)&d_wp_batch_, sizeof(WarpParams) * count));
-        wp_batch_cap_ = count;
-    }
     if (n_tr > 0) {
         CUDA_TRY(cudaMemcpyAsync(h_lanes_[0].transforms, all_tr, sizeof(float) * 3 * n_tr,
                                  device_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
@@ -1030,6 +1080,26 @@ vs_status Engine::render_chunk(const float* all_tr, bool device_in, int n_total,
         launches_ += 1;
     }
     n_frames_ = n_tr;
+    clip_total_ = n_total;
+    return VS_OK;
+}
+
+vs_status Engine::render_prepared(const uint8_t* d_frames, int w, int h, int first, int count, uint8_t* d_out, int* ow, int* oh,
+                                  bool host_sync) {
+    const int n_total = clip_total_;
+    if (n_lanes_ != 1 || n_total < 1) return vs_set_error(VS_ERR_INVALID_ARG, "no clip transforms set on this handle");
+    if (!d_frames || !d_out || first < 0 || count <= 0 || first + count > n_total)
+        return vs_set_error(VS_ERR_INVALID_ARG, "bad chunk");
+    CUDA_TRY(cudaSetDevice(device_));
+    const int b = p_.border_size;
+    const int mode = b <= 0 ? 0 : (p_.crop_n_zoom ? ((w - 2 * b > 0 && h - 2 * b > 0) ? 2 : 0) : 1);
+    if (w != W_ || h != H_) return vs_set_error(VS_ERR_INVALID_ARG, "frame size differs from the clip's");
+    if (count > wp_batch_cap_) {
+        // (stream-ordered: the warp of the previous chunk may still be reading the old array)
+        if (d_wp_batch_) CUDA_TRY(cudaFreeAsync(d_wp_batch_, stream_));
+        CUDA_TRY(cudaMallocAsync((void**)&d_wp_batch_, sizeof(WarpParams) * count, stream_));
+        wp_batch_cap_ = count;
+    }
     const int gate = clampi(smoothing_radius_, 5, 35);
     const int ow_ = mode == 1 ? w + 2 * b : w, oh_ = mode == 1 ? h + 2 * b : h;
     *ow = ow_; *oh = oh_;
@@ -1049,6 +1119,6 @@ vs_status Engine::render_chunk(const float* all_tr, bool device_in, int n_total,
                                    cudaMemcpyDeviceToDevice, stream_));
     }
     n_out_ = n_warp;
-    if (!device_in) CUDA_TRY(cudaStreamSynchronize(stream_));
+    if (host_sync) CUDA_TRY(cudaStreamSynchronize(stream_));
     return VS_OK;
 }

@@ -62,10 +62,21 @@ public:
     // `out` is host memory (the call returns when it is filled) or, with device_out, device memory (asynchronous: the
     // copy is ordered on the public stream, see join()).
     vs_status analyze_chunk(const uint8_t* d_frames, int w, int h, int first, int count, float* out, bool device_out, int* n_out);
+    // Lock-step analysis of n_lanes() chunks at once (one launch per stage for all of them): lane l analyses `count` frames
+    // starting at an EVEN frame number first_l >= 4 of the clip; d_frames[l] points at frame first_l - 2 (the halo), tight
+    // rows, count + 2 frames.  Writes the `count` transforms of generateTransform calls first_l .. first_l + count - 1 of
+    // lane l to d_out[l] (device memory, 3 floats each).  Asynchronous like analyze_chunk(device_out).  The frame numbers
+    // themselves are not needed: motion estimation is pairwise-local, only the parity of the chunk start matters.
+    vs_status analyze_chunks_lockstep(const uint8_t* const* d_frames, int w, int h, int count, float* const* d_out);
     // all_tr_host: the n_total-1 transforms of the whole clip.  d_frames: frames [first, first+count).
     // all_tr is host memory (synchronous call) or, with device_in, device memory (asynchronous on the public stream)
     vs_status render_chunk(const float* all_tr, bool device_in, int n_total, const uint8_t* d_frames, int w, int h, int first,
                            int count, uint8_t* d_out, int* ow, int* oh);
+    // the two halves of render_chunk: the clip's transform list -> this handle's trajectory (once per clip), then any number
+    // of chunks smoothed and warped against it
+    vs_status set_clip_transforms(const float* all_tr, bool device_in, int n_total, int w, int h);
+    vs_status render_prepared(const uint8_t* d_frames, int w, int h, int first, int count, uint8_t* d_out, int* ow, int* oh,
+                              bool host_sync);
 
     // per-stage CUDA-event timing (off by default; used by bench.py and the profiles)
     void set_timing(bool on);
@@ -159,6 +170,7 @@ private:
     unsigned char* d_tmaps_ = nullptr;   // tensor-map scratch for the warp kernel (batches of more than 8 lanes)
     WarpParams* d_wp_batch_ = nullptr;
     int wp_batch_cap_ = 0;
+    int clip_total_ = 0;              // frames of the clip whose transforms set_clip_transforms() installed (0: none)
     std::vector<float*> traj_bufs_;
     uint64_t launches_ = 0;
 

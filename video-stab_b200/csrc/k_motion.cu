@@ -808,10 +808,16 @@ void launch_smooth_only(const LaneDev* lanes, int n_lanes, StepInfo info, cudaSt
 // smoothing become batch kernels.
 //   k_traj_build    path_ = running sum of transforms_ in float32, STRICTLY in the reference's sequential
 //                   order (Stabilizer.cpp:681-687) so the result is bit-identical to a streamed run; three
-//                   lanes (x, y, angle) walk the clip, the |t| / atan2 terms are filled in parallel.
+//                   lanes (x, y, angle) walk the clip tile by tile through shared memory, the |t| / atan2 terms
+//                   are filled in parallel.
 //   k_smooth_batch  one thread per output frame replays applyNextSmoothTransform's smoothing for the path
 //                   length the streamed reference would have seen when that frame left the queue.
+#define TRAJ_TILE 2048
 __global__ void __launch_bounds__(256) k_traj_build(const LaneDev* __restrict__ lanes, int n_tr) {
+    // The running sum is a chain of dependent float32 additions (one rounding per frame: no scan reproduces it), so the
+    // chain itself stays on three threads; what a long clip needs is that each link costs an FADD, not a trip to HBM:
+    // the block stages TRAJ_TILE frames in shared memory, the three chains run over the tile, the block writes it back.
+    __shared__ float st[3 * TRAJ_TILE];
     const LaneDev& L = lanes[blockIdx.z];
     const int tid = threadIdx.x;
     for (int i = tid; i < n_tr; i += blockDim.x) {
@@ -819,13 +825,21 @@ __global__ void __launch_bounds__(256) k_traj_build(const LaneDev* __restrict__ 
         L.aux[2 * i] = f_sqrt(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)));
         L.aux[2 * i + 1] = f_atan2(ty, tx);
     }
-    if (tid < 3) {
-        float acc = 0.f;
-        for (int i = 0; i < n_tr; ++i) {
-            const float t = L.transforms[3 * i + tid];
-            acc = (i == 0) ? t : __fadd_rn(acc, t);
-            L.path[3 * i + tid] = acc;
+    float acc = 0.f;
+    for (int base = 0; base < n_tr; base += TRAJ_TILE) {
+        const int m = min(TRAJ_TILE, n_tr - base);
+        for (int i = tid; i < 3 * m; i += blockDim.x) st[i] = L.transforms[3 * (size_t)base + i];
+        __syncthreads();
+        if (tid < 3) {
+            for (int i = 0; i < m; ++i) {
+                const float t = st[3 * i + tid];
+                acc = (base + i == 0) ? t : __fadd_rn(acc, t);
+                st[3 * i + tid] = acc;
+            }
         }
+        __syncthreads();
+        for (int i = tid; i < 3 * m; i += blockDim.x) L.path[3 * (size_t)base + i] = st[i];
+        __syncthreads();
     }
 }
 

@@ -155,13 +155,29 @@ def stabilize_chunk_distributed(st: Stabilizer, frames, halo_frames: int, n_tota
     return full
 
 
-def stabilize_rank_chunks(st: Stabilizer, chunk_frames: dict, n_total: int, n_chunks: int, my_chunks, out_ring, group=None):
+def lockstep_chunking(n_total: int, world: int, max_lanes: int = 64, min_frames: int = 40):
+    """Number of temporal chunks per rank for the lock-step analysis: as many (<= max_lanes) as divide the clip into equal
+    chunks of an even number (>= min_frames) of frames - equal chunks advance in lock-step, even starts keep the corner
+    re-detection (every second frame) aligned across chunks.  None if the clip length does not divide that way."""
+    for cpr in range(max_lanes, 1, -1):
+        n_chunks = world * cpr
+        if n_total % n_chunks == 0:
+            per = n_total // n_chunks
+            if per % 2 == 0 and per >= min_frames:
+                return cpr
+    return None
+
+
+def stabilize_rank_chunks(st: Stabilizer, chunk_frames: dict, n_total: int, n_chunks: int, my_chunks, out_ring, group=None,
+                          batch=None):
     """One rank's share of a long clip cut into `n_chunks` temporal chunks (n_chunks a multiple of the world size; rank r
     owns the contiguous block `my_chunks`).  chunk_frames[c]: (halo + count, H, W, 3) uint8 CUDA tensor of frames
     [first_c - halo_c, first_c + count_c).  Every chunk is analysed, ONE all-gather stitches the transforms of the whole
     clip (device to device), then every chunk is smoothed and warped into `out_ring` ((max count, H', W', 3); reused chunk
-    after chunk when a rank owns several).  Asynchronous on the handle's streams and torch's current stream; returns the
-    stitched (n_total-1, 3) transform tensor."""
+    after chunk when a rank owns several).  With `batch` (a StabilizerBatch) the rank's chunks that start at an even frame
+    >= 4 and have the common length are analysed in LOCK-STEP, batch.n at a time (one launch per stage for all of them);
+    the rest (the clip's first chunk, a shorter last one) go through `st` frame by frame, concurrently.  Asynchronous on
+    the handles' streams and torch's current stream; returns the stitched (n_total-1, 3) transform tensor."""
     import torch
     import torch.distributed as dist
     my_chunks = list(my_chunks)
@@ -175,13 +191,30 @@ def stabilize_rank_chunks(st: Stabilizer, chunk_frames: dict, n_total: int, n_ch
     ev0 = torch.cuda.Event()
     ev0.record(cur)
     st.wait_event(ev0.cuda_event)                      # `local` was zeroed on torch's stream
+    lock = []
+    if batch is not None:
+        batch.wait_event(ev0.cuda_event)
+        for k, c in enumerate(my_chunks):
+            first, count = chunk_bounds(n_total, n_chunks, c)
+            if first >= 4 and first % 2 == 0 and count == per and halo(first) == 2:
+                lock.append((k, c))
+        lock = lock[: (len(lock) // batch.n) * batch.n] if len(lock) >= batch.n else []
+    in_lock = {c for _, c in lock}
+    for r0 in range(0, len(lock), batch.n if batch is not None else 1):
+        grp = lock[r0:r0 + batch.n]
+        batch.clip_analyze_device([chunk_frames[c].data_ptr() for _, c in grp], w, h, per,
+                                  [local[k * per].data_ptr() for k, _ in grp])
     for k, c in enumerate(my_chunks):
         first, count = chunk_bounds(n_total, n_chunks, c)
-        if count > 0:
+        if count > 0 and c not in in_lock:
             analyze_chunk_device(st, chunk_frames[c].data_ptr(), w, h, first, count, local[k * per].data_ptr())
     ev = torch.cuda.Event()
     ev.record(ext)
     cur.wait_event(ev)
+    if lock:
+        evb = torch.cuda.Event()
+        evb.record(torch.cuda.ExternalStream(batch.stream, device=dev))
+        cur.wait_event(evb)
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     if world > 1:
         gathered = torch.empty((n_chunks * per, 3), dtype=torch.float32, device=dev)
@@ -192,11 +225,14 @@ def stabilize_rank_chunks(st: Stabilizer, chunk_frames: dict, n_total: int, n_ch
     ev2 = torch.cuda.Event()
     ev2.record(cur)
     st.wait_event(ev2.cuda_event)
+    check(lib.vs_clip_set_transforms_device(st._h, full.data_ptr(), n_total, w, h))      # trajectory rebuilt once per clip
+    ow, oh = C.c_int(), C.c_int()
     for c in my_chunks:
         first, count = chunk_bounds(n_total, n_chunks, c)
         if count > 0:
             hl = halo(first)
-            render_chunk_device(st, full.data_ptr(), n_total, chunk_frames[c].data_ptr() + hl * fb, w, h, first, count, out_ring.data_ptr())
+            check(lib.vs_clip_render_prepared_device(st._h, chunk_frames[c].data_ptr() + hl * fb, w, h, first, count,
+                                                     out_ring.data_ptr(), C.byref(ow), C.byref(oh)))
     return full
 
 

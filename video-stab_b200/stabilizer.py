@@ -388,6 +388,16 @@ class StabilizerBatch:
         fa = (C.c_void_p * self.n)(*d_frames)
         check(lib.vs_batch_build_levels(self._h, fa, w, h, stride, parts))
 
+    def clip_analyze_device(self, d_frames, w, h, count, d_transforms_out):
+        """Lock-step analysis of n temporal chunks of a clip (vs_batch_clip_analyze_device): d_frames[l] = device address
+        of frame first_l - 2 of chunk l (first_l even, >= 4), d_transforms_out[l] = device address of count x 3 float32."""
+        fa = (C.c_void_p * self.n)(*d_frames)
+        oa = (C.c_void_p * self.n)(*d_transforms_out)
+        check(lib.vs_batch_clip_analyze_device(self._h, fa, w, h, count, oa))
+
+    def wait_event(self, cuda_event: int) -> None:
+        check(lib.vs_batch_wait_event(self._h, C.c_void_p(cuda_event)))
+
     def sync(self):
         check(lib.vs_batch_sync(self._h))
 
