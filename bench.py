@@ -8,7 +8,7 @@
 N = 1 (BASELINE configs[1]): one 1920x1080 live stream, smoothing radius 15.  A *step* is one pass of the hot path over
 256 consecutive frames of that stream, read in place from a 126-frame sequence resident in HBM (784 MB > the 126 MB L2).
 N > 1 (BASELINE configs[3]): 64 concurrent 1080p streams sharded s mod N over the ranks, each rank advancing its
-64/N streams in lock-step through one StabilizerBatch; a step advances every stream by 8 frames (512 frames per step
+64/N streams in lock-step through one StabilizerBatch; a step advances every stream by 32 frames (2048 frames per step
 in total, fixed as N grows: strong scaling).  No collective on this data path.  The same figure for 64 streams on ONE
 GPU is in `config4` of the N = 1 line, so the strong-scaling curve has its base point.
 
@@ -47,7 +47,7 @@ FRAMES_PER_STEP = 256          # config 2: frames of the single stream per step
 SEQ_FRAMES = 64                # distinct generated frames; laid out ping-pong (126 frames) so the sequence loops without a jump
 SMOOTHING_RADIUS = 15
 C4_STREAMS = 64                # config 4: concurrent streams in total
-C4_FRAMES = 8                  # frames every stream advances per step  (64 x 8 = 512 frames per step, all ranks together)
+C4_FRAMES = 32                 # frames every stream advances per step  (64 x 32 = 2048 frames per step, all ranks together: ~3 ms at N = 8)
 C4_CLIP = 24                   # generated frames per stream (ping-pong: 46-frame loop)
 C5_FRAMES = 18000              # config 5: 10 minutes at 30 fps
 C5_CHUNKS = 8
