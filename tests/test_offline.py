@@ -95,8 +95,9 @@ def test_chunked_clip_equals_streamed(kw):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("w,h,n,world", [(640, 360, 480, 1), (1280, 720, 960, 2)])
-def test_lockstep_chunk_analysis_equals_streamed(w, h, n, world):
+@pytest.mark.parametrize("w,h,n,world,method", [(640, 360, 480, 1, "box"), (1280, 720, 960, 2, "box"),
+                                                 (640, 360, 480, 1, "gaussian"), (640, 360, 480, 1, "kalman")])
+def test_lockstep_chunk_analysis_equals_streamed(w, h, n, world, method):
     """The lock-step analysis (vs_batch_clip_analyze_device: all of a rank's chunks advance together, one launch per stage)
     and the prepared render (vs_clip_set_transforms_device once, vs_clip_render_prepared_device per chunk) against the
     streamed stabilize() + flush() of the whole clip: transforms bit for bit, every output frame equal.  `world` ranks are
@@ -107,7 +108,7 @@ def test_lockstep_chunk_analysis_equals_streamed(w, h, n, world):
     dev = torch.device("cuda", 0)
     gen = synthclip.DeviceClip(w, h, n, 777, dev)
     clip = gen.frames(0, n)
-    params = vsb.Parameters(smoothingRadius=9)
+    params = vsb.Parameters(smoothingRadius=9, smoothingMethod=method)       # (kalman: the recursion continues from chunk to chunk)
     fb = h * w * 3
     st = vsb.Stabilizer(params)
     ring = torch.empty((n + 1, h, w, 3), dtype=torch.uint8, device=dev)

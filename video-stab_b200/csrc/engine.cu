@@ -380,6 +380,7 @@ vs_status Engine::clean() {
     for (bool& b : out_free_set_) b = false;
     for (bool& b : c_pending_) b = false;
     queue_.clear();
+    kalman_next_ = -1; clip_total_ = 0;
     first_ = true;
     next_index_ = 0;
     n_frames_ = 0;
@@ -1081,6 +1082,7 @@ vs_status Engine::set_clip_transforms(const float* all_tr, bool device_in, int n
     }
     n_frames_ = n_tr;
     clip_total_ = n_total;
+    kalman_next_ = 0;
     return VS_OK;
 }
 
@@ -1109,7 +1111,10 @@ vs_status Engine::render_prepared(const uint8_t* d_frames, int w, int h, int fir
     const int n_warp = (first + count == n_total) ? count - 1 : count;
     if (n_warp > 0) {
         StepInfo base = step_info(0);
-        launch_smooth_batch(d_lanes_, 1, base, first, n_warp, n_total, gate, d_wp_batch_, stream_);
+        // (Kalman: the recursion continues where the previous chunk of this clip left it, else it restarts at frame 0)
+        const int kal_from = (first == kalman_next_ && first > 0) ? first : 0;
+        launch_smooth_batch(d_lanes_, 1, base, first, n_warp, n_total, gate, d_wp_batch_, kal_from, stream_);
+        kalman_next_ = first + n_warp;
         launches_ += 1 + launch_warp_frames_mode(d_frames, w, h, tight_in, frame_bytes_, d_out, tight_out, oframe, d_wp_batch_, n_warp,
                                                  mode, b, border_mode_, d_scratch_, stream_);
     }

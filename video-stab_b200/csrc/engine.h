@@ -170,6 +170,7 @@ private:
     unsigned char* d_tmaps_ = nullptr;   // tensor-map scratch for the warp kernel (batches of more than 8 lanes)
     WarpParams* d_wp_batch_ = nullptr;
     int wp_batch_cap_ = 0;
+    int kalman_next_ = 0;             // clip mode: the Kalman state on the device stands at output frame kalman_next_ - 1
     int clip_total_ = 0;              // frames of the clip whose transforms set_clip_transforms() installed (0: none)
     std::vector<float*> traj_bufs_;
     uint64_t launches_ = 0;

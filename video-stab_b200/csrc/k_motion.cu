@@ -398,7 +398,30 @@ void warp_params_from_T(const float* T, WarpParams* wp) {
 
 // Smoothing + intent + matrix for the frame being emitted.  Runs on one thread (sequential float32
 // arithmetic in the reference's order); S.gk is scratch for the gaussian taps.
-static __device__ void smooth_and_setup(const LaneDev& L, WarpParams* wp_out, const StepInfo& info, float* gk, Traj path, Traj trf, Traj aux) {
+// gaussianFilterConvolve's kernel (Stabilizer.cpp:1364-1383): size from sigma, taps exp(-x^2 / (2 sigma^2)) normalised by their
+// float32 sum accumulated left to right.  Returns the size; taps are only written when it fits the scratch (<= 512).
+static __device__ int gaussian_taps(float sigma, float* gk) {
+    int ksz = max(3, (int)ceilf(__fmul_rn(6.f, sigma)));
+    if ((ksz & 1) == 0) ++ksz;
+    const int c = ksz / 2;
+    if (ksz <= 512) {
+        float tot = 0.f;
+        for (int j = 0; j < ksz; ++j) {
+            float x = (float)(j - c);
+            float arg = __fdiv_rn(-__fmul_rn(x, x), __fmul_rn(__fmul_rn(2.f, sigma), sigma));
+            float kv = (float)exp((double)arg);
+            gk[j] = kv;
+            tot = __fadd_rn(tot, kv);
+        }
+        for (int j = 0; j < ksz; ++j) gk[j] = __fdiv_rn(gk[j], tot);
+    }
+    return ksz;
+}
+
+// taps_ready: gk already holds gaussian_taps(info.gaussian_sigma) (clip mode computes them once per block)
+//             sm_pre: clip mode, Kalman: this frame's filter output, computed by k_kalman_pass
+static __device__ void smooth_and_setup(const LaneDev& L, WarpParams* wp_out, const StepInfo& info, float* gk, Traj path, Traj trf, Traj aux,
+                                        bool taps_ready = false, const float* sm_pre = nullptr) {
     const int i = info.pop_index, n = info.path_len_at_pop;
     vs_output_record rec;
     rec.index = i; rec.passthrough = 0; rec.path_len = n; rec.radius = 0; rec.intent = 0;
@@ -422,15 +445,7 @@ static __device__ void smooth_and_setup(const LaneDev& L, WarpParams* wp_out, co
         int c = ksz / 2;
         if (i - c < path.base) { path.p = L.path; path.base = 0; }      // window reaches below the staged tail
         if (n > c && ksz <= 512) {
-            float tot = 0.f;
-            for (int j = 0; j < ksz; ++j) {
-                float x = (float)(j - c);
-                float arg = __fdiv_rn(-__fmul_rn(x, x), __fmul_rn(__fmul_rn(2.f, sigma), sigma));
-                float kv = (float)exp((double)arg);
-                gk[j] = kv;
-                tot = __fadd_rn(tot, kv);
-            }
-            for (int j = 0; j < ksz; ++j) gk[j] = __fdiv_rn(gk[j], tot);
+            if (!taps_ready) gaussian_taps(sigma, gk);
             for (int comp = 0; comp < 3; ++comp) {
                 float s = 0.f;
                 for (int j = 0; j < ksz; ++j) {
@@ -445,6 +460,9 @@ static __device__ void smooth_and_setup(const LaneDev& L, WarpParams* wp_out, co
             }
             have = true;
         }
+    } else if (info.method == 2 && sm_pre) {
+        sm[0] = sm_pre[0]; sm[1] = sm_pre[1]; sm[2] = sm_pre[2];
+        have = true;
     } else if (info.method == 2) {                          // kalmanFilterSmooth :1416-1458, incremental
         for (int comp = 0; comp < 3; ++comp) {
             float* ks = L.kalman + 6 * comp;                // x0 x1 P00 P01 P10 P11
@@ -844,23 +862,15 @@ __global__ void __launch_bounds__(256) k_traj_build(const LaneDev* __restrict__ 
 }
 
 __global__ void __launch_bounds__(128) k_smooth_batch(const LaneDev* __restrict__ lanes, StepInfo base, int first, int count,
-                                                       int n_total, int gate, WarpParams* __restrict__ wps) {
+                                                       int n_total, int gate, WarpParams* __restrict__ wps, int kal_from) {
     __shared__ float gk[512];
     const LaneDev& L = lanes[blockIdx.z];
     const int n_tr = n_total - 1;
-    if (base.method != 0) {
-        // gaussian taps / Kalman state are shared scratch: walk the frames sequentially on one thread
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            for (int i = (base.method == 2 ? 0 : first); i < first + count; ++i) {
-                StepInfo info = base;
-                info.pop_index = i;
-                info.path_len_at_pop = min(i + gate - 1, n_tr);
-                info.n_out = max(i - first, 0);
-                smooth_and_setup(L, L.wp, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
-                if (i >= first) wps[i - first] = *L.wp;
-            }
-        }
-        return;
+    // box, gaussian and (the filter outputs being in wps[k].T already, k_kalman_pass) Kalman smoothing: one thread per output
+    // frame replays its own window in the reference's order; the gaussian taps depend on sigma alone, once per block
+    if (base.method == 1) {
+        if (threadIdx.x == 0) gaussian_taps(base.gaussian_sigma, gk);
+        __syncthreads();
     }
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
@@ -869,14 +879,53 @@ __global__ void __launch_bounds__(128) k_smooth_batch(const LaneDev* __restrict_
     info.pop_index = i;
     info.path_len_at_pop = min(i + gate - 1, n_tr);
     info.n_out = k;
-    // box smoothing touches no shared scratch; every thread writes its own record and warp set-up
-    smooth_and_setup(L, wps + k, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0});
+    float pre[3] = {0.f, 0.f, 0.f};
+    if (base.method == 2) { pre[0] = wps[k].T[0]; pre[1] = wps[k].T[1]; pre[2] = wps[k].T[2]; }
+    smooth_and_setup(L, wps + k, info, gk, Traj{L.path, 0}, Traj{L.transforms, 0}, Traj{L.aux, 0}, true, base.method == 2 ? pre : nullptr);
+}
+
+// Clip mode, Kalman smoothing (kalmanFilterSmooth, Stabilizer.cpp:1416-1458): the filter is a recursion over the frames, one
+// independent chain per component.  Three threads walk frames kal_from .. first + count - 1 with the state in registers (it lives
+// in L.kalman between calls) and leave the outputs of frames >= first in wps[i - first].T[component] for k_smooth_batch.
+__global__ void __launch_bounds__(32) k_kalman_pass(const LaneDev* __restrict__ lanes, int kal_from, int first, int count,
+                                                    WarpParams* __restrict__ wps) {
+    const LaneDev& L = lanes[blockIdx.z];
+    const int comp = threadIdx.x;
+    if (comp >= 3) return;
+    float* ks = L.kalman + 6 * comp;                // x0 x1 P00 P01 P10 P11
+    float k0s = ks[0], k1s = ks[1], k2s = ks[2], k3s = ks[3], k4s = ks[4], k5s = ks[5];
+    for (int i = kal_from; i < first + count; ++i) {
+        const float z = L.path[3 * (size_t)i + comp];
+        float out;
+        if (i == 0) {
+            k0s = z; k1s = 0.f; k2s = k3s = k4s = k5s = 0.f;
+            out = z;
+        } else {
+            // predict: x' = A x ; P' = A P A^T + Q, A = [1 1; 0 1], Q = 0.01 I
+            float x0 = __fadd_rn(k0s, k1s), x1 = k1s;
+            float t00 = __fadd_rn(k2s, k4s), t01 = __fadd_rn(k3s, k5s), t10 = k4s, t11 = k5s;
+            float p00 = __fadd_rn(__fadd_rn(t00, t01), 0.01f), p01 = t01;
+            float p10 = __fadd_rn(t10, t11), p11 = __fadd_rn(t11, 0.01f);
+            // correct: H = [1 0], R = 0.1
+            float sden = __fadd_rn(p00, 0.1f);
+            float g0 = __fdiv_rn(p00, sden), g1 = __fdiv_rn(p01, sden);
+            float y = __fsub_rn(z, x0);
+            k0s = __fadd_rn(x0, __fmul_rn(g0, y));
+            k1s = __fadd_rn(x1, __fmul_rn(g1, y));
+            k2s = __fsub_rn(p00, __fmul_rn(g0, p00)); k3s = __fsub_rn(p01, __fmul_rn(g0, p01));
+            k4s = __fsub_rn(p10, __fmul_rn(g1, p00)); k5s = __fsub_rn(p11, __fmul_rn(g1, p01));
+            out = k0s;
+        }
+        if (i >= first) wps[i - first].T[comp] = out;
+    }
+    ks[0] = k0s; ks[1] = k1s; ks[2] = k2s; ks[3] = k3s; ks[4] = k4s; ks[5] = k5s;
 }
 
 void launch_traj_build(const LaneDev* lanes, int n_lanes, int n_tr, cudaStream_t st) {
     k_traj_build<<<dim3(1, 1, n_lanes), 256, 0, st>>>(lanes, n_tr);
 }
 void launch_smooth_batch(const LaneDev* lanes, int n_lanes, StepInfo base, int first, int count, int n_total, int gate,
-                         WarpParams* wps, cudaStream_t st) {
-    k_smooth_batch<<<dim3((count + 127) / 128, 1, n_lanes), 128, 0, st>>>(lanes, base, first, count, n_total, gate, wps);
+                         WarpParams* wps, int kal_from, cudaStream_t st) {
+    if (base.method == 2) k_kalman_pass<<<dim3(1, 1, n_lanes), 32, 0, st>>>(lanes, kal_from, first, count, wps);
+    k_smooth_batch<<<dim3((count + 127) / 128, 1, n_lanes), 128, 0, st>>>(lanes, base, first, count, n_total, gate, wps, kal_from);
 }

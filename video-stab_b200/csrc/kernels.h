@@ -51,7 +51,7 @@ void launch_smooth_only(const LaneDev* lanes, int n_lanes, StepInfo info, cudaSt
 // offline clip mode: trajectory of the whole clip + batched smoothing (k_motion.cu)
 void launch_traj_build(const LaneDev* lanes, int n_lanes, int n_tr, cudaStream_t st);
 void launch_smooth_batch(const LaneDev* lanes, int n_lanes, StepInfo base, int first, int count, int n_total, int gate,
-                         WarpParams* wps, cudaStream_t st);
+                         WarpParams* wps, int kal_from, cudaStream_t st);
 
 // ---- k_warp.cu : copyMakeBorder + warpAffine + crop/zoom (Stabilizer.cpp:981-990, 1056-1060, 1108-1124)
 struct WarpGeom {
