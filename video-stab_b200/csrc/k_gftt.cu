@@ -255,9 +255,26 @@ static __device__ unsigned long long radix_select(const unsigned long long* __re
     return S.prefix;
 }
 
+// Descending bitonic sort of n keys (n a power of two >= 32) in shared memory.  Compare-exchange distances below 32 stay inside a
+// warp: those stages run on registers with shuffles (no block barrier); only the distances >= 32 go through shared memory.
+static __device__ __forceinline__ unsigned long long bitonic_warp_stages(unsigned long long v, int i, int k, int j) {
+    for (; j > 0; j >>= 1) {
+        const unsigned long long p = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool keep_max = (((i & j) == 0) == ((i & k) == 0));      // descending block: the lower index keeps the larger key
+        v = keep_max ? (v > p ? v : p) : (v < p ? v : p);
+    }
+    return v;
+}
 static __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+    // k = 2 .. 32: every stage is warp-local
+    for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
+        unsigned long long v = a[i];
+        for (int k = 2; k <= 32; k <<= 1) v = bitonic_warp_stages(v, i, k, k >> 1);
+        a[i] = v;
+    }
+    __syncthreads();
+    for (int k = 64; k <= n; k <<= 1) {
+        for (int j = k >> 1; j >= 32; j >>= 1) {
             for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
                 int ixj = i ^ j;
                 if (ixj > i) {
@@ -268,6 +285,8 @@ static __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
             }
             __syncthreads();
         }
+        for (int i = threadIdx.x; i < n; i += SEL_THREADS) a[i] = bitonic_warp_stages(a[i], i, k, 16);
+        __syncthreads();
     }
 }
 
@@ -320,17 +339,22 @@ static __device__ bool greedy_pass(float2* kp_out, const unsigned* sxy, const in
                     }
                 }
             }
-            // earlier lanes of this batch closer than minDistance.  Only lanes that survived the grid test can
-            // ever be accepted, so only those are walked (the mask is warp-uniform: no divergence).
+            // earlier lanes of this batch closer than minDistance: all 32 candidates of the batch are read back from shared
+            // memory (broadcast 128-bit loads, nothing depends on anything) and tested; only lanes that survived the grid test
+            // can ever be accepted, so only their bits count
             ok = ok && !hit;
-            unsigned walk = __ballot_sync(FULL, ok);
-            while (walk) {
-                const int k = __ffs(walk) - 1;
-                walk &= walk - 1u;
-                const unsigned o = __shfl_sync(FULL, xy, k);
-                const int ddx = x - (int)(o & 0xffffu), ddy = y - (int)(o >> 16);
-                if ((ddx * ddx + ddy * ddy) < imd2) cmask |= 1u << k;
+            const unsigned walk = __ballot_sync(FULL, ok);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                const uint4 q4 = *reinterpret_cast<const uint4*>(sxy + base + 4 * k4);
+                const unsigned qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int ddx = x - (int)(qv[s4] & 0xffffu), ddy = y - (int)(qv[s4] >> 16);
+                    cmask |= ((ddx * ddx + ddy * ddy) < imd2) ? (1u << (4 * k4 + s4)) : 0u;
+                }
             }
+            cmask &= walk;
             cmask &= lt;
         }
         unsigned undecided = __ballot_sync(FULL, ok);
