@@ -721,7 +721,7 @@ def run_gpu(args, rank, world, local_rank):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             produced = 0
-            lead = 6                                       # untimed: the handles allocate their 4K buffers on their first frames
+            lead = 24                                      # untimed: the handles allocate their 4K buffers on their first frames and at the first output (frame 15)
             for k in range(frames + lead):
                 if k == lead:
                     st3.sync()
