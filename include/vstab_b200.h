@@ -249,6 +249,19 @@ vs_status vs_clip_set_transforms_device(vs_stabilizer* s, const float* d_all_tra
 vs_status vs_clip_render_prepared_device(vs_stabilizer* s, const uint8_t* d_frames, int width, int height, int first, int count,
                                          uint8_t* d_out, int* out_width, int* out_height);
 
+/* ---- decoder / encoder hand-off ---------------------------------------------------
+ * The reference ingests BGR from a GStreamer appsink and hands BGR to an appsrc; the colour conversion from and to the codecs'
+ * NV12 happens on the CPU inside its pipelines (`videoconvert`, examples/vsg.cpp:91-134, 230-311).  With a hardware decoder the
+ * frames are NV12 surfaces in device memory: these two calls convert on the device, so decode -> vs_stabilizer_push_device
+ * (VS_PUSH_BORROW) -> encode never touches the host.  Asynchronous on `stream` (a cudaStream_t as void*, NULL = the default
+ * stream); order the stabilizer behind the conversion with vs_stabilizer_wait_event.  d_y: height rows of width bytes;
+ * d_uv: height / 2 rows of width bytes (U, V interleaved); width and height even.  Arithmetic: OpenCV's 8-bit BT.601
+ * limited-range fixed point, bit-exact with cv::cvtColor(COLOR_YUV2BGR_NV12) and cv::cvtColor(COLOR_BGR2YUV_I420). */
+vs_status vs_nv12_to_bgr_device(const uint8_t* d_y, size_t y_stride, const uint8_t* d_uv, size_t uv_stride, int width, int height,
+                                uint8_t* d_bgr, size_t bgr_stride, void* stream);
+vs_status vs_bgr_to_nv12_device(const uint8_t* d_bgr, size_t bgr_stride, int width, int height, uint8_t* d_y, size_t y_stride,
+                                uint8_t* d_uv, size_t uv_stride, void* stream);
+
 /* ---- roll correction ------------------------------------------------------------
  * Replaces vs::RollCorrection::autoCorrectRoll(input, params) (reference include/video/RollCorrection.h:16-51,
  * src/RollCorrection.cpp:16-155), the stage that runs immediately before stabilize() in the reference's pipeline

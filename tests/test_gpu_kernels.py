@@ -320,3 +320,81 @@ def test_good_features_other_block_sizes(vsb, cv2_noopt, w, h, block, q, md):
     got = vsb.kernels.good_features(_dev(g), 200, q, md, block_size=block)
     assert len(ref) > 20
     assert np.array_equal(got, ref), f"first difference at {next((i for i in range(min(len(got), len(ref))) if not np.array_equal(got[i], ref[i])), None)} of {len(ref)} / {len(got)}"
+
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (1280, 720), (3840, 2160), (642, 362), (64, 2)])
+def test_nv12_bgr_conversions_bit_exact(vsb, cv2_noopt, w, h):
+    """Decoder / encoder hand-off (vs_nv12_to_bgr_device, vs_bgr_to_nv12_device): bit-exact with cv2's NV12 -> BGR and
+    BGR -> I420 (U, V interleaved), on random bytes (every saturation case), aligned and unaligned widths / views."""
+    cv2 = cv2_noopt
+    rng = np.random.default_rng(w + h)
+    nv = rng.integers(0, 256, (h * 3 // 2, w), dtype=np.uint8)
+    nv[:8, :8] = 0
+    nv[8:16, :8] = 255
+    ref = cv2.cvtColor(nv, cv2.COLOR_YUV2BGR_NV12)
+    got = vsb.kernels.nv12_to_bgr(_dev(nv)).cpu().numpy()
+    assert np.array_equal(got, ref), np.abs(got.astype(int) - ref).max()
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    i420 = cv2.cvtColor(img, cv2.COLOR_BGR2YUV_I420)
+    flat, q = i420.reshape(-1), (h // 2) * (w // 2)
+    u = flat[h * w:h * w + q].reshape(h // 2, w // 2)
+    v = flat[h * w + q:].reshape(h // 2, w // 2)
+    ref_nv = np.concatenate([i420[:h], np.stack([u, v], -1).reshape(h // 2, w)], 0)
+    got_nv = vsb.kernels.bgr_to_nv12(_dev(img)).cpu().numpy()
+    assert np.array_equal(got_nv, ref_nv), np.abs(got_nv.astype(int) - ref_nv).max()
+    if w > 200:
+        # views into larger surfaces: pitch 2048-style strides and an odd byte offset (the per-block path)
+        big = torch.zeros((h * 3 // 2, w + 37), dtype=torch.uint8, device="cuda")
+        big[:, 5:5 + w] = _dev(nv)
+        view = big[:, 5:5 + w]
+        out = torch.zeros((h, w + 11, 3), dtype=torch.uint8, device="cuda")
+        vsb.kernels.nv12_to_bgr(view, out=out[:, 3:3 + w])
+        assert np.array_equal(out[:, 3:3 + w].cpu().numpy(), ref)
+        back = torch.zeros((h * 3 // 2, w + 37), dtype=torch.uint8, device="cuda")
+        vsb.kernels.bgr_to_nv12(_dev(img), out=back[:, 4:4 + w])
+        assert np.array_equal(back[:, 4:4 + w].cpu().numpy(), ref_nv)
+
+
+def test_nv12_round_trip_through_the_stabilizer(vsb):
+    """NV12 surface -> BGR on the device -> vs_stabilizer_push_device (borrowed) -> NV12, stream-ordered with events only:
+    the decode -> stabilize -> encode shape of INTEGRATION.md.  The BGR frames the stabilizer sees equal the host-converted ones,
+    so its outputs equal those of the host-fed handle."""
+    import cv2
+    w, h, n = 640, 360, 20
+    clip = synthclip.make_clip(w, h, n, 99)
+    nvs = []
+    for f in clip:
+        i420 = cv2.cvtColor(f, cv2.COLOR_BGR2YUV_I420)
+        u = i420[h:h + h // 4].reshape(h // 2, w // 2)
+        v = i420[h + h // 4:].reshape(h // 2, w // 2)
+        nvs.append(np.concatenate([i420[:h], np.stack([u, v], -1).reshape(h // 2, w)], 0))
+    params = vsb.Parameters(smoothingRadius=5)
+    ref_st = vsb.Stabilizer(params)
+    ref_out = []
+    for nv in nvs:
+        o = ref_st.stabilize(cv2.cvtColor(nv, cv2.COLOR_YUV2BGR_NV12))
+        ref_out.append(None if o is None else o.copy())
+    st = vsb.Stabilizer(params)
+    dec = torch.cuda.Stream()
+    d_nv = [_dev(nv) for nv in nvs]
+    bgr = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    outs = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    enc = torch.empty((n, h * 3 // 2, w), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ext = torch.cuda.ExternalStream(st.stream)
+    produced = []
+    for k in range(n):
+        vsb.kernels.nv12_to_bgr(d_nv[k], out=bgr[k], stream=dec.cuda_stream)
+        ev = torch.cuda.Event()
+        ev.record(dec)
+        st.wait_event(ev.cuda_event)
+        got = st.push_device(bgr[k].data_ptr(), w, h, w * 3, outs[k].data_ptr(), w * 3, h * w * 3, borrow=True)
+        if got is not None:
+            vsb.kernels.bgr_to_nv12(outs[k], out=enc[k], stream=st.stream)
+            produced.append(k)
+    st.sync()
+    assert produced == [k for k in range(n) if ref_out[k] is not None]
+    for k in produced:
+        assert np.array_equal(outs[k].cpu().numpy(), ref_out[k])
+        i420 = cv2.cvtColor(ref_out[k], cv2.COLOR_BGR2YUV_I420)
+        assert np.array_equal(enc[k, :h].cpu().numpy(), i420[:h])

@@ -120,6 +120,8 @@ SYMBOLS = {
     "vs_batch_build_pyramids": (_I, [_P, C.POINTER(_P), _I, _I, _SZ]),
     "vs_batch_build_levels": (_I, [_P, C.POINTER(_P), _I, _I, _SZ, _I]),
     "vs_batch_sync": (_I, [_P]),
+    "vs_nv12_to_bgr_device": (_I, [_U8P, _SZ, _U8P, _SZ, _I, _I, _U8P, _SZ, _P]),
+    "vs_bgr_to_nv12_device": (_I, [_U8P, _SZ, _I, _I, _U8P, _SZ, _U8P, _SZ, _P]),
     "vs_batch_join": (_I, [_P]),
     "vs_batch_wait_event": (_I, [_P, _P]),
     "vs_batch_clip_analyze_device": (_I, [_P, C.POINTER(_P), _I, _I, _I, C.POINTER(_P)]),

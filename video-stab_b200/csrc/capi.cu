@@ -656,6 +656,27 @@ vs_status vs_k_warp_affine_bgr8(const uint8_t* d_src, int src_w, int src_h, size
     API_END
 }
 
+vs_status vs_nv12_to_bgr_device(const uint8_t* d_y, size_t y_stride, const uint8_t* d_uv, size_t uv_stride, int width, int height,
+                                uint8_t* d_bgr, size_t bgr_stride, void* stream) {
+    if (!d_y || !d_uv || !d_bgr || width < 2 || height < 2 || (width & 1) || (height & 1))
+        return vs_set_error(VS_ERR_INVALID_ARG, "NV12 needs non-null planes and even dimensions");
+    if (y_stride < (size_t)width || uv_stride < (size_t)width || bgr_stride < (size_t)width * 3)
+        return vs_set_error(VS_ERR_INVALID_ARG, "row stride smaller than a row");
+    launch_nv12_to_bgr(d_y, y_stride, d_uv, uv_stride, width, height, d_bgr, bgr_stride, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return VS_OK;
+}
+vs_status vs_bgr_to_nv12_device(const uint8_t* d_bgr, size_t bgr_stride, int width, int height, uint8_t* d_y, size_t y_stride,
+                                uint8_t* d_uv, size_t uv_stride, void* stream) {
+    if (!d_y || !d_uv || !d_bgr || width < 2 || height < 2 || (width & 1) || (height & 1))
+        return vs_set_error(VS_ERR_INVALID_ARG, "NV12 needs non-null planes and even dimensions");
+    if (y_stride < (size_t)width || uv_stride < (size_t)width || bgr_stride < (size_t)width * 3)
+        return vs_set_error(VS_ERR_INVALID_ARG, "row stride smaller than a row");
+    launch_bgr_to_nv12(d_bgr, bgr_stride, width, height, d_y, y_stride, d_uv, uv_stride, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return VS_OK;
+}
+
 vs_status vs_k_resize_linear_u8(const uint8_t* d_src, int sw, int sh, size_t sstride, int channels, uint8_t* d_dst,
                                 int dw, int dh, size_t dstride, void* stream) {
     if (!d_src || !d_dst || (channels != 1 && channels != 3)) return vs_set_error(VS_ERR_INVALID_ARG, "bad argument");

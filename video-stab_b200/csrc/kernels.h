@@ -86,3 +86,9 @@ void launch_fade_update(uint8_t* hist, const MutPtrPack& outs, size_t out_stride
 void launch_content_mask(const uint8_t* d_bgr, int w, int h, size_t stride, uint8_t* d_mask, uint8_t* d_scratch, cudaStream_t st);
 vs_status auto_zoom_crop_device(const uint8_t* d_bgr, int w, int h, size_t stride, uint8_t* d_out, size_t out_stride, size_t out_capacity,
                                 int* ow, int* oh, cudaStream_t st);
+
+// ---- k_nv12.cu : NV12 <-> packed BGR on the device (decoder / encoder hand-off; OpenCV's 8-bit BT.601 fixed point)
+void launch_nv12_to_bgr(const uint8_t* y, size_t y_stride, const uint8_t* uv, size_t uv_stride, int w, int h, uint8_t* bgr,
+                        size_t bgr_stride, cudaStream_t st);
+void launch_bgr_to_nv12(const uint8_t* bgr, size_t bgr_stride, int w, int h, uint8_t* y, size_t y_stride, uint8_t* uv,
+                        size_t uv_stride, cudaStream_t st);

@@ -100,3 +100,26 @@ def warp_output(src, T, mode: int, border_size: int = 0, border_mode: int = 0):
     check(lib.vs_k_warp_output(src.data_ptr(), w, h, src.stride(0), Tm.ctypes.data, mode, border_size, border_mode,
                                dst.data_ptr(), dst.stride(0), C.byref(ow), C.byref(oh), None))
     return dst
+
+
+def nv12_to_bgr(nv12, out=None, stream: int = 0):
+    """(H * 3 / 2, W) uint8 cuda tensor (Y plane, then the interleaved UV plane) -> (H, W, 3) BGR; cv2.COLOR_YUV2BGR_NV12."""
+    torch = _t()
+    h32, w = nv12.shape
+    h = h32 * 2 // 3
+    if out is None:
+        out = torch.empty((h, w, 3), dtype=torch.uint8, device=nv12.device)
+    check(lib.vs_nv12_to_bgr_device(nv12.data_ptr(), nv12.stride(0), nv12[h:].data_ptr(), nv12.stride(0), w, h,
+                                    out.data_ptr(), out.stride(0), stream))
+    return out
+
+
+def bgr_to_nv12(bgr, out=None, stream: int = 0):
+    """(H, W, 3) BGR uint8 cuda tensor -> (H * 3 / 2, W) NV12; cv2.COLOR_BGR2YUV_I420 with U and V interleaved."""
+    torch = _t()
+    h, w, _ = bgr.shape
+    if out is None:
+        out = torch.empty((h * 3 // 2, w), dtype=torch.uint8, device=bgr.device)
+    check(lib.vs_bgr_to_nv12_device(bgr.data_ptr(), bgr.stride(0), w, h, out.data_ptr(), out.stride(0), out[h:].data_ptr(),
+                                    out.stride(0), stream))
+    return out
