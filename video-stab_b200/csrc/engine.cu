@@ -5,6 +5,7 @@
 // the device, so a step is a pure launch sequence with no host<->device round trip.
 #include "engine.h"
 
+#include <nvtx3/nvToolsExt.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,10 +24,17 @@ vs_status vs_set_error(vs_status st, const char* msg) {
 }
 extern "C" const char* vs_last_error(void) { return g_err; }
 
-// ---- optional per-stage CUDA-event timing (bench / profiles); off by default
+// ---- optional per-stage CUDA-event timing (bench / profiles) and NVTX ranges (VS_NVTX=1: the enqueue of every stage shows
+//      up as a named range in ncu / Nsight timelines and can be filtered on with `ncu --nvtx --nvtx-include`); both off by default
+static bool nvtx_on() {
+    static const bool v = [] { const char* e = getenv("VS_NVTX"); return e && *e == '1'; }();
+    return v;
+}
+static const char* const k_stage_names[] = {"vs.gray_resize", "vs.pyrdown", "vs.pyr_lk", "vs.motion", "vs.gftt", "vs.warp"};
 struct StageScope {
-    Engine* e; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    Engine* e; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; bool range = false;
     StageScope(Engine* e_, int s, cudaStream_t st_) : e(e_), stage(s), st(st_) {
+        if (nvtx_on() && s >= 0 && s < (int)(sizeof(k_stage_names) / sizeof(k_stage_names[0]))) { nvtxRangePushA(k_stage_names[s]); range = true; }
         if (e->timing_on() && (only_stage() < 0 || only_stage() == s)) { a = e->take_event(); b = e->take_event(); cudaEventRecord(a, st); }
     }
     // VS_TRACE_STAGE=<stage>: time only that stage (two events per frame instead of twelve: an almost unperturbed pipeline)
@@ -34,7 +42,10 @@ struct StageScope {
         static int v = [] { const char* e = getenv("VS_TRACE_STAGE"); return e ? atoi(e) : -1; }();
         return v;
     }
-    ~StageScope() { if (a) { cudaEventRecord(b, st); e->add_pending(stage, a, b); } }
+    ~StageScope() {
+        if (a) { cudaEventRecord(b, st); e->add_pending(stage, a, b); }
+        if (range) nvtxRangePop();
+    }
 };
 
 cudaEvent_t Engine::take_event() {
