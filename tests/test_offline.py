@@ -26,6 +26,31 @@ def test_chunk_bounds_cover_the_clip():
     assert [offline.halo(f) for f in (0, 1, 2, 3, 4, 5, 6, 100, 101)] == [0, 1, 2, 1, 2, 1, 2, 2, 1]
 
 
+def test_lockstep_chunking_gives_equal_even_chunks():
+    """offline.lockstep_chunking: equal chunks of an even number of frames (>= 40), at most 64 per rank, for the clip lengths and
+    world sizes of BASELINE config 5; every chunk but the clip's first starts at an even frame >= 4 with a two-frame halo."""
+    import __graft_entry__
+    __graft_entry__.build()
+    from video_stab_b200 import offline
+    for n in (18000, 4096, 9000, 600):
+        for world in (1, 2, 4, 8):
+            cpr = offline.lockstep_chunking(n, world)
+            if cpr is None:
+                continue
+            chunks = world * cpr
+            per = n // chunks
+            assert 2 <= cpr <= 64 and per * chunks == n and per % 2 == 0 and per >= 40
+            per_s, idx = offline.stitch_index(n, chunks)
+            assert per_s == per and len(idx) == n - 1
+            for c in range(chunks):
+                first, count = offline.chunk_bounds(n, chunks, c)
+                assert count == per and first == c * per
+                if c:
+                    assert first % 2 == 0 and first >= 4 and offline.halo(first) == 2
+    assert offline.lockstep_chunking(18000, 1) == 60 and offline.lockstep_chunking(18000, 8) == 45
+    assert offline.lockstep_chunking(37, 2) is None
+
+
 def _stitch_worker(rank, world, port, n_total, q):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
