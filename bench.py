@@ -30,10 +30,11 @@ import argparse
 import json
 import os
 
-# A handle overlaps its stages on six CUDA streams (eight with the pipelined host path); the default of 8 hardware
-# queues would alias them with the other streams of this process and add false dependencies.  Must be set before
-# the CUDA context exists.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# Hardware work queues of the process (must be set before the CUDA context exists).  Measured on this pool (profiles/r02_summary.md):
+# with 32 queues two lock-step groups on one GPU (N = 8: 14 streams) run 5 % faster than with the default 8, but page-locked
+# host <-> device copies - the plain duplex ceiling itself - lose 8 - 24 % and become erratic; one live stream and the 64-stream
+# batch do not care.  So: the default at N = 1, where the host-buffer figure is the headline; 32 when a rank drives several groups.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "8")
 import subprocess
 import sys
 import threading

@@ -211,7 +211,7 @@ vs_status vs_stabilizer_first_corners(vs_stabilizer* s, float* xy, int capacity,
 vs_status vs_stabilizer_launch_count(vs_stabilizer* s, uint64_t* n);
 
 /* Per-stage device timing with CUDA events on the handle's stream (off by default; bench/profiles).
- * stage: 0 resize+gray, 1 pyrDown, 2 PyrLK, 3 RANSAC+trajectory+smoothing, 4 GFTT, 5 warp.
+ * stage: 0 resize+gray, 1 pyrDown, 2 PyrLK, 3 RANSAC+trajectory+smoothing, 4 GFTT, 5 warp, 6 / 7 copy-in / copy-out of the host path.
  * vs_*_stage_time synchronises and returns the summed duration and launch-group count since enabling. */
 vs_status vs_stabilizer_set_timing(vs_stabilizer* s, int enable);
 vs_status vs_stabilizer_stage_time(vs_stabilizer* s, int stage, double* total_ms, long long* count);

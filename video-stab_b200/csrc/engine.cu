@@ -30,7 +30,7 @@ static bool nvtx_on() {
     static const bool v = [] { const char* e = getenv("VS_NVTX"); return e && *e == '1'; }();
     return v;
 }
-static const char* const k_stage_names[] = {"vs.gray_resize", "vs.pyrdown", "vs.pyr_lk", "vs.motion", "vs.gftt", "vs.warp"};
+static const char* const k_stage_names[] = {"vs.gray_resize", "vs.pyrdown", "vs.pyr_lk", "vs.motion", "vs.gftt", "vs.warp", "vs.copy_in", "vs.copy_out"};
 struct StageScope {
     Engine* e; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; bool range = false;
     StageScope(Engine* e_, int s, cudaStream_t st_) : e(e_), stage(s), st(st_) {
@@ -100,9 +100,10 @@ vs_status Engine::create(const vs_params& p, int device, int n_lanes, Engine** o
         return vs_set_error(VS_ERR_UNSUPPORTED, "max_corners must be 1..2048 (<= 0 means 'unlimited' to cv::goodFeaturesToTrack; the corner buffers are fixed-size)");
     if (p.adaptive_smoothing && n_lanes > 1)
         return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing makes the latency gate data dependent; single-stream handles only");
-    // A handle uses up to nine streams (seven + two copy streams); the default of eight hardware queues would make two of
-    // them share one.  Only effective when the process has not initialised CUDA yet, never overrides the user's value.
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    // A handle uses up to nine streams (seven + two copy streams), one more than the default number of hardware queues
+    // (CUDA_DEVICE_MAX_CONNECTIONS = 8).  The library does not touch that setting: on the B200 boxes it was measured on, raising
+    // it helps a process that drives several handles at once (+5 % for two lock-step groups) and costs the page-locked copies of
+    // the host-buffer path 8 - 24 % (profiles/r02_summary.md); the application knows which of the two it is.
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) {
@@ -726,10 +727,11 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
     if (pipe) {
         CUDA_TRY(cudaEventRecord(evOutReady_[oslot], stream_));
         CUDA_TRY(cudaStreamWaitEvent(sO_, evOutReady_[oslot], 0));
-        for (int l = 0; l < n_lanes_; ++l) {
+        { StageScope tcopy(this, VS_STAGE_D2H, sO_);
+          for (int l = 0; l < n_lanes_; ++l) {
             if (out_stride == tight && dstride == tight) CUDA_TRY(cudaMemcpyAsync(outs[l], dst.p[l], tight * (size_t)h, cudaMemcpyDeviceToHost, sO_));
             else CUDA_TRY(cudaMemcpy2DAsync(outs[l], out_stride, dst.p[l], dstride, tight, h, cudaMemcpyDeviceToHost, sO_));
-        }
+          } }
         CUDA_TRY(cudaEventRecord(evOutFree_[oslot], sO_));
         out_free_set_[oslot] = true;
     } else if (host_io) {
@@ -779,6 +781,7 @@ vs_status Engine::push(const uint8_t* const* frames, int w, int h, size_t stride
         // the ring slot is refilled only after the warp that last read it (another stream) has finished
         cudaStream_t cs = pipe ? sH_ : sp();
         if (multi_ && ring_ev_set_[e.slot]) CUDA_TRY(cudaStreamWaitEvent(cs, evRing_[e.slot], 0));
+        StageScope tcopy(this, VS_STAGE_H2D, cs);
         for (int l = 0; l < n_lanes_; ++l) {
             uint8_t* dst = d_ring_ + ((size_t)l * ring_slots_ + e.slot) * frame_bytes_;
             const cudaMemcpyKind kind = host_io ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;

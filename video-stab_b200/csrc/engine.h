@@ -13,7 +13,7 @@
 enum { VS_IO_DEVICE = 0, VS_IO_HOST_SYNC = 1, VS_IO_HOST_PIPE = 2 };   // where push()/flush() frames live
 #define VS_TRACK_STREAMS 2                // LK of frame n runs on tracking stream n % 2 (four measured no faster)
 #define VS_OUT_SLOTS 3                    // output staging frames of the pipelined host path
-enum { VS_STAGE_GRAY = 0, VS_STAGE_PYRDOWN, VS_STAGE_LK, VS_STAGE_MOTION, VS_STAGE_GFTT, VS_STAGE_WARP, VS_N_STAGES };
+enum { VS_STAGE_GRAY = 0, VS_STAGE_PYRDOWN, VS_STAGE_LK, VS_STAGE_MOTION, VS_STAGE_GFTT, VS_STAGE_WARP, VS_STAGE_H2D, VS_STAGE_D2H, VS_N_STAGES };
 
 struct QueueEntry {
     int index;                               // frameIndexQueue_

@@ -335,7 +335,7 @@ class Stabilizer:
         return np.frombuffer(buf, np.float32, 3 * min(n.value, capacity)).reshape(-1, 3).copy()
 
 
-STAGES = ("resize_gray", "pyrdown", "pyr_lk", "motion", "gftt", "warp")
+STAGES = ("resize_gray", "pyrdown", "pyr_lk", "motion", "gftt", "warp", "copy_in", "copy_out")
 
 
 def _stage_times(set_fn, get_fn, h):
