@@ -430,8 +430,8 @@ def test_multi_stream_engine_equals_single_stream(vsb, monkeypatch, w, h, n, kw)
             monkeypatch.setenv("VS_SINGLE_STREAM", "1")
         else:
             monkeypatch.delenv("VS_SINGLE_STREAM", raising=False)
-        if rep == 4:                                   # opt-in variant: RANSAC half of the motion step behind LK
-            monkeypatch.setenv("VS_SPLIT_MOTION", "1")
+        if rep == 4:                                   # the motion step as one kernel (default: RANSAC half behind LK)
+            monkeypatch.setenv("VS_SPLIT_MOTION", "0")
         out = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize()
         st = vsb.Stabilizer(vsb.Parameters(**kw))

@@ -151,10 +151,12 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     // warp.  adaptive_smoothing reads one int back per frame, so that mode stays on one stream.
     // VS_SINGLE_STREAM=1 runs everything on the public stream (verification: the multi-stream engine must reproduce it)
     multi_ = !p.adaptive_smoothing && !getenv("VS_SINGLE_STREAM");
-    // VS_SPLIT_MOTION=1: run the frame-independent half of the motion step behind LK on the tracking streams.  It
-    // shortens the sequential chain (27.2 -> 24.5 us device-side) but costs one more launch per frame, and the loop is
-    // host-bound: measured 5 - 10 % SLOWER end to end in bench.py, so it is off by default.
-    split_motion_ = getenv("VS_SPLIT_MOTION") != nullptr;
+    // The frame-independent half of the motion step (status filter, RANSAC, refit) runs behind LK on the tracking
+    // streams, which shortens the sequential chain on the motion stream (27.2 -> 24.5 us device-side) for one more
+    // launch per frame.  Measured on config 2 (two boxes, alternating runs): +12 % frames/s with the default 8 CUDA
+    // connections (42.6k vs 37.8k), -3 % with 32 connections; batches and the host-buffer path are unaffected or
+    // better.  VS_SPLIT_MOTION=0 keeps the step in one kernel.
+    { const char* e = getenv("VS_SPLIT_MOTION"); split_motion_ = !(e && e[0] == '0'); }
     if (multi_) {
         // The analysis kernels are small and latency-critical (a single CTA for k_motion / k_select), the warp is one
         // machine-filling grid: the analysis streams get the higher priority so their CTAs are placed first whenever

@@ -132,7 +132,7 @@ private:
     bool evB_set_[VS_EV_RING] = {}, evA_set_[VS_EV_RING] = {}, evW_set_[2] = {};
     int last_detect_frame_ = -100;
     bool c_pending_[VS_KP_SLOTS] = {};
-    bool split_motion_ = false;
+    bool split_motion_ = true;
     bool lk_tma_ = false;                     // the tracker stages its patches with TMA (tensor maps built for every lane)
     bool lk_tma() const { return lk_tma_; }
     cudaStream_t sH_ = nullptr, sO_ = nullptr; // copy-in / copy-out streams of the pipelined host path
