@@ -84,7 +84,7 @@ typedef struct vs_params {
     int32_t jitter_frequency;         /* inert */
     int32_t separate_translation_rotation; /* inert */
     int32_t use_imu_data;             /* inert */
-    int32_t enable_virtual_canvas;    /* enableVirtualCanvas — VS_ERR_UNSUPPORTED if set     */
+    int32_t enable_virtual_canvas;    /* enableVirtualCanvas — single-stream handles, scales >= 1 */
     float   canvas_scale_factor;
     int32_t temporal_buffer_size;
     float   canvas_blend_weight;
@@ -314,6 +314,21 @@ vs_status vs_auto_zoom_crop(const uint8_t* bgr, int width, int height, size_t st
 vs_status vs_auto_zoom_crop_device(const uint8_t* d_bgr, int width, int height, size_t stride, double margin_percent,
                                    uint8_t* d_out, size_t out_stride, size_t out_capacity, int* out_width, int* out_height,
                                    void* stream);
+/* ---- Stabilizer::applyVirtualCanvasStabilization on its own (Stabilizer.cpp:2066-2443) ----------------------------------
+ * The output stage `enable_virtual_canvas` switches on inside vs_stabilizer_push*, as a handle of its own: it keeps the temporal
+ * frame buffer (device) and the canvas size.  One call = updateTemporalFrameBuffer (:2153-2167) + applyVirtualCanvasStabilization
+ * for one frame with its correction (dx, dy, da).  `recent_transforms` (3 floats each, oldest first; the tail of the reference's
+ * transforms_) is read by the first call only, where adaptive_canvas_size sizes the canvas (:2280-2314).  Device frames;
+ * the call synchronises `stream` once (twice on frames that contain pixels of gray <= 1, whose mask goes to the host for
+ * cv::findContours as in the reference) and returns with the output enqueued.  Only the canvas fields of vs_params are read. */
+typedef struct vs_canvas vs_canvas;
+vs_status vs_canvas_create(const vs_params* params, int device, vs_canvas** out);
+void      vs_canvas_destroy(vs_canvas* c);
+vs_status vs_canvas_apply_device(vs_canvas* c, const uint8_t* d_bgr, int width, int height, size_t stride, const float* transform3,
+                                 const float* recent_transforms, int n_recent, uint8_t* d_out, size_t out_stride, void* stream);
+/* canvas scale chosen by the first call (0 before it) and the number of regions the last call filled */
+vs_status vs_canvas_info(vs_canvas* c, float* scale, int* regions_filled);
+
 /* the host half on its own: crop rectangle from a (closed) content mask in host memory.  found = 0: no contour (frame unchanged) */
 vs_status vs_auto_zoom_rect_from_mask(const uint8_t* mask, int width, int height, size_t stride, int* x, int* y, int* w, int* h,
                                       int* found);

@@ -331,6 +331,8 @@ def _declare(lib):
         "vsref_n_smoothed": (ci, [vp]), "vsref_get_smoothed": (None, [vp, vp, ci]),
         "vsref_n_keypoints": (ci, [vp]), "vsref_get_keypoints": (None, [vp, vp, ci]),
         "vsref_set_transforms": (None, [vp, vp, ci]),
+        "vsref_vc_last": (ci, [vp, vp, vp]),
+        "vsref_vc_apply": (ci, [vp, vp, ci, ci, cz, vp, vp, cz, PI, PI]),
         "vsref_box_filter": (ci, [vp, vp, ci, vp]),
         "vsref_gaussian_filter": (ci, [vp, vp, ci, cf, vp]),
         "vsref_kalman_filter": (ci, [vp, vp, ci, vp]),
@@ -407,7 +409,8 @@ class RefStabilizer:
 
     def _on_op(self, op, kw):
         if op == "warp":
-            self._warp = kw["T"]
+            if self._warp is None:                 # the frame's own warp; the virtual canvas warps temporal frames after it
+                self._warp = kw["T"]
             return
         if self._cur is None:
             return
@@ -519,6 +522,25 @@ class RefStabilizer:
 
     def smoothing_radius(self):
         return self.lib.vsref_smoothing_radius(self.h)
+
+    def vc_apply(self, frame: np.ndarray, t3) -> np.ndarray:
+        """The reference's virtual canvas stage on one frame with correction (dx, dy, da) (Stabilizer.cpp:1130-1134)."""
+        frame = np.ascontiguousarray(frame)
+        h, w = frame.shape[:2]
+        t = np.ascontiguousarray(np.asarray(t3, f32).reshape(3))
+        out = self._buf(w, h, 0)
+        ow, oh = C.c_int(), C.c_int()
+        rc = self.lib.vsref_vc_apply(self.h, _fp(frame), w, h, frame.strides[0], _fp(t), _fp(out), out.size, C.byref(ow), C.byref(oh))
+        if rc != 1:
+            raise RuntimeError(f"reference virtual canvas failed rc={rc}: {self.ops.errors[-3:]}")
+        return out[: ow.value * oh.value * 3].reshape(oh.value, ow.value, 3).copy()
+
+    def vc_last(self):
+        """virtual canvas: (correction (dx, dy, da) of the frame emitted last, canvas scale, temporal buffer length)"""
+        t = np.zeros(3, f32)
+        sc = C.c_float()
+        n = self.lib.vsref_vc_last(self.h, _fp(t), C.byref(sc))
+        return t, sc.value, n
 
     # ---- the pure-host functions on their own
     def set_transforms(self, t):

@@ -145,6 +145,31 @@ void vsref_get_transforms(void *s, float *dst, int cap) { copy3(static_cast<Stab
 void vsref_get_path(void *s, float *dst, int cap) { copy3(static_cast<Stabilizer *>(s)->path_, dst, cap); }
 int vsref_n_smoothed(void *s) { return (int)static_cast<Stabilizer *>(s)->smoothedPath_.size(); }
 void vsref_get_smoothed(void *s, float *dst, int cap) { copy3(static_cast<Stabilizer *>(s)->smoothedPath_, dst, cap); }
+// virtual canvas stage called on its own, exactly as applyNextSmoothTransform does (Stabilizer.cpp:1130-1134): the private
+// members updateTemporalFrameBuffer + applyVirtualCanvasStabilization on one frame and its correction.  transforms_ (read when the
+// canvas is first sized) can be seeded with vsref_set_transforms.
+int vsref_vc_apply(void *s, const unsigned char *bgr, int w, int h, size_t stride, const float *t3, unsigned char *dst, size_t cap, int *ow, int *oh) {
+    try {
+        auto *st = static_cast<Stabilizer *>(s);
+        cv::Mat frame(h, w, CV_8UC3);
+        for (int y = 0; y < h; y++) std::memcpy(frame.ptr(y), bgr + (size_t)y * stride, (size_t)w * 3);
+        cv::Vec3f t(t3[0], t3[1], t3[2]);
+        st->updateTemporalFrameBuffer(frame, t);
+        return emit(st->applyVirtualCanvasStabilization(frame, t), dst, cap, ow, oh);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "vsref_vc_apply: %s\n", e.what());
+        return -1;
+    }
+}
+// virtual canvas (Stabilizer.cpp:2066-2167): the correction of the frame emitted last and the canvas scale in use
+int vsref_vc_last(void *s, float *t3, float *scale) {
+    auto *st = static_cast<Stabilizer *>(s);
+    *scale = st->currentCanvasScale_;
+    if (st->temporalTransformBuffer_.empty()) return 0;
+    const cv::Vec3f &v = st->temporalTransformBuffer_.back();
+    t3[0] = v[0]; t3[1] = v[1]; t3[2] = v[2];
+    return (int)st->temporalTransformBuffer_.size();
+}
 int vsref_n_keypoints(void *s) { return (int)static_cast<Stabilizer *>(s)->prevKeypointsCPU_.size(); }
 void vsref_get_keypoints(void *s, float *dst, int cap) {
     auto &v = static_cast<Stabilizer *>(s)->prevKeypointsCPU_;

@@ -284,3 +284,34 @@ def test_golden_fixture_is_what_the_reference_produces(name):
     assert np.array_equal(bits(g["out_smoothed"]), bits(np.stack([r.smoothed for r in o])))
     assert np.array_equal(bits(g["out_T"]), bits(np.stack([np.zeros((2, 3), np.float32) if r.T is None else r.T for r in o])))
     assert np.array_equal(g["out_crc"], [zlib.crc32(np.ascontiguousarray(f).tobytes()) & 0xFFFFFFFF for f in outs])
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(canvasScaleFactor=1.3, adaptiveCanvasSize=False),
+                                dict(canvasScaleFactor=1.0, adaptiveCanvasSize=False, temporalBufferSize=4, edgeBlendRadius=7, canvasBlendWeight=0.45),
+                                dict(minCanvasScale=1.0, maxCanvasScale=1.9)])
+def test_virtual_canvas_restatement_equals_compiled_reference(kw):
+    """oracle/virtual_canvas_ref.py against the reference's own applyVirtualCanvasStabilization (Stabilizer.cpp:2066-2443,
+    compiled unmodified): the same frames and corrections give bit-equal frames, whole-canvas fills, dark-object fills and the
+    adaptive canvas size included."""
+    from oracle.virtual_canvas_ref import VirtualCanvasRef
+    w, h, n = 320, 180, 12
+    clip = np.maximum(synthclip.make_clip(w, h, n, 5), 6)
+    clip[:, 60:75, 100:130] = 0
+    clip[:, 0:9, 200:230] = 0
+    clip[4:, 120:160, 20:60] = 1
+    rng = np.random.default_rng(3)
+    corr = np.stack([rng.uniform(-40, 40, n), rng.uniform(-25, 25, n), rng.uniform(-0.03, 0.03, n)], axis=1).astype(np.float32)
+    corr[::5, :2] = np.round(corr[::5, :2])
+    recent = (rng.uniform(-1, 1, (35, 3)) * 75).astype(np.float32)
+    ref = ref_lib.RefStabilizer(dict(enableVirtualCanvas=True, **kw), record=False)
+    ref.set_transforms(recent)
+    mine = VirtualCanvasRef(**kw)
+    fills = 0
+    for k in range(n):
+        want = ref.vc_apply(clip[k], corr[k])
+        got = mine.apply(clip[k], corr[k], recent)
+        assert np.array_equal(want, got), f"frame {k} differs"
+        fills += len(mine.filled)
+    assert mine.scale == ref.vc_last()[1]
+    if kw.get("canvasScaleFactor", 1.5) < 1.4:
+        assert fills > 0

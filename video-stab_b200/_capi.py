@@ -108,6 +108,10 @@ SYMBOLS = {
     "vs_roll_reset": (_I, [_P]),
     "vs_roll_state": (_I, [_P, C.POINTER(C.c_double), _IP, _IP, C.POINTER(C.c_uint64)]),
     "vs_roll_debug": (_I, [_P, _IP, _IP, _P, _P, _P, _I]),
+    "vs_canvas_create": (_I, [C.POINTER(VsParams), _I, C.POINTER(_P)]),
+    "vs_canvas_destroy": (None, [_P]),
+    "vs_canvas_apply_device": (_I, [_P, _U8P, _I, _I, _SZ, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _U8P, _SZ, _P]),
+    "vs_canvas_info": (_I, [_P, C.POINTER(C.c_float), _IP]),
     "vs_auto_zoom_crop": (_I, [_U8P, _I, _I, _SZ, C.c_double, _I, _U8P, _SZ, _SZ, _IP, _IP]),
     "vs_auto_zoom_crop_device": (_I, [_U8P, _I, _I, _SZ, C.c_double, _U8P, _SZ, _SZ, _IP, _IP, _P]),
     "vs_auto_zoom_rect_from_mask": (_I, [_U8P, _I, _I, _SZ, _IP, _IP, _IP, _IP, _IP]),

@@ -5,5 +5,6 @@ from . import kernels  # noqa: F401
 from . import offline  # noqa: F401
 from .roll import RollCorrection, RollParameters  # noqa: F401
 from .autozoom import AutoZoomCrop  # noqa: F401
+from .canvas import VirtualCanvas  # noqa: F401
 
-__all__ = ["lib", "LIB_PATH", "VsError", "Parameters", "Stabilizer", "StabilizerBatch", "kernels", "offline", "RollCorrection", "RollParameters", "AutoZoomCrop"]
+__all__ = ["lib", "LIB_PATH", "VsError", "Parameters", "Stabilizer", "StabilizerBatch", "kernels", "offline", "RollCorrection", "RollParameters", "AutoZoomCrop", "VirtualCanvas"]

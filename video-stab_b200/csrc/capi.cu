@@ -484,6 +484,56 @@ vs_status vs_roll_params_from_yaml(const char* path, vs_roll_params* p) {
     return vs_roll_params_from_yaml_string(ss.str().c_str(), p);
     API_END
 }
+// ---- virtual canvas stage on its own (canvas.h)
+struct vs_canvas { VirtualCanvas vc; int device; };
+static vs_status canvas_params_ok(const vs_params& p) {
+    if (p.temporal_buffer_size < 0 || p.temporal_buffer_size > 240)
+        return vs_set_error(VS_ERR_UNSUPPORTED, "temporal_buffer_size must be 0..240 (frames kept on the device)");
+    const float lo = p.adaptive_canvas_size ? (p.min_canvas_scale < p.canvas_scale_factor ? p.min_canvas_scale : p.canvas_scale_factor) : p.canvas_scale_factor;
+    if (!(lo >= 1.0f) || !(p.max_canvas_scale <= 8.0f) || !(p.canvas_scale_factor <= 8.0f))
+        return vs_set_error(VS_ERR_UNSUPPORTED, "virtual canvas scales must lie in 1..8 (a canvas smaller than the frame is not built)");
+    return VS_OK;
+}
+vs_status vs_canvas_create(const vs_params* params, int device, vs_canvas** out) {
+    if (!params || !out) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
+    API_BEGIN
+    *out = nullptr;
+    vs_status st = canvas_params_ok(*params);
+    if (st != VS_OK) return st;
+    vs_canvas* c = new vs_canvas;
+    c->device = device;
+    c->vc.configure(*params);
+    *out = c;
+    return VS_OK;
+    API_END
+}
+void vs_canvas_destroy(vs_canvas* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    delete c;
+}
+vs_status vs_canvas_apply_device(vs_canvas* c, const uint8_t* d_bgr, int width, int height, size_t stride, const float* transform3,
+                                 const float* recent_transforms, int n_recent, uint8_t* d_out, size_t out_stride, void* stream) {
+    if (!c || !d_bgr || !d_out || !transform3 || width < 4 || height < 4 || (n_recent > 0 && !recent_transforms))
+        return vs_set_error(VS_ERR_INVALID_ARG, "virtual canvas: bad argument");
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (stride == 0) stride = (size_t)width * 3;
+    if (out_stride == 0) out_stride = (size_t)width * 3;
+    if (stride < (size_t)width * 3 || out_stride < (size_t)width * 3) return vs_set_error(VS_ERR_INVALID_ARG, "stride smaller than a row");
+    if (n_recent > 30) { recent_transforms += 3 * (size_t)(n_recent - 30); n_recent = 30; }
+    int launches = 0;
+    return c->vc.apply(d_bgr, width, height, stride, transform3, recent_transforms, n_recent < 0 ? 0 : n_recent, d_out, out_stride,
+                       (cudaStream_t)stream, &launches);
+    API_END
+}
+vs_status vs_canvas_info(vs_canvas* c, float* scale, int* regions_filled) {
+    if (!c) return vs_set_error(VS_ERR_INVALID_ARG, "null handle");
+    if (scale) *scale = c->vc.scale();
+    if (regions_filled) *regions_filled = c->vc.regions_last();
+    return VS_OK;
+}
+
 vs_status vs_roll_create(const vs_roll_params* params, int device, vs_roll** out) {
     if (!params || !out) return vs_set_error(VS_ERR_INVALID_ARG, "null argument");
     API_BEGIN

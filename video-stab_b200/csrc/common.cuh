@@ -42,7 +42,7 @@ struct WarpParams {
     double m[6];        // inverted matrix (cv::warpAffine's M after invertAffineTransform)
     float  T[6];        // forward float32 matrix (for the record)
     int    passthrough; // 1: copy the frame unchanged (Stabilizer.cpp:774-780)
-    int    pad;
+    float  da;          // the correction angle behind T (the virtual canvas stage needs it unrounded by cos / sin)
 };
 
 // Per-lane device state.  An array of these lives in HBM; kernels index it with blockIdx.z.

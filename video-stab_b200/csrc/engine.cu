@@ -92,7 +92,14 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 vs_status Engine::create(const vs_params& p, int device, int n_lanes, Engine** out) {
     *out = nullptr;
     if (n_lanes < 1 || n_lanes > VS_MAX_GROUP) return vs_set_error(VS_ERR_INVALID_ARG, "n_streams must be 1..64");
-    if (p.enable_virtual_canvas) return vs_set_error(VS_ERR_UNSUPPORTED, "enable_virtual_canvas is not built yet");
+    if (p.enable_virtual_canvas && !p.crop_n_zoom) {                                // the stage is skipped with crop_n_zoom (Stabilizer.cpp:1110-1127)
+        if (n_lanes > 1) return vs_set_error(VS_ERR_UNSUPPORTED, "enable_virtual_canvas reads one transform back per frame; single-stream handles only");
+        if (p.temporal_buffer_size < 0 || p.temporal_buffer_size > 240)
+            return vs_set_error(VS_ERR_UNSUPPORTED, "temporal_buffer_size must be 0..240 (frames kept on the device)");
+        const float lo = p.adaptive_canvas_size ? (p.min_canvas_scale < p.canvas_scale_factor ? p.min_canvas_scale : p.canvas_scale_factor) : p.canvas_scale_factor;
+        if (!(lo >= 1.0f) || !(p.max_canvas_scale <= 8.0f) || !(p.canvas_scale_factor <= 8.0f))
+            return vs_set_error(VS_ERR_UNSUPPORTED, "virtual canvas scales must lie in 1..8 (a canvas smaller than the frame is not built)");
+    }
     // block_size applies to the first-frame detection only (Stabilizer.cpp:355-357); the window must stay inside the 16-pixel
     // reflect frame kept around every gray level
     if (p.block_size < 1 || p.block_size > 23) return vs_set_error(VS_ERR_UNSUPPORTED, "block_size must be 1..23");
@@ -188,6 +195,8 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
                  : !strcmp(p.border_type, "replicate") ? 1 : !strcmp(p.border_type, "wrap") ? 3 : 0;
     if (p.crop_n_zoom) border_mode_ = 0;
     fade_ = !strcmp(p.border_type, "fade") && p.border_size > 0 && !p.crop_n_zoom;     // :914-916
+    vc_on_ = p.enable_virtual_canvas && !p.crop_n_zoom;                                // :1110-1134
+    canvas_.configure(p);
     method_ = !strcmp(p.smoothing_method, "gaussian") ? 1 : !strcmp(p.smoothing_method, "kalman") ? 2 : 0;
     smoothing_radius_ = p.smoothing_radius;
     cap_first_ = p.max_corners > 0 ? (p.max_corners < MO_MAXP_HOST ? p.max_corners : MO_MAXP_HOST) : MO_MAXP_HOST;
@@ -357,6 +366,8 @@ void Engine::free_all() {
 
 Engine::~Engine() {
     cudaSetDevice(device_);
+    canvas_.reset();
+    if (h_vc_wp_) cudaFreeHost(h_vc_wp_);
     free_all();
 }
 
@@ -627,7 +638,7 @@ vs_status Engine::setup_ready() {
 // must leave the handle exactly as it was (the call can simply be repeated with a larger buffer).
 vs_status Engine::check_out_buffer(bool passthrough, uint8_t* const* outs, size_t out_stride, size_t out_capacity) const {
     const int b = p_.border_size;
-    const bool grows = !passthrough && b > 0 && !p_.crop_n_zoom;                      // copyMakeBorder path, :981-990
+    const bool grows = !passthrough && b > 0 && !p_.crop_n_zoom && !vc_on_;              // copyMakeBorder path, :981-990 (the canvas stage returns frame size)
     const int w = grows ? W_ + 2 * b : W_, h = grows ? H_ + 2 * b : H_;
     const size_t tight = (size_t)w * 3;
     if (out_stride == 0) out_stride = tight;
@@ -650,7 +661,8 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
     queue_.pop_front();
     const bool passthrough = e.index >= n_frames_;                                    // :774-780
     const int b = p_.border_size;
-    const int mode = (passthrough || b <= 0) ? 0 : (p_.crop_n_zoom ? 2 : 1);
+    const bool canvas = vc_on_ && !passthrough;                                          // :1129-1134: replaces the warped frame
+    const int mode = (passthrough || b <= 0 || canvas) ? 0 : (p_.crop_n_zoom ? 2 : 1);
     int w = W_, h = H_;
     if (mode == 1) { w = W_ + 2 * b; h = H_ + 2 * b; }
     if (mode == 2 && (W_ - 2 * b <= 0 || H_ - 2 * b <= 0)) {}                         // :1114-1115 handled below
@@ -681,6 +693,34 @@ vs_status Engine::emit(uint8_t* const* outs, size_t out_stride, size_t out_capac
         }
         for (int l = 0; l < n_lanes_; ++l)
             CUDA_TRY(cudaMemcpy2DAsync(dst.p[l], dstride, e.frames[l], e.stride, tight, h, cudaMemcpyDeviceToDevice, stream_));
+    } else if (canvas && canvas_.never_fills() && canvas_.geometry(W_, H_)) {
+        // nothing can be filled with this canvas: the frame moves by whole pixels, taken from the set-up block on the device
+        int nl = 0;
+        { StageScope t(this, VS_STAGE_WARP, stream_);
+          VS_TRY(canvas_.apply_async(e.frames[0], W_, H_, e.stride, h_lanes_[0].wpb[n_out_ % VS_WP_SLOTS], dst.p[0], dstride, stream_, &nl)); }
+        launches_ += nl;
+    } else if (canvas) {
+        // The correction (dx, dy, da) of this output is read back: the stage's rectangles are integer functions of it and its
+        // region logic runs on the host, as in the reference.  The warp itself is not launched - its result is discarded by
+        // the reference (:1133), and so is the fade history it would update.
+        WarpParams* h_wp = nullptr;
+        if (!h_vc_wp_) CUDA_TRY(cudaMallocHost((void**)&h_vc_wp_, sizeof(WarpParams) + sizeof(float) * 90));
+        h_wp = reinterpret_cast<WarpParams*>(h_vc_wp_);
+        float* h_recent = reinterpret_cast<float*>(h_vc_wp_ + sizeof(WarpParams));
+        CUDA_TRY(cudaMemcpyAsync(h_wp, h_lanes_[0].wpb[n_out_ % VS_WP_SLOTS], sizeof(WarpParams), cudaMemcpyDeviceToHost, stream_));
+        int n_recent = 0;
+        if (!canvas_.sized()) {                                                     // first output: transforms_ sizes the canvas
+            n_recent = n_frames_ < 30 ? n_frames_ : 30;
+            if (n_recent > 0)
+                CUDA_TRY(cudaMemcpyAsync(h_recent, h_lanes_[0].transforms + 3 * (size_t)(n_frames_ - n_recent), sizeof(float) * 3 * n_recent,
+                                         cudaMemcpyDeviceToHost, stream_));
+        }
+        CUDA_TRY(cudaStreamSynchronize(stream_));
+        const float T3[3] = {h_wp->T[2], h_wp->T[5], h_wp->da};
+        int nl = 0;
+        { StageScope t(this, VS_STAGE_WARP, stream_);
+          VS_TRY(canvas_.apply(e.frames[0], W_, H_, e.stride, T3, h_recent, n_recent, dst.p[0], dstride, stream_, &nl)); }
+        launches_ += nl;
     } else {
         PtrPack src;
         for (int l = 0; l < n_lanes_; ++l) src.p[l] = e.frames[l];
@@ -884,7 +924,7 @@ vs_status Engine::flush_many(uint8_t* outs, size_t out_stride, size_t out_frame_
         // one (width, height) per call: stop before a frame of another size (the clip's last frame comes back
         // un-warped, i.e. without the copyMakeBorder margin - Stabilizer.cpp:774-780)
         const bool passthrough = queue_.front().index >= n_frames_;
-        const int b = (!passthrough && p_.border_size > 0 && !p_.crop_n_zoom) ? p_.border_size : 0;
+        const int b = (!passthrough && p_.border_size > 0 && !p_.crop_n_zoom && !vc_on_) ? p_.border_size : 0;
         if (*n_produced > 0 && (W_ + 2 * b != *ow || H_ + 2 * b != *oh)) break;
         uint8_t* o = outs + (size_t)(*n_produced) * out_frame_capacity;
         int produced = 0;
@@ -951,6 +991,7 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
     if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "clip mode uses single-lane handles");
     if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
     if (p_.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode filters carry state from frame to frame; not available in clip mode");
+    if (vc_on_) return vs_set_error(VS_ERR_UNSUPPORTED, "enable_virtual_canvas keeps a temporal frame buffer; not available in clip mode");
     if (!d_frames || first < 0 || count <= 0) return vs_set_error(VS_ERR_INVALID_ARG, "bad chunk");
     CUDA_TRY(cudaSetDevice(device_));
     VS_TRY(clean());
@@ -1011,6 +1052,7 @@ vs_status Engine::analyze_chunk(const uint8_t* d_frames, int w, int h, int first
 vs_status Engine::analyze_chunks_lockstep(const uint8_t* const* d_frames, int w, int h, int count, float* const* d_out) {
     if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
     if (p_.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode filters carry state from frame to frame; not available in clip mode");
+    if (vc_on_) return vs_set_error(VS_ERR_UNSUPPORTED, "enable_virtual_canvas keeps a temporal frame buffer; not available in clip mode");
     if (!d_frames || !d_out || count <= 0) return vs_set_error(VS_ERR_INVALID_ARG, "bad chunk");
     for (int l = 0; l < n_lanes_; ++l)
         if (!d_frames[l] || !d_out[l]) return vs_set_error(VS_ERR_INVALID_ARG, "null chunk pointer");
@@ -1069,6 +1111,7 @@ vs_status Engine::set_clip_transforms(const float* all_tr, bool device_in, int n
     if (n_lanes_ != 1) return vs_set_error(VS_ERR_INVALID_ARG, "clip mode uses single-lane handles");
     if (p_.adaptive_smoothing) return vs_set_error(VS_ERR_UNSUPPORTED, "adaptive_smoothing is not available in clip mode");
     if (p_.drone_high_freq_mode) return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode filters carry state from frame to frame; not available in clip mode");
+    if (vc_on_) return vs_set_error(VS_ERR_UNSUPPORTED, "enable_virtual_canvas keeps a temporal frame buffer; not available in clip mode");
     if (!all_tr || n_total < 1) return vs_set_error(VS_ERR_INVALID_ARG, "bad clip");
     CUDA_TRY(cudaSetDevice(device_));
     if (device_in) {

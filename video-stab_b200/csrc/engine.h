@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "canvas.h"
 #include "kernels.h"
 
 enum { VS_IO_DEVICE = 0, VS_IO_HOST_SYNC = 1, VS_IO_HOST_PIPE = 2 };   // where push()/flush() frames live
@@ -165,6 +166,9 @@ private:
     uint8_t* d_scratch_ = nullptr;    // [lane][frame]      (crop+zoom first pass)
     uint8_t* d_fade_ = nullptr;       // border_type "fade": [lane][history] then [lane][blended source], bordered size
     bool fade_ = false, fade_hist_valid_ = false;
+    bool vc_on_ = false;              // enable_virtual_canvas (and no crop_n_zoom): canvas.h replaces the warp
+    VirtualCanvas canvas_;
+    uint8_t* h_vc_wp_ = nullptr;      // page-locked landing block: the output's WarpParams + up to 30 transforms
     int fade_count_ = 0;              // fadeFrameCount_
     int fade_w_ = 0, fade_h_ = 0;
     unsigned char* d_tmaps_ = nullptr;   // tensor-map scratch for the warp kernel (batches of more than 8 lanes)

@@ -393,7 +393,7 @@ void warp_params_from_T(const float* T, WarpParams* wp) {
     invert_affine(T, wp->m);
     for (int i = 0; i < 6; ++i) wp->T[i] = T[i];
     wp->passthrough = 0;
-    wp->pad = 0;
+    wp->da = 0.f;
 }
 
 // Smoothing + intent + matrix for the frame being emitted.  Runs on one thread (sequential float32
@@ -430,7 +430,7 @@ static __device__ void smooth_and_setup(const LaneDev& L, WarpParams* wp_out, co
     WarpParams wp;
     if (i >= n) {                                           // Stabilizer.cpp:774-780
         rec.passthrough = 1;
-        wp.passthrough = 1; wp.pad = 0;
+        wp.passthrough = 1; wp.da = 0.f;
         for (int k = 0; k < 6; ++k) { wp.m[k] = (k == 0 || k == 4) ? 1. : 0.; wp.T[k] = (k == 0 || k == 4) ? 1.f : 0.f; }
         *wp_out = wp;
         if (info.n_out < L.record_capacity) L.orec[info.n_out] = rec;
@@ -510,7 +510,7 @@ static __device__ void smooth_and_setup(const LaneDev& L, WarpParams* wp_out, co
     float T[6] = {cs, -sn, dx, sn, cs, dy};
     invert_affine(T, wp.m);
     for (int k = 0; k < 6; ++k) { wp.T[k] = T[k]; rec.T[k] = T[k]; }
-    wp.passthrough = 0; wp.pad = 0;
+    wp.passthrough = 0; wp.da = da;
     *wp_out = wp;
     if (info.n_out < L.record_capacity) L.orec[info.n_out] = rec;
 }
@@ -549,7 +549,7 @@ static __device__ void smooth_and_setup_warp(const LaneDev& L, WarpParams* wp_ou
     WarpParams wp;
     invert_affine(T, wp.m);
     for (int k = 0; k < 6; ++k) { wp.T[k] = T[k]; rec.T[k] = T[k]; }
-    wp.passthrough = 0; wp.pad = 0;
+    wp.passthrough = 0; wp.da = da;
     *wp_out = wp;
     if (info.n_out < L.record_capacity) L.orec[info.n_out] = rec;
 }
