@@ -30,7 +30,7 @@ evaluated in float32 without contraction.
 the reference (both call sites pass -1 to shouldApplyConditionalCLAHE, which then always returns false).  The HF state is
 set in the constructor only; clean() does not reset it.
 
-Out of scope here (non-default flags): `enable_virtual_canvas`.
+`enable_virtual_canvas` is restated separately, in oracle/virtual_canvas_ref.py.
 
 The two process-global `static` counters of the reference (`frameTicker` :260,
 `featureDetectionCounter` :696) are per-instance here: parity is defined per stream
