@@ -317,14 +317,44 @@ def test_drone_high_freq_mode_vs_live_oracle(vsb, cv2_noopt, case):
         assert d.max() <= 12 and (d > 1).mean() < 1e-3
 
 
-def test_drone_mode_other_analysis_sizes_are_refused(vsb):
-    st = vsb.Stabilizer(vsb.Parameters(droneHighFreqMode=True))
+@pytest.mark.parametrize("w,h,kw,asize", [(640, 360, dict(), (640, 360)), (640, 480, dict(), (640, 480)),
+                                          (1920, 1200, dict(), (960, 600)), (1920, 1080, dict(hfAnalysisMaxWidth=1280), (1280, 720)),
+                                          (1000, 562, dict(), (960, 538)), (1280, 720, dict(hfAnalysisMaxWidth=320), (320, 180)),
+                                          (644, 362, dict(), (644, 362)), (1280, 720, dict(hfAnalysisMaxWidth=650), (650, 364))])
+def test_drone_mode_other_analysis_sizes_vs_live_oracle(vsb, cv2_noopt, w, h, kw, asize):
+    """calculateDroneAnalysisSize (Stabilizer.cpp:2447-2466): min(hf_analysis_max_width, width) wide, the frame's aspect ratio,
+    both made even - pyramids, detector and tracker at that size instead of 960 x 540."""
+    from oracle import run_clip
+    from oracle.stabilizer_ref import Parameters as RP
+    n = 36
+    clip = synthclip.make_clip(w, h, n, 29)
+    P = dict(smoothingRadius=8, droneHighFreqMode=True, **kw)
+    ref_outs, ref = run_clip(clip, RP(**P))
+    outs, st = _run(vsb, clip, vsb.Parameters(**P))
+    assert len(outs) == len(ref_outs) == n
+    half_diag = 0.5 * float(np.hypot(*asize))
+    for i, fr in enumerate(ref.frame_records):
+        rec = st.frame_record(i)
+        if fr.prev_pts is not None and len(fr.prev_pts):
+            assert rec.n_prev_pts == len(fr.prev_pts), f"frame {i}: {rec.n_prev_pts} points vs {len(fr.prev_pts)}"
+            assert rec.n_tracked == int(np.count_nonzero(fr.status)), f"frame {i}: tracked {rec.n_tracked} vs {int(np.count_nonzero(fr.status))}"
+        d = np.abs(np.asarray(rec.transform, np.float32) - fr.transform)
+        assert d[0] < 1e-3 and d[1] < 1e-3 and d[2] * half_diag < 1e-3, f"frame {i}: {rec.transform} vs {fr.transform}"
+    band = 40
+    for k, (a, b) in enumerate(zip(outs, ref_outs)):
+        assert a.shape == b.shape
+        d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+        # transforms agree to 1e-3 px (DESIGN.md 2): a source coordinate may land in the neighbouring 1/32-px bin for isolated pixels
+        inner = d[band:-band, band:-band]
+        assert int((inner > 1).sum()) <= 24 and int(inner.max()) <= 12, f"output {k}: {int((inner > 1).sum())} pixels off by > 1 LSB, max {int(inner.max())}"
+        assert (d > 1).mean() < 1e-3
+
+
+def test_drone_mode_analysis_sizes_that_are_refused(vsb):
+    st = vsb.Stabilizer(vsb.Parameters(droneHighFreqMode=True, hfAnalysisMaxWidth=48))
     with pytest.raises(vsb.VsError) as ei:
-        st.stabilize(np.zeros((480, 640, 3), np.uint8))           # 4:3 -> 640x480 analysis size in the reference
+        st.stabilize(np.zeros((1080, 1920, 3), np.uint8))         # 48 x 26: OpenCV's tracker would drop pyramid levels
     assert ei.value.status == 7
-    st2 = vsb.Stabilizer(vsb.Parameters(droneHighFreqMode=True, hfAnalysisMaxWidth=1280))
-    with pytest.raises(vsb.VsError):
-        st2.stabilize(np.zeros((1080, 1920, 3), np.uint8))
 
 
 @pytest.mark.parametrize("borrow", [True, False])

@@ -217,29 +217,13 @@ vs_status Engine::alloc_fixed() {
     VS_TRY(dalloc(allocs_, &d_detect_counters_, (size_t)n_lanes_ * 4));      // [generation][lane][eig_max, cand_count]
     int* small_counters = nullptr;
     VS_TRY(dalloc(allocs_, &small_counters, (size_t)n_lanes_ * (1 + VS_KP_SLOTS)));
-    size_t gw = gftt_grid_words(VS_FW, VS_FH, p_.min_distance);
-    size_t gw2 = gftt_grid_words(VS_AW, VS_AH, 15.0);
-    if (gw2 > gw) gw = gw2;
-    gw2 = gftt_grid_words(VS_AW, VS_AH, p_.min_distance);     // single-kernel entry point on a 960x540 image
-    if (gw2 > gw) gw = gw2;
     traj_bufs_.clear();
     if (n_lanes_ > 8) VS_TRY(dalloc(allocs_, &d_tmaps_, (size_t)VS_MAX_GROUP * 128));
     for (int l = 0; l < n_lanes_; ++l) {
         LaneDev& L = h_lanes_[l];
-        for (int s = 0; s < VS_PYR_SLOTS; ++s) {
-            int w = VS_AW, h = VS_AH;
-            for (int k = 0; k < VS_LEVELS; ++k) {
-                VS_TRY(alloc_level(allocs_, w, h, &L.pyr[s].lv[k]));
-                w = (w + 1) / 2; h = (h + 1) / 2;
-            }
-        }
         VS_TRY(alloc_level(allocs_, VS_FW, VS_FH, &L.small0));
-        VS_TRY(dalloc(allocs_, &L.cand, (size_t)VS_AW * VS_AH));
-        VS_TRY(dalloc(allocs_, &L.grid, gw));
         L.eig_max = d_detect_counters_ + 2 * l;
         L.cand_count = (int*)(d_detect_counters_ + 2 * l + 1);
-        VS_TRY(dalloc(allocs_, &L.cand2, (size_t)VS_AW * VS_AH));
-        VS_TRY(dalloc(allocs_, &L.grid2, gw));
         L.eig_max2 = d_detect_counters_ + 2 * n_lanes_ + 2 * l;
         L.cand_count2 = (int*)(d_detect_counters_ + 2 * n_lanes_ + 2 * l + 1);
         L.kp_count = small_counters + (1 + VS_KP_SLOTS) * l;
@@ -277,6 +261,34 @@ vs_status Engine::alloc_fixed() {
         L.kp_capacity = kp_cap_;
         L.log_depth = log_depth_;
         L.record_capacity = traj_cap_;
+    }
+    return alloc_analysis(VS_AW, VS_AH);
+}
+
+// Everything whose size follows the analysis image: the pyramids, the detector's candidate list and min-distance grids, and
+// the tracker's tensor maps.  960 x 540 (Stabilizer.cpp:410) at creation; drone_high_freq_mode picks its own size on the
+// first frame (calculateDroneAnalysisSize, :2447-2466) and calls this again (the previous buffers stay allocated until the
+// handle is destroyed).
+vs_status Engine::alloc_analysis(int aw, int ah) {
+    aw_ = aw; ah_ = ah;
+    size_t gw = gftt_grid_words(VS_FW, VS_FH, p_.min_distance);
+    size_t gw2 = gftt_grid_words(aw, ah, 15.0);
+    if (gw2 > gw) gw = gw2;
+    gw2 = gftt_grid_words(aw, ah, p_.min_distance);           // single-kernel entry point on an analysis-size image
+    if (gw2 > gw) gw = gw2;
+    for (int l = 0; l < n_lanes_; ++l) {
+        LaneDev& L = h_lanes_[l];
+        for (int s = 0; s < VS_PYR_SLOTS; ++s) {
+            int w = aw, h = ah;
+            for (int k = 0; k < VS_LEVELS; ++k) {
+                VS_TRY(alloc_level(allocs_, w, h, &L.pyr[s].lv[k]));
+                w = (w + 1) / 2; h = (h + 1) / 2;
+            }
+        }
+        VS_TRY(dalloc(allocs_, &L.cand, (size_t)aw * ah));
+        VS_TRY(dalloc(allocs_, &L.grid, gw));
+        VS_TRY(dalloc(allocs_, &L.cand2, (size_t)aw * ah));
+        VS_TRY(dalloc(allocs_, &L.grid2, gw));
         // tensor maps of this lane's pyramid planes (TMA-staged tracker, k_lk.cu); without them the tracker uses plain loads
         L.lk_maps = nullptr;
         if (l == 0 || lk_tma_) {
@@ -418,13 +430,19 @@ vs_status Engine::clean() {
 
 vs_status Engine::ensure_geometry(int w, int h, bool need_ring, bool need_out, bool need_scratch) {
     if (p_.drone_high_freq_mode) {
-        // calculateDroneAnalysisSize (Stabilizer.cpp:2447-2466): the analysis kernels are built for 960x540
+        // calculateDroneAnalysisSize (Stabilizer.cpp:2447-2466)
         const int mw = p_.hf_analysis_max_width < w ? p_.hf_analysis_max_width : w;
         const float aspect = (float)h / (float)w;
-        const int ah = (int)((float)mw * aspect);
-        if ((mw / 2) * 2 != VS_AW || (ah / 2) * 2 != VS_AH)
-            return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode: only frames whose drone analysis size is 960x540 "
-                                                    "(hf_analysis_max_width 960, 16:9 input at least 960 wide) are supported");
+        const int ah0 = (int)((float)mw * aspect);
+        const int aw = (mw / 2) * 2, ah = (ah0 / 2) * 2;
+        if (aw != aw_ || ah != ah_) {
+            // the tracker always runs three pyramid levels; OpenCV drops the levels that are no larger than the 15 x 15 window (:611-619)
+            if (aw > 4096 || ((aw + 1) / 2 + 1) / 2 <= VS_WIN || ((ah + 1) / 2 + 1) / 2 <= VS_WIN)
+                return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode: the drone analysis size (min(hf_analysis_max_width, width) x matching "
+                                                        "height, both made even) must be at least 62 x 62 and at most 4096 wide");
+            VS_TRY(sync());
+            VS_TRY(alloc_analysis(aw, ah));
+        }
     }
     if (W_ == 0) {
         W_ = w; H_ = h;
@@ -505,7 +523,7 @@ vs_status Engine::redetect(int cur, int frame_no, int record_frame_no, cudaEvent
     }
     StageScope t(this, VS_STAGE_GFTT, sc(gen));
     int mc = p_.max_corners < 200 ? p_.max_corners : 200;       // (the counters were left zeroed by the previous k_select)
-    launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, record_frame_no, gen, ks, sc(gen));   // :740-744
+    launch_good_features(d_lanes_, n_lanes_, cur, mc, 0.02, 15.0, record_frame_no, gen, ks, sc(gen), 3, nullptr, aw_, ah_);   // :740-744
     if (multi_) { CUDA_TRY(cudaEventRecord(evC_[ks], sc(gen))); c_pending_[ks] = true; last_detect_frame_ = frame_no; }
     launches_ += 2;
     return VS_OK;
@@ -530,8 +548,8 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
     for (int l = 0; l < n_lanes_; ++l) src.p[l] = e.frames[l];
     if (frame_no == 1) {
         // prevGray is still the 480x270 first-frame image: cv::resize it up (Stabilizer.cpp:598-603)
-        launch_upsample_small(d_lanes_, n_lanes_, prev, sp());
-        launch_pyrdown(d_lanes_, n_lanes_, prev, sp());
+        launch_upsample_small(d_lanes_, n_lanes_, prev, sp(), aw_, ah_);
+        launch_pyrdown(d_lanes_, n_lanes_, prev, sp(), aw_, ah_);
         launches_ += 2;
     }
     if (multi_) {
@@ -549,9 +567,9 @@ vs_status Engine::generate_transform(const QueueEntry& e, bool* will_pop) {
             CUDA_TRY(cudaStreamWaitEvent(sp(), evB_[guard & (VS_EV_RING - 1)], 0));
     }
     { StageScope t(this, VS_STAGE_GRAY, sp());
-      launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sp()); }       // :449-450
+      launch_gray_resize(d_lanes_, n_lanes_, src, W_, H_, e.stride, cur, sp(), aw_, ah_); }       // :449-450
     { StageScope t(this, VS_STAGE_PYRDOWN, sp());
-      launch_pyrdown(d_lanes_, n_lanes_, cur, sp()); }
+      launch_pyrdown(d_lanes_, n_lanes_, cur, sp(), aw_, ah_); }
     if (multi_) {
         CUDA_TRY(cudaEventRecord(evP_[frame_no & (VS_EV_RING - 1)], sp()));
         // LK(n) and LK(n+1) are independent (key points are not advanced between detections, Appendix B Q4): they

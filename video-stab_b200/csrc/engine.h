@@ -107,6 +107,7 @@ private:
     Engine() = default;
     vs_status init(const vs_params& p, int device, int n_lanes);
     vs_status alloc_fixed();
+    vs_status alloc_analysis(int aw, int ah);
     vs_status ensure_geometry(int w, int h, bool need_ring, bool need_out, bool need_scratch);
     vs_status grow_trajectory();
     vs_status generate_transform(const QueueEntry& e, bool* will_pop);
@@ -166,6 +167,7 @@ private:
     uint8_t* d_scratch_ = nullptr;    // [lane][frame]      (crop+zoom first pass)
     uint8_t* d_fade_ = nullptr;       // border_type "fade": [lane][history] then [lane][blended source], bordered size
     bool fade_ = false, fade_hist_valid_ = false;
+    int aw_ = VS_AW, ah_ = VS_AH;     // analysis size the pyramids are allocated with (alloc_analysis)
     bool vc_on_ = false;              // enable_virtual_canvas (and no crop_n_zoom): canvas.h replaces the warp
     VirtualCanvas canvas_;
     uint8_t* h_vc_wp_ = nullptr;      // page-locked landing block: the output's WarpParams + up to 30 transforms

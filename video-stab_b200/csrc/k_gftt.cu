@@ -621,8 +621,8 @@ size_t gftt_grid_words(int w, int h, double min_dist) {
 }
 
 void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_corners, double quality,
-                          double min_dist, int record_frame_no, int gen, int kp_slot, cudaStream_t st, int block_size, float* eig_scratch) {
-    const int w = slot < 0 ? VS_FW : VS_AW, h = slot < 0 ? VS_FH : VS_AH;
+                          double min_dist, int record_frame_no, int gen, int kp_slot, cudaStream_t st, int block_size, float* eig_scratch, int aw, int ah) {
+    const int w = slot < 0 ? VS_FW : aw, h = slot < 0 ? VS_FH : ah;
     // the attribute is per DEVICE (a process may hold handles on several GPUs): once per device, not once per process
     static bool attr_set[64] = {};
     int dev = 0;

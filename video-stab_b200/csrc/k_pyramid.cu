@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(256) k_gray_quarter(const LaneDev* __restrict_
 }
 
 void launch_gray_resize(const LaneDev* lanes, int n_lanes, const PtrPack& src, int w, int h, size_t stride,
-                        int slot, cudaStream_t st) {
-    int aw = slot < 0 ? VS_FW : VS_AW, ah = slot < 0 ? VS_FH : VS_AH;
+                        int slot, cudaStream_t st, int aw_full, int ah_full) {
+    int aw = slot < 0 ? VS_FW : aw_full, ah = slot < 0 ? VS_FH : ah_full;
     dim3 grid((aw + 2 * VS_PAD + 127) / 128, ah + 2 * VS_PAD, n_lanes);
     double sx = 1.0 / ((double)aw / (double)w), sy = 1.0 / ((double)ah / (double)h);
     bool aligned = slot >= 0 && stride % 8 == 0 && aw % 4 == 0;
@@ -205,9 +205,9 @@ __global__ void __launch_bounds__(128) k_upsample_small(const LaneDev* __restric
     d.base[(ptrdiff_t)py * d.pitch + px] = (uint8_t)vres(h0, h1, ty.a0, ty.a1);
 }
 
-void launch_upsample_small(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st) {
-    dim3 grid((VS_AW + 2 * VS_PAD + 127) / 128, VS_AH + 2 * VS_PAD, n_lanes);
-    k_upsample_small<<<grid, 128, 0, st>>>(lanes, slot, 1.0 / ((double)VS_AW / VS_FW), 1.0 / ((double)VS_AH / VS_FH));
+void launch_upsample_small(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st, int aw, int ah) {
+    dim3 grid((aw + 2 * VS_PAD + 127) / 128, ah + 2 * VS_PAD, n_lanes);
+    k_upsample_small<<<grid, 128, 0, st>>>(lanes, slot, 1.0 / ((double)aw / VS_FW), 1.0 / ((double)ah / VS_FH));
 }
 
 // ---------------------------------------------------------------- cv::pyrDown
@@ -334,8 +334,8 @@ __global__ void __launch_bounds__(256) k_pyrdown2(const LaneDev* __restrict__ la
     }
 }
 
-void launch_pyrdown(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st) {
-    const int w2 = ((VS_AW + 1) / 2 + 1) / 2, h2 = ((VS_AH + 1) / 2 + 1) / 2;
+void launch_pyrdown(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st, int aw, int ah) {
+    const int w2 = ((aw + 1) / 2 + 1) / 2, h2 = ((ah + 1) / 2 + 1) / 2;
     dim3 grid((w2 + PD_T2 - 1) / PD_T2, (h2 + PD_T2 - 1) / PD_T2, n_lanes);
     k_pyrdown2<<<grid, 256, 0, st>>>(lanes, slot);
 }

@@ -14,12 +14,13 @@ struct MutPtrPack {
 // ---- k_pyramid.cu : resize + gray + pyrDown (Stabilizer.cpp:304-305,449-450,602; pyramid of :611)
 // full-res BGR -> padded gray level `dst_level` of every lane's pyramid slot `slot`
 // (slot < 0: the lanes' `small0` first-frame level)
+// aw x ah: the analysis size the lanes' pyramids were allocated with (960 x 540 unless drone_high_freq_mode chose another)
 void launch_gray_resize(const LaneDev* lanes, int n_lanes, const PtrPack& src, int w, int h, size_t stride,
-                        int slot, cudaStream_t st);
+                        int slot, cudaStream_t st, int aw = VS_AW, int ah = VS_AH);
 // gray `small0` (480x270) -> level 0 of pyramid slot `slot`, cv::resize INTER_LINEAR up-sampling (:602)
-void launch_upsample_small(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st);
+void launch_upsample_small(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st, int aw = VS_AW, int ah = VS_AH);
 // levels 1 and 2 of pyramid slot `slot` from level 0 (cv::pyrDown x2)
-void launch_pyrdown(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st);
+void launch_pyrdown(const LaneDev* lanes, int n_lanes, int slot, cudaStream_t st, int aw = VS_AW, int ah = VS_AH);
 // generic cv::resize INTER_LINEAR on tightly addressed 8UC1/8UC3 (tests, crop+zoom second pass)
 void launch_resize_linear(const uint8_t* src, int sw, int sh, size_t sstride, int ch,
                           uint8_t* dst, int dw, int dh, size_t dstride, cudaStream_t st);
@@ -32,7 +33,7 @@ void launch_unpack_level(GrayLevel src, uint8_t* dst, cudaStream_t st);
 // (and first_corners when slot < 0).  record_frame_no > 0: also log into the frame record ring.
 void launch_good_features(const LaneDev* lanes, int n_lanes, int slot, int max_corners, double quality,
                           double min_dist, int record_frame_no, int gen, int kp_slot, cudaStream_t st, int block_size = 3,
-                          float* eig_scratch = nullptr);   // block_size != 3: per-pixel eigenvalue map in eig_scratch (n_lanes * w * h floats)
+                          float* eig_scratch = nullptr, int aw = VS_AW, int ah = VS_AH);   // block_size != 3: per-pixel eigenvalue map in eig_scratch (n_lanes * w * h floats)
 size_t gftt_grid_words(int w, int h, double min_dist);
 
 // ---- k_lk.cu : cv::calcOpticalFlowPyrLK (Stabilizer.cpp:611-619)
