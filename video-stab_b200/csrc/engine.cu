@@ -164,6 +164,7 @@ vs_status Engine::init(const vs_params& p, int device, int n_lanes) {
     // connections (42.6k vs 37.8k), -3 % with 32 connections; batches and the host-buffer path are unaffected or
     // better.  VS_SPLIT_MOTION=0 keeps the step in one kernel.
     { const char* e = getenv("VS_SPLIT_MOTION"); split_motion_ = !(e && e[0] == '0'); }
+    if (const char* e = getenv("VS_TRACK_N")) { const int v = atoi(e); if (v >= 1 && v <= VS_TRACK_STREAMS) track_n_ = v; }
     if (multi_) {
         // The analysis kernels are small and latency-critical (a single CTA for k_motion / k_select), the warp is one
         // machine-filling grid: the analysis streams get the higher priority so their CTAs are placed first whenever

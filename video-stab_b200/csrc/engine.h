@@ -12,7 +12,7 @@
 #include "kernels.h"
 
 enum { VS_IO_DEVICE = 0, VS_IO_HOST_SYNC = 1, VS_IO_HOST_PIPE = 2 };   // where push()/flush() frames live
-#define VS_TRACK_STREAMS 2                // LK of frame n runs on tracking stream n % 2 (four measured no faster)
+#define VS_TRACK_STREAMS 4                // tracking streams created; LK of frame n runs on stream n % track_n_
 #define VS_OUT_SLOTS 3                    // output staging frames of the pipelined host path
 enum { VS_STAGE_GRAY = 0, VS_STAGE_PYRDOWN, VS_STAGE_LK, VS_STAGE_MOTION, VS_STAGE_GFTT, VS_STAGE_WARP, VS_STAGE_H2D, VS_STAGE_D2H, VS_N_STAGES };
 
@@ -113,7 +113,7 @@ private:
     vs_status generate_transform(const QueueEntry& e, bool* will_pop);
     vs_status first_frame_detect(const PtrPack& src, int w, int h, size_t stride);
     vs_status redetect(int cur, int frame_no, int record_frame_no, cudaEvent_t level0_ready);
-    cudaStream_t sa(int frame_no) const { return multi_ ? sA_[frame_no % VS_TRACK_STREAMS] : stream_; }
+    cudaStream_t sa(int frame_no) const { return multi_ ? sA_[frame_no % track_n_] : stream_; }
     cudaStream_t sp() const { return multi_ ? sP_ : stream_; }
     cudaStream_t sm() const { return multi_ ? sM_ : stream_; }
     vs_status setup_slot_guard();
@@ -167,6 +167,7 @@ private:
     uint8_t* d_scratch_ = nullptr;    // [lane][frame]      (crop+zoom first pass)
     uint8_t* d_fade_ = nullptr;       // border_type "fade": [lane][history] then [lane][blended source], bordered size
     bool fade_ = false, fade_hist_valid_ = false;
+    int track_n_ = 2;                 // tracking streams in use (VS_TRACK_N=1..4)
     int aw_ = VS_AW, ah_ = VS_AH;     // analysis size the pyramids are allocated with (alloc_analysis)
     bool vc_on_ = false;              // enable_virtual_canvas (and no crop_n_zoom): canvas.h replaces the warp
     VirtualCanvas canvas_;
