@@ -701,14 +701,25 @@ k_warp_quad(const __grid_constant__ TmapPack pack, const CUtensorMap* __restrict
     unsigned long long* const S_mbar = reinterpret_cast<unsigned long long*>(S_box + 2);   // [2]
     int* const S_misc = reinterpret_cast<int*>(S_mbar + 2);                            // [tile of the strip]: irregular-step mask
 
-    const int z = blockIdx.z;
+    // CTAs are dispatched in linear block order.  When the frame height is not a whole number of strips the last strip of every
+    // frame is short (1080 rows = 4 x 256 + 56): those CTAs are moved to the END of the order, so that they fill the slots the
+    // last round of full strips leaves idle instead of leaving a quarter-filled extra round (longest work first).
+    int bx = blockIdx.x, by = blockIdx.y, z = blockIdx.z;
+    {
+        const int nx = gridDim.x, ny = gridDim.y, nz = gridDim.z;
+        if (ny > 1 && dh - (ny - 1) * rows_per_cta < rows_per_cta) {
+            const unsigned L = blockIdx.x + nx * (blockIdx.y + ny * blockIdx.z), F = (unsigned)nx * (ny - 1) * nz;
+            if (L < F) { bx = L % nx; const unsigned r = L / nx; by = r % (ny - 1); z = r / (ny - 1); }
+            else { const unsigned r = L - F; bx = r % nx; z = r / nx; by = ny - 1; }
+        }
+    }
     const double* __restrict__ m = lanes_mode ? lanes[z].wpb[wp_slot]->m : wps[z].m;
     uint8_t* __restrict__ dst = lanes_mode ? dstp.p[z] : dst0 + (size_t)z * dframe;
     const CUtensorMap* tmap = dmaps ? dmaps + (lanes_mode ? z : 0) : &pack.m[lanes_mode ? z : 0];
     const int zc = lanes_mode ? 0 : z;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * WT_W, ys = blockIdx.y * rows_per_cta;
+    const int x0 = bx * WT_W, ys = by * rows_per_cta;
     const int ye = min(ys + rows_per_cta, dh);
     const uint32_t s_raw = (uint32_t)__cvta_generic_to_shared(S_raw);
     const uint32_t s_mbar = (uint32_t)__cvta_generic_to_shared(S_mbar);
