@@ -205,7 +205,9 @@ def test_device_api_and_batch_equal_single(vsb):
 
 @pytest.mark.parametrize("kw", [dict(smoothingRadius=6), dict(smoothingRadius=5, borderType="reflect", borderSize=12),
                                 dict(smoothingRadius=7, cropNZoom=True, borderSize=16),
-                                dict(smoothingRadius=5, adaptiveSmoothing=True)])
+                                dict(smoothingRadius=5, adaptiveSmoothing=True),
+                                dict(smoothingRadius=5, enableVirtualCanvas=True, borderSize=8),
+                                dict(smoothingRadius=6, enableVirtualCanvas=True, canvasScaleFactor=1.25, adaptiveCanvasSize=False)])
 def test_push_many_equals_per_frame_push(vsb, kw):
     """The pipelined host call (copy-in / compute / copy-out streams, staging rings) returns exactly the frames
     of n stabilize() calls + flush(), for ragged chunk sizes, page-locked and pageable buffers, more frames than the
@@ -357,15 +359,16 @@ def test_drone_mode_analysis_sizes_that_are_refused(vsb):
     assert ei.value.status == 7
 
 
-@pytest.mark.parametrize("borrow", [True, False])
-def test_async_device_pipeline_is_deterministic(vsb, borrow):
+@pytest.mark.parametrize("borrow,canvas", [(True, False), (False, False), (True, True), (False, True)])
+def test_async_device_pipeline_is_deterministic(vsb, borrow, canvas):
     """The asynchronous device-pointer path keeps five streams busy (pyramid of frame n+1 while frame n is tracked,
     detections of two frames in flight, warp of an older frame).  Its frames must equal the per-frame synchronous host
     path - which serialises everything - on every repetition, with more frames than ring slots / event slots, and
     with the internal ring copy (borrow=False) as well as frames read in place."""
     w, h, n = 1280, 720, 100
     clip = synthclip.make_clip(w, h, n, 4321)
-    params = vsb.Parameters(smoothingRadius=7)
+    # canvas: the virtual-canvas stage in its asynchronous form (the shift is read from the set-up block on the device)
+    params = vsb.Parameters(smoothingRadius=7, enableVirtualCanvas=canvas)
     ref, _ = _run(vsb, clip, params)
     want = [zlib.crc32(o.tobytes()) for o in ref]
     d_clip = torch.from_numpy(clip).cuda()
