@@ -7,11 +7,13 @@
 //     (cv::findContours, :2224-2241);
 //   * a region is filled from the most recent older frame of the temporal buffer whose motion-compensated copy covers more
 //     than half of it (:2244-2273, :2401-2421), warped by cv::warpAffine(BORDER_REFLECT) with the relative motion
-//     (:2423-2443), cut out, resized to the region (:2318-2350) and alpha-blended with a quadratic-free linear edge ramp
-//     (:2352-2399).
+//     (:2423-2443), cut out, resized to the region (:2318-2350) and alpha-blended with a linear edge ramp (:2352-2399).
 // Here nothing canvas-sized is ever written: one kernel computes every output pixel from the frame and, inside regions, from
 // the taps of the older frame (warp, resize and blend composed per pixel, in the reference's fixed-point / float32 steps).
-// The contour logic runs on the host as in the reference (autozoom_host.h), and only on frames that contain dark pixels.
+// When the canvas' black surround encloses the frame it is the only external contour and the one region is the whole canvas: no
+// contour work at all (and with a canvas of at least twice the frame's area nothing can ever be filled: the stage is then a
+// whole-pixel shift read from the device, fully asynchronous).  Otherwise the contour logic runs on the host as in the reference
+// (autozoom_host.h), and only on frames that contain dark pixels.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
