@@ -93,7 +93,7 @@ typedef struct vs_params {
     float   min_canvas_scale;
     int32_t preserve_edge_quality;
     int32_t edge_blend_radius;
-    int32_t drone_high_freq_mode;     /* droneHighFreqMode (analysis width a multiple of 8)  */
+    int32_t drone_high_freq_mode;     /* droneHighFreqMode (analysis size >= 62x62)          */
     float   hf_shake_px;
     int32_t hf_analysis_max_width;
     float   hf_rot_lp_alpha;

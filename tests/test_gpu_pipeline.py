@@ -322,7 +322,8 @@ def test_drone_high_freq_mode_vs_live_oracle(vsb, cv2_noopt, case):
 @pytest.mark.parametrize("w,h,kw,asize", [(640, 360, dict(), (640, 360)), (640, 480, dict(), (640, 480)),
                                           (1920, 1200, dict(), (960, 600)), (1920, 1080, dict(hfAnalysisMaxWidth=1280), (1280, 720)),
                                           (1000, 562, dict(), (960, 538)), (1280, 720, dict(hfAnalysisMaxWidth=320), (320, 180)),
-                                          (1280, 720, dict(hfAnalysisMaxWidth=648), (648, 364))])
+                                          (1280, 720, dict(hfAnalysisMaxWidth=648), (648, 364)), (644, 362, dict(), (644, 362)),
+                                          (1280, 720, dict(hfAnalysisMaxWidth=650), (650, 364)), (1280, 720, dict(hfAnalysisMaxWidth=646), (646, 362))])
 def test_drone_mode_other_analysis_sizes_vs_live_oracle(vsb, cv2_noopt, w, h, kw, asize):
     """calculateDroneAnalysisSize (Stabilizer.cpp:2447-2466): min(hf_analysis_max_width, width) wide, the frame's aspect ratio,
     both made even - pyramids, detector and tracker at that size instead of 960 x 540."""
@@ -353,13 +354,10 @@ def test_drone_mode_other_analysis_sizes_vs_live_oracle(vsb, cv2_noopt, w, h, kw
 
 
 def test_drone_mode_analysis_sizes_that_are_refused(vsb):
-    st = vsb.Stabilizer(vsb.Parameters(droneHighFreqMode=True))
+    st = vsb.Stabilizer(vsb.Parameters(droneHighFreqMode=True, hfAnalysisMaxWidth=48))
     with pytest.raises(vsb.VsError) as ei:
-        st.stabilize(np.zeros((362, 644, 3), np.uint8))           # 644 x 362 analysis size: width not a multiple of 8
+        st.stabilize(np.zeros((1080, 1920, 3), np.uint8))         # 48 x 26: OpenCV's tracker would drop pyramid levels
     assert ei.value.status == 7
-    st2 = vsb.Stabilizer(vsb.Parameters(droneHighFreqMode=True, hfAnalysisMaxWidth=48))
-    with pytest.raises(vsb.VsError):
-        st2.stabilize(np.zeros((1080, 1920, 3), np.uint8))        # 48 x 26: OpenCV's tracker would drop pyramid levels
 
 
 @pytest.mark.parametrize("borrow,canvas", [(True, False), (False, False), (True, True), (False, True)])
@@ -506,7 +504,7 @@ def _sweep_case(seed):
     # drone mode at any frame size: its analysis image is min(960, width) wide with the frame's aspect ratio (every third
     # 16:9 frame of at least 960 columns - the 960 x 540 analysis size - and every fourth of the others)
     big = (w * 9 == h * 16) and w >= 960
-    if rng.integers(0, 3 if big else 4) == 0 and min(w, 960) % 8 == 0:        # (analysis widths that are not multiples of 8 are refused)
+    if rng.integers(0, 3 if big else 4) == 0:
         kw["droneHighFreqMode"] = True
     return w, h, kw
 

@@ -437,12 +437,10 @@ vs_status Engine::ensure_geometry(int w, int h, bool need_ring, bool need_out, b
         const int ah0 = (int)((float)mw * aspect);
         const int aw = (mw / 2) * 2, ah = (ah0 / 2) * 2;
         if (aw != aw_ || ah != ah_) {
-            // k_pyrdown2 computes and stores pixel PAIRS of levels 1 and 2 (their widths must be even: the analysis width a multiple
-            // of 8 - 644 passed most runs and failed some, the pad column behind an odd last column is written twice); the
-            // tracker always runs three levels, and OpenCV drops those no larger than the 15 x 15 window (:611-619)
-            if (aw % 8 != 0 || aw > 4096 || ((aw + 1) / 2 + 1) / 2 <= VS_WIN || ((ah + 1) / 2 + 1) / 2 <= VS_WIN)
+            // the tracker always runs three pyramid levels; OpenCV drops the levels that are no larger than the 15 x 15 window (:611-619)
+            if (aw > 4096 || ((aw + 1) / 2 + 1) / 2 <= VS_WIN || ((ah + 1) / 2 + 1) / 2 <= VS_WIN)
                 return vs_set_error(VS_ERR_UNSUPPORTED, "drone_high_freq_mode: the drone analysis size (min(hf_analysis_max_width, width) x matching "
-                                                        "height, both made even) must have a width that is a multiple of 8, at least 64 x 62, at most 4096 wide");
+                                                        "height, both made even) must be at least 62 x 62 and at most 4096 wide");
             VS_TRY(sync());
             VS_TRY(alloc_analysis(aw, ah));
         }

@@ -224,16 +224,20 @@ void launch_upsample_small(const LaneDev* lanes, int n_lanes, int slot, cudaStre
 // two horizontally adjacent pixels (x even, both inside the level) as one 16-bit store, plus their reflect-101 images
 static __device__ __forceinline__ void store2_with_mirrors(const GrayLevel& lv, int x, int y, unsigned short v2) {
     uint8_t* r = lv.base + (ptrdiff_t)y * lv.pitch;
-    *reinterpret_cast<unsigned short*>(r + x) = v2;
+    // A level of odd width ends in half a pair: only its first pixel exists.  The column behind it belongs to the frame and is
+    // written by the owner of its reflect-101 source (x = w - 2); storing the pair there would race with that store.
+    const bool pair = x + 1 < lv.w;
+    if (pair) *reinterpret_cast<unsigned short*>(r + x) = v2; else r[x] = (uint8_t)v2;
     int ym = INT_MIN;
     if (y >= 1 && y <= VS_PAD) ym = -y;
     else if (y >= lv.h - 1 - VS_PAD && y <= lv.h - 2) ym = 2 * (lv.h - 1) - y;
     uint8_t* rm = lv.base + (ptrdiff_t)(ym == INT_MIN ? y : ym) * lv.pitch;
-    if (ym != INT_MIN) *reinterpret_cast<unsigned short*>(rm + x) = v2;
+    if (ym != INT_MIN) { if (pair) *reinterpret_cast<unsigned short*>(rm + x) = v2; else rm[x] = (uint8_t)v2; }
     if (x <= VS_PAD || x + 1 >= lv.w - 1 - VS_PAD) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int xx = x + k;
+            if (k == 1 && !pair) break;
             int xm = INT_MIN;
             if (xx >= 1 && xx <= VS_PAD) xm = -xx;
             else if (xx >= lv.w - 1 - VS_PAD && xx <= lv.w - 2) xm = 2 * (lv.w - 1) - xx;
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(256) k_pyrdown2(const LaneDev* __restrict__ la
     // 3. level 1, column pass (in-image positions), stored by the owner
     for (int i = tid; i < PD_R1 * (PD_R1 / 2); i += 256) {
         const int r = i / (PD_R1 / 2), m = i - r * (PD_R1 / 2), c = 2 * m;
-        const int x1 = x1o + c, y1 = y1o + r;                 // x1 is even and the level width is even: a pair is inside or outside together
+        const int x1 = x1o + c, y1 = y1o + r;                 // x1 is even; the second pixel of the last pair of an odd-width level lies outside (3b, store2_with_mirrors)
         if ((unsigned)x1 < (unsigned)g1.w && (unsigned)y1 < (unsigned)g1.h) {
             const uint32_t acc = H1w[2 * r][m] + 4u * H1w[2 * r + 1][m] + 6u * H1w[2 * r + 2][m] + 4u * H1w[2 * r + 3][m] + H1w[2 * r + 4][m];
             const uint32_t v = ((acc + 0x00800080u) >> 8) & 0x00FF00FFu;
