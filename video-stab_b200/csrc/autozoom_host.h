@@ -79,8 +79,14 @@ static inline void find_external_contours_padded(signed char* work, int w, int h
         for (int x = 1; x <= w + 1; ++x) {
             int p = row[x];
             if (p == prev) {
-                // runs of equal pixels (almost the whole image) are skipped eight at a time
+                // runs of equal pixels (almost the whole image) are skipped 32, then eight at a time
                 const unsigned long long pat = 0x0101010101010101ull * (unsigned char)prev;
+                while (x + 32 <= w + 1) {
+                    unsigned long long v[4];
+                    std::memcpy(v, row + x, 32);
+                    if (((v[0] ^ pat) | (v[1] ^ pat) | (v[2] ^ pat) | (v[3] ^ pat)) != 0) break;
+                    x += 32;
+                }
                 while (x + 8 <= w + 1) {
                     unsigned long long v;
                     std::memcpy(&v, row + x, 8);
@@ -103,11 +109,24 @@ static inline void find_external_contours_padded(signed char* work, int w, int h
 }
 static inline void pad_mask(const uint8_t* mask, int w, int h, size_t stride, std::vector<signed char>& work) {
     const int step = w + 2;
-    work.assign((size_t)step * (h + 2), 0);
+    work.resize((size_t)step * (h + 2));                // every byte is written below: the zero frame, then the rows
+    std::memset(work.data(), 0, step);
+    std::memset(work.data() + (size_t)(h + 1) * step, 0, step);
     for (int y = 0; y < h; ++y) {
         const uint8_t* m = mask + (size_t)y * stride;
         signed char* d = work.data() + (size_t)(y + 1) * step + 1;
-        for (int x = 0; x < w; ++x) d[x] = m[x] ? 1 : 0;
+        d[-1] = 0; d[w] = 0;
+        int x = 0;
+        for (; x + 8 <= w; x += 8) {                    // eight pixels at a time: any non-zero byte -> 1
+            unsigned long long v;
+            std::memcpy(&v, m + x, 8);
+            v = (v & 0x0F0F0F0F0F0F0F0Full) | ((v >> 4) & 0x0F0F0F0F0F0F0F0Full);
+            v |= (v >> 2) & 0x0303030303030303ull;
+            v |= (v >> 1);
+            v &= 0x0101010101010101ull;
+            std::memcpy(d + x, &v, 8);
+        }
+        for (; x < w; ++x) d[x] = m[x] ? 1 : 0;
     }
 }
 static inline void find_external_contours(const uint8_t* mask, int w, int h, size_t stride, std::vector<std::vector<Pt>>& contours,
@@ -188,21 +207,31 @@ static inline bool crop_rect_from_padded(signed char* work, int w, int h, Rect* 
     }
     //      Everything else: a 4-connected flood from the frame that never enters a border pixel marks the OUTSIDE (it only
     //      ever visits the corners the content leaves free, other components included: they are not part of the drawn contour).
+    //      Span by span: a seed is widened to the run of free pixels around it, the rows above and below are searched for the
+    //      starts of free runs under that span (every pixel is marked once and looked at a few times, no per-pixel stack traffic).
     {
+        auto is_free = [&](int q) { const signed char v = work[q]; return v != AZ_BORDER && v != AZ_EXT; };
         std::vector<int> stack;
         stack.push_back(0);
-        work[0] = AZ_EXT;
         while (!stack.empty()) {
             const int p = stack.back();
             stack.pop_back();
-            const int y = p / step, x = p - y * step;
-            const int nx[4] = {x + 1, x - 1, x, x}, ny[4] = {y, y, y + 1, y - 1};
-            for (int k = 0; k < 4; ++k) {
-                if (nx[k] < 0 || nx[k] > w + 1 || ny[k] < 0 || ny[k] > h + 1) continue;
-                const int q = ny[k] * step + nx[k];
-                if (work[q] == AZ_BORDER || work[q] == AZ_EXT) continue;
-                work[q] = AZ_EXT;
-                stack.push_back(q);
+            if (!is_free(p)) continue;
+            const int y = p / step, row = y * step;
+            int xl = p - row, xr = xl;
+            while (xl > 0 && is_free(row + xl - 1)) --xl;
+            while (xr < w + 1 && is_free(row + xr + 1)) ++xr;
+            std::memset(work + row + xl, AZ_EXT, (size_t)(xr - xl + 1));
+            for (int dy = -1; dy <= 1; dy += 2) {
+                const int ny = y + dy;
+                if (ny < 0 || ny > h + 1) continue;
+                const int nrow = ny * step;
+                bool in_run = false;
+                for (int x = xl; x <= xr; ++x) {
+                    const bool f = is_free(nrow + x);
+                    if (f && !in_run) stack.push_back(nrow + x);
+                    in_run = f;
+                }
             }
         }
     }
@@ -238,7 +267,7 @@ static inline bool crop_rect_from_padded(signed char* work, int w, int h, Rect* 
     return true;
 }
 static inline bool crop_rect_from_mask(const uint8_t* mask, int w, int h, size_t stride, Rect* out) {
-    std::vector<signed char> work;
+    static thread_local std::vector<signed char> work;   // kept between calls: a fresh 8 MB vector costs more in page faults than the search
     pad_mask(mask, w, h, stride, work);
     return crop_rect_from_padded(work.data(), w, h, out);
 }
